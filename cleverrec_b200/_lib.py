@@ -1,0 +1,101 @@
+"""ctypes binding of libcleverrec_b200.so (the C ABI declared in include/cleverrec_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or the machine has no B200 the first
+call raises.  torch is used only to own device memory and the current stream."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcleverrec_b200.so")
+
+OPT_SGD, OPT_ADAGRAD, OPT_ADAM = 0, 1, 2
+ADAM_TF1, ADAM_LAZY = 0, 1
+LOSS_BPR, LOSS_CROSS_ENTROPY, LOSS_SQUARE, LOSS_HINGE = 0, 1, 2, 3
+SCORE_DOT, SCORE_GMF, SCORE_SQDIST, SCORE_DOT_BIAS = 0, 1, 2, 3
+
+EXPORTS = [
+    "crb_abi_version", "crb_last_error", "crb_create", "crb_destroy", "crb_set_history", "crb_sample_pairwise",
+    "crb_sample_pointwise", "crb_sample_cml", "crb_epoch_rows", "crb_train_step_bpr", "crb_train_epoch_bpr",
+    "crb_train_step_pointwise", "crb_adam_flush", "crb_score_pairs", "crb_topk_segments", "crb_score_topk",
+    "crb_score_topk_stats", "crb_launch_count",
+]
+
+
+class CrbTable(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("s1", C.c_void_p), ("s2", C.c_void_p), ("last", C.c_void_p), ("rows", C.c_int64),
+                ("dim", C.c_int32), ("_pad", C.c_int32)]
+
+
+class CrbOpt(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("adam_mode", C.c_int32), ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
+                ("eps", C.c_double), ("step", C.c_int64)]
+
+
+class CrbError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "cleverrec_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (building it is `python -m cleverrec_b200.build`).  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libcleverrec_b200.so not built: run `python -m cleverrec_b200.build` (needs nvcc); "
+                          "cleverrec_b200 has no CPU / PyTorch fallback path")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32, u64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float
+    lib.crb_last_error.restype = C.c_char_p
+    lib.crb_abi_version.restype = C.c_int
+    lib.crb_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.crb_destroy.argtypes = [vp]
+    lib.crb_set_history.argtypes = [vp, i64, i64, i64, vp, vp, vp, vp, vp]
+    lib.crb_sample_pairwise.argtypes = [vp, u64, u32, i64, i64, i32, vp, vp, vp, vp, vp]
+    lib.crb_sample_pointwise.argtypes = [vp, u64, u32, i64, i64, i32, vp, vp, vp, vp, vp]
+    lib.crb_sample_cml.argtypes = [vp, u64, u32, i64, i64, i32, vp, vp, vp, vp]
+    lib.crb_epoch_rows.argtypes = [vp, i32, i32]
+    lib.crb_epoch_rows.restype = i64
+    lib.crb_train_step_bpr.argtypes = [vp, C.POINTER(CrbTable), C.POINTER(CrbTable), C.POINTER(CrbOpt), vp, vp, vp, i64, f32, vp, vp]
+    lib.crb_train_epoch_bpr.argtypes = [vp, C.POINTER(CrbTable), C.POINTER(CrbTable), C.POINTER(CrbOpt), u64, u32, i64, i64, i64,
+                                        i32, f32, vp, vp]
+    lib.crb_train_step_pointwise.argtypes = [vp, i32, C.POINTER(CrbTable), C.POINTER(CrbTable), vp, vp, vp, C.POINTER(CrbOpt), i32,
+                                             vp, vp, vp, i64, f32, vp, vp]
+    lib.crb_adam_flush.argtypes = [vp, C.POINTER(CrbTable), C.POINTER(CrbOpt), vp]
+    lib.crb_score_pairs.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, i64, vp, vp]
+    lib.crb_topk_segments.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
+    lib.crb_score_topk.argtypes = [vp, i32, vp, vp, vp, i64, i32, vp, vp, i64, i32, i32, vp, vp, vp]
+    lib.crb_score_topk_stats.argtypes = [vp, C.POINTER(C.c_int64 * 4)]
+    lib.crb_launch_count.argtypes = [vp]
+    lib.crb_launch_count.restype = i64
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise CrbError(rc, load().crb_last_error().decode("utf-8", "replace"))
+
+
+def ptr(x):
+    """Raw address of a torch tensor (device or host), a NumPy array (host) or None."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        if not x.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return x.ctypes.data
+    if not x.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return x.data_ptr()
+
+
+def current_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,174 @@
+// Handle, workspace and error plumbing of libcleverrec_b200.so.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void crb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* crb_last_error(void) { return g_err; }
+extern "C" int crb_abi_version(void) { return CRB_ABI_VERSION; }
+
+extern "C" int crb_create(int device, crb_handle** out) {
+    CRB_CHECK_ARG(out, "out is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        crb_set_error("no CUDA device available (%s); cleverrec_b200 has no CPU path", e == cudaSuccess ? "count == 0" : cudaGetErrorString(e));
+        return CRB_ERR_CUDA;
+    }
+    CRB_CHECK_ARG(device >= 0 && device < n, "device index out of range");
+    CRB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CRB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        crb_set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return CRB_ERR_UNSUPPORTED;
+    }
+    crb_handle* h = (crb_handle*)calloc(1, sizeof(crb_handle));
+    if (!h) {
+        crb_set_error("out of host memory");
+        return CRB_ERR_ARG;
+    }
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->loss_blocks = h->sm_count * 8;
+    CRB_CUDA(cudaMalloc(&h->ctr, sizeof(crb_step_ctr)));
+    CRB_CUDA(cudaMemset(h->ctr, 0, sizeof(crb_step_ctr)));
+    CRB_CUDA(cudaMalloc(&h->block_loss, sizeof(double) * h->loss_blocks));
+    CRB_CUDA(cudaMemset(h->block_loss, 0, sizeof(double) * h->loss_blocks));
+    CRB_CUDA(cudaMalloc(&h->lrt, sizeof(float) * CRB_LRT_TABLE));
+    h->lrt_lr = -1.0;
+    *out = h;
+    return CRB_OK;
+}
+
+static void free_ws(crb_handle* h) {
+    for (int k = 0; k < 4; ++k) { cudaFree(h->idx[k]); h->idx[k] = nullptr; }
+    for (int k = 0; k < 3; ++k) { cudaFree(h->rank[k]); h->rank[k] = nullptr; }
+    cudaFree(h->yv); h->yv = nullptr;
+    cudaFree(h->dup_grad); h->dup_grad = nullptr;
+    cudaFree(h->dup_t); h->dup_t = nullptr;
+    cudaFree(h->dup_rows); h->dup_rows = nullptr;
+    cudaFree(h->work); h->work = nullptr;
+    cudaFree(h->multi); h->multi = nullptr;
+    cudaFree(h->partial); h->partial = nullptr;
+    h->cap_batch = 0;
+    h->cap_dim = 0;
+}
+
+extern "C" int crb_destroy(crb_handle* h) {
+    if (!h) return CRB_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    free_ws(h);
+    cudaFree(h->meta[0]);
+    cudaFree(h->meta[1]);
+    cudaFree(h->ctr);
+    cudaFree(h->block_loss);
+    cudaFree(h->loss_dev);
+    cudaFree(h->lrt);
+    cudaFree(h->dense_grad);
+    cudaFree(h->eval_ws);
+    free(h);
+    return CRB_OK;
+}
+
+extern "C" int64_t crb_launch_count(crb_handle* h) { return h ? h->launches : -1; }
+
+extern "C" int crb_set_history(crb_handle* h, int64_t n_users, int64_t n_items, int64_t n_pos, const int32_t* pos_user,
+                               const int32_t* pos_item, const int64_t* seen_rowptr, const int32_t* seen_cols, void* stream) {
+    CRB_CHECK_ARG(h, "null handle");
+    CRB_CHECK_ARG(n_users > 0 && n_items > 0 && n_pos >= 0, "sizes");
+    CRB_CHECK_ARG(n_users < 0x7fffffffLL && n_items < 0x7fffffffLL, "row ids are int32");
+    CRB_CHECK_ARG(crb_is_device_ptr(seen_rowptr), "seen_rowptr must be a device pointer");
+    CRB_CHECK_ARG(n_pos == 0 || (crb_is_device_ptr(pos_user) && crb_is_device_ptr(pos_item)), "pos_user/pos_item must be device pointers");
+    (void)stream;
+    h->n_users = n_users;
+    h->n_items = n_items;
+    h->n_pos = n_pos;
+    h->pos_user = pos_user;
+    h->pos_item = pos_item;
+    h->seen_rowptr = seen_rowptr;
+    h->seen_cols = seen_cols;
+    return CRB_OK;
+}
+
+int crb_meta_reserve(crb_handle* h, int which, int64_t rows, cudaStream_t s) {
+    if (h->meta_rows[which] >= rows) return CRB_OK;
+    CRB_CUDA(cudaStreamSynchronize(s));
+    cudaFree(h->meta[which]);
+    h->meta[which] = nullptr;
+    h->meta_rows[which] = 0;
+    CRB_CUDA(cudaMalloc(&h->meta[which], sizeof(unsigned long long) * rows));
+    CRB_CUDA(cudaMemsetAsync(h->meta[which], 0, sizeof(unsigned long long) * rows, s));
+    h->meta_rows[which] = rows;
+    return CRB_OK;
+}
+
+int crb_ws_reserve(crb_handle* h, int64_t batch, int32_t dim, int64_t steps, cudaStream_t s) {
+    if (steps > h->cap_steps) {
+        CRB_CUDA(cudaStreamSynchronize(s));
+        cudaFree(h->loss_dev);
+        h->loss_dev = nullptr;
+        CRB_CUDA(cudaMalloc(&h->loss_dev, sizeof(double) * steps));
+        h->cap_steps = steps;
+    }
+    if (batch <= h->cap_batch && dim <= h->cap_dim) return CRB_OK;
+    CRB_CUDA(cudaStreamSynchronize(s));
+    int64_t nb = batch > h->cap_batch ? batch : h->cap_batch;
+    int32_t nd = dim > h->cap_dim ? dim : h->cap_dim;
+    free_ws(h);
+    const int64_t occ = 3 * nb;
+    for (int k = 0; k < 4; ++k) CRB_CUDA(cudaMalloc(&h->idx[k], sizeof(int32_t) * nb));
+    for (int k = 0; k < 3; ++k) CRB_CUDA(cudaMalloc(&h->rank[k], sizeof(uint32_t) * nb));
+    CRB_CUDA(cudaMalloc(&h->yv, sizeof(float) * nb));
+    CRB_CUDA(cudaMalloc(&h->dup_grad, sizeof(float) * occ * nd));
+    CRB_CUDA(cudaMalloc(&h->dup_t, sizeof(uint32_t) * occ));
+    CRB_CUDA(cudaMalloc(&h->dup_rows, sizeof(crb_dup_row) * (occ / 2 + 1)));
+    CRB_CUDA(cudaMalloc(&h->work, sizeof(crb_work) * (occ / 2 + occ / CRB_DUP_CHUNK + 2)));
+    CRB_CUDA(cudaMalloc(&h->multi, sizeof(unsigned int) * (occ / CRB_DUP_CHUNK + 2)));
+    h->cap_partial = 2 * (occ / CRB_DUP_CHUNK) + 2;
+    CRB_CUDA(cudaMalloc(&h->partial, sizeof(float) * h->cap_partial * nd));
+    h->cap_batch = nb;
+    h->cap_dim = nd;
+    return CRB_OK;
+}
+
+int crb_eval_ws_reserve(crb_handle* h, int64_t bytes) {
+    if (bytes <= h->eval_ws_bytes) return CRB_OK;
+    CRB_CUDA(cudaDeviceSynchronize());
+    cudaFree(h->eval_ws);
+    h->eval_ws = nullptr;
+    h->eval_ws_bytes = 0;
+    CRB_CUDA(cudaMalloc(&h->eval_ws, bytes));
+    h->eval_ws_bytes = bytes;
+    return CRB_OK;
+}
+
+// lr_t(s) = lr * sqrt(1 - beta2^s) / (1 - beta1^s) evaluated in double like TF / the torch restatement, rounded to fp32
+int crb_lrt_prepare(crb_handle* h, const crb_opt* opt, cudaStream_t s) {
+    if (h->lrt_lr == opt->lr && h->lrt_b1 == opt->beta1 && h->lrt_b2 == opt->beta2) return CRB_OK;
+    float* host = (float*)malloc(sizeof(float) * CRB_LRT_TABLE);
+    if (!host) { crb_set_error("out of host memory"); return CRB_ERR_ARG; }
+    const double lr = opt->lr, b1 = opt->beta1, b2 = opt->beta2;
+    host[0] = 0.f;
+    for (int t = 1; t < CRB_LRT_TABLE; ++t) host[t] = (float)(lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t)));
+    cudaError_t e = cudaMemcpyAsync(h->lrt, host, sizeof(float) * CRB_LRT_TABLE, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    free(host);
+    CRB_CUDA(e);
+    h->lrt_lr = opt->lr;
+    h->lrt_b1 = opt->beta1;
+    h->lrt_b2 = opt->beta2;
+    return CRB_OK;
+}

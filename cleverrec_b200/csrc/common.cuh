@@ -1,0 +1,159 @@
+// Shared internals of libcleverrec_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/cleverrec_b200.h"
+
+#define CRB_SAMPLER_MAX_BLOCKS 4096u  // attempt guard (oracle/philox.py MAX_BLOCKS)
+#define CRB_LRT_TABLE 65536           // Adam lr_t table length; beyond it lr_t == lr in fp32
+#define CRB_DUP_CHUNK 256             // slots per work item of the duplicate-row reduction
+
+void crb_set_error(const char* fmt, ...);
+
+#define CRB_CUDA(call)                                                                      \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            crb_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return CRB_ERR_CUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+
+#define CRB_CHECK_ARG(cond, msg)             \
+    do {                                     \
+        if (!(cond)) {                       \
+            crb_set_error("bad argument: %s", msg); \
+            return CRB_ERR_ARG;              \
+        }                                    \
+    } while (0)
+
+// Device-side counters of one training step (zeroed by the step's first kernel's predecessor memset).
+struct crb_step_ctr {
+    unsigned int dup_slots;   // total gradient slots handed to duplicate rows
+    unsigned int dup_rows;    // number of duplicate rows
+    unsigned int work_items;  // chunk work items of the duplicate reduction
+    unsigned int multi_rows;  // duplicate rows with more than one chunk
+    unsigned int sampler_err; // a positive ran out of attempts
+    unsigned int partial_slots; // partial-sum rows handed to multi-chunk duplicate rows
+    unsigned int pad[2];
+};
+
+struct crb_dup_row {   // one row that occurs >= 2 times in the batch
+    int32_t row;
+    int32_t table;     // 0 = user-side table, 1 = item-side table
+    uint32_t base;     // first gradient slot
+    uint32_t cnt;      // occurrences
+    uint32_t wbase;    // first work item
+    uint32_t nchunk;
+    uint32_t pbase;    // first partial-sum row (multi-chunk rows only)
+    uint32_t pad;
+};
+
+struct crb_work {      // one chunk of one duplicate row
+    uint32_t dup;      // index into dup rows
+    uint32_t chunk;
+};
+
+struct crb_handle {
+    int device;
+    int sm_count;
+    // history (borrowed device pointers)
+    int64_t n_users, n_items, n_pos;
+    const int32_t* pos_user;
+    const int32_t* pos_item;
+    const int64_t* seen_rowptr;
+    const int32_t* seen_cols;
+    // per-row batch multiplicity words: low 32 bits = count, high 32 bits = slot base
+    unsigned long long* meta[2];
+    int64_t meta_rows[2];
+    // per-step workspace (grown on demand)
+    int64_t cap_batch;     // triplets
+    int32_t cap_dim;
+    int32_t* idx[4];       // sampled u, i, j, nbr (or staged host feeds)
+    float* yv;             // sampled / staged labels
+    uint32_t* rank[3];     // occurrence rank of u, i, j inside their row
+    float* dup_grad;       // [3*cap_batch, dim] gradient slots of duplicate occurrences
+    uint32_t* dup_t;       // [3*cap_batch] triplet index of each slot (deterministic order)
+    crb_dup_row* dup_rows; // [3*cap_batch]
+    crb_work* work;        // [3*cap_batch]
+    unsigned int* multi;   // [3*cap_batch / CRB_DUP_CHUNK + 1] indices of multi-chunk duplicate rows
+    int64_t cap_partial;   // rows of `partial`
+    float* partial;        // [3*cap_batch / CRB_DUP_CHUNK + rows] * dim  chunk partial sums
+    crb_step_ctr* ctr;     // device
+    double* block_loss;    // [loss_blocks]
+    double* loss_dev;      // [cap_steps] when the caller's loss buffer is on the host
+    int64_t cap_steps;
+    int loss_blocks;
+    float* lrt;            // Adam lr_t table (device), built for (lr, beta1, beta2)
+    double lrt_lr, lrt_b1, lrt_b2;
+    float* dense_grad;     // small dense-variable gradient accumulator (h_gmf, ...)
+    int64_t cap_dense;
+    // evaluation workspace
+    void* eval_ws;
+    int64_t eval_ws_bytes;
+    int64_t topk_stats[4];
+    int64_t launches;
+};
+
+static inline bool crb_is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ---------------------------------------------------------------------------------- device helpers
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+template <int LANES>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float dot4(float4 a, float4 b) {
+    return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
+}
+
+// numerically stable softplus(-x) = -log(sigmoid(x)) and sigmoid(x) - 1 = -sigmoid(-x)
+__device__ __forceinline__ float softplus_neg(float x) { return fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x))); }
+__device__ __forceinline__ float sigmoid_f(float x) {
+    float e = expf(-fabsf(x));
+    float s = 1.f / (1.f + e);
+    return x >= 0.f ? s : 1.f - s;  // 1-s == e/(1+e) up to rounding
+}
+
+// Philox4x32-10 (same constants as oracle/philox.py)
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                       uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// internal entry points shared between translation units
+int crb_ws_reserve(crb_handle* h, int64_t batch, int32_t dim, int64_t steps, cudaStream_t s);
+int crb_meta_reserve(crb_handle* h, int which, int64_t rows, cudaStream_t s);
+int crb_eval_ws_reserve(crb_handle* h, int64_t bytes);
+int crb_lrt_prepare(crb_handle* h, const crb_opt* opt, cudaStream_t s);
+int crb_launch_sample_pairwise(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t first, int64_t count, int32_t neg_ratio,
+                               int32_t* u, int32_t* i, int32_t* j, int32_t* nbr, bool count_rows, cudaStream_t s);

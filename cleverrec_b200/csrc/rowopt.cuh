@@ -1,0 +1,164 @@
+// Row-sparse optimizer application (TF-1 semantics, SURVEY.md 2.4 / utils/tools.py:79-87) and the
+// "duplicate row" machinery shared by every row-sparse training step.
+//
+// One training step treats a table row in one of two ways, decided by its multiplicity in the batch
+// (counted with one 32-bit atomic per occurrence into crb_handle::meta):
+//   * multiplicity 1  -> the sample's own lane group applies the optimizer in place: the row is read once
+//                        and written once, which is the algorithmic minimum (24*d / 48*d / 72*d bytes per
+//                        triplet for SGD / Adagrad / Adam).
+//   * multiplicity >1 -> TF de-duplicates IndexedSlices by summing and applies once per unique row, and all
+//                        occurrences must see the pre-step value.  The occurrences write their gradient to
+//                        slots [base, base+cnt); a second kernel sums the slots (in triplet order when the row
+//                        has <= 32 occurrences, so the result is deterministic) and applies once.
+#pragma once
+#include "common.cuh"
+
+struct TableDev {
+    float* w;
+    float* s1;
+    float* s2;
+    int32_t* last;
+};
+
+struct OptDev {
+    float lr;      // SGD / Adagrad learning rate
+    float lr_t;    // Adam: lr * sqrt(1-b2^t)/(1-b1^t) of this step
+    float b1, b2, eps;
+    int32_t step;  // 1-based index of this step
+    const float* lrt;  // lr_t table for replay (CRB_ADAM_TF1)
+};
+
+enum { OPT_SGD = 0, OPT_ADAGRAD = 1, OPT_ADAM_LAZY = 2, OPT_ADAM_TF1 = 3 };
+
+template <int OPT> struct OptTraits {
+    static constexpr bool has_s1 = OPT != OPT_SGD;
+    static constexpr bool has_s2 = OPT == OPT_ADAM_LAZY || OPT == OPT_ADAM_TF1;
+    static constexpr bool replay = OPT == OPT_ADAM_TF1;
+};
+
+__device__ __forceinline__ float lrt_at(const OptDev& o, int s) { return s < CRB_LRT_TABLE ? o.lrt[s] : o.lr; }
+
+// One decay-only Adam step (a row that was not touched at step s under tf.train.AdamOptimizer's sparse apply):
+// m *= b1; v *= b2; w -= lr_s * m / (sqrt(v) + eps).  No contraction: matches the op-by-op TF/torch sequence.
+__device__ __forceinline__ void adam_decay_elem(float& w, float& m, float& v, float lr_s, float b1, float b2, float eps) {
+    m = __fmul_rn(m, b1);
+    v = __fmul_rn(v, b2);
+    w = __fsub_rn(w, __fdiv_rn(__fmul_rn(lr_s, m), __fadd_rn(__fsqrt_rn(v), eps)));
+}
+
+__device__ __forceinline__ void adam_decay4(float4& W, float4& M, float4& V, float lr_s, const OptDev& o) {
+    adam_decay_elem(W.x, M.x, V.x, lr_s, o.b1, o.b2, o.eps);
+    adam_decay_elem(W.y, M.y, V.y, lr_s, o.b1, o.b2, o.eps);
+    adam_decay_elem(W.z, M.z, V.z, lr_s, o.b1, o.b2, o.eps);
+    adam_decay_elem(W.w, M.w, V.w, lr_s, o.b1, o.b2, o.eps);
+}
+
+// tf.train.AdagradOptimizer sparse apply: acc += g*g; w -= lr * g / sqrt(acc)  (no epsilon, acc starts at 0.1)
+__device__ __forceinline__ void adagrad_elem(float& w, float& acc, float g, float lr) {
+    acc = __fadd_rn(acc, __fmul_rn(g, g));
+    w = __fsub_rn(w, __fdiv_rn(__fmul_rn(lr, g), __fsqrt_rn(acc)));
+}
+
+__device__ __forceinline__ void adam_touch_elem(float& w, float& m, float& v, float g, const OptDev& o) {
+    m = __fadd_rn(__fmul_rn(m, o.b1), __fmul_rn(g, __fsub_rn(1.f, o.b1)));
+    v = __fadd_rn(__fmul_rn(v, o.b2), __fmul_rn(__fmul_rn(g, g), __fsub_rn(1.f, o.b2)));
+    w = __fsub_rn(w, __fdiv_rn(__fmul_rn(o.lr_t, m), __fadd_rn(__fsqrt_rn(v), o.eps)));
+}
+
+// Per lane-group view of one row: VPL float4 chunks per lane, chunk index c = gl + LANES*v, valid iff 4c < dim.
+template <int LANES, int VPL> struct RowRegs {
+    float4 w[VPL];
+    float4 s1[VPL];
+    float4 s2[VPL];
+    int32_t last;
+};
+
+template <int LANES, int VPL>
+__device__ __forceinline__ void row_load_w(RowRegs<LANES, VPL>& r, const TableDev& T, int64_t row, int dim, int gl) {
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        int c = (gl + LANES * v) * 4;
+        r.w[v] = c < dim ? ld4(T.w + row * dim + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <int LANES, int VPL, int OPT>
+__device__ __forceinline__ void row_load_state(RowRegs<LANES, VPL>& r, const TableDev& T, int64_t row, int dim, int gl) {
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        int c = (gl + LANES * v) * 4;
+        if (OptTraits<OPT>::has_s1) r.s1[v] = c < dim ? ld4(T.s1 + row * dim + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+        if (OptTraits<OPT>::has_s2) r.s2[v] = c < dim ? ld4(T.s2 + row * dim + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+    }
+    if (OptTraits<OPT>::replay) r.last = T.last[row];
+}
+
+// CRB_ADAM_TF1: apply the decay-only steps last+1 .. step-1 in registers so that r.w is the value the dense TF
+// update would hold before this step.
+template <int LANES, int VPL, int OPT>
+__device__ __forceinline__ void row_replay(RowRegs<LANES, VPL>& r, const OptDev& o, int upto /*exclusive*/) {
+    if (!OptTraits<OPT>::replay) return;
+    for (int s = r.last + 1; s < upto; ++s) {
+        const float lr_s = lrt_at(o, s);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) adam_decay4(r.w[v], r.s1[v], r.s2[v], lr_s, o);
+    }
+}
+
+// Apply this step's update with gradient g and store the row (+ slots).
+template <int LANES, int VPL, int OPT>
+__device__ __forceinline__ void row_apply_store(RowRegs<LANES, VPL>& r, const float4* g, const TableDev& T, int64_t row, int dim,
+                                                int gl, const OptDev& o) {
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        const int c = (gl + LANES * v) * 4;
+        if (c >= dim) continue;
+        float4 W = r.w[v], G = g[v];
+        if (OPT == OPT_SGD) {
+            W.x = __fsub_rn(W.x, __fmul_rn(o.lr, G.x));
+            W.y = __fsub_rn(W.y, __fmul_rn(o.lr, G.y));
+            W.z = __fsub_rn(W.z, __fmul_rn(o.lr, G.z));
+            W.w = __fsub_rn(W.w, __fmul_rn(o.lr, G.w));
+        } else if (OPT == OPT_ADAGRAD) {
+            float4 A = r.s1[v];
+            adagrad_elem(W.x, A.x, G.x, o.lr);
+            adagrad_elem(W.y, A.y, G.y, o.lr);
+            adagrad_elem(W.z, A.z, G.z, o.lr);
+            adagrad_elem(W.w, A.w, G.w, o.lr);
+            st4(T.s1 + row * dim + c, A);
+        } else {
+            float4 M = r.s1[v], V = r.s2[v];
+            adam_touch_elem(W.x, M.x, V.x, G.x, o);
+            adam_touch_elem(W.y, M.y, V.y, G.y, o);
+            adam_touch_elem(W.z, M.z, V.z, G.z, o);
+            adam_touch_elem(W.w, M.w, V.w, G.w, o);
+            st4(T.s1 + row * dim + c, M);
+            st4(T.s2 + row * dim + c, V);
+        }
+        st4(T.w + row * dim + c, W);
+    }
+    if (OptTraits<OPT>::replay && gl == 0) T.last[row] = o.step;
+}
+
+// Arguments of the duplicate-row kernels (shared by all row-sparse steps)
+struct DupArgs {
+    TableDev tab[2];
+    unsigned long long* meta[2];
+    int dim;
+    OptDev opt;
+    const crb_dup_row* dup_rows;
+    const crb_work* work;
+    const unsigned int* multi;   // indices of multi-chunk duplicate rows
+    const float* dup_grad;
+    const uint32_t* dup_t;
+    float* partial;
+    const crb_step_ctr* ctr;
+};
+
+int crb_launch_dup_pipeline(crb_handle* h, const DupArgs& a, int opt_kind, cudaStream_t s);
+int crb_launch_assign(crb_handle* h, int64_t batch, int n_roles, const int32_t* const* idx, const int* role_table,
+                      cudaStream_t s);
+int crb_count_rows(crb_handle* h, int64_t batch, int n_roles, const int32_t* const* idx, const int* role_table, cudaStream_t s);
+int crb_opt_to_dev(crb_handle* h, const crb_opt* opt, OptDev* out, int* opt_kind, cudaStream_t s);
+int crb_table_check(const crb_table* T, int opt_kind, const char* name);
+int crb_launch_loss_final(crb_handle* h, double* loss_out_dev, cudaStream_t s);

@@ -1,0 +1,245 @@
+// Evaluation kernels in canonical fp32 arithmetic (reference: each model's `_predict` + the ranking part of
+// model/RankingRecommender.py:198-299).  "Canonical" = one sequential fp32 fma chain over k = 0..d-1 per
+// (user, item) pair, the definition oracle/crb_oracle.c restates, so that ranks and top-K ids are bit-exact.
+//   score_pairs_kernel      sess.run(pre_scores, {u_idx, i_idx})        test_model_loo :257-278
+//   topk_segments_kernel    np.argsort(-scores_u)[:K] per user           test_model_loo :281-288
+//   fullrank_exact_kernel   matmul + argsort + seen filter + first K     test_model_rs  :203-240
+#include "score_common.cuh"
+
+template <int KIND>
+__global__ void __launch_bounds__(256) score_pairs_kernel(const float* __restrict__ P, const float* __restrict__ Q,
+                                                          const float* __restrict__ hvec, int dim, const int32_t* __restrict__ u,
+                                                          const int32_t* __restrict__ it, int64_t n, float* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const int32_t item = it[k];
+        out[k] = canonical_score<KIND>(P + (int64_t)u[k] * dim, Q + (int64_t)item * dim, hvec, item, dim);
+    }
+}
+
+// One warp per user segment: K rounds of arg-best over the remaining candidates.
+__global__ void __launch_bounds__(256) topk_segments_kernel(const float* __restrict__ scores, const int64_t* __restrict__ offsets,
+                                                            int64_t n_users, int K, int ascending, int32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t usr = warp; usr < n_users; usr += n_warps) {
+        const int64_t lo = offsets[usr], hi = offsets[usr + 1];
+        unsigned long long prev = ~0ULL;  // keys are strictly decreasing from round to round
+        for (int r = 0; r < K; ++r) {
+            unsigned long long best = 0ULL;
+            for (int64_t p = lo + lane; p < hi; p += 32) {
+                const unsigned long long key = rank_key(scores[p], (uint32_t)(p - lo), ascending);
+                if (key < prev && key > best) best = key;
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+                best = other > best ? other : best;
+            }
+            if (lane == 0) out[usr * K + r] = best ? (int32_t)key_index(best) : -1;
+            if (!best) {  // fewer than K candidates
+                for (int q = r + 1 + lane; q < K; q += 32) out[usr * K + q] = -1;
+                break;
+            }
+            prev = best;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------- exact full-rank top-K
+// One CTA per user.  Threads stride over the catalogue, compute the canonical score and push (key) into a shared
+// candidate buffer when it beats the CTA's current K-th key; a full buffer is compacted by a bitonic sort.
+#define FR_CAP 1024
+template <int KIND>
+__global__ void __launch_bounds__(256) fullrank_exact_kernel(const float* __restrict__ P, const float* __restrict__ Q,
+                                                             const float* __restrict__ hvec, int64_t n_items, int dim,
+                                                             const int32_t* __restrict__ users, const int32_t* __restrict__ hist_users,
+                                                             const int32_t* __restrict__ todo, int64_t n_todo,
+                                                             const int64_t* __restrict__ seen_rowptr, const int32_t* __restrict__ seen_cols,
+                                                             int K, int32_t* __restrict__ out_items, float* __restrict__ out_scores) {
+    extern __shared__ float s_user[];  // dim floats
+    __shared__ unsigned long long buf[FR_CAP];
+    __shared__ int s_count;
+    __shared__ unsigned long long s_thr;
+    constexpr int ASC = KIND == CRB_SCORE_SQDIST ? 1 : 0;
+    for (int64_t w = blockIdx.x; w < n_todo; w += gridDim.x) {
+        const int64_t k = todo ? todo[w] : w;
+        const int32_t urow = users[k];
+        const int32_t hu = hist_users ? hist_users[k] : urow;
+        __syncthreads();
+        for (int c = threadIdx.x; c < dim; c += blockDim.x) s_user[c] = P[(int64_t)urow * dim + c];
+        if (threadIdx.x == 0) { s_count = 0; s_thr = 0ULL; }
+        __syncthreads();
+        const int64_t h_lo = hu >= 0 ? seen_rowptr[hu] : 0, h_hi = hu >= 0 ? seen_rowptr[hu + 1] : 0;
+        for (int64_t base = 0; base < n_items; base += blockDim.x) {
+            const int64_t item = base + threadIdx.x;
+            unsigned long long key = 0ULL;
+            if (item < n_items) {
+                const float sc = canonical_score<KIND>(s_user, Q + item * dim, hvec, (int32_t)item, dim);
+                key = rank_key(sc, (uint32_t)item, ASC);
+                if (key <= s_thr) key = 0ULL;
+                else if (sorted_contains(seen_cols, h_lo, h_hi, (int32_t)item)) key = 0ULL;
+            }
+            // the buffer may overflow inside one sweep of 256 items: compact first when fewer than 256 slots remain
+            __syncthreads();
+            if (s_count > FR_CAP - 256) {
+                block_sort_desc<FR_CAP>(buf, s_count);
+                if (threadIdx.x == 0) {
+                    if (s_count > K) s_count = K;
+                    if (s_count == K) s_thr = buf[K - 1];
+                }
+                __syncthreads();
+            }
+            if (key) buf[atomicAdd(&s_count, 1)] = key;
+        }
+        __syncthreads();
+        block_sort_desc<FR_CAP>(buf, s_count);
+        for (int r = threadIdx.x; r < K; r += blockDim.x) {
+            const bool ok = r < s_count;
+            out_items[k * K + r] = ok ? (int32_t)key_index(buf[r]) : -1;
+            if (out_scores) out_scores[k * K + r] = ok ? key_score(buf[r], ASC) : 0.f;
+        }
+    }
+}
+
+static int grid_for(crb_handle* h, int64_t n, int per_block) {
+    int64_t b = (n + per_block - 1) / per_block;
+    int64_t cap = (int64_t)h->sm_count * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// host<->device staging helper for the evaluation entry points
+struct Stage {
+    crb_handle* h;
+    cudaStream_t s;
+    char* base;
+    int64_t used, cap;
+    void* take(int64_t bytes) {
+        bytes = (bytes + 255) & ~(int64_t)255;
+        if (used + bytes > cap) return nullptr;
+        void* p = base + used;
+        used += bytes;
+        return p;
+    }
+};
+
+template <typename T>
+static int stage_in(Stage& st, const T* src, int64_t n, const T** out) {
+    if (!src) { *out = nullptr; return CRB_OK; }
+    if (crb_is_device_ptr(src)) { *out = src; return CRB_OK; }
+    void* d = st.take(sizeof(T) * n);
+    if (!d) { crb_set_error("evaluation workspace too small"); return CRB_ERR_ARG; }
+    CRB_CUDA(cudaMemcpyAsync(d, src, sizeof(T) * n, cudaMemcpyHostToDevice, st.s));
+    *out = (const T*)d;
+    return CRB_OK;
+}
+
+template <typename T>
+static int stage_out(Stage& st, T* dst, int64_t n, T** dev) {
+    if (!dst) { *dev = nullptr; return CRB_OK; }
+    if (crb_is_device_ptr(dst)) { *dev = dst; return CRB_OK; }
+    void* d = st.take(sizeof(T) * n);
+    if (!d) { crb_set_error("evaluation workspace too small"); return CRB_ERR_ARG; }
+    *dev = (T*)d;
+    return CRB_OK;
+}
+
+template <typename T>
+static int stage_back(Stage& st, T* dst, const T* dev, int64_t n, bool* need_sync) {
+    if (!dst || dst == dev) return CRB_OK;
+    CRB_CUDA(cudaMemcpyAsync(dst, dev, sizeof(T) * n, cudaMemcpyDeviceToHost, st.s));
+    *need_sync = true;
+    return CRB_OK;
+}
+
+extern "C" int crb_score_pairs(crb_handle* h, int32_t kind, const float* P, const float* Q, const float* hvec, int32_t dim,
+                               const int32_t* u, const int32_t* i, int64_t n, float* scores, void* stream) {
+    CRB_CHECK_ARG(h && P && Q && u && i && scores, "null argument");
+    CRB_CHECK_ARG(dim > 0 && n >= 0, "sizes");
+    CRB_CHECK_ARG(kind == CRB_SCORE_DOT || kind == CRB_SCORE_SQDIST || hvec, "this score kind needs hvec");
+    if (n == 0) return CRB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    CRB_CUDA(cudaSetDevice(h->device));
+    int rc = crb_eval_ws_reserve(h, 12 * n + 4096);
+    if (rc) return rc;
+    Stage st = {h, s, (char*)h->eval_ws, 0, h->eval_ws_bytes};
+    const int32_t *du, *di;
+    float* ds;
+    if ((rc = stage_in(st, u, n, &du))) return rc;
+    if ((rc = stage_in(st, i, n, &di))) return rc;
+    if ((rc = stage_out(st, scores, n, &ds))) return rc;
+    const int grid = grid_for(h, n, 256);
+    switch (kind) {
+        case CRB_SCORE_DOT: score_pairs_kernel<CRB_SCORE_DOT><<<grid, 256, 0, s>>>(P, Q, hvec, dim, du, di, n, ds); break;
+        case CRB_SCORE_GMF: score_pairs_kernel<CRB_SCORE_GMF><<<grid, 256, 0, s>>>(P, Q, hvec, dim, du, di, n, ds); break;
+        case CRB_SCORE_SQDIST: score_pairs_kernel<CRB_SCORE_SQDIST><<<grid, 256, 0, s>>>(P, Q, hvec, dim, du, di, n, ds); break;
+        case CRB_SCORE_DOT_BIAS: score_pairs_kernel<CRB_SCORE_DOT_BIAS><<<grid, 256, 0, s>>>(P, Q, hvec, dim, du, di, n, ds); break;
+        default: crb_set_error("unknown score kind %d", kind); return CRB_ERR_ARG;
+    }
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    bool sync = false;
+    if ((rc = stage_back(st, scores, ds, n, &sync))) return rc;
+    if (sync) CRB_CUDA(cudaStreamSynchronize(s));
+    return CRB_OK;
+}
+
+extern "C" int crb_topk_segments(crb_handle* h, const float* scores, const int64_t* offsets, int64_t n_users, int32_t K,
+                                 int32_t ascending, int32_t* topk_pos, void* stream) {
+    CRB_CHECK_ARG(h && scores && offsets && topk_pos, "null argument");
+    CRB_CHECK_ARG(K >= 1 && n_users >= 0, "sizes");
+    if (n_users == 0) return CRB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    CRB_CUDA(cudaSetDevice(h->device));
+    int64_t total = 0;
+    const bool off_dev = crb_is_device_ptr(offsets);
+    if (off_dev) {
+        CRB_CUDA(cudaMemcpyAsync(&total, offsets + n_users, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        CRB_CUDA(cudaStreamSynchronize(s));
+    } else {
+        total = offsets[n_users];
+    }
+    int rc = crb_eval_ws_reserve(h, 4 * total + 8 * (n_users + 1) + 4 * n_users * K + 4096);
+    if (rc) return rc;
+    Stage st = {h, s, (char*)h->eval_ws, 0, h->eval_ws_bytes};
+    const float* dsc;
+    const int64_t* doff;
+    int32_t* dout;
+    if ((rc = stage_in(st, scores, total, &dsc))) return rc;
+    if ((rc = stage_in(st, offsets, n_users + 1, &doff))) return rc;
+    if ((rc = stage_out(st, topk_pos, n_users * K, &dout))) return rc;
+    topk_segments_kernel<<<grid_for(h, n_users, 8), 256, 0, s>>>(dsc, doff, n_users, K, ascending, dout);
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    bool sync = false;
+    if ((rc = stage_back(st, topk_pos, dout, n_users * K, &sync))) return rc;
+    if (sync) CRB_CUDA(cudaStreamSynchronize(s));
+    return CRB_OK;
+}
+
+int crb_launch_fullrank_exact(crb_handle* h, int32_t kind, const float* P, const float* Q, const float* hvec, int64_t n_items,
+                              int32_t dim, const int32_t* users, const int32_t* hist_users, const int32_t* todo, int64_t n_todo,
+                              int32_t K, int32_t* out_items, float* out_scores, cudaStream_t s) {
+    if (n_todo <= 0) return CRB_OK;
+    CRB_CHECK_ARG(K >= 1 && K <= 256, "K must be in [1,256]");
+    int grid = (int)(n_todo < (int64_t)h->sm_count * 8 ? n_todo : (int64_t)h->sm_count * 8);
+    const size_t sm = sizeof(float) * dim;
+#define FR_CASE(KD)                                                                                                          \
+    case KD:                                                                                                                 \
+        fullrank_exact_kernel<KD><<<grid, 256, sm, s>>>(P, Q, hvec, n_items, dim, users, hist_users, todo, n_todo, h->seen_rowptr, \
+                                                        h->seen_cols, K, out_items, out_scores);                             \
+        break;
+    switch (kind) {
+        FR_CASE(CRB_SCORE_DOT)
+        FR_CASE(CRB_SCORE_GMF)
+        FR_CASE(CRB_SCORE_SQDIST)
+        FR_CASE(CRB_SCORE_DOT_BIAS)
+        default: crb_set_error("unknown score kind %d", kind); return CRB_ERR_ARG;
+    }
+#undef FR_CASE
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}

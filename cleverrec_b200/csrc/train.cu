@@ -1,0 +1,609 @@
+// Fused training steps of the dot-product family (reference: model/ranking/BPR.py:31-44, GMF.py:37-49, MF per
+// SURVEY F6).  One step = what `sess.run([self.train, self.loss], feed)` does in the reference:
+//   gather rows -> interaction -> loss -> backward -> de-duplicated row-sparse optimizer apply.
+// Kernels per step (all on one stream, no host synchronisation):
+//   K1 count_rows / sample_kernel<.,true>  one 32-bit atomic per row occurrence -> multiplicity + occurrence rank
+//   K2 assign_kernel                        duplicate rows get a slot range, a work list is built
+//   K3 *_step_kernel                        the fused gather/forward/backward; rows of multiplicity 1 are updated
+//                                           in place (read once, written once); duplicates store their gradient
+//   K4 dup_reduce_kernel / dup_final_kernel slot sums (deterministic order for <= 32 occurrences) + one apply
+//   K5 loss_final_kernel                    fixed-order sum of the per-block loss partials
+#include <cstddef>
+
+#include "rowopt.cuh"
+
+// ------------------------------------------------------------------------------------------------ K1 / K2
+struct RoleArgs {
+    const int32_t* idx[3];
+    uint32_t* rank[3];
+    unsigned long long* meta[3];  // meta table of each role
+    int table[3];
+    int n_roles;
+};
+
+__global__ void __launch_bounds__(256) count_rows_kernel(RoleArgs a, int64_t batch) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < batch; t += stride) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            if (r < a.n_roles) a.rank[r][t] = atomicAdd(reinterpret_cast<unsigned int*>(a.meta[r] + a.idx[r][t]), 1u);
+    }
+}
+
+__global__ void __launch_bounds__(256) assign_kernel(RoleArgs a, int64_t batch, crb_step_ctr* ctr, crb_dup_row* dup_rows,
+                                                     crb_work* work, unsigned int* multi) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < batch; t += stride) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            if (r >= a.n_roles) continue;
+            if (a.rank[r][t] != 1u) continue;  // exactly one occurrence of every duplicated row has rank 1
+            const int32_t row = a.idx[r][t];
+            unsigned int* m = reinterpret_cast<unsigned int*>(a.meta[r] + row);
+            const uint32_t c = m[0];
+            const uint32_t base = atomicAdd(&ctr->dup_slots, c);
+            m[1] = base;
+            const uint32_t k = atomicAdd(&ctr->dup_rows, 1u);
+            const uint32_t nch = (c + CRB_DUP_CHUNK - 1) / CRB_DUP_CHUNK;
+            const uint32_t wb = atomicAdd(&ctr->work_items, nch);
+            uint32_t pb = 0;
+            if (nch > 1) {
+                pb = atomicAdd(&ctr->partial_slots, nch);
+                multi[atomicAdd(&ctr->multi_rows, 1u)] = k;
+            }
+            crb_dup_row d;
+            d.row = row; d.table = a.table[r]; d.base = base; d.cnt = c; d.wbase = wb; d.nchunk = nch; d.pbase = pb; d.pad = 0;
+            dup_rows[k] = d;
+            for (uint32_t q = 0; q < nch; ++q) { crb_work w; w.dup = k; w.chunk = q; work[wb + q] = w; }
+        }
+    }
+}
+
+static int flat_grid(crb_handle* h, int64_t n, int per_block) {
+    int64_t b = (n + per_block - 1) / per_block;
+    int64_t cap = (int64_t)h->sm_count * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+int crb_count_rows(crb_handle* h, int64_t batch, int n_roles, const int32_t* const* idx, const int* role_table, cudaStream_t s) {
+    RoleArgs a;
+    a.n_roles = n_roles;
+    for (int r = 0; r < 3; ++r) {
+        a.idx[r] = r < n_roles ? idx[r] : nullptr;
+        a.rank[r] = h->rank[r];
+        a.table[r] = r < n_roles ? role_table[r] : 0;
+        a.meta[r] = h->meta[a.table[r]];
+    }
+    count_rows_kernel<<<flat_grid(h, batch, 256), 256, 0, s>>>(a, batch);
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}
+
+int crb_launch_assign(crb_handle* h, int64_t batch, int n_roles, const int32_t* const* idx, const int* role_table, cudaStream_t s) {
+    RoleArgs a;
+    a.n_roles = n_roles;
+    for (int r = 0; r < 3; ++r) {
+        a.idx[r] = r < n_roles ? idx[r] : nullptr;
+        a.rank[r] = h->rank[r];
+        a.table[r] = r < n_roles ? role_table[r] : 0;
+        a.meta[r] = h->meta[a.table[r]];
+    }
+    assign_kernel<<<flat_grid(h, batch, 256), 256, 0, s>>>(a, batch, h->ctr, h->dup_rows, h->work, h->multi);
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ K4
+// Sum of gradient slots [lo, hi) of one duplicate row into acc (lane-group view).  Rows with <= 32 occurrences
+// are summed in ascending triplet order (deterministic); longer ones in slot order.
+template <int LANES, int VPL>
+__device__ __forceinline__ void sum_slots(float4* acc, const float* __restrict__ dup_grad, const uint32_t* __restrict__ dup_t,
+                                          uint32_t lo, uint32_t hi, bool ordered, int dim, int gl) {
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ordered) {
+        int64_t prev = -1;
+        for (uint32_t k = lo; k < hi; ++k) {
+            int64_t best = 0x7fffffffffffLL;
+            uint32_t bs = lo;
+            for (uint32_t q = lo; q < hi; ++q) {
+                int64_t tq = (int64_t)dup_t[q];
+                if (tq > prev && tq < best) { best = tq; bs = q; }
+            }
+            prev = best;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                int c = (gl + LANES * v) * 4;
+                if (c < dim) {
+                    float4 g = ld4(dup_grad + (int64_t)bs * dim + c);
+                    acc[v].x += g.x; acc[v].y += g.y; acc[v].z += g.z; acc[v].w += g.w;
+                }
+            }
+        }
+    } else {
+        for (uint32_t q = lo; q < hi; ++q) {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                int c = (gl + LANES * v) * 4;
+                if (c < dim) {
+                    float4 g = ld4(dup_grad + (int64_t)q * dim + c);
+                    acc[v].x += g.x; acc[v].y += g.y; acc[v].z += g.z; acc[v].w += g.w;
+                }
+            }
+        }
+    }
+}
+
+template <int LANES, int VPL, int OPT>
+__device__ __forceinline__ void dup_apply(const DupArgs& a, const crb_dup_row& d, const float4* acc, int gl) {
+    const TableDev& T = a.tab[d.table];
+    RowRegs<LANES, VPL> r;
+    row_load_w<LANES, VPL>(r, T, d.row, a.dim, gl);
+    row_load_state<LANES, VPL, OPT>(r, T, d.row, a.dim, gl);
+    row_replay<LANES, VPL, OPT>(r, a.opt, a.opt.step);
+    row_apply_store<LANES, VPL, OPT>(r, acc, T, d.row, a.dim, gl, a.opt);
+    if (gl == 0) a.meta[d.table][d.row] = 0ULL;
+}
+
+template <int LANES, int VPL, int OPT>
+__global__ void __launch_bounds__(256) dup_reduce_kernel(DupArgs a) {
+    const int gl = threadIdx.x % LANES;
+    const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / LANES;
+    const uint32_t n_work = a.ctr->work_items;
+    for (int64_t k = group; k < n_work; k += n_groups) {
+        const crb_work w = a.work[k];
+        const crb_dup_row d = a.dup_rows[w.dup];
+        const uint32_t lo = d.base + w.chunk * CRB_DUP_CHUNK;
+        const uint32_t hi = min(d.base + d.cnt, lo + CRB_DUP_CHUNK);
+        float4 acc[VPL];
+        sum_slots<LANES, VPL>(acc, a.dup_grad, a.dup_t, lo, hi, d.cnt <= 32u, a.dim, gl);
+        if (d.nchunk == 1) {
+            dup_apply<LANES, VPL, OPT>(a, d, acc, gl);
+        } else {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                int c = (gl + LANES * v) * 4;
+                if (c < a.dim) st4(a.partial + (int64_t)(d.pbase + w.chunk) * a.dim + c, acc[v]);
+            }
+        }
+    }
+}
+
+template <int LANES, int VPL, int OPT>
+__global__ void __launch_bounds__(256) dup_final_kernel(DupArgs a) {
+    const int gl = threadIdx.x % LANES;
+    const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / LANES;
+    const uint32_t n_multi = a.ctr->multi_rows;
+    for (int64_t k = group; k < n_multi; k += n_groups) {
+        const crb_dup_row d = a.dup_rows[a.multi[k]];
+        float4 acc[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t q = 0; q < d.nchunk; ++q) {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                int c = (gl + LANES * v) * 4;
+                if (c < a.dim) {
+                    float4 g = ld4(a.partial + (int64_t)(d.pbase + q) * a.dim + c);
+                    acc[v].x += g.x; acc[v].y += g.y; acc[v].z += g.z; acc[v].w += g.w;
+                }
+            }
+        }
+        dup_apply<LANES, VPL, OPT>(a, d, acc, gl);
+    }
+}
+
+template <int LANES, int VPL>
+static int launch_dup_t(crb_handle* h, const DupArgs& a, int opt_kind, cudaStream_t s) {
+    const int grid = h->sm_count * 4;
+#define CRB_DUP_CASE(O)                                                \
+    case O:                                                            \
+        dup_reduce_kernel<LANES, VPL, O><<<grid, 256, 0, s>>>(a);      \
+        dup_final_kernel<LANES, VPL, O><<<h->sm_count, 256, 0, s>>>(a); \
+        break;
+    switch (opt_kind) {
+        CRB_DUP_CASE(OPT_SGD)
+        CRB_DUP_CASE(OPT_ADAGRAD)
+        CRB_DUP_CASE(OPT_ADAM_LAZY)
+        CRB_DUP_CASE(OPT_ADAM_TF1)
+    }
+#undef CRB_DUP_CASE
+    h->launches += 2;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}
+
+#define CRB_DIM_DISPATCH(dim, FN, ...)                                   \
+    ((dim) <= 32 ? FN<8, 1>(__VA_ARGS__)                                 \
+     : (dim) <= 64 ? FN<16, 1>(__VA_ARGS__)                              \
+     : (dim) <= 128 ? FN<32, 1>(__VA_ARGS__)                             \
+     : (dim) <= 256 ? FN<32, 2>(__VA_ARGS__)                             \
+                    : FN<32, 4>(__VA_ARGS__))
+
+int crb_launch_dup_pipeline(crb_handle* h, const DupArgs& a, int opt_kind, cudaStream_t s) {
+    return CRB_DIM_DISPATCH(a.dim, launch_dup_t, h, a, opt_kind, s);
+}
+
+// ------------------------------------------------------------------------------------------------ K5
+__global__ void loss_final_kernel(const double* __restrict__ block_loss, int n, double* out) {
+    // one warp, fixed order: lane l sums entries l, l+32, ...; then a fixed shuffle tree
+    double v = 0.0;
+    for (int k = threadIdx.x; k < n; k += 32) v += block_loss[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) *out = v;
+}
+
+int crb_launch_loss_final(crb_handle* h, double* loss_out_dev, cudaStream_t s) {
+    loss_final_kernel<<<1, 32, 0, s>>>(h->block_loss, h->loss_blocks, loss_out_dev);
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}
+
+// block-level reduction of the per-thread double loss; result to block_loss[blockIdx.x]
+__device__ __forceinline__ void block_loss_store(double v, double* block_loss) {
+    __shared__ double sm[8];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) sm[w] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += sm[k];
+        block_loss[blockIdx.x] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ optimizer plumbing
+int crb_opt_to_dev(crb_handle* h, const crb_opt* opt, OptDev* o, int* opt_kind, cudaStream_t s) {
+    CRB_CHECK_ARG(opt, "opt is null");
+    CRB_CHECK_ARG(opt->step >= 1 && opt->step < 0x7fffffffLL, "opt.step must be >= 1");
+    o->lr = (float)opt->lr;
+    o->b1 = (float)opt->beta1;
+    o->b2 = (float)opt->beta2;
+    o->eps = (float)opt->eps;
+    o->step = (int32_t)opt->step;
+    o->lr_t = 0.f;
+    o->lrt = h->lrt;
+    switch (opt->kind) {
+        case CRB_OPT_SGD: *opt_kind = OPT_SGD; break;
+        case CRB_OPT_ADAGRAD: *opt_kind = OPT_ADAGRAD; break;
+        case CRB_OPT_ADAM: {
+            *opt_kind = opt->adam_mode == CRB_ADAM_LAZY ? OPT_ADAM_LAZY : OPT_ADAM_TF1;
+            const double t = (double)opt->step;
+            o->lr_t = (float)(opt->lr * sqrt(1.0 - pow(opt->beta2, t)) / (1.0 - pow(opt->beta1, t)));
+            int rc = crb_lrt_prepare(h, opt, s);
+            if (rc) return rc;
+            break;
+        }
+        default:
+            crb_set_error("unknown optimizer kind %d", opt->kind);
+            return CRB_ERR_ARG;
+    }
+    return CRB_OK;
+}
+
+int crb_table_check(const crb_table* T, int opt_kind, const char* name) {
+    if (!T || !T->w || T->rows <= 0 || T->dim <= 0 || (T->dim % 4) != 0 || T->dim > 512) {
+        crb_set_error("table %s: need w != NULL, rows > 0, dim %% 4 == 0, dim <= 512", name);
+        return CRB_ERR_ARG;
+    }
+    if (((uintptr_t)T->w & 15) != 0) { crb_set_error("table %s: w must be 16-byte aligned", name); return CRB_ERR_ARG; }
+    if (opt_kind != OPT_SGD && !T->s1) { crb_set_error("table %s: optimizer slot s1 is NULL", name); return CRB_ERR_ARG; }
+    if ((opt_kind == OPT_ADAM_LAZY || opt_kind == OPT_ADAM_TF1) && !T->s2) { crb_set_error("table %s: optimizer slot s2 is NULL", name); return CRB_ERR_ARG; }
+    if (opt_kind == OPT_ADAM_TF1 && !T->last) { crb_set_error("table %s: CRB_ADAM_TF1 needs the `last` step array", name); return CRB_ERR_ARG; }
+    return CRB_OK;
+}
+
+static TableDev to_dev(const crb_table* T) {
+    TableDev d;
+    d.w = T->w; d.s1 = T->s1; d.s2 = T->s2; d.last = T->last;
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------------ K3: BPR
+struct BprArgs {
+    TableDev P, Q;
+    unsigned long long* metaU;
+    unsigned long long* metaI;
+    const int32_t* u;
+    const int32_t* i;
+    const int32_t* j;
+    const uint32_t* rk[3];
+    int64_t batch;
+    int dim;
+    float reg;
+    OptDev opt;
+    float* dup_grad;
+    uint32_t* dup_t;
+    double* block_loss;
+};
+
+// one row of the triplet after the forward/backward: in place when it is the batch's only occurrence, else a slot
+template <int LANES, int VPL, int OPT>
+__device__ __forceinline__ void emit_row(RowRegs<LANES, VPL>& r, const float4* g, const TableDev& T, unsigned long long* meta,
+                                         int32_t row, unsigned long long m, uint32_t rank, uint32_t t, uint32_t role, int dim,
+                                         int gl, const OptDev& o, float* dup_grad, uint32_t* dup_t) {
+    const uint32_t cnt = (uint32_t)m;
+    if (cnt == 1u) {
+        row_apply_store<LANES, VPL, OPT>(r, g, T, row, dim, gl, o);
+        if (gl == 0) meta[row] = 0ULL;
+    } else {
+        const uint32_t slot = (uint32_t)(m >> 32) + rank;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            int c = (gl + LANES * v) * 4;
+            if (c < dim) st4(dup_grad + (int64_t)slot * dim + c, g[v]);
+        }
+        if (gl == 0) dup_t[slot] = (t << 2) | role;  // unique, ordered key of the occurrence
+    }
+}
+
+template <int LANES, int VPL, int OPT>
+__global__ void __launch_bounds__(256) bpr_step_kernel(BprArgs a) {
+    constexpr int GPW = 32 / LANES;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % LANES;
+    const int sub = lane / LANES;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double loss_acc = 0.0;
+    for (int64_t base = warp * GPW; base < a.batch; base += n_warps * GPW) {
+        const int64_t t = base + sub;
+        const bool active = t < a.batch;
+        const int64_t tt = active ? t : a.batch - 1;
+        const int32_t u = a.u[tt], i = a.i[tt], j = a.j[tt];
+        const unsigned long long mu = a.metaU[u], mi = a.metaI[i], mj = a.metaI[j];
+        RowRegs<LANES, VPL> ru, ri, rj;
+        row_load_w<LANES, VPL>(ru, a.P, u, a.dim, gl);
+        row_load_w<LANES, VPL>(ri, a.Q, i, a.dim, gl);
+        row_load_w<LANES, VPL>(rj, a.Q, j, a.dim, gl);
+        // optimizer slots are only needed here for rows this group will update in place; CRB_ADAM_TF1 needs them for
+        // every row because the forward must see the replayed (dense-equivalent) value.
+        const bool su = OptTraits<OPT>::replay || (uint32_t)mu == 1u;
+        const bool si = OptTraits<OPT>::replay || (uint32_t)mi == 1u;
+        const bool sj = OptTraits<OPT>::replay || (uint32_t)mj == 1u;
+        if (OptTraits<OPT>::has_s1) {
+            if (su) row_load_state<LANES, VPL, OPT>(ru, a.P, u, a.dim, gl);
+            if (si) row_load_state<LANES, VPL, OPT>(ri, a.Q, i, a.dim, gl);
+            if (sj) row_load_state<LANES, VPL, OPT>(rj, a.Q, j, a.dim, gl);
+        }
+        row_replay<LANES, VPL, OPT>(ru, a.opt, a.opt.step);
+        row_replay<LANES, VPL, OPT>(ri, a.opt, a.opt.step);
+        row_replay<LANES, VPL, OPT>(rj, a.opt, a.opt.step);
+        // forward: x = p_u.(q_i - q_j)  (BPR.py:39-41);  l2 = |p_u|^2 + |q_i|^2 + |q_j|^2 (BPR.py:42-43)
+        float x = 0.f, sq = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const float4 p = ru.w[v], qi = ri.w[v], qj = rj.w[v];
+            const float4 dq = make_float4(qi.x - qj.x, qi.y - qj.y, qi.z - qj.z, qi.w - qj.w);
+            x += dot4(p, dq);
+            sq += dot4(p, p) + dot4(qi, qi) + dot4(qj, qj);
+        }
+        x = group_sum<LANES>(x);
+        sq = group_sum<LANES>(sq);
+        // d/dx softplus(-x) = sigmoid(x) - 1 = -sigmoid(-x)
+        const float g = -sigmoid_f(-x);
+        if (active && gl == 0) loss_acc += (double)(softplus_neg(x) + a.reg * 0.5f * sq);
+        float4 gu[VPL], gi[VPL], gj[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const float4 p = ru.w[v], qi = ri.w[v], qj = rj.w[v];
+            gu[v] = make_float4(fmaf(g, qi.x - qj.x, a.reg * p.x), fmaf(g, qi.y - qj.y, a.reg * p.y),
+                                fmaf(g, qi.z - qj.z, a.reg * p.z), fmaf(g, qi.w - qj.w, a.reg * p.w));
+            gi[v] = make_float4(fmaf(g, p.x, a.reg * qi.x), fmaf(g, p.y, a.reg * qi.y), fmaf(g, p.z, a.reg * qi.z),
+                                fmaf(g, p.w, a.reg * qi.w));
+            gj[v] = make_float4(fmaf(-g, p.x, a.reg * qj.x), fmaf(-g, p.y, a.reg * qj.y), fmaf(-g, p.z, a.reg * qj.z),
+                                fmaf(-g, p.w, a.reg * qj.w));
+        }
+        if (active) {
+            emit_row<LANES, VPL, OPT>(ru, gu, a.P, a.metaU, u, mu, a.rk[0][t], (uint32_t)t, 0u, a.dim, gl, a.opt, a.dup_grad, a.dup_t);
+            emit_row<LANES, VPL, OPT>(ri, gi, a.Q, a.metaI, i, mi, a.rk[1][t], (uint32_t)t, 1u, a.dim, gl, a.opt, a.dup_grad, a.dup_t);
+            emit_row<LANES, VPL, OPT>(rj, gj, a.Q, a.metaI, j, mj, a.rk[2][t], (uint32_t)t, 2u, a.dim, gl, a.opt, a.dup_grad, a.dup_t);
+        }
+    }
+    block_loss_store(loss_acc, a.block_loss);
+}
+
+template <int LANES, int VPL>
+static int launch_bpr_t(crb_handle* h, const BprArgs& a, int opt_kind, cudaStream_t s) {
+    // grid == loss_blocks so that every block_loss entry is rewritten each step
+    const int grid = h->loss_blocks;
+    switch (opt_kind) {
+        case OPT_SGD: bpr_step_kernel<LANES, VPL, OPT_SGD><<<grid, 256, 0, s>>>(a); break;
+        case OPT_ADAGRAD: bpr_step_kernel<LANES, VPL, OPT_ADAGRAD><<<grid, 256, 0, s>>>(a); break;
+        case OPT_ADAM_LAZY: bpr_step_kernel<LANES, VPL, OPT_ADAM_LAZY><<<grid, 256, 0, s>>>(a); break;
+        case OPT_ADAM_TF1: bpr_step_kernel<LANES, VPL, OPT_ADAM_TF1><<<grid, 256, 0, s>>>(a); break;
+    }
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}
+
+// stage a possibly-host int32 feed into the handle workspace; returns the device pointer to use
+static int stage_i32(crb_handle* h, const int32_t* src, int slot, int64_t n, const int32_t** out, cudaStream_t s) {
+    if (crb_is_device_ptr(src)) { *out = src; return CRB_OK; }
+    CRB_CUDA(cudaMemcpyAsync(h->idx[slot], src, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+    *out = h->idx[slot];
+    return CRB_OK;
+}
+
+static int finish_loss(crb_handle* h, double* loss_out, int64_t n, cudaStream_t s) {
+    // device buffers were written in place by loss_final_kernel; host buffers get one copy + sync
+    if (!loss_out || crb_is_device_ptr(loss_out)) return CRB_OK;
+    CRB_CUDA(cudaMemcpyAsync(loss_out, h->loss_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    CRB_CUDA(cudaStreamSynchronize(s));
+    return CRB_OK;
+}
+
+// the part of one BPR step after the indices are on the device and (optionally) already counted
+static int bpr_step_device(crb_handle* h, const crb_table* P, const crb_table* Q, const OptDev& od, int opt_kind,
+                           const int32_t* u, const int32_t* i, const int32_t* j, int64_t batch, float reg, bool counted,
+                           double* loss_dev, cudaStream_t s) {
+    const int32_t* idx[3] = {u, i, j};
+    const int role_table[3] = {0, 1, 1};
+    int rc;
+    if (!counted) {
+        rc = crb_count_rows(h, batch, 3, idx, role_table, s);
+        if (rc) return rc;
+    }
+    rc = crb_launch_assign(h, batch, 3, idx, role_table, s);
+    if (rc) return rc;
+    BprArgs a;
+    a.P = to_dev(P); a.Q = to_dev(Q);
+    a.metaU = h->meta[0]; a.metaI = h->meta[1];
+    a.u = u; a.i = i; a.j = j;
+    a.rk[0] = h->rank[0]; a.rk[1] = h->rank[1]; a.rk[2] = h->rank[2];
+    a.batch = batch; a.dim = P->dim; a.reg = reg; a.opt = od;
+    a.dup_grad = h->dup_grad; a.dup_t = h->dup_t; a.block_loss = h->block_loss;
+    rc = CRB_DIM_DISPATCH(a.dim, launch_bpr_t, h, a, opt_kind, s);
+    if (rc) return rc;
+    DupArgs d;
+    d.tab[0] = a.P; d.tab[1] = a.Q;
+    d.meta[0] = h->meta[0]; d.meta[1] = h->meta[1];
+    d.dim = a.dim; d.opt = od;
+    d.dup_rows = h->dup_rows; d.work = h->work; d.multi = h->multi;
+    d.dup_grad = h->dup_grad; d.dup_t = h->dup_t; d.partial = h->partial; d.ctr = h->ctr;
+    rc = crb_launch_dup_pipeline(h, d, opt_kind, s);
+    if (rc) return rc;
+    return crb_launch_loss_final(h, loss_dev, s);
+}
+
+static int zero_step_counters(crb_handle* h, cudaStream_t s) {
+    // everything except sampler_err (sticky until reported)
+    CRB_CUDA(cudaMemsetAsync(h->ctr, 0, offsetof(crb_step_ctr, sampler_err), s));
+    CRB_CUDA(cudaMemsetAsync(&h->ctr->partial_slots, 0, sizeof(unsigned int), s));
+    return CRB_OK;
+}
+
+static int bpr_common_checks(crb_handle* h, const crb_table* P, const crb_table* Q, const crb_opt* opt, OptDev* od, int* opt_kind,
+                             int64_t batch, int64_t steps, cudaStream_t s) {
+    CRB_CHECK_ARG(h, "null handle");
+    int rc = crb_opt_to_dev(h, opt, od, opt_kind, s);
+    if (rc) return rc;
+    if ((rc = crb_table_check(P, *opt_kind, "P"))) return rc;
+    if ((rc = crb_table_check(Q, *opt_kind, "Q"))) return rc;
+    CRB_CHECK_ARG(P->dim == Q->dim, "P.dim != Q.dim");
+    CRB_CHECK_ARG(batch > 0 && batch < 0x40000000LL, "batch must be in [1, 2^30)");
+    CRB_CUDA(cudaSetDevice(h->device));
+    if ((rc = crb_ws_reserve(h, batch, P->dim, steps, s))) return rc;
+    if ((rc = crb_meta_reserve(h, 0, P->rows, s))) return rc;
+    if ((rc = crb_meta_reserve(h, 1, Q->rows, s))) return rc;
+    return CRB_OK;
+}
+
+extern "C" int crb_train_step_bpr(crb_handle* h, const crb_table* P, const crb_table* Q, const crb_opt* opt, const int32_t* u,
+                                  const int32_t* i, const int32_t* j, int64_t batch, float reg, double* loss_out, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    OptDev od;
+    int opt_kind = 0;
+    int rc = bpr_common_checks(h, P, Q, opt, &od, &opt_kind, batch, 1, s);
+    if (rc) return rc;
+    CRB_CHECK_ARG(u && i && j, "null index feed");
+    const int32_t *du, *di, *dj;
+    if ((rc = stage_i32(h, u, 0, batch, &du, s))) return rc;
+    if ((rc = stage_i32(h, i, 1, batch, &di, s))) return rc;
+    if ((rc = stage_i32(h, j, 2, batch, &dj, s))) return rc;
+    if ((rc = zero_step_counters(h, s))) return rc;
+    double* ld = (loss_out && crb_is_device_ptr(loss_out)) ? loss_out : h->loss_dev;
+    rc = bpr_step_device(h, P, Q, od, opt_kind, du, di, dj, batch, reg, false, ld, s);
+    if (rc) return rc;
+    return finish_loss(h, loss_out, 1, s);
+}
+
+extern "C" int crb_train_epoch_bpr(crb_handle* h, const crb_table* P, const crb_table* Q, const crb_opt* opt, uint64_t seed,
+                                   uint32_t epoch, int64_t first, int64_t batch, int64_t n_steps, int32_t neg_ratio, float reg,
+                                   double* loss_out, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    OptDev od;
+    int opt_kind = 0;
+    CRB_CHECK_ARG(n_steps >= 1, "n_steps");
+    int rc = bpr_common_checks(h, P, Q, opt, &od, &opt_kind, batch, n_steps, s);
+    if (rc) return rc;
+    const int64_t rows = crb_epoch_rows(h, neg_ratio, 0);
+    CRB_CHECK_ARG(first >= 0 && first < rows, "first row outside the epoch");
+    const bool host_loss = !(loss_out && crb_is_device_ptr(loss_out));
+    crb_opt step_opt = *opt;
+    for (int64_t k = 0; k < n_steps; ++k) {
+        const int64_t lo = first + k * batch;
+        if (lo >= rows) { crb_set_error("step %lld starts past the end of the epoch", (long long)k); return CRB_ERR_ARG; }
+        const int64_t b = (rows - lo) < batch ? (rows - lo) : batch;
+        step_opt.step = opt->step + k;
+        if ((rc = crb_opt_to_dev(h, &step_opt, &od, &opt_kind, s))) return rc;
+        if ((rc = zero_step_counters(h, s))) return rc;
+        rc = crb_launch_sample_pairwise(h, seed, epoch, lo, b, neg_ratio, h->idx[0], h->idx[1], h->idx[2], nullptr, true, s);
+        if (rc) return rc;
+        double* ld = host_loss ? h->loss_dev + k : loss_out + k;
+        rc = bpr_step_device(h, P, Q, od, opt_kind, h->idx[0], h->idx[1], h->idx[2], b, reg, true, ld, s);
+        if (rc) return rc;
+    }
+    if (loss_out && host_loss) {
+        rc = finish_loss(h, loss_out, n_steps, s);
+        if (rc) return rc;
+    }
+    // sampler attempt overflow is sticky in ctr->sampler_err; report it when the caller synchronises on a host loss
+    if (loss_out && host_loss) {
+        unsigned int err = 0;
+        CRB_CUDA(cudaMemcpy(&err, &h->ctr->sampler_err, sizeof(err), cudaMemcpyDeviceToHost));
+        if (err) {
+            CRB_CUDA(cudaMemset(&h->ctr->sampler_err, 0, sizeof(err)));
+            crb_set_error("sampler: %u rows found no admissible negative", err);
+            return CRB_ERR_SAMPLER;
+        }
+    }
+    return CRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ Adam flush
+template <int OPT>
+__global__ void __launch_bounds__(256) adam_flush_kernel(TableDev T, int64_t rows, int dim, OptDev o) {
+    // thread per float4 chunk; brings the row up to o.step (inclusive) with decay-only steps
+    const int64_t chunks_per_row = dim / 4;
+    const int64_t n = rows * chunks_per_row;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const int64_t row = k / chunks_per_row;
+        const int last = T.last[row];
+        if (last >= o.step) continue;
+        float4 W = ld4(T.w + k * 4), M = ld4(T.s1 + k * 4), V = ld4(T.s2 + k * 4);
+        for (int s = last + 1; s <= o.step; ++s) adam_decay4(W, M, V, lrt_at(o, s), o);
+        st4(T.w + k * 4, W); st4(T.s1 + k * 4, M); st4(T.s2 + k * 4, V);
+    }
+}
+
+__global__ void __launch_bounds__(256) set_last_kernel(int32_t* last, int64_t rows, int32_t step) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < rows; k += stride)
+        if (last[k] < step) last[k] = step;
+}
+
+extern "C" int crb_adam_flush(crb_handle* h, const crb_table* T, const crb_opt* opt, void* stream) {
+    CRB_CHECK_ARG(h && T && opt, "null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (opt->kind != CRB_OPT_ADAM || opt->adam_mode != CRB_ADAM_TF1) return CRB_OK;
+    if (opt->step < 1) return CRB_OK;  // nothing applied yet
+    OptDev od;
+    int opt_kind = 0;
+    int rc = crb_opt_to_dev(h, opt, &od, &opt_kind, s);
+    if (rc) return rc;
+    if ((rc = crb_table_check(T, opt_kind, "T"))) return rc;
+    const int64_t n = T->rows * (T->dim / 4);
+    adam_flush_kernel<OPT_ADAM_TF1><<<flat_grid(h, n, 256), 256, 0, s>>>(to_dev(T), T->rows, T->dim, od);
+    set_last_kernel<<<flat_grid(h, T->rows, 256), 256, 0, s>>>(T->last, T->rows, od.step);
+    h->launches += 2;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}
+
+extern "C" int crb_train_step_pointwise(crb_handle* h, int32_t kind, const crb_table* P, const crb_table* Q, float* hvec, float* h_s1,
+                                        float* h_s2, const crb_opt* opt, int32_t loss_kind, const int32_t* u, const int32_t* i,
+                                        const float* y, int64_t batch, float reg, double* loss_out, void* stream) {
+    crb_set_error("pointwise step not built yet");
+    return CRB_ERR_UNSUPPORTED;
+}

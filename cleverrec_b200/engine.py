@@ -1,0 +1,220 @@
+"""Thin Python object layer over the C ABI: device memory is owned by torch tensors, every numeric operation is
+one call into libcleverrec_b200.so.  This is the replacement for the reference's `tf.Session` (main.py:39-45):
+the mirror classes under cleverrec_b200/model call it where the reference calls `self.sess.run`."""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CrbOpt, CrbTable, check, ptr
+
+
+class Table(object):
+    """One TF variable [rows, dim] + its optimizer slot variables, on the device."""
+
+    def __init__(self, w, optimizer, adam_mode="tf1"):
+        assert w.is_cuda and w.dtype == torch.float32 and w.dim() == 2 and w.is_contiguous()
+        self.w = w
+        self.s1 = self.s2 = self.last = None
+        if optimizer == "Adagrad":
+            self.s1 = torch.full_like(w, 0.1)  # tf.train.AdagradOptimizer initial_accumulator_value
+        elif optimizer == "Adam":
+            self.s1, self.s2 = torch.zeros_like(w), torch.zeros_like(w)
+            if adam_mode == "tf1":
+                self.last = torch.zeros(w.shape[0], dtype=torch.int32, device=w.device)
+        self.c = CrbTable(ptr(self.w), ptr(self.s1), ptr(self.s2), ptr(self.last), w.shape[0], w.shape[1], 0)
+
+    @property
+    def rows(self):
+        return self.w.shape[0]
+
+    @property
+    def dim(self):
+        return self.w.shape[1]
+
+
+class Optimizer(object):
+    """utils/tools.py:79-87 get_optimizer with TF-1 defaults; `t` counts applied steps."""
+    KINDS = {"SGD": _lib.OPT_SGD, "Adagrad": _lib.OPT_ADAGRAD, "Adam": _lib.OPT_ADAM}
+
+    def __init__(self, kind, lr, adam_mode="tf1", beta1=0.9, beta2=0.999, eps=1e-8):
+        if kind not in self.KINDS:
+            raise ValueError("optimizer must be one of SGD/Adam/Adagrad, got %r" % (kind,))
+        if adam_mode not in ("tf1", "lazy"):
+            raise ValueError("adam_mode must be 'tf1' or 'lazy'")
+        self.kind, self.lr, self.adam_mode = kind, float(lr), adam_mode
+        self.beta1, self.beta2, self.eps = beta1, beta2, eps
+        self.t = 0
+
+    def c(self, step):
+        return CrbOpt(self.KINDS[self.kind], _lib.ADAM_TF1 if self.adam_mode == "tf1" else _lib.ADAM_LAZY, self.lr, self.beta1,
+                      self.beta2, self.eps, step)
+
+
+class Engine(object):
+    def __init__(self, device=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("cleverrec_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        h = C.c_void_p()
+        check(self.lib.crb_create(device, C.byref(h)))
+        self.h = h
+        self._hist = None
+        self.n_users = self.n_items = self.n_pos = 0
+
+    def close(self):
+        if self.h:
+            self.lib.crb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    @property
+    def launches(self):
+        return int(self.lib.crb_launch_count(self.h))
+
+    # ------------------------------------------------------------------ history
+    def set_history_arrays(self, n_users, n_items, pos_user, pos_item, seen_rowptr, seen_cols):
+        """Arrays as produced by history_from_dict (NumPy or torch, host or device)."""
+        def dev(a, dt):
+            t = torch.as_tensor(a)
+            return t.to(device=self.device, dtype=dt).contiguous()
+        pu, pi = dev(pos_user, torch.int32), dev(pos_item, torch.int32)
+        rp, sc = dev(seen_rowptr, torch.int64), dev(seen_cols, torch.int32)
+        if sc.numel() == 0:
+            sc = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._hist = (pu, pi, rp, sc)  # keep alive: the library borrows the pointers
+        self.n_users, self.n_items, self.n_pos = int(n_users), int(n_items), int(pu.numel())
+        check(self.lib.crb_set_history(self.h, n_users, n_items, self.n_pos, ptr(pu) if self.n_pos else None,
+                                       ptr(pi) if self.n_pos else None, ptr(rp), ptr(sc), self.stream))
+
+    def set_history(self, ui_train, n_users, n_items):
+        self.set_history_arrays(n_users, n_items, *history_from_dict(ui_train, n_users))
+
+    def epoch_rows(self, neg_ratio, kind="pairwise"):
+        return int(self.lib.crb_epoch_rows(self.h, neg_ratio, {"pairwise": 0, "pointwise": 1, "cml": 2}[kind]))
+
+    # ------------------------------------------------------------------ sampler
+    def sample_pairwise(self, seed, epoch, first, count, neg_ratio, with_nbr=False):
+        u, i, j = (torch.empty(count, dtype=torch.int32, device=self.device) for _ in range(3))
+        nbr = torch.empty(count, dtype=torch.int32, device=self.device) if with_nbr else None
+        check(self.lib.crb_sample_pairwise(self.h, seed, epoch, first, count, neg_ratio, ptr(u), ptr(i), ptr(j), ptr(nbr), self.stream))
+        return (u, i, j, nbr) if with_nbr else (u, i, j)
+
+    def sample_pointwise(self, seed, epoch, first, count, neg_ratio, with_nbr=False):
+        u, i = (torch.empty(count, dtype=torch.int32, device=self.device) for _ in range(2))
+        y = torch.empty(count, dtype=torch.float32, device=self.device)
+        nbr = torch.empty(count, dtype=torch.int32, device=self.device) if with_nbr else None
+        check(self.lib.crb_sample_pointwise(self.h, seed, epoch, first, count, neg_ratio, ptr(u), ptr(i), ptr(y), ptr(nbr), self.stream))
+        return (u, i, y, nbr) if with_nbr else (u, i, y)
+
+    def sample_cml(self, seed, epoch, first, count, neg_ratio):
+        u, i = (torch.empty(count, dtype=torch.int32, device=self.device) for _ in range(2))
+        neg = torch.empty((count, neg_ratio), dtype=torch.int32, device=self.device)
+        check(self.lib.crb_sample_cml(self.h, seed, epoch, first, count, neg_ratio, ptr(u), ptr(i), ptr(neg), self.stream))
+        return u, i, neg
+
+    # ------------------------------------------------------------------ training
+    @staticmethod
+    def _feed_i32(x):
+        """Feeds may be host (NumPy / list, like a TF feed_dict) or device tensors; the library stages host buffers."""
+        if isinstance(x, torch.Tensor):
+            return x if x.dtype == torch.int32 else x.to(torch.int32)
+        return np.ascontiguousarray(np.asarray(x), dtype=np.int32)
+
+    def train_step_bpr(self, P, Q, opt, u, i, j, reg, loss_out=None):
+        """One `sess.run([train, loss], {u_idx, i_idx, j_idx})` of BPR.  Returns the loss as a Python float when
+        loss_out is None (host read, synchronises), else writes it to the 1-element double device tensor."""
+        u, i, j = self._feed_i32(u), self._feed_i32(i), self._feed_i32(j)
+        opt.t += 1
+        co = opt.c(opt.t)
+        host = np.zeros(1, dtype=np.float64) if loss_out is None else None
+        check(self.lib.crb_train_step_bpr(self.h, C.byref(P.c), C.byref(Q.c), C.byref(co), ptr(u), ptr(i), ptr(j), len(u),
+                                          float(reg), ptr(host) if loss_out is None else ptr(loss_out), self.stream))
+        return float(host[0]) if loss_out is None else None
+
+    def train_epoch_bpr(self, P, Q, opt, seed, epoch, first, batch, n_steps, neg_ratio, reg, loss_out):
+        """n_steps fused sample+train steps; loss_out: double tensor [n_steps] on the device (no sync) or NumPy (sync)."""
+        co = opt.c(opt.t + 1)
+        check(self.lib.crb_train_epoch_bpr(self.h, C.byref(P.c), C.byref(Q.c), C.byref(co), seed, epoch, first, batch, n_steps,
+                                           neg_ratio, float(reg), ptr(loss_out), self.stream))
+        opt.t += n_steps
+
+    def adam_flush(self, table, opt):
+        if opt.kind == "Adam" and opt.adam_mode == "tf1" and opt.t > 0:
+            co = opt.c(opt.t)
+            check(self.lib.crb_adam_flush(self.h, C.byref(table.c), C.byref(co), self.stream))
+
+    # ------------------------------------------------------------------ evaluation
+    def score_pairs(self, kind, P, Q, u, i, hvec=None, out=None):
+        """Scores of flattened (user, item) pairs in canonical fp32.  u/i host or device; returns NumPy when the
+        feeds are host arrays (like sess.run), else a device tensor."""
+        u, i = self._feed_i32(u), self._feed_i32(i)
+        n = len(u)
+        host = not isinstance(u, torch.Tensor)
+        if out is None:
+            out = np.empty(n, dtype=np.float32) if host else torch.empty(n, dtype=torch.float32, device=self.device)
+        check(self.lib.crb_score_pairs(self.h, kind, ptr(P), ptr(Q), ptr(hvec), P.shape[1], ptr(u), ptr(i), n, ptr(out), self.stream))
+        return out
+
+    def topk_segments(self, scores, offsets, K, ascending=False):
+        n_users = len(offsets) - 1
+        host = not isinstance(scores, torch.Tensor)
+        if host:
+            scores = np.ascontiguousarray(scores, dtype=np.float32)
+            offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+            out = np.empty((n_users, K), dtype=np.int32)
+        else:
+            offsets = torch.as_tensor(offsets, dtype=torch.int64, device=self.device)
+            out = torch.empty((n_users, K), dtype=torch.int32, device=self.device)
+        check(self.lib.crb_topk_segments(self.h, ptr(scores), ptr(offsets), n_users, K, 1 if ascending else 0, ptr(out), self.stream))
+        return out
+
+    def score_topk(self, kind, P, Q, users, K, hvec=None, hist_users=None, exact=False, n_items=None, return_scores=False):
+        """Best K unseen item ids of each user (test_model_rs).  users host -> NumPy out; device -> tensors."""
+        users = self._feed_i32(users)
+        n = len(users)
+        host = not isinstance(users, torch.Tensor)
+        if hist_users is not None:
+            hist_users = self._feed_i32(hist_users)
+        n_items = Q.shape[0] if n_items is None else n_items
+        if host:
+            items = np.empty((n, K), dtype=np.int32)
+            scores = np.empty((n, K), dtype=np.float32) if return_scores else None
+        else:
+            items = torch.empty((n, K), dtype=torch.int32, device=self.device)
+            scores = torch.empty((n, K), dtype=torch.float32, device=self.device) if return_scores else None
+        check(self.lib.crb_score_topk(self.h, kind, ptr(P), ptr(Q), ptr(hvec), n_items, P.shape[1], ptr(users), ptr(hist_users), n, K,
+                                      1 if exact else 0, ptr(items), ptr(scores), self.stream))
+        return (items, scores) if return_scores else items
+
+    def score_topk_stats(self):
+        st = (C.c_int64 * 4)()
+        check(self.lib.crb_score_topk_stats(self.h, C.byref(st)))
+        return {"certified": st[0], "exact_rerun": st[1], "max_candidates": st[2]}
+
+
+def history_from_dict(ui_train, n_users):
+    """data.ui_train (dict[int -> list[int]], RankingPreprocess.py:117) -> flat positives in the enumeration order of
+    utils/sampler.py:50-52 + per-user sorted-unique CSR (the `seen_items` sets)."""
+    users = list(ui_train.keys())
+    lens = np.fromiter((len(ui_train[u]) for u in users), dtype=np.int64, count=len(users))
+    pos_user = np.repeat(np.asarray(users, dtype=np.int32), lens)
+    pos_item = np.fromiter((i for u in users for i in ui_train[u]), dtype=np.int32, count=int(lens.sum()))
+    key = np.unique(pos_user.astype(np.int64) * (1 << 31) + pos_item.astype(np.int64))
+    su, sc = (key >> 31).astype(np.int64), (key & ((1 << 31) - 1)).astype(np.int32)
+    seen_rowptr = np.zeros(n_users + 1, dtype=np.int64)
+    np.cumsum(np.bincount(su, minlength=n_users), out=seen_rowptr[1:])
+    return pos_user, pos_item, seen_rowptr, sc

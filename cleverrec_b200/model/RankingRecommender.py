@@ -1,0 +1,176 @@
+" Recommender for Ranking Model -- mirror of the reference model/RankingRecommender.py (hot-path parts). "
+# Same public surface as the reference class:
+#   train_model() -> float                       mean of the per-step *summed* losses   (:33-61)
+#   test_model_loo() / test_model_rs()           -> (HR, MRR, NDCG) defaultdict(list)   (:250-299 / :198-247)
+#   run_model()                                   epoch loop, log format, best-by-NDCG@topk[0] (:395-440)
+# What changed underneath: the sampler, every sess.run and the argsort/top-K run in libcleverrec_b200.so.
+import math
+import time
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+from .Recommender import Recommender
+from ..utils.metrics import batch_ranking_metrics
+from ..utils.tools import timer
+
+
+class RankingRecommender(Recommender):
+    def __init__(self, sess, data, configs, logger):
+        super(RankingRecommender, self).__init__(sess, data, configs, logger)
+        self.neg_ratio = int(configs['neg_ratio'])
+        self.model_params += ', neg_ratio=%d' % self.neg_ratio
+        # Testing data
+        self.test_users = list(data.ui_test.keys())
+        self.test_batches = math.ceil(len(self.test_users) / self.batch_size_t)
+        self.epoch = 0            # epochs sampled so far (the sampler's `epoch` counter)
+        self.engine.set_history(data.ui_train, self._history_rows(), data.item_nums)
+        self._test_cache = None
+
+    def _history_rows(self):
+        return self.data.user_nums
+
+    # ---- what a model provides -------------------------------------------------------------------------------
+    def _train_epoch_pairwise(self, epoch, n_rows, n_batches, losses):
+        """Run all steps of one pairwise epoch; losses: double device tensor [n_batches]."""
+        raise NotImplementedError
+
+    def _train_epoch_pointwise(self, epoch, n_rows, n_batches, losses):
+        raise NotImplementedError
+
+    def _score_spec(self):
+        """-> (kind, P_tensor, Q_tensor, hvec_or_None) for crb_score_pairs / crb_score_topk."""
+        raise NotImplementedError
+
+    def _before_eval(self):
+        pass
+
+    # ---- Train the model (Single epoch) ----------------------------------------------------------------------
+    def train_model(self):
+        if self.is_pairwise == 'True':
+            n_rows = self.engine.epoch_rows(self.neg_ratio, 'pairwise')
+            n_batches = math.ceil(n_rows / self.batch_size)
+            losses = torch.zeros(n_batches, dtype=torch.float64, device=self.engine.device)
+            self._train_epoch_pairwise(self.epoch, n_rows, n_batches, losses)
+        else:
+            n_rows = self.engine.epoch_rows(self.neg_ratio, 'pointwise')
+            n_batches = math.ceil(n_rows / self.batch_size)
+            losses = torch.zeros(n_batches, dtype=torch.float64, device=self.engine.device)
+            self._train_epoch_pointwise(self.epoch, n_rows, n_batches, losses)
+        self.epoch += 1
+        total_loss = float(losses.sum().item())  # one device->host read per epoch
+        return total_loss / n_batches
+
+    # ---- Leave-One-Out / Random split with 1000 negative items ---------------------------------------------
+    def _loo_feed(self):
+        """Flattened (u_idx, i_idx) of all test users in test_users order (RankingRecommender.py:257-264), built once."""
+        if self._test_cache is None:
+            ui_test = self.data.ui_test
+            lens = np.fromiter((len(ui_test[u]) for u in self.test_users), dtype=np.int64, count=len(self.test_users))
+            offsets = np.zeros(len(self.test_users) + 1, dtype=np.int64)
+            np.cumsum(lens, out=offsets[1:])
+            u_idx = np.repeat(np.asarray(self.test_users, dtype=np.int32), lens)
+            i_idx = np.fromiter((i for u in self.test_users for i in ui_test[u]), dtype=np.int32, count=int(offsets[-1]))
+            dev = self.engine.device
+            self._test_cache = (offsets, torch.from_numpy(u_idx).to(dev), torch.from_numpy(i_idx).to(dev), i_idx)
+        return self._test_cache
+
+    def _pair_users(self, u_idx):
+        """user-side row of each flattened pair (FISM-like models override: rows of the precomputed user matrix)."""
+        return u_idx
+
+    def test_model_loo(self):
+        HR, MRR, NDCG = defaultdict(list), defaultdict(list), defaultdict(list)  # evaluation metrics
+        self._before_eval()
+        offsets, u_dev, i_dev, i_host = self._loo_feed()
+        kind, P, Q, hvec = self._score_spec()
+        K = self.topk[-1]
+        for t_id in range(self.test_batches):
+            a, b = t_id * self.batch_size_t, min((t_id + 1) * self.batch_size_t, len(self.test_users))
+            lo, hi = int(offsets[a]), int(offsets[b])
+            # Predict: pre_scores = sess.run(self.pre_scores, {u_idx, i_idx})
+            scores = self.engine.score_pairs(kind, P, Q, self._pair_users(u_dev[lo:hi]), i_dev[lo:hi], hvec=hvec)
+            # Evaluate: args_u = np.argsort(-pre_scores_u)[:topk[-1]]  (ascending for cml_like)
+            seg = torch.from_numpy(offsets[a:b + 1] - lo).to(self.engine.device)
+            args = self.engine.topk_segments(scores, seg, K, ascending=self.cml_like).cpu().numpy()
+            real_lists, rec = [], np.full((b - a, K), -1, dtype=np.int64)
+            for k in range(b - a):
+                u = self.test_users[a + k]
+                real_items = self.data.ui_test[u][self.neg_samples:]
+                if not isinstance(real_items, list):  # loo
+                    real_items = [real_items]
+                real_lists.append(real_items)
+                valid = args[k] >= 0
+                rec[k, valid] = i_host[offsets[a + k] + args[k][valid]]  # np.take(ui_test[u], args_u)
+            for kid in range(len(self.topk)):
+                hr, mrr, ndcg = batch_ranking_metrics(real_lists, rec, self.topk[kid])
+                HR[kid].extend(hr.tolist())
+                MRR[kid].extend(mrr.tolist())
+                NDCG[kid].extend(ndcg.tolist())
+        return HR, MRR, NDCG
+
+    # ---- Random split with all ------------------------------------------------------------------------------
+    def _fullrank_users(self, cur_users):
+        """-> (user rows into P, history user ids or None)"""
+        return np.asarray(cur_users, dtype=np.int32), None
+
+    def test_model_rs(self):
+        HR, MRR, NDCG = defaultdict(list), defaultdict(list), defaultdict(list)  # evaluation metrics
+        self._before_eval()
+        kind, P, Q, hvec = self._score_spec()
+        K = self.topk[-1]
+        for t_id in range(self.test_batches):
+            cur_users = self.test_users[t_id * self.batch_size_t:(t_id + 1) * self.batch_size_t]
+            rows, hist = self._fullrank_users(cur_users)
+            # pre_scores = sess.run(...); argsort; skip ui_train[u]; first topk[-1]  -> one fused call
+            topk_items = self.engine.score_topk(kind, P, Q, rows, K, hvec=hvec, hist_users=hist, exact=self.score_exact,
+                                                n_items=self.data.item_nums)
+            real_lists = [self.data.ui_test[u] for u in cur_users]
+            for kid in range(len(self.topk)):
+                hr, mrr, ndcg = batch_ranking_metrics(real_lists, topk_items, self.topk[kid])
+                HR[kid].extend(hr.tolist())
+                MRR[kid].extend(mrr.tolist())
+                NDCG[kid].extend(ndcg.tolist())
+        return HR, MRR, NDCG
+
+    @timer('run_model')
+    def run_model(self):
+        self.build_model()  # allocate + initialise tables (the reference builds the graph and runs the initializer)
+
+        best_ndcg10, best_epoch = 0, 0  # Record best metrics w.r.t. NDCG@10
+        best_metrics = {}
+        for epoch in range(self.epoches):
+            # Train
+            t1 = time.time()
+            avg_loss = self.train_model()
+            self.logger.info(' epoch %d\n  Training loss: %.4f, time: %s' % (epoch + 1, avg_loss, time.strftime('%H:%M:%S', time.gmtime(time.time() - t1))))
+
+            # Test
+            t2 = time.time()
+            if (epoch + 1) % self.T:  # Test every T epoches
+                continue
+            if self.configs['data.split_way'] == 'loo' or self.neg_samples > 0:  # loo/random sampling with 1000 ...
+                HR, MRR, NDCG = self.test_model_loo()
+            else:  # random split
+                HR, MRR, NDCG = self.test_model_rs()
+            self.logger.info('  Testing time: %s' % time.strftime('%H:%M:%S', time.gmtime(time.time() - t2)))
+
+            # Record best performance
+            best_flag = False
+            for id in range(len(self.topk)):
+                hr, mrr, ndcg = np.mean(HR[id]), np.mean(MRR[id]), np.mean(NDCG[id])
+                self.logger.info('  (k=%d) HR=%.4f, MRR=%.4f, NDCG=%.4f' % (self.topk[id], hr, mrr, ndcg))
+                if id == 0 and ndcg > best_ndcg10:
+                    best_flag = True
+                    best_ndcg10 = ndcg
+                if best_flag:
+                    best_metrics[id] = (hr, mrr, ndcg)
+                    best_epoch = epoch + 1
+
+        # Final results
+        self.logger.info('best_epoch: %d' % best_epoch)
+        for id in range(len(self.topk)):
+            hr, mrr, ndcg = best_metrics[id]
+            self.logger.info('  (k=%d) HR=%.4f, MRR=%.4f, NDCG=%.4f' % (self.topk[id], hr, mrr, ndcg))
+        return best_epoch, best_metrics

@@ -1,0 +1,59 @@
+# coding: utf-8
+""" Base Recommender for Ranking/Rating Model -- mirror of the reference model/Recommender.py:9-40.
+
+Same constructor `(sess, data, configs, logger)`, same config keys, same abstract methods.  `sess` is the
+reference's tf.Session slot: pass None (an Engine is created on `gpu.id`... see engine_device) or an existing
+cleverrec_b200.engine.Engine to share one device handle between models."""
+import torch
+
+from ..engine import Engine
+from ..utils.tools import get_initializer, get_optimizer
+
+
+class Recommender(object):
+    def __init__(self, sess, data, configs, logger):
+        self.model = configs['recommender']
+        self.sess, self.data, self.configs, self.logger = sess, data, configs, logger
+        # Common parameters
+        self._get_common_params()
+
+    def _get_common_params(self):
+        c = self.configs
+        self.epoches, self.batch_size, self.batch_size_t, self.lr, self.neg_samples = int(c['epoches']), int(c['batch_size']), \
+            int(c['test.batch_size']), float(c['lr']), int(c['test.neg_samples'])
+        self.fism_like, self.cml_like = 'fism_like' in c, 'cml_like' in c
+        self.is_pairwise = c['is_pairwise']  # the *string* 'True'/'False', compared as such (RankingRecommender.py:35)
+        # B200-path keys (all optional; defaults keep the reference's behaviour)
+        self.seed = int(c.get('seed', 0))
+        self.adam_mode = c.get('adam_mode', 'tf1')          # 'tf1' = tf.train.AdamOptimizer semantics, 'lazy' = LazyAdam
+        self.score_exact = c.get('score_exact', 'False') == 'True'  # full-rank eval on CUDA cores instead of tcgen05
+        self.init_generator = torch.Generator().manual_seed(self.seed)
+        self.initializer = get_initializer(c['init_method'], float(c['stddev']), generator=self.init_generator)
+        if self.initializer is None:
+            raise ValueError('unknown init_method %r' % c['init_method'])
+        self.regularizer = None  # the reference attaches an l2_regularizer that never reaches any loss
+        self.loss_func = c['loss_func']
+        self.optimizer = get_optimizer(c['optimizer'], self.lr, adam_mode=self.adam_mode)
+        if self.optimizer is None:
+            raise ValueError('unknown optimizer %r' % c['optimizer'])
+        self.saved_model_dir = c['saved_dir']
+        self.T = int(c['test.interval'])  # Test every T epoches
+        self.topk = list(map(int, c['topk'][1:-1].split(',')))
+        self.model_params = 'lr=%s, loss_func=%s' % (self.lr, c['loss_func'])
+        # device handle
+        if isinstance(self.sess, Engine):
+            self.engine = self.sess
+        else:
+            self.engine = Engine(int(c.get('engine.device', 0)))
+
+    def build_model(self):
+        raise NotImplementedError
+
+    def train_model(self):
+        raise NotImplementedError
+
+    def test_model(self):
+        raise NotImplementedError
+
+    def run_model(self):
+        raise NotImplementedError

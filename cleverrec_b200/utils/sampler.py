@@ -1,0 +1,66 @@
+# coding: utf-8
+""" Sample instances for training -- drop-in signatures of the reference utils/sampler.py:10-99.
+
+The reference materialises an epoch with Python loops over np.random; here the epoch is drawn by the CUDA sampler
+(cleverrec_b200/csrc/sampler.cu) and copied back so callers get the same tuple of NumPy int arrays.  The model
+classes do not use these functions in their training loop (they call the fused sample+train entry point); they
+exist so code written against the reference's sampler API keeps working."""
+import math
+
+import numpy as np
+
+from ..engine import Engine
+
+_state = {"engine": None, "data_id": None, "epoch": 0, "seed": 0}
+
+
+def set_seed(seed):
+    _state["seed"] = int(seed)
+    _state["epoch"] = 0
+
+
+def _engine_for(data):
+    if _state["engine"] is None:
+        _state["engine"] = Engine(0)
+    if _state["data_id"] != id(data):
+        _state["engine"].set_history(data.ui_train, data.user_nums, data.item_nums)
+        _state["data_id"] = id(data)
+    return _state["engine"]
+
+
+def _next_epoch():
+    e = _state["epoch"]
+    _state["epoch"] += 1
+    return e
+
+
+# Get training instances for pointwise learning
+def pointwise_ranking_sampler(data, neg_ratio, batch_size, fism_like=False):
+    eng = _engine_for(data)
+    n = eng.epoch_rows(neg_ratio, "pointwise")
+    out = eng.sample_pointwise(_state["seed"], _next_epoch(), 0, n, neg_ratio, with_nbr=fism_like)
+    res = (math.ceil(n / batch_size), out[0].cpu().numpy().astype(np.int64), out[1].cpu().numpy().astype(np.int64),
+           out[2].cpu().numpy().astype(np.float64))
+    if fism_like:
+        res = res + (out[3].cpu().numpy().astype(np.int64),)
+    return res
+
+
+# Get training instances for pairwise learning
+def pairwise_ranking_sampler(data, neg_ratio, batch_size, fism_like=False):
+    eng = _engine_for(data)
+    n = eng.epoch_rows(neg_ratio, "pairwise")
+    out = eng.sample_pairwise(_state["seed"], _next_epoch(), 0, n, neg_ratio, with_nbr=fism_like)
+    res = (math.ceil(n / batch_size),) + tuple(t.cpu().numpy().astype(np.int64) for t in out[:3])
+    if fism_like:
+        res = res + (out[3].cpu().numpy().astype(np.int64),)
+    return res
+
+
+# For CML
+def ranking_sampler_cml(data, neg_ratio, batch_size):
+    eng = _engine_for(data)
+    n = eng.epoch_rows(neg_ratio, "cml")
+    u, i, neg = eng.sample_cml(_state["seed"], _next_epoch(), 0, n, neg_ratio)
+    return (math.ceil(n / batch_size), u.cpu().numpy().astype(np.int64), i.cpu().numpy().astype(np.int64),
+            neg.cpu().numpy().astype(np.int64))

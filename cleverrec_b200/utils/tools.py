@@ -1,0 +1,102 @@
+# coding: utf-8
+"""Factories of the reference's utils/tools.py:9-87 for the B200 path: re_index, timer, logger, initializer and
+optimizer.  (get_loss lives in the CUDA kernels; the social/graph helpers :116-297 are out of scope.)"""
+import functools
+import logging
+import math
+import os
+import sys
+import time
+
+import torch
+
+from ..engine import Optimizer
+
+
+# Reindex ids (utils/tools.py:9-15)
+def re_index(data_set):
+    data_map = {}
+    id = 0
+    for d in data_set:
+        data_map[d] = id
+        id += 1
+    return data_map
+
+
+# Time cost decorator (utils/tools.py:18-28)
+def timer(text):
+    def decorator(func):
+        @functools.wraps(func)
+        def wrapper(*args, **kwargs):
+            t1 = time.time()
+            print('Start %s...' % text)
+            res = func(*args, **kwargs)
+            print('%s done, time: %s' % (text, time.strftime('%H:%M:%S', time.gmtime(time.time() - t1))))
+            return res
+        return wrapper
+    return decorator
+
+
+# Logger (utils/tools.py:31-48): same format, file + stdout
+def get_logger(log_dir, model):
+    if not os.path.exists(log_dir):
+        os.makedirs(log_dir)
+    logger = logging.getLogger()
+    logger.setLevel(logging.DEBUG)
+    formatter = logging.Formatter('%(asctime)s  %(message)s', datefmt='%Y-%m-%d %H:%M:%S')
+    fh = logging.FileHandler(os.path.join(log_dir, model + '.log'))
+    fh.setLevel(logging.DEBUG)
+    fh.setFormatter(formatter)
+    ch = logging.StreamHandler(sys.stdout)
+    ch.setLevel(logging.DEBUG)
+    ch.setFormatter(formatter)
+    logger.addHandler(fh)
+    logger.addHandler(ch)
+    return logger
+
+
+# Initializer (utils/tools.py:51-63).  Returns a callable shape -> fp32 CPU tensor (the reference's initializer
+# objects are called as `self.initializer(shape_)`).  'xavier_uniform' (used by the shipped FISM/GMF/NeuMF/NAIS
+# confs but unknown to the reference factory) is treated as 'xavier'.
+def get_initializer(init_method, stddev=None, generator=None):
+    init_method = init_method.strip()
+
+    def fans(shape):
+        if len(shape) == 1:
+            return shape[0], shape[0]
+        return shape[0], shape[1]
+
+    def normal(shape):
+        return torch.randn(*shape, generator=generator) * stddev
+
+    def tnormal(shape):  # truncated at 2 sigma, re-drawn
+        t = torch.empty(*shape)
+        torch.nn.init.trunc_normal_(t, mean=0.0, std=stddev, a=-2 * stddev, b=2 * stddev, generator=generator)
+        return t
+
+    def uniform(shape):
+        return (torch.rand(*shape, generator=generator) * 2 - 1) * stddev
+
+    def xavier(shape):
+        fi, fo = fans(shape)
+        limit = math.sqrt(6.0 / (fi + fo))
+        return (torch.rand(*shape, generator=generator) * 2 - 1) * limit
+
+    def xavier_normal(shape):  # variance_scaling_initializer(factor=1, FAN_AVG, uniform=False): truncated normal
+        fi, fo = fans(shape)
+        sd = math.sqrt(1.3 * 2.0 / (fi + fo))
+        t = torch.empty(*shape)
+        torch.nn.init.trunc_normal_(t, mean=0.0, std=sd, a=-2 * sd, b=2 * sd, generator=generator)
+        return t
+
+    table = {'normal': normal, 'tnormal': tnormal, 'uniform': uniform, 'xavier': xavier, 'xavier_uniform': xavier,
+             'xavier_normal': xavier_normal}
+    return table.get(init_method)
+
+
+# Optimizer (utils/tools.py:79-87)
+def get_optimizer(optimizer, lr, adam_mode='tf1'):
+    optimizer = optimizer.strip().strip("'\"")
+    if optimizer in ('SGD', 'Adam', 'Adagrad'):
+        return Optimizer(optimizer, lr, adam_mode=adam_mode)
+    return None

@@ -1,0 +1,172 @@
+/*
+ * cleverrec_b200 -- C ABI of the B200-native hot path (libcleverrec_b200.so).
+ *
+ * This is the drop-in boundary.  In the reference every numeric operation of the hot path is
+ * one `self.sess.run(fetches, feed_dict)` into TensorFlow-1 (model/RankingRecommender.py:46,59,
+ * 85,98,221,278) preceded by a Python sampler call (utils/sampler.py:10-99).  Each entry point
+ * below replaces one of those calls; the comment on it cites the reference interface it stands
+ * for.  INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain C types only; every function returns 0 on success or a negative crb_status and
+ *    leaves a thread-local message readable through crb_last_error().
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  All work is
+ *    enqueued asynchronously on it unless a HOST output pointer forces a synchronisation.
+ *  - table pointers (crb_table) are DEVICE pointers owned by the caller (torch tensors).
+ *  - index / label / output buffers may be DEVICE or HOST pointers: the library inspects them
+ *    with cudaPointerGetAttributes and stages host buffers itself (that is the path `e2e` in
+ *    bench.py times: host feed in, host loss/ranks out, exactly like a TF feed_dict).
+ *  - there is NO CPU implementation behind any entry point: without a CUDA device every call
+ *    fails with CRB_ERR_CUDA.
+ */
+#ifndef CLEVERREC_B200_H
+#define CLEVERREC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRB_ABI_VERSION 1
+
+typedef enum {
+    CRB_OK = 0,
+    CRB_ERR_ARG = -1,      /* bad argument (null pointer, dim not multiple of 4, ...) */
+    CRB_ERR_CUDA = -2,     /* a CUDA runtime call failed; message holds cudaGetErrorString */
+    CRB_ERR_STATE = -3,    /* call order (e.g. sampling before crb_set_history) */
+    CRB_ERR_SAMPLER = -4,  /* a user has fewer than neg_ratio unseen items (the reference loops forever) */
+    CRB_ERR_UNSUPPORTED = -5
+} crb_status;
+
+typedef struct crb_handle crb_handle;
+
+/* One embedding table with its optimizer slots (TF variables + slot variables).
+ *  w    [rows, dim] fp32 row-major, 16-byte aligned, dim % 4 == 0
+ *  s1   Adagrad accumulator (init 0.1) | Adam m   (NULL for SGD)
+ *  s2   Adam v                                   (NULL unless Adam)
+ *  last int32 [rows]: step of the last Adam update of the row (NULL unless adam_mode == CRB_ADAM_TF1)  */
+typedef struct {
+    float* w;
+    float* s1;
+    float* s2;
+    int32_t* last;
+    int64_t rows;
+    int32_t dim;
+    int32_t _pad;
+} crb_table;
+
+enum { CRB_OPT_SGD = 0, CRB_OPT_ADAGRAD = 1, CRB_OPT_ADAM = 2 };
+/* CRB_ADAM_TF1 : tf.train.AdamOptimizer sparse-apply semantics (moments of EVERY row decay every step and
+ *                every row moves) realised row-sparsely by replaying a row's missed steps
+ *                when it is next touched / at crb_adam_flush -- identical result, sparse traffic.
+ * CRB_ADAM_LAZY: LazyAdam (touched rows only).  A documented deviation; throughput mode.            */
+enum { CRB_ADAM_TF1 = 0, CRB_ADAM_LAZY = 1 };
+
+/* utils/tools.py:79-87 (get_optimizer) with TF-1 defaults. `step` is the 1-based index of THIS step. */
+typedef struct {
+    int32_t kind;
+    int32_t adam_mode;
+    double lr;     /* doubles: Adam's lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t) is evaluated in double (as TF/Python do) */
+    double beta1;  /* then rounded to fp32; the kernels use the fp32 roundings of lr, beta1, beta2, eps         */
+    double beta2;
+    double eps;
+    int64_t step;
+} crb_opt;
+
+/* utils/tools.py:66-76 (get_loss) */
+enum { CRB_LOSS_BPR = 0, CRB_LOSS_CROSS_ENTROPY = 1, CRB_LOSS_SQUARE = 2, CRB_LOSS_HINGE = 3 };
+
+/* score kinds for the evaluation entry points (each model's `_predict`) */
+enum {
+    CRB_SCORE_DOT = 0,      /* BPR.py:49,51  MF               s = p_u . q_i                        */
+    CRB_SCORE_GMF = 1,      /* GMF.py:40,43                   s = sum_k (p_uk*q_ik)*h_k  (the logit; sigmoid is monotone) */
+    CRB_SCORE_SQDIST = 2,   /* CML.py:82,84                   s = sum_k (p_uk-q_ik)^2   (ascending is better)           */
+    CRB_SCORE_DOT_BIAS = 3  /* FISM.py:53,70                  s = p_u . q_i + b_i  (p_u = precomputed user vector)      */
+};
+
+int crb_abi_version(void);
+const char* crb_last_error(void);
+
+/* main.py:39-45 (tf.Session creation) -> one handle per device. */
+int crb_create(int device, crb_handle** out);
+int crb_destroy(crb_handle* h);
+
+/* data.ui_train (model/RankingPreprocess.py:117) in device form.
+ *  pos_user/pos_item [n_pos]: the positives in the order utils/sampler.py:50-52 enumerates them
+ *  seen_rowptr [n_users+1], seen_cols: per-user sorted unique history (the `seen_items` sets)
+ * DEVICE pointers, borrowed until the next call / crb_destroy. */
+int crb_set_history(crb_handle* h, int64_t n_users, int64_t n_items, int64_t n_pos,
+                    const int32_t* pos_user, const int32_t* pos_item,
+                    const int64_t* seen_rowptr, const int32_t* seen_cols, void* stream);
+
+/* utils/sampler.py:46-74 pairwise_ranking_sampler: rows [first, first+count) of the epoch's shuffled
+ * triplet list.  nbr (fism_like's u_neighbors_num) may be NULL.  Outputs: DEVICE int32. */
+int crb_sample_pairwise(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t first, int64_t count,
+                        int32_t neg_ratio, int32_t* u, int32_t* i, int32_t* j, int32_t* nbr, void* stream);
+/* utils/sampler.py:10-43 pointwise_ranking_sampler (1 positive + neg_ratio negatives per positive). */
+int crb_sample_pointwise(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t first, int64_t count,
+                         int32_t neg_ratio, int32_t* u, int32_t* i, float* y, int32_t* nbr, void* stream);
+/* utils/sampler.py:77-99 ranking_sampler_cml: neg is [count, neg_ratio] row-major. */
+int crb_sample_cml(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t first, int64_t count,
+                   int32_t neg_ratio, int32_t* u, int32_t* i, int32_t* neg, void* stream);
+/* number of rows in one epoch of each sampler (utils/sampler.py:65 `train_nums`) */
+int64_t crb_epoch_rows(crb_handle* h, int32_t neg_ratio, int32_t sampler_kind /*0 pairwise,1 pointwise,2 cml*/);
+
+/* sess.run([self.train, self.loss], {u_idx, i_idx, j_idx})  for model/ranking/BPR.py:31-44.
+ * loss_out (double*, DEVICE or HOST) receives this step's summed loss (`loss_val`). */
+int crb_train_step_bpr(crb_handle* h, const crb_table* P, const crb_table* Q, const crb_opt* opt,
+                       const int32_t* u, const int32_t* i, const int32_t* j, int64_t batch,
+                       float reg, double* loss_out, void* stream);
+
+/* One call = `n_steps` iterations of RankingRecommender.train_model's loop body (:39-46) with the
+ * sampler fused in: step k trains on epoch rows [first + k*batch, min(first+(k+1)*batch, epoch_rows)).
+ * loss_out[k] (DEVICE or HOST double[n_steps]).  opt->step is the index of the first step. */
+int crb_train_epoch_bpr(crb_handle* h, const crb_table* P, const crb_table* Q, const crb_opt* opt,
+                        uint64_t seed, uint32_t epoch, int64_t first, int64_t batch, int64_t n_steps,
+                        int32_t neg_ratio, float reg, double* loss_out, void* stream);
+
+/* sess.run([train, loss], {u_idx, i_idx, y}) for the pointwise dot-product family:
+ *   kind CRB_SCORE_DOT : MF   (BPR.py:39 dot + get_loss('square'|'cross_entropy'))
+ *   kind CRB_SCORE_GMF : GMF  (GMF.py:37-49), h/h_s1/h_s2 = the dense variable h_gmf and its slots */
+int crb_train_step_pointwise(crb_handle* h, int32_t kind, const crb_table* P, const crb_table* Q,
+                             float* hvec, float* h_s1, float* h_s2, const crb_opt* opt, int32_t loss_kind,
+                             const int32_t* u, const int32_t* i, const float* y, int64_t batch,
+                             float reg, double* loss_out, void* stream);
+
+/* Bring every row of a CRB_ADAM_TF1 table up to `step` (call before reading w: evaluation, checkpoint). */
+int crb_adam_flush(crb_handle* h, const crb_table* T, const crb_opt* opt, void* stream);
+
+/* sess.run(self.pre_scores, {u_idx, i_idx}) on flattened (user, candidate) pairs -- test_model_loo,
+ * model/RankingRecommender.py:257-278.  Canonical arithmetic: one sequential fp32 fma chain over k.
+ * scores: float[n] DEVICE or HOST.  hvec: GMF h (kind GMF) or item bias (kind DOT_BIAS), else NULL. */
+int crb_score_pairs(crb_handle* h, int32_t kind, const float* P, const float* Q, const float* hvec, int32_t dim,
+                    const int32_t* u, const int32_t* i, int64_t n, float* scores, void* stream);
+
+/* Lines :281-288 of test_model_loo for a ragged batch: user k owns scores[offsets[k]..offsets[k+1]); writes the
+ * positions of its best K candidates (score descending -- ascending when `ascending` --, ties by position
+ * ascending; -1 padded) to topk_pos[k*K..].  DEVICE or HOST buffers. */
+int crb_topk_segments(crb_handle* h, const float* scores, const int64_t* offsets, int64_t n_users, int32_t K,
+                      int32_t ascending, int32_t* topk_pos, void* stream);
+
+/* test_model_rs, model/RankingRecommender.py:203-240: all-item scores of `users`, seen items (crb_set_history)
+ * skipped, best K item ids per user.  `exact`=1: fp32 canonical arithmetic on CUDA cores.  `exact`=0: bf16
+ * tcgen05 tensor-core pass produces certified candidate sets that are re-scored in canonical fp32, so the
+ * returned ids are identical to exact=1 (users whose certificate fails are re-run exactly, on the GPU).
+ * P: [*, dim] user vectors indexed by `users` (for FISM pass precomputed vectors and users = 0..n-1 with
+ * hist_users = the real ids).  topk_items int32 [n_users*K], topk_scores float [n_users*K] (may be NULL). */
+int crb_score_topk(crb_handle* h, int32_t kind, const float* P, const float* Q, const float* hvec,
+                   int64_t n_items, int32_t dim, const int32_t* users, const int32_t* hist_users, int64_t n_users,
+                   int32_t K, int32_t exact, int32_t* topk_items, float* topk_scores, void* stream);
+
+/* statistics of the last crb_score_topk(exact=0) call: [0] users certified by the tensor-core pass,
+ * [1] users re-run exactly, [2] candidate slots used (max over users). */
+int crb_score_topk_stats(crb_handle* h, int64_t stats[4]);
+
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
+int64_t crb_launch_count(crb_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLEVERREC_B200_H */
