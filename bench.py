@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on synthetic data of the named shape.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload s_large|ml1m|tiny]
+
+metric  : BPR train triplets/sec (one triplet = sampled on the device, scored, back-propagated and applied:
+          K1 sampler+count, K2 assign, K3 fused step, K4 duplicate reduce, K5 loss), whole job over all N GPUs.
+workload: s_large = BASELINE configs[4], the configuration the metric is quoted on: 10M users x 2M items, d=128,
+          1e9 interactions (mean history 100, uniform item popularity), B = 2^20 triplets / step / GPU, neg_ratio 4,
+          Adam with tf.train.AdamOptimizer semantics (CRB_ADAM_TF1).  It fits one GPU (about 31 GB).
+value   : device-timed throughput, inputs resident in HBM.   e2e: the same step driven through the C ABI with HOST
+          index buffers (pinned) in and the HOST loss out every step -- the reference's feed_dict / fetch boundary.
+One JSON line on stdout (rank 0).  `--impl reference` times the oracle port of the reference's CPU path."""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: users, items, dim, mean history, batch per GPU, neg_ratio
+    "s_large": dict(users=10_000_000, items=2_000_000, dim=128, mean_hist=100, batch=1 << 20, neg_ratio=4),
+    "ml1m": dict(users=6040, items=3706, dim=64, mean_hist=165, batch=6144, neg_ratio=4),
+    "tiny": dict(users=20000, items=5000, dim=64, mean_hist=30, batch=1 << 14, neg_ratio=4),
+}
+METRIC, UNIT = "bpr_train_triplets_per_sec", "triplets/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------------------------- synthetic data (device)
+def build_history_device(torch, dev, users, items, mean_hist, seed, user_lo=0, user_hi=None):
+    """Per-user sorted unique histories for users [user_lo, user_hi) drawn on the device, chunk by chunk.
+    Returns (pos_user int32 [global ids], pos_item int32, rowptr int64 over ALL `users` rows)."""
+    user_hi = users if user_hi is None else user_hi
+    g = torch.Generator(device=dev).manual_seed(seed)
+    pu, pi, counts = [], [], []
+    chunk = max(1, min(user_hi - user_lo, (1 << 27) // max(1, mean_hist)))
+    for a in range(user_lo, user_hi, chunk):
+        b = min(user_hi, a + chunk)
+        # history length: 1 + Poisson-like (sum of uniforms) around mean_hist, clipped to the catalogue
+        lens = torch.clamp((torch.rand(b - a, device=dev, generator=g) * 2 * (mean_hist - 1)).long() + 1, max=items // 2)
+        tot = int(lens.sum().item())
+        uid = torch.repeat_interleave(torch.arange(a, b, device=dev, dtype=torch.int64), lens)
+        it = torch.randint(0, items, (tot,), device=dev, generator=g, dtype=torch.int64)
+        key = torch.unique(uid * items + it)  # sorted, duplicates dropped
+        del uid, it
+        ku = torch.div(key, items, rounding_mode="floor")
+        pu.append(ku.to(torch.int32))
+        pi.append((key - ku * items).to(torch.int32))
+        counts.append(torch.bincount(ku - a, minlength=b - a))
+        del key, ku
+    cnt = torch.zeros(users, dtype=torch.int64, device=dev)
+    cnt[user_lo:user_hi] = torch.cat(counts)
+    rowptr = torch.zeros(users + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(cnt, 0, out=rowptr[1:])
+    return torch.cat(pu), torch.cat(pi), rowptr
+
+
+# --------------------------------------------------------------------------------------------- reference arm (CPU)
+def cpu_reference_steps(w, n_steps, batch, threads, seed=0):
+    """The reference's CPU path restated (oracle/): Python-loop sampler with np.random (utils/sampler.py:46-74) +
+    one TF-1 graph step per batch in torch-CPU fp32 (BPR.py:31-44, Adam).  Returns seconds per step list."""
+    import torch
+    from oracle import ref_host as H
+    from oracle import tf1_restatement as T
+    torch.set_num_threads(threads)
+    rs = np.random.RandomState(seed)
+    np.random.seed(seed)
+    items, dim, R = w["items"], w["dim"], w["neg_ratio"]
+    n_users = max(8, int(math.ceil(batch / (R * w["mean_hist"]))))  # users whose full epoch is about one batch
+    ui_train = {}
+    for u in range(n_users):
+        n = int(min(items // 2, 1 + rs.randint(0, 2 * (w["mean_hist"] - 1) + 1)))
+        ui_train[u] = np.unique(rs.randint(0, items, n)).tolist()
+
+    class D(object):
+        pass
+    data = D()
+    data.ui_train, data.item_nums, data.user_nums = ui_train, items, n_users
+    g = torch.Generator().manual_seed(seed)
+    params = {"P": torch.randn(n_users, dim, generator=g) * 0.01, "Q": torch.randn(items, dim, generator=g) * 0.01}
+    opt = T.TF1Optimizer("Adam", 1e-3, adam_mode="lazy")  # row-sparse apply: generous to the CPU baseline
+    times, done = [], 0
+    for _ in range(n_steps):
+        t0 = time.perf_counter()
+        out = H.pairwise_ranking_sampler(data, R, batch)
+        n = min(batch, out[1].shape[0])
+        b = {"u": torch.from_numpy(out[1][:n]), "i": torch.from_numpy(out[2][:n]), "j": torch.from_numpy(out[3][:n])}
+        T.bpr_step_rowsparse(params, b, 0.01, opt)
+        times.append(time.perf_counter() - t0)
+        done = n
+    return times, done, n_users
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch = min(w["batch"], 1 << 17)  # bounded sample per step (sampler is ~2e5 triplets/s/core in pure Python)
+    times, done, n_users = cpu_reference_steps(w, args.warmup + args.steps, batch, threads)
+    t = times[args.warmup:]
+    ms = 1000.0 * sum(t) / len(t)
+    value = done / (ms / 1000.0)
+    sample = ("%d triplets/step: reference-algorithm Python sampler (np.random, utils/sampler.py:46-74) over %d synthetic users + "
+              "restated TF-1 BPR/Adam step in torch-CPU fp32 (row-sparse apply), %d-item x d=%d table" % (done, n_users, w["items"], w["dim"]))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "users": w["users"], "items": w["items"], "dim": w["dim"], "batch_per_step": done,
+                       "neg_ratio": w["neg_ratio"], "optimizer": "Adam"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+    from cleverrec_b200.engine import Engine, Optimizer, Table
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = Engine(local)
+    users, items, dim, B, R = w["users"], w["items"], w["dim"], w["batch"], w["neg_ratio"]
+    reg, opt_kind, adam_mode = 0.01, args.optimizer, args.adam_mode
+
+    # ---- data + tables (weak scaling: every rank owns users/world rows of P, its users' histories, and -- round 1 --
+    # a full replica of Q; see DESIGN.md "multi-GPU") ----
+    u_lo, u_hi = (users * rank) // world, (users * (rank + 1)) // world
+    t_setup = time.time()
+    pu, pi, rowptr = build_history_device(torch, dev, users, items, w["mean_hist"], seed=1234 + rank, user_lo=u_lo, user_hi=u_hi)
+    eng.set_history_arrays(users, items, pu, pi, rowptr, pi)
+    n_pos = int(pu.numel())
+    g = torch.Generator(device=dev).manual_seed(0)
+    P = Table(torch.randn(users, dim, device=dev, generator=g) * 0.01, opt_kind, adam_mode)
+    Q = Table(torch.randn(items, dim, device=dev, generator=g) * 0.01, opt_kind, adam_mode)
+    opt = Optimizer(opt_kind, 1e-3, adam_mode=adam_mode)
+    torch.cuda.synchronize()
+    t_setup = time.time() - t_setup
+    rows = eng.epoch_rows(R, "pairwise")
+    steps_total = args.warmup + args.steps
+    assert rows >= B, "workload smaller than one batch"
+    if steps_total * B > rows:
+        raise SystemExit("steps*batch exceeds one epoch of the synthetic workload")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident run: value ----
+    losses = torch.zeros(steps_total, dtype=torch.float64, device=dev)
+    eng.train_epoch_bpr(P, Q, opt, 7, 0, 0, B, args.warmup, R, reg, losses)  # warm-up steps
+    clocks = ClockSampler(local)
+    clocks.start()
+    eng.profile(True)
+    eng.profile_read()
+    l0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    eng.train_epoch_bpr(P, Q, opt, 7, 0, args.warmup * B, B, args.steps, R, reg, losses[args.warmup:])
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    k3_ms, k3_n = eng.profile_read()
+    eng.profile(False)
+    launches = eng.launches - l0
+    clk = clocks.summary()
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total / 1000.0)
+    loss_last = float(losses[-1].item())
+
+    # ---- e2e: host feed in (pinned), host loss out, every step, through the C ABI ----
+    n_e2e = args.steps
+    first = steps_total * B
+    if first + (n_e2e + 1) * B > rows:
+        first = 0
+    feeds = []
+    for k in range(n_e2e + 1):
+        u, i, j = eng.sample_pairwise(7, 0, first + k * B, B, R)
+        feeds.append(tuple(x.cpu().pin_memory() for x in (u, i, j)))
+    eng.train_step_bpr(P, Q, opt, *feeds[n_e2e], reg=reg)  # warm
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(n_e2e):
+        eng.train_step_bpr(P, Q, opt, feeds[k][0], feeds[k][1], feeds[k][2], reg=reg)  # returns the host loss (sync)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * B * n_e2e / e2e_s
+
+    # ---- roofline of the dominant kernel (K3 fused step) ----
+    hbm, tf, which = peaks()
+    per_triplet = {"SGD": 24, "Adagrad": 48, "Adam": 72}[opt_kind] * dim  # algorithmic bytes / triplet
+    k3_avg_ms = k3_ms / max(1, k3_n)
+    achieved = per_triplet * B / (k3_avg_ms / 1000.0) / 1e9 if k3_n else None
+    roofline = {"bound": "hbm", "kernel": "bpr_step_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                "frac": (achieved / hbm) if achieved else None, "traffic": None, "peak_source": which,
+                "algorithmic_bytes_per_launch": per_triplet * B, "kernel_ms": k3_avg_ms, "kernel_share_of_step": k3_avg_ms / ms_step,
+                "step_frac": per_triplet * B / (ms_step / 1000.0) / 1e9 / hbm}
+    traffic_file = os.path.join(ROOT, "profiles", "r01_bpr_step_traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get(args.workload)
+        except Exception:
+            pass
+
+    # ---- secondary metric: full-rank top-20 evaluation users/sec ----
+    ev = None
+    if args.eval_users > 0:
+        eng.adam_flush(P, opt)
+        eng.adam_flush(Q, opt)
+        n_eval = min(args.eval_users, u_hi - u_lo)
+        eu = torch.arange(u_lo, u_lo + n_eval, device=dev, dtype=torch.int32)
+        try:
+            eng.score_topk(0, P.w, Q.w, eu[: min(n_eval, 4096)], 20, exact=args.eval_exact)  # warm
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            eng.score_topk(0, P.w, Q.w, eu, 20, exact=args.eval_exact)
+            e1.record()
+            barrier()
+            ems = e0.elapsed_time(e1)
+            flops = 2.0 * n_eval * items * dim
+            ev = {"metric": "fullrank_top20_eval_users_per_sec", "value": world * n_eval / (ems / 1000.0), "unit": "users/s", "users": n_eval,
+                  "items": items, "ms": ems, "path": "fp32 CUDA cores (exact)" if args.eval_exact else "bf16 tcgen05 + certified fp32 rescoring",
+                  "roofline": {"bound": "tensor", "achieved": flops / (ems / 1000.0) / 1e12, "peak": tf, "unit": "TFLOP/s",
+                               "frac": flops / (ems / 1000.0) / 1e12 / tf}}
+            if not args.eval_exact:
+                ev["stats"] = eng.score_topk_stats()
+        except Exception as e:  # reported, never hidden
+            ev = {"error": str(e)}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        times, done, n_users = cpu_reference_steps(w, 3, min(B, 1 << 17), threads)
+        sec = sum(times[1:]) / len(times[1:])
+        cpu = {"value": done / sec, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d triplets/step x 2 timed steps: reference-algorithm Python sampler (utils/sampler.py:46-74) + restated TF-1 BPR/Adam "
+                         "step (torch-CPU fp32, row-sparse apply), %d users, %d items, d=%d" % (done, n_users, items, dim)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "users": users, "items": items, "dim": dim, "interactions_per_gpu": n_pos, "batch_per_gpu": B,
+                           "neg_ratio": R, "optimizer": opt_kind, "adam_mode": adam_mode if opt_kind == "Adam" else None, "reg": reg,
+                           "l2_policy": "inputs larger than L2 (tables %.1f GB vs 126 MB L2)" % ((users + items) * dim * 4 / 1e9),
+                           "parallelism": "dp%d: user rows + histories sharded, item table replicated" % world, "setup_s": round(t_setup, 1)},
+                "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 8, "steps": n_e2e},
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "eval": ev, "final_loss": loss_last}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("CRB_WORKLOAD", "s_large"), choices=sorted(WORKLOADS))
+    ap.add_argument("--optimizer", default="Adam", choices=["SGD", "Adagrad", "Adam"])
+    ap.add_argument("--adam-mode", dest="adam_mode", default="tf1", choices=["tf1", "lazy"])
+    ap.add_argument("--eval-users", dest="eval_users", type=int, default=32768)
+    ap.add_argument("--eval-exact", dest="eval_exact", action="store_true")
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3  # timing rule: W >= 3
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -19,7 +19,7 @@ EXPORTS = [
     "crb_abi_version", "crb_last_error", "crb_create", "crb_destroy", "crb_set_history", "crb_sample_pairwise",
     "crb_sample_pointwise", "crb_sample_cml", "crb_epoch_rows", "crb_train_step_bpr", "crb_train_epoch_bpr",
     "crb_train_step_pointwise", "crb_adam_flush", "crb_score_pairs", "crb_topk_segments", "crb_score_topk",
-    "crb_score_topk_stats", "crb_launch_count",
+    "crb_score_topk_stats", "crb_launch_count", "crb_profile_enable", "crb_profile_read",
 ]
 
 
@@ -74,6 +74,8 @@ def load():
     lib.crb_score_topk_stats.argtypes = [vp, C.POINTER(C.c_int64 * 4)]
     lib.crb_launch_count.argtypes = [vp]
     lib.crb_launch_count.restype = i64
+    lib.crb_profile_enable.argtypes = [vp, i32]
+    lib.crb_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     _lib = lib
     return lib
 

@@ -79,6 +79,7 @@ extern "C" int crb_destroy(crb_handle* h) {
     cudaFree(h->lrt);
     cudaFree(h->dense_grad);
     cudaFree(h->eval_ws);
+    if (h->prof_ev) { for (int k = 0; k < 2 * CRB_PROF_CAP; ++k) cudaEventDestroy(h->prof_ev[k]); free(h->prof_ev); }
     free(h);
     return CRB_OK;
 }
@@ -170,5 +171,54 @@ int crb_lrt_prepare(crb_handle* h, const crb_opt* opt, cudaStream_t s) {
     h->lrt_lr = opt->lr;
     h->lrt_b1 = opt->beta1;
     h->lrt_b2 = opt->beta2;
+    return CRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ profiling hook
+static int prof_drain(crb_handle* h) {
+    for (int k = 0; k < h->prof_n; ++k) {
+        float ms = 0.f;
+        CRB_CUDA(cudaEventSynchronize(h->prof_ev[2 * k + 1]));
+        CRB_CUDA(cudaEventElapsedTime(&ms, h->prof_ev[2 * k], h->prof_ev[2 * k + 1]));
+        h->prof_ms += (double)ms;
+        h->prof_launches++;
+    }
+    h->prof_n = 0;
+    return CRB_OK;
+}
+
+int crb_prof_begin(crb_handle* h, cudaStream_t s) {
+    if (!h->prof_on) return CRB_OK;
+    if (h->prof_n == CRB_PROF_CAP) { int rc = prof_drain(h); if (rc) return rc; }
+    CRB_CUDA(cudaEventRecord(h->prof_ev[2 * h->prof_n], s));
+    return CRB_OK;
+}
+
+int crb_prof_end(crb_handle* h, cudaStream_t s) {
+    if (!h->prof_on) return CRB_OK;
+    CRB_CUDA(cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], s));
+    h->prof_n++;
+    return CRB_OK;
+}
+
+extern "C" int crb_profile_enable(crb_handle* h, int32_t on) {
+    CRB_CHECK_ARG(h, "null handle");
+    if (on && !h->prof_ev) {
+        h->prof_ev = (cudaEvent_t*)calloc(2 * CRB_PROF_CAP, sizeof(cudaEvent_t));
+        for (int k = 0; k < 2 * CRB_PROF_CAP; ++k) CRB_CUDA(cudaEventCreate(&h->prof_ev[k]));
+    }
+    if (!on && h->prof_on) { int rc = prof_drain(h); if (rc) return rc; }
+    h->prof_on = on ? 1 : 0;
+    return CRB_OK;
+}
+
+extern "C" int crb_profile_read(crb_handle* h, double* step_kernel_ms, int64_t* n_launches) {
+    CRB_CHECK_ARG(h && step_kernel_ms && n_launches, "null argument");
+    int rc = prof_drain(h);
+    if (rc) return rc;
+    *step_kernel_ms = h->prof_ms;
+    *n_launches = h->prof_launches;
+    h->prof_ms = 0.0;
+    h->prof_launches = 0;
     return CRB_OK;
 }

@@ -96,7 +96,16 @@ struct crb_handle {
     int64_t eval_ws_bytes;
     int64_t topk_stats[4];
     int64_t launches;
+    // profiling hook
+    int prof_on;
+    int prof_n;          // event pairs recorded since last read
+    cudaEvent_t* prof_ev; // 2 * CRB_PROF_CAP events
+    double prof_ms;
+    int64_t prof_launches;
 };
+#define CRB_PROF_CAP 1024
+int crb_prof_begin(crb_handle* h, cudaStream_t s);
+int crb_prof_end(crb_handle* h, cudaStream_t s);
 
 static inline bool crb_is_device_ptr(const void* p) {
     if (!p) return false;

@@ -217,6 +217,7 @@ static int sampler_epilogue(crb_handle* h, cudaStream_t s) {
 extern "C" int crb_sample_pairwise(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t first, int64_t count,
                                    int32_t neg_ratio, int32_t* u, int32_t* i, int32_t* j, int32_t* nbr, void* stream) {
     CRB_CHECK_ARG(h, "null handle");
+    if (count == 0) return CRB_OK;
     int rc = check_outputs_device(u, i, j);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
@@ -228,6 +229,7 @@ extern "C" int crb_sample_pairwise(crb_handle* h, uint64_t seed, uint32_t epoch,
 extern "C" int crb_sample_pointwise(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t first, int64_t count,
                                     int32_t neg_ratio, int32_t* u, int32_t* i, float* y, int32_t* nbr, void* stream) {
     CRB_CHECK_ARG(h, "null handle");
+    if (count == 0) return CRB_OK;
     int rc = check_outputs_device(u, i, y);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
@@ -246,6 +248,7 @@ extern "C" int crb_sample_pointwise(crb_handle* h, uint64_t seed, uint32_t epoch
 extern "C" int crb_sample_cml(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t first, int64_t count, int32_t neg_ratio,
                               int32_t* u, int32_t* i, int32_t* neg, void* stream) {
     CRB_CHECK_ARG(h, "null handle");
+    if (count == 0) return CRB_OK;
     int rc = check_outputs_device(u, i, neg);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;

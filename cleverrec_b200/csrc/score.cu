@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(256) fullrank_exact_kernel(const float* __rest
                 else if (sorted_contains(seen_cols, h_lo, h_hi, (int32_t)item)) key = 0ULL;
             }
             // the buffer may overflow inside one sweep of 256 items: compact first when fewer than 256 slots remain
-            __syncthreads();
-            if (s_count > FR_CAP - 256) {
+            // (the vote makes the decision uniform: the last thread to arrive has seen every push of the previous sweep)
+            if (__syncthreads_or(s_count > FR_CAP - 256)) {
                 block_sort_desc<FR_CAP>(buf, s_count);
                 if (threadIdx.x == 0) {
                     if (s_count > K) s_count = K;

@@ -1,8 +1,622 @@
-// placeholder until the tcgen05 path lands (replaced in the next commit)
+// Full-rank scoring on the 5th-generation tensor cores (reference: tf.matmul(u_embed, Q, transpose_b=True) + np.argsort +
+// seen filter, model/ranking/BPR.py:51 and model/RankingRecommender.py:221-240).
+//
+//   prep_*_kernel     fp32 tables -> bf16 operand copies (K padded to 64; bias / -|q|^2 folded in as two extra K columns)
+//   score_tc_kernel   persistent, warp-specialised: warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle), warp 1 = one
+//                     elected thread issuing tcgen05.mma (M=128 x N=128 x K=16, two M halves per CTA = 256 users share every
+//                     item tile), accumulators double-buffered in TMEM (2 x 256 columns), warps 4-11 = epilogue: tcgen05.ld,
+//                     seen items masked with a per-row cursor into the user's sorted history, running per-row threshold,
+//                     candidates appended to a per-row list; the score matrix never reaches HBM.
+//   rescore_kernel    canonical fp32 re-scoring of each user's candidates + certificate: every unlisted item has
+//                     approx <= theta, |approx - canonical| <= eps, so if the K-th canonical score beats theta + eps the
+//                     returned ids are exactly those of the fp32 path.  Uncertified users go to fullrank_exact_kernel.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
 #include "score_common.cuh"
+
+#define TC_C 128          // candidate slots per (user, split)
+#define TC_KEEP 64        // kept by a compaction
+#define TC_BM 256         // users per CTA (2 x UMMA_M=128)
+#define TC_BN 128         // items per tile
+#define TC_THREADS 384    // 4 control warps + 8 epilogue warps
+#define TC_MAX_KB 3       // K blocks of 64 -> d_pad <= 192
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4, LBO (unused
+// for swizzled K-major) = 1, SBO = 1024 B (8 rows x 128 B) >> 4, version = 1 (sm_100), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major, N = 128, M = 128
+#define TC_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24))
+
+// ------------------------------------------------------------------------------------------------ operand preparation
+struct PrepArgs {
+    const float* src;       // fp32 table
+    const float* hvec;      // GMF h / item bias
+    const int32_t* rows;    // row ids to take (users) or NULL for 0..n-1
+    int64_t n, n_pad;
+    int dim, d_pad, kind;
+    __nv_bfloat16* dst;     // [n_pad, d_pad]
+    float* norm;            // users: |p| (or |p.h|);   items: unused
+    float* aux;             // users (SQDIST): sum p^2 in fp32
+    unsigned int* maxbits;  // items: max |q| as float bits; [1]: max |bias|
+};
+
+// one warp per row.  is_user selects the A-operand rules.
+template <bool IS_USER>
+__global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < a.n_pad; r += n_warps) {
+        __nv_bfloat16* out = a.dst + r * a.d_pad;
+        if (r >= a.n) {
+            for (int k = lane; k < a.d_pad; k += 32) out[k] = __float2bfloat16(0.f);
+            continue;
+        }
+        const float* src = a.src + (int64_t)(a.rows ? a.rows[r] : r) * a.dim;
+        float sq = 0.f;
+        for (int k = lane; k < a.dim; k += 32) {
+            float x = src[k];
+            if (IS_USER && a.kind == CRB_SCORE_GMF) x = __fmul_rn(x, a.hvec[k]);
+            sq = fmaf(x, x, sq);
+            if (!IS_USER && a.kind == CRB_SCORE_SQDIST) x = 2.f * x;
+            out[k] = __float2bfloat16(x);
+        }
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        // two augmentation columns carry a per-item fp32 constant as hi + lo bf16 parts (A side holds 1, 1)
+        const bool aug = a.kind == CRB_SCORE_SQDIST || a.kind == CRB_SCORE_DOT_BIAS;
+        for (int k = a.dim + lane; k < a.d_pad; k += 32) {
+            float x = 0.f;
+            if (aug && k < a.dim + 2) {
+                if (IS_USER) {
+                    x = 1.f;
+                } else {
+                    const float c = a.kind == CRB_SCORE_SQDIST ? -sq : a.hvec[r];
+                    const float hi = __bfloat162float(__float2bfloat16(c));
+                    x = (k == a.dim) ? hi : (c - hi);
+                }
+            }
+            out[k] = __float2bfloat16(x);
+        }
+        if (lane == 0) {
+            if (IS_USER) {
+                a.norm[r] = sqrtf(sq);
+                if (a.aux) a.aux[r] = sq;
+            } else {
+                atomicMax(a.maxbits, __float_as_uint(sqrtf(sq)));
+                if (a.kind == CRB_SCORE_DOT_BIAS) atomicMax(a.maxbits + 1, __float_as_uint(fabsf(a.hvec[r])));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ main kernel
+struct TcArgs {
+    int64_t n_users;        // real users in this pass
+    int64_t n_users_pad;    // multiple of TC_BM
+    int64_t n_items;        // real items
+    int n_tiles;            // item tiles (n_items_pad / TC_BN)
+    int n_splits, tiles_per_split;
+    int kb;                 // K blocks of 64
+    int stages;             // smem stages for B
+    const int32_t* users;       // [n_users] row ids (history lookup when hist_users == NULL)
+    const int32_t* hist_users;  // or NULL
+    const int64_t* seen_rowptr;
+    const int32_t* seen_cols;
+    unsigned long long* cand;   // [n_splits, n_users_pad, TC_C]  (approx score bits << 32 | item)
+    int32_t* cand_cnt;          // [n_splits, n_users_pad]
+    float* cand_thr;            // [n_splits, n_users_pad]
+};
+
+__device__ __forceinline__ unsigned long long approx_key(unsigned long long e) {
+    // candidate entry -> ordering key (larger = better approx score, then smaller item id)
+    const uint32_t f = (uint32_t)(e >> 32);
+    const uint32_t ord = (f & 0x80000000u) ? ~f : (f | 0x80000000u);
+    return ((unsigned long long)ord << 32) | (unsigned long long)(~(uint32_t)e);
+}
+
+// Warp-cooperative compaction of one row's candidate list: keep the TC_KEEP best by approximate score, return the new
+// threshold (score of the best dropped entry).  list has n <= TC_C entries; every lane takes 4.
+__device__ __forceinline__ float compact_list(unsigned long long* list, int n, int lane) {
+    unsigned long long e[4], k[4];
+    int rank[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int idx = lane + 32 * t;
+        e[t] = idx < n ? __ldcg(list + idx) : 0ULL;
+        k[t] = idx < n ? approx_key(e[t]) : 0ULL;
+        rank[t] = 0;
+    }
+    for (int j = 0; j < 32; ++j) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const unsigned long long other = __shfl_sync(0xffffffffu, k[t], j);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) rank[s] += (other > k[s]) ? 1 : 0;
+        }
+    }
+    float thr = -INFINITY;
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const bool valid = (lane + 32 * t) < n;
+        if (valid && rank[t] < TC_KEEP) __stcg(list + rank[t], e[t]);
+        const unsigned hit = __ballot_sync(0xffffffffu, valid && rank[t] == TC_KEEP);
+        if (hit) thr = __shfl_sync(0xffffffffu, __uint_as_float((uint32_t)(e[t] >> 32)), __ffs(hit) - 1);
+    }
+    __syncwarp();
+    return thr;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                  const __grid_constant__ CUtensorMap map_b, TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    // 128-byte swizzle atoms need 1024-byte aligned operand tiles: align by hand (the launch reserves the slack)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t a_bytes = 2u * a.kb * 16384u;  // 2 halves x kb boxes of [128 rows x 128 B]
+    const uint32_t b_bytes = (uint32_t)a.kb * 16384u;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + a_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)a.stages * b_bytes);
+    uint64_t* b_full = bars;                 // [stages]
+    uint64_t* b_empty = bars + 4;            // [stages]
+    uint64_t* a_full = bars + 8;
+    uint64_t* a_empty = bars + 9;
+    uint64_t* t_full = bars + 10;            // [2]
+    uint64_t* t_empty = bars + 12;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t m_tiles = a.n_users_pad / TC_BM;
+    const int64_t n_work = m_tiles * a.n_splits;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, a_phase = 0;
+            for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int64_t mt = w / a.n_splits;
+                const int sp = (int)(w % a.n_splits);
+                const int t0 = sp * a.tiles_per_split, t1 = min(a.n_tiles, t0 + a.tiles_per_split);
+                mbar_wait(a_empty, a_phase ^ 1);
+                mbar_expect_tx(a_full, a_bytes);
+                for (int h = 0; h < 2; ++h)
+                    for (int kb = 0; kb < a.kb; ++kb)
+                        tma_load_2d(smem_a + (size_t)(h * a.kb + kb) * 16384, &map_a, kb * 64, (int)(mt * TC_BM + h * 128), a_full);
+                a_phase ^= 1;
+                for (int t = t0; t < t1; ++t) {
+                    mbar_wait(b_empty + stage, phase ^ 1);
+                    mbar_expect_tx(b_full + stage, b_bytes);
+                    for (int kb = 0; kb < a.kb; ++kb)
+                        tma_load_2d(smem_b + (size_t)stage * b_bytes + (size_t)kb * 16384, &map_b, kb * 64, t * TC_BN, b_full + stage);
+                    if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (one elected thread) =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
+            for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int sp = (int)(w % a.n_splits);
+                const int t0 = sp * a.tiles_per_split, t1 = min(a.n_tiles, t0 + a.tiles_per_split);
+                mbar_wait(a_full, a_phase);
+                a_phase ^= 1;
+                for (int t = t0; t < t1; ++t) {
+                    mbar_wait(t_empty + acc, acc_phase ^ 1);   // epilogue has drained this accumulator stage
+                    mbar_wait(b_full + stage, phase);          // TMA bytes have landed
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t b_addr = smem_u32(smem_b + (size_t)stage * b_bytes);
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t d_tmem = tmem_base + acc * 256u + (uint32_t)h * 128u;
+                        for (int kb = 0; kb < a.kb; ++kb) {
+                            const uint32_t a_addr = smem_u32(smem_a + (size_t)(h * a.kb + kb) * 16384);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)  // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzle atom
+                                umma_bf16(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + kb * 16384 + k * 32), TC_IDESC,
+                                          (kb | k) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(b_empty + stage);  // smem stage reusable once these MMAs retire
+                    umma_commit(t_full + acc);     // accumulator ready for the epilogue
+                    if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
+                    if (++acc == 2u) { acc = 0; acc_phase ^= 1; }
+                }
+                umma_commit(a_empty);  // A tile reusable after the last item tile's MMAs
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue: 8 warps, one TMEM lane (= one user) per thread =================
+        const int ew = warp - 4, half = ew >> 2, quad = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4)..+31
+        const int row = half * 128 + quad * 32 + lane;
+        uint32_t acc = 0, acc_phase = 0;
+        for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int64_t mt = w / a.n_splits;
+            const int sp = (int)(w % a.n_splits);
+            const int t0 = sp * a.tiles_per_split, t1 = min(a.n_tiles, t0 + a.tiles_per_split);
+            const int64_t g = mt * TC_BM + row;  // user slot of this thread
+            const bool live = g < a.n_users;
+            unsigned long long* list = a.cand + ((int64_t)sp * a.n_users_pad + g) * TC_C;
+            float theta = -INFINITY;
+            int cnt = 0;
+            // cursor into the user's sorted history: first seen item >= first item of this split
+            int64_t hp = 0, hend = 0;
+            int32_t seen_cur = 0x7fffffff;
+            if (live) {
+                const int32_t hu = a.hist_users ? a.hist_users[g] : a.users[g];
+                if (hu >= 0) {
+                    int64_t lo = a.seen_rowptr[hu], hi = a.seen_rowptr[hu + 1];
+                    hend = hi;
+                    const int32_t first = t0 * TC_BN;
+                    while (lo < hi) {
+                        const int64_t mid = (lo + hi) >> 1;
+                        if (__ldg(a.seen_cols + mid) < first) lo = mid + 1; else hi = mid;
+                    }
+                    hp = lo;
+                    if (hp < hend) seen_cur = __ldg(a.seen_cols + hp);
+                }
+            }
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(t_full + acc, acc_phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (int c = 0; c < TC_BN / 32; ++c) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256u + (uint32_t)half * 128u + (uint32_t)c * 32u, v);
+                    const int32_t c0 = t * TC_BN + c * 32;
+                    if (live) {
+                        // mask seen items (amortised O(|history|) per user) and the padding past the catalogue
+                        while (seen_cur < c0 + 32) {
+                            const int idx = seen_cur - c0;
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) v[k] = (k == idx) ? -INFINITY : v[k];
+                            ++hp;
+                            seen_cur = hp < hend ? __ldg(a.seen_cols + hp) : 0x7fffffff;
+                        }
+                        if ((int64_t)c0 + 32 > a.n_items) {
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) v[k] = ((int64_t)c0 + k >= a.n_items) ? -INFINITY : v[k];
+                        }
+                        float mx = v[0];
+#pragma unroll
+                        for (int k = 1; k + 1 < 32; k += 2) mx = fmaxf(mx, fmaxf(v[k], v[k + 1]));
+                        mx = fmaxf(mx, v[31]);
+                        if (mx > theta) {
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) {
+                                if (v[k] > theta) {
+                                    __stcg(list + cnt, ((unsigned long long)__float_as_uint(v[k]) << 32) | (unsigned long long)(uint32_t)(c0 + k));
+                                    ++cnt;
+                                }
+                            }
+                        }
+                    }
+                    // a list that could overflow in the next chunk is compacted by the whole warp
+                    unsigned need = __ballot_sync(0xffffffffu, cnt > TC_C - 32);
+                    while (need) {
+                        const int src = __ffs(need) - 1;
+                        need &= need - 1;
+                        const int n = __shfl_sync(0xffffffffu, cnt, src);
+                        unsigned long long* lst = a.cand + ((int64_t)sp * a.n_users_pad + (mt * TC_BM + half * 128 + quad * 32 + src)) * TC_C;
+                        const float thr = compact_list(lst, n, lane);
+                        if (lane == src) { theta = fmaxf(theta, thr); cnt = TC_KEEP; }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t_empty + acc);
+                if (++acc == 2u) { acc = 0; acc_phase ^= 1; }
+            }
+            a.cand_cnt[(int64_t)sp * a.n_users_pad + g] = live ? cnt : 0;
+            a.cand_thr[(int64_t)sp * a.n_users_pad + g] = theta;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ certified re-scoring
+struct RescoreArgs {
+    int kind, dim, K, n_splits;
+    int64_t n_users, n_users_pad;
+    const float* P;
+    const float* Q;
+    const float* hvec;
+    const int32_t* users;
+    unsigned long long* cand;
+    const int32_t* cand_cnt;
+    const float* cand_thr;
+    const float* pnorm;
+    const float* psq;
+    const unsigned int* maxbits;
+    float cbound;
+    int32_t* out_items;
+    float* out_scores;
+    int32_t* todo;
+    unsigned int* counters;  // [0] uncertified users, [1] max candidates
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(256) rescore_kernel(RescoreArgs a) {
+    constexpr int ASC = KIND == CRB_SCORE_SQDIST ? 1 : 0;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t g = warp; g < a.n_users; g += n_warps) {
+        const float* p = a.P + (int64_t)a.users[g] * a.dim;
+        float theta = -INFINITY;
+        int total = 0;
+        for (int sp = 0; sp < a.n_splits; ++sp) {
+            const int64_t slot = (int64_t)sp * a.n_users_pad + g;
+            const int n = a.cand_cnt[slot];
+            theta = fmaxf(theta, a.cand_thr[slot]);
+            unsigned long long* list = a.cand + slot * TC_C;
+            for (int k = lane; k < n; k += 32) {  // canonical score, entry rewritten as a ranking key
+                const uint32_t item = (uint32_t)list[k];
+                const float sc = canonical_score<KIND>(p, a.Q + (int64_t)item * a.dim, a.hvec, (int32_t)item, a.dim);
+                list[k] = rank_key(sc, item, ASC);
+            }
+            total += n;
+        }
+        __syncwarp();
+        if (lane == 0) atomicMax(a.counters + 1, (unsigned int)total);
+        // K rounds of arg-best over all splits' lists
+        unsigned long long prev = ~0ULL, kth = 0ULL;
+        for (int r = 0; r < a.K; ++r) {
+            unsigned long long best = 0ULL;
+            for (int sp = 0; sp < a.n_splits; ++sp) {
+                const int64_t slot = (int64_t)sp * a.n_users_pad + g;
+                const int n = a.cand_cnt[slot];
+                const unsigned long long* list = a.cand + slot * TC_C;
+                for (int k = lane; k < n; k += 32) {
+                    const unsigned long long key = list[k];
+                    if (key < prev && key > best) best = key;
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+                best = other > best ? other : best;
+            }
+            if (lane == 0) {
+                a.out_items[g * a.K + r] = best ? (int32_t)key_index(best) : -1;
+                if (a.out_scores) a.out_scores[g * a.K + r] = best ? key_score(best, ASC) : 0.f;
+            }
+            if (best) { prev = best; kth = best; } else { kth = 0ULL; prev = 0ULL; }
+        }
+        // certificate
+        bool ok;
+        if (theta == -INFINITY) {
+            ok = true;  // nothing was ever dropped: every unseen item is in the lists
+        } else if (kth == 0ULL) {
+            ok = false; // fewer than K listed although items were dropped
+        } else {
+            const float qmax = __uint_as_float(a.maxbits[0]);
+            const float ek = key_score(kth, ASC);
+            if (KIND == CRB_SCORE_SQDIST) {
+                const float s = a.pnorm[g] + qmax;
+                const float eps = a.cbound * s * s;
+                ok = ek < (a.psq[g] - theta) - eps;      // unlisted: dist >= |p|^2 - theta - eps
+            } else {
+                float eps = a.cbound * a.pnorm[g] * qmax;
+                if (KIND == CRB_SCORE_DOT_BIAS) eps += a.cbound * __uint_as_float(a.maxbits[1]);
+                ok = ek > theta + eps;                   // unlisted: score <= theta + eps
+            }
+        }
+        if (!ok && lane == 0) a.todo[atomicAdd(a.counters, 1u)] = (int32_t)g;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*encode_fn_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map(CUtensorMap* map, void* base, int64_t rows, int d_pad) {
+    static encode_fn_t encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CRB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { crb_set_error("cuTensorMapEncodeTiled not available"); return CRB_ERR_CUDA; }
+        encode = (encode_fn_t)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)d_pad * 2};
+    const cuuint32_t box[2] = {64, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { crb_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return CRB_ERR_CUDA; }
+    return CRB_OK;
+}
+
+static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
 int crb_score_topk_tc(crb_handle* h, int32_t kind, const float* P, const float* Q, const float* hvec, int64_t n_items, int32_t dim,
                       const int32_t* users, const int32_t* hist_users, int64_t n_users, int32_t K, int32_t* topk_items,
                       float* topk_scores, cudaStream_t s) {
-    crb_set_error("tensor-core scoring not built yet");
-    return CRB_ERR_UNSUPPORTED;
+    CRB_CHECK_ARG(K >= 1 && K <= 32, "tensor-core path supports K <= 32");
+    const bool aug = kind == CRB_SCORE_SQDIST || kind == CRB_SCORE_DOT_BIAS;
+    const int d_pad = (int)round_up(dim + (aug ? 2 : 0), 64);
+    const int kb = d_pad / 64;
+    if (kb > TC_MAX_KB) {
+        // operand tile would not fit in shared memory: this size runs on the exact kernel (documented in DESIGN.md)
+        h->topk_stats[0] = 0; h->topk_stats[1] = n_users; h->topk_stats[2] = 0;
+        return crb_launch_fullrank_exact(h, kind, P, Q, hvec, n_items, dim, users, hist_users, nullptr, n_users, K, topk_items, topk_scores, s);
+    }
+    CRB_CHECK_ARG(n_items < 0x7fffff00LL, "catalogue too large");
+    const int64_t n_items_pad = round_up(n_items, TC_BN);
+    const int n_tiles = (int)(n_items_pad / TC_BN);
+    const int64_t pass_users = n_users < (1 << 20) ? n_users : (1 << 20);
+    const int64_t pass_pad = round_up(pass_users, TC_BM);
+    const int64_t m_tiles_max = pass_pad / TC_BM;
+    int n_splits = 1;
+    if (m_tiles_max < 2 * h->sm_count) {
+        n_splits = (int)((2 * h->sm_count + m_tiles_max - 1) / m_tiles_max);
+        if (n_splits > n_tiles) n_splits = n_tiles;
+        if (n_splits > 64) n_splits = 64;
+    }
+    const int tiles_per_split = (n_tiles + n_splits - 1) / n_splits;
+    n_splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
+    // workspace
+    const int64_t slots = (int64_t)n_splits * pass_pad;
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) { int64_t o = off; off += (bytes + 1023) & ~(int64_t)1023; return o; };
+    const int64_t o_qb = take(n_items_pad * d_pad * 2), o_pb = take(pass_pad * d_pad * 2), o_cand = take(slots * TC_C * 8);
+    const int64_t o_cnt = take(slots * 4), o_thr = take(slots * 4), o_pn = take(pass_pad * 4), o_psq = take(pass_pad * 4);
+    const int64_t o_todo = take(pass_pad * 4), o_misc = take(64);
+    int rc = crb_eval_ws_reserve(h, off + 1024);
+    if (rc) return rc;
+    char* ws = (char*)(((uintptr_t)h->eval_ws + 1023) & ~(uintptr_t)1023);
+    __nv_bfloat16* qb = (__nv_bfloat16*)(ws + o_qb);
+    __nv_bfloat16* pb = (__nv_bfloat16*)(ws + o_pb);
+    unsigned int* misc = (unsigned int*)(ws + o_misc);  // [0..1] max bits, [2] uncertified, [3] max candidates
+    CRB_CUDA(cudaMemsetAsync(misc, 0, 64, s));
+    const int prep_grid = h->sm_count * 8;
+    PrepArgs pq = {Q, hvec, nullptr, n_items, n_items_pad, dim, d_pad, kind, qb, nullptr, nullptr, misc};
+    prep_kernel<false><<<prep_grid, 256, 0, s>>>(pq);
+    h->launches++;
+    CUtensorMap map_b;
+    if ((rc = make_map(&map_b, qb, n_items_pad, d_pad))) return rc;
+    // shared memory plan
+    const size_t a_bytes = (size_t)2 * kb * 16384, b_bytes = (size_t)kb * 16384;
+    int stages = (int)((size_t)(220 * 1024 - a_bytes) / b_bytes);
+    if (stages > 4) stages = 4;
+    if (stages < 2) { crb_set_error("internal: shared memory plan"); return CRB_ERR_UNSUPPORTED; }
+    const size_t smem_bytes = a_bytes + stages * b_bytes + 256 + 1024;
+    CRB_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    const float cbound = 1.0f / 128.0f + (float)d_pad * (1.0f / 4194304.0f);
+    int64_t certified = 0, rerun = 0, maxcand = 0;
+    for (int64_t u0 = 0; u0 < n_users; u0 += pass_users) {
+        const int64_t nu = (n_users - u0) < pass_users ? (n_users - u0) : pass_users;
+        const int64_t nu_pad = round_up(nu, TC_BM);
+        PrepArgs pu = {P, hvec, users + u0, nu, nu_pad, dim, d_pad, kind, pb, (float*)(ws + o_pn), (float*)(ws + o_psq), nullptr};
+        prep_kernel<true><<<prep_grid, 256, 0, s>>>(pu);
+        CUtensorMap map_a;
+        if ((rc = make_map(&map_a, pb, nu_pad, d_pad))) return rc;
+        TcArgs ta;
+        ta.n_users = nu; ta.n_users_pad = nu_pad; ta.n_items = n_items; ta.n_tiles = n_tiles; ta.n_splits = n_splits;
+        ta.tiles_per_split = tiles_per_split; ta.kb = kb; ta.stages = stages; ta.users = users + u0;
+        ta.hist_users = hist_users ? hist_users + u0 : nullptr; ta.seen_rowptr = h->seen_rowptr; ta.seen_cols = h->seen_cols;
+        ta.cand = (unsigned long long*)(ws + o_cand); ta.cand_cnt = (int32_t*)(ws + o_cnt); ta.cand_thr = (float*)(ws + o_thr);
+        const int64_t n_work = (nu_pad / TC_BM) * n_splits;
+        const int grid = (int)(n_work < h->sm_count ? n_work : h->sm_count);
+        score_tc_kernel<<<grid, TC_THREADS, smem_bytes, s>>>(map_a, map_b, ta);
+        CRB_CUDA(cudaGetLastError());
+        CRB_CUDA(cudaMemsetAsync(misc + 2, 0, 8, s));
+        RescoreArgs ra;
+        ra.kind = kind; ra.dim = dim; ra.K = K; ra.n_splits = n_splits; ra.n_users = nu; ra.n_users_pad = nu_pad;
+        ra.P = P; ra.Q = Q; ra.hvec = hvec; ra.users = users + u0; ra.cand = ta.cand; ra.cand_cnt = ta.cand_cnt; ra.cand_thr = ta.cand_thr;
+        ra.pnorm = (const float*)(ws + o_pn); ra.psq = (const float*)(ws + o_psq); ra.maxbits = misc; ra.cbound = cbound;
+        ra.out_items = topk_items + u0 * K; ra.out_scores = topk_scores ? topk_scores + u0 * K : nullptr;
+        ra.todo = (int32_t*)(ws + o_todo); ra.counters = misc + 2;
+        const int rgrid = (int)((nu + 7) / 8 < (int64_t)h->sm_count * 8 ? (nu + 7) / 8 : (int64_t)h->sm_count * 8);
+        switch (kind) {
+            case CRB_SCORE_DOT: rescore_kernel<CRB_SCORE_DOT><<<rgrid, 256, 0, s>>>(ra); break;
+            case CRB_SCORE_GMF: rescore_kernel<CRB_SCORE_GMF><<<rgrid, 256, 0, s>>>(ra); break;
+            case CRB_SCORE_SQDIST: rescore_kernel<CRB_SCORE_SQDIST><<<rgrid, 256, 0, s>>>(ra); break;
+            case CRB_SCORE_DOT_BIAS: rescore_kernel<CRB_SCORE_DOT_BIAS><<<rgrid, 256, 0, s>>>(ra); break;
+            default: crb_set_error("unknown score kind %d", kind); return CRB_ERR_ARG;
+        }
+        h->launches += 3;
+        CRB_CUDA(cudaGetLastError());
+        unsigned int cnts[2] = {0, 0};
+        CRB_CUDA(cudaMemcpyAsync(cnts, misc + 2, 8, cudaMemcpyDeviceToHost, s));
+        CRB_CUDA(cudaStreamSynchronize(s));
+        if (cnts[0]) {
+            // todo holds pass-local user slots: the exact kernel indexes users/outputs of this pass
+            rc = crb_launch_fullrank_exact(h, kind, P, Q, hvec, n_items, dim, users + u0, hist_users ? hist_users + u0 : nullptr,
+                                           (const int32_t*)(ws + o_todo), cnts[0], K, topk_items + u0 * K,
+                                           topk_scores ? topk_scores + u0 * K : nullptr, s);
+            if (rc) return rc;
+        }
+        certified += nu - cnts[0];
+        rerun += cnts[0];
+        if ((int64_t)cnts[1] > maxcand) maxcand = cnts[1];
+    }
+    h->topk_stats[0] = certified; h->topk_stats[1] = rerun; h->topk_stats[2] = maxcand; h->topk_stats[3] = n_splits;
+    return CRB_OK;
 }

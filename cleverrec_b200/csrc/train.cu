@@ -462,8 +462,10 @@ static int bpr_step_device(crb_handle* h, const crb_table* P, const crb_table* Q
     a.rk[0] = h->rank[0]; a.rk[1] = h->rank[1]; a.rk[2] = h->rank[2];
     a.batch = batch; a.dim = P->dim; a.reg = reg; a.opt = od;
     a.dup_grad = h->dup_grad; a.dup_t = h->dup_t; a.block_loss = h->block_loss;
+    if ((rc = crb_prof_begin(h, s))) return rc;
     rc = CRB_DIM_DISPATCH(a.dim, launch_bpr_t, h, a, opt_kind, s);
     if (rc) return rc;
+    if ((rc = crb_prof_end(h, s))) return rc;
     DupArgs d;
     d.tab[0] = a.P; d.tab[1] = a.Q;
     d.meta[0] = h->meta[0]; d.meta[1] = h->meta[1];

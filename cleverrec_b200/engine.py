@@ -85,6 +85,15 @@ class Engine(object):
     def launches(self):
         return int(self.lib.crb_launch_count(self.h))
 
+    def profile(self, on):
+        check(self.lib.crb_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        """-> (milliseconds spent in the fused step kernel, launches) since the last read"""
+        ms, n = C.c_double(), C.c_int64()
+        check(self.lib.crb_profile_read(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     # ------------------------------------------------------------------ history
     def set_history_arrays(self, n_users, n_items, pos_user, pos_item, seen_rowptr, seen_cols):
         """Arrays as produced by history_from_dict (NumPy or torch, host or device)."""

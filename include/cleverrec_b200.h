@@ -166,6 +166,12 @@ int crb_score_topk_stats(crb_handle* h, int64_t stats[4]);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 int64_t crb_launch_count(crb_handle* h);
 
+/* Measurement hook (bench.py's roofline): while enabled, the fused step kernel (K3, the dominant kernel) of every
+ * training step is bracketed by CUDA events on its own stream.  crb_profile_read synchronises, returns the summed
+ * kernel milliseconds and the number of launches since the last read, and resets the accumulators. */
+int crb_profile_enable(crb_handle* h, int32_t on);
+int crb_profile_read(crb_handle* h, double* step_kernel_ms, int64_t* n_launches);
+
 #ifdef __cplusplus
 }
 #endif

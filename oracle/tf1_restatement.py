@@ -283,3 +283,36 @@ def to_torch(d, dtype=torch.float32):
         else:
             out[k] = torch.tensor(a.astype(np.int64))
     return out
+
+
+def bpr_step_rowsparse(params, batch, reg, opt):
+    """BPR step with IndexedSlices-style handling (gradients only for gathered rows, de-duplicated by unique +
+    segment-sum like TF's _deduplicate_indexed_slices) and a row-sparse Adam/Adagrad/SGD apply.  Same maths as
+    train_step(bpr_loss, ...) with adam_mode='lazy' but without materialising dense table gradients -- this is the
+    version bench.py times as the CPU baseline (the generous one for the CPU)."""
+    P, Q = params["P"], params["Q"]
+    u, i, j = batch["u"], batch["i"], batch["j"]
+    ue, ie, je = (t.detach().requires_grad_(True) for t in (P[u], Q[i], Q[j]))
+    x = (ue * ie).sum(1) - (ue * je).sum(1)
+    loss = F.softplus(-x).sum() + reg * (l2_loss(ue) + l2_loss(ie) + l2_loss(je))
+    gu, gi, gj = torch.autograd.grad(loss, [ue, ie, je])
+    opt.t += 1
+    with torch.no_grad():
+        for name, idx, g in (("P", u, gu), ("Q", torch.cat([i, j]), torch.cat([gi, gj]))):
+            rows, inv = torch.unique(idx, return_inverse=True)
+            G = torch.zeros(rows.shape[0], g.shape[1], dtype=g.dtype).index_add_(0, inv, g)
+            var = params[name]
+            if opt.kind == "SGD":
+                var[rows] -= opt.lr * G
+            elif opt.kind == "Adagrad":
+                acc = opt._slot(name + "/acc", var, 0.1)
+                a = acc[rows] + G * G
+                acc[rows] = a
+                var[rows] -= opt.lr * G / torch.sqrt(a)
+            else:
+                m, v = opt._slot(name + "/m", var), opt._slot(name + "/v", var)
+                mr = m[rows] * opt.beta1 + G * (1 - opt.beta1)
+                vr = v[rows] * opt.beta2 + (G * G) * (1 - opt.beta2)
+                m[rows], v[rows] = mr, vr
+                var[rows] -= opt.lr_t() * mr / (torch.sqrt(vr) + opt.eps)
+    return float(loss.detach())

@@ -1,0 +1,80 @@
+"""-m gpu: evaluation kernels against the C oracle (oracle/crb_oracle.c): scores, ranks and top-K ids bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import synthetic_data
+from oracle import c_oracle as O
+from oracle import philox as X
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from cleverrec_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+@pytest.mark.parametrize("d", [7, 16, 64, 128])
+def test_score_pairs_bit_exact(eng, kind, d):
+    rs = np.random.RandomState(d + kind)
+    U, I, n = 50, 70, 5000
+    P, Q = rs.randn(U, d).astype(np.float32), rs.randn(I, d).astype(np.float32)
+    hvec = rs.randn(d if kind == 1 else I).astype(np.float32) if kind in (1, 3) else None
+    u, i = rs.randint(0, U, n), rs.randint(0, I, n)
+    want = O.score_pairs(kind, P, Q, u, i, hvec)
+    Pd, Qd = torch.tensor(P).cuda(), torch.tensor(Q).cuda()
+    hd = torch.tensor(hvec).cuda() if hvec is not None else None
+    got_host = eng.score_pairs(kind, Pd, Qd, u, i, hvec=hd)  # host feed -> host scores (sess.run style)
+    got_dev = eng.score_pairs(kind, Pd, Qd, torch.tensor(u, dtype=torch.int32).cuda(), torch.tensor(i, dtype=torch.int32).cuda(), hvec=hd)
+    assert np.array_equal(got_host.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(got_dev.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("ascending", [False, True])
+def test_topk_segments_with_ties_and_ragged(eng, ascending):
+    rs = np.random.RandomState(1)
+    lens = np.array([100, 1, 0, 1001, 19, 20, 21, 333])
+    offsets = np.concatenate([[0], np.cumsum(lens)])
+    scores = np.round(rs.randn(offsets[-1]) * 4).astype(np.float32) / 4  # heavy ties
+    scores[5] = -0.0
+    want = O.topk_segments(scores, offsets, 20, ascending)
+    got = eng.topk_segments(scores, offsets, 20, ascending)
+    assert np.array_equal(got, want)
+    got_d = eng.topk_segments(torch.tensor(scores).cuda(), offsets, 20, ascending).cpu().numpy()
+    assert np.array_equal(got_d, want)
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+@pytest.mark.parametrize("exact", [True, False])
+def test_fullrank_topk_bit_exact(eng, kind, exact):
+    d = synthetic_data(150, 3000, 60, seed=kind)
+    pu, pi, rp, sc = X.build_history(d.ui_train, d.user_nums)
+    eng.set_history(d.ui_train, d.user_nums, d.item_nums)
+    rs = np.random.RandomState(kind)
+    dim = 64
+    P, Q = (rs.randn(d.user_nums, dim) * 0.1).astype(np.float32), (rs.randn(d.item_nums, dim) * 0.1).astype(np.float32)
+    Q[100] = Q[200]  # exact score ties between two items
+    hvec = (rs.randn(dim if kind == 1 else d.item_nums) * 0.1).astype(np.float32) if kind in (1, 3) else None
+    users = np.arange(d.user_nums, dtype=np.int32)  # includes users with no history (u % 11 == 7)
+    want_i, want_s = O.fullrank_topk(kind, P, Q, users, rp, sc, 20, hvec)
+    Pd, Qd = torch.tensor(P).cuda(), torch.tensor(Q).cuda()
+    hd = torch.tensor(hvec).cuda() if hvec is not None else None
+    got_i, got_s = eng.score_topk(kind, Pd, Qd, users, 20, hvec=hd, exact=exact, return_scores=True)
+    assert np.array_equal(got_i, want_i)
+    assert np.array_equal(got_s.view(np.uint32), want_s.view(np.uint32))
+
+
+def test_fullrank_small_catalogue_pads(eng):
+    ui = {0: [0, 1, 2], 1: [3]}
+    eng.set_history(ui, 3, 8)
+    rs = np.random.RandomState(0)
+    P, Q = rs.randn(3, 16).astype(np.float32), rs.randn(8, 16).astype(np.float32)
+    pu, pi, rp, sc = X.build_history(ui, 3)
+    want, _ = O.fullrank_topk(0, P, Q, np.arange(3), rp, sc, 10)
+    got = eng.score_topk(0, torch.tensor(P).cuda(), torch.tensor(Q).cuda(), np.arange(3, dtype=np.int32), 10, exact=True)
+    assert np.array_equal(got, want) and (got[0, 5:] == -1).all()

@@ -1,0 +1,47 @@
+"""Host-side logic of the mirror package that needs no GPU: metric vectorisation, history flattening, configs."""
+import numpy as np
+
+from conftest import synthetic_data
+from oracle import ref_host as H
+
+
+def test_batch_metrics_bit_identical_to_reference_formula():
+    from cleverrec_b200.utils.metrics import batch_ranking_metrics, cal_ranking_metrics
+    rs = np.random.RandomState(1)
+    for K in (1, 5, 10, 20):
+        real_lists, recs = [], []
+        for _ in range(300):
+            real_lists.append(rs.permutation(50)[:rs.randint(1, 9)].tolist())
+            recs.append(rs.permutation(50)[:20])
+        recs = np.asarray(recs)
+        recs[::7, 15:] = -1  # padded rows (fewer than K candidates)
+        hr, mrr, ndcg = batch_ranking_metrics(real_lists, recs, K)
+        for k in range(len(real_lists)):
+            want = H.cal_ranking_metrics(real_lists[k], recs[k, :K], K)
+            assert (hr[k], mrr[k], ndcg[k]) == want
+            assert cal_ranking_metrics(real_lists[k], recs[k, :K], K) == want
+
+
+def test_history_from_dict_matches_oracle_builder():
+    from cleverrec_b200.engine import history_from_dict
+    from oracle import philox as X
+    d = synthetic_data(60, 150, 12, seed=4)
+    d.ui_train[5] = d.ui_train[5] + d.ui_train[5][:3]  # duplicated interactions (Ciao has them)
+    a = history_from_dict(d.ui_train, d.user_nums)
+    b = X.build_history(d.ui_train, d.user_nums)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_initializers_and_config_parsing():
+    import torch
+    from cleverrec_b200.utils.tools import get_initializer, re_index
+    g = torch.Generator().manual_seed(0)
+    w = get_initializer('normal ', 0.01, g)([2000, 64])  # trailing blank as in conf/BPR.properties:13
+    assert abs(float(w.std()) - 0.01) < 5e-4 and w.dtype == torch.float32
+    x = get_initializer('xavier_uniform', 0.01, g)([100, 28])
+    assert float(x.abs().max()) <= (6.0 / 128) ** 0.5 + 1e-7
+    t = get_initializer('tnormal', 0.5, g)([4000])
+    assert float(t.abs().max()) <= 1.0
+    assert get_initializer('nope', 0.1) is None
+    assert re_index(['b', 'a']) == {'b': 0, 'a': 1}
