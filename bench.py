@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: users, items, dim, mean history, batch per GPU, neg_ratio
     "s_large": dict(users=10_000_000, items=2_000_000, dim=128, mean_hist=100, batch=1 << 20, neg_ratio=4),
+    "medium": dict(users=2_000_000, items=500_000, dim=128, mean_hist=50, batch=1 << 18, neg_ratio=4),  # profiling size (ncu replays)
     "ml1m": dict(users=6040, items=3706, dim=64, mean_hist=165, batch=6144, neg_ratio=4),
     "tiny": dict(users=20000, items=5000, dim=64, mean_hist=30, batch=1 << 14, neg_ratio=4),
 }

@@ -87,17 +87,25 @@ __device__ __forceinline__ void row_load_state(RowRegs<LANES, VPL>& r, const Tab
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         int c = (gl + LANES * v) * 4;
-        if (OptTraits<OPT>::has_s1) r.s1[v] = c < dim ? ld4(T.s1 + row * dim + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+        // padding lanes (c >= dim): Adam m = 0 so a replayed decay step leaves their w at exactly 0; Adagrad acc = 1
+        const float pad1 = OptTraits<OPT>::has_s2 ? 0.f : 1.f;
+        if (OptTraits<OPT>::has_s1) r.s1[v] = c < dim ? ld4(T.s1 + row * dim + c) : make_float4(pad1, pad1, pad1, pad1);
         if (OptTraits<OPT>::has_s2) r.s2[v] = c < dim ? ld4(T.s2 + row * dim + c) : make_float4(1.f, 1.f, 1.f, 1.f);
     }
-    if (OptTraits<OPT>::replay) r.last = T.last[row];
+}
+
+// CRB_ADAM_TF1 bookkeeping.  `last` = step of the row's last update; 0 = never updated, i.e. m = v = 0 (the slots are
+// created as zeros), for which every decay-only step is an exact no-op (w -= lr*0/(0+eps)) and is skipped.
+template <int OPT>
+__device__ __forceinline__ bool replay_pending(int last, const OptDev& o) {
+    return OptTraits<OPT>::replay && last != 0 && last < o.step - 1;
 }
 
 // CRB_ADAM_TF1: apply the decay-only steps last+1 .. step-1 in registers so that r.w is the value the dense TF
 // update would hold before this step.
 template <int LANES, int VPL, int OPT>
 __device__ __forceinline__ void row_replay(RowRegs<LANES, VPL>& r, const OptDev& o, int upto /*exclusive*/) {
-    if (!OptTraits<OPT>::replay) return;
+    if (!OptTraits<OPT>::replay || r.last == 0) return;
     for (int s = r.last + 1; s < upto; ++s) {
         const float lr_s = lrt_at(o, s);
 #pragma unroll

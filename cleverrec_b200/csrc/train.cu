@@ -32,29 +32,57 @@ __global__ void __launch_bounds__(256) count_rows_kernel(RoleArgs a, int64_t bat
 
 __global__ void __launch_bounds__(256) assign_kernel(RoleArgs a, int64_t batch, crb_step_ctr* ctr, crb_dup_row* dup_rows,
                                                      crb_work* work, unsigned int* multi) {
+    // One occurrence of every duplicated row has rank 1: it allocates the row's slot range, work items and partial rows.
+    // The five global counters are bumped once per warp (warp-aggregated), not once per row.
+    const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < batch; t += stride) {
+    const int64_t rounds = (batch + stride - 1) / stride;
+    for (int64_t it = 0; it < rounds; ++it) {
+        const int64_t t = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             if (r >= a.n_roles) continue;
-            if (a.rank[r][t] != 1u) continue;  // exactly one occurrence of every duplicated row has rank 1
-            const int32_t row = a.idx[r][t];
-            unsigned int* m = reinterpret_cast<unsigned int*>(a.meta[r] + row);
-            const uint32_t c = m[0];
-            const uint32_t base = atomicAdd(&ctr->dup_slots, c);
-            m[1] = base;
-            const uint32_t k = atomicAdd(&ctr->dup_rows, 1u);
-            const uint32_t nch = (c + CRB_DUP_CHUNK - 1) / CRB_DUP_CHUNK;
-            const uint32_t wb = atomicAdd(&ctr->work_items, nch);
-            uint32_t pb = 0;
-            if (nch > 1) {
-                pb = atomicAdd(&ctr->partial_slots, nch);
-                multi[atomicAdd(&ctr->multi_rows, 1u)] = k;
+            const bool mine = t < batch && a.rank[r][t] == 1u;
+            const unsigned vote = __ballot_sync(0xffffffffu, mine);
+            if (!vote) continue;
+            int32_t row = 0;
+            uint32_t c = 0, nch = 0;
+            unsigned int* m = nullptr;
+            if (mine) {
+                row = a.idx[r][t];
+                m = reinterpret_cast<unsigned int*>(a.meta[r] + row);
+                c = m[0];
+                nch = (c + CRB_DUP_CHUNK - 1) / CRB_DUP_CHUNK;
             }
-            crb_dup_row d;
-            d.row = row; d.table = a.table[r]; d.base = base; d.cnt = c; d.wbase = wb; d.nchunk = nch; d.pbase = pb; d.pad = 0;
-            dup_rows[k] = d;
-            for (uint32_t q = 0; q < nch; ++q) { crb_work w; w.dup = k; w.chunk = q; work[wb + q] = w; }
+            const uint32_t pch = nch > 1 ? nch : 0u, one = mine ? 1u : 0u, mul = nch > 1 ? 1u : 0u;
+            // inclusive warp scans of (c, 1, nch, pch, mul)
+            uint32_t sc = c, s1 = one, sn = nch, sp = pch, sm = mul;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t tc = __shfl_up_sync(0xffffffffu, sc, o), t1 = __shfl_up_sync(0xffffffffu, s1, o);
+                const uint32_t tn = __shfl_up_sync(0xffffffffu, sn, o), tp = __shfl_up_sync(0xffffffffu, sp, o);
+                const uint32_t tm = __shfl_up_sync(0xffffffffu, sm, o);
+                if (lane >= o) { sc += tc; s1 += t1; sn += tn; sp += tp; sm += tm; }
+            }
+            uint32_t bc = 0, b1 = 0, bn = 0, bp = 0, bm = 0;
+            if (lane == 31) {
+                bc = atomicAdd(&ctr->dup_slots, sc);
+                b1 = atomicAdd(&ctr->dup_rows, s1);
+                bn = atomicAdd(&ctr->work_items, sn);
+                if (sp) bp = atomicAdd(&ctr->partial_slots, sp);
+                if (sm) bm = atomicAdd(&ctr->multi_rows, sm);
+            }
+            bc = __shfl_sync(0xffffffffu, bc, 31); b1 = __shfl_sync(0xffffffffu, b1, 31); bn = __shfl_sync(0xffffffffu, bn, 31);
+            bp = __shfl_sync(0xffffffffu, bp, 31); bm = __shfl_sync(0xffffffffu, bm, 31);
+            if (mine) {
+                const uint32_t base = bc + sc - c, k = b1 + s1 - 1u, wb = bn + sn - nch, pb = bp + sp - pch;
+                m[1] = base;
+                if (nch > 1) multi[bm + sm - 1u] = k;
+                crb_dup_row d;
+                d.row = row; d.table = a.table[r]; d.base = base; d.cnt = c; d.wbase = wb; d.nchunk = nch; d.pbase = pb; d.pad = 0;
+                dup_rows[k] = d;
+                for (uint32_t q = 0; q < nch; ++q) { crb_work w; w.dup = k; w.chunk = q; work[wb + q] = w; }
+            }
         }
     }
 }
@@ -143,6 +171,7 @@ __device__ __forceinline__ void dup_apply(const DupArgs& a, const crb_dup_row& d
     const TableDev& T = a.tab[d.table];
     RowRegs<LANES, VPL> r;
     row_load_w<LANES, VPL>(r, T, d.row, a.dim, gl);
+    r.last = OptTraits<OPT>::replay ? T.last[d.row] : 0;
     row_load_state<LANES, VPL, OPT>(r, T, d.row, a.dim, gl);
     row_replay<LANES, VPL, OPT>(r, a.opt, a.opt.step);
     row_apply_store<LANES, VPL, OPT>(r, acc, T, d.row, a.dim, gl, a.opt);
@@ -346,7 +375,7 @@ __device__ __forceinline__ void emit_row(RowRegs<LANES, VPL>& r, const float4* g
 }
 
 template <int LANES, int VPL, int OPT>
-__global__ void __launch_bounds__(256) bpr_step_kernel(BprArgs a) {
+__global__ void __launch_bounds__(256, 3) bpr_step_kernel(BprArgs a) {
     constexpr int GPW = 32 / LANES;
     const int lane = threadIdx.x & 31;
     const int gl = lane % LANES;
@@ -364,19 +393,22 @@ __global__ void __launch_bounds__(256) bpr_step_kernel(BprArgs a) {
         row_load_w<LANES, VPL>(ru, a.P, u, a.dim, gl);
         row_load_w<LANES, VPL>(ri, a.Q, i, a.dim, gl);
         row_load_w<LANES, VPL>(rj, a.Q, j, a.dim, gl);
-        // optimizer slots are only needed here for rows this group will update in place; CRB_ADAM_TF1 needs them for
-        // every row because the forward must see the replayed (dense-equivalent) value.
-        const bool su = OptTraits<OPT>::replay || (uint32_t)mu == 1u;
-        const bool si = OptTraits<OPT>::replay || (uint32_t)mi == 1u;
-        const bool sj = OptTraits<OPT>::replay || (uint32_t)mj == 1u;
+        // optimizer slots are needed here only for rows this group will update in place, or -- CRB_ADAM_TF1 -- rows with
+        // missed decay steps, because the forward must see the replayed (dense-equivalent) value.
+        ru.last = OptTraits<OPT>::replay ? a.P.last[u] : 0;
+        ri.last = OptTraits<OPT>::replay ? a.Q.last[i] : 0;
+        rj.last = OptTraits<OPT>::replay ? a.Q.last[j] : 0;
+        const bool su = (uint32_t)mu == 1u || replay_pending<OPT>(ru.last, a.opt);
+        const bool si = (uint32_t)mi == 1u || replay_pending<OPT>(ri.last, a.opt);
+        const bool sj = (uint32_t)mj == 1u || replay_pending<OPT>(rj.last, a.opt);
         if (OptTraits<OPT>::has_s1) {
             if (su) row_load_state<LANES, VPL, OPT>(ru, a.P, u, a.dim, gl);
             if (si) row_load_state<LANES, VPL, OPT>(ri, a.Q, i, a.dim, gl);
             if (sj) row_load_state<LANES, VPL, OPT>(rj, a.Q, j, a.dim, gl);
         }
-        row_replay<LANES, VPL, OPT>(ru, a.opt, a.opt.step);
-        row_replay<LANES, VPL, OPT>(ri, a.opt, a.opt.step);
-        row_replay<LANES, VPL, OPT>(rj, a.opt, a.opt.step);
+        if (replay_pending<OPT>(ru.last, a.opt)) row_replay<LANES, VPL, OPT>(ru, a.opt, a.opt.step);
+        if (replay_pending<OPT>(ri.last, a.opt)) row_replay<LANES, VPL, OPT>(ri, a.opt, a.opt.step);
+        if (replay_pending<OPT>(rj.last, a.opt)) row_replay<LANES, VPL, OPT>(rj, a.opt, a.opt.step);
         // forward: x = p_u.(q_i - q_j)  (BPR.py:39-41);  l2 = |p_u|^2 + |q_i|^2 + |q_j|^2 (BPR.py:42-43)
         float x = 0.f, sq = 0.f;
 #pragma unroll
@@ -572,7 +604,7 @@ __global__ void __launch_bounds__(256) adam_flush_kernel(TableDev T, int64_t row
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
         const int64_t row = k / chunks_per_row;
         const int last = T.last[row];
-        if (last >= o.step) continue;
+        if (last == 0 || last >= o.step) continue;  // never updated (m = v = 0: decay steps are exact no-ops) or up to date
         float4 W = ld4(T.w + k * 4), M = ld4(T.s1 + k * 4), V = ld4(T.s2 + k * 4);
         for (int s = last + 1; s <= o.step; ++s) adam_decay4(W, M, V, lrt_at(o, s), o);
         st4(T.w + k * 4, W); st4(T.s1 + k * 4, M); st4(T.s2 + k * 4, V);
@@ -582,7 +614,7 @@ __global__ void __launch_bounds__(256) adam_flush_kernel(TableDev T, int64_t row
 __global__ void __launch_bounds__(256) set_last_kernel(int32_t* last, int64_t rows, int32_t step) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < rows; k += stride)
-        if (last[k] < step) last[k] = step;
+        if (last[k] != 0 && last[k] < step) last[k] = step;
 }
 
 extern "C" int crb_adam_flush(crb_handle* h, const crb_table* T, const crb_opt* opt, void* stream) {
@@ -603,9 +635,232 @@ extern "C" int crb_adam_flush(crb_handle* h, const crb_table* T, const crb_opt* 
     return CRB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ K3: pointwise MF / GMF
+// sess.run([train, loss], {u_idx, i_idx, y}): logit = sum_k p_uk q_ik (MF) or sum_k (p_uk q_ik) h_k (GMF.py:43);
+// loss = get_loss(loss_func, y, logits) + reg*(l2(p_u) + l2(q_i)) (GMF.py:48).  h is a dense variable: its gradient is
+// reduced per block in a fixed order, summed over blocks by dense_apply_kernel, which then applies TF's dense optimizer.
+struct PwArgs {
+    TableDev P, Q;
+    unsigned long long* metaU;
+    unsigned long long* metaI;
+    const int32_t* u;
+    const int32_t* i;
+    const float* y;
+    const uint32_t* rk[2];
+    const float* hvec;     // NULL for MF
+    float* hpart;          // [gridDim.x, dim] per-block partial gradient of h
+    int64_t batch;
+    int dim;
+    int loss_kind;
+    float reg;
+    OptDev opt;
+    float* dup_grad;
+    uint32_t* dup_t;
+    double* block_loss;
+};
+
+template <int LANES, int VPL, int OPT, bool GMF>
+__global__ void __launch_bounds__(256) pointwise_step_kernel(PwArgs a) {
+    constexpr int GPW = 32 / LANES;
+    __shared__ float4 s_h[GMF ? 256 * VPL : 1];
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % LANES;
+    const int sub = lane / LANES;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float4 hreg[VPL], gh[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        const int c = (gl + LANES * v) * 4;
+        hreg[v] = (GMF && c < a.dim) ? ld4(a.hvec + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+        gh[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    double loss_acc = 0.0;
+    for (int64_t base = warp * GPW; base < a.batch; base += n_warps * GPW) {
+        const int64_t t = base + sub;
+        const bool active = t < a.batch;
+        const int64_t tt = active ? t : a.batch - 1;
+        const int32_t u = a.u[tt], i = a.i[tt];
+        const float y = a.y[tt];
+        const unsigned long long mu = a.metaU[u], mi = a.metaI[i];
+        RowRegs<LANES, VPL> ru, ri;
+        row_load_w<LANES, VPL>(ru, a.P, u, a.dim, gl);
+        row_load_w<LANES, VPL>(ri, a.Q, i, a.dim, gl);
+        ru.last = OptTraits<OPT>::replay ? a.P.last[u] : 0;
+        ri.last = OptTraits<OPT>::replay ? a.Q.last[i] : 0;
+        const bool su = (uint32_t)mu == 1u || replay_pending<OPT>(ru.last, a.opt);
+        const bool si = (uint32_t)mi == 1u || replay_pending<OPT>(ri.last, a.opt);
+        if (OptTraits<OPT>::has_s1) {
+            if (su) row_load_state<LANES, VPL, OPT>(ru, a.P, u, a.dim, gl);
+            if (si) row_load_state<LANES, VPL, OPT>(ri, a.Q, i, a.dim, gl);
+        }
+        if (replay_pending<OPT>(ru.last, a.opt)) row_replay<LANES, VPL, OPT>(ru, a.opt, a.opt.step);
+        if (replay_pending<OPT>(ri.last, a.opt)) row_replay<LANES, VPL, OPT>(ri, a.opt, a.opt.step);
+        float x = 0.f, sq = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const float4 p = ru.w[v], q = ri.w[v], hh = hreg[v];
+            const float4 pq = make_float4(p.x * q.x, p.y * q.y, p.z * q.z, p.w * q.w);
+            x += GMF ? dot4(pq, hh) : (pq.x + pq.y + pq.z + pq.w);
+            sq += dot4(p, p) + dot4(q, q);
+        }
+        x = group_sum<LANES>(x);
+        sq = group_sum<LANES>(sq);
+        float g, l;
+        if (a.loss_kind == CRB_LOSS_CROSS_ENTROPY) {  // utils/tools.py:68-69
+            l = fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x)));
+            g = sigmoid_f(x) - y;
+        } else {                                       // 'square', utils/tools.py:74-75
+            l = (y - x) * (y - x);
+            g = 2.f * (x - y);
+        }
+        if (active && gl == 0) loss_acc += (double)(l + a.reg * 0.5f * sq);
+        float4 gu[VPL], gi[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const float4 p = ru.w[v], q = ri.w[v], hh = hreg[v];
+            gu[v] = make_float4(fmaf(g, q.x * hh.x, a.reg * p.x), fmaf(g, q.y * hh.y, a.reg * p.y), fmaf(g, q.z * hh.z, a.reg * p.z),
+                                fmaf(g, q.w * hh.w, a.reg * p.w));
+            gi[v] = make_float4(fmaf(g, p.x * hh.x, a.reg * q.x), fmaf(g, p.y * hh.y, a.reg * q.y), fmaf(g, p.z * hh.z, a.reg * q.z),
+                                fmaf(g, p.w * hh.w, a.reg * q.w));
+            if (GMF && active) {
+                gh[v].x = fmaf(g, p.x * q.x, gh[v].x); gh[v].y = fmaf(g, p.y * q.y, gh[v].y);
+                gh[v].z = fmaf(g, p.z * q.z, gh[v].z); gh[v].w = fmaf(g, p.w * q.w, gh[v].w);
+            }
+        }
+        if (active) {
+            emit_row<LANES, VPL, OPT>(ru, gu, a.P, a.metaU, u, mu, a.rk[0][t], (uint32_t)t, 0u, a.dim, gl, a.opt, a.dup_grad, a.dup_t);
+            emit_row<LANES, VPL, OPT>(ri, gi, a.Q, a.metaI, i, mi, a.rk[1][t], (uint32_t)t, 1u, a.dim, gl, a.opt, a.dup_grad, a.dup_t);
+        }
+    }
+    if (GMF) {
+        // fixed-order block reduction of the h gradient: thread -> smem, then one thread per float4 chunk sums the groups
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) s_h[threadIdx.x * VPL + v] = gh[v];
+        __syncthreads();
+        constexpr int GROUPS = 256 / LANES;
+        for (int c = threadIdx.x; c < LANES * VPL; c += blockDim.x) {
+            const int l = c % LANES, v = c / LANES;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int gI = 0; gI < GROUPS; ++gI) {
+                const float4 t4 = s_h[(gI * LANES + l) * VPL + v];
+                acc.x += t4.x; acc.y += t4.y; acc.z += t4.z; acc.w += t4.w;
+            }
+            const int col = (l + LANES * v) * 4;
+            if (col < a.dim) st4(a.hpart + (int64_t)blockIdx.x * a.dim + col, acc);
+        }
+    }
+    block_loss_store(loss_acc, a.block_loss);
+}
+
+// TF dense apply of a small dense variable (ApplyGradientDescent / ApplyAdagrad / ApplyAdam) whose gradient arrives as
+// per-block partials [n_parts, n]; summed in block order (deterministic).
+__global__ void __launch_bounds__(256) dense_apply_kernel(float* w, float* s1, float* s2, const float* parts, int n_parts, int n,
+                                                         int opt_kind, OptDev o) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        float g = 0.f;
+        for (int p = 0; p < n_parts; ++p) g += parts[(int64_t)p * n + k];
+        float x = w[k];
+        if (opt_kind == OPT_SGD) {
+            x = __fsub_rn(x, __fmul_rn(o.lr, g));
+        } else if (opt_kind == OPT_ADAGRAD) {
+            float acc = __fadd_rn(s1[k], __fmul_rn(g, g));
+            s1[k] = acc;
+            x = __fsub_rn(x, __fdiv_rn(__fmul_rn(o.lr, g), __fsqrt_rn(acc)));
+        } else {  // ApplyAdam: m += (g-m)(1-b1); v += (g*g-v)(1-b2); var -= (m*lr_t)/(sqrt(v)+eps)
+            float m = s1[k], v = s2[k];
+            m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), __fsub_rn(1.f, o.b1)));
+            v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), __fsub_rn(1.f, o.b2)));
+            s1[k] = m; s2[k] = v;
+            x = __fsub_rn(x, __fdiv_rn(__fmul_rn(m, o.lr_t), __fadd_rn(__fsqrt_rn(v), o.eps)));
+        }
+        w[k] = x;
+    }
+}
+
+template <int LANES, int VPL>
+static int launch_pw_t(crb_handle* h, const PwArgs& a, int opt_kind, bool gmf, cudaStream_t s) {
+    const int grid = h->loss_blocks;
+#define CRB_PW_CASE(O)                                                                        \
+    case O:                                                                                   \
+        if (gmf) pointwise_step_kernel<LANES, VPL, O, true><<<grid, 256, 0, s>>>(a);          \
+        else pointwise_step_kernel<LANES, VPL, O, false><<<grid, 256, 0, s>>>(a);             \
+        break;
+    switch (opt_kind) {
+        CRB_PW_CASE(OPT_SGD)
+        CRB_PW_CASE(OPT_ADAGRAD)
+        CRB_PW_CASE(OPT_ADAM_LAZY)
+        CRB_PW_CASE(OPT_ADAM_TF1)
+    }
+#undef CRB_PW_CASE
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}
+
 extern "C" int crb_train_step_pointwise(crb_handle* h, int32_t kind, const crb_table* P, const crb_table* Q, float* hvec, float* h_s1,
                                         float* h_s2, const crb_opt* opt, int32_t loss_kind, const int32_t* u, const int32_t* i,
                                         const float* y, int64_t batch, float reg, double* loss_out, void* stream) {
-    crb_set_error("pointwise step not built yet");
-    return CRB_ERR_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    OptDev od;
+    int opt_kind = 0;
+    int rc = bpr_common_checks(h, P, Q, opt, &od, &opt_kind, batch, 1, s);
+    if (rc) return rc;
+    CRB_CHECK_ARG(u && i && y, "null feed");
+    CRB_CHECK_ARG(kind == CRB_SCORE_DOT || kind == CRB_SCORE_GMF, "kind must be CRB_SCORE_DOT (MF) or CRB_SCORE_GMF");
+    CRB_CHECK_ARG(loss_kind == CRB_LOSS_CROSS_ENTROPY || loss_kind == CRB_LOSS_SQUARE, "pointwise loss must be cross_entropy or square");
+    const bool gmf = kind == CRB_SCORE_GMF;
+    if (gmf) {
+        CRB_CHECK_ARG(hvec && crb_is_device_ptr(hvec), "GMF needs the device vector h");
+        CRB_CHECK_ARG(opt_kind == OPT_SGD || h_s1, "h optimizer slot s1 is NULL");
+        CRB_CHECK_ARG((opt_kind != OPT_ADAM_LAZY && opt_kind != OPT_ADAM_TF1) || h_s2, "h optimizer slot s2 is NULL");
+        const int64_t need = (int64_t)h->loss_blocks * P->dim;
+        if (need > h->cap_dense) {
+            CRB_CUDA(cudaStreamSynchronize(s));
+            cudaFree(h->dense_grad);
+            h->dense_grad = nullptr;
+            CRB_CUDA(cudaMalloc(&h->dense_grad, sizeof(float) * need));
+            h->cap_dense = need;
+        }
+    }
+    const int32_t *du, *di;
+    if ((rc = stage_i32(h, u, 0, batch, &du, s))) return rc;
+    if ((rc = stage_i32(h, i, 1, batch, &di, s))) return rc;
+    const float* dy = y;
+    if (!crb_is_device_ptr(y)) {
+        CRB_CUDA(cudaMemcpyAsync(h->yv, y, sizeof(float) * batch, cudaMemcpyHostToDevice, s));
+        dy = h->yv;
+    }
+    if ((rc = zero_step_counters(h, s))) return rc;
+    const int32_t* idx[3] = {du, di, nullptr};
+    const int role_table[3] = {0, 1, 0};
+    if ((rc = crb_count_rows(h, batch, 2, idx, role_table, s))) return rc;
+    if ((rc = crb_launch_assign(h, batch, 2, idx, role_table, s))) return rc;
+    PwArgs a;
+    a.P = to_dev(P); a.Q = to_dev(Q);
+    a.metaU = h->meta[0]; a.metaI = h->meta[1];
+    a.u = du; a.i = di; a.y = dy;
+    a.rk[0] = h->rank[0]; a.rk[1] = h->rank[1];
+    a.hvec = gmf ? hvec : nullptr; a.hpart = h->dense_grad;
+    a.batch = batch; a.dim = P->dim; a.loss_kind = loss_kind; a.reg = reg; a.opt = od;
+    a.dup_grad = h->dup_grad; a.dup_t = h->dup_t; a.block_loss = h->block_loss;
+    if ((rc = crb_prof_begin(h, s))) return rc;
+    rc = CRB_DIM_DISPATCH(a.dim, launch_pw_t, h, a, opt_kind, gmf, s);
+    if (rc) return rc;
+    if ((rc = crb_prof_end(h, s))) return rc;
+    DupArgs d;
+    d.tab[0] = a.P; d.tab[1] = a.Q;
+    d.meta[0] = h->meta[0]; d.meta[1] = h->meta[1];
+    d.dim = a.dim; d.opt = od;
+    d.dup_rows = h->dup_rows; d.work = h->work; d.multi = h->multi;
+    d.dup_grad = h->dup_grad; d.dup_t = h->dup_t; d.partial = h->partial; d.ctr = h->ctr;
+    if ((rc = crb_launch_dup_pipeline(h, d, opt_kind, s))) return rc;
+    if (gmf) {
+        dense_apply_kernel<<<1, 256, 0, s>>>(hvec, h_s1, h_s2, h->dense_grad, h->loss_blocks, P->dim, opt_kind == OPT_ADAM_TF1 ? OPT_ADAM_LAZY : opt_kind, od);
+        h->launches++;
+        CRB_CUDA(cudaGetLastError());
+    }
+    double* ld = (loss_out && crb_is_device_ptr(loss_out)) ? loss_out : h->loss_dev;
+    if ((rc = crb_launch_loss_final(h, ld, s))) return rc;
+    return finish_loss(h, loss_out, 1, s);
 }

@@ -161,6 +161,22 @@ class Engine(object):
                                            neg_ratio, float(reg), ptr(loss_out), self.stream))
         opt.t += n_steps
 
+    def train_step_pointwise(self, kind, P, Q, opt, u, i, y, reg, loss_kind, hvec=None, h_s1=None, h_s2=None, loss_out=None):
+        """One `sess.run([train, loss], {u_idx, i_idx, y})` of MF (kind SCORE_DOT) / GMF (kind SCORE_GMF, hvec = h_gmf and
+        its optimizer slots, device tensors).  Host or device feeds; returns the loss when loss_out is None."""
+        u, i = self._feed_i32(u), self._feed_i32(i)
+        if not isinstance(y, torch.Tensor):
+            y = np.ascontiguousarray(np.asarray(y), dtype=np.float32)
+        elif y.dtype != torch.float32:
+            y = y.to(torch.float32)
+        opt.t += 1
+        co = opt.c(opt.t)
+        host = np.zeros(1, dtype=np.float64) if loss_out is None else None
+        check(self.lib.crb_train_step_pointwise(self.h, kind, C.byref(P.c), C.byref(Q.c), ptr(hvec), ptr(h_s1), ptr(h_s2), C.byref(co),
+                                                loss_kind, ptr(u), ptr(i), ptr(y), len(u), float(reg),
+                                                ptr(host) if loss_out is None else ptr(loss_out), self.stream))
+        return float(host[0]) if loss_out is None else None
+
     def adam_flush(self, table, opt):
         if opt.kind == "Adam" and opt.adam_mode == "tf1" and opt.t > 0:
             co = opt.c(opt.t)
