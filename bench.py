@@ -329,10 +329,17 @@ def main():
     ap.add_argument("--eval-users", dest="eval_users", type=int, default=32768)
     ap.add_argument("--eval-exact", dest="eval_exact", action="store_true")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--users", type=int, default=0, help="override the workload's user count (experiments)")
+    ap.add_argument("--items", type=int, default=0)
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--dim", type=int, default=0)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rule: W >= 3
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    for k in ("users", "items", "batch", "dim"):
+        if getattr(args, k):
+            w[k] = getattr(args, k)
     if args.impl == "reference":
         run_reference(args, w)
     else:

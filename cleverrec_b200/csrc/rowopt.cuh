@@ -24,6 +24,7 @@ struct OptDev {
     float lr;      // SGD / Adagrad learning rate
     float lr_t;    // Adam: lr * sqrt(1-b2^t)/(1-b1^t) of this step
     float b1, b2, eps;
+    float omb1, omb2;  // 1 - b1, 1 - b2 in fp32
     int32_t step;  // 1-based index of this step
     const float* lrt;  // lr_t table for replay (CRB_ADAM_TF1)
 };
@@ -38,12 +39,23 @@ template <int OPT> struct OptTraits {
 
 __device__ __forceinline__ float lrt_at(const OptDev& o, int s) { return s < CRB_LRT_TABLE ? o.lrt[s] : o.lr; }
 
+// Optimizer arithmetic.  Multiplies/adds are plain IEEE ops without contraction (the op-by-op sequence of TF's kernels);
+// the square root and the division use the SFU approximations (sqrt.approx / rcp.approx, <= 2 ulp), which keeps the step
+// kernel inside the instruction cache (the IEEE expansions made the CRB_ADAM_TF1 variant 4.5k instructions) and is far
+// inside the 1e-4 parity tolerance.  The dense flush, the replay and the touched-row update share these functions, so a
+// replayed row is bit-identical to a densely decayed one.
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // One decay-only Adam step (a row that was not touched at step s under tf.train.AdamOptimizer's sparse apply):
-// m *= b1; v *= b2; w -= lr_s * m / (sqrt(v) + eps).  No contraction: matches the op-by-op TF/torch sequence.
+// m *= b1; v *= b2; w -= lr_s * m / (sqrt(v) + eps).
 __device__ __forceinline__ void adam_decay_elem(float& w, float& m, float& v, float lr_s, float b1, float b2, float eps) {
     m = __fmul_rn(m, b1);
     v = __fmul_rn(v, b2);
-    w = __fsub_rn(w, __fdiv_rn(__fmul_rn(lr_s, m), __fadd_rn(__fsqrt_rn(v), eps)));
+    w = __fsub_rn(w, __fdividef(__fmul_rn(lr_s, m), __fadd_rn(sqrt_approx(v), eps)));
 }
 
 __device__ __forceinline__ void adam_decay4(float4& W, float4& M, float4& V, float lr_s, const OptDev& o) {
@@ -56,13 +68,13 @@ __device__ __forceinline__ void adam_decay4(float4& W, float4& M, float4& V, flo
 // tf.train.AdagradOptimizer sparse apply: acc += g*g; w -= lr * g / sqrt(acc)  (no epsilon, acc starts at 0.1)
 __device__ __forceinline__ void adagrad_elem(float& w, float& acc, float g, float lr) {
     acc = __fadd_rn(acc, __fmul_rn(g, g));
-    w = __fsub_rn(w, __fdiv_rn(__fmul_rn(lr, g), __fsqrt_rn(acc)));
+    w = __fsub_rn(w, __fdividef(__fmul_rn(lr, g), sqrt_approx(acc)));
 }
 
 __device__ __forceinline__ void adam_touch_elem(float& w, float& m, float& v, float g, const OptDev& o) {
-    m = __fadd_rn(__fmul_rn(m, o.b1), __fmul_rn(g, __fsub_rn(1.f, o.b1)));
-    v = __fadd_rn(__fmul_rn(v, o.b2), __fmul_rn(__fmul_rn(g, g), __fsub_rn(1.f, o.b2)));
-    w = __fsub_rn(w, __fdiv_rn(__fmul_rn(o.lr_t, m), __fadd_rn(__fsqrt_rn(v), o.eps)));
+    m = __fadd_rn(__fmul_rn(m, o.b1), __fmul_rn(g, o.omb1));
+    v = __fadd_rn(__fmul_rn(v, o.b2), __fmul_rn(__fmul_rn(g, g), o.omb2));
+    w = __fsub_rn(w, __fdividef(__fmul_rn(o.lr_t, m), __fadd_rn(sqrt_approx(v), o.eps)));
 }
 
 // Per lane-group view of one row: VPL float4 chunks per lane, chunk index c = gl + LANES*v, valid iff 4c < dim.

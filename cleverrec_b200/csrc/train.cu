@@ -269,7 +269,7 @@ __global__ void loss_final_kernel(const double* __restrict__ block_loss, int n, 
 }
 
 int crb_launch_loss_final(crb_handle* h, double* loss_out_dev, cudaStream_t s) {
-    loss_final_kernel<<<1, 32, 0, s>>>(h->block_loss, h->loss_blocks, loss_out_dev);
+    loss_final_kernel<<<1, 32, 0, s>>>(h->block_loss, h->step_grid, loss_out_dev);
     h->launches++;
     CRB_CUDA(cudaGetLastError());
     return CRB_OK;
@@ -297,6 +297,8 @@ int crb_opt_to_dev(crb_handle* h, const crb_opt* opt, OptDev* o, int* opt_kind, 
     o->b1 = (float)opt->beta1;
     o->b2 = (float)opt->beta2;
     o->eps = (float)opt->eps;
+    o->omb1 = 1.f - o->b1;
+    o->omb2 = 1.f - o->b2;
     o->step = (int32_t)opt->step;
     o->lr_t = 0.f;
     o->lrt = h->lrt;
@@ -443,16 +445,36 @@ __global__ void __launch_bounds__(256, 3) bpr_step_kernel(BprArgs a) {
     block_loss_store(loss_acc, a.block_loss);
 }
 
+// Persistent launch: exactly one wave of resident CTAs (SM count x occupancy), each looping over the batch.
+template <typename K>
+static int persistent_grid(crb_handle* h, K kernel, int64_t work_groups, int groups_per_block) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 2; }
+    int64_t grid = (int64_t)h->sm_count * occ;
+    const int64_t need = (work_groups + groups_per_block - 1) / groups_per_block;
+    if (grid > need) grid = need;
+    if (grid > h->loss_blocks) grid = h->loss_blocks;
+    if (grid < 1) grid = 1;
+    h->step_grid = (int)grid;
+    return (int)grid;
+}
+
 template <int LANES, int VPL>
 static int launch_bpr_t(crb_handle* h, const BprArgs& a, int opt_kind, cudaStream_t s) {
-    // grid == loss_blocks so that every block_loss entry is rewritten each step
-    const int grid = h->loss_blocks;
-    switch (opt_kind) {
-        case OPT_SGD: bpr_step_kernel<LANES, VPL, OPT_SGD><<<grid, 256, 0, s>>>(a); break;
-        case OPT_ADAGRAD: bpr_step_kernel<LANES, VPL, OPT_ADAGRAD><<<grid, 256, 0, s>>>(a); break;
-        case OPT_ADAM_LAZY: bpr_step_kernel<LANES, VPL, OPT_ADAM_LAZY><<<grid, 256, 0, s>>>(a); break;
-        case OPT_ADAM_TF1: bpr_step_kernel<LANES, VPL, OPT_ADAM_TF1><<<grid, 256, 0, s>>>(a); break;
+    const int gpb = 256 / LANES;
+#define CRB_BPR_CASE(O)                                                                                    \
+    case O: {                                                                                              \
+        const int grid = persistent_grid(h, bpr_step_kernel<LANES, VPL, O>, a.batch, gpb);                 \
+        bpr_step_kernel<LANES, VPL, O><<<grid, 256, 0, s>>>(a);                                            \
+        break;                                                                                             \
     }
+    switch (opt_kind) {
+        CRB_BPR_CASE(OPT_SGD)
+        CRB_BPR_CASE(OPT_ADAGRAD)
+        CRB_BPR_CASE(OPT_ADAM_LAZY)
+        CRB_BPR_CASE(OPT_ADAM_TF1)
+    }
+#undef CRB_BPR_CASE
     h->launches++;
     CRB_CUDA(cudaGetLastError());
     return CRB_OK;
@@ -769,8 +791,8 @@ __global__ void __launch_bounds__(256) dense_apply_kernel(float* w, float* s1, f
             x = __fsub_rn(x, __fdiv_rn(__fmul_rn(o.lr, g), __fsqrt_rn(acc)));
         } else {  // ApplyAdam: m += (g-m)(1-b1); v += (g*g-v)(1-b2); var -= (m*lr_t)/(sqrt(v)+eps)
             float m = s1[k], v = s2[k];
-            m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), __fsub_rn(1.f, o.b1)));
-            v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), __fsub_rn(1.f, o.b2)));
+            m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), o.omb1));
+            v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), o.omb2));
             s1[k] = m; s2[k] = v;
             x = __fsub_rn(x, __fdiv_rn(__fmul_rn(m, o.lr_t), __fadd_rn(__fsqrt_rn(v), o.eps)));
         }
@@ -780,11 +802,16 @@ __global__ void __launch_bounds__(256) dense_apply_kernel(float* w, float* s1, f
 
 template <int LANES, int VPL>
 static int launch_pw_t(crb_handle* h, const PwArgs& a, int opt_kind, bool gmf, cudaStream_t s) {
-    const int grid = h->loss_blocks;
-#define CRB_PW_CASE(O)                                                                        \
-    case O:                                                                                   \
-        if (gmf) pointwise_step_kernel<LANES, VPL, O, true><<<grid, 256, 0, s>>>(a);          \
-        else pointwise_step_kernel<LANES, VPL, O, false><<<grid, 256, 0, s>>>(a);             \
+    const int gpb = 256 / LANES;
+#define CRB_PW_CASE(O)                                                                                       \
+    case O:                                                                                                  \
+        if (gmf) {                                                                                           \
+            const int grid = persistent_grid(h, pointwise_step_kernel<LANES, VPL, O, true>, a.batch, gpb);   \
+            pointwise_step_kernel<LANES, VPL, O, true><<<grid, 256, 0, s>>>(a);                              \
+        } else {                                                                                             \
+            const int grid = persistent_grid(h, pointwise_step_kernel<LANES, VPL, O, false>, a.batch, gpb);  \
+            pointwise_step_kernel<LANES, VPL, O, false><<<grid, 256, 0, s>>>(a);                             \
+        }                                                                                                    \
         break;
     switch (opt_kind) {
         CRB_PW_CASE(OPT_SGD)
@@ -856,7 +883,7 @@ extern "C" int crb_train_step_pointwise(crb_handle* h, int32_t kind, const crb_t
     d.dup_grad = h->dup_grad; d.dup_t = h->dup_t; d.partial = h->partial; d.ctr = h->ctr;
     if ((rc = crb_launch_dup_pipeline(h, d, opt_kind, s))) return rc;
     if (gmf) {
-        dense_apply_kernel<<<1, 256, 0, s>>>(hvec, h_s1, h_s2, h->dense_grad, h->loss_blocks, P->dim, opt_kind == OPT_ADAM_TF1 ? OPT_ADAM_LAZY : opt_kind, od);
+        dense_apply_kernel<<<1, 256, 0, s>>>(hvec, h_s1, h_s2, h->dense_grad, h->step_grid, P->dim, opt_kind == OPT_ADAM_TF1 ? OPT_ADAM_LAZY : opt_kind, od);
         h->launches++;
         CRB_CUDA(cudaGetLastError());
     }
