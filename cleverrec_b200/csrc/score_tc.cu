@@ -38,10 +38,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"  // sleeps in hardware up to the hint (ns)
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
             : "memory");
     } while (!done);
 }
@@ -167,44 +167,41 @@ struct TcArgs {
     float* cand_thr;            // [n_splits, n_users_pad]
 };
 
-__device__ __forceinline__ unsigned long long approx_key(unsigned long long e) {
-    // candidate entry -> ordering key (larger = better approx score, then smaller item id)
-    const uint32_t f = (uint32_t)(e >> 32);
-    const uint32_t ord = (f & 0x80000000u) ? ~f : (f | 0x80000000u);
-    return ((unsigned long long)ord << 32) | (unsigned long long)(~(uint32_t)e);
-}
+__device__ __forceinline__ uint32_t ord_bits(uint32_t f) { return (f & 0x80000000u) ? ~f : (f | 0x80000000u); }
 
-// Warp-cooperative compaction of one row's candidate list: keep the TC_KEEP best by approximate score, return the new
-// threshold (score of the best dropped entry).  list has n <= TC_C entries; every lane takes 4.
-__device__ __forceinline__ float compact_list(unsigned long long* list, int n, int lane) {
-    unsigned long long e[4], k[4];
-    int rank[4];
+// Warp-cooperative compaction of one row's candidate list (n <= TC_C entries, 4 per lane): T = the TC_KEEP-th largest
+// approximate score, found by a 32-step radix descent on the order-preserving score bits (count via one warp reduction per
+// bit); entries with score > T are kept (<= TC_KEEP-1 of them, packed to the front in lane order), everything <= T is dropped
+// and T becomes the row's threshold.  Returns T; *kept receives the new count.
+__device__ __forceinline__ float compact_list(unsigned long long* list, int n, int lane, int* kept) {
+    unsigned long long e[4];
+    uint32_t o[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const int idx = lane + 32 * t;
         e[t] = idx < n ? __ldcg(list + idx) : 0ULL;
-        k[t] = idx < n ? approx_key(e[t]) : 0ULL;
-        rank[t] = 0;
+        o[t] = idx < n ? ord_bits((uint32_t)(e[t] >> 32)) : 0u;  // 0 is below every real score (ord of a real float is >= 1... NaN aside)
     }
-    for (int j = 0; j < 32; ++j) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const unsigned long long other = __shfl_sync(0xffffffffu, k[t], j);
-#pragma unroll
-            for (int s = 0; s < 4; ++s) rank[s] += (other > k[s]) ? 1 : 0;
-        }
+    uint32_t T = 0;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = T | (1u << bit);
+        const int c = (o[0] >= cand) + (o[1] >= cand) + (o[2] >= cand) + (o[3] >= cand);
+        if (__reduce_add_sync(0xffffffffu, c) >= TC_KEEP) T = cand;
     }
-    float thr = -INFINITY;
     __syncwarp();
+    int base = 0;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-        const bool valid = (lane + 32 * t) < n;
-        if (valid && rank[t] < TC_KEEP) __stcg(list + rank[t], e[t]);
-        const unsigned hit = __ballot_sync(0xffffffffu, valid && rank[t] == TC_KEEP);
-        if (hit) thr = __shfl_sync(0xffffffffu, __uint_as_float((uint32_t)(e[t] >> 32)), __ffs(hit) - 1);
+        const bool keep = o[t] > T;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) __stcg(list + base + __popc(m & ((1u << lane) - 1u)), e[t]);
+        base += __popc(m);
     }
     __syncwarp();
-    return thr;
+    *kept = base;
+    const uint32_t f = (T & 0x80000000u) ? (T & 0x7fffffffu) : ~T;  // inverse of ord_bits
+    return __uint_as_float(f);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_constant__ CUtensorMap map_a,
@@ -356,18 +353,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
 #pragma unroll
                             for (int k = 0; k < 32; ++k) v[k] = ((int64_t)c0 + k >= a.n_items) ? -INFINITY : v[k];
                         }
-                        float mx = v[0];
+                        // 8 group maxima (3-input max) -> row maximum; only groups that beat the threshold are scanned
+                        float gm[8];
 #pragma unroll
-                        for (int k = 1; k + 1 < 32; k += 2) mx = fmaxf(mx, fmaxf(v[k], v[k + 1]));
-                        mx = fmaxf(mx, v[31]);
+                        for (int q = 0; q < 8; ++q) gm[q] = fmaxf(fmaxf(v[4 * q], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3]));
+                        const float mx = fmaxf(fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])), fmaxf(fmaxf(gm[4], gm[5]), fmaxf(gm[6], gm[7])));
                         if (mx > theta) {
+                            unsigned long long* wp = list + cnt;
 #pragma unroll
-                            for (int k = 0; k < 32; ++k) {
-                                if (v[k] > theta) {
-                                    __stcg(list + cnt, ((unsigned long long)__float_as_uint(v[k]) << 32) | (unsigned long long)(uint32_t)(c0 + k));
-                                    ++cnt;
+                            for (int q = 0; q < 8; ++q) {
+                                if (gm[q] > theta) {
+#pragma unroll
+                                    for (int k = 4 * q; k < 4 * q + 4; ++k) {
+                                        if (v[k] > theta) {
+                                            __stcg(wp, ((unsigned long long)__float_as_uint(v[k]) << 32) | (unsigned long long)(uint32_t)(c0 + k));
+                                            ++wp;
+                                        }
+                                    }
                                 }
                             }
+                            cnt = (int)(wp - list);
                         }
                     }
                     // a list that could overflow in the next chunk is compacted by the whole warp
@@ -377,8 +382,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                         need &= need - 1;
                         const int n = __shfl_sync(0xffffffffu, cnt, src);
                         unsigned long long* lst = a.cand + ((int64_t)sp * a.n_users_pad + (mt * TC_BM + half * 128 + quad * 32 + src)) * TC_C;
-                        const float thr = compact_list(lst, n, lane);
-                        if (lane == src) { theta = fmaxf(theta, thr); cnt = TC_KEEP; }
+                        int kept;
+                        const float thr = compact_list(lst, n, lane, &kept);
+                        if (lane == src) { theta = fmaxf(theta, thr); cnt = kept; }
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
