@@ -20,6 +20,7 @@ EXPORTS = [
     "crb_sample_pointwise", "crb_sample_cml", "crb_epoch_rows", "crb_train_step_bpr", "crb_train_epoch_bpr",
     "crb_train_step_pointwise", "crb_adam_flush", "crb_score_pairs", "crb_topk_segments", "crb_score_topk",
     "crb_score_topk_stats", "crb_launch_count", "crb_profile_enable", "crb_profile_read",
+    "crb_train_step_cml", "crb_set_history_lists", "crb_train_step_fism", "crb_fism_user_vectors", "crb_clip_rows",
 ]
 
 
@@ -76,6 +77,12 @@ def load():
     lib.crb_launch_count.restype = i64
     lib.crb_profile_enable.argtypes = [vp, i32]
     lib.crb_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    T, O = C.POINTER(CrbTable), C.POINTER(CrbOpt)
+    lib.crb_train_step_cml.argtypes = [vp, T, T, vp, vp, O, vp, vp, vp, i64, i32, f32, f32, i64, vp, vp]
+    lib.crb_set_history_lists.argtypes = [vp, vp, vp]
+    lib.crb_train_step_fism.argtypes = [vp, T, T, T, vp, vp, vp, O, vp, vp, vp, vp, i64, f32, f32, f32, i64, vp, vp]
+    lib.crb_fism_user_vectors.argtypes = [vp, vp, i32, vp, vp, i64, f32, vp, vp]
+    lib.crb_clip_rows.argtypes = [vp, vp, vp, i64, i32, f32, vp]
     _lib = lib
     return lib
 

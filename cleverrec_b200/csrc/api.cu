@@ -47,6 +47,7 @@ extern "C" int crb_create(int device, crb_handle** out) {
     CRB_CUDA(cudaMalloc(&h->block_loss, sizeof(double) * h->loss_blocks));
     CRB_CUDA(cudaMemset(h->block_loss, 0, sizeof(double) * h->loss_blocks));
     CRB_CUDA(cudaMalloc(&h->lrt, sizeof(float) * CRB_LRT_TABLE));
+    CRB_CUDA(cudaMalloc(&h->dense_loss, sizeof(double) * 4 * h->loss_blocks));
     h->lrt_lr = -1.0;
     *out = h;
     return CRB_OK;
@@ -77,6 +78,7 @@ extern "C" int crb_destroy(crb_handle* h) {
     cudaFree(h->block_loss);
     cudaFree(h->loss_dev);
     cudaFree(h->lrt);
+    cudaFree(h->dense_loss);
     cudaFree(h->dense_grad);
     cudaFree(h->eval_ws);
     if (h->prof_ev) { for (int k = 0; k < 2 * CRB_PROF_CAP; ++k) cudaEventDestroy(h->prof_ev[k]); free(h->prof_ev); }
@@ -101,6 +103,8 @@ extern "C" int crb_set_history(crb_handle* h, int64_t n_users, int64_t n_items, 
     h->pos_item = pos_item;
     h->seen_rowptr = seen_rowptr;
     h->seen_cols = seen_cols;
+    h->list_start = nullptr;
+    h->list_len = nullptr;
     return CRB_OK;
 }
 

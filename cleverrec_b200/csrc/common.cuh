@@ -66,6 +66,9 @@ struct crb_handle {
     const int32_t* pos_item;
     const int64_t* seen_rowptr;
     const int32_t* seen_cols;
+    const int64_t* list_start;  // per-user offset / length of the interaction list inside pos_item (FISM / NAIS)
+    const int32_t* list_len;
+    double* dense_loss;         // [4 * loss_blocks] per-block partials of the dense loss terms
     // per-row batch multiplicity words: low 32 bits = count, high 32 bits = slot base
     unsigned long long* meta[2];
     int64_t meta_rows[2];

@@ -111,6 +111,15 @@ class Engine(object):
 
     def set_history(self, ui_train, n_users, n_items):
         self.set_history_arrays(n_users, n_items, *history_from_dict(ui_train, n_users))
+        # per-user interaction lists (order and duplicates kept) inside pos_item: FISM / NAIS need them
+        users = np.fromiter(ui_train.keys(), dtype=np.int64, count=len(ui_train))
+        lens = np.fromiter((len(v) for v in ui_train.values()), dtype=np.int64, count=len(ui_train))
+        start = np.zeros(n_users, dtype=np.int64)
+        ln = np.zeros(n_users, dtype=np.int32)
+        start[users] = np.concatenate([[0], np.cumsum(lens)[:-1]]) if len(users) else []
+        ln[users] = lens
+        self._lists = (torch.from_numpy(start).to(self.device), torch.from_numpy(ln).to(self.device))
+        check(self.lib.crb_set_history_lists(self.h, ptr(self._lists[0]), ptr(self._lists[1])))
 
     def epoch_rows(self, neg_ratio, kind="pairwise"):
         return int(self.lib.crb_epoch_rows(self.h, neg_ratio, {"pairwise": 0, "pointwise": 1, "cml": 2}[kind]))
@@ -176,6 +185,47 @@ class Engine(object):
                                                 loss_kind, ptr(u), ptr(i), ptr(y), len(u), float(reg),
                                                 ptr(host) if loss_out is None else ptr(loss_out), self.stream))
         return float(host[0]) if loss_out is None else None
+
+    def train_step_cml(self, P, Q, opt, u, i, neg, margin, reg, item_nums, loss_out=None):
+        """One `sess.run([train, loss], {u_idx, i_idx, neg_items})` of CML (dense optimizer apply on both tables)."""
+        u, i = self._feed_i32(u), self._feed_i32(i)
+        neg = neg.to(torch.int32).contiguous() if isinstance(neg, torch.Tensor) else np.ascontiguousarray(np.asarray(neg), dtype=np.int32)
+        for T_ in (P, Q):
+            if getattr(T_, "grad", None) is None:
+                T_.grad = torch.zeros_like(T_.w)
+        opt.t += 1
+        co = opt.c(opt.t)
+        host = np.zeros(1, dtype=np.float64) if loss_out is None else None
+        check(self.lib.crb_train_step_cml(self.h, C.byref(P.c), C.byref(Q.c), ptr(P.grad), ptr(Q.grad), C.byref(co), ptr(u), ptr(i), ptr(neg),
+                                          len(u), neg.shape[1], float(margin), float(reg), int(item_nums),
+                                          ptr(host) if loss_out is None else ptr(loss_out), self.stream))
+        return float(host[0]) if loss_out is None else None
+
+    def train_step_fism(self, P, Q, B, opt, u, i, j, nbr, alpha, reg, reg_bias, conf_batch_size, loss_out=None):
+        """One `sess.run([train, loss], {u_idx, i_idx, j_idx, u_neighbors_num})` of FISM (pairwise)."""
+        u, i, j, nbr = (self._feed_i32(x) for x in (u, i, j, nbr))
+        for T_ in (P, Q, B):
+            if getattr(T_, "grad", None) is None:
+                T_.grad = torch.zeros_like(T_.w)
+        opt.t += 1
+        co = opt.c(opt.t)
+        host = np.zeros(1, dtype=np.float64) if loss_out is None else None
+        check(self.lib.crb_train_step_fism(self.h, C.byref(P.c), C.byref(Q.c), C.byref(B.c), ptr(P.grad), ptr(Q.grad), ptr(B.grad), C.byref(co),
+                                           ptr(u), ptr(i), ptr(j), ptr(nbr), len(u), float(alpha), float(reg), float(reg_bias),
+                                           int(conf_batch_size), ptr(host) if loss_out is None else ptr(loss_out), self.stream))
+        return float(host[0]) if loss_out is None else None
+
+    def fism_user_vectors(self, P, users, nbr, alpha):
+        users = torch.as_tensor(np.asarray(users), dtype=torch.int32).to(self.device) if not isinstance(users, torch.Tensor) else users.to(torch.int32)
+        nbr = torch.as_tensor(np.asarray(nbr), dtype=torch.int32).to(self.device) if not isinstance(nbr, torch.Tensor) else nbr.to(torch.int32)
+        out = torch.empty((users.numel(), P.shape[1]), dtype=torch.float32, device=self.device)
+        check(self.lib.crb_fism_user_vectors(self.h, ptr(P), P.shape[1], ptr(users), ptr(nbr), users.numel(), float(alpha), ptr(out), self.stream))
+        return out
+
+    def clip_rows(self, src, max_norm=1.0):
+        dst = torch.empty_like(src)
+        check(self.lib.crb_clip_rows(self.h, ptr(src), ptr(dst), src.shape[0], src.shape[1], float(max_norm), self.stream))
+        return dst
 
     def adam_flush(self, table, opt):
         if opt.kind == "Adam" and opt.adam_mode == "tf1" and opt.t > 0:

@@ -134,6 +134,34 @@ int crb_train_step_pointwise(crb_handle* h, int32_t kind, const crb_table* P, co
                              const int32_t* u, const int32_t* i, const float* y, int64_t batch,
                              float reg, double* loss_out, void* stream);
 
+/* sess.run([train, loss], {u_idx, i_idx, neg_items}) for model/ranking/CML.py:39-70 (train_model_cml,
+ * RankingRecommender.py:90-100).  The covariance regulariser makes both table gradients dense in the reference, so TF
+ * applies the DENSE optimizer form to every row: gradP/gradQ are caller-owned zeroed [rows, dim] device buffers (left zeroed).
+ * neg: int32 [batch, neg_ratio].  item_nums enters the WARP rank weight (CML.py:52). */
+int crb_train_step_cml(crb_handle* h, const crb_table* P, const crb_table* Q, float* gradP, float* gradQ, const crb_opt* opt,
+                       const int32_t* u, const int32_t* i, const int32_t* neg, int64_t batch, int32_t neg_ratio,
+                       float margin, float reg, int64_t item_nums, double* loss_out, void* stream);
+
+/* Per-user interaction lists inside pos_item (the `items` lists of data.ui_train, order and duplicates kept): what
+ * get_ui_sp_mat (utils/tools.py:90-97) encodes.  DEVICE arrays [n_users], borrowed.  Call after crb_set_history. */
+int crb_set_history_lists(crb_handle* h, const int64_t* list_start, const int32_t* list_len);
+
+/* sess.run([train, loss], {u_idx, i_idx, j_idx, u_neighbors_num}) for model/ranking/FISM.py:40-63 (pairwise).  P, Q are
+ * [(I+1), dim]; B is the bias vector as a crb_table with dim = 1 and rows padded to a multiple of 4.  All three gradients
+ * are dense in the reference (L2 over whole tables, FISM.py:57): gradP/gradQ/gradB as for CML.  conf_batch_size is the
+ * configured batch_size that divides the L2 term (not the fed batch length). */
+int crb_train_step_fism(crb_handle* h, const crb_table* P, const crb_table* Q, const crb_table* B, float* gradP, float* gradQ,
+                        float* gradB, const crb_opt* opt, const int32_t* u, const int32_t* i, const int32_t* j,
+                        const int32_t* nbr, int64_t batch, float alpha, float reg, float reg_bias, int64_t conf_batch_size,
+                        double* loss_out, void* stream);
+
+/* FISM.py:70 `coeff * u_neighbors_embed` for evaluation: out[k] = nbr[k]^-alpha * mean(P[list(users[k])]).  DEVICE buffers. */
+int crb_fism_user_vectors(crb_handle* h, const float* P, int32_t dim, const int32_t* users, const int32_t* nbr, int64_t n,
+                          float alpha, float* out, void* stream);
+
+/* tf.clip_by_norm(rows, max_norm, axes=[1]) (CML.py:72-78): dst may alias src. */
+int crb_clip_rows(crb_handle* h, const float* src, float* dst, int64_t rows, int32_t dim, float max_norm, void* stream);
+
 /* Bring every row of a CRB_ADAM_TF1 table up to `step` (call before reading w: evaluation, checkpoint). */
 int crb_adam_flush(crb_handle* h, const crb_table* T, const crb_opt* opt, void* stream);
 
