@@ -21,6 +21,7 @@ EXPORTS = [
     "crb_train_step_pointwise", "crb_adam_flush", "crb_score_pairs", "crb_topk_segments", "crb_score_topk",
     "crb_score_topk_stats", "crb_launch_count", "crb_profile_enable", "crb_profile_read",
     "crb_train_step_cml", "crb_set_history_lists", "crb_train_step_fism", "crb_fism_user_vectors", "crb_clip_rows",
+    "crb_train_step_neumf", "crb_score_pairs_neumf", "crb_mask_seen",
 ]
 
 
@@ -83,6 +84,9 @@ def load():
     lib.crb_train_step_fism.argtypes = [vp, T, T, T, vp, vp, vp, O, vp, vp, vp, vp, i64, f32, f32, f32, i64, vp, vp]
     lib.crb_fism_user_vectors.argtypes = [vp, vp, i32, vp, vp, i64, f32, vp, vp]
     lib.crb_clip_rows.argtypes = [vp, vp, vp, i64, i32, f32, vp]
+    lib.crb_train_step_neumf.argtypes = [vp, T, T, T, T, vp, vp, vp, vp, vp, vp, vp, i32, O, i32, vp, vp, vp, i64, f32, f32, vp, vp]
+    lib.crb_score_pairs_neumf.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, i64, vp, vp]
+    lib.crb_mask_seen.argtypes = [vp, vp, vp, i64, i64, f32, vp]
     _lib = lib
     return lib
 

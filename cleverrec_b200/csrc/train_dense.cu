@@ -582,3 +582,20 @@ extern "C" int crb_clip_rows(crb_handle* h, const float* src, float* dst, int64_
     CRB_CUDA(cudaGetLastError());
     return CRB_OK;
 }
+
+// shared with train_neumf.cu / train_nais.cu: TF dense optimizer apply of one table from its dense gradient buffer
+int crb_dense_table_apply(crb_handle* h, const crb_table* T, float* grad, int opt_kind, const OptDev& od, float l2, double* loss_part,
+                          int* grid_out, cudaStream_t s) {
+    int rc = check_dense_table(T, grad, opt_kind, "dense table");
+    if (rc) return rc;
+    DenseApplyArgs da;
+    da.dim = T->dim; da.opt_kind = dense_opt_kind(opt_kind); da.opt = od; da.cov = 0.f; da.mean = nullptr; da.mean_sum = nullptr;
+    da.loss_cov = 0.f; da.l2 = l2; da.loss_l2 = l2;
+    da.T = {T->w, T->s1, T->s2, grad, T->rows}; da.loss_part = loss_part;
+    const int g = dgrid(h, T->rows, 8);
+    dense_table_apply_kernel<<<g, 256, 0, s>>>(da);
+    h->launches++;
+    if (grid_out) *grid_out = g;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}

@@ -162,6 +162,23 @@ int crb_fism_user_vectors(crb_handle* h, const float* P, int32_t dim, const int3
 /* tf.clip_by_norm(rows, max_norm, axes=[1]) (CML.py:72-78): dst may alias src. */
 int crb_clip_rows(crb_handle* h, const float* src, float* dst, int64_t rows, int32_t dim, float max_norm, void* stream);
 
+/* sess.run([train, loss], {u_idx, i_idx, y}) for model/ranking/NeuMF.py:58-95.  Tables: GMF pair [.,E], MLP pair [.,L0/2].
+ * `dense` packs the dense variables in this order: for k in layers: W_k [layers[k], layers[k]/2] row-major, b_k; then
+ * h_neumf [E + layers[-1]/2]  (layers[k+1] == layers[k]/2, n_layers <= 4, L0 <= 512).  g* are zeroed dense gradient
+ * buffers of the tables (left zeroed); dense_s1/s2 the optimizer slots of `dense`. */
+int crb_train_step_neumf(crb_handle* h, const crb_table* Pg, const crb_table* Qg, const crb_table* Pm, const crb_table* Qm,
+                         float* gPg, float* gQg, float* gPm, float* gQm, float* dense, float* dense_s1, float* dense_s2,
+                         int32_t n_layers, const crb_opt* opt, int32_t loss_kind, const int32_t* u, const int32_t* i,
+                         const float* y, int64_t batch, float reg1, float reg2, double* loss_out, void* stream);
+
+/* NeuMF._predict (NeuMF.py:97-105) on flattened pairs: the logit (sigmoid is monotone) in canonical order.  DEVICE buffers. */
+int crb_score_pairs_neumf(crb_handle* h, const float* Pg, const float* Qg, const float* Pm, const float* Qm, const float* dense,
+                          int32_t E, int32_t Em, int32_t n_layers, const int32_t* u, const int32_t* i, int64_t n,
+                          float* scores, void* stream);
+
+/* RankingRecommender.py:235-240 as a mask: scores[k, item] = value for every item users[k] has seen.  DEVICE buffers. */
+int crb_mask_seen(crb_handle* h, float* scores, const int32_t* users, int64_t n_users, int64_t n_items, float value, void* stream);
+
 /* Bring every row of a CRB_ADAM_TF1 table up to `step` (call before reading w: evaluation, checkpoint). */
 int crb_adam_flush(crb_handle* h, const crb_table* T, const crb_opt* opt, void* stream);
 

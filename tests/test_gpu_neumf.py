@@ -1,0 +1,69 @@
+"""-m gpu: NeuMF step and scoring (csrc/train_neumf.cu) against the torch restatement of model/ranking/NeuMF.py:58-105."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tf1_restatement as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from cleverrec_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _pack(params, layers, E):
+    parts = []
+    for k in range(len(layers)):
+        parts += [params["W_%d" % k].reshape(-1), params["b_%d" % k].reshape(-1)]
+    parts.append(params["h_neumf"].reshape(-1))
+    return torch.cat(parts)
+
+
+@pytest.mark.parametrize("kind", ["SGD", "Adagrad", "Adam"])
+@pytest.mark.parametrize("layers,E", [([128, 64, 32], 32), ([16, 8], 8)])
+def test_neumf_steps(eng, kind, layers, E):
+    from cleverrec_b200 import _lib
+    from cleverrec_b200.engine import Optimizer, Table
+    U, I = 40, 60
+    g = torch.Generator().manual_seed(len(layers))
+    rnd = lambda *s: torch.randn(*s, generator=g) * 0.2
+    ref = {"P_gmf": rnd(U, E), "Q_gmf": rnd(I, E), "P_mlp": rnd(U, layers[0] // 2), "Q_mlp": rnd(I, layers[0] // 2)}
+    for k, n in enumerate(layers):
+        ref["W_%d" % k], ref["b_%d" % k] = rnd(n, n // 2), rnd(n // 2)
+    ref["h_neumf"] = rnd(E + layers[-1] // 2)
+    lr = 0.02 if kind != "Adam" else 0.005
+    opt, ropt = Optimizer(kind, lr, adam_mode="lazy"), T.TF1Optimizer(kind, lr, adam_mode="tf1")
+    tabs = [Table(ref[n].clone().cuda(), kind, "lazy") for n in ("P_gmf", "Q_gmf", "P_mlp", "Q_mlp")]
+    dense = _pack(ref, layers, E).cuda()
+    s1 = torch.full_like(dense, 0.1) if kind == "Adagrad" else (torch.zeros_like(dense) if kind == "Adam" else None)
+    s2 = torch.zeros_like(dense) if kind == "Adam" else None
+    hp = {"reg1": 1e-2, "reg2": 1e-3, "n_layers": len(layers), "loss_func": "cross_entropy"}
+    rs = np.random.RandomState(1)
+    sparse = {"P_gmf": ["u"], "Q_gmf": ["i"], "P_mlp": ["u"], "Q_mlp": ["i"]}
+    for B in (128, 1, 77):
+        u, i = rs.randint(0, U, B), rs.randint(0, I, B)
+        y = (rs.rand(B) < 0.25).astype(np.float32)
+        got = eng.train_step_neumf(tabs, dense, s1, s2, len(layers), opt, u, i, y, 1e-2, 1e-3, _lib.LOSS_CROSS_ENTROPY)
+        b = {"u": torch.tensor(u), "i": torch.tensor(i), "y": torch.tensor(y)}
+        want = T.train_step(T.neumf_loss, ref, b, hp, ropt, sparse_index=sparse)
+        assert abs(got - want) <= 5e-5 * abs(want), (got, want)
+    rtol, atol = (3e-4, 3e-5) if kind == "Adam" else (3e-5, 2e-6)
+    for t_, name in zip(tabs, ("P_gmf", "Q_gmf", "P_mlp", "Q_mlp")):
+        got, want = t_.w.cpu().numpy(), ref[name].numpy()
+        bad = ~np.isclose(got, want, rtol=rtol, atol=atol)
+        assert bad.sum() <= max(1, 3e-3 * bad.size), (name, int(bad.sum()), float(np.abs(got - want).max()))
+    got, want = dense.cpu().numpy(), _pack(ref, layers, E).numpy()
+    bad = ~np.isclose(got, want, rtol=rtol, atol=atol)
+    assert bad.sum() <= max(1, 3e-3 * bad.size), ("dense", int(bad.sum()), float(np.abs(got - want).max()))
+    # scoring: canonical logits agree with the restatement's logits to fp32 rounding
+    u, i = rs.randint(0, U, 500), rs.randint(0, I, 500)
+    sc = eng.score_pairs_neumf(tabs, dense, len(layers), u, i).cpu().numpy()
+    cur = {n: t_.w.cpu() for t_, n in zip(tabs, ("P_gmf", "Q_gmf", "P_mlp", "Q_mlp"))}
+    cur.update({k: v for k, v in ref.items() if k not in cur})
+    lg, _ = T.neumf_logits({k: v.double() for k, v in cur.items()}, torch.tensor(u), torch.tensor(i), len(layers))
+    np.testing.assert_allclose(sc, lg.numpy(), rtol=2e-4, atol=2e-5)
