@@ -22,6 +22,7 @@ EXPORTS = [
     "crb_score_topk_stats", "crb_launch_count", "crb_profile_enable", "crb_profile_read",
     "crb_train_step_cml", "crb_set_history_lists", "crb_train_step_fism", "crb_fism_user_vectors", "crb_clip_rows",
     "crb_train_step_neumf", "crb_score_pairs_neumf", "crb_mask_seen",
+    "crb_sample_nais", "crb_train_step_nais", "crb_train_epoch_nais", "crb_score_nais",
 ]
 
 
@@ -87,6 +88,10 @@ def load():
     lib.crb_train_step_neumf.argtypes = [vp, T, T, T, T, vp, vp, vp, vp, vp, vp, vp, i32, O, i32, vp, vp, vp, i64, f32, f32, vp, vp]
     lib.crb_score_pairs_neumf.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, i64, vp, vp]
     lib.crb_mask_seen.argtypes = [vp, vp, vp, i64, i64, f32, vp]
+    lib.crb_sample_nais.argtypes = [vp, u64, u32, i64, i32, i32, vp, vp, vp]
+    lib.crb_train_step_nais.argtypes = [vp, T, T, T, vp, vp, vp, vp, vp, vp, i32, O, vp, i32, vp, vp, i32, f32, f32, vp, vp]
+    lib.crb_train_epoch_nais.argtypes = [vp, T, T, T, vp, vp, vp, vp, vp, vp, i32, O, u64, u32, vp, vp, i64, i32, f32, f32, vp, vp]
+    lib.crb_score_nais.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, i32, vp, i32, f32, vp, vp]
     _lib = lib
     return lib
 

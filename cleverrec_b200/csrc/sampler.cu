@@ -131,6 +131,23 @@ __global__ void __launch_bounds__(256) sample_kernel(SamplerArgs a, int64_t firs
     }
 }
 
+// NAIS per-user batch (RankingRecommender.py:64-80): for every positive of the user, in list order: the positive (label 1) then
+// its neg_ratio negatives (label 0).  One thread per positive; same negative stream as the other samplers.
+__global__ void __launch_bounds__(128) sample_nais_kernel(SamplerArgs a, int64_t pos_first, int n_pos_user, int32_t* __restrict__ targets,
+                                                          float* __restrict__ y, crb_step_ctr* ctr) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_pos_user) return;
+    const uint64_t p = (uint64_t)(pos_first + k);
+    const int32_t u = a.pos_user[p];
+    int32_t acc[CRB_MAX_NEG];
+    const bool ok = draw_negatives(p, u, a.neg_ratio, acc, a);
+    const int64_t base = (int64_t)k * (a.neg_ratio + 1);
+    targets[base] = a.pos_item[p];
+    y[base] = 1.f;
+    for (uint32_t q = 0; q < a.neg_ratio; ++q) { targets[base + 1 + q] = ok ? acc[q] : 0; y[base + 1 + q] = 0.f; }
+    if (!ok) atomicAdd(&ctr->sampler_err, 1u);
+}
+
 static void host_perm_keys(uint64_t seed, uint32_t epoch, uint32_t keys[6]) {
     uint32_t a[4], b[4];
     philox4x32_10(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, epoch, (uint32_t)seed, (uint32_t)(seed >> 32), a);
@@ -269,4 +286,26 @@ extern "C" int64_t crb_epoch_rows(crb_handle* h, int32_t neg_ratio, int32_t samp
     if (sampler_kind == 0) return h->n_pos * neg_ratio;
     if (sampler_kind == 1) return h->n_pos * (neg_ratio + 1);
     return h->n_pos;
+}
+
+int crb_launch_sample_nais(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t pos_first, int32_t n_pos_user, int32_t neg_ratio,
+                           int32_t* targets, float* y, cudaStream_t s) {
+    SamplerArgs a;
+    int rc = make_args(h, seed, epoch, neg_ratio, 2, &a);
+    if (rc) return rc;
+    CRB_CHECK_ARG(pos_first >= 0 && n_pos_user >= 1 && pos_first + n_pos_user <= h->n_pos, "positives outside the history");
+    sample_nais_kernel<<<(n_pos_user + 127) / 128, 128, 0, s>>>(a, pos_first, n_pos_user, targets, y, h->ctr);
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}
+
+extern "C" int crb_sample_nais(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t pos_first, int32_t n_pos_user, int32_t neg_ratio,
+                               int32_t* targets, float* y, void* stream) {
+    CRB_CHECK_ARG(h, "null handle");
+    CRB_CHECK_ARG(crb_is_device_ptr(targets) && crb_is_device_ptr(y), "sampler outputs must be device pointers");
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = crb_launch_sample_nais(h, seed, epoch, pos_first, n_pos_user, neg_ratio, targets, y, s);
+    if (rc) return rc;
+    return sampler_epilogue(h, s);
 }

@@ -1,0 +1,104 @@
+# coding: utf-8
+" NAIS: Neural Attentive Item Similarity Model (2018) -- mirror of the reference model/ranking/NAIS_single.py (one user per step). "
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+from .. import RankingRecommender as _rr
+from ...engine import Table
+from ...utils.metrics import cal_ranking_metrics
+
+
+class NAIS_single(_rr.RankingRecommender):
+    def __init__(self, sess, data, configs, logger):
+        super(NAIS_single, self).__init__(sess, data, configs, logger)
+        self.embed_size, self.atten_size, self.reg = int(configs['embed_size']), int(configs['atten_size']), float(configs['reg'])
+        self.beta = float(configs['beta'])  # The smoothing coefficient of Softmax
+        self.atten_type = configs['atten_type']
+        if self.atten_type == 'concat':
+            raise NotImplementedError("atten_type=concat is not built; the shipped conf (atten_type='prod', quoted) takes the product branch")
+        logger.info(' model_params: embed_size=%d, atten_size=%d, atten_type=%s, reg=%s, beta=%s' % (self.embed_size, self.atten_size,
+                    self.atten_type, self.reg, self.beta) + ', ' + self.model_params)
+        # Specify training and testing model (NAIS_single.py:20-21)
+        self.train_model = self.train_model_nais
+        self.test_model_rs, self.test_model_loo = self.test_model_rs_nais, self.test_model_loo_nais
+        users = list(data.ui_train.keys())
+        lens = np.asarray([len(data.ui_train[u]) for u in users], dtype=np.int64)
+        self._list_start = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+        self._list_len = lens.astype(np.int32)
+        self._train_users = users
+
+    def _create_params(self, init=None):
+        """NAIS_single.py:40-57: P, Q [(I+1), d], bias/b/h ~ U(-0.1, 0.1), W [d, atten_size]."""
+        dev, kind, n = self.engine.device, self.optimizer.kind, self.data.item_nums + 1
+        g = self.init_generator
+
+        def get(name, fn):
+            return torch.as_tensor(np.asarray(init[name]), dtype=torch.float32) if init and name in init else fn()
+        unif = lambda *s: torch.rand(*s, generator=g) * 0.2 - 0.1
+        self.P = Table(get('P', lambda: self.initializer([n, self.embed_size])).to(dev).contiguous(), kind, 'lazy')
+        self.Q = Table(get('Q', lambda: self.initializer([n, self.embed_size])).to(dev).contiguous(), kind, 'lazy')
+        b = get('bias', lambda: unif(n))
+        self.B = Table(torch.cat([b, torch.zeros((-n) % 4)]).reshape(-1, 1).to(dev).contiguous(), kind, 'lazy')
+        self.n_bias = n
+        W = get('W', lambda: self.initializer([self.embed_size, self.atten_size]))
+        self.dense = torch.cat([W.reshape(-1), get('b', lambda: unif(self.atten_size)), get('h', lambda: unif(self.atten_size))]).to(dev)
+        self.dense_s1 = torch.full_like(self.dense, 0.1) if kind == 'Adagrad' else (torch.zeros_like(self.dense) if kind == 'Adam' else None)
+        self.dense_s2 = torch.zeros_like(self.dense) if kind == 'Adam' else None
+
+    def build_model(self, init=None):
+        self._create_params(init)
+
+    @property
+    def bias(self):
+        return self.B.w.reshape(-1)[:self.n_bias].contiguous()
+
+    def train_step(self, u_idx, i_idx, y, loss_out=None):
+        """sess.run([train, loss], {u_idx: history, u_nbrs_num, i_idx, i_nums, y})  (NAIS_single.py:82-90)."""
+        return self.engine.train_step_nais(self.P, self.Q, self.B, self.dense, self.dense_s1, self.dense_s2, self.atten_size, self.optimizer,
+                                           u_idx, i_idx, y, self.beta, self.reg, loss_out=loss_out)
+
+    # Form mini-batch by user (RankingRecommender.py:64-87): one optimizer step per user, in data.ui_train order
+    def train_model_nais(self):
+        losses = torch.zeros(len(self._train_users), dtype=torch.float64, device=self.engine.device)
+        self.engine.train_epoch_nais(self.P, self.Q, self.B, self.dense, self.dense_s1, self.dense_s2, self.atten_size, self.optimizer, self.seed,
+                                     self.epoch, self._list_start, self._list_len, self.neg_ratio, self.beta, self.reg, losses)
+        self.epoch += 1
+        return float(losses.sum().item()) / len(self._train_users)
+
+    def _scores(self, u, targets):
+        hist = self.data.ui_train[u] if u in self.data.ui_train else [self.data.item_nums]
+        return self.engine.score_nais(self.P.w, self.Q.w, self.bias, self.dense, self.atten_size, hist, targets, self.beta).cpu().numpy()
+
+    def test_model_loo_nais(self):  # RankingRecommender.py:330-348
+        HR, MRR, NDCG = defaultdict(list), defaultdict(list), defaultdict(list)
+        for u in self.test_users:
+            i_idx = self.data.ui_test[u]
+            pre_scores = self._scores(u, i_idx)
+            args_u = np.argsort(-pre_scores, kind='stable')[:self.topk[-1]]
+            real_items = self.data.ui_test[u][self.neg_samples:]
+            for kid in range(len(self.topk)):
+                rec_items = np.take(self.data.ui_test[u], args_u[:self.topk[kid]])
+                hr_u, mrr_u, ndcg_u = cal_ranking_metrics(real_items, rec_items, self.topk[kid])
+                HR[kid].append(hr_u); MRR[kid].append(mrr_u); NDCG[kid].append(ndcg_u)
+        return HR, MRR, NDCG
+
+    def test_model_rs_nais(self):  # RankingRecommender.py:301-328
+        HR, MRR, NDCG = defaultdict(list), defaultdict(list), defaultdict(list)
+        all_items = torch.arange(self.data.item_nums, dtype=torch.int32, device=self.engine.device)
+        for u in self.test_users:
+            seen_items = set(self.data.ui_train[u]) if u in self.data.ui_train else set()
+            pre_scores = self._scores(u, all_items)  # the reference scores id=item_nums too and drops it
+            args_u = np.argsort(-pre_scores, kind='stable')
+            topk_items = np.zeros(self.topk[-1])
+            count, j = 0, 0
+            while count < self.topk[-1]:
+                if args_u[j] not in seen_items:
+                    topk_items[count] = args_u[j]
+                    count += 1
+                j += 1
+            for kid in range(len(self.topk)):
+                hr_u, mrr_u, ndcg_u = cal_ranking_metrics(self.data.ui_test[u], topk_items[:self.topk[kid]], self.topk[kid])
+                HR[kid].append(hr_u); MRR[kid].append(mrr_u); NDCG[kid].append(ndcg_u)
+        return HR, MRR, NDCG

@@ -179,6 +179,32 @@ int crb_score_pairs_neumf(crb_handle* h, const float* Pg, const float* Qg, const
 /* RankingRecommender.py:235-240 as a mask: scores[k, item] = value for every item users[k] has seen.  DEVICE buffers. */
 int crb_mask_seen(crb_handle* h, float* scores, const int32_t* users, int64_t n_users, int64_t n_items, float value, void* stream);
 
+/* The per-user batch of train_model_nais (RankingRecommender.py:64-80): targets [(1+neg_ratio)*n] = each positive followed by
+ * its negatives, y the labels; the user's positives are pos_item[pos_first .. pos_first+n).  DEVICE outputs. */
+int crb_sample_nais(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t pos_first, int32_t n_pos_user, int32_t neg_ratio,
+                    int32_t* targets, float* y, void* stream);
+
+/* sess.run([train, loss], {u_idx: history, i_idx: targets, y}) for model/ranking/NAIS_single.py:59-90 (product attention;
+ * one step per user).  P, Q [(I+1), dim]; B the item bias as a dim-1 table padded to a multiple of 4 rows; `dense` packs
+ * W [dim, atten_size] row-major, b [atten_size], h [atten_size].  hist / targets / y are DEVICE arrays. */
+int crb_train_step_nais(crb_handle* h, const crb_table* P, const crb_table* Q, const crb_table* B, float* gradP, float* gradQ,
+                        float* gradB, float* dense, float* dense_s1, float* dense_s2, int32_t atten_size, const crb_opt* opt,
+                        const int32_t* hist, int32_t n_hist, const int32_t* targets, const float* y, int32_t n_targets,
+                        float beta, float reg, double* loss_out, void* stream);
+
+/* train_model_nais (RankingRecommender.py:64-87) for n_users users in one call: sampler + one step per user.
+ * list_start / list_len: HOST arrays (offset and length of each user's interaction list inside pos_item, in the order the
+ * reference iterates data.ui_train); loss_out: DEVICE double [n_users]; opt->step = index of the first step. */
+int crb_train_epoch_nais(crb_handle* h, const crb_table* P, const crb_table* Q, const crb_table* B, float* gradP, float* gradQ,
+                         float* gradB, float* dense, float* dense_s1, float* dense_s2, int32_t atten_size, const crb_opt* opt,
+                         uint64_t seed, uint32_t epoch, const int64_t* list_start, const int32_t* list_len, int64_t n_users,
+                         int32_t neg_ratio, float beta, float reg, double* loss_out, void* stream);
+
+/* NAIS_single._predict (NAIS_single.py:92-97) for one user: scores[t] = s_t . q_t + bias_t over `targets`.  DEVICE buffers. */
+int crb_score_nais(crb_handle* h, const float* P, const float* Q, const float* bias, const float* dense, int32_t dim,
+                   int32_t atten_size, const int32_t* hist, int32_t n_hist, const int32_t* targets, int32_t n_targets,
+                   float beta, float* scores, void* stream);
+
 /* Bring every row of a CRB_ADAM_TF1 table up to `step` (call before reading w: evaluation, checkpoint). */
 int crb_adam_flush(crb_handle* h, const crb_table* T, const crb_opt* opt, void* stream);
 
