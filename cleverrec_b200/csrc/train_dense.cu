@@ -463,11 +463,12 @@ extern "C" int crb_train_step_cml(crb_handle* h, const crb_table* P, const crb_t
     const int parts = h->sm_count * 4;                       // column-sum partial blocks per table
     const int grid = dgrid(h, batch, 256 / 32);
     // dense workspace: [neg staging as int32][colsum partials P, Q][mean][mean_sum]
-    const int64_t need = (int64_t)batch * neg_ratio + 2 * (int64_t)parts * dim + dim + 8;
+    const int64_t neg_floats = (((int64_t)batch * neg_ratio + 3) / 4) * 4;   // keeps the float4 views behind it 16-byte aligned
+    const int64_t need = neg_floats + 2 * (int64_t)parts * dim + dim + 8;
     if ((rc = dense_ws(h, need, s))) return rc;
     if ((rc = crb_ws_reserve(h, batch, dim, 4, s))) return rc;
     int32_t* neg_scratch = reinterpret_cast<int32_t*>(h->dense_grad);
-    float* part_p = h->dense_grad + (int64_t)batch * neg_ratio;
+    float* part_p = h->dense_grad + neg_floats;
     float* part_q = part_p + (int64_t)parts * dim;
     float* mean = part_q + (int64_t)parts * dim;
     float* mean_sum = mean + dim;
