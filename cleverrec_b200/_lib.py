@@ -23,6 +23,8 @@ EXPORTS = [
     "crb_train_step_cml", "crb_set_history_lists", "crb_train_step_fism", "crb_fism_user_vectors", "crb_clip_rows",
     "crb_train_step_neumf", "crb_score_pairs_neumf", "crb_mask_seen",
     "crb_sample_nais", "crb_train_step_nais", "crb_train_epoch_nais", "crb_score_nais",
+    "crb_shard_step_compute", "crb_shard_apply_inbox", "crb_shard_inbox_overflow", "crb_malloc", "crb_free", "crb_ipc_export",
+    "crb_ipc_open", "crb_ipc_close",
 ]
 
 
@@ -34,6 +36,15 @@ class CrbTable(C.Structure):
 class CrbOpt(C.Structure):
     _fields_ = [("kind", C.c_int32), ("adam_mode", C.c_int32), ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
                 ("eps", C.c_double), ("step", C.c_int64)]
+
+
+MAX_RANKS = 8
+
+
+class CrbShard(C.Structure):
+    _fields_ = [("n_ranks", C.c_int32), ("rank", C.c_int32), ("inbox_cap", C.c_int64), ("q", CrbTable * MAX_RANKS),
+                ("inbox_grad", C.c_void_p * MAX_RANKS), ("inbox_row", C.c_void_p * MAX_RANKS), ("inbox_key", C.c_void_p * MAX_RANKS),
+                ("inbox_cnt", C.c_void_p * MAX_RANKS)]
 
 
 class CrbError(RuntimeError):
@@ -92,6 +103,15 @@ def load():
     lib.crb_train_step_nais.argtypes = [vp, T, T, T, vp, vp, vp, vp, vp, vp, i32, O, vp, i32, vp, vp, i32, f32, f32, vp, vp]
     lib.crb_train_epoch_nais.argtypes = [vp, T, T, T, vp, vp, vp, vp, vp, vp, i32, O, u64, u32, vp, vp, i64, i32, f32, f32, vp, vp]
     lib.crb_score_nais.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, i32, vp, i32, f32, vp, vp]
+    S = C.POINTER(CrbShard)
+    lib.crb_shard_step_compute.argtypes = [vp, T, S, O, vp, vp, vp, u64, u32, i64, i32, i64, f32, vp, vp]
+    lib.crb_shard_apply_inbox.argtypes = [vp, S, O, vp]
+    lib.crb_shard_inbox_overflow.argtypes = [vp, S, C.POINTER(i32), vp]
+    lib.crb_malloc.argtypes = [vp, i64, C.POINTER(vp)]
+    lib.crb_free.argtypes = [vp, vp]
+    lib.crb_ipc_export.argtypes = [vp, vp, C.c_char_p]
+    lib.crb_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    lib.crb_ipc_close.argtypes = [vp, vp]
     _lib = lib
     return lib
 

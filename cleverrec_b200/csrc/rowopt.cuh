@@ -160,6 +160,40 @@ __device__ __forceinline__ void row_apply_store(RowRegs<LANES, VPL>& r, const fl
     if (OptTraits<OPT>::replay && gl == 0) T.last[row] = o.step;
 }
 
+// one row of the triplet after the forward/backward: in place when it is the batch's only occurrence, else a slot
+template <int LANES, int VPL, int OPT>
+__device__ __forceinline__ void emit_row(RowRegs<LANES, VPL>& r, const float4* g, const TableDev& T, unsigned long long* meta,
+                                         int32_t row, unsigned long long m, uint32_t rank, uint32_t t, uint32_t role, int dim,
+                                         int gl, const OptDev& o, float* dup_grad, uint32_t* dup_t) {
+    const uint32_t cnt = (uint32_t)m;
+    if (cnt == 1u) {
+        row_apply_store<LANES, VPL, OPT>(r, g, T, row, dim, gl, o);
+        if (gl == 0) meta[row] = 0ULL;
+    } else {
+        const uint32_t slot = (uint32_t)(m >> 32) + rank;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            int c = (gl + LANES * v) * 4;
+            if (c < dim) st4(dup_grad + (int64_t)slot * dim + c, g[v]);
+        }
+        if (gl == 0) dup_t[slot] = (t << 2) | role;  // unique, ordered key of the occurrence
+    }
+}
+
+// block-level reduction of the per-thread double loss; result to block_loss[blockIdx.x]
+__device__ __forceinline__ void block_loss_store(double v, double* block_loss) {
+    __shared__ double sm_loss_[8];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) sm_loss_[w] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += sm_loss_[k];
+        block_loss[blockIdx.x] = t;
+    }
+}
+
 // Arguments of the duplicate-row kernels (shared by all row-sparse steps)
 struct DupArgs {
     TableDev tab[2];
@@ -177,8 +211,11 @@ struct DupArgs {
 
 int crb_launch_dup_pipeline(crb_handle* h, const DupArgs& a, int opt_kind, cudaStream_t s);
 int crb_launch_assign(crb_handle* h, int64_t batch, int n_roles, const int32_t* const* idx, const int* role_table,
-                      cudaStream_t s);
-int crb_count_rows(crb_handle* h, int64_t batch, int n_roles, const int32_t* const* idx, const int* role_table, cudaStream_t s);
+                      cudaStream_t s, const unsigned int* n_dev = nullptr);
+int crb_count_rows(crb_handle* h, int64_t batch, int n_roles, const int32_t* const* idx, const int* role_table, cudaStream_t s,
+                   const unsigned int* n_dev = nullptr);
 int crb_opt_to_dev(crb_handle* h, const crb_opt* opt, OptDev* out, int* opt_kind, cudaStream_t s);
 int crb_table_check(const crb_table* T, int opt_kind, const char* name);
 int crb_launch_loss_final(crb_handle* h, double* loss_out_dev, cudaStream_t s);
+TableDev crb_to_dev(const crb_table* T);
+int crb_zero_step_counters(crb_handle* h, cudaStream_t s);

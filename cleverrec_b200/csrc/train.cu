@@ -19,9 +19,11 @@ struct RoleArgs {
     unsigned long long* meta[3];  // meta table of each role
     int table[3];
     int n_roles;
+    const unsigned int* n_dev;   // optional device-side element count (inbox): effective batch = min(batch, *n_dev)
 };
 
 __global__ void __launch_bounds__(256) count_rows_kernel(RoleArgs a, int64_t batch) {
+    if (a.n_dev && (int64_t)*a.n_dev < batch) batch = (int64_t)*a.n_dev;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < batch; t += stride) {
 #pragma unroll
@@ -34,6 +36,7 @@ __global__ void __launch_bounds__(256) assign_kernel(RoleArgs a, int64_t batch, 
                                                      crb_work* work, unsigned int* multi) {
     // One occurrence of every duplicated row has rank 1: it allocates the row's slot range, work items and partial rows.
     // The five global counters are bumped once per warp (warp-aggregated), not once per row.
+    if (a.n_dev && (int64_t)*a.n_dev < batch) batch = (int64_t)*a.n_dev;
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t rounds = (batch + stride - 1) / stride;
@@ -95,9 +98,11 @@ static int flat_grid(crb_handle* h, int64_t n, int per_block) {
     return (int)b;
 }
 
-int crb_count_rows(crb_handle* h, int64_t batch, int n_roles, const int32_t* const* idx, const int* role_table, cudaStream_t s) {
+int crb_count_rows(crb_handle* h, int64_t batch, int n_roles, const int32_t* const* idx, const int* role_table, cudaStream_t s,
+                   const unsigned int* n_dev) {
     RoleArgs a;
     a.n_roles = n_roles;
+    a.n_dev = n_dev;
     for (int r = 0; r < 3; ++r) {
         a.idx[r] = r < n_roles ? idx[r] : nullptr;
         a.rank[r] = h->rank[r];
@@ -110,9 +115,11 @@ int crb_count_rows(crb_handle* h, int64_t batch, int n_roles, const int32_t* con
     return CRB_OK;
 }
 
-int crb_launch_assign(crb_handle* h, int64_t batch, int n_roles, const int32_t* const* idx, const int* role_table, cudaStream_t s) {
+int crb_launch_assign(crb_handle* h, int64_t batch, int n_roles, const int32_t* const* idx, const int* role_table, cudaStream_t s,
+                      const unsigned int* n_dev) {
     RoleArgs a;
     a.n_roles = n_roles;
+    a.n_dev = n_dev;
     for (int r = 0; r < 3; ++r) {
         a.idx[r] = r < n_roles ? idx[r] : nullptr;
         a.rank[r] = h->rank[r];
@@ -276,7 +283,7 @@ int crb_launch_loss_final(crb_handle* h, double* loss_out_dev, cudaStream_t s) {
 }
 
 // block-level reduction of the per-thread double loss; result to block_loss[blockIdx.x]
-__device__ __forceinline__ void block_loss_store(double v, double* block_loss) {
+__device__ __forceinline__ void block_loss_store_(double v, double* block_loss) {
     __shared__ double sm[8];
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     const int w = threadIdx.x >> 5;
@@ -332,7 +339,7 @@ int crb_table_check(const crb_table* T, int opt_kind, const char* name) {
     return CRB_OK;
 }
 
-static TableDev to_dev(const crb_table* T) {
+TableDev crb_to_dev(const crb_table* T) {
     TableDev d;
     d.w = T->w; d.s1 = T->s1; d.s2 = T->s2; d.last = T->last;
     return d;
@@ -355,26 +362,6 @@ struct BprArgs {
     uint32_t* dup_t;
     double* block_loss;
 };
-
-// one row of the triplet after the forward/backward: in place when it is the batch's only occurrence, else a slot
-template <int LANES, int VPL, int OPT>
-__device__ __forceinline__ void emit_row(RowRegs<LANES, VPL>& r, const float4* g, const TableDev& T, unsigned long long* meta,
-                                         int32_t row, unsigned long long m, uint32_t rank, uint32_t t, uint32_t role, int dim,
-                                         int gl, const OptDev& o, float* dup_grad, uint32_t* dup_t) {
-    const uint32_t cnt = (uint32_t)m;
-    if (cnt == 1u) {
-        row_apply_store<LANES, VPL, OPT>(r, g, T, row, dim, gl, o);
-        if (gl == 0) meta[row] = 0ULL;
-    } else {
-        const uint32_t slot = (uint32_t)(m >> 32) + rank;
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-            int c = (gl + LANES * v) * 4;
-            if (c < dim) st4(dup_grad + (int64_t)slot * dim + c, g[v]);
-        }
-        if (gl == 0) dup_t[slot] = (t << 2) | role;  // unique, ordered key of the occurrence
-    }
-}
 
 template <int LANES, int VPL, int OPT>
 __global__ void __launch_bounds__(256, 3) bpr_step_kernel(BprArgs a) {
@@ -510,7 +497,7 @@ static int bpr_step_device(crb_handle* h, const crb_table* P, const crb_table* Q
     rc = crb_launch_assign(h, batch, 3, idx, role_table, s);
     if (rc) return rc;
     BprArgs a;
-    a.P = to_dev(P); a.Q = to_dev(Q);
+    a.P = crb_to_dev(P); a.Q = crb_to_dev(Q);
     a.metaU = h->meta[0]; a.metaI = h->meta[1];
     a.u = u; a.i = i; a.j = j;
     a.rk[0] = h->rank[0]; a.rk[1] = h->rank[1]; a.rk[2] = h->rank[2];
@@ -531,7 +518,7 @@ static int bpr_step_device(crb_handle* h, const crb_table* P, const crb_table* Q
     return crb_launch_loss_final(h, loss_dev, s);
 }
 
-static int zero_step_counters(crb_handle* h, cudaStream_t s) {
+int crb_zero_step_counters(crb_handle* h, cudaStream_t s) {
     // everything except sampler_err (sticky until reported)
     CRB_CUDA(cudaMemsetAsync(h->ctr, 0, offsetof(crb_step_ctr, sampler_err), s));
     CRB_CUDA(cudaMemsetAsync(&h->ctr->partial_slots, 0, sizeof(unsigned int), s));
@@ -566,7 +553,7 @@ extern "C" int crb_train_step_bpr(crb_handle* h, const crb_table* P, const crb_t
     if ((rc = stage_i32(h, u, 0, batch, &du, s))) return rc;
     if ((rc = stage_i32(h, i, 1, batch, &di, s))) return rc;
     if ((rc = stage_i32(h, j, 2, batch, &dj, s))) return rc;
-    if ((rc = zero_step_counters(h, s))) return rc;
+    if ((rc = crb_zero_step_counters(h, s))) return rc;
     double* ld = (loss_out && crb_is_device_ptr(loss_out)) ? loss_out : h->loss_dev;
     rc = bpr_step_device(h, P, Q, od, opt_kind, du, di, dj, batch, reg, false, ld, s);
     if (rc) return rc;
@@ -592,7 +579,7 @@ extern "C" int crb_train_epoch_bpr(crb_handle* h, const crb_table* P, const crb_
         const int64_t b = (rows - lo) < batch ? (rows - lo) : batch;
         step_opt.step = opt->step + k;
         if ((rc = crb_opt_to_dev(h, &step_opt, &od, &opt_kind, s))) return rc;
-        if ((rc = zero_step_counters(h, s))) return rc;
+        if ((rc = crb_zero_step_counters(h, s))) return rc;
         rc = crb_launch_sample_pairwise(h, seed, epoch, lo, b, neg_ratio, h->idx[0], h->idx[1], h->idx[2], nullptr, true, s);
         if (rc) return rc;
         double* ld = host_loss ? h->loss_dev + k : loss_out + k;
@@ -650,7 +637,7 @@ extern "C" int crb_adam_flush(crb_handle* h, const crb_table* T, const crb_opt* 
     if (rc) return rc;
     if ((rc = crb_table_check(T, opt_kind, "T"))) return rc;
     const int64_t n = T->rows * (T->dim / 4);
-    adam_flush_kernel<OPT_ADAM_TF1><<<flat_grid(h, n, 256), 256, 0, s>>>(to_dev(T), T->rows, T->dim, od);
+    adam_flush_kernel<OPT_ADAM_TF1><<<flat_grid(h, n, 256), 256, 0, s>>>(crb_to_dev(T), T->rows, T->dim, od);
     set_last_kernel<<<flat_grid(h, T->rows, 256), 256, 0, s>>>(T->last, T->rows, od.step);
     h->launches += 2;
     CRB_CUDA(cudaGetLastError());
@@ -858,13 +845,13 @@ extern "C" int crb_train_step_pointwise(crb_handle* h, int32_t kind, const crb_t
         CRB_CUDA(cudaMemcpyAsync(h->yv, y, sizeof(float) * batch, cudaMemcpyHostToDevice, s));
         dy = h->yv;
     }
-    if ((rc = zero_step_counters(h, s))) return rc;
+    if ((rc = crb_zero_step_counters(h, s))) return rc;
     const int32_t* idx[3] = {du, di, nullptr};
     const int role_table[3] = {0, 1, 0};
     if ((rc = crb_count_rows(h, batch, 2, idx, role_table, s))) return rc;
     if ((rc = crb_launch_assign(h, batch, 2, idx, role_table, s))) return rc;
     PwArgs a;
-    a.P = to_dev(P); a.Q = to_dev(Q);
+    a.P = crb_to_dev(P); a.Q = crb_to_dev(Q);
     a.metaU = h->meta[0]; a.metaI = h->meta[1];
     a.u = du; a.i = di; a.y = dy;
     a.rk[0] = h->rank[0]; a.rk[1] = h->rank[1];

@@ -1,0 +1,380 @@
+// Multi-GPU BPR step over NVLink peer memory.  One process per GPU.  Users (rows of P, their histories, their
+// sampling) are partitioned across ranks; the item table Q is row-sharded (owner = item % G, local row = item / G) and every
+// rank maps every shard through CUDA IPC, so no NCCL all-to-all, no id de-duplication and no host synchronisation is needed:
+//
+//   phase 1  shard_step_kernel   each rank, for its own B triplets: gathers p_u locally and q_i, q_j STRAIGHT FROM THE OWNER'S HBM
+//                                (peer loads over NVLink), forward/backward, applies the user row locally (same multiplicity
+//                                machinery as the single-GPU step) and writes the two item gradients into the OWNER's inbox:
+//                                one system-scope atomic claims a slot, then 128-bit peer stores.
+//   -- cross-rank barrier (a one-element NCCL all-reduce enqueued on the same stream by the caller) --
+//   phase 2  inbox_apply_kernel  each owner de-duplicates its inbox (count -> assign), applies rows that arrived once in place and
+//                                reduces the others through the duplicate-slot pipeline: one optimizer apply per unique row with
+//                                the gradient summed over ALL ranks -- the semantics of one TF step on the union batch.
+//   -- barrier --
+#include <cstddef>
+
+#include "rowopt.cuh"
+
+struct ShardDev {
+    int n_ranks, rank;
+    int64_t inbox_cap;
+    TableDev q[CRB_MAX_RANKS];
+    float* inbox_grad[CRB_MAX_RANKS];
+    int32_t* inbox_row[CRB_MAX_RANKS];
+    uint32_t* inbox_key[CRB_MAX_RANKS];
+    unsigned int* inbox_cnt[CRB_MAX_RANKS];   // [0] entries, [1] overflow flag
+};
+
+struct ShardStepArgs {
+    TableDev P;
+    unsigned long long* metaU;
+    ShardDev sh;
+    const int32_t* u;   // local user rows
+    const int32_t* i;   // GLOBAL item ids
+    const int32_t* j;
+    const uint32_t* rk_u;
+    int64_t batch;
+    int dim;
+    float reg;
+    OptDev opt;
+    float* dup_grad;
+    uint32_t* dup_t;
+    double* block_loss;
+};
+
+// claims a slot in the owner's inbox (lane `leader` of the group issues the system-scope atomic) and stores the gradient there
+template <int LANES, int VPL>
+__device__ __forceinline__ void send_item_grad(const ShardDev& sh, int owner, int32_t local_row, uint32_t key, const float4* g, int dim, int gl,
+                                               int leader_lane, bool active) {
+    unsigned int slot = 0;
+    if (active && gl == 0) slot = atomicAdd_system(sh.inbox_cnt[owner], 1u);
+    slot = __shfl_sync(0xffffffffu, slot, leader_lane);
+    if (!active) return;
+    if ((int64_t)slot >= sh.inbox_cap) {
+        if (gl == 0) atomicExch_system(sh.inbox_cnt[owner] + 1, 1u);   // overflow: reported by crb_shard_apply_inbox
+        return;
+    }
+    if (gl == 0) { sh.inbox_row[owner][slot] = local_row; sh.inbox_key[owner][slot] = key; }
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        const int c = (gl + LANES * v) * 4;
+        if (c < dim) st4(sh.inbox_grad[owner] + (int64_t)slot * dim + c, g[v]);
+    }
+}
+
+template <int LANES, int VPL, int OPT>
+__global__ void __launch_bounds__(256, 3) shard_step_kernel(ShardStepArgs a) {
+    constexpr int GPW = 32 / LANES;
+    const int lane = threadIdx.x & 31, gl = lane % LANES, sub = lane / LANES;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int G = a.sh.n_ranks;
+    double loss_acc = 0.0;
+    for (int64_t base = warp * GPW; base < a.batch; base += n_warps * GPW) {
+        const int64_t t = base + sub;
+        const bool active = t < a.batch;
+        const int64_t tt = active ? t : a.batch - 1;
+        const int32_t u = a.u[tt], i = a.i[tt], j = a.j[tt];
+        const int oi = i % G, oj = j % G;
+        const int32_t li = i / G, lj = j / G;
+        const TableDev& Qi = a.sh.q[oi];
+        const TableDev& Qj = a.sh.q[oj];
+        const unsigned long long mu = a.metaU[u];
+        RowRegs<LANES, VPL> ru, ri, rj;
+        row_load_w<LANES, VPL>(ru, a.P, u, a.dim, gl);
+        row_load_w<LANES, VPL>(ri, Qi, li, a.dim, gl);   // peer load when oi != rank
+        row_load_w<LANES, VPL>(rj, Qj, lj, a.dim, gl);
+        ru.last = OptTraits<OPT>::replay ? a.P.last[u] : 0;
+        ri.last = OptTraits<OPT>::replay ? Qi.last[li] : 0;
+        rj.last = OptTraits<OPT>::replay ? Qj.last[lj] : 0;
+        const bool su = (uint32_t)mu == 1u || replay_pending<OPT>(ru.last, a.opt);
+        const bool si = replay_pending<OPT>(ri.last, a.opt), sj = replay_pending<OPT>(rj.last, a.opt);
+        if (OptTraits<OPT>::has_s1) {
+            if (su) row_load_state<LANES, VPL, OPT>(ru, a.P, u, a.dim, gl);
+            if (si) row_load_state<LANES, VPL, OPT>(ri, Qi, li, a.dim, gl);
+            if (sj) row_load_state<LANES, VPL, OPT>(rj, Qj, lj, a.dim, gl);
+        }
+        if (replay_pending<OPT>(ru.last, a.opt)) row_replay<LANES, VPL, OPT>(ru, a.opt, a.opt.step);
+        if (si) row_replay<LANES, VPL, OPT>(ri, a.opt, a.opt.step);
+        if (sj) row_replay<LANES, VPL, OPT>(rj, a.opt, a.opt.step);
+        float x = 0.f, sq = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const float4 p = ru.w[v], qi = ri.w[v], qj = rj.w[v];
+            const float4 dq = make_float4(qi.x - qj.x, qi.y - qj.y, qi.z - qj.z, qi.w - qj.w);
+            x += dot4(p, dq);
+            sq += dot4(p, p) + dot4(qi, qi) + dot4(qj, qj);
+        }
+        x = group_sum<LANES>(x);
+        sq = group_sum<LANES>(sq);
+        const float g = -sigmoid_f(-x);
+        if (active && gl == 0) loss_acc += (double)(softplus_neg(x) + a.reg * 0.5f * sq);
+        float4 gu[VPL], gi[VPL], gj[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const float4 p = ru.w[v], qi = ri.w[v], qj = rj.w[v];
+            gu[v] = make_float4(fmaf(g, qi.x - qj.x, a.reg * p.x), fmaf(g, qi.y - qj.y, a.reg * p.y), fmaf(g, qi.z - qj.z, a.reg * p.z),
+                                fmaf(g, qi.w - qj.w, a.reg * p.w));
+            gi[v] = make_float4(fmaf(g, p.x, a.reg * qi.x), fmaf(g, p.y, a.reg * qi.y), fmaf(g, p.z, a.reg * qi.z), fmaf(g, p.w, a.reg * qi.w));
+            gj[v] = make_float4(fmaf(-g, p.x, a.reg * qj.x), fmaf(-g, p.y, a.reg * qj.y), fmaf(-g, p.z, a.reg * qj.z), fmaf(-g, p.w, a.reg * qj.w));
+        }
+        if (active)
+            emit_row<LANES, VPL, OPT>(ru, gu, a.P, a.metaU, u, mu, a.rk_u[t], (uint32_t)t, 0u, a.dim, gl, a.opt, a.dup_grad, a.dup_t);
+        // ordering key of the occurrence: unique and identical from run to run -> deterministic duplicate sums at the owner
+        const uint32_t kbase = ((uint32_t)a.sh.rank * (uint32_t)a.batch + (uint32_t)tt) << 1;
+        send_item_grad<LANES, VPL>(a.sh, oi, li, kbase, gi, a.dim, gl, sub * LANES, active);
+        send_item_grad<LANES, VPL>(a.sh, oj, lj, kbase | 1u, gj, a.dim, gl, sub * LANES, active);
+    }
+    __threadfence_system();   // peer stores visible before the kernel retires (the barrier that follows orders them across ranks)
+    block_loss_store(loss_acc, a.block_loss);
+}
+
+struct InboxArgs {
+    TableDev Q;
+    unsigned long long* meta;
+    const float* grad;
+    const int32_t* row;
+    const uint32_t* key;
+    const unsigned int* cnt;
+    const uint32_t* rk;
+    int64_t cap;
+    int dim;
+    OptDev opt;
+    float* dup_grad;
+    uint32_t* dup_t;
+};
+
+template <int LANES, int VPL, int OPT>
+__global__ void __launch_bounds__(256, 3) inbox_apply_kernel(InboxArgs a) {
+    constexpr int GPW = 32 / LANES;
+    const int lane = threadIdx.x & 31, gl = lane % LANES, sub = lane / LANES;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int64_t n = *a.cnt;
+    if (n > a.cap) n = a.cap;
+    for (int64_t base = warp * GPW; base < n; base += n_warps * GPW) {
+        const int64_t e = base + sub;
+        if (e >= n) continue;   // no warp-wide shuffles below
+        const int32_t row = a.row[e];
+        const unsigned long long m = a.meta[row];
+        RowRegs<LANES, VPL> r;
+        row_load_w<LANES, VPL>(r, a.Q, row, a.dim, gl);
+        r.last = OptTraits<OPT>::replay ? a.Q.last[row] : 0;
+        const bool single = (uint32_t)m == 1u;
+        if (OptTraits<OPT>::has_s1 && single) row_load_state<LANES, VPL, OPT>(r, a.Q, row, a.dim, gl);
+        if (single && replay_pending<OPT>(r.last, a.opt)) row_replay<LANES, VPL, OPT>(r, a.opt, a.opt.step);
+        float4 g[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const int c = (gl + LANES * v) * 4;
+            g[v] = c < a.dim ? ld4(a.grad + e * a.dim + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const uint32_t key = a.key[e];
+        emit_row<LANES, VPL, OPT>(r, g, a.Q, a.meta, row, m, a.rk[e], key >> 2, key & 3u, a.dim, gl, a.opt, a.dup_grad, a.dup_t);
+    }
+}
+
+static int shard_to_dev(const crb_shard* sh, ShardDev* d) {
+    CRB_CHECK_ARG(sh && sh->n_ranks >= 1 && sh->n_ranks <= CRB_MAX_RANKS && sh->rank >= 0 && sh->rank < sh->n_ranks, "shard descriptor");
+    CRB_CHECK_ARG(sh->inbox_cap > 0, "inbox capacity");
+    d->n_ranks = sh->n_ranks; d->rank = sh->rank; d->inbox_cap = sh->inbox_cap;
+    for (int r = 0; r < sh->n_ranks; ++r) {
+        CRB_CHECK_ARG(sh->q[r].w && sh->inbox_grad[r] && sh->inbox_row[r] && sh->inbox_key[r] && sh->inbox_cnt[r], "shard descriptor: null peer pointer");
+        d->q[r] = crb_to_dev(&sh->q[r]);
+        d->inbox_grad[r] = sh->inbox_grad[r]; d->inbox_row[r] = sh->inbox_row[r]; d->inbox_key[r] = sh->inbox_key[r];
+        d->inbox_cnt[r] = sh->inbox_cnt[r];
+    }
+    return CRB_OK;
+}
+
+template <typename K>
+static int one_wave(crb_handle* h, K kernel, int64_t groups, int gpb) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 2; }
+    int64_t grid = (int64_t)h->sm_count * occ;
+    const int64_t need = (groups + gpb - 1) / gpb;
+    if (grid > need) grid = need;
+    if (grid > h->loss_blocks) grid = h->loss_blocks;
+    if (grid < 1) grid = 1;
+    return (int)grid;
+}
+
+template <int LANES, int VPL>
+static int launch_shard_t(crb_handle* h, const ShardStepArgs& a, int opt_kind, cudaStream_t s) {
+    const int gpb = 256 / LANES;
+#define CRB_SH_CASE(O)                                                                          \
+    case O: {                                                                                   \
+        const int grid = one_wave(h, shard_step_kernel<LANES, VPL, O>, a.batch, gpb);           \
+        h->step_grid = grid;                                                                    \
+        shard_step_kernel<LANES, VPL, O><<<grid, 256, 0, s>>>(a);                               \
+        break;                                                                                  \
+    }
+    switch (opt_kind) { CRB_SH_CASE(OPT_SGD) CRB_SH_CASE(OPT_ADAGRAD) CRB_SH_CASE(OPT_ADAM_LAZY) CRB_SH_CASE(OPT_ADAM_TF1) }
+#undef CRB_SH_CASE
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}
+
+template <int LANES, int VPL>
+static int launch_inbox_t(crb_handle* h, const InboxArgs& a, int opt_kind, cudaStream_t s) {
+    const int gpb = 256 / LANES;
+#define CRB_IN_CASE(O)                                                                          \
+    case O: {                                                                                   \
+        const int grid = one_wave(h, inbox_apply_kernel<LANES, VPL, O>, a.cap, gpb);            \
+        inbox_apply_kernel<LANES, VPL, O><<<grid, 256, 0, s>>>(a);                              \
+        break;                                                                                  \
+    }
+    switch (opt_kind) { CRB_IN_CASE(OPT_SGD) CRB_IN_CASE(OPT_ADAGRAD) CRB_IN_CASE(OPT_ADAM_LAZY) CRB_IN_CASE(OPT_ADAM_TF1) }
+#undef CRB_IN_CASE
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}
+
+#define CRB_DIM_DISPATCH(dim, FN, ...)                                   \
+    ((dim) <= 32 ? FN<8, 1>(__VA_ARGS__)                                 \
+     : (dim) <= 64 ? FN<16, 1>(__VA_ARGS__)                              \
+     : (dim) <= 128 ? FN<32, 1>(__VA_ARGS__)                             \
+     : (dim) <= 256 ? FN<32, 2>(__VA_ARGS__)                             \
+                    : FN<32, 4>(__VA_ARGS__))
+
+static void fill_dup(crb_handle* h, DupArgs* d, const TableDev& t0, const TableDev& t1, int dim, const OptDev& od) {
+    d->tab[0] = t0; d->tab[1] = t1;
+    d->meta[0] = h->meta[0]; d->meta[1] = h->meta[1];
+    d->dim = dim; d->opt = od;
+    d->dup_rows = h->dup_rows; d->work = h->work; d->multi = h->multi;
+    d->dup_grad = h->dup_grad; d->dup_t = h->dup_t; d->partial = h->partial; d->ctr = h->ctr;
+}
+
+// phase 1.  u: local user rows, i/j: global item ids (DEVICE or HOST); or u == NULL: sample rows [first, first+batch) of this rank's
+// epoch (crb_set_history holds the rank's own users with GLOBAL item ids).
+extern "C" int crb_shard_step_compute(crb_handle* h, const crb_table* P, const crb_shard* shard, const crb_opt* opt, const int32_t* u,
+                                      const int32_t* i, const int32_t* j, uint64_t seed, uint32_t epoch, int64_t first, int32_t neg_ratio,
+                                      int64_t batch, float reg, double* loss_out, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    CRB_CHECK_ARG(h && P && shard, "null argument");
+    CRB_CHECK_ARG(batch > 0 && (int64_t)shard->n_ranks * batch < 0x20000000LL, "batch");
+    OptDev od;
+    int opt_kind = 0;
+    int rc = crb_opt_to_dev(h, opt, &od, &opt_kind, s);
+    if (rc) return rc;
+    if ((rc = crb_table_check(P, opt_kind, "P"))) return rc;
+    ShardStepArgs a;
+    if ((rc = shard_to_dev(shard, &a.sh))) return rc;
+    CRB_CHECK_ARG(shard->q[shard->rank].dim == P->dim, "P.dim != Q.dim");
+    CRB_CUDA(cudaSetDevice(h->device));
+    if ((rc = crb_ws_reserve(h, batch, P->dim, 4, s))) return rc;
+    if ((rc = crb_meta_reserve(h, 0, P->rows, s))) return rc;
+    if ((rc = crb_zero_step_counters(h, s))) return rc;
+    const int32_t *du = u, *di = i, *dj = j;
+    if (!u) {
+        if ((rc = crb_launch_sample_pairwise(h, seed, epoch, first, batch, neg_ratio, h->idx[0], h->idx[1], h->idx[2], nullptr, false, s))) return rc;
+        du = h->idx[0]; di = h->idx[1]; dj = h->idx[2];
+    } else {
+        CRB_CHECK_ARG(i && j, "null index feed");
+        if (!crb_is_device_ptr(u)) { CRB_CUDA(cudaMemcpyAsync(h->idx[0], u, 4 * batch, cudaMemcpyHostToDevice, s)); du = h->idx[0]; }
+        if (!crb_is_device_ptr(i)) { CRB_CUDA(cudaMemcpyAsync(h->idx[1], i, 4 * batch, cudaMemcpyHostToDevice, s)); di = h->idx[1]; }
+        if (!crb_is_device_ptr(j)) { CRB_CUDA(cudaMemcpyAsync(h->idx[2], j, 4 * batch, cudaMemcpyHostToDevice, s)); dj = h->idx[2]; }
+    }
+    const int32_t* idx[3] = {du, nullptr, nullptr};
+    const int role_table[3] = {0, 0, 0};
+    if ((rc = crb_count_rows(h, batch, 1, idx, role_table, s))) return rc;
+    if ((rc = crb_launch_assign(h, batch, 1, idx, role_table, s))) return rc;
+    a.P = crb_to_dev(P); a.metaU = h->meta[0]; a.u = du; a.i = di; a.j = dj; a.rk_u = h->rank[0];
+    a.batch = batch; a.dim = P->dim; a.reg = reg; a.opt = od; a.dup_grad = h->dup_grad; a.dup_t = h->dup_t; a.block_loss = h->block_loss;
+    if ((rc = crb_prof_begin(h, s))) return rc;
+    if ((rc = CRB_DIM_DISPATCH(a.dim, launch_shard_t, h, a, opt_kind, s))) return rc;
+    if ((rc = crb_prof_end(h, s))) return rc;
+    DupArgs d;
+    fill_dup(h, &d, a.P, a.P, a.dim, od);
+    if ((rc = crb_launch_dup_pipeline(h, d, opt_kind, s))) return rc;
+    double* ld = (loss_out && crb_is_device_ptr(loss_out)) ? loss_out : h->loss_dev;
+    if ((rc = crb_launch_loss_final(h, ld, s))) return rc;
+    if (loss_out && !crb_is_device_ptr(loss_out)) {
+        CRB_CUDA(cudaMemcpyAsync(loss_out, h->loss_dev, sizeof(double), cudaMemcpyDeviceToHost, s));
+        CRB_CUDA(cudaStreamSynchronize(s));
+    }
+    return CRB_OK;
+}
+
+// phase 2 (after the cross-rank barrier): reduce + apply this rank's inbox, then empty it.
+extern "C" int crb_shard_apply_inbox(crb_handle* h, const crb_shard* shard, const crb_opt* opt, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    CRB_CHECK_ARG(h && shard, "null argument");
+    OptDev od;
+    int opt_kind = 0;
+    int rc = crb_opt_to_dev(h, opt, &od, &opt_kind, s);
+    if (rc) return rc;
+    ShardDev sd;
+    if ((rc = shard_to_dev(shard, &sd))) return rc;
+    const crb_table* Q = &shard->q[shard->rank];
+    if ((rc = crb_table_check(Q, opt_kind, "Q shard"))) return rc;
+    CRB_CUDA(cudaSetDevice(h->device));
+    const int64_t cap = shard->inbox_cap;
+    if ((rc = crb_ws_reserve(h, cap, Q->dim, 4, s))) return rc;
+    if ((rc = crb_meta_reserve(h, 1, Q->rows, s))) return rc;
+    if ((rc = crb_zero_step_counters(h, s))) return rc;
+    const int r = shard->rank;
+    const int32_t* idx[3] = {sd.inbox_row[r], nullptr, nullptr};
+    const int role_table[3] = {1, 0, 0};
+    if ((rc = crb_count_rows(h, cap, 1, idx, role_table, s, sd.inbox_cnt[r]))) return rc;
+    if ((rc = crb_launch_assign(h, cap, 1, idx, role_table, s, sd.inbox_cnt[r]))) return rc;
+    InboxArgs a;
+    a.Q = sd.q[r]; a.meta = h->meta[1]; a.grad = sd.inbox_grad[r]; a.row = sd.inbox_row[r]; a.key = sd.inbox_key[r]; a.cnt = sd.inbox_cnt[r];
+    a.rk = h->rank[0]; a.cap = cap; a.dim = Q->dim; a.opt = od; a.dup_grad = h->dup_grad; a.dup_t = h->dup_t;
+    if ((rc = CRB_DIM_DISPATCH(a.dim, launch_inbox_t, h, a, opt_kind, s))) return rc;
+    DupArgs d;
+    fill_dup(h, &d, a.Q, a.Q, a.dim, od);
+    if ((rc = crb_launch_dup_pipeline(h, d, opt_kind, s))) return rc;
+    // overflow flag is sticky until read by crb_shard_inbox_overflow; the entry counter is reset for the next step
+    CRB_CUDA(cudaMemsetAsync(sd.inbox_cnt[r], 0, sizeof(unsigned int), s));
+    return CRB_OK;
+}
+
+extern "C" int crb_shard_inbox_overflow(crb_handle* h, const crb_shard* shard, int32_t* overflowed, void* stream) {
+    CRB_CHECK_ARG(h && shard && overflowed, "null argument");
+    unsigned int v = 0;
+    CRB_CUDA(cudaMemcpyAsync(&v, shard->inbox_cnt[shard->rank] + 1, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CRB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    *overflowed = (int32_t)v;
+    return CRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ peer memory plumbing
+extern "C" int crb_malloc(crb_handle* h, int64_t bytes, void** out) {
+    CRB_CHECK_ARG(h && out && bytes > 0, "bad argument");
+    CRB_CUDA(cudaSetDevice(h->device));
+    CRB_CUDA(cudaMalloc(out, (size_t)bytes));
+    CRB_CUDA(cudaMemset(*out, 0, (size_t)bytes));
+    return CRB_OK;
+}
+extern "C" int crb_free(crb_handle* h, void* p) {
+    CRB_CHECK_ARG(h, "null handle");
+    CRB_CUDA(cudaSetDevice(h->device));
+    CRB_CUDA(cudaFree(p));
+    return CRB_OK;
+}
+extern "C" int crb_ipc_export(crb_handle* h, void* dev_ptr, unsigned char handle64[64]) {
+    CRB_CHECK_ARG(h && dev_ptr && handle64, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    cudaIpcMemHandle_t hd;
+    CRB_CUDA(cudaSetDevice(h->device));
+    CRB_CUDA(cudaIpcGetMemHandle(&hd, dev_ptr));
+    memcpy(handle64, &hd, 64);
+    return CRB_OK;
+}
+extern "C" int crb_ipc_open(crb_handle* h, const unsigned char handle64[64], void** out) {
+    CRB_CHECK_ARG(h && handle64 && out, "null argument");
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, 64);
+    CRB_CUDA(cudaSetDevice(h->device));
+    CRB_CUDA(cudaIpcOpenMemHandle(out, hd, cudaIpcMemLazyEnablePeerAccess));
+    return CRB_OK;
+}
+extern "C" int crb_ipc_close(crb_handle* h, void* p) {
+    CRB_CHECK_ARG(h, "null handle");
+    CRB_CUDA(cudaSetDevice(h->device));
+    CRB_CUDA(cudaIpcCloseMemHandle(p));
+    return CRB_OK;
+}

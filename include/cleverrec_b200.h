@@ -74,6 +74,22 @@ typedef struct {
     int64_t step;
 } crb_opt;
 
+/* Multi-GPU (one process per GPU, one box): the item table is row-sharded, owner = item % n_ranks, local row = item / n_ranks.
+ * Every rank maps every shard and every inbox into its own address space (crb_malloc + crb_ipc_export / crb_ipc_open), so
+ * q[r] / inbox_*[r] are pointers valid ON THIS DEVICE to rank r's memory (NVLink peer access); index `rank` is local memory.
+ * An inbox holds item gradients sent by all ranks during one step: grad [inbox_cap, dim], row/key [inbox_cap], cnt [2]. */
+#define CRB_MAX_RANKS 8
+typedef struct {
+    int32_t n_ranks;
+    int32_t rank;
+    int64_t inbox_cap;
+    crb_table q[CRB_MAX_RANKS];
+    float* inbox_grad[CRB_MAX_RANKS];
+    int32_t* inbox_row[CRB_MAX_RANKS];
+    uint32_t* inbox_key[CRB_MAX_RANKS];
+    uint32_t* inbox_cnt[CRB_MAX_RANKS];
+} crb_shard;
+
 /* utils/tools.py:66-76 (get_loss) */
 enum { CRB_LOSS_BPR = 0, CRB_LOSS_CROSS_ENTROPY = 1, CRB_LOSS_SQUARE = 2, CRB_LOSS_HINGE = 3 };
 
@@ -204,6 +220,25 @@ int crb_train_epoch_nais(crb_handle* h, const crb_table* P, const crb_table* Q, 
 int crb_score_nais(crb_handle* h, const float* P, const float* Q, const float* bias, const float* dense, int32_t dim,
                    int32_t atten_size, const int32_t* hist, int32_t n_hist, const int32_t* targets, int32_t n_targets,
                    float beta, float* scores, void* stream);
+
+/* Multi-GPU BPR step, phase 1 (every rank, same step index): sess.run([train, loss]) on this rank's slice of the union batch.
+ * P: this rank's user rows; u = local user rows, i/j = GLOBAL item ids (DEVICE or HOST), or u == NULL to sample rows
+ * [first, first+batch) of this rank's epoch (crb_set_history holds the rank's own users, item ids global).  Item rows are read
+ * from their owners over peer memory; item gradients are written into the owners' inboxes.  The caller then runs a cross-rank
+ * barrier on the same stream, crb_shard_apply_inbox, and a second barrier. */
+int crb_shard_step_compute(crb_handle* h, const crb_table* P, const crb_shard* shard, const crb_opt* opt, const int32_t* u,
+                           const int32_t* i, const int32_t* j, uint64_t seed, uint32_t epoch, int64_t first, int32_t neg_ratio,
+                           int64_t batch, float reg, double* loss_out, void* stream);
+/* phase 2: de-duplicate this rank's inbox, one optimizer apply per unique item row with the gradient summed over all ranks. */
+int crb_shard_apply_inbox(crb_handle* h, const crb_shard* shard, const crb_opt* opt, void* stream);
+int crb_shard_inbox_overflow(crb_handle* h, const crb_shard* shard, int32_t* overflowed, void* stream);
+
+/* Peer-memory plumbing: cudaMalloc'd (zeroed) buffers that can be exported to the other ranks of the box through CUDA IPC. */
+int crb_malloc(crb_handle* h, int64_t bytes, void** out);
+int crb_free(crb_handle* h, void* p);
+int crb_ipc_export(crb_handle* h, void* dev_ptr, unsigned char handle64[64]);
+int crb_ipc_open(crb_handle* h, const unsigned char handle64[64], void** out);
+int crb_ipc_close(crb_handle* h, void* p);
 
 /* Bring every row of a CRB_ADAM_TF1 table up to `step` (call before reading w: evaluation, checkpoint). */
 int crb_adam_flush(crb_handle* h, const crb_table* T, const crb_opt* opt, void* stream);

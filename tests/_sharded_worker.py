@@ -1,0 +1,74 @@
+"""Worker for tests/test_gpu2_sharded.py (launched with torch.distributed.run, one process per GPU): ShardedBPR over NVLink
+peer memory must reproduce the single-GPU step on the union batch."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cleverrec_b200.dist import ShardedBPR, user_range  # noqa: E402
+from cleverrec_b200.engine import Engine, Optimizer, Table  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = Engine(local)
+    U, I, d, B = 64, 101, 64, 256
+    g = torch.Generator().manual_seed(0)
+    P0, Q0 = torch.randn(U, d, generator=g) * 0.1, torch.randn(I, d, generator=g) * 0.1
+    ok = True
+    for kind, mode in (("SGD", "tf1"), ("Adagrad", "tf1"), ("Adam", "tf1"), ("Adam", "lazy")):
+        lo, hi = user_range(U, rank, world)
+        m = ShardedBPR(eng, U, I, d, kind, 0.05 if kind != "Adam" else 0.01, mode, B, init_P=P0[lo:hi], init_Q=Q0)
+        ref = None
+        if rank == 0:
+            ref = (Table(P0.clone().cuda(), kind, mode), Table(Q0.clone().cuda(), kind, mode), Optimizer(kind, m.opt.lr, adam_mode=mode))
+        rs = np.random.RandomState(5)
+        for step in range(4):
+            feeds = []
+            for r in range(world):  # every rank draws all feeds so rank 0 can build the union batch
+                l, h_ = user_range(U, r, world)
+                n = B if step != 2 else 37
+                feeds.append((rs.randint(l, h_, n), rs.randint(0, I, n), rs.randint(0, I, n)))
+            u, i, j = feeds[rank]
+            loss = m.step(0.01, feed=(u - lo, i, j))
+            t = torch.tensor([loss], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t)
+            if rank == 0:
+                uu, ii, jj = (np.concatenate([f[k] for f in feeds]) for k in range(3))
+                want = eng.train_step_bpr(ref[0], ref[1], ref[2], uu, ii, jj, 0.01)
+                if abs(float(t.item()) - want) > 1e-5 * abs(want):
+                    print("LOSS MISMATCH", kind, mode, step, float(t.item()), want)
+                    ok = False
+        assert not m.inbox_overflowed()
+        m.flush()
+        Qfull = m.gather_Q()
+        Pparts = [torch.zeros(user_range(U, r, world)[1] - user_range(U, r, world)[0], d, device="cuda") for r in range(world)]
+        for r in range(world):
+            if r == rank:
+                Pparts[r].copy_(m.P.w)
+            dist.broadcast(Pparts[r], src=r)
+        if rank == 0:
+            eng.adam_flush(ref[0], ref[2]); eng.adam_flush(ref[1], ref[2])
+            rtol, atol = (1e-4, 1e-5) if kind == "Adam" else (1e-5, 2e-7)
+            for name, got, want in (("P", torch.cat(Pparts), ref[0].w), ("Q", Qfull, ref[1].w)):
+                bad = ~torch.isclose(got, want, rtol=rtol, atol=atol)
+                if bad.float().mean() > 1e-3:
+                    print("TABLE MISMATCH", kind, mode, name, int(bad.sum()), float((got - want).abs().max()))
+                    ok = False
+        m.close()
+    # device-sampled path runs and stays finite
+    flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("SHARDED_OK" if flag.item() == 1.0 else "SHARDED_FAIL")
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()

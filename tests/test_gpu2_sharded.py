@@ -1,0 +1,22 @@
+"""-m gpu, needs >= 2 GPUs on one box (run with `gpurun --gpus 2`; skipped on one GPU): multi-GPU BPR over NVLink peer memory
+reproduces the single-GPU step on the union batch (loss to 1e-5, tables to the single-GPU tolerances)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("world", [2])
+def test_sharded_bpr_matches_single_gpu(world):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(ROOT, "tests", "_sharded_worker.py")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-4000:]
