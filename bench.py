@@ -173,21 +173,31 @@ def run_ours(args, w):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    elif args.sharded:  # experiment: the multi-GPU code path on one GPU (every "peer" is local memory)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29541")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
     eng = Engine(local)
     users, items, dim, B, R = w["users"], w["items"], w["dim"], w["batch"], w["neg_ratio"]
     reg, opt_kind, adam_mode = 0.01, args.optimizer, args.adam_mode
 
-    # ---- data + tables (weak scaling: every rank owns users/world rows of P, its users' histories, and -- round 1 --
-    # a full replica of Q; see DESIGN.md "multi-GPU") ----
+    # ---- data + tables.  Users (rows of P, histories, sampling) are partitioned across ranks; at N > 1 the item table is
+    # row-sharded (owner = item % N) and read / updated over NVLink peer memory (cleverrec_b200/dist.py) ----
     u_lo, u_hi = (users * rank) // world, (users * (rank + 1)) // world
     t_setup = time.time()
-    pu, pi, rowptr = build_history_device(torch, dev, users, items, w["mean_hist"], seed=1234 + rank, user_lo=u_lo, user_hi=u_hi)
-    eng.set_history_arrays(users, items, pu, pi, rowptr, pi)
+    pu, pi, rowptr = build_history_device(torch, dev, u_hi - u_lo, items, w["mean_hist"], seed=1234 + rank)
+    eng.set_history_arrays(u_hi - u_lo, items, pu, pi, rowptr, pi)
     n_pos = int(pu.numel())
-    g = torch.Generator(device=dev).manual_seed(0)
-    P = Table(torch.randn(users, dim, device=dev, generator=g) * 0.01, opt_kind, adam_mode)
-    Q = Table(torch.randn(items, dim, device=dev, generator=g) * 0.01, opt_kind, adam_mode)
-    opt = Optimizer(opt_kind, 1e-3, adam_mode=adam_mode)
+    g = torch.Generator(device=dev).manual_seed(rank)
+    sharded = None
+    if world == 1 and not args.sharded:
+        P = Table(torch.randn(users, dim, device=dev, generator=g) * 0.01, opt_kind, adam_mode)
+        Q = Table(torch.randn(items, dim, device=dev, generator=g) * 0.01, opt_kind, adam_mode)
+        opt = Optimizer(opt_kind, 1e-3, adam_mode=adam_mode)
+    else:
+        from cleverrec_b200.dist import ShardedBPR
+        sharded = ShardedBPR(eng, users, items, dim, opt_kind, 1e-3, adam_mode, B, seed=rank)
+        P, opt = sharded.P, sharded.opt
     torch.cuda.synchronize()
     t_setup = time.time() - t_setup
     rows = eng.epoch_rows(R, "pairwise")
@@ -202,9 +212,16 @@ def run_ours(args, w):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def run_steps(first_step, n, losses):
+        if sharded is None:
+            eng.train_epoch_bpr(P, Q, opt, 7, 0, first_step * B, B, n, R, reg, losses)
+        else:
+            for k in range(n):
+                sharded.step(reg, neg_ratio=R, seed=7, epoch=0, first=(first_step + k) * B, batch=B, loss_out=losses[k:k + 1])
+
     # ---- device-resident run: value ----
     losses = torch.zeros(steps_total, dtype=torch.float64, device=dev)
-    eng.train_epoch_bpr(P, Q, opt, 7, 0, 0, B, args.warmup, R, reg, losses)  # warm-up steps
+    run_steps(0, args.warmup, losses)  # warm-up steps
     clocks = ClockSampler(local)
     clocks.start()
     eng.profile(True)
@@ -213,7 +230,7 @@ def run_ours(args, w):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    eng.train_epoch_bpr(P, Q, opt, 7, 0, args.warmup * B, B, args.steps, R, reg, losses[args.warmup:])
+    run_steps(args.warmup, args.steps, losses[args.warmup:])
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -238,11 +255,16 @@ def run_ours(args, w):
     for k in range(n_e2e + 1):
         u, i, j = eng.sample_pairwise(7, 0, first + k * B, B, R)
         feeds.append(tuple(x.cpu().pin_memory() for x in (u, i, j)))
-    eng.train_step_bpr(P, Q, opt, *feeds[n_e2e], reg=reg)  # warm
+
+    def e2e_step(f):
+        if sharded is None:
+            return eng.train_step_bpr(P, Q, opt, f[0], f[1], f[2], reg=reg)  # returns the host loss (sync)
+        return sharded.step(reg, feed=f)
+    e2e_step(feeds[n_e2e])  # warm
     barrier()
     t0 = time.perf_counter()
     for k in range(n_e2e):
-        eng.train_step_bpr(P, Q, opt, feeds[k][0], feeds[k][1], feeds[k][2], reg=reg)  # returns the host loss (sync)
+        e2e_step(feeds[k])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -250,13 +272,14 @@ def run_ours(args, w):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * B * n_e2e / e2e_s
+    overflow = sharded.inbox_overflowed() if sharded is not None else False
 
     # ---- roofline of the dominant kernel (K3 fused step) ----
     hbm, tf, which = peaks()
     per_triplet = {"SGD": 24, "Adagrad": 48, "Adam": 72}[opt_kind] * dim  # algorithmic bytes / triplet
     k3_avg_ms = k3_ms / max(1, k3_n)
     achieved = per_triplet * B / (k3_avg_ms / 1000.0) / 1e9 if k3_n else None
-    roofline = {"bound": "hbm", "kernel": "bpr_step_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "bpr_step_kernel" if world == 1 else "shard_step_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                 "frac": (achieved / hbm) if achieved else None, "traffic": None, "peak_source": which,
                 "algorithmic_bytes_per_launch": per_triplet * B, "kernel_ms": k3_avg_ms, "kernel_share_of_step": k3_avg_ms / ms_step,
                 "step_frac": per_triplet * B / (ms_step / 1000.0) / 1e9 / hbm}
@@ -269,7 +292,7 @@ def run_ours(args, w):
 
     # ---- secondary metric: full-rank top-20 evaluation users/sec ----
     ev = None
-    if args.eval_users > 0:
+    if args.eval_users > 0 and sharded is None:
         eng.adam_flush(P, opt)
         eng.adam_flush(Q, opt)
         n_eval = min(args.eval_users, u_hi - u_lo)
@@ -309,7 +332,9 @@ def run_ours(args, w):
                 "config": {"workload": args.workload, "users": users, "items": items, "dim": dim, "interactions_per_gpu": n_pos, "batch_per_gpu": B,
                            "neg_ratio": R, "optimizer": opt_kind, "adam_mode": adam_mode if opt_kind == "Adam" else None, "reg": reg,
                            "l2_policy": "inputs larger than L2 (tables %.1f GB vs 126 MB L2)" % ((users + items) * dim * 4 / 1e9),
-                           "parallelism": "dp%d: user rows + histories sharded, item table replicated" % world, "setup_s": round(t_setup, 1)},
+                           "parallelism": ("single GPU" if world == 1 else "%d ranks: users partitioned, item table row-sharded (item %% N), rows and gradients "
+                                           "over NVLink peer memory, NCCL only as the step barrier" % world), "inbox_overflow": overflow,
+                           "setup_s": round(t_setup, 1)},
                 "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 8, "steps": n_e2e},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "eval": ev, "final_loss": loss_last}
         print(json.dumps(line), flush=True)
@@ -329,6 +354,7 @@ def main():
     ap.add_argument("--eval-users", dest="eval_users", type=int, default=32768)
     ap.add_argument("--eval-exact", dest="eval_exact", action="store_true")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--sharded", action="store_true", help="use the multi-GPU code path even at N=1 (experiments)")
     ap.add_argument("--users", type=int, default=0, help="override the workload's user count (experiments)")
     ap.add_argument("--items", type=int, default=0)
     ap.add_argument("--batch", type=int, default=0)

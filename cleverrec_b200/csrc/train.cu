@@ -28,7 +28,10 @@ __global__ void __launch_bounds__(256) count_rows_kernel(RoleArgs a, int64_t bat
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < batch; t += stride) {
 #pragma unroll
         for (int r = 0; r < 3; ++r)
-            if (r < a.n_roles) a.rank[r][t] = atomicAdd(reinterpret_cast<unsigned int*>(a.meta[r] + a.idx[r][t]), 1u);
+            if (r < a.n_roles) {
+                const int32_t row = a.idx[r][t];   // negative = hole (multi-GPU inbox): never counted, never ranked 1
+                a.rank[r][t] = row < 0 ? 0xFFFFFFFFu : atomicAdd(reinterpret_cast<unsigned int*>(a.meta[r] + row), 1u);
+            }
     }
 }
 

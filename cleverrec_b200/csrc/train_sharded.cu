@@ -42,19 +42,32 @@ struct ShardStepArgs {
     double* block_loss;
 };
 
-// claims a slot in the owner's inbox (lane `leader` of the group issues the system-scope atomic) and stores the gradient there
+#define SH_CHUNK 32u   // inbox slots a warp reserves per system-scope atomic (unused ones stay holes: row = -1)
+
+// Takes one slot of the owner's inbox for every active group of the warp and stores the gradient there.  Slots are handed out
+// from per-warp reservations of SH_CHUNK (one system-scope atomic on the owner's counter per 32 gradients instead of one per
+// gradient: the single hot counter was the bottleneck of the first version).
 template <int LANES, int VPL>
-__device__ __forceinline__ void send_item_grad(const ShardDev& sh, int owner, int32_t local_row, uint32_t key, const float4* g, int dim, int gl,
-                                               int leader_lane, bool active) {
-    unsigned int slot = 0;
-    if (active && gl == 0) slot = atomicAdd_system(sh.inbox_cnt[owner], 1u);
-    slot = __shfl_sync(0xffffffffu, slot, leader_lane);
+__device__ __forceinline__ void send_item_grad(const ShardDev& sh, unsigned int* s_base, unsigned int* s_left, int owner, int32_t local_row,
+                                               uint32_t key, const float4* g, int dim, int gl, int sub, bool active) {
+    constexpr int GPW = 32 / LANES;
+    unsigned int slot = 0xFFFFFFFFu;
+#pragma unroll
+    for (int q = 0; q < GPW; ++q) {
+        if (sub == q && gl == 0 && active) {
+            if (s_left[owner] == 0u) { s_base[owner] = atomicAdd_system(sh.inbox_cnt[owner], SH_CHUNK); s_left[owner] = SH_CHUNK; }
+            slot = s_base[owner]++;
+            s_left[owner]--;
+        }
+        __syncwarp();
+    }
+    slot = __shfl_sync(0xffffffffu, slot, sub * LANES);
     if (!active) return;
     if ((int64_t)slot >= sh.inbox_cap) {
-        if (gl == 0) atomicExch_system(sh.inbox_cnt[owner] + 1, 1u);   // overflow: reported by crb_shard_apply_inbox
+        if (gl == 0) atomicExch_system(sh.inbox_cnt[owner] + 1, 1u);   // overflow: reported by crb_shard_inbox_overflow
         return;
     }
-    if (gl == 0) { sh.inbox_row[owner][slot] = local_row; sh.inbox_key[owner][slot] = key; }
+    if (gl == 0) { sh.inbox_key[owner][slot] = key; sh.inbox_row[owner][slot] = local_row; }
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         const int c = (gl + LANES * v) * 4;
@@ -69,34 +82,46 @@ __global__ void __launch_bounds__(256, 3) shard_step_kernel(ShardStepArgs a) {
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int G = a.sh.n_ranks;
+    __shared__ unsigned int s_resv[8][2][CRB_MAX_RANKS];   // per warp: next slot / slots left of the current reservation per owner
+    if (lane < CRB_MAX_RANKS) { s_resv[threadIdx.x >> 5][0][lane] = 0u; s_resv[threadIdx.x >> 5][1][lane] = 0u; }
+    __syncwarp();
+    unsigned int* s_base = s_resv[threadIdx.x >> 5][0];
+    unsigned int* s_left = s_resv[threadIdx.x >> 5][1];
     double loss_acc = 0.0;
-    for (int64_t base = warp * GPW; base < a.batch; base += n_warps * GPW) {
+    // Software pipeline: indices two iterations ahead, embedding rows one iteration ahead -- the (remote) row loads of triplet
+    // n+1 are in flight while triplet n is computed and stored.  Out-of-range iterations clamp to the last triplet (loads only).
+    const int64_t stride = n_warps * GPW;
+    const int64_t base0 = warp * GPW;
+    auto clampt = [&](int64_t b) { const int64_t t_ = b + sub; return t_ < a.batch ? t_ : a.batch - 1; };
+    int32_t nu, ni, nj;          // indices of the next iteration
+    int32_t fu, fi, fj;          // indices two iterations ahead
+    { const int64_t t0 = clampt(base0); nu = a.u[t0]; ni = a.i[t0]; nj = a.j[t0]; }
+    { const int64_t t1 = clampt(base0 + stride); fu = a.u[t1]; fi = a.i[t1]; fj = a.j[t1]; }
+    RowRegs<LANES, VPL> nru, nri, nrj;
+    row_load_w<LANES, VPL>(nru, a.P, nu, a.dim, gl);
+    row_load_w<LANES, VPL>(nri, a.sh.q[ni % G], ni / G, a.dim, gl);
+    row_load_w<LANES, VPL>(nrj, a.sh.q[nj % G], nj / G, a.dim, gl);
+    for (int64_t base = base0; base < a.batch; base += stride) {
         const int64_t t = base + sub;
         const bool active = t < a.batch;
         const int64_t tt = active ? t : a.batch - 1;
-        const int32_t u = a.u[tt], i = a.i[tt], j = a.j[tt];
+        const int32_t u = nu, i = ni, j = nj;
+        RowRegs<LANES, VPL> ru = nru, ri = nri, rj = nrj;
+        // issue the next iteration's row loads and the indices after that
+        nu = fu; ni = fi; nj = fj;
+        row_load_w<LANES, VPL>(nru, a.P, nu, a.dim, gl);
+        row_load_w<LANES, VPL>(nri, a.sh.q[ni % G], ni / G, a.dim, gl);   // peer load when the owner is another rank
+        row_load_w<LANES, VPL>(nrj, a.sh.q[nj % G], nj / G, a.dim, gl);
+        { const int64_t t2 = clampt(base + 2 * stride); fu = a.u[t2]; fi = a.i[t2]; fj = a.j[t2]; }
         const int oi = i % G, oj = j % G;
         const int32_t li = i / G, lj = j / G;
-        const TableDev& Qi = a.sh.q[oi];
-        const TableDev& Qj = a.sh.q[oj];
         const unsigned long long mu = a.metaU[u];
-        RowRegs<LANES, VPL> ru, ri, rj;
-        row_load_w<LANES, VPL>(ru, a.P, u, a.dim, gl);
-        row_load_w<LANES, VPL>(ri, Qi, li, a.dim, gl);   // peer load when oi != rank
-        row_load_w<LANES, VPL>(rj, Qj, lj, a.dim, gl);
+        // item rows are always current at a step boundary (the owner decays its whole shard in phase 2), so only the local user
+        // row can have missed steps to replay
         ru.last = OptTraits<OPT>::replay ? a.P.last[u] : 0;
-        ri.last = OptTraits<OPT>::replay ? Qi.last[li] : 0;
-        rj.last = OptTraits<OPT>::replay ? Qj.last[lj] : 0;
         const bool su = (uint32_t)mu == 1u || replay_pending<OPT>(ru.last, a.opt);
-        const bool si = replay_pending<OPT>(ri.last, a.opt), sj = replay_pending<OPT>(rj.last, a.opt);
-        if (OptTraits<OPT>::has_s1) {
-            if (su) row_load_state<LANES, VPL, OPT>(ru, a.P, u, a.dim, gl);
-            if (si) row_load_state<LANES, VPL, OPT>(ri, Qi, li, a.dim, gl);
-            if (sj) row_load_state<LANES, VPL, OPT>(rj, Qj, lj, a.dim, gl);
-        }
+        if (OptTraits<OPT>::has_s1 && su) row_load_state<LANES, VPL, OPT>(ru, a.P, u, a.dim, gl);
         if (replay_pending<OPT>(ru.last, a.opt)) row_replay<LANES, VPL, OPT>(ru, a.opt, a.opt.step);
-        if (si) row_replay<LANES, VPL, OPT>(ri, a.opt, a.opt.step);
-        if (sj) row_replay<LANES, VPL, OPT>(rj, a.opt, a.opt.step);
         float x = 0.f, sq = 0.f;
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
@@ -122,8 +147,8 @@ __global__ void __launch_bounds__(256, 3) shard_step_kernel(ShardStepArgs a) {
             emit_row<LANES, VPL, OPT>(ru, gu, a.P, a.metaU, u, mu, a.rk_u[t], (uint32_t)t, 0u, a.dim, gl, a.opt, a.dup_grad, a.dup_t);
         // ordering key of the occurrence: unique and identical from run to run -> deterministic duplicate sums at the owner
         const uint32_t kbase = ((uint32_t)a.sh.rank * (uint32_t)a.batch + (uint32_t)tt) << 1;
-        send_item_grad<LANES, VPL>(a.sh, oi, li, kbase, gi, a.dim, gl, sub * LANES, active);
-        send_item_grad<LANES, VPL>(a.sh, oj, lj, kbase | 1u, gj, a.dim, gl, sub * LANES, active);
+        send_item_grad<LANES, VPL>(a.sh, s_base, s_left, oi, li, kbase, gi, a.dim, gl, sub, active);
+        send_item_grad<LANES, VPL>(a.sh, s_base, s_left, oj, lj, kbase | 1u, gj, a.dim, gl, sub, active);
     }
     __threadfence_system();   // peer stores visible before the kernel retires (the barrier that follows orders them across ranks)
     block_loss_store(loss_acc, a.block_loss);
@@ -156,6 +181,7 @@ __global__ void __launch_bounds__(256, 3) inbox_apply_kernel(InboxArgs a) {
         const int64_t e = base + sub;
         if (e >= n) continue;   // no warp-wide shuffles below
         const int32_t row = a.row[e];
+        if (row < 0) continue;   // hole of a partly used reservation
         const unsigned long long m = a.meta[row];
         RowRegs<LANES, VPL> r;
         row_load_w<LANES, VPL>(r, a.Q, row, a.dim, gl);
@@ -327,8 +353,12 @@ extern "C" int crb_shard_apply_inbox(crb_handle* h, const crb_shard* shard, cons
     DupArgs d;
     fill_dup(h, &d, a.Q, a.Q, a.dim, od);
     if ((rc = crb_launch_dup_pipeline(h, d, opt_kind, s))) return rc;
+    // CRB_ADAM_TF1: bring every row of the shard to this step (rows not touched now take their decay-only step), so that the next
+    // step's readers -- local or over NVLink -- never need a row's `last` (a dependent 4-byte peer load cost 2.3 ms per step)
+    if ((rc = crb_adam_flush(h, Q, opt, stream))) return rc;
     // overflow flag is sticky until read by crb_shard_inbox_overflow; the entry counter is reset for the next step
     CRB_CUDA(cudaMemsetAsync(sd.inbox_cnt[r], 0, sizeof(unsigned int), s));
+    CRB_CUDA(cudaMemsetAsync(sd.inbox_row[r], 0xFF, sizeof(int32_t) * (size_t)cap, s));   // every slot is a hole until written
     return CRB_OK;
 }
 

@@ -91,9 +91,10 @@ class ShardedBPR(object):
         if optimizer == "Adagrad":
             self.q["s1"].tensor.fill_(0.1)
         # every rank may receive up to 2 * batch * world gradients per step (2 per triplet); hubs make the split uneven
-        self.inbox_cap = int(2 * batch * min(self.world, 2) + 4096) if self.world > 1 else 2 * batch
+        self.inbox_cap = int(2 * batch * min(self.world, 2)) + 32 * 4096 * self.world  # + slack for partly used reservations
         self.inbox = {"grad": _DeviceBuffer(engine, (self.inbox_cap, dim), torch.float32), "row": _DeviceBuffer(engine, (self.inbox_cap,), torch.int32),
                       "key": _DeviceBuffer(engine, (self.inbox_cap,), torch.int32), "cnt": _DeviceBuffer(engine, (4,), torch.int32)}
+        self.inbox["row"].tensor.fill_(-1)   # every slot is a hole until a gradient is written into it
         self._map_peers()
         self._flag = torch.zeros(1, device=dev)
         torch.cuda.synchronize()
