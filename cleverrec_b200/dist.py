@@ -194,3 +194,94 @@ class ShardedBPR(object):
         for b in list(self.q.values()) + list(self.inbox.values()):
             b.tensor = None
             self.engine.lib.crb_free(self.engine.h, b.ptr)
+
+
+# ---------------------------------------------------------------------------------------------- evaluation across the item shards
+def transpose_history(seen_rowptr, seen_cols, u_lo, n_users_total, world, rank, group=None):
+    """Each rank holds the histories of ITS users (global item ids).  Evaluation needs the opposite cut: for ALL users, the seen
+    items that live on THIS rank's item shard (owner = item % world), as local rows.  One all-to-all of (user, local row) pairs at
+    set-up; works on CPU tensors with gloo (tests) and CUDA tensors with NCCL.  -> (rowptr int64 [n_users_total+1], cols int32)."""
+    dev = seen_cols.device
+    counts = (seen_rowptr[1:] - seen_rowptr[:-1])
+    users = torch.repeat_interleave(torch.arange(counts.numel(), device=dev, dtype=torch.int64) + u_lo, counts)
+    cols = seen_cols.to(torch.int64)
+    owner = cols % world
+    order = torch.argsort(owner, stable=True)
+    send_counts = torch.bincount(owner, minlength=world)
+    send_u, send_i = users[order].contiguous(), (cols // world)[order].contiguous()
+    recv_counts = torch.empty_like(send_counts)
+    if world > 1:
+        dist.all_to_all_single(recv_counts, send_counts, group=group)
+    else:
+        recv_counts.copy_(send_counts)
+    sc, rc = send_counts.tolist(), recv_counts.tolist()
+    recv_u = torch.empty(sum(rc), dtype=torch.int64, device=dev)
+    recv_i = torch.empty(sum(rc), dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_to_all_single(recv_u, send_u, rc, sc, group=group)
+        dist.all_to_all_single(recv_i, send_i, rc, sc, group=group)
+    else:
+        recv_u.copy_(send_u); recv_i.copy_(send_i)
+    stride = int(recv_i.max().item()) + 1 if recv_i.numel() else 1
+    key = torch.unique(recv_u * stride + recv_i)  # sorted by (user, local row)
+    ku = torch.div(key, stride, rounding_mode="floor")
+    rowptr = torch.zeros(n_users_total + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(torch.bincount(ku, minlength=n_users_total), 0, out=rowptr[1:])
+    return rowptr, (key - ku * stride).to(torch.int32)
+
+
+def merge_topk(ids_per_rank, scores_per_rank, K, ascending=False):
+    """Exact global top-K from every shard's exact local top-K: candidates ordered by (score, global id) with the documented tie
+    rule.  ids/scores: lists of [n, K] tensors (ids global, -1 = padding).  Pure tensor logic (CPU-testable)."""
+    ids = torch.cat(ids_per_rank, dim=1).to(torch.int64)
+    sc = torch.cat(scores_per_rank, dim=1).to(torch.float32)
+    pad = ids < 0
+    worst = float("inf") if ascending else float("-inf")
+    sc = torch.where(pad, torch.full_like(sc, worst), sc)
+    ids_key = torch.where(pad, torch.full_like(ids, 1 << 40), ids)
+    order = torch.argsort(ids_key, dim=1, stable=True)               # id ascending first ...
+    ids, sc = torch.gather(ids, 1, order), torch.gather(sc, 1, order)
+    order = torch.argsort(sc, dim=1, descending=not ascending, stable=True)[:, :K]   # ... then a stable sort by score
+    return torch.gather(ids, 1, order).to(torch.int32), torch.gather(sc, 1, order)
+
+
+class ShardedEval(object):
+    """Full-rank top-K of this rank's users against the row-sharded item table (test_model_rs across ranks): the users' vectors are
+    broadcast batch by batch, every rank ranks them against ITS item shard with the single-GPU kernels (crb_score_topk, seen items
+    masked from the transposed history), and the G x K candidates per user are merged at the user's owner."""
+
+    def __init__(self, model, seen_rowptr, seen_cols, kind=_lib.SCORE_DOT):
+        self.m, self.kind = model, kind
+        self.world, self.rank = model.world, model.rank
+        dev = model.engine.device
+        rowptr, cols = transpose_history(seen_rowptr.to(dev), seen_cols.to(dev), model.u_lo, model.n_users, self.world, self.rank, model.group)
+        self.eng = Engine(dev.index)   # a second handle on the same device: its history is the transposed one
+        pu = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.eng.set_history_arrays(model.n_users, model.q_rows, pu[:0], pu[:0], rowptr, cols)
+
+    def topk(self, K, batch_users=1 << 16, exact=False):
+        m, dev = self.m, self.m.engine.device
+        m.flush()
+        out = torch.full((m.u_hi - m.u_lo, K), -1, dtype=torch.int32, device=dev)
+        Qw = m.q["w"].tensor
+        for owner in range(self.world):
+            lo, hi = user_range(m.n_users, owner, self.world)
+            for a in range(lo, hi, batch_users):
+                b = min(hi, a + batch_users)
+                rows = m.P.w[a - lo:b - lo].contiguous() if owner == self.rank else torch.empty(b - a, m.dim, device=dev)
+                if self.world > 1:
+                    dist.broadcast(rows, src=owner, group=m.group)
+                local_u = torch.arange(b - a, dtype=torch.int32, device=dev)
+                hist_u = torch.arange(a, b, dtype=torch.int32, device=dev)
+                ids, sc = self.eng.score_topk(self.kind, rows, Qw, local_u, K, hist_users=hist_u, exact=exact, n_items=m.q_rows, return_scores=True)
+                gids = torch.where(ids >= 0, ids * self.world + self.rank, ids)   # local row -> global item id
+                if self.world > 1:
+                    all_ids = [torch.empty_like(gids) for _ in range(self.world)] if owner == self.rank else None
+                    all_sc = [torch.empty_like(sc) for _ in range(self.world)] if owner == self.rank else None
+                    dist.gather(gids, all_ids, dst=owner, group=m.group)
+                    dist.gather(sc, all_sc, dst=owner, group=m.group)
+                else:
+                    all_ids, all_sc = [gids], [sc]
+                if owner == self.rank:
+                    out[a - lo:b - lo] = merge_topk(all_ids, all_sc, K, ascending=self.kind == _lib.SCORE_SQDIST)[0]
+        return out

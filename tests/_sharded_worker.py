@@ -61,6 +61,36 @@ def main():
                     print("TABLE MISMATCH", kind, mode, name, int(bad.sum()), float((got - want).abs().max()))
                     ok = False
         m.close()
+    # ---- evaluation across the item shards: per-shard exact top-K merged at the owner == single-GPU top-K on the gathered tables
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    from conftest import synthetic_data
+    from cleverrec_b200.dist import ShardedEval, shard_history
+    from cleverrec_b200.engine import history_from_dict
+    data = synthetic_data(U, I, 9, seed=4)
+    lo, hi = user_range(U, rank, world)
+    m = ShardedBPR(eng, U, I, d, "Adagrad", 0.05, "tf1", B, init_P=P0[lo:hi], init_Q=Q0)
+    mine, n_local = shard_history(data.ui_train, U, rank, world)
+    m.set_history(mine, n_local)
+    for step in range(3):   # device-sampled steps
+        m.step(0.01, neg_ratio=2, seed=9, epoch=0, first=step * 64, batch=64)
+    _, _, rp, sc = history_from_dict(mine, n_local)
+    for exact in (True, False):
+        ev = ShardedEval(m, torch.from_numpy(rp), torch.from_numpy(sc))
+        got = ev.topk(10, batch_users=20, exact=exact)
+        Qfull = m.gather_Q()
+        Pparts = [torch.zeros(user_range(U, r, world)[1] - user_range(U, r, world)[0], d, device="cuda") for r in range(world)]
+        for r in range(world):
+            if r == rank:
+                Pparts[r].copy_(m.P.w)
+            dist.broadcast(Pparts[r], src=r)
+        ref_eng = Engine(local)
+        ref_eng.set_history(data.ui_train, U, I)
+        want = ref_eng.score_topk(0, torch.cat(Pparts), Qfull, torch.arange(lo, hi, dtype=torch.int32, device="cuda"), 10, exact=True)
+        if not torch.equal(got, want):
+            print("EVAL MISMATCH rank", rank, "exact", exact, int((got != want).sum()))
+            ok = False
+        ref_eng.close()
+    m.close()
     # device-sampled path runs and stays finite
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -55,3 +55,53 @@ def test_partition_helpers_single_process():
         assert [user_range(n, r, w)[0] for r in range(w)] + [n] == [0] + [user_range(n, r, w)[1] for r in range(w)]
     items = np.arange(1000)
     assert np.array_equal(item_owner(items, 8) + 8 * item_local_row(items, 8), items)
+
+
+EVAL_WORKER = r'''
+import os, sys
+import numpy as np, torch
+import torch.distributed as dist
+sys.path.insert(0, %r)
+sys.path.insert(0, os.path.join(%r, "tests"))
+from conftest import synthetic_data
+from cleverrec_b200.dist import user_range, shard_history, transpose_history, merge_topk, shard_rows
+from cleverrec_b200.engine import history_from_dict
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+d = synthetic_data(64, 45, 7, seed=2)
+mine, n_local = shard_history(d.ui_train, d.user_nums, rank, world)
+lo, hi = user_range(d.user_nums, rank, world)
+_, _, rowptr, cols = history_from_dict(mine, n_local)
+tp, tc = transpose_history(torch.from_numpy(rowptr), torch.from_numpy(cols), lo, d.user_nums, world, rank)
+# for every user: the local rows of its seen items that live on this shard
+for u in range(d.user_nums):
+    want = sorted(i // world for i in set(d.ui_train.get(u, [])) if i %% world == rank)
+    assert tc[tp[u]:tp[u + 1]].tolist() == want, (u, want)
+# merge of per-shard exact top-K == global top-K (ties by id)
+rs = np.random.RandomState(0)
+scores = np.round(rs.randn(10, d.item_nums) * 2).astype(np.float32) / 2   # heavy ties
+K = 6
+mine_items = np.arange(rank, d.item_nums, world)
+loc = torch.from_numpy(scores[:, mine_items])
+order = torch.argsort(-loc, dim=1, stable=True)[:, :K]
+ids = torch.from_numpy(mine_items)[order].to(torch.int32)
+sc = torch.gather(loc, 1, order)
+all_ids, all_sc = [torch.empty_like(ids) for _ in range(world)], [torch.empty_like(sc) for _ in range(world)]
+dist.all_gather(all_ids, ids); dist.all_gather(all_sc, sc)
+got, _ = merge_topk(all_ids, all_sc, K)
+want = np.argsort(-scores, axis=1, kind="stable")[:, :K]
+assert np.array_equal(got.numpy(), want), (got, want)
+if rank == 0:
+    print("EVAL_PARTITION_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_transposed_history_and_topk_merge_two_processes(tmp_path):
+    script = tmp_path / "w2.py"
+    script.write_text(EVAL_WORKER % (ROOT, ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29521",
+           str(script)]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "EVAL_PARTITION_OK" in r.stdout, r.stdout[-3000:]
