@@ -316,6 +316,29 @@ def run_ours(args, w):
         except Exception as e:  # reported, never hidden
             ev = {"error": str(e)}
 
+    if args.eval_users > 0 and sharded is not None:
+        from cleverrec_b200.dist import ShardedEval
+        try:
+            n_eval = min(args.eval_users, u_hi - u_lo)
+            sev = ShardedEval(sharded, rowptr, pi)
+            sev.topk(20, batch_users=n_eval, limit=n_eval)  # warm (also flushes pending Adam decay and sizes the workspace)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            sev.topk(20, batch_users=n_eval, limit=n_eval)
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+            flops = 2.0 * world * n_eval * items * dim
+            ev = {"metric": "fullrank_top20_eval_users_per_sec", "value": world * n_eval / (ems / 1000.0), "unit": "users/s", "users": world * n_eval,
+                  "items": items, "ms": ems, "path": "bf16 tcgen05 per item shard + certified fp32 rescoring + merge at the owner",
+                  "roofline": {"bound": "tensor", "achieved": flops / (ems / 1000.0) / 1e12 / world, "peak": tf, "unit": "TFLOP/s per GPU",
+                               "frac": flops / (ems / 1000.0) / 1e12 / world / tf}}
+        except Exception as e:
+            ev = {"error": str(e)}
+
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -259,13 +259,16 @@ class ShardedEval(object):
         pu = torch.zeros(1, dtype=torch.int32, device=dev)
         self.eng.set_history_arrays(model.n_users, model.q_rows, pu[:0], pu[:0], rowptr, cols)
 
-    def topk(self, K, batch_users=1 << 16, exact=False):
+    def topk(self, K, batch_users=1 << 16, exact=False, limit=None):
+        """limit: evaluate only the first `limit` users of every rank (benchmarks)."""
         m, dev = self.m, self.m.engine.device
         m.flush()
         out = torch.full((m.u_hi - m.u_lo, K), -1, dtype=torch.int32, device=dev)
         Qw = m.q["w"].tensor
         for owner in range(self.world):
             lo, hi = user_range(m.n_users, owner, self.world)
+            if limit is not None:
+                hi = min(hi, lo + limit)
             for a in range(lo, hi, batch_users):
                 b = min(hi, a + batch_users)
                 rows = m.P.w[a - lo:b - lo].contiguous() if owner == self.rank else torch.empty(b - a, m.dim, device=dev)
