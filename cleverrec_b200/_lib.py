@@ -24,7 +24,7 @@ EXPORTS = [
     "crb_train_step_neumf", "crb_score_pairs_neumf", "crb_mask_seen",
     "crb_sample_nais", "crb_train_step_nais", "crb_train_epoch_nais", "crb_score_nais",
     "crb_shard_step_compute", "crb_shard_apply_inbox", "crb_shard_inbox_overflow", "crb_malloc", "crb_free", "crb_ipc_export",
-    "crb_ipc_open", "crb_ipc_close",
+    "crb_ipc_open", "crb_ipc_close", "crb_np_seed", "crb_np_set_state", "crb_np_get_state", "crb_sample_epoch_numpy",
 ]
 
 
@@ -112,6 +112,10 @@ def load():
     lib.crb_ipc_export.argtypes = [vp, vp, C.c_char_p]
     lib.crb_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     lib.crb_ipc_close.argtypes = [vp, vp]
+    lib.crb_np_seed.argtypes = [vp, u32]
+    lib.crb_np_set_state.argtypes = [vp, vp, i32]
+    lib.crb_np_get_state.argtypes = [vp, vp, C.POINTER(i32)]
+    lib.crb_sample_epoch_numpy.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     _lib = lib
     return lib
 

@@ -79,6 +79,7 @@ extern "C" int crb_destroy(crb_handle* h) {
     cudaFree(h->loss_dev);
     cudaFree(h->lrt);
     cudaFree(h->dense_loss);
+    cudaFree(h->np_state); cudaFree(h->np_raw); cudaFree(h->np_scratch); cudaFree(h->np_sort_tmp); cudaFree(h->np_result);
     cudaFree(h->dense_grad);
     cudaFree(h->eval_ws);
     if (h->prof_ev) { for (int k = 0; k < 2 * CRB_PROF_CAP; ++k) cudaEventDestroy(h->prof_ev[k]); free(h->prof_ev); }

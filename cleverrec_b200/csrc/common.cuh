@@ -100,6 +100,16 @@ struct crb_handle {
     int64_t eval_ws_bytes;
     int64_t topk_stats[4];
     int64_t launches;
+    // numpy_stream sampler mode (sampler_np.cu)
+    void* np_state;        // device RandomState (624 words + pos)
+    int np_seeded;
+    void* np_raw;          // raw 32-bit outputs scratch
+    int64_t np_raw_cap;
+    void* np_scratch;
+    int64_t np_scratch_cap;
+    void* np_sort_tmp;
+    int64_t np_sort_cap;
+    int64_t* np_result;
     // profiling hook
     int prof_on;
     int prof_n;          // event pairs recorded since last read

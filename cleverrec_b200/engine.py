@@ -144,6 +144,47 @@ class Engine(object):
         check(self.lib.crb_sample_cml(self.h, seed, epoch, first, count, neg_ratio, ptr(u), ptr(i), ptr(neg), self.stream))
         return u, i, neg
 
+    # ------------------------------------------------------------------ numpy_stream sampler mode (bit-exact reference samplers)
+    def np_seed(self, seed):
+        """np.random.seed(seed) for the device copy of NumPy's legacy global stream."""
+        check(self.lib.crb_np_seed(self.h, int(seed) & 0xFFFFFFFF))
+
+    def np_set_state(self, state=None):
+        """Import np.random.get_state() (default: NumPy's current global state)."""
+        st = np.random.get_state() if state is None else state
+        key = np.ascontiguousarray(st[1], dtype=np.uint32)
+        check(self.lib.crb_np_set_state(self.h, ptr(key), int(st[2])))
+
+    def np_get_state(self):
+        """The device stream as a tuple accepted by np.random.set_state."""
+        key = np.zeros(624, dtype=np.uint32)
+        pos = C.c_int32()
+        check(self.lib.crb_np_get_state(self.h, ptr(key), C.byref(pos)))
+        return ("MT19937", key, int(pos.value), 0, 0.0)
+
+    def sample_epoch_numpy(self, kind, neg_ratio, with_nbr=False):
+        """One epoch exactly as the reference sampler returns it under the current stream.  kind: pairwise|pointwise|cml|negatives."""
+        dev = self.device
+        n_pos = self.n_pos
+        if kind == "negatives":
+            negs = torch.empty((n_pos, neg_ratio), dtype=torch.int32, device=dev)
+            check(self.lib.crb_sample_epoch_numpy(self.h, 3, neg_ratio, None, None, ptr(negs), None, self.stream))
+            return negs
+        n = {"pairwise": n_pos * neg_ratio, "pointwise": n_pos * (neg_ratio + 1), "cml": n_pos}[kind]
+        u, i = torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.int32, device=dev)
+        if kind == "pairwise":
+            j = torch.empty(n, dtype=torch.int32, device=dev)
+            nbr = torch.empty(n, dtype=torch.int32, device=dev) if with_nbr else None
+            check(self.lib.crb_sample_epoch_numpy(self.h, 0, neg_ratio, ptr(u), ptr(i), ptr(j), ptr(nbr), self.stream))
+            return (u, i, j, nbr) if with_nbr else (u, i, j)
+        if kind == "pointwise":
+            y = torch.empty(n, dtype=torch.float32, device=dev)
+            check(self.lib.crb_sample_epoch_numpy(self.h, 1, neg_ratio, ptr(u), ptr(i), ptr(y), None, self.stream))
+            return u, i, y
+        neg = torch.empty((n, neg_ratio), dtype=torch.int32, device=dev)
+        check(self.lib.crb_sample_epoch_numpy(self.h, 2, neg_ratio, ptr(u), ptr(i), ptr(neg), None, self.stream))
+        return u, i, neg
+
     # ------------------------------------------------------------------ training
     @staticmethod
     def _feed_i32(x):

@@ -11,12 +11,29 @@ import numpy as np
 
 from ..engine import Engine
 
-_state = {"engine": None, "data_id": None, "epoch": 0, "seed": 0}
+_state = {"engine": None, "data_id": None, "epoch": 0, "seed": 0, "mode": "philox"}
 
 
 def set_seed(seed):
     _state["seed"] = int(seed)
     _state["epoch"] = 0
+
+
+def set_mode(mode):
+    """'philox' (default): the counter-based device sampler, same distribution as the reference, its own stream.
+    'numpy_stream': the reference's output BIT FOR BIT -- the device adopts NumPy's current global RandomState
+    (np.random.get_state()), draws the epoch exactly as utils/sampler.py would, and hands the advanced state back to NumPy,
+    so `np.random.seed(s); pairwise_ranking_sampler(...)` returns the reference's arrays."""
+    if mode not in ("philox", "numpy_stream"):
+        raise ValueError("sampler mode must be 'philox' or 'numpy_stream'")
+    _state["mode"] = mode
+
+
+def _numpy_epoch(eng, kind, neg_ratio, with_nbr=False):
+    eng.np_set_state()
+    out = eng.sample_epoch_numpy(kind, neg_ratio, with_nbr=with_nbr) if kind == "pairwise" else eng.sample_epoch_numpy(kind, neg_ratio)
+    np.random.set_state(eng.np_get_state())
+    return out
 
 
 def _engine_for(data):
@@ -38,6 +55,10 @@ def _next_epoch():
 def pointwise_ranking_sampler(data, neg_ratio, batch_size, fism_like=False):
     eng = _engine_for(data)
     n = eng.epoch_rows(neg_ratio, "pointwise")
+    if _state["mode"] == "numpy_stream":
+        out = _numpy_epoch(eng, "pointwise", neg_ratio)
+        return (math.ceil(n / batch_size), out[0].cpu().numpy().astype(np.int64), out[1].cpu().numpy().astype(np.int64),
+                out[2].cpu().numpy().astype(np.float64))
     out = eng.sample_pointwise(_state["seed"], _next_epoch(), 0, n, neg_ratio, with_nbr=fism_like)
     res = (math.ceil(n / batch_size), out[0].cpu().numpy().astype(np.int64), out[1].cpu().numpy().astype(np.int64),
            out[2].cpu().numpy().astype(np.float64))
@@ -50,7 +71,10 @@ def pointwise_ranking_sampler(data, neg_ratio, batch_size, fism_like=False):
 def pairwise_ranking_sampler(data, neg_ratio, batch_size, fism_like=False):
     eng = _engine_for(data)
     n = eng.epoch_rows(neg_ratio, "pairwise")
-    out = eng.sample_pairwise(_state["seed"], _next_epoch(), 0, n, neg_ratio, with_nbr=fism_like)
+    if _state["mode"] == "numpy_stream":
+        out = _numpy_epoch(eng, "pairwise", neg_ratio, with_nbr=fism_like)
+    else:
+        out = eng.sample_pairwise(_state["seed"], _next_epoch(), 0, n, neg_ratio, with_nbr=fism_like)
     res = (math.ceil(n / batch_size),) + tuple(t.cpu().numpy().astype(np.int64) for t in out[:3])
     if fism_like:
         res = res + (out[3].cpu().numpy().astype(np.int64),)
@@ -61,6 +85,9 @@ def pairwise_ranking_sampler(data, neg_ratio, batch_size, fism_like=False):
 def ranking_sampler_cml(data, neg_ratio, batch_size):
     eng = _engine_for(data)
     n = eng.epoch_rows(neg_ratio, "cml")
-    u, i, neg = eng.sample_cml(_state["seed"], _next_epoch(), 0, n, neg_ratio)
+    if _state["mode"] == "numpy_stream":
+        u, i, neg = _numpy_epoch(eng, "cml", neg_ratio)
+    else:
+        u, i, neg = eng.sample_cml(_state["seed"], _next_epoch(), 0, n, neg_ratio)
     return (math.ceil(n / batch_size), u.cpu().numpy().astype(np.int64), i.cpu().numpy().astype(np.int64),
             neg.cpu().numpy().astype(np.int64))

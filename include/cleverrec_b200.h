@@ -126,6 +126,22 @@ int crb_sample_pointwise(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t f
 /* utils/sampler.py:77-99 ranking_sampler_cml: neg is [count, neg_ratio] row-major. */
 int crb_sample_cml(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t first, int64_t count,
                    int32_t neg_ratio, int32_t* u, int32_t* i, int32_t* neg, void* stream);
+/* ---- `numpy_stream` sampler mode: the reference's samplers bit for bit -------------------------------------------------
+ * The device keeps a copy of NumPy's legacy global RandomState (MT19937 key[624] + pos).  crb_np_seed == np.random.seed(int);
+ * crb_np_set_state / crb_np_get_state exchange the state with np.random.get_state() / set_state() (key and pos fields), so a
+ * run can interleave reference code (e.g. RankingPreprocess) and device sampling on ONE stream exactly like the reference. */
+int crb_np_seed(crb_handle* h, uint32_t seed);
+int crb_np_set_state(crb_handle* h, const uint32_t* key624, int32_t pos);
+int crb_np_get_state(crb_handle* h, uint32_t* key624, int32_t* pos);
+/* One whole epoch exactly as the reference sampler returns it (utils/sampler.py), advancing the stream like the reference:
+ *  kind 0 pairwise_ranking_sampler   u,i [N], third = j int32 [N], nbr int32 [N] or NULL            N = n_pos * neg_ratio
+ *  kind 1 pointwise_ranking_sampler  u,i [N], third = y float [N]                                   N = n_pos * (neg_ratio + 1)
+ *  kind 2 ranking_sampler_cml        u,i [N], third = neg int32 [N, neg_ratio]                      N = n_pos
+ *  kind 3 negatives only, in draw order (train_model_nais, RankingRecommender.py:64-80): third = int32 [n_pos, neg_ratio]
+ * DEVICE outputs.  The call synchronises (the number of random values consumed is data dependent). */
+int crb_sample_epoch_numpy(crb_handle* h, int32_t kind, int32_t neg_ratio, int32_t* u, int32_t* i, void* third, int32_t* nbr,
+                           void* stream);
+
 /* number of rows in one epoch of each sampler (utils/sampler.py:65 `train_nums`) */
 int64_t crb_epoch_rows(crb_handle* h, int32_t neg_ratio, int32_t sampler_kind /*0 pairwise,1 pointwise,2 cml*/);
 
