@@ -46,8 +46,30 @@ class RankingRecommender(Recommender):
     def _before_eval(self):
         pass
 
+    # ---- numpy_stream mode: the epoch the reference's sampler would return for NumPy's CURRENT global state (np.random.seed(s)
+    # before run_model reproduces the reference's triplet sequence bit for bit), fed batch by batch like RankingRecommender.py:39-46
+    def _train_epoch_numpy_stream(self):
+        import numpy as np_
+        eng = self.engine
+        eng.np_set_state()
+        if self.is_pairwise == 'True':
+            feeds = eng.sample_epoch_numpy('pairwise', self.neg_ratio, with_nbr=self.fism_like)
+        else:
+            feeds = eng.sample_epoch_numpy('pointwise', self.neg_ratio)
+        np_.random.set_state(eng.np_get_state())
+        n_rows = feeds[0].numel()
+        n_batches = math.ceil(n_rows / self.batch_size)
+        losses = torch.zeros(n_batches, dtype=torch.float64, device=eng.device)
+        for k in range(n_batches):
+            sl = slice(k * self.batch_size, min((k + 1) * self.batch_size, n_rows))
+            self.train_step(*(f[sl] for f in feeds), loss_out=losses[k:k + 1])
+        self.epoch += 1
+        return float(losses.sum().item()) / n_batches
+
     # ---- Train the model (Single epoch) ----------------------------------------------------------------------
     def train_model(self):
+        if self.sampler_mode == 'numpy_stream':
+            return self._train_epoch_numpy_stream()
         if self.is_pairwise == 'True':
             n_rows = self.engine.epoch_rows(self.neg_ratio, 'pairwise')
             n_batches = math.ceil(n_rows / self.batch_size)

@@ -26,6 +26,9 @@ class Recommender(object):
         # B200-path keys (all optional; defaults keep the reference's behaviour)
         self.seed = int(c.get('seed', 0))
         self.adam_mode = c.get('adam_mode', 'tf1')          # 'tf1' = tf.train.AdamOptimizer semantics, 'lazy' = LazyAdam
+        self.sampler_mode = c.get('sampler', 'philox')        # 'philox' | 'numpy_stream' (the reference's np.random stream, bit for bit)
+        if self.sampler_mode not in ('philox', 'numpy_stream'):
+            raise ValueError("sampler must be 'philox' or 'numpy_stream'")
         self.score_exact = c.get('score_exact', 'False') == 'True'  # full-rank eval on CUDA cores instead of tcgen05
         self.init_generator = torch.Generator().manual_seed(self.seed)
         self.initializer = get_initializer(c['init_method'], float(c['stddev']), generator=self.init_generator)

@@ -33,9 +33,9 @@ class BPR(_rr.RankingRecommender):
         self.engine.train_epoch_bpr(self.P, self.Q, self.optimizer, self.seed, epoch, 0, self.batch_size, n_batches,
                                     self.neg_ratio, self.reg, losses)
 
-    def train_step(self, u_idx, i_idx, j_idx):
+    def train_step(self, u_idx, i_idx, j_idx, loss_out=None):
         """Feed-style single step (the reference's `sess.run([train, loss], {u_idx, i_idx, j_idx})`)."""
-        return self.engine.train_step_bpr(self.P, self.Q, self.optimizer, u_idx, i_idx, j_idx, self.reg)
+        return self.engine.train_step_bpr(self.P, self.Q, self.optimizer, u_idx, i_idx, j_idx, self.reg, loss_out=loss_out)
 
     def _before_eval(self):
         self.engine.adam_flush(self.P, self.optimizer)

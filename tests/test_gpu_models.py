@@ -107,3 +107,27 @@ def test_run_model_all_log_lines(caplog):
     with caplog.at_level(logging.INFO):
         best_epoch, best = m.run_model()
     assert 'Training loss:' in caplog.text and 'best_epoch:' in caplog.text and best_epoch >= 1
+
+
+def test_numpy_stream_training_follows_the_reference_triplets():
+    """sampler=numpy_stream: after np.random.seed(s) the model trains on exactly the triplet sequence the reference's sampler
+    produces, so an epoch equals the restated TF graph fed with the restated reference sampler's batches."""
+    import torch
+    from oracle import tf1_restatement as T
+    data = _data('loo', 49)
+    m = _model('BPR', data, sampler='numpy_stream', optimizer='SGD', lr=0.05, batch_size=256)
+    P0, Q0 = m.P.w.cpu().clone(), m.Q.w.cpu().clone()
+    np.random.seed(77)
+    got = m.train_model()
+    state_after = np.random.get_state()
+    np.random.seed(77)
+    tr = H.pairwise_ranking_sampler(data, m.neg_ratio, 256)
+    assert np.array_equal(np.random.get_state()[1], state_after[1]) and np.random.get_state()[2] == state_after[2]
+    ref, ropt, total = {"P": P0, "Q": Q0}, T.TF1Optimizer("SGD", 0.05), 0.0
+    for k in range(tr[0]):
+        sl = slice(k * 256, (k + 1) * 256)
+        b = {"u": torch.tensor(tr[1][sl]), "i": torch.tensor(tr[2][sl]), "j": torch.tensor(tr[3][sl])}
+        total += T.train_step(T.bpr_loss, ref, b, {"reg": m.reg}, ropt, sparse_index={"P": ["u"], "Q": ["i", "j"]})
+    assert abs(got - total / tr[0]) <= 1e-5 * abs(total / tr[0])
+    np.testing.assert_allclose(m.P.w.cpu().numpy(), ref["P"].numpy(), rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(m.Q.w.cpu().numpy(), ref["Q"].numpy(), rtol=2e-5, atol=1e-6)
