@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcleverrec_b200.so")
+LIB_PATH = os.environ.get("CRB_LIB_PATH") or os.path.join(_HERE, "libcleverrec_b200.so")  # CRB_LIB_PATH: A/B builds of the same library
 
 OPT_SGD, OPT_ADAGRAD, OPT_ADAM = 0, 1, 2
 ADAM_TF1, ADAM_LAZY = 0, 1

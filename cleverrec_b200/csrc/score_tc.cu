@@ -11,6 +11,7 @@
 //                     approx <= theta, |approx - canonical| <= eps, so if the K-th canonical score beats theta + eps the
 //                     returned ids are exactly those of the fp32 path.  Uncertified users go to fullrank_exact_kernel.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 
 #include "score_common.cuh"
@@ -19,7 +20,10 @@
 #define TC_KEEP 64        // kept by a compaction
 #define TC_BM 256         // users per CTA (2 x UMMA_M=128)
 #define TC_BN 128         // items per tile
-#define TC_THREADS 384    // 4 control warps + 8 epilogue warps
+#ifndef TC_CH
+#define TC_CH 2            // column halves of a tile, each scanned by its own set of 8 warps with its own candidate lists
+#endif
+#define TC_THREADS (128 + 256 * TC_CH)   // 4 control warps + 8 epilogue warps per column half
 #define TC_MAX_KB 3       // K blocks of 64 -> d_pad <= 192
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -62,21 +66,29 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t r[32];
+// Asynchronous TMEM load of 32 consecutive columns of this thread's lane (issue only) ...
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
           "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
           "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-#pragma unroll
-    for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+}
+// ... and the wait that makes the registers valid.  They are passed as in/out operands so that the compiler cannot schedule a
+// use of them above the wait.
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                   "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                   "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
 }
 
 // K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4, LBO (unused
@@ -165,29 +177,39 @@ struct TcArgs {
     unsigned long long* cand;   // [n_splits, n_users_pad, TC_C]  (approx score bits << 32 | item)
     int32_t* cand_cnt;          // [n_splits, n_users_pad]
     float* cand_thr;            // [n_splits, n_users_pad]
+    int debug;                  // experiments only (CRB_TC_DEBUG): 1 = read TMEM but skip the scan, 2 = skip the TMEM read too
 };
 
 __device__ __forceinline__ uint32_t ord_bits(uint32_t f) { return (f & 0x80000000u) ? ~f : (f | 0x80000000u); }
 
-// Warp-cooperative compaction of one row's candidate list (n <= TC_C entries, 4 per lane): T = the TC_KEEP-th largest
-// approximate score, found by a 32-step radix descent on the order-preserving score bits (count via one warp reduction per
-// bit); entries with score > T are kept (<= TC_KEEP-1 of them, packed to the front in lane order), everything <= T is dropped
-// and T becomes the row's threshold.  Returns T; *kept receives the new count.
+// Warp-cooperative compaction of one row's candidate list (n <= TC_C entries, 4 per lane).  ANY threshold T is valid for the
+// certificate as long as every dropped entry has score <= T; the list only needs to shrink enough to make room.  So instead of
+// an exact selection (a 32-step radix descent was the straggler that stalled the 2-deep accumulator pipeline) T is found by
+// bisection on the order-preserving score bits between the list's min and max, stopping as soon as the number of kept entries
+// (score > T) lies in [TC_KEEP_MIN, TC_KEEP]: typically 4-6 warp reductions.  Kept entries are packed to the front.
+// Returns T as a float; *kept receives the new count.
+#define TC_KEEP_MIN 32
 __device__ __forceinline__ float compact_list(unsigned long long* list, int n, int lane, int* kept) {
     unsigned long long e[4];
     uint32_t o[4];
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const int idx = lane + 32 * t;
         e[t] = idx < n ? __ldcg(list + idx) : 0ULL;
-        o[t] = idx < n ? ord_bits((uint32_t)(e[t] >> 32)) : 0u;  // 0 is below every real score (ord of a real float is >= 1... NaN aside)
+        o[t] = idx < n ? ord_bits((uint32_t)(e[t] >> 32)) : 0u;
+        if (idx < n) { lo = min(lo, o[t]); hi = max(hi, o[t]); }
     }
-    uint32_t T = 0;
-#pragma unroll 1
-    for (int bit = 31; bit >= 0; --bit) {
-        const uint32_t cand = T | (1u << bit);
-        const int c = (o[0] >= cand) + (o[1] >= cand) + (o[2] >= cand) + (o[3] >= cand);
-        if (__reduce_add_sync(0xffffffffu, c) >= TC_KEEP) T = cand;
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    // invariants: count(o > hi) <= TC_KEEP (0 at the start);  count(o > lo - 1) would be n (too many)
+    uint32_t T = hi;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        const int c = (o[0] > mid) + (o[1] > mid) + (o[2] > mid) + (o[3] > mid);
+        const int tot = __reduce_add_sync(0xffffffffu, c);
+        if (tot > TC_KEEP) { lo = mid + 1; T = hi; }
+        else { hi = mid; T = mid; if (tot >= TC_KEEP_MIN) break; }
     }
     __syncwarp();
     int base = 0;
@@ -231,7 +253,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
         for (int s = 0; s < a.stages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 8 * TC_CH); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -302,8 +324,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             }
         }
     } else if (warp >= 4) {
-        // ================= epilogue: 8 warps, one TMEM lane (= one user) per thread =================
-        const int ew = warp - 4, half = ew >> 2, quad = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4)..+31
+        // ================= epilogue: 16 warps; a thread owns one TMEM lane (= one user) and one column half of every tile ======
+        const int ew = warp - 4, half = (ew >> 2) & 1, quad = warp & 3, ch = ew >> 3;  // a warp may only touch TMEM lanes 32*(warp%4)..+31
         const int row = half * 128 + quad * 32 + lane;
         uint32_t acc = 0, acc_phase = 0;
         for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -312,8 +334,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             const int t0 = sp * a.tiles_per_split, t1 = min(a.n_tiles, t0 + a.tiles_per_split);
             const int64_t g = mt * TC_BM + row;  // user slot of this thread
             const bool live = g < a.n_users;
-            unsigned long long* list = a.cand + ((int64_t)sp * a.n_users_pad + g) * TC_C;
-            float theta = -INFINITY;
+            const int64_t lslot = (int64_t)(sp * TC_CH + ch) * a.n_users_pad;   // this (split, column half)'s lists
+            unsigned long long* list = a.cand + (lslot + g) * TC_C;
+            float theta = a.debug == 3 ? INFINITY : -INFINITY;   // debug 3: fast path only (nothing ever beats the threshold)
             int cnt = 0;
             // cursor into the user's sorted history: first seen item >= first item of this split
             int64_t hp = 0, hend = 0;
@@ -335,10 +358,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             for (int t = t0; t < t1; ++t) {
                 mbar_wait(t_full + acc, acc_phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
+                // software pipeline over the 4 column chunks of the tile: chunk c+1 is being read out of TMEM while chunk c is scanned
+                const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256u + (uint32_t)half * 128u;
+#ifndef TC_EPI_PIPELINE
+#define TC_EPI_PIPELINE 0   // measured 2x slower (code size / registers): kept only as an A/B switch
+#endif
+#if TC_EPI_PIPELINE
+                uint32_t rbuf[2][32];
+                tmem_ld32_issue(t_lane, rbuf[0]);
+#pragma unroll
                 for (int c = 0; c < TC_BN / 32; ++c) {
+                    tmem_ld32_wait(rbuf[c & 1]);
+                    if (c + 1 < TC_BN / 32) tmem_ld32_issue(t_lane + (uint32_t)(c + 1) * 32u, rbuf[(c + 1) & 1]);
                     float v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256u + (uint32_t)half * 128u + (uint32_t)c * 32u, v);
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(rbuf[c & 1][k]);
+#else
+#pragma unroll 1
+                for (int c = ch * (TC_BN / 32 / TC_CH); c < (ch + 1) * (TC_BN / 32 / TC_CH); ++c) {
+                    uint32_t rb[32];
+                    if (a.debug == 2) continue;
+                    tmem_ld32_issue(t_lane + (uint32_t)c * 32u, rb);
+                    tmem_ld32_wait(rb);
+                    if (a.debug == 1) { if (rb[0] == 0x12345678u && rb[31] == 0x9abcdef0u) cnt = 0; continue; }
+                    float v[32];
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(rb[k]);
+#endif
                     const int32_t c0 = t * TC_BN + c * 32;
                     if (live) {
                         // mask seen items (amortised O(|history|) per user) and the padding past the catalogue
@@ -381,7 +427,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                         const int src = __ffs(need) - 1;
                         need &= need - 1;
                         const int n = __shfl_sync(0xffffffffu, cnt, src);
-                        unsigned long long* lst = a.cand + ((int64_t)sp * a.n_users_pad + (mt * TC_BM + half * 128 + quad * 32 + src)) * TC_C;
+                        unsigned long long* lst = a.cand + (lslot + (mt * TC_BM + half * 128 + quad * 32 + src)) * TC_C;
                         int kept;
                         const float thr = compact_list(lst, n, lane, &kept);
                         if (lane == src) { theta = fmaxf(theta, thr); cnt = kept; }
@@ -392,8 +438,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 if (lane == 0) mbar_arrive(t_empty + acc);
                 if (++acc == 2u) { acc = 0; acc_phase ^= 1; }
             }
-            a.cand_cnt[(int64_t)sp * a.n_users_pad + g] = live ? cnt : 0;
-            a.cand_thr[(int64_t)sp * a.n_users_pad + g] = theta;
+            a.cand_cnt[lslot + g] = live ? cnt : 0;
+            a.cand_thr[lslot + g] = theta;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -548,7 +594,7 @@ int crb_score_topk_tc(crb_handle* h, int32_t kind, const float* P, const float* 
     const int tiles_per_split = (n_tiles + n_splits - 1) / n_splits;
     n_splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
     // workspace
-    const int64_t slots = (int64_t)n_splits * pass_pad;
+    const int64_t slots = (int64_t)n_splits * TC_CH * pass_pad;   // one candidate list per (split, column half, user)
     int64_t off = 0;
     auto take = [&](int64_t bytes) { int64_t o = off; off += (bytes + 1023) & ~(int64_t)1023; return o; };
     const int64_t o_qb = take(n_items_pad * d_pad * 2), o_pb = take(pass_pad * d_pad * 2), o_cand = take(slots * TC_C * 8);
@@ -587,6 +633,7 @@ int crb_score_topk_tc(crb_handle* h, int32_t kind, const float* P, const float* 
         ta.n_users = nu; ta.n_users_pad = nu_pad; ta.n_items = n_items; ta.n_tiles = n_tiles; ta.n_splits = n_splits;
         ta.tiles_per_split = tiles_per_split; ta.kb = kb; ta.stages = stages; ta.users = users + u0;
         ta.hist_users = hist_users ? hist_users + u0 : nullptr; ta.seen_rowptr = h->seen_rowptr; ta.seen_cols = h->seen_cols;
+        ta.debug = getenv("CRB_TC_DEBUG") ? atoi(getenv("CRB_TC_DEBUG")) : 0;
         ta.cand = (unsigned long long*)(ws + o_cand); ta.cand_cnt = (int32_t*)(ws + o_cnt); ta.cand_thr = (float*)(ws + o_thr);
         const int64_t n_work = (nu_pad / TC_BM) * n_splits;
         const int grid = (int)(n_work < h->sm_count ? n_work : h->sm_count);
@@ -594,7 +641,7 @@ int crb_score_topk_tc(crb_handle* h, int32_t kind, const float* P, const float* 
         CRB_CUDA(cudaGetLastError());
         CRB_CUDA(cudaMemsetAsync(misc + 2, 0, 8, s));
         RescoreArgs ra;
-        ra.kind = kind; ra.dim = dim; ra.K = K; ra.n_splits = n_splits; ra.n_users = nu; ra.n_users_pad = nu_pad;
+        ra.kind = kind; ra.dim = dim; ra.K = K; ra.n_splits = n_splits * TC_CH; ra.n_users = nu; ra.n_users_pad = nu_pad;
         ra.P = P; ra.Q = Q; ra.hvec = hvec; ra.users = users + u0; ra.cand = ta.cand; ra.cand_cnt = ta.cand_cnt; ra.cand_thr = ta.cand_thr;
         ra.pnorm = (const float*)(ws + o_pn); ra.psq = (const float*)(ws + o_psq); ra.maxbits = misc; ra.cbound = cbound;
         ra.out_items = topk_items + u0 * K; ra.out_scores = topk_scores ? topk_scores + u0 * K : nullptr;
@@ -612,6 +659,7 @@ int crb_score_topk_tc(crb_handle* h, int32_t kind, const float* P, const float* 
         unsigned int cnts[2] = {0, 0};
         CRB_CUDA(cudaMemcpyAsync(cnts, misc + 2, 8, cudaMemcpyDeviceToHost, s));
         CRB_CUDA(cudaStreamSynchronize(s));
+        if (ta.debug) cnts[0] = 0;   // experiments: results are meaningless, do not re-run anyone
         if (cnts[0]) {
             // todo holds pass-local user slots: the exact kernel indexes users/outputs of this pass
             rc = crb_launch_fullrank_exact(h, kind, P, Q, hvec, n_items, dim, users + u0, hist_users ? hist_users + u0 : nullptr,
