@@ -53,7 +53,71 @@ extern "C" int crb_create(int device, crb_handle** out) {
     return CRB_OK;
 }
 
+void crb_alt_swap(crb_handle* h) {
+#define CRB_SWAP(a, b) do { auto t__ = (a); (a) = (b); (b) = t__; } while (0)
+    for (int k = 0; k < 3; ++k) { CRB_SWAP(h->idx[k], h->alt.idx[k]); CRB_SWAP(h->rank[k], h->alt.rank[k]); }
+    for (int k = 0; k < 2; ++k) { CRB_SWAP(h->meta[k], h->alt.meta[k]); CRB_SWAP(h->meta_rows[k], h->alt.meta_rows[k]); }
+    CRB_SWAP(h->ctr, h->alt.ctr);
+    CRB_SWAP(h->dup_rows, h->alt.dup_rows);
+    CRB_SWAP(h->work, h->alt.work);
+    CRB_SWAP(h->multi, h->alt.multi);
+#undef CRB_SWAP
+    h->alt_active ^= 1;
+}
+
+static void free_alt_ws(crb_handle* h) {
+    for (int k = 0; k < 3; ++k) { cudaFree(h->alt.idx[k]); h->alt.idx[k] = nullptr; cudaFree(h->alt.rank[k]); h->alt.rank[k] = nullptr; }
+    cudaFree(h->alt.dup_rows); h->alt.dup_rows = nullptr;
+    cudaFree(h->alt.work); h->alt.work = nullptr;
+    cudaFree(h->alt.multi); h->alt.multi = nullptr;
+    h->alt.cap_batch = 0;
+}
+
+int crb_alt_reserve(crb_handle* h, cudaStream_t s) {
+    if (h->alt_active) crb_alt_swap(h);
+    if (!h->aux_stream) {
+        CRB_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+        CRB_CUDA(cudaEventCreateWithFlags(&h->ev_entry, cudaEventDisableTiming));
+        for (int k = 0; k < 2; ++k) {
+            CRB_CUDA(cudaEventCreateWithFlags(&h->ev_prep[k], cudaEventDisableTiming));
+            CRB_CUDA(cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming));
+        }
+        CRB_CUDA(cudaMalloc(&h->alt.ctr, sizeof(crb_step_ctr)));
+        CRB_CUDA(cudaMemset(h->alt.ctr, 0, sizeof(crb_step_ctr)));
+    }
+    if (h->alt.cap_batch != h->cap_batch) {
+        CRB_CUDA(cudaStreamSynchronize(s));
+        CRB_CUDA(cudaStreamSynchronize(h->aux_stream));
+        free_alt_ws(h);
+        const int64_t nb = h->cap_batch, occ = 3 * nb;
+        for (int k = 0; k < 3; ++k) {
+            CRB_CUDA(cudaMalloc(&h->alt.idx[k], sizeof(int32_t) * nb));
+            CRB_CUDA(cudaMalloc(&h->alt.rank[k], sizeof(uint32_t) * nb));
+        }
+        CRB_CUDA(cudaMalloc(&h->alt.dup_rows, sizeof(crb_dup_row) * (occ / 2 + 1)));
+        CRB_CUDA(cudaMalloc(&h->alt.work, sizeof(crb_work) * (occ / 2 + occ / CRB_DUP_CHUNK + 2)));
+        CRB_CUDA(cudaMalloc(&h->alt.multi, sizeof(unsigned int) * (occ / CRB_DUP_CHUNK + 2)));
+        h->alt.cap_batch = nb;
+    }
+    for (int w = 0; w < 2; ++w) {
+        if (h->alt.meta_rows[w] == h->meta_rows[w]) continue;
+        CRB_CUDA(cudaStreamSynchronize(s));
+        CRB_CUDA(cudaStreamSynchronize(h->aux_stream));
+        cudaFree(h->alt.meta[w]);
+        h->alt.meta[w] = nullptr;
+        h->alt.meta_rows[w] = 0;
+        if (h->meta_rows[w] > 0) {
+            CRB_CUDA(cudaMalloc(&h->alt.meta[w], sizeof(unsigned long long) * h->meta_rows[w]));
+            CRB_CUDA(cudaMemsetAsync(h->alt.meta[w], 0, sizeof(unsigned long long) * h->meta_rows[w], s));
+            h->alt.meta_rows[w] = h->meta_rows[w];
+        }
+    }
+    return CRB_OK;
+}
+
 static void free_ws(crb_handle* h) {
+    if (h->alt_active) crb_alt_swap(h);
+    free_alt_ws(h);
     for (int k = 0; k < 4; ++k) { cudaFree(h->idx[k]); h->idx[k] = nullptr; }
     for (int k = 0; k < 3; ++k) { cudaFree(h->rank[k]); h->rank[k] = nullptr; }
     cudaFree(h->yv); h->yv = nullptr;
@@ -74,6 +138,14 @@ extern "C" int crb_destroy(crb_handle* h) {
     free_ws(h);
     cudaFree(h->meta[0]);
     cudaFree(h->meta[1]);
+    cudaFree(h->alt.meta[0]);
+    cudaFree(h->alt.meta[1]);
+    cudaFree(h->alt.ctr);
+    if (h->aux_stream) {
+        cudaStreamDestroy(h->aux_stream);
+        cudaEventDestroy(h->ev_entry);
+        for (int k = 0; k < 2; ++k) { cudaEventDestroy(h->ev_prep[k]); cudaEventDestroy(h->ev_done[k]); }
+    }
     cudaFree(h->ctr);
     cudaFree(h->block_loss);
     cudaFree(h->loss_dev);
@@ -110,6 +182,7 @@ extern "C" int crb_set_history(crb_handle* h, int64_t n_users, int64_t n_items, 
 }
 
 int crb_meta_reserve(crb_handle* h, int which, int64_t rows, cudaStream_t s) {
+    if (h->alt_active) crb_alt_swap(h);
     if (h->meta_rows[which] >= rows) return CRB_OK;
     CRB_CUDA(cudaStreamSynchronize(s));
     cudaFree(h->meta[which]);

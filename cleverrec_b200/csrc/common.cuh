@@ -110,6 +110,23 @@ struct crb_handle {
     void* np_sort_tmp;
     int64_t np_sort_cap;
     int64_t* np_result;
+    // Second copy of the sampling / assignment state of a step.  crb_train_epoch_bpr prepares step k+1 (K1 sampler+count, K2
+    // assign) on `aux_stream` into one copy while step k's K3/K4 consume the other; crb_alt_swap exchanges the pointers below
+    // with the handle's own (kernels receive the pointers by value at launch, so swapping between launches is safe).
+    struct {
+        int32_t* idx[3];
+        uint32_t* rank[3];
+        unsigned long long* meta[2];
+        int64_t meta_rows[2];
+        crb_step_ctr* ctr;
+        crb_dup_row* dup_rows;
+        crb_work* work;
+        unsigned int* multi;
+        int64_t cap_batch;
+    } alt;
+    int alt_active;          // 1 while the handle's fields hold the alternate copy
+    cudaStream_t aux_stream;
+    cudaEvent_t ev_entry, ev_prep[2], ev_done[2];
     // profiling hook
     int prof_on;
     int prof_n;          // event pairs recorded since last read
@@ -178,6 +195,8 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
 int crb_ws_reserve(crb_handle* h, int64_t batch, int32_t dim, int64_t steps, cudaStream_t s);
 int crb_meta_reserve(crb_handle* h, int which, int64_t rows, cudaStream_t s);
 int crb_eval_ws_reserve(crb_handle* h, int64_t bytes);
+int crb_alt_reserve(crb_handle* h, cudaStream_t s);   // allocate / resize the alternate step state to match the primary
+void crb_alt_swap(crb_handle* h);
 int crb_lrt_prepare(crb_handle* h, const crb_opt* opt, cudaStream_t s);
 int crb_launch_sample_pairwise(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t first, int64_t count, int32_t neg_ratio,
                                int32_t* u, int32_t* i, int32_t* j, int32_t* nbr, bool count_rows, cudaStream_t s);

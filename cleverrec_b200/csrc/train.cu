@@ -38,9 +38,11 @@ __global__ void __launch_bounds__(256) count_rows_kernel(RoleArgs a, int64_t bat
 __global__ void __launch_bounds__(256) assign_kernel(RoleArgs a, int64_t batch, crb_step_ctr* ctr, crb_dup_row* dup_rows,
                                                      crb_work* work, unsigned int* multi) {
     // One occurrence of every duplicated row has rank 1: it allocates the row's slot range, work items and partial rows.
-    // The five global counters are bumped once per warp (warp-aggregated), not once per row.
+    // The five global counters live in one 32-byte sector, so every atomic on them serialises in one L2 slice: they are
+    // bumped once per BLOCK (warp scan -> scan of the 8 warp totals -> one atomic per counter), not once per row or warp.
     if (a.n_dev && (int64_t)*a.n_dev < batch) batch = (int64_t)*a.n_dev;
-    const int lane = threadIdx.x & 31;
+    __shared__ uint32_t s_tot[8][5];    // per-warp totals, then per-warp exclusive bases (global)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t rounds = (batch + stride - 1) / stride;
     for (int64_t it = 0; it < rounds; ++it) {
@@ -49,8 +51,7 @@ __global__ void __launch_bounds__(256) assign_kernel(RoleArgs a, int64_t batch, 
         for (int r = 0; r < 3; ++r) {
             if (r >= a.n_roles) continue;
             const bool mine = t < batch && a.rank[r][t] == 1u;
-            const unsigned vote = __ballot_sync(0xffffffffu, mine);
-            if (!vote) continue;
+            if (!__syncthreads_or(mine)) continue;   // block-uniform
             int32_t row = 0;
             uint32_t c = 0, nch = 0;
             unsigned int* m = nullptr;
@@ -70,16 +71,21 @@ __global__ void __launch_bounds__(256) assign_kernel(RoleArgs a, int64_t batch, 
                 const uint32_t tm = __shfl_up_sync(0xffffffffu, sm, o);
                 if (lane >= o) { sc += tc; s1 += t1; sn += tn; sp += tp; sm += tm; }
             }
-            uint32_t bc = 0, b1 = 0, bn = 0, bp = 0, bm = 0;
-            if (lane == 31) {
-                bc = atomicAdd(&ctr->dup_slots, sc);
-                b1 = atomicAdd(&ctr->dup_rows, s1);
-                bn = atomicAdd(&ctr->work_items, sn);
-                if (sp) bp = atomicAdd(&ctr->partial_slots, sp);
-                if (sm) bm = atomicAdd(&ctr->multi_rows, sm);
+            if (lane == 31) { s_tot[wid][0] = sc; s_tot[wid][1] = s1; s_tot[wid][2] = sn; s_tot[wid][3] = sp; s_tot[wid][4] = sm; }
+            __syncthreads();
+            if (wid == 0 && lane < 5) {
+                // lane q owns counter q: exclusive prefix over the 8 warps, one atomic for the block
+                uint32_t pre[8], tot = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) { pre[w] = tot; tot += s_tot[w][lane]; }
+                unsigned int* cp = lane == 0 ? &ctr->dup_slots : lane == 1 ? &ctr->dup_rows : lane == 2 ? &ctr->work_items
+                                   : lane == 3 ? &ctr->partial_slots : &ctr->multi_rows;
+                const uint32_t gb = tot ? atomicAdd(cp, tot) : 0u;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) s_tot[w][lane] = gb + pre[w];
             }
-            bc = __shfl_sync(0xffffffffu, bc, 31); b1 = __shfl_sync(0xffffffffu, b1, 31); bn = __shfl_sync(0xffffffffu, bn, 31);
-            bp = __shfl_sync(0xffffffffu, bp, 31); bm = __shfl_sync(0xffffffffu, bm, 31);
+            __syncthreads();
+            const uint32_t bc = s_tot[wid][0], b1 = s_tot[wid][1], bn = s_tot[wid][2], bp = s_tot[wid][3], bm = s_tot[wid][4];
             if (mine) {
                 const uint32_t base = bc + sc - c, k = b1 + s1 - 1u, wb = bn + sn - nch, pb = bp + sp - pch;
                 m[1] = base;
@@ -89,6 +95,7 @@ __global__ void __launch_bounds__(256) assign_kernel(RoleArgs a, int64_t batch, 
                 dup_rows[k] = d;
                 for (uint32_t q = 0; q < nch; ++q) { crb_work w; w.dup = k; w.chunk = q; work[wb + q] = w; }
             }
+            __syncthreads();   // s_tot is reused by the next role / round
         }
     }
 }
@@ -176,33 +183,59 @@ __device__ __forceinline__ void sum_slots(float4* acc, const float* __restrict__
     }
 }
 
+// The optimizer apply of one duplicate row is split in two so that the row's own loads (w, slots, last) are in flight while
+// its gradient slots are being summed: dup_load issues them, dup_finish replays / applies / stores.
 template <int LANES, int VPL, int OPT>
-__device__ __forceinline__ void dup_apply(const DupArgs& a, const crb_dup_row& d, const float4* acc, int gl) {
+__device__ __forceinline__ void dup_load(RowRegs<LANES, VPL>& r, const DupArgs& a, const crb_dup_row& d, int gl) {
     const TableDev& T = a.tab[d.table];
-    RowRegs<LANES, VPL> r;
     row_load_w<LANES, VPL>(r, T, d.row, a.dim, gl);
     r.last = OptTraits<OPT>::replay ? T.last[d.row] : 0;
     row_load_state<LANES, VPL, OPT>(r, T, d.row, a.dim, gl);
+}
+
+template <int LANES, int VPL, int OPT>
+__device__ __forceinline__ void dup_finish(RowRegs<LANES, VPL>& r, const DupArgs& a, const crb_dup_row& d, const float4* acc, int gl) {
+    const TableDev& T = a.tab[d.table];
     row_replay<LANES, VPL, OPT>(r, a.opt, a.opt.step);
     row_apply_store<LANES, VPL, OPT>(r, acc, T, d.row, a.dim, gl, a.opt);
     if (gl == 0) a.meta[d.table][d.row] = 0ULL;
 }
 
 template <int LANES, int VPL, int OPT>
+__device__ __forceinline__ void dup_apply(const DupArgs& a, const crb_dup_row& d, const float4* acc, int gl) {
+    RowRegs<LANES, VPL> r;
+    dup_load<LANES, VPL, OPT>(r, a, d, gl);
+    dup_finish<LANES, VPL, OPT>(r, a, d, acc, gl);
+}
+
+// One lane group per work item (= one duplicate row, or one 256-slot chunk of a very frequent one).  The loop is software
+// pipelined: the next item's descriptors (work -> dup_rows, two dependent loads) are fetched while the current item's slots
+// and row are in flight, so a group's critical path per item is one memory round trip instead of four.
+template <int LANES, int VPL, int OPT>
 __global__ void __launch_bounds__(256) dup_reduce_kernel(DupArgs a) {
     const int gl = threadIdx.x % LANES;
     const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
     const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / LANES;
-    const uint32_t n_work = a.ctr->work_items;
-    for (int64_t k = group; k < n_work; k += n_groups) {
-        const crb_work w = a.work[k];
-        const crb_dup_row d = a.dup_rows[w.dup];
+    const int64_t n_work = a.ctr->work_items;
+    int64_t k = group;
+    if (k >= n_work) return;
+    crb_work w = a.work[k];
+    crb_dup_row d = a.dup_rows[w.dup];
+    while (true) {
+        const int64_t kn = k + n_groups;
+        const bool more = kn < n_work;
+        crb_work wn = w;
+        if (more) wn = a.work[kn];
         const uint32_t lo = d.base + w.chunk * CRB_DUP_CHUNK;
         const uint32_t hi = min(d.base + d.cnt, lo + CRB_DUP_CHUNK);
+        RowRegs<LANES, VPL> r;
+        if (d.nchunk == 1) dup_load<LANES, VPL, OPT>(r, a, d, gl);
         float4 acc[VPL];
         sum_slots<LANES, VPL>(acc, a.dup_grad, a.dup_t, lo, hi, d.cnt <= 32u, a.dim, gl);
+        crb_dup_row dn = d;
+        if (more) dn = a.dup_rows[wn.dup];
         if (d.nchunk == 1) {
-            dup_apply<LANES, VPL, OPT>(a, d, acc, gl);
+            dup_finish<LANES, VPL, OPT>(r, a, d, acc, gl);
         } else {
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
@@ -210,6 +243,8 @@ __global__ void __launch_bounds__(256) dup_reduce_kernel(DupArgs a) {
                 if (c < a.dim) st4(a.partial + (int64_t)(d.pbase + w.chunk) * a.dim + c, acc[v]);
             }
         }
+        if (!more) break;
+        k = kn; w = wn; d = dn;
     }
 }
 
@@ -486,10 +521,9 @@ static int finish_loss(crb_handle* h, double* loss_out, int64_t n, cudaStream_t 
     return CRB_OK;
 }
 
-// the part of one BPR step after the indices are on the device and (optionally) already counted
-static int bpr_step_device(crb_handle* h, const crb_table* P, const crb_table* Q, const OptDev& od, int opt_kind,
-                           const int32_t* u, const int32_t* i, const int32_t* j, int64_t batch, float reg, bool counted,
-                           double* loss_dev, cudaStream_t s) {
+// K2 (and K1's counting half when the sampler did not do it) of one BPR step: everything that depends only on the indices
+static int bpr_step_prepare(crb_handle* h, const int32_t* u, const int32_t* i, const int32_t* j, int64_t batch, bool counted,
+                            cudaStream_t s) {
     const int32_t* idx[3] = {u, i, j};
     const int role_table[3] = {0, 1, 1};
     int rc;
@@ -497,8 +531,14 @@ static int bpr_step_device(crb_handle* h, const crb_table* P, const crb_table* Q
         rc = crb_count_rows(h, batch, 3, idx, role_table, s);
         if (rc) return rc;
     }
-    rc = crb_launch_assign(h, batch, 3, idx, role_table, s);
-    if (rc) return rc;
+    return crb_launch_assign(h, batch, 3, idx, role_table, s);
+}
+
+// K3, K4, K5 of one BPR step (reads the state bpr_step_prepare left in the handle's current step set)
+static int bpr_step_compute(crb_handle* h, const crb_table* P, const crb_table* Q, const OptDev& od, int opt_kind,
+                            const int32_t* u, const int32_t* i, const int32_t* j, int64_t batch, float reg, double* loss_dev,
+                            cudaStream_t s) {
+    int rc;
     BprArgs a;
     a.P = crb_to_dev(P); a.Q = crb_to_dev(Q);
     a.metaU = h->meta[0]; a.metaI = h->meta[1];
@@ -519,6 +559,20 @@ static int bpr_step_device(crb_handle* h, const crb_table* P, const crb_table* Q
     rc = crb_launch_dup_pipeline(h, d, opt_kind, s);
     if (rc) return rc;
     return crb_launch_loss_final(h, loss_dev, s);
+}
+
+// the part of one BPR step after the indices are on the device and (optionally) already counted
+static int bpr_step_device(crb_handle* h, const crb_table* P, const crb_table* Q, const OptDev& od, int opt_kind,
+                           const int32_t* u, const int32_t* i, const int32_t* j, int64_t batch, float reg, bool counted,
+                           double* loss_dev, cudaStream_t s) {
+    int rc = bpr_step_prepare(h, u, i, j, batch, counted, s);
+    if (rc) return rc;
+    return bpr_step_compute(h, P, Q, od, opt_kind, u, i, j, batch, reg, loss_dev, s);
+}
+
+__global__ void merge_sampler_err_kernel(crb_step_ctr* into, crb_step_ctr* from) {
+    into->sampler_err += from->sampler_err;
+    from->sampler_err = 0;
 }
 
 int crb_zero_step_counters(crb_handle* h, cudaStream_t s) {
@@ -576,18 +630,46 @@ extern "C" int crb_train_epoch_bpr(crb_handle* h, const crb_table* P, const crb_
     CRB_CHECK_ARG(first >= 0 && first < rows, "first row outside the epoch");
     const bool host_loss = !(loss_out && crb_is_device_ptr(loss_out));
     crb_opt step_opt = *opt;
+    // Two copies of the sampling / assignment state: step k's K1 (sampler + row counts) and K2 (slot assignment) run on the
+    // auxiliary stream into copy k & 1 while step k-1's K3/K4 (the HBM-bound part) run on the caller's stream from the other
+    // copy.  K1/K2 never touch the tables, so the only ordering needed is: prepare(k) after compute(k-2) released the copy,
+    // compute(k) after prepare(k).
+    const bool overlap = n_steps > 1;
+    struct Restore { crb_handle* h; ~Restore() { if (h->alt_active) crb_alt_swap(h); } } restore{h};
+    cudaStream_t ps = s;
+    if (overlap) {
+        if ((rc = crb_alt_reserve(h, s))) return rc;
+        ps = h->aux_stream;
+        CRB_CUDA(cudaEventRecord(h->ev_entry, s));
+        CRB_CUDA(cudaStreamWaitEvent(ps, h->ev_entry, 0));
+    }
     for (int64_t k = 0; k < n_steps; ++k) {
         const int64_t lo = first + k * batch;
         if (lo >= rows) { crb_set_error("step %lld starts past the end of the epoch", (long long)k); return CRB_ERR_ARG; }
         const int64_t b = (rows - lo) < batch ? (rows - lo) : batch;
+        const int set = (int)(k & 1);
+        if (overlap && h->alt_active != set) crb_alt_swap(h);
         step_opt.step = opt->step + k;
         if ((rc = crb_opt_to_dev(h, &step_opt, &od, &opt_kind, s))) return rc;
-        if ((rc = crb_zero_step_counters(h, s))) return rc;
-        rc = crb_launch_sample_pairwise(h, seed, epoch, lo, b, neg_ratio, h->idx[0], h->idx[1], h->idx[2], nullptr, true, s);
+        if (overlap && k >= 2) CRB_CUDA(cudaStreamWaitEvent(ps, h->ev_done[set], 0));
+        if ((rc = crb_zero_step_counters(h, ps))) return rc;
+        rc = crb_launch_sample_pairwise(h, seed, epoch, lo, b, neg_ratio, h->idx[0], h->idx[1], h->idx[2], nullptr, true, ps);
         if (rc) return rc;
+        if ((rc = bpr_step_prepare(h, h->idx[0], h->idx[1], h->idx[2], b, true, ps))) return rc;
+        if (overlap) {
+            CRB_CUDA(cudaEventRecord(h->ev_prep[set], ps));
+            CRB_CUDA(cudaStreamWaitEvent(s, h->ev_prep[set], 0));
+        }
         double* ld = host_loss ? h->loss_dev + k : loss_out + k;
-        rc = bpr_step_device(h, P, Q, od, opt_kind, h->idx[0], h->idx[1], h->idx[2], b, reg, true, ld, s);
+        rc = bpr_step_compute(h, P, Q, od, opt_kind, h->idx[0], h->idx[1], h->idx[2], b, reg, ld, s);
         if (rc) return rc;
+        if (overlap) CRB_CUDA(cudaEventRecord(h->ev_done[set], s));
+    }
+    // the sampler's sticky error word lives in the step counters: fold the alternate copy's into the primary's
+    if (overlap) {
+        if (h->alt_active) crb_alt_swap(h);
+        merge_sampler_err_kernel<<<1, 1, 0, s>>>(h->ctr, h->alt.ctr);
+        CRB_CUDA(cudaGetLastError());
     }
     if (loss_out && host_loss) {
         rc = finish_loss(h, loss_out, n_steps, s);
