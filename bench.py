@@ -216,8 +216,7 @@ def run_ours(args, w):
         if sharded is None:
             eng.train_epoch_bpr(P, Q, opt, 7, 0, first_step * B, B, n, R, reg, losses)
         else:
-            for k in range(n):
-                sharded.step(reg, neg_ratio=R, seed=7, epoch=0, first=(first_step + k) * B, batch=B, loss_out=losses[k:k + 1])
+            sharded.run_steps(n, reg, neg_ratio=R, seed=7, epoch=0, first=first_step * B, batch=B, loss_out=losses)
 
     # ---- device-resident run: value ----
     losses = torch.zeros(steps_total, dtype=torch.float64, device=dev)
@@ -333,7 +332,7 @@ def run_ours(args, w):
             ems = float(t.item())
             flops = 2.0 * world * n_eval * items * dim
             ev = {"metric": "fullrank_top20_eval_users_per_sec", "value": world * n_eval / (ems / 1000.0), "unit": "users/s", "users": world * n_eval,
-                  "items": items, "ms": ems, "path": "bf16 tcgen05 per item shard + certified fp32 rescoring + merge at the owner",
+                  "items": items, "ms": ems, "path": "item shards all-gathered over NVLink once, then every rank ranks its own users: bf16 tcgen05 + certified fp32 rescoring",
                   "roofline": {"bound": "tensor", "achieved": flops / (ems / 1000.0) / 1e12 / world, "peak": tf, "unit": "TFLOP/s per GPU",
                                "frac": flops / (ems / 1000.0) / 1e12 / world / tf}}
         except Exception as e:

@@ -116,8 +116,11 @@ int crb_alt_reserve(crb_handle* h, cudaStream_t s) {
 }
 
 static void free_ws(crb_handle* h) {
+    if (h->aux_stream) cudaStreamSynchronize(h->aux_stream);
     if (h->alt_active) crb_alt_swap(h);
     free_alt_ws(h);
+    h->prep_valid = 0;
+    cudaFree(h->dup_src); h->dup_src = nullptr;
     for (int k = 0; k < 4; ++k) { cudaFree(h->idx[k]); h->idx[k] = nullptr; }
     for (int k = 0; k < 3; ++k) { cudaFree(h->rank[k]); h->rank[k] = nullptr; }
     cudaFree(h->yv); h->yv = nullptr;
@@ -213,6 +216,7 @@ int crb_ws_reserve(crb_handle* h, int64_t batch, int32_t dim, int64_t steps, cud
     CRB_CUDA(cudaMalloc(&h->yv, sizeof(float) * nb));
     CRB_CUDA(cudaMalloc(&h->dup_grad, sizeof(float) * occ * nd));
     CRB_CUDA(cudaMalloc(&h->dup_t, sizeof(uint32_t) * occ));
+    CRB_CUDA(cudaMalloc(&h->dup_src, sizeof(uint32_t) * occ));
     CRB_CUDA(cudaMalloc(&h->dup_rows, sizeof(crb_dup_row) * (occ / 2 + 1)));
     CRB_CUDA(cudaMalloc(&h->work, sizeof(crb_work) * (occ / 2 + occ / CRB_DUP_CHUNK + 2)));
     CRB_CUDA(cudaMalloc(&h->multi, sizeof(unsigned int) * (occ / CRB_DUP_CHUNK + 2)));

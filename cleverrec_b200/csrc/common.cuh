@@ -80,6 +80,7 @@ struct crb_handle {
     uint32_t* rank[3];     // occurrence rank of u, i, j inside their row
     float* dup_grad;       // [3*cap_batch, dim] gradient slots of duplicate occurrences
     uint32_t* dup_t;       // [3*cap_batch] triplet index of each slot (deterministic order)
+    uint32_t* dup_src;     // [3*cap_batch] source row of each slot when gradients are summed in place (DupArgs::dup_src)
     crb_dup_row* dup_rows; // [3*cap_batch]
     crb_work* work;        // [3*cap_batch]
     unsigned int* multi;   // [3*cap_batch / CRB_DUP_CHUNK + 1] indices of multi-chunk duplicate rows
@@ -125,6 +126,12 @@ struct crb_handle {
         int64_t cap_batch;
     } alt;
     int alt_active;          // 1 while the handle's fields hold the alternate copy
+    // a sharded step prepared ahead of time in the alternate copy (crb_shard_step_prepare)
+    int prep_valid;
+    uint64_t prep_seed;
+    uint32_t prep_epoch;
+    int64_t prep_first, prep_batch;
+    int32_t prep_neg_ratio;
     cudaStream_t aux_stream;
     cudaEvent_t ev_entry, ev_prep[2], ev_done[2];
     // profiling hook

@@ -207,11 +207,15 @@ struct DupArgs {
     const uint32_t* dup_t;
     float* partial;
     const crb_step_ctr* ctr;
+    // Optional indirection (multi-GPU inbox): slot q's gradient is row dup_src[q] of src_grad instead of row q of dup_grad, so
+    // gradients that already sit in a buffer are summed from where they are instead of being copied into slots first.
+    const uint32_t* dup_src = nullptr;
+    const float* src_grad = nullptr;
 };
 
 int crb_launch_dup_pipeline(crb_handle* h, const DupArgs& a, int opt_kind, cudaStream_t s);
 int crb_launch_assign(crb_handle* h, int64_t batch, int n_roles, const int32_t* const* idx, const int* role_table,
-                      cudaStream_t s, const unsigned int* n_dev = nullptr);
+                      cudaStream_t s, const unsigned int* n_dev = nullptr, bool every_row = false);
 int crb_count_rows(crb_handle* h, int64_t batch, int n_roles, const int32_t* const* idx, const int* role_table, cudaStream_t s,
                    const unsigned int* n_dev = nullptr);
 int crb_opt_to_dev(crb_handle* h, const crb_opt* opt, OptDev* out, int* opt_kind, cudaStream_t s);

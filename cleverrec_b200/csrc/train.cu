@@ -36,8 +36,9 @@ __global__ void __launch_bounds__(256) count_rows_kernel(RoleArgs a, int64_t bat
 }
 
 __global__ void __launch_bounds__(256) assign_kernel(RoleArgs a, int64_t batch, crb_step_ctr* ctr, crb_dup_row* dup_rows,
-                                                     crb_work* work, unsigned int* multi) {
+                                                     crb_work* work, unsigned int* multi, uint32_t alloc_rank) {
     // One occurrence of every duplicated row has rank 1: it allocates the row's slot range, work items and partial rows.
+    // (alloc_rank == 0 instead lets the FIRST occurrence allocate, i.e. every row gets a slot range -- the multi-GPU inbox.)
     // The five global counters live in one 32-byte sector, so every atomic on them serialises in one L2 slice: they are
     // bumped once per BLOCK (warp scan -> scan of the 8 warp totals -> one atomic per counter), not once per row or warp.
     if (a.n_dev && (int64_t)*a.n_dev < batch) batch = (int64_t)*a.n_dev;
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(256) assign_kernel(RoleArgs a, int64_t batch, 
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             if (r >= a.n_roles) continue;
-            const bool mine = t < batch && a.rank[r][t] == 1u;
+            const bool mine = t < batch && a.rank[r][t] == alloc_rank;
             if (!__syncthreads_or(mine)) continue;   // block-uniform
             int32_t row = 0;
             uint32_t c = 0, nch = 0;
@@ -126,7 +127,7 @@ int crb_count_rows(crb_handle* h, int64_t batch, int n_roles, const int32_t* con
 }
 
 int crb_launch_assign(crb_handle* h, int64_t batch, int n_roles, const int32_t* const* idx, const int* role_table, cudaStream_t s,
-                      const unsigned int* n_dev) {
+                      const unsigned int* n_dev, bool every_row) {
     RoleArgs a;
     a.n_roles = n_roles;
     a.n_dev = n_dev;
@@ -136,7 +137,7 @@ int crb_launch_assign(crb_handle* h, int64_t batch, int n_roles, const int32_t* 
         a.table[r] = r < n_roles ? role_table[r] : 0;
         a.meta[r] = h->meta[a.table[r]];
     }
-    assign_kernel<<<flat_grid(h, batch, 256), 256, 0, s>>>(a, batch, h->ctr, h->dup_rows, h->work, h->multi);
+    assign_kernel<<<flat_grid(h, batch, 256), 256, 0, s>>>(a, batch, h->ctr, h->dup_rows, h->work, h->multi, every_row ? 0u : 1u);
     h->launches++;
     CRB_CUDA(cudaGetLastError());
     return CRB_OK;
@@ -147,7 +148,7 @@ int crb_launch_assign(crb_handle* h, int64_t batch, int n_roles, const int32_t* 
 // are summed in ascending triplet order (deterministic); longer ones in slot order.
 template <int LANES, int VPL>
 __device__ __forceinline__ void sum_slots(float4* acc, const float* __restrict__ dup_grad, const uint32_t* __restrict__ dup_t,
-                                          uint32_t lo, uint32_t hi, bool ordered, int dim, int gl) {
+                                          const uint32_t* __restrict__ dup_src, uint32_t lo, uint32_t hi, bool ordered, int dim, int gl) {
 #pragma unroll
     for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ordered) {
@@ -164,7 +165,7 @@ __device__ __forceinline__ void sum_slots(float4* acc, const float* __restrict__
             for (int v = 0; v < VPL; ++v) {
                 int c = (gl + LANES * v) * 4;
                 if (c < dim) {
-                    float4 g = ld4(dup_grad + (int64_t)bs * dim + c);
+                    float4 g = ld4(dup_grad + (int64_t)(dup_src ? dup_src[bs] : bs) * dim + c);
                     acc[v].x += g.x; acc[v].y += g.y; acc[v].z += g.z; acc[v].w += g.w;
                 }
             }
@@ -175,7 +176,7 @@ __device__ __forceinline__ void sum_slots(float4* acc, const float* __restrict__
             for (int v = 0; v < VPL; ++v) {
                 int c = (gl + LANES * v) * 4;
                 if (c < dim) {
-                    float4 g = ld4(dup_grad + (int64_t)q * dim + c);
+                    float4 g = ld4(dup_grad + (int64_t)(dup_src ? dup_src[q] : q) * dim + c);
                     acc[v].x += g.x; acc[v].y += g.y; acc[v].z += g.z; acc[v].w += g.w;
                 }
             }
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(256) dup_reduce_kernel(DupArgs a) {
         RowRegs<LANES, VPL> r;
         if (d.nchunk == 1) dup_load<LANES, VPL, OPT>(r, a, d, gl);
         float4 acc[VPL];
-        sum_slots<LANES, VPL>(acc, a.dup_grad, a.dup_t, lo, hi, d.cnt <= 32u, a.dim, gl);
+        sum_slots<LANES, VPL>(acc, a.dup_src ? a.src_grad : a.dup_grad, a.dup_t, a.dup_src, lo, hi, d.cnt <= 32u, a.dim, gl);
         crb_dup_row dn = d;
         if (more) dn = a.dup_rows[wn.dup];
         if (d.nchunk == 1) {

@@ -155,48 +155,30 @@ __global__ void __launch_bounds__(256, 3) shard_step_kernel(ShardStepArgs a) {
 }
 
 struct InboxArgs {
-    TableDev Q;
     unsigned long long* meta;
-    const float* grad;
     const int32_t* row;
     const uint32_t* key;
     const unsigned int* cnt;
     const uint32_t* rk;
     int64_t cap;
-    int dim;
-    OptDev opt;
-    float* dup_grad;
+    uint32_t* dup_src;
     uint32_t* dup_t;
 };
 
-template <int LANES, int VPL, int OPT>
-__global__ void __launch_bounds__(256, 3) inbox_apply_kernel(InboxArgs a) {
-    constexpr int GPW = 32 / LANES;
-    const int lane = threadIdx.x & 31, gl = lane % LANES, sub = lane / LANES;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+// Phase 2 never copies a gradient: every row that received at least one gradient owns a slot range (assign_kernel with
+// alloc_rank 0), this kernel -- one thread per inbox entry -- only records WHERE the row's gradients are (slot -> inbox entry, plus
+// the ordering key), and dup_reduce_kernel sums them straight out of the inbox (DupArgs::dup_src) in key order and applies the
+// optimizer once per row.  A gradient that crossed NVLink is read from HBM exactly once.
+__global__ void __launch_bounds__(256) inbox_index_kernel(InboxArgs a) {
     int64_t n = *a.cnt;
     if (n > a.cap) n = a.cap;
-    for (int64_t base = warp * GPW; base < n; base += n_warps * GPW) {
-        const int64_t e = base + sub;
-        if (e >= n) continue;   // no warp-wide shuffles below
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
         const int32_t row = a.row[e];
         if (row < 0) continue;   // hole of a partly used reservation
-        const unsigned long long m = a.meta[row];
-        RowRegs<LANES, VPL> r;
-        row_load_w<LANES, VPL>(r, a.Q, row, a.dim, gl);
-        r.last = OptTraits<OPT>::replay ? a.Q.last[row] : 0;
-        const bool single = (uint32_t)m == 1u;
-        if (OptTraits<OPT>::has_s1 && single) row_load_state<LANES, VPL, OPT>(r, a.Q, row, a.dim, gl);
-        if (single && replay_pending<OPT>(r.last, a.opt)) row_replay<LANES, VPL, OPT>(r, a.opt, a.opt.step);
-        float4 g[VPL];
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-            const int c = (gl + LANES * v) * 4;
-            g[v] = c < a.dim ? ld4(a.grad + e * a.dim + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        const uint32_t key = a.key[e];
-        emit_row<LANES, VPL, OPT>(r, g, a.Q, a.meta, row, m, a.rk[e], key >> 2, key & 3u, a.dim, gl, a.opt, a.dup_grad, a.dup_t);
+        const uint32_t slot = (uint32_t)(a.meta[row] >> 32) + a.rk[e];
+        a.dup_src[slot] = (uint32_t)e;
+        a.dup_t[slot] = a.key[e];
     }
 }
 
@@ -242,22 +224,6 @@ static int launch_shard_t(crb_handle* h, const ShardStepArgs& a, int opt_kind, c
     return CRB_OK;
 }
 
-template <int LANES, int VPL>
-static int launch_inbox_t(crb_handle* h, const InboxArgs& a, int opt_kind, cudaStream_t s) {
-    const int gpb = 256 / LANES;
-#define CRB_IN_CASE(O)                                                                          \
-    case O: {                                                                                   \
-        const int grid = one_wave(h, inbox_apply_kernel<LANES, VPL, O>, a.cap, gpb);            \
-        inbox_apply_kernel<LANES, VPL, O><<<grid, 256, 0, s>>>(a);                              \
-        break;                                                                                  \
-    }
-    switch (opt_kind) { CRB_IN_CASE(OPT_SGD) CRB_IN_CASE(OPT_ADAGRAD) CRB_IN_CASE(OPT_ADAM_LAZY) CRB_IN_CASE(OPT_ADAM_TF1) }
-#undef CRB_IN_CASE
-    h->launches++;
-    CRB_CUDA(cudaGetLastError());
-    return CRB_OK;
-}
-
 #define CRB_DIM_DISPATCH(dim, FN, ...)                                   \
     ((dim) <= 32 ? FN<8, 1>(__VA_ARGS__)                                 \
      : (dim) <= 64 ? FN<16, 1>(__VA_ARGS__)                              \
@@ -271,6 +237,38 @@ static void fill_dup(crb_handle* h, DupArgs* d, const TableDev& t0, const TableD
     d->dim = dim; d->opt = od;
     d->dup_rows = h->dup_rows; d->work = h->work; d->multi = h->multi;
     d->dup_grad = h->dup_grad; d->dup_t = h->dup_t; d->partial = h->partial; d->ctr = h->ctr;
+}
+
+// Optional phase 0: sample rows [first, first+batch) of this rank's epoch and count / assign the user rows NOW, on the handle's
+// auxiliary stream, into the alternate copy of the step state -- typically called right after crb_shard_step_compute of the
+// previous step, so that it overlaps that step's barriers and inbox phase (none of it touches the tables).  The next
+// crb_shard_step_compute with u == NULL and the same (seed, epoch, first, neg_ratio, batch) consumes it.  reserve_rows >= batch
+// sizes the workspace once for both phases (pass the inbox capacity) so that no later call reallocates it under the prepared step.
+extern "C" int crb_shard_step_prepare(crb_handle* h, const crb_table* P, uint64_t seed, uint32_t epoch, int64_t first, int32_t neg_ratio,
+                                      int64_t batch, int64_t reserve_rows, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    CRB_CHECK_ARG(h && P, "null argument");
+    CRB_CHECK_ARG(batch > 0, "batch");
+    CRB_CUDA(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = crb_ws_reserve(h, reserve_rows > batch ? reserve_rows : batch, P->dim, 4, s))) return rc;
+    if ((rc = crb_meta_reserve(h, 0, P->rows, s))) return rc;
+    if ((rc = crb_alt_reserve(h, s))) return rc;
+    cudaStream_t ps = h->aux_stream;
+    // the alternate copy is free once the last compute that used it has finished; a freshly zeroed meta needs the caller's stream
+    CRB_CUDA(cudaEventRecord(h->ev_entry, s));
+    CRB_CUDA(cudaStreamWaitEvent(ps, h->ev_entry, 0));
+    crb_alt_swap(h);
+    struct Restore { crb_handle* h; ~Restore() { if (h->alt_active) crb_alt_swap(h); } } restore{h};
+    if ((rc = crb_zero_step_counters(h, ps))) return rc;
+    if ((rc = crb_launch_sample_pairwise(h, seed, epoch, first, batch, neg_ratio, h->idx[0], h->idx[1], h->idx[2], nullptr, false, ps))) return rc;
+    const int32_t* idx[3] = {h->idx[0], nullptr, nullptr};
+    const int role_table[3] = {0, 0, 0};
+    if ((rc = crb_count_rows(h, batch, 1, idx, role_table, ps))) return rc;
+    if ((rc = crb_launch_assign(h, batch, 1, idx, role_table, ps))) return rc;
+    CRB_CUDA(cudaEventRecord(h->ev_prep[1], ps));
+    h->prep_valid = 1; h->prep_seed = seed; h->prep_epoch = epoch; h->prep_first = first; h->prep_batch = batch; h->prep_neg_ratio = neg_ratio;
+    return CRB_OK;
 }
 
 // phase 1.  u: local user rows, i/j: global item ids (DEVICE or HOST); or u == NULL: sample rows [first, first+batch) of this rank's
@@ -292,9 +290,18 @@ extern "C" int crb_shard_step_compute(crb_handle* h, const crb_table* P, const c
     CRB_CUDA(cudaSetDevice(h->device));
     if ((rc = crb_ws_reserve(h, batch, P->dim, 4, s))) return rc;
     if ((rc = crb_meta_reserve(h, 0, P->rows, s))) return rc;
-    if ((rc = crb_zero_step_counters(h, s))) return rc;
+    const bool prepared = !u && h->prep_valid && h->prep_seed == seed && h->prep_epoch == epoch && h->prep_first == first &&
+                          h->prep_batch == batch && h->prep_neg_ratio == neg_ratio;
+    struct Restore { crb_handle* h; ~Restore() { if (h->alt_active) crb_alt_swap(h); } } restore{h};
+    if (prepared) {
+        h->prep_valid = 0;
+        CRB_CUDA(cudaStreamWaitEvent(s, h->ev_prep[1], 0));
+        crb_alt_swap(h);   // K3 / K4 / K5 below read the prepared copy
+    } else if ((rc = crb_zero_step_counters(h, s))) return rc;
     const int32_t *du = u, *di = i, *dj = j;
-    if (!u) {
+    if (prepared) {
+        du = h->idx[0]; di = h->idx[1]; dj = h->idx[2];
+    } else if (!u) {
         if ((rc = crb_launch_sample_pairwise(h, seed, epoch, first, batch, neg_ratio, h->idx[0], h->idx[1], h->idx[2], nullptr, false, s))) return rc;
         du = h->idx[0]; di = h->idx[1]; dj = h->idx[2];
     } else {
@@ -305,8 +312,10 @@ extern "C" int crb_shard_step_compute(crb_handle* h, const crb_table* P, const c
     }
     const int32_t* idx[3] = {du, nullptr, nullptr};
     const int role_table[3] = {0, 0, 0};
-    if ((rc = crb_count_rows(h, batch, 1, idx, role_table, s))) return rc;
-    if ((rc = crb_launch_assign(h, batch, 1, idx, role_table, s))) return rc;
+    if (!prepared) {
+        if ((rc = crb_count_rows(h, batch, 1, idx, role_table, s))) return rc;
+        if ((rc = crb_launch_assign(h, batch, 1, idx, role_table, s))) return rc;
+    }
     a.P = crb_to_dev(P); a.metaU = h->meta[0]; a.u = du; a.i = di; a.j = dj; a.rk_u = h->rank[0];
     a.batch = batch; a.dim = P->dim; a.reg = reg; a.opt = od; a.dup_grad = h->dup_grad; a.dup_t = h->dup_t; a.block_loss = h->block_loss;
     if ((rc = crb_prof_begin(h, s))) return rc;
@@ -345,13 +354,20 @@ extern "C" int crb_shard_apply_inbox(crb_handle* h, const crb_shard* shard, cons
     const int32_t* idx[3] = {sd.inbox_row[r], nullptr, nullptr};
     const int role_table[3] = {1, 0, 0};
     if ((rc = crb_count_rows(h, cap, 1, idx, role_table, s, sd.inbox_cnt[r]))) return rc;
-    if ((rc = crb_launch_assign(h, cap, 1, idx, role_table, s, sd.inbox_cnt[r]))) return rc;
+    if ((rc = crb_launch_assign(h, cap, 1, idx, role_table, s, sd.inbox_cnt[r], /*every_row=*/true))) return rc;
     InboxArgs a;
-    a.Q = sd.q[r]; a.meta = h->meta[1]; a.grad = sd.inbox_grad[r]; a.row = sd.inbox_row[r]; a.key = sd.inbox_key[r]; a.cnt = sd.inbox_cnt[r];
-    a.rk = h->rank[0]; a.cap = cap; a.dim = Q->dim; a.opt = od; a.dup_grad = h->dup_grad; a.dup_t = h->dup_t;
-    if ((rc = CRB_DIM_DISPATCH(a.dim, launch_inbox_t, h, a, opt_kind, s))) return rc;
+    a.meta = h->meta[1]; a.row = sd.inbox_row[r]; a.key = sd.inbox_key[r]; a.cnt = sd.inbox_cnt[r];
+    a.rk = h->rank[0]; a.cap = cap; a.dup_src = h->dup_src; a.dup_t = h->dup_t;
+    {
+        int64_t blocks = (cap + 255) / 256, capb = (int64_t)h->sm_count * 16;
+        inbox_index_kernel<<<(int)(blocks < capb ? blocks : capb), 256, 0, s>>>(a);
+        h->launches++;
+        CRB_CUDA(cudaGetLastError());
+    }
     DupArgs d;
-    fill_dup(h, &d, a.Q, a.Q, a.dim, od);
+    fill_dup(h, &d, sd.q[r], sd.q[r], Q->dim, od);
+    d.dup_src = h->dup_src;
+    d.src_grad = sd.inbox_grad[r];
     if ((rc = crb_launch_dup_pipeline(h, d, opt_kind, s))) return rc;
     // CRB_ADAM_TF1: bring every row of the shard to this step (rows not touched now take their decay-only step), so that the next
     // step's readers -- local or over NVLink -- never need a row's `last` (a dependent 4-byte peer load cost 2.3 ms per step)

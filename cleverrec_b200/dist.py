@@ -154,6 +154,29 @@ class ShardedBPR(object):
         self.barrier()
         return float(host[0]) if loss_out is None else None
 
+    def run_steps(self, n_steps, reg, neg_ratio, seed, epoch, first, batch=None, loss_out=None):
+        """n synchronous steps over consecutive batches of this rank's epoch, sampled on the device.  Step k+1's index work
+        (sampler, user-row counting and slot assignment) is prepared on the engine's auxiliary stream while step k's barriers and
+        inbox phase run (crb_shard_step_prepare).  loss_out: device float64 [n_steps] or None."""
+        eng, lib = self.engine, self.engine.lib
+        batch = self.batch if batch is None else batch
+
+        def prepare(k):
+            check(lib.crb_shard_step_prepare(eng.h, C.byref(self.P.c), seed, epoch, first + k * batch, neg_ratio, batch, self.inbox_cap, eng.stream))
+        prepare(0)
+        host = np.zeros(1, dtype=np.float64)
+        for k in range(n_steps):
+            self.opt.t += 1
+            co = self.opt.c(self.opt.t)
+            lo = ptr(host) if loss_out is None else ptr(loss_out[k:k + 1])
+            check(lib.crb_shard_step_compute(eng.h, C.byref(self.P.c), C.byref(self.shard), C.byref(co), None, None, None, seed, epoch,
+                                             first + k * batch, neg_ratio, batch, float(reg), lo, eng.stream))
+            if k + 1 < n_steps:
+                prepare(k + 1)
+            self.barrier()
+            check(lib.crb_shard_apply_inbox(eng.h, C.byref(self.shard), C.byref(co), eng.stream))
+            self.barrier()
+
     def inbox_overflowed(self):
         v = C.c_int32()
         check(self.engine.lib.crb_shard_inbox_overflow(self.engine.h, C.byref(self.shard), C.byref(v), self.engine.stream))
@@ -246,21 +269,45 @@ def merge_topk(ids_per_rank, scores_per_rank, K, ascending=False):
 
 
 class ShardedEval(object):
-    """Full-rank top-K of this rank's users against the row-sharded item table (test_model_rs across ranks): the users' vectors are
-    broadcast batch by batch, every rank ranks them against ITS item shard with the single-GPU kernels (crb_score_topk, seen items
-    masked from the transposed history), and the G x K candidates per user are merged at the user's owner."""
+    """Full-rank top-K of this rank's users (test_model_rs across ranks).  Two layouts:
 
-    def __init__(self, model, seen_rowptr, seen_cols, kind=_lib.SCORE_DOT):
-        self.m, self.kind = model, kind
+    mode="replicate" (default): the item shards are all-gathered once per evaluation into a full copy of Q on every rank
+        (2M x 128 fp32 = 1 GB, a few ms over NVLink) and every rank ranks ITS OWN users with the single-GPU tensor-core path
+        against its own history CSR.  No per-batch collective, no merge; throughput scales with the number of ranks, and the ids
+        are those of the single-GPU path by construction.
+    mode="shard": for catalogues that do not fit one GPU.  The users' vectors are broadcast batch by batch, every rank ranks
+        them against ITS item shard (seen items masked from the transposed history), and the G x K candidates per user are merged
+        at the user's owner."""
+
+    def __init__(self, model, seen_rowptr, seen_cols, kind=_lib.SCORE_DOT, mode="replicate"):
+        assert mode in ("replicate", "shard")
+        self.m, self.kind, self.mode = model, kind, mode
         self.world, self.rank = model.world, model.rank
         dev = model.engine.device
+        if mode == "replicate":
+            self.eng = None   # the model's own engine already holds this rank's history (local user rows, global item ids)
+            return
         rowptr, cols = transpose_history(seen_rowptr.to(dev), seen_cols.to(dev), model.u_lo, model.n_users, self.world, self.rank, model.group)
         self.eng = Engine(dev.index)   # a second handle on the same device: its history is the transposed one
         pu = torch.zeros(1, dtype=torch.int32, device=dev)
         self.eng.set_history_arrays(model.n_users, model.q_rows, pu[:0], pu[:0], rowptr, cols)
 
+    def _topk_replicated(self, K, batch_users, exact, limit):
+        m, dev = self.m, self.m.engine.device
+        Qfull = m.gather_Q()   # flushes pending Adam decay, then one all-gather
+        m.engine.adam_flush(m.P, m.opt)
+        n = m.u_hi - m.u_lo if limit is None else min(m.u_hi - m.u_lo, limit)
+        out = torch.full((m.u_hi - m.u_lo, K), -1, dtype=torch.int32, device=dev)
+        for a in range(0, n, batch_users):
+            b = min(n, a + batch_users)
+            users = torch.arange(a, b, dtype=torch.int32, device=dev)
+            out[a:b] = m.engine.score_topk(self.kind, m.P.w, Qfull, users, K, exact=exact)
+        return out
+
     def topk(self, K, batch_users=1 << 16, exact=False, limit=None):
         """limit: evaluate only the first `limit` users of every rank (benchmarks)."""
+        if self.mode == "replicate":
+            return self._topk_replicated(K, batch_users, exact, limit)
         m, dev = self.m, self.m.engine.device
         m.flush()
         out = torch.full((m.u_hi - m.u_lo, K), -1, dtype=torch.int32, device=dev)

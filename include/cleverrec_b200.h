@@ -245,6 +245,12 @@ int crb_score_nais(crb_handle* h, const float* P, const float* Q, const float* b
 int crb_shard_step_compute(crb_handle* h, const crb_table* P, const crb_shard* shard, const crb_opt* opt, const int32_t* u,
                            const int32_t* i, const int32_t* j, uint64_t seed, uint32_t epoch, int64_t first, int32_t neg_ratio,
                            int64_t batch, float reg, double* loss_out, void* stream);
+/* Optional phase 0 of the NEXT step: sample rows [first, first+batch) and count / assign the user rows on the handle's auxiliary
+ * stream, so that this index-only work (utils/sampler.py:46-74 + the feed slicing of RankingRecommender.py:38-46) overlaps the
+ * current step's barriers and inbox phase.  Consumed by the next crb_shard_step_compute with u == NULL and the same
+ * (seed, epoch, first, neg_ratio, batch).  reserve_rows >= batch sizes the workspace once for both phases (the inbox capacity). */
+int crb_shard_step_prepare(crb_handle* h, const crb_table* P, uint64_t seed, uint32_t epoch, int64_t first, int32_t neg_ratio,
+                           int64_t batch, int64_t reserve_rows, void* stream);
 /* phase 2: de-duplicate this rank's inbox, one optimizer apply per unique item row with the gradient summed over all ranks. */
 int crb_shard_apply_inbox(crb_handle* h, const crb_shard* shard, const crb_opt* opt, void* stream);
 int crb_shard_inbox_overflow(crb_handle* h, const crb_shard* shard, int32_t* overflowed, void* stream);

@@ -74,8 +74,8 @@ def main():
     for step in range(3):   # device-sampled steps
         m.step(0.01, neg_ratio=2, seed=9, epoch=0, first=step * 64, batch=64)
     _, _, rp, sc = history_from_dict(mine, n_local)
-    for exact in (True, False):
-        ev = ShardedEval(m, torch.from_numpy(rp), torch.from_numpy(sc))
+    for exact, mode in ((True, "shard"), (False, "shard"), (True, "replicate"), (False, "replicate")):
+        ev = ShardedEval(m, torch.from_numpy(rp), torch.from_numpy(sc), mode=mode)
         got = ev.topk(10, batch_users=20, exact=exact)
         Qfull = m.gather_Q()
         Pparts = [torch.zeros(user_range(U, r, world)[1] - user_range(U, r, world)[0], d, device="cuda") for r in range(world)]
@@ -87,10 +87,28 @@ def main():
         ref_eng.set_history(data.ui_train, U, I)
         want = ref_eng.score_topk(0, torch.cat(Pparts), Qfull, torch.arange(lo, hi, dtype=torch.int32, device="cuda"), 10, exact=True)
         if not torch.equal(got, want):
-            print("EVAL MISMATCH rank", rank, "exact", exact, int((got != want).sum()))
+            print("EVAL MISMATCH rank", rank, "exact", exact, mode, int((got != want).sum()))
             ok = False
         ref_eng.close()
     m.close()
+    # ---- run_steps (next step's sampling / counting prepared on the auxiliary stream) == the same steps one by one
+    outs = []
+    for pipelined in (False, True):
+        m = ShardedBPR(eng, U, I, d, "Adam", 0.01, "tf1", 64, init_P=P0[lo:hi], init_Q=Q0)
+        m.set_history(mine, n_local)
+        losses = torch.zeros(5, dtype=torch.float64, device="cuda")
+        if pipelined:
+            m.run_steps(5, 0.01, neg_ratio=2, seed=9, epoch=0, first=0, batch=64, loss_out=losses)
+        else:
+            for step in range(5):
+                m.step(0.01, neg_ratio=2, seed=9, epoch=0, first=step * 64, batch=64, loss_out=losses[step:step + 1])
+        m.flush()
+        outs.append((losses.cpu().numpy().copy(), m.P.w.cpu().numpy().copy(), m.gather_Q().cpu().numpy().copy()))
+        m.close()
+    for k, name in enumerate(("loss", "P", "Q")):
+        if not np.allclose(outs[0][k], outs[1][k], rtol=1e-6, atol=1e-8):
+            print("RUN_STEPS MISMATCH rank", rank, name, float(np.abs(outs[0][k] - outs[1][k]).max()))
+            ok = False
     # device-sampled path runs and stays finite
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
