@@ -12,6 +12,7 @@
 //                                the gradient summed over ALL ranks -- the semantics of one TF step on the union batch.
 //   -- barrier --
 #include <cstddef>
+#include <stdlib.h>
 
 #include "rowopt.cuh"
 
@@ -40,6 +41,7 @@ struct ShardStepArgs {
     float* dup_grad;
     uint32_t* dup_t;
     double* block_loss;
+    int debug;   // experiments only (CRB_SH_DEBUG): 1 = no gradient sends, 2 = item rows read from the local shard, 3 = both
 };
 
 #define SH_CHUNK 32u   // inbox slots a warp reserves per system-scope atomic (unused ones stay holes: row = -1)
@@ -82,37 +84,48 @@ __global__ void __launch_bounds__(256, 3) shard_step_kernel(ShardStepArgs a) {
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int G = a.sh.n_ranks;
+    const int RG = (a.debug & 2) ? 1 : G;              // debug: every read goes to the local shard
+    const int RO = (a.debug & 2) ? a.sh.rank : 0;
+#define SH_Q(item) a.sh.q[(a.debug & 2) ? RO : (item) % RG]
     __shared__ unsigned int s_resv[8][2][CRB_MAX_RANKS];   // per warp: next slot / slots left of the current reservation per owner
     if (lane < CRB_MAX_RANKS) { s_resv[threadIdx.x >> 5][0][lane] = 0u; s_resv[threadIdx.x >> 5][1][lane] = 0u; }
     __syncwarp();
     unsigned int* s_base = s_resv[threadIdx.x >> 5][0];
     unsigned int* s_left = s_resv[threadIdx.x >> 5][1];
     double loss_acc = 0.0;
-    // Software pipeline: indices two iterations ahead, embedding rows one iteration ahead -- the (remote) row loads of triplet
-    // n+1 are in flight while triplet n is computed and stored.  Out-of-range iterations clamp to the last triplet (loads only).
+    // Software pipeline.  Item rows mostly live on other GPUs (2-3 us away over NVLink), so they are requested TWO iterations ahead;
+    // the local user row one iteration ahead; indices three iterations ahead.  Out-of-range iterations clamp to the last triplet
+    // (loads only).
     const int64_t stride = n_warps * GPW;
     const int64_t base0 = warp * GPW;
     auto clampt = [&](int64_t b) { const int64_t t_ = b + sub; return t_ < a.batch ? t_ : a.batch - 1; };
-    int32_t nu, ni, nj;          // indices of the next iteration
-    int32_t fu, fi, fj;          // indices two iterations ahead
+    int32_t u1, i1, j1;          // indices of iteration n+1 (its item rows are in flight, its user row is about to be)
+    int32_t u2, i2, j2;          // indices of iteration n+2
+    int32_t nu, ni, nj;          // indices of the current iteration
     { const int64_t t0 = clampt(base0); nu = a.u[t0]; ni = a.i[t0]; nj = a.j[t0]; }
-    { const int64_t t1 = clampt(base0 + stride); fu = a.u[t1]; fi = a.i[t1]; fj = a.j[t1]; }
-    RowRegs<LANES, VPL> nru, nri, nrj;
+    { const int64_t t1 = clampt(base0 + stride); u1 = a.u[t1]; i1 = a.i[t1]; j1 = a.j[t1]; }
+    { const int64_t t2 = clampt(base0 + 2 * stride); u2 = a.u[t2]; i2 = a.i[t2]; j2 = a.j[t2]; }
+    RowRegs<LANES, VPL> nru, nri, nrj, fri, frj;
+    row_load_w<LANES, VPL>(nri, SH_Q(ni), ni / G, a.dim, gl);
+    row_load_w<LANES, VPL>(nrj, SH_Q(nj), nj / G, a.dim, gl);
+    row_load_w<LANES, VPL>(fri, SH_Q(i1), i1 / G, a.dim, gl);
+    row_load_w<LANES, VPL>(frj, SH_Q(j1), j1 / G, a.dim, gl);
     row_load_w<LANES, VPL>(nru, a.P, nu, a.dim, gl);
-    row_load_w<LANES, VPL>(nri, a.sh.q[ni % G], ni / G, a.dim, gl);
-    row_load_w<LANES, VPL>(nrj, a.sh.q[nj % G], nj / G, a.dim, gl);
     for (int64_t base = base0; base < a.batch; base += stride) {
         const int64_t t = base + sub;
         const bool active = t < a.batch;
         const int64_t tt = active ? t : a.batch - 1;
         const int32_t u = nu, i = ni, j = nj;
         RowRegs<LANES, VPL> ru = nru, ri = nri, rj = nrj;
-        // issue the next iteration's row loads and the indices after that
-        nu = fu; ni = fi; nj = fj;
+        // rotate the pipeline: iteration n+1's item rows were requested last time; request n+2's (peer loads when the owner is
+        // another rank) and n+1's user row
+        nu = u1; ni = i1; nj = j1;
+        nri = fri; nrj = frj;
         row_load_w<LANES, VPL>(nru, a.P, nu, a.dim, gl);
-        row_load_w<LANES, VPL>(nri, a.sh.q[ni % G], ni / G, a.dim, gl);   // peer load when the owner is another rank
-        row_load_w<LANES, VPL>(nrj, a.sh.q[nj % G], nj / G, a.dim, gl);
-        { const int64_t t2 = clampt(base + 2 * stride); fu = a.u[t2]; fi = a.i[t2]; fj = a.j[t2]; }
+        row_load_w<LANES, VPL>(fri, SH_Q(i2), i2 / G, a.dim, gl);
+        row_load_w<LANES, VPL>(frj, SH_Q(j2), j2 / G, a.dim, gl);
+        u1 = u2; i1 = i2; j1 = j2;
+        { const int64_t t3 = clampt(base + 3 * stride); u2 = a.u[t3]; i2 = a.i[t3]; j2 = a.j[t3]; }
         const int oi = i % G, oj = j % G;
         const int32_t li = i / G, lj = j / G;
         const unsigned long long mu = a.metaU[u];
@@ -147,8 +160,10 @@ __global__ void __launch_bounds__(256, 3) shard_step_kernel(ShardStepArgs a) {
             emit_row<LANES, VPL, OPT>(ru, gu, a.P, a.metaU, u, mu, a.rk_u[t], (uint32_t)t, 0u, a.dim, gl, a.opt, a.dup_grad, a.dup_t);
         // ordering key of the occurrence: unique and identical from run to run -> deterministic duplicate sums at the owner
         const uint32_t kbase = ((uint32_t)a.sh.rank * (uint32_t)a.batch + (uint32_t)tt) << 1;
-        send_item_grad<LANES, VPL>(a.sh, s_base, s_left, oi, li, kbase, gi, a.dim, gl, sub, active);
-        send_item_grad<LANES, VPL>(a.sh, s_base, s_left, oj, lj, kbase | 1u, gj, a.dim, gl, sub, active);
+        if (!(a.debug & 1)) {
+            send_item_grad<LANES, VPL>(a.sh, s_base, s_left, oi, li, kbase, gi, a.dim, gl, sub, active);
+            send_item_grad<LANES, VPL>(a.sh, s_base, s_left, oj, lj, kbase | 1u, gj, a.dim, gl, sub, active);
+        }
     }
     __threadfence_system();   // peer stores visible before the kernel retires (the barrier that follows orders them across ranks)
     block_loss_store(loss_acc, a.block_loss);
@@ -318,6 +333,7 @@ extern "C" int crb_shard_step_compute(crb_handle* h, const crb_table* P, const c
     }
     a.P = crb_to_dev(P); a.metaU = h->meta[0]; a.u = du; a.i = di; a.j = dj; a.rk_u = h->rank[0];
     a.batch = batch; a.dim = P->dim; a.reg = reg; a.opt = od; a.dup_grad = h->dup_grad; a.dup_t = h->dup_t; a.block_loss = h->block_loss;
+    a.debug = getenv("CRB_SH_DEBUG") ? atoi(getenv("CRB_SH_DEBUG")) : 0;
     if ((rc = crb_prof_begin(h, s))) return rc;
     if ((rc = CRB_DIM_DISPATCH(a.dim, launch_shard_t, h, a, opt_kind, s))) return rc;
     if ((rc = crb_prof_end(h, s))) return rc;
