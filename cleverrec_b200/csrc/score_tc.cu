@@ -63,32 +63,42 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same MMA with the two shared-memory descriptors given as (low word, common high word): the high word (SBO, version, swizzle
+// mode) never changes and the low word (start address >> 4, LBO) moves by a compile-time constant from one MMA to the next, so
+// the issuing loop is one add per operand instead of rebuilding two 64-bit descriptors (21 SASS instructions per MMA before).
+__device__ __forceinline__ void umma_bf16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Asynchronous TMEM load of 32 consecutive columns of this thread's lane (issue only) ...
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
+// TMEM load of 32 consecutive fp32 columns of this thread's lane, and the wait that makes the registers valid (one asm block:
+// the compiler must not schedule a use between the two).
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+          "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]),
+          "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]),
+          "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
         : "r"(taddr)
         : "memory");
-}
-// ... and the wait that makes the registers valid.  They are passed as in/out operands so that the compiler cannot schedule a
-// use of them above the wait.
-__device__ __forceinline__ void tmem_ld32_wait(uint32_t* r) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
-                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
-                   "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
-                   "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-                 :
-                 : "memory");
 }
 
 // K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4, LBO (unused
@@ -177,7 +187,7 @@ struct TcArgs {
     unsigned long long* cand;   // [n_splits, n_users_pad, TC_C]  (approx score bits << 32 | item)
     int32_t* cand_cnt;          // [n_splits, n_users_pad]
     float* cand_thr;            // [n_splits, n_users_pad]
-    int debug;                  // experiments only (CRB_TC_DEBUG): 1 = read TMEM but skip the scan, 2 = skip the TMEM read too
+    int debug;                  // experiments only (-DTC_DEBUG_SWITCHES, CRB_TC_DEBUG): 1 = read TMEM but skip the scan, 2 = skip the TMEM read too, 3 = scan only
 };
 
 __device__ __forceinline__ uint32_t ord_bits(uint32_t f) { return (f & 0x80000000u) ? ~f : (f | 0x80000000u); }
@@ -292,41 +302,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (one elected thread) =================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
-            for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-                const int sp = (int)(w % a.n_splits);
-                const int t0 = sp * a.tiles_per_split, t1 = min(a.n_tiles, t0 + a.tiles_per_split);
-                mbar_wait(a_full, a_phase);
-                a_phase ^= 1;
-                for (int t = t0; t < t1; ++t) {
-                    mbar_wait(t_empty + acc, acc_phase ^ 1);   // epilogue has drained this accumulator stage
-                    mbar_wait(b_full + stage, phase);          // TMA bytes have landed
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t b_addr = smem_u32(smem_b + (size_t)stage * b_bytes);
+        // ================= MMA issuer =================
+        // The whole warp runs the loop (so that everything below is warp-uniform and lives in uniform registers); only the
+        // tcgen05 instructions themselves are issued by one elected lane.
+        const bool leader = elect_one();
+        uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
+        const uint32_t desc_hi = (uint32_t)(umma_desc(0) >> 32);
+        const uint32_t a_lo0 = (uint32_t)umma_desc(smem_u32(smem_a)), b_lo0 = (uint32_t)umma_desc(smem_u32(smem_b));
+        const uint32_t b_stage_step = b_bytes >> 4;
+        for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int sp = (int)(w % a.n_splits);
+            const int t0 = sp * a.tiles_per_split, t1 = min(a.n_tiles, t0 + a.tiles_per_split);
+            mbar_wait(a_full, a_phase);
+            a_phase ^= 1;
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(t_empty + acc, acc_phase ^ 1);   // epilogue has drained this accumulator stage
+                mbar_wait(b_full + stage, phase);          // TMA bytes have landed
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (leader) {
+                    const uint32_t b_lo = b_lo0 + stage * b_stage_step;
+#pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const uint32_t d_tmem = tmem_base + acc * 256u + (uint32_t)h * 128u;
+                        const uint32_t a_lo = a_lo0 + (uint32_t)h * (uint32_t)a.kb * 1024u;   // 16384 B per K block, >> 4
                         for (int kb = 0; kb < a.kb; ++kb) {
-                            const uint32_t a_addr = smem_u32(smem_a + (size_t)(h * a.kb + kb) * 16384);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)  // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzle atom
-                                umma_bf16(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + kb * 16384 + k * 32), TC_IDESC,
-                                          (kb | k) ? 1u : 0u);
+                            for (int k = 0; k < 4; ++k)  // UMMA_K = 16 bf16 = 32 bytes (>> 4 = 2) inside the 128-byte swizzle atom
+                                umma_bf16_lh(d_tmem, a_lo + kb * 1024 + k * 2, b_lo + kb * 1024 + k * 2, desc_hi, TC_IDESC, (kb | k) ? 1u : 0u);
                         }
                     }
                     umma_commit(b_empty + stage);  // smem stage reusable once these MMAs retire
                     umma_commit(t_full + acc);     // accumulator ready for the epilogue
-                    if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
-                    if (++acc == 2u) { acc = 0; acc_phase ^= 1; }
                 }
-                umma_commit(a_empty);  // A tile reusable after the last item tile's MMAs
+                __syncwarp();
+                if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
+                if (++acc == 2u) { acc = 0; acc_phase ^= 1; }
             }
+            if (leader) umma_commit(a_empty);  // A tile reusable after the last item tile's MMAs
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ================= epilogue: 16 warps; a thread owns one TMEM lane (= one user) and one column half of every tile ======
+        // This loop is instruction-issue bound (profiles/r01_tc_epilogue_decomposition.md): every instruction below is paid
+        // 32768 times per 128-item tile and SM.  The common path per 32 scores is: TMEM load, one compare for "anything special
+        // in this chunk" (seen item or catalogue end), a 3-input max tree, one compare against the row's threshold.
         const int ew = warp - 4, half = (ew >> 2) & 1, quad = warp & 3, ch = ew >> 3;  // a warp may only touch TMEM lanes 32*(warp%4)..+31
         const int row = half * 128 + quad * 32 + lane;
+        const int32_t n_items32 = (int32_t)a.n_items;
         uint32_t acc = 0, acc_phase = 0;
         for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
             const int64_t mt = w / a.n_splits;
@@ -336,7 +358,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             const bool live = g < a.n_users;
             const int64_t lslot = (int64_t)(sp * TC_CH + ch) * a.n_users_pad;   // this (split, column half)'s lists
             unsigned long long* list = a.cand + (lslot + g) * TC_C;
-            float theta = a.debug == 3 ? INFINITY : -INFINITY;   // debug 3: fast path only (nothing ever beats the threshold)
+#ifdef TC_DEBUG_SWITCHES
+            float theta = (!live || a.debug == 3) ? INFINITY : -INFINITY;   // debug 3: fast path only
+#else
+            float theta = live ? -INFINITY : INFINITY;   // a padding row never lists anything
+#endif
             int cnt = 0;
             // cursor into the user's sorted history: first seen item >= first item of this split
             int64_t hp = 0, hend = 0;
@@ -355,82 +381,82 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                     if (hp < hend) seen_cur = __ldg(a.seen_cols + hp);
                 }
             }
+            // first column at which a chunk needs the special path: the next seen item or the end of the catalogue
+            int32_t special_at = live ? min(seen_cur, n_items32) : 0x7fffffff;
             for (int t = t0; t < t1; ++t) {
                 mbar_wait(t_full + acc, acc_phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                // software pipeline over the 4 column chunks of the tile: chunk c+1 is being read out of TMEM while chunk c is scanned
                 const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256u + (uint32_t)half * 128u;
-#ifndef TC_EPI_PIPELINE
-#define TC_EPI_PIPELINE 0   // measured 2x slower (code size / registers): kept only as an A/B switch
-#endif
-#if TC_EPI_PIPELINE
-                uint32_t rbuf[2][32];
-                tmem_ld32_issue(t_lane, rbuf[0]);
-#pragma unroll
-                for (int c = 0; c < TC_BN / 32; ++c) {
-                    tmem_ld32_wait(rbuf[c & 1]);
-                    if (c + 1 < TC_BN / 32) tmem_ld32_issue(t_lane + (uint32_t)(c + 1) * 32u, rbuf[(c + 1) & 1]);
-                    float v[32];
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(rbuf[c & 1][k]);
-#else
 #pragma unroll 1
                 for (int c = ch * (TC_BN / 32 / TC_CH); c < (ch + 1) * (TC_BN / 32 / TC_CH); ++c) {
-                    uint32_t rb[32];
-                    if (a.debug == 2) continue;
-                    tmem_ld32_issue(t_lane + (uint32_t)c * 32u, rb);
-                    tmem_ld32_wait(rb);
-                    if (a.debug == 1) { if (rb[0] == 0x12345678u && rb[31] == 0x9abcdef0u) cnt = 0; continue; }
                     float v[32];
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(rb[k]);
+#ifdef TC_DEBUG_SWITCHES
+                    if (a.debug == 2) continue;
+#endif
+                    tmem_ld32(t_lane + (uint32_t)c * 32u, v);
+#ifdef TC_DEBUG_SWITCHES
+                    if (a.debug == 1) { if (v[0] == 1.2345e30f && v[31] == 5.4321e30f) cnt = 0; continue; }
 #endif
                     const int32_t c0 = t * TC_BN + c * 32;
-                    if (live) {
-                        // mask seen items (amortised O(|history|) per user) and the padding past the catalogue
+                    if (special_at < c0 + 32) {
+                        // rare: mask seen items (amortised O(|history|) per user) and the padding past the catalogue
                         while (seen_cur < c0 + 32) {
-                            const int idx = seen_cur - c0;
-#pragma unroll
-                            for (int k = 0; k < 32; ++k) v[k] = (k == idx) ? -INFINITY : v[k];
+                            switch (seen_cur - c0) {   // a jump, not 32 selects
+#define TC_MASK_CASE(k) case k: v[k] = -INFINITY; break;
+                                TC_MASK_CASE(0) TC_MASK_CASE(1) TC_MASK_CASE(2) TC_MASK_CASE(3) TC_MASK_CASE(4) TC_MASK_CASE(5) TC_MASK_CASE(6)
+                                TC_MASK_CASE(7) TC_MASK_CASE(8) TC_MASK_CASE(9) TC_MASK_CASE(10) TC_MASK_CASE(11) TC_MASK_CASE(12)
+                                TC_MASK_CASE(13) TC_MASK_CASE(14) TC_MASK_CASE(15) TC_MASK_CASE(16) TC_MASK_CASE(17) TC_MASK_CASE(18)
+                                TC_MASK_CASE(19) TC_MASK_CASE(20) TC_MASK_CASE(21) TC_MASK_CASE(22) TC_MASK_CASE(23) TC_MASK_CASE(24)
+                                TC_MASK_CASE(25) TC_MASK_CASE(26) TC_MASK_CASE(27) TC_MASK_CASE(28) TC_MASK_CASE(29) TC_MASK_CASE(30)
+                                TC_MASK_CASE(31)
+#undef TC_MASK_CASE
+                                default: break;
+                            }
                             ++hp;
                             seen_cur = hp < hend ? __ldg(a.seen_cols + hp) : 0x7fffffff;
                         }
-                        if ((int64_t)c0 + 32 > a.n_items) {
+                        if (c0 + 32 > n_items32) {
 #pragma unroll
-                            for (int k = 0; k < 32; ++k) v[k] = ((int64_t)c0 + k >= a.n_items) ? -INFINITY : v[k];
+                            for (int k = 0; k < 32; ++k) v[k] = (c0 + k >= n_items32) ? -INFINITY : v[k];
                         }
-                        // 8 group maxima (3-input max) -> row maximum; only groups that beat the threshold are scanned
-                        float gm[8];
+                        special_at = min(seen_cur, n_items32);   // past the catalogue every chunk stays special
+                    }
+                    // 8 group maxima (3-input max) -> row maximum; only groups that beat the threshold are scanned
+                    float gm[8];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) gm[q] = fmaxf(fmaxf(v[4 * q], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3]));
-                        const float mx = fmaxf(fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])), fmaxf(fmaxf(gm[4], gm[5]), fmaxf(gm[6], gm[7])));
-                        if (mx > theta) {
-                            unsigned long long* wp = list + cnt;
+                    for (int q = 0; q < 8; ++q) gm[q] = fmaxf(fmaxf(v[4 * q], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3]));
+                    const float mx = fmaxf(fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])), fmaxf(fmaxf(gm[4], gm[5]), fmaxf(gm[6], gm[7])));
+                    const bool hit = mx > theta;
+                    if (__any_sync(0xffffffffu, hit)) {
+                        if (hit) {
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
                                 if (gm[q] > theta) {
-#pragma unroll
-                                    for (int k = 4 * q; k < 4 * q + 4; ++k) {
-                                        if (v[k] > theta) {
-                                            __stcg(wp, ((unsigned long long)__float_as_uint(v[k]) << 32) | (unsigned long long)(uint32_t)(c0 + k));
-                                            ++wp;
-                                        }
-                                    }
+                                    // bit k: element k of the group passes.  The loop's trip count is data dependent, which keeps
+                                    // the compiler from predicating four store sequences per group (110 instructions per hit chunk).
+                                    unsigned m = (v[4 * q] > theta ? 1u : 0u) | (v[4 * q + 1] > theta ? 2u : 0u) |
+                                                 (v[4 * q + 2] > theta ? 4u : 0u) | (v[4 * q + 3] > theta ? 8u : 0u);
+                                    do {
+                                        const int k = __ffs(m) - 1;
+                                        m &= m - 1;
+                                        const float sc = k == 0 ? v[4 * q] : k == 1 ? v[4 * q + 1] : k == 2 ? v[4 * q + 2] : v[4 * q + 3];
+                                        __stcg(list + cnt, ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned long long)(uint32_t)(c0 + 4 * q + k));
+                                        ++cnt;
+                                    } while (m);
                                 }
                             }
-                            cnt = (int)(wp - list);
                         }
-                    }
-                    // a list that could overflow in the next chunk is compacted by the whole warp
-                    unsigned need = __ballot_sync(0xffffffffu, cnt > TC_C - 32);
-                    while (need) {
-                        const int src = __ffs(need) - 1;
-                        need &= need - 1;
-                        const int n = __shfl_sync(0xffffffffu, cnt, src);
-                        unsigned long long* lst = a.cand + (lslot + (mt * TC_BM + half * 128 + quad * 32 + src)) * TC_C;
-                        int kept;
-                        const float thr = compact_list(lst, n, lane, &kept);
-                        if (lane == src) { theta = fmaxf(theta, thr); cnt = kept; }
+                        // a list that could overflow in the next chunk is compacted by the whole warp
+                        unsigned need = __ballot_sync(0xffffffffu, cnt > TC_C - 32);
+                        while (need) {
+                            const int src = __ffs(need) - 1;
+                            need &= need - 1;
+                            const int n = __shfl_sync(0xffffffffu, cnt, src);
+                            unsigned long long* lst = a.cand + (lslot + (mt * TC_BM + half * 128 + quad * 32 + src)) * TC_C;
+                            int kept;
+                            const float thr = compact_list(lst, n, lane, &kept);
+                            if (lane == src) { theta = fmaxf(theta, thr); cnt = kept; }
+                        }
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -659,7 +685,9 @@ int crb_score_topk_tc(crb_handle* h, int32_t kind, const float* P, const float* 
         unsigned int cnts[2] = {0, 0};
         CRB_CUDA(cudaMemcpyAsync(cnts, misc + 2, 8, cudaMemcpyDeviceToHost, s));
         CRB_CUDA(cudaStreamSynchronize(s));
+#ifdef TC_DEBUG_SWITCHES
         if (ta.debug) cnts[0] = 0;   // experiments: results are meaningless, do not re-run anyone
+#endif
         if (cnts[0]) {
             // todo holds pass-local user slots: the exact kernel indexes users/outputs of this pass
             rc = crb_launch_fullrank_exact(h, kind, P, Q, hvec, n_items, dim, users + u0, hist_users ? hist_users + u0 : nullptr,
