@@ -373,7 +373,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("CRB_WORKLOAD", "s_large"), choices=sorted(WORKLOADS))
     ap.add_argument("--optimizer", default="Adam", choices=["SGD", "Adagrad", "Adam"])
     ap.add_argument("--adam-mode", dest="adam_mode", default="tf1", choices=["tf1", "lazy"])
-    ap.add_argument("--eval-users", dest="eval_users", type=int, default=32768)
+    ap.add_argument("--eval-users", dest="eval_users", type=int, default=262144)
     ap.add_argument("--eval-exact", dest="eval_exact", action="store_true")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     ap.add_argument("--sharded", action="store_true", help="use the multi-GPU code path even at N=1 (experiments)")

@@ -56,14 +56,20 @@ __global__ void __launch_bounds__(256) fullrank_exact_kernel(const float* __rest
                                                              const int32_t* __restrict__ users, const int32_t* __restrict__ hist_users,
                                                              const int32_t* __restrict__ todo, int64_t n_todo,
                                                              const int64_t* __restrict__ seen_rowptr, const int32_t* __restrict__ seen_cols,
-                                                             int K, int32_t* __restrict__ out_items, float* __restrict__ out_scores) {
+                                                             int K, int32_t* __restrict__ out_items, float* __restrict__ out_scores,
+                                                             int n_chunks, unsigned long long* __restrict__ part) {
+    // n_chunks > 1 (few users, e.g. the tensor-core path's uncertified ones): the catalogue is cut into n_chunks ranges, one CTA
+    // per (user, range) writes the range's best K keys to `part`, and fullrank_merge_kernel takes the best K of those -- the same
+    // ids as one sweep, because ranking keys are a strict total order.
     extern __shared__ float s_user[];  // dim floats
     __shared__ unsigned long long buf[FR_CAP];
     __shared__ int s_count;
     __shared__ unsigned long long s_thr;
     constexpr int ASC = KIND == CRB_SCORE_SQDIST ? 1 : 0;
-    for (int64_t w = blockIdx.x; w < n_todo; w += gridDim.x) {
-        const int64_t k = todo ? todo[w] : w;
+    const int64_t chunk_len = (n_items + n_chunks - 1) / n_chunks;
+    for (int64_t w = blockIdx.x; w < n_todo * n_chunks; w += gridDim.x) {
+        const int64_t k = todo ? todo[w / n_chunks] : w / n_chunks;
+        const int64_t item_lo = (w % n_chunks) * chunk_len, item_hi = min(n_items, item_lo + chunk_len);
         const int32_t urow = users[k];
         const int32_t hu = hist_users ? hist_users[k] : urow;
         __syncthreads();
@@ -71,10 +77,10 @@ __global__ void __launch_bounds__(256) fullrank_exact_kernel(const float* __rest
         if (threadIdx.x == 0) { s_count = 0; s_thr = 0ULL; }
         __syncthreads();
         const int64_t h_lo = hu >= 0 ? seen_rowptr[hu] : 0, h_hi = hu >= 0 ? seen_rowptr[hu + 1] : 0;
-        for (int64_t base = 0; base < n_items; base += blockDim.x) {
+        for (int64_t base = item_lo; base < item_hi; base += blockDim.x) {
             const int64_t item = base + threadIdx.x;
             unsigned long long key = 0ULL;
-            if (item < n_items) {
+            if (item < item_hi) {
                 const float sc = canonical_score<KIND>(s_user, Q + item * dim, hvec, (int32_t)item, dim);
                 key = rank_key(sc, (uint32_t)item, ASC);
                 if (key <= s_thr) key = 0ULL;
@@ -96,9 +102,37 @@ __global__ void __launch_bounds__(256) fullrank_exact_kernel(const float* __rest
         block_sort_desc<FR_CAP>(buf, s_count);
         for (int r = threadIdx.x; r < K; r += blockDim.x) {
             const bool ok = r < s_count;
+            if (n_chunks > 1) { part[w * K + r] = ok ? buf[r] : 0ULL; continue; }
             out_items[k * K + r] = ok ? (int32_t)key_index(buf[r]) : -1;
             if (out_scores) out_scores[k * K + r] = ok ? key_score(buf[r], ASC) : 0.f;
         }
+    }
+}
+
+// one warp per user: K rounds of arg-best over the user's n_chunks * K partial keys
+__global__ void __launch_bounds__(32) fullrank_merge_kernel(const unsigned long long* __restrict__ part, const int32_t* __restrict__ todo,
+                                                            int n_chunks, int K, int ascending, int32_t* __restrict__ out_items,
+                                                            float* __restrict__ out_scores) {
+    const int lane = threadIdx.x;
+    const int64_t w = blockIdx.x, k = todo ? todo[w] : w;
+    const unsigned long long* keys = part + w * n_chunks * K;
+    const int n = n_chunks * K;
+    unsigned long long prev = ~0ULL;
+    for (int r = 0; r < K; ++r) {
+        unsigned long long best = 0ULL;
+        for (int q = lane; q < n; q += 32) {
+            const unsigned long long key = keys[q];
+            if (key < prev && key > best) best = key;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        if (lane == 0) {
+            out_items[k * K + r] = best ? (int32_t)key_index(best) : -1;
+            if (out_scores) out_scores[k * K + r] = best ? key_score(best, ascending) : 0.f;
+        }
+        prev = best ? best : 0ULL;
     }
 }
 
@@ -224,12 +258,23 @@ int crb_launch_fullrank_exact(crb_handle* h, int32_t kind, const float* P, const
                               int32_t K, int32_t* out_items, float* out_scores, cudaStream_t s) {
     if (n_todo <= 0) return CRB_OK;
     CRB_CHECK_ARG(K >= 1 && K <= 256, "K must be in [1,256]");
-    int grid = (int)(n_todo < (int64_t)h->sm_count * 8 ? n_todo : (int64_t)h->sm_count * 8);
+    // few users: cut the catalogue so that the machine is full (8 CTAs per SM), ranges of at least 4096 items
+    int n_chunks = 1;
+    if (n_todo < (int64_t)h->sm_count * 4) {
+        n_chunks = (int)(((int64_t)h->sm_count * 8 + n_todo - 1) / n_todo);
+        const int64_t max_chunks = (n_items + 4095) / 4096;
+        if (n_chunks > max_chunks) n_chunks = (int)max_chunks;
+        if (n_chunks < 1) n_chunks = 1;
+    }
+    const int64_t work = n_todo * n_chunks;
+    int grid = (int)(work < (int64_t)h->sm_count * 8 ? work : (int64_t)h->sm_count * 8);
     const size_t sm = sizeof(float) * dim;
+    unsigned long long* part = nullptr;
+    if (n_chunks > 1) CRB_CUDA(cudaMallocAsync(&part, sizeof(unsigned long long) * work * K, s));
 #define FR_CASE(KD)                                                                                                          \
     case KD:                                                                                                                 \
         fullrank_exact_kernel<KD><<<grid, 256, sm, s>>>(P, Q, hvec, n_items, dim, users, hist_users, todo, n_todo, h->seen_rowptr, \
-                                                        h->seen_cols, K, out_items, out_scores);                             \
+                                                        h->seen_cols, K, out_items, out_scores, n_chunks, part);             \
         break;
     switch (kind) {
         FR_CASE(CRB_SCORE_DOT)
@@ -241,5 +286,11 @@ int crb_launch_fullrank_exact(crb_handle* h, int32_t kind, const float* P, const
 #undef FR_CASE
     h->launches++;
     CRB_CUDA(cudaGetLastError());
+    if (n_chunks > 1) {
+        fullrank_merge_kernel<<<(int)n_todo, 32, 0, s>>>(part, todo, n_chunks, K, kind == CRB_SCORE_SQDIST ? 1 : 0, out_items, out_scores);
+        h->launches++;
+        CRB_CUDA(cudaGetLastError());
+        CRB_CUDA(cudaFreeAsync(part, s));
+    }
     return CRB_OK;
 }

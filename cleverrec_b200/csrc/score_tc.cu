@@ -16,7 +16,8 @@
 
 #include "score_common.cuh"
 
-#define TC_C 128          // candidate slots per (user, split)
+#define TC_C 256          // candidate slots per (user, split, column half)
+#define TC_EPL (TC_C / 32) // list entries per lane in a compaction
 #define TC_KEEP 64        // kept by a compaction
 #define TC_BM 256         // users per CTA (2 x UMMA_M=128)
 #define TC_BN 128         // items per tile
@@ -192,7 +193,7 @@ struct TcArgs {
 
 __device__ __forceinline__ uint32_t ord_bits(uint32_t f) { return (f & 0x80000000u) ? ~f : (f | 0x80000000u); }
 
-// Warp-cooperative compaction of one row's candidate list (n <= TC_C entries, 4 per lane).  ANY threshold T is valid for the
+// Warp-cooperative compaction of one row's candidate list (n <= TC_C entries, TC_EPL per lane).  ANY threshold T is valid for the
 // certificate as long as every dropped entry has score <= T; the list only needs to shrink enough to make room.  So instead of
 // an exact selection (a 32-step radix descent was the straggler that stalled the 2-deep accumulator pipeline) T is found by
 // bisection on the order-preserving score bits between the list's min and max, stopping as soon as the number of kept entries
@@ -200,11 +201,11 @@ __device__ __forceinline__ uint32_t ord_bits(uint32_t f) { return (f & 0x8000000
 // Returns T as a float; *kept receives the new count.
 #define TC_KEEP_MIN 32
 __device__ __forceinline__ float compact_list(unsigned long long* list, int n, int lane, int* kept) {
-    unsigned long long e[4];
-    uint32_t o[4];
+    unsigned long long e[TC_EPL];
+    uint32_t o[TC_EPL];
     uint32_t lo = 0xFFFFFFFFu, hi = 0u;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < TC_EPL; ++t) {
         const int idx = lane + 32 * t;
         e[t] = idx < n ? __ldcg(list + idx) : 0ULL;
         o[t] = idx < n ? ord_bits((uint32_t)(e[t] >> 32)) : 0u;
@@ -216,7 +217,9 @@ __device__ __forceinline__ float compact_list(unsigned long long* list, int n, i
     uint32_t T = hi;
     while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
-        const int c = (o[0] > mid) + (o[1] > mid) + (o[2] > mid) + (o[3] > mid);
+        int c = 0;
+#pragma unroll
+        for (int t = 0; t < TC_EPL; ++t) c += (o[t] > mid);
         const int tot = __reduce_add_sync(0xffffffffu, c);
         if (tot > TC_KEEP) { lo = mid + 1; T = hi; }
         else { hi = mid; T = mid; if (tot >= TC_KEEP_MIN) break; }
@@ -224,7 +227,7 @@ __device__ __forceinline__ float compact_list(unsigned long long* list, int n, i
     __syncwarp();
     int base = 0;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < TC_EPL; ++t) {
         const bool keep = o[t] > T;
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         if (keep) __stcg(list + base + __popc(m & ((1u << lane) - 1u)), e[t]);
@@ -426,9 +429,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
 #pragma unroll
                     for (int q = 0; q < 8; ++q) gm[q] = fmaxf(fmaxf(v[4 * q], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3]));
                     const float mx = fmaxf(fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])), fmaxf(fmaxf(gm[4], gm[5]), fmaxf(gm[6], gm[7])));
-                    const bool hit = mx > theta;
-                    if (__any_sync(0xffffffffu, hit)) {
-                        if (hit) {
+                    if (mx > theta) {
+                        {
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
                                 if (gm[q] > theta) {
@@ -446,23 +448,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                                 }
                             }
                         }
-                        // a list that could overflow in the next chunk is compacted by the whole warp
-                        unsigned need = __ballot_sync(0xffffffffu, cnt > TC_C - 32);
-                        while (need) {
-                            const int src = __ffs(need) - 1;
-                            need &= need - 1;
-                            const int n = __shfl_sync(0xffffffffu, cnt, src);
-                            unsigned long long* lst = a.cand + (lslot + (mt * TC_BM + half * 128 + quad * 32 + src)) * TC_C;
-                            int kept;
-                            const float thr = compact_list(lst, n, lane, &kept);
-                            if (lane == src) { theta = fmaxf(theta, thr); cnt = kept; }
-                        }
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(t_empty + acc);
                 if (++acc == 2u) { acc = 0; acc_phase ^= 1; }
+                // Compaction is OFF the accumulator hand-off: the TMEM stage has just been released, so the ~1500 cycles a
+                // compaction takes (list round trip through L2 + bisection) overlap the next tiles' MMAs instead of stalling them.
+                // A list is compacted as soon as the next tile could overflow it (worst case 32 appends per chunk).
+                unsigned need = __ballot_sync(0xffffffffu, cnt > TC_C - 32 * (TC_BN / 32 / TC_CH));
+                while (need) {
+                    const int src = __ffs(need) - 1;
+                    need &= need - 1;
+                    const int n = __shfl_sync(0xffffffffu, cnt, src);
+                    unsigned long long* lst = a.cand + (lslot + (mt * TC_BM + half * 128 + quad * 32 + src)) * TC_C;
+                    int kept;
+                    const float thr = compact_list(lst, n, lane, &kept);
+                    if (lane == src) { theta = fmaxf(theta, thr); cnt = kept; }
+                }
             }
             a.cand_cnt[lslot + g] = live ? cnt : 0;
             a.cand_thr[lslot + g] = theta;
@@ -608,14 +612,20 @@ int crb_score_topk_tc(crb_handle* h, int32_t kind, const float* P, const float* 
     CRB_CHECK_ARG(n_items < 0x7fffff00LL, "catalogue too large");
     const int64_t n_items_pad = round_up(n_items, TC_BN);
     const int n_tiles = (int)(n_items_pad / TC_BN);
-    const int64_t pass_users = n_users < (1 << 20) ? n_users : (1 << 20);
+    const int64_t pass_users = n_users < (1 << 18) ? n_users : (1 << 18);   // bounds the candidate-list workspace (1 GB)
     const int64_t pass_pad = round_up(pass_users, TC_BM);
     const int64_t m_tiles_max = pass_pad / TC_BM;
+    // Item splits: a work item is (256-user tile, item range); every extra range costs a list start-up (the first ~10^4 items of
+    // a list produce half of its appends) and more candidates to re-score, taken here as 150 tiles' worth.  Pick the split count
+    // that minimises waves x (tiles per range + overhead) on this machine.
     int n_splits = 1;
-    if (m_tiles_max < 2 * h->sm_count) {
-        n_splits = (int)((2 * h->sm_count + m_tiles_max - 1) / m_tiles_max);
-        if (n_splits > n_tiles) n_splits = n_tiles;
-        if (n_splits > 64) n_splits = 64;
+    {
+        double best = 0.0;
+        for (int n = 1; n <= 64 && n <= n_tiles; ++n) {
+            const int64_t waves = (m_tiles_max * n + h->sm_count - 1) / h->sm_count;
+            const double cost = (double)waves * ((double)((n_tiles + n - 1) / n) + 150.0);
+            if (n == 1 || cost < best * 0.97) { if (n == 1 || cost < best) { best = cost; n_splits = n; } }
+        }
     }
     const int tiles_per_split = (n_tiles + n_splits - 1) / n_splits;
     n_splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;

@@ -78,3 +78,22 @@ def test_fullrank_small_catalogue_pads(eng):
     want, _ = O.fullrank_topk(0, P, Q, np.arange(3), rp, sc, 10)
     got = eng.score_topk(0, torch.tensor(P).cuda(), torch.tensor(Q).cuda(), np.arange(3, dtype=np.int32), 10, exact=True)
     assert np.array_equal(got, want) and (got[0, 5:] == -1).all()
+
+
+@pytest.mark.parametrize("kind", [0, 2])
+def test_fullrank_exact_few_users_chunked_catalogue(eng, kind):
+    """Few users against a catalogue large enough to be cut into ranges (fullrank_exact_kernel n_chunks > 1 + merge): the path the
+    tensor-core kernel's uncertified users take.  Same ids and score bits as the oracle's single sweep; heavy ties included."""
+    d = synthetic_data(7, 40000, 50, seed=10 + kind)
+    pu, pi, rp, sc = X.build_history(d.ui_train, d.user_nums)
+    eng.set_history(d.ui_train, d.user_nums, d.item_nums)
+    rs = np.random.RandomState(kind)
+    dim = 32
+    P, Q = (rs.randn(d.user_nums, dim) * 0.1).astype(np.float32), (rs.randn(d.item_nums, dim) * 0.1).astype(np.float32)
+    Q[5000:5040] = Q[100]     # 41-way exact tie that straddles range boundaries
+    Q[39990:] = Q[100]
+    users = np.array([6, 0, 3], dtype=np.int32)
+    want_i, want_s = O.fullrank_topk(kind, P, Q, users, rp, sc, 50, None)
+    got_i, got_s = eng.score_topk(kind, torch.tensor(P).cuda(), torch.tensor(Q).cuda(), users, 50, exact=True, return_scores=True)
+    assert np.array_equal(got_i, want_i)
+    assert np.array_equal(got_s.view(np.uint32), want_s.view(np.uint32))
