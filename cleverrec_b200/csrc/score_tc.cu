@@ -254,9 +254,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
     uint64_t* b_empty = bars + 4;            // [stages]
     uint64_t* a_full = bars + 8;
     uint64_t* a_empty = bars + 9;
-    uint64_t* t_full = bars + 10;            // [2]
-    uint64_t* t_empty = bars + 12;           // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    // accumulator hand-off barriers, one pair per (stage, M half): a half's 8 epilogue warps start as soon as ITS 8 MMAs have
+    // retired and release it independently, so the MMA pipe stays busy as long as epilogue + hand-off latency <= 1.5 tile times
+    // (with whole-tile barriers the bound was 1.0 and the two sides ping-ponged: each waited on the other ~30% of the time)
+    uint64_t* t_full = bars + 10;            // [2 stages][2 halves]
+    uint64_t* t_empty = bars + 14;           // [2 stages][2 halves]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
         for (int s = 0; s < a.stages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 8 * TC_CH); }
+        for (int s = 0; s < 4; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 4 * TC_CH); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -319,13 +322,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             mbar_wait(a_full, a_phase);
             a_phase ^= 1;
             for (int t = t0; t < t1; ++t) {
-                mbar_wait(t_empty + acc, acc_phase ^ 1);   // epilogue has drained this accumulator stage
                 mbar_wait(b_full + stage, phase);          // TMA bytes have landed
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (leader) {
-                    const uint32_t b_lo = b_lo0 + stage * b_stage_step;
+                const uint32_t b_lo = b_lo0 + stage * b_stage_step;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < 2; ++h) {
+                    mbar_wait(t_empty + acc * 2 + h, acc_phase ^ 1);   // this half's epilogue warps have drained the stage
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (leader) {
                         const uint32_t d_tmem = tmem_base + acc * 256u + (uint32_t)h * 128u;
                         const uint32_t a_lo = a_lo0 + (uint32_t)h * (uint32_t)a.kb * 1024u;   // 16384 B per K block, >> 4
                         for (int kb = 0; kb < a.kb; ++kb) {
@@ -333,11 +336,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                             for (int k = 0; k < 4; ++k)  // UMMA_K = 16 bf16 = 32 bytes (>> 4 = 2) inside the 128-byte swizzle atom
                                 umma_bf16_lh(d_tmem, a_lo + kb * 1024 + k * 2, b_lo + kb * 1024 + k * 2, desc_hi, TC_IDESC, (kb | k) ? 1u : 0u);
                         }
+                        if (h == 1) umma_commit(b_empty + stage);  // smem stage reusable once these MMAs retire
+                        umma_commit(t_full + acc * 2 + h);         // this half's accumulator is ready for its epilogue warps
                     }
-                    umma_commit(b_empty + stage);  // smem stage reusable once these MMAs retire
-                    umma_commit(t_full + acc);     // accumulator ready for the epilogue
+                    __syncwarp();
                 }
-                __syncwarp();
                 if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
                 if (++acc == 2u) { acc = 0; acc_phase ^= 1; }
             }
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             // first column at which a chunk needs the special path: the next seen item or the end of the catalogue
             int32_t special_at = live ? min(seen_cur, n_items32) : 0x7fffffff;
             for (int t = t0; t < t1; ++t) {
-                mbar_wait(t_full + acc, acc_phase);
+                mbar_wait(t_full + acc * 2 + half, acc_phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256u + (uint32_t)half * 128u;
 #pragma unroll 1
@@ -401,27 +404,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                     if (a.debug == 1) { if (v[0] == 1.2345e30f && v[31] == 5.4321e30f) cnt = 0; continue; }
 #endif
                     const int32_t c0 = t * TC_BN + c * 32;
+                    uint32_t skip = 0;   // bit k: column c0 + k must not be listed (seen by the user, or past the catalogue)
                     if (special_at < c0 + 32) {
-                        // rare: mask seen items (amortised O(|history|) per user) and the padding past the catalogue
+                        // rare: seen items (amortised O(|history|) per user) and the padding past the catalogue.  The scores stay
+                        // where they are (masking one of 32 registers by a run-time index costs 64 instructions); the bit mask
+                        // is applied where candidates are appended.  A seen item can only make the chunk take the slow path.
                         while (seen_cur < c0 + 32) {
-                            switch (seen_cur - c0) {   // a jump, not 32 selects
-#define TC_MASK_CASE(k) case k: v[k] = -INFINITY; break;
-                                TC_MASK_CASE(0) TC_MASK_CASE(1) TC_MASK_CASE(2) TC_MASK_CASE(3) TC_MASK_CASE(4) TC_MASK_CASE(5) TC_MASK_CASE(6)
-                                TC_MASK_CASE(7) TC_MASK_CASE(8) TC_MASK_CASE(9) TC_MASK_CASE(10) TC_MASK_CASE(11) TC_MASK_CASE(12)
-                                TC_MASK_CASE(13) TC_MASK_CASE(14) TC_MASK_CASE(15) TC_MASK_CASE(16) TC_MASK_CASE(17) TC_MASK_CASE(18)
-                                TC_MASK_CASE(19) TC_MASK_CASE(20) TC_MASK_CASE(21) TC_MASK_CASE(22) TC_MASK_CASE(23) TC_MASK_CASE(24)
-                                TC_MASK_CASE(25) TC_MASK_CASE(26) TC_MASK_CASE(27) TC_MASK_CASE(28) TC_MASK_CASE(29) TC_MASK_CASE(30)
-                                TC_MASK_CASE(31)
-#undef TC_MASK_CASE
-                                default: break;
-                            }
+                            const int idx = seen_cur - c0;
+                            if (idx >= 0) skip |= 1u << idx;
                             ++hp;
                             seen_cur = hp < hend ? __ldg(a.seen_cols + hp) : 0x7fffffff;
                         }
-                        if (c0 + 32 > n_items32) {
-#pragma unroll
-                            for (int k = 0; k < 32; ++k) v[k] = (c0 + k >= n_items32) ? -INFINITY : v[k];
-                        }
+                        if (c0 + 32 > n_items32) skip |= c0 >= n_items32 ? 0xffffffffu : (0xffffffffu << (n_items32 - c0));
                         special_at = min(seen_cur, n_items32);   // past the catalogue every chunk stays special
                     }
                     // 8 group maxima (3-input max) -> row maximum; only groups that beat the threshold are scanned
@@ -436,15 +430,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                                 if (gm[q] > theta) {
                                     // bit k: element k of the group passes.  The loop's trip count is data dependent, which keeps
                                     // the compiler from predicating four store sequences per group (110 instructions per hit chunk).
-                                    unsigned m = (v[4 * q] > theta ? 1u : 0u) | (v[4 * q + 1] > theta ? 2u : 0u) |
-                                                 (v[4 * q + 2] > theta ? 4u : 0u) | (v[4 * q + 3] > theta ? 8u : 0u);
-                                    do {
+                                    unsigned m = ((v[4 * q] > theta ? 1u : 0u) | (v[4 * q + 1] > theta ? 2u : 0u) |
+                                                  (v[4 * q + 2] > theta ? 4u : 0u) | (v[4 * q + 3] > theta ? 8u : 0u)) & ~(skip >> (4 * q));
+                                    while (m) {
                                         const int k = __ffs(m) - 1;
                                         m &= m - 1;
                                         const float sc = k == 0 ? v[4 * q] : k == 1 ? v[4 * q + 1] : k == 2 ? v[4 * q + 2] : v[4 * q + 3];
                                         __stcg(list + cnt, ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned long long)(uint32_t)(c0 + 4 * q + k));
                                         ++cnt;
-                                    } while (m);
+                                    }
                                 }
                             }
                         }
@@ -452,7 +446,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(t_empty + acc);
+                if (lane == 0) mbar_arrive(t_empty + acc * 2 + half);
                 if (++acc == 2u) { acc = 0; acc_phase ^= 1; }
                 // Compaction is OFF the accumulator hand-off: the TMEM stage has just been released, so the ~1500 cycles a
                 // compaction takes (list round trip through L2 + bisection) overlap the next tiles' MMAs instead of stalling them.
