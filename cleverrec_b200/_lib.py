@@ -24,7 +24,7 @@ EXPORTS = [
     "crb_train_step_neumf", "crb_score_pairs_neumf", "crb_mask_seen",
     "crb_sample_nais", "crb_train_step_nais", "crb_train_epoch_nais", "crb_score_nais",
     "crb_shard_step_compute", "crb_shard_step_prepare", "crb_shard_apply_inbox", "crb_shard_inbox_overflow", "crb_malloc", "crb_free", "crb_ipc_export",
-    "crb_ipc_open", "crb_ipc_close", "crb_np_seed", "crb_np_set_state", "crb_np_get_state", "crb_sample_epoch_numpy",
+    "crb_ipc_open", "crb_ipc_close", "crb_build_history", "crb_np_seed", "crb_np_set_state", "crb_np_get_state", "crb_sample_epoch_numpy",
 ]
 
 
@@ -71,6 +71,7 @@ def load():
     lib.crb_create.argtypes = [C.c_int, C.POINTER(vp)]
     lib.crb_destroy.argtypes = [vp]
     lib.crb_set_history.argtypes = [vp, i64, i64, i64, vp, vp, vp, vp, vp]
+    lib.crb_build_history.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, C.POINTER(i64), vp, vp, vp]
     lib.crb_sample_pairwise.argtypes = [vp, u64, u32, i64, i64, i32, vp, vp, vp, vp, vp]
     lib.crb_sample_pointwise.argtypes = [vp, u64, u32, i64, i64, i32, vp, vp, vp, vp, vp]
     lib.crb_sample_cml.argtypes = [vp, u64, u32, i64, i64, i32, vp, vp, vp, vp]

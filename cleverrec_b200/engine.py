@@ -109,6 +109,31 @@ class Engine(object):
         check(self.lib.crb_set_history(self.h, n_users, n_items, self.n_pos, ptr(pu) if self.n_pos else None,
                                        ptr(pi) if self.n_pos else None, ptr(rp), ptr(sc), self.stream))
 
+    def build_history(self, users, items, n_users, n_items):
+        """The training split's (user, item) rows -- int32 columns in file order, NumPy or torch, host or device -- straight to the
+        device history (crb_build_history): no dict of lists, no Python sets.  Equivalent to
+        set_history(train.groupby('u_id').i_id.apply(list).to_dict(), ...) (model/RankingPreprocess.py:117)."""
+        def col(a):
+            if isinstance(a, torch.Tensor):
+                return a.to(dtype=torch.int32).contiguous()
+            return np.ascontiguousarray(a, dtype=np.int32)
+        users, items = col(users), col(items)
+        n = int(len(users))
+        dev = self.device
+        pu, pi = torch.empty(max(n, 1), dtype=torch.int32, device=dev), torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        rp, sc = torch.empty(n_users + 1, dtype=torch.int64, device=dev), torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        start, ln = torch.empty(n_users + 1, dtype=torch.int64, device=dev), torch.empty(n_users, dtype=torch.int32, device=dev)
+        n_seen = C.c_int64(0)
+        check(self.lib.crb_build_history(self.h, ptr(users), ptr(items), n, n_users, n_items, ptr(pu), ptr(pi), ptr(rp), ptr(sc),
+                                         C.byref(n_seen), ptr(start), ptr(ln), self.stream))
+        sc = sc[:max(int(n_seen.value), 1)]
+        self._hist = (pu[:n], pi[:n], rp, sc)
+        self.n_users, self.n_items, self.n_pos = int(n_users), int(n_items), n
+        check(self.lib.crb_set_history(self.h, n_users, n_items, n, ptr(pu) if n else None, ptr(pi) if n else None, ptr(rp), ptr(sc), self.stream))
+        self._lists = (start, ln)
+        check(self.lib.crb_set_history_lists(self.h, ptr(start), ptr(ln)))
+        return self._hist
+
     def set_history(self, ui_train, n_users, n_items):
         self.set_history_arrays(n_users, n_items, *history_from_dict(ui_train, n_users))
         # per-user interaction lists (order and duplicates kept) inside pos_item: FISM / NAIS need them

@@ -116,6 +116,18 @@ int crb_set_history(crb_handle* h, int64_t n_users, int64_t n_items, int64_t n_p
                     const int32_t* pos_user, const int32_t* pos_item,
                     const int64_t* seen_rowptr, const int32_t* seen_cols, void* stream);
 
+/* Native builder of the arrays above from the training split's (user, item) rows -- replaces the dict / list / set forms of
+ * model/RankingPreprocess.py:117 (`groupby('u_id').i_id.apply(list).to_dict()`), utils/sampler.py:53 and
+ * model/RankingRecommender.py:222-240 (`set(ui_train[u])`), which cannot be materialised at 1e9 interactions.
+ *  users/items [n]: int32 rows of the training split in file order, ids already re-indexed (HOST or DEVICE)
+ *  pos_user/pos_item [n]: grouped by user (ascending id = the groupby order), row order kept inside a user      DEVICE out
+ *  seen_rowptr [n_users+1], seen_cols [n] (first *n_seen entries valid): sorted-unique per user                  DEVICE out
+ *  list_start [n_users+1], list_len [n_users]: each user's list inside pos_item (crb_set_history_lists), or NULL  DEVICE out
+ * Synchronises the stream (n_seen is a host value).  Ids outside their range are an error (CRB_ERR_ARG). */
+int crb_build_history(crb_handle* h, const int32_t* users, const int32_t* items, int64_t n, int64_t n_users, int64_t n_items,
+                      int32_t* pos_user, int32_t* pos_item, int64_t* seen_rowptr, int32_t* seen_cols, int64_t* n_seen,
+                      int64_t* list_start, int32_t* list_len, void* stream);
+
 /* utils/sampler.py:46-74 pairwise_ranking_sampler: rows [first, first+count) of the epoch's shuffled
  * triplet list.  nbr (fism_like's u_neighbors_num) may be NULL.  Outputs: DEVICE int32. */
 int crb_sample_pairwise(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t first, int64_t count,
