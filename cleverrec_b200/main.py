@@ -33,8 +33,12 @@ if __name__ == '__main__':
     logger = get_logger(configs['log.dir'], configs['recommender'])
     logger.info('=' * 100)
     logger.info('Current model: %s' % configs['recommender'])
-    # data: the reference's own model/RankingPreprocess.py (pure pandas, kept as-is; SURVEY 2.1 'boundary producer')
-    sys.path.insert(0, root)
-    from model.RankingPreprocess import RankingPreprocess
+    # data: the packaged mirror of model/RankingPreprocess.py (same split and evaluation negatives bit for bit under the same
+    # np.random.seed -- tests/test_preprocess.py); `data.preprocess=reference` uses the reference checkout's own class instead
+    if configs.get('data.preprocess', 'packaged') == 'reference':
+        sys.path.insert(0, root)
+        from model.RankingPreprocess import RankingPreprocess
+    else:
+        from cleverrec_b200.model.RankingPreprocess import RankingPreprocess
     data = RankingPreprocess(configs, logger)
     run(configs, data, logger)

@@ -25,7 +25,12 @@ class RankingRecommender(Recommender):
         self.test_users = list(data.ui_test.keys())
         self.test_batches = math.ceil(len(self.test_users) / self.batch_size_t)
         self.epoch = 0            # epochs sampled so far (the sampler's `epoch` counter)
-        self.engine.set_history(data.ui_train, self._history_rows(), data.item_nums)
+        if getattr(data, 'train_rows', None) is not None:
+            # the packaged RankingPreprocess also keeps the training split as two int32 columns in the dict's enumeration
+            # order: the device history is built from them natively (csrc/history.cu) instead of walking the dict of lists
+            self.engine.build_history(data.train_rows[0], data.train_rows[1], self._history_rows(), data.item_nums)
+        else:
+            self.engine.set_history(data.ui_train, self._history_rows(), data.item_nums)
         self._test_cache = None
 
     def _history_rows(self):
@@ -189,6 +194,8 @@ class RankingRecommender(Recommender):
                 if best_flag:
                     best_metrics[id] = (hr, mrr, ndcg)
                     best_epoch = epoch + 1
+                    if id == len(self.topk) - 1 and self.configs.get('save_model', 'False') == 'True':
+                        self.save_model()   # the reference's commented-out saver.save (:432-433), opt-in
 
         # Final results
         self.logger.info('best_epoch: %d' % best_epoch)

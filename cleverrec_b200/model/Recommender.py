@@ -52,6 +52,29 @@ class Recommender(object):
     def build_model(self):
         raise NotImplementedError
 
+    # ---- checkpoints (utils/tools.py save_checkpoint): same variable names as the reference's per-model Saver maps ----
+    def _variables(self):
+        """dict Saver-name -> tensor, e.g. {'BPR_params/P': ..., 'BPR_params/Q': ...}."""
+        raise NotImplementedError
+
+    def _flush_before_read(self):
+        """Tables under CRB_ADAM_TF1 carry pending decay-only steps until flushed."""
+        from ..engine import Table
+        seen = set()
+        for v in list(vars(self).values()) + list(getattr(self, 'tables', {}).values()) + list(getattr(self, 'tabs', [])):
+            if isinstance(v, Table) and v.last is not None and id(v) not in seen:   # only CRB_ADAM_TF1 tables defer decay steps
+                seen.add(id(v))
+                self.engine.adam_flush(v, self.optimizer)
+
+    def save_model(self, step=None):
+        """What `self.saver.save(self.sess, saved_dir/model/model)` (RankingRecommender.py:433, commented out in the reference)
+        would write.  Enabled from run_model by the config key save_model=True."""
+        import os
+        from ..utils.tools import save_checkpoint
+        self._flush_before_read()
+        torch.cuda.synchronize(self.engine.device)
+        return save_checkpoint(os.path.join(self.saved_model_dir, self.model), self.model, self._variables(), step)
+
     def train_model(self):
         raise NotImplementedError
 

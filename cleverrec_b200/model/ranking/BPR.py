@@ -28,6 +28,9 @@ class BPR(_rr.RankingRecommender):
     def build_model(self, init=None):
         self._create_params(init)
 
+    def _variables(self):   # BPR.py:53-58
+        return {'BPR_params/P': self.P.w, 'BPR_params/Q': self.Q.w}
+
     # sess.run([self.train, self.loss], ...) for every batch of the epoch, sampler fused in (BPR.py:31-44)
     def _train_epoch_pairwise(self, epoch, n_rows, n_batches, losses):
         self.engine.train_epoch_bpr(self.P, self.Q, self.optimizer, self.seed, epoch, 0, self.batch_size, n_batches,

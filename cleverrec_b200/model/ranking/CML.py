@@ -32,6 +32,9 @@ class CML(_rr.RankingRecommender):
     def build_model(self, init=None):
         self._create_params(init)
 
+    def _variables(self):   # CML.py:86-91
+        return {'cml_params/P': self.P.w, 'cml_params/Q': self.Q.w}
+
     def train_step(self, u_idx, i_idx, neg_items, loss_out=None):
         """sess.run([train, loss], {u_idx, i_idx, neg_items})  (CML.py:39-61)."""
         out = self.engine.train_step_cml(self.P, self.Q, self.optimizer, u_idx, i_idx, neg_items, self.margin, self.reg,

@@ -37,6 +37,9 @@ class FISM(_rr.RankingRecommender):
     def build_model(self, init=None):
         self._create_params(init)
 
+    def _variables(self):   # FISM.py:72-77 -- 'FISM_paras/P' is the reference's spelling; NAIS_single.py:36 restores by it
+        return {'FISM_paras/P': self.P.w, 'FISM_params/Q': self.Q.w, 'FISM_params/b': self.b}
+
     @property
     def b(self):
         return self.B.w.reshape(-1)[:self.n_bias]

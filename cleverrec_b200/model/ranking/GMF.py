@@ -41,6 +41,12 @@ class GMF(_rr.RankingRecommender):
     def build_model(self, init=None):
         self._create_params(init)
 
+    def _variables(self):   # GMF.py:59-64 (MF, which has no reference source, saves under its own class name)
+        out = {'%s_params/P' % self.model: self.P.w, '%s_params/Q' % self.model: self.Q.w}
+        if self.h_gmf is not None:
+            out['%s_params/h_gmf' % self.model] = self.h_gmf
+        return out
+
     def train_step(self, u_idx, i_idx, y, loss_out=None):
         """Feed-style step: sess.run([train, loss], {u_idx, i_idx, y})  (GMF.py:45-49)."""
         return self.engine.train_step_pointwise(self.score_kind, self.P, self.Q, self.optimizer, u_idx, i_idx, y, self.reg,

@@ -48,7 +48,28 @@ class NAIS_single(_rr.RankingRecommender):
         self.dense_s2 = torch.zeros_like(self.dense) if kind == 'Adam' else None
 
     def build_model(self, init=None):
-        self._create_params(init)
+        self._create_params(self._with_pretrained(init))
+
+    def _with_pretrained(self, init):
+        """NAIS_single.py:35-38 `_load_fism_params`: P, Q and the item bias start from a trained FISM (config key fism_pretrain =
+        the FISM checkpoint directory), as the NAIS paper prescribes.  The reference defines the restore but never calls it and
+        its shipped conf has no such key; here it runs when the key is present and a checkpoint exists.  Explicit `init` wins."""
+        from ...utils.tools import latest_checkpoint, load_checkpoint
+        ckpt = latest_checkpoint(self.configs.get('fism_pretrain'))
+        if ckpt is None:
+            if 'fism_pretrain' in self.configs:
+                self.logger.info(' fism_pretrain=%s holds no checkpoint: training from scratch' % self.configs['fism_pretrain'])
+            return init
+        v = load_checkpoint(ckpt)
+        out = {'P': v['FISM_paras/P'], 'Q': v['FISM_params/Q'], 'bias': v['FISM_params/b']}
+        out.update(init or {})
+        self.logger.info(' restored P, Q, bias from %s' % ckpt)
+        return out
+
+    def _variables(self):   # NAIS_single.py:99-106
+        d, a = self.embed_size, self.atten_size
+        return {'NAIS_paras/P': self.P.w, 'NAIS_params/Q': self.Q.w, 'NAIS_params/bias': self.bias, 'NAIS_params/W': self.dense[:d * a].reshape(d, a),
+                'NAIS_params/b': self.dense[d * a:d * a + a], 'NAIS_params/h': self.dense[d * a + a:d * a + 2 * a]}
 
     @property
     def bias(self):

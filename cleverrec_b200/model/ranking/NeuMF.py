@@ -59,7 +59,40 @@ class NeuMF(_rr.RankingRecommender):
         self.dense_s2 = torch.zeros_like(self.dense) if kind == 'Adam' else None
 
     def build_model(self, init=None):
-        self._create_params(init)
+        self._create_params(self._with_pretrained(init))
+
+    def _with_pretrained(self, init):
+        """NeuMF.py:46-56,127-139: when both gmf_pretrain and mlp_pretrain name checkpoint directories, the GMF branch starts from a
+        trained GMF ('GMF_params/{P,Q,h_gmf}'), the MLP branch from a trained MLP ('MLP_params/{P,Q,h_mlp,W_k,b_k}'), and
+        h_neumf = 0.5 * concat(h_gmf, h_mlp).  The shipped conf names ./saved_model/{GMF,MLP}, which nothing ever writes in the
+        reference (saver.save is commented out) so its restore raises; here missing checkpoints are logged and skipped.
+        Explicit `init` entries win."""
+        from ...utils.tools import latest_checkpoint, load_checkpoint
+        if not ('gmf_pretrain' in self.configs and 'mlp_pretrain' in self.configs):
+            return init
+        g, m = latest_checkpoint(self.configs['gmf_pretrain']), latest_checkpoint(self.configs['mlp_pretrain'])
+        if g is None or m is None:
+            self.logger.info(' gmf_pretrain / mlp_pretrain hold no checkpoint: training from scratch')
+            return init
+        vg, vm = load_checkpoint(g), load_checkpoint(m)
+        out = {'P_gmf': vg['GMF_params/P'], 'Q_gmf': vg['GMF_params/Q'], 'P_mlp': vm['MLP_params/P'], 'Q_mlp': vm['MLP_params/Q']}
+        for k in range(len(self.layers)):
+            out['W_%d' % k], out['b_%d' % k] = vm['MLP_params/W_%d' % k], vm['MLP_params/b_%d' % k]
+        out['h_neumf'] = 0.5 * np.concatenate([vg['GMF_params/h_gmf'], vm['MLP_params/h_mlp']])
+        out.update(init or {})
+        self.logger.info(' restored the GMF branch from %s and the MLP branch from %s' % (g, m))
+        return out
+
+    def _variables(self):   # NeuMF.py:107-116; plus the two halves of h_neumf under the GMF / MLP names so that a NeuMF
+        # checkpoint can itself seed a later run's gmf_pretrain / mlp_pretrain
+        layout, _ = self.dense_layout()
+        out = {'NeuMF_params/P_gmf': self.P_gmf.w, 'NeuMF_params/Q_gmf': self.Q_gmf.w, 'NeuMF_params/P_mlp': self.P_mlp.w,
+               'NeuMF_params/Q_mlp': self.Q_mlp.w}
+        for name, (off, shape) in layout.items():
+            out['NeuMF_params/' + name] = self.dense[off:off + int(np.prod(shape))].reshape(shape)
+        h = out['NeuMF_params/h_neumf']
+        out['NeuMF_params/h_gmf'], out['NeuMF_params/h_mlp'] = h[:self.embed_size], h[self.embed_size:]
+        return out
 
     def train_step(self, u_idx, i_idx, y, loss_out=None):
         """sess.run([train, loss], {u_idx, i_idx, y})  (NeuMF.py:87-95)."""

@@ -100,3 +100,39 @@ def get_optimizer(optimizer, lr, adam_mode='tf1'):
     if optimizer in ('SGD', 'Adam', 'Adagrad'):
         return Optimizer(optimizer, lr, adam_mode=adam_mode)
     return None
+
+
+# ------------------------------------------------------------------------------------------------ checkpoints
+# The reference builds a tf.train.Saver per model with an explicit variable-name map (BPR.py:53-58, GMF.py:59-64,
+# NeuMF.py:107-116, FISM.py:72-77, NAIS_single.py:99-106) and restores by those names for pretraining (NeuMF.py:127-139,
+# NAIS_single.py:35-38); its `saver.save` call is commented out (RankingRecommender.py:432-433).  Here a checkpoint is one
+# `.npz` per save under <saved_dir>/<model>/, keyed by the SAME variable names (typos such as 'FISM_paras/P' included, because
+# the restore side spells them the same way), fp32 arrays.
+def save_checkpoint(directory, model, variables, step=None):
+    """variables: dict name -> torch tensor / ndarray.  Returns the file written."""
+    import numpy as np
+    os.makedirs(directory, exist_ok=True)
+    path = os.path.join(directory, model + ('' if step is None else '-%d' % step) + '.npz')
+    arrays = {}
+    for name, v in variables.items():
+        a = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+        arrays[name.replace('/', '__')] = np.ascontiguousarray(a, dtype=np.float32)
+    tmp = path + '.tmp.npz'
+    np.savez(tmp, **arrays)
+    os.replace(tmp, path)
+    return path
+
+
+def latest_checkpoint(directory):
+    """tf.train.latest_checkpoint: newest `.npz` in the directory, or None."""
+    if not directory or not os.path.isdir(directory):
+        return None
+    files = [os.path.join(directory, f) for f in os.listdir(directory) if f.endswith('.npz') and not f.endswith('.tmp.npz')]
+    return max(files, key=os.path.getmtime) if files else None
+
+
+def load_checkpoint(path):
+    """-> dict variable name -> fp32 ndarray."""
+    import numpy as np
+    with np.load(path) as z:
+        return {k.replace('__', '/'): z[k] for k in z.files}

@@ -8,6 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+REFERENCE_ROOT = os.environ.get("CRB_REFERENCE_ROOT", "/root/reference")   # read-only mount; absent on the GPU box
 
 
 def pytest_configure(config):

@@ -76,3 +76,23 @@ def test_training_improves_ranking_quality(split_loo):
         m.train_model()
     hr1 = np.mean(m.test_model_loo()[0][0])
     assert hr1 > hr0 + 0.1  # random init ~0.10 -> learned
+
+
+def test_native_history_path_trains_identically(split_loo):
+    """data.train_rows (packaged RankingPreprocess) -> Engine.build_history gives the same epoch, losses and tables as the dict path."""
+    from conftest import Data
+    tu = np.repeat(np.asarray(list(split_loo.ui_train.keys()), dtype=np.int32), [len(v) for v in split_loo.ui_train.values()])
+    ti = np.asarray([i for v in split_loo.ui_train.values() for i in v], dtype=np.int32)
+    with_rows = Data(split_loo.user_nums, split_loo.item_nums, split_loo.ui_train, split_loo.ui_test)
+    with_rows.train_rows = (tu, ti)
+    a, b = _model(split_loo, optimizer='Adagrad', lr=0.05), _model(with_rows, optimizer='Adagrad', lr=0.05)
+    # same sampled epoch (the sampler is integer-exact), so the two runs differ only by the summation order of hub rows with more
+    # than 32 occurrences in a batch (slot order, SURVEY 8e 'Determinism'): equal to fp32 round-off
+    ua, ia, ja = a.engine.sample_pairwise(5, 0, 0, 4096, 4)
+    ub, ib, jb = b.engine.sample_pairwise(5, 0, 0, 4096, 4)
+    assert torch.equal(ua, ub) and torch.equal(ia, ib) and torch.equal(ja, jb)
+    la, lb = a.train_model(), b.train_model()
+    assert abs(la - lb) <= 1e-7 * abs(la)
+    assert torch.allclose(a.P.w, b.P.w, rtol=1e-5, atol=1e-7) and torch.allclose(a.Q.w, b.Q.w, rtol=1e-5, atol=1e-7)
+    ha, hb = a.test_model_loo(), b.test_model_loo()
+    assert abs(np.mean(ha[0][0]) - np.mean(hb[0][0])) < 0.01

@@ -131,3 +131,77 @@ def test_numpy_stream_training_follows_the_reference_triplets():
     assert abs(got - total / tr[0]) <= 1e-5 * abs(total / tr[0])
     np.testing.assert_allclose(m.P.w.cpu().numpy(), ref["P"].numpy(), rtol=2e-5, atol=1e-6)
     np.testing.assert_allclose(m.Q.w.cpu().numpy(), ref["Q"].numpy(), rtol=2e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ checkpoints / pretraining
+def test_checkpoint_round_trip_every_model(tmp_path):
+    """save_model() writes the reference's Saver variable names; the arrays are the (flushed) tables."""
+    from cleverrec_b200.utils.tools import latest_checkpoint, load_checkpoint
+    data = _data('loo', 49)
+    names = {'BPR': {'BPR_params/P', 'BPR_params/Q'}, 'GMF': {'GMF_params/P', 'GMF_params/Q', 'GMF_params/h_gmf'},
+             'CML': {'cml_params/P', 'cml_params/Q'}, 'FISM': {'FISM_paras/P', 'FISM_params/Q', 'FISM_params/b'},
+             'NAIS_single': {'NAIS_paras/P', 'NAIS_params/Q', 'NAIS_params/bias', 'NAIS_params/W', 'NAIS_params/b', 'NAIS_params/h'}}
+    for name, want in names.items():
+        m = _model(name, data, saved_dir=str(tmp_path))
+        m.train_model()
+        path = m.save_model()
+        assert path == latest_checkpoint(str(tmp_path / name))
+        v = load_checkpoint(path)
+        assert set(v) == want, name
+        for key, arr in v.items():
+            assert arr.dtype == np.float32 and np.all(np.isfinite(arr))
+        first = sorted(want)[0]
+        table = m.P.w if first.endswith('/P') else None
+        if table is not None:
+            assert np.array_equal(v[first], table.cpu().numpy())   # after the flush: what evaluation would read
+
+
+def test_run_model_saves_on_best_when_asked(tmp_path):
+    from cleverrec_b200.utils.tools import latest_checkpoint
+    m = _model('BPR', _data('loo', 49), saved_dir=str(tmp_path), save_model='True', epoches=2)
+    m.run_model()
+    assert latest_checkpoint(str(tmp_path / 'BPR')) is not None
+    m2 = _model('BPR', _data('loo', 49), saved_dir=str(tmp_path / 'off'), epoches=1)   # default: the reference never saves
+    m2.run_model()
+    assert latest_checkpoint(str(tmp_path / 'off' / 'BPR')) is None
+
+
+def test_nais_starts_from_trained_fism(tmp_path):
+    """NAIS_single.py:35-38: P, Q, bias restored from the FISM checkpoint by the reference's variable names."""
+    data = _data('loo', 49)
+    f = _model('FISM', data, saved_dir=str(tmp_path))
+    for _ in range(3):
+        f.train_model()
+    f.save_model()
+    n = _model('NAIS_single', data, fism_pretrain=str(tmp_path / 'FISM'))
+    assert np.array_equal(n.P.w.cpu().numpy(), f.P.w.cpu().numpy()) and np.array_equal(n.Q.w.cpu().numpy(), f.Q.w.cpu().numpy())
+    assert np.array_equal(n.bias.cpu().numpy(), f.b.cpu().numpy())
+    assert np.isfinite(n.train_model())
+    fresh = _model('NAIS_single', data, fism_pretrain=str(tmp_path / 'nothing_here'))   # no checkpoint: logged, trains from scratch
+    assert not np.array_equal(fresh.P.w.cpu().numpy(), f.P.w.cpu().numpy())
+
+
+def test_neumf_starts_from_gmf_and_mlp_checkpoints(tmp_path):
+    """NeuMF.py:46-56,127-139: branches restored by name, h_neumf = 0.5 * concat(h_gmf, h_mlp).  The MLP branch comes from a NeuMF
+    checkpoint re-keyed to the 'MLP_params/*' names (the standalone MLP model is outside the hot-path scope)."""
+    from cleverrec_b200.utils.tools import load_checkpoint, save_checkpoint
+    data = _data('loo', 49)
+    g = _model('GMF', data, saved_dir=str(tmp_path), embed_size=16)
+    g.train_model()
+    g.save_model()
+    donor = _model('NeuMF', data, saved_dir=str(tmp_path))
+    donor.train_model()
+    v = load_checkpoint(donor.save_model())
+    mlp = {'MLP_params/P': v['NeuMF_params/P_mlp'], 'MLP_params/Q': v['NeuMF_params/Q_mlp'], 'MLP_params/h_mlp': v['NeuMF_params/h_mlp']}
+    for k in range(3):
+        mlp['MLP_params/W_%d' % k], mlp['MLP_params/b_%d' % k] = v['NeuMF_params/W_%d' % k], v['NeuMF_params/b_%d' % k]
+    save_checkpoint(str(tmp_path / 'MLP'), 'MLP', mlp)
+    m = _model('NeuMF', data, gmf_pretrain=str(tmp_path / 'GMF'), mlp_pretrain=str(tmp_path / 'MLP'))
+    assert np.array_equal(m.P_gmf.w.cpu().numpy(), g.P.w.cpu().numpy()) and np.array_equal(m.Q_mlp.w.cpu().numpy(), v['NeuMF_params/Q_mlp'])
+    layout, _ = m.dense_layout()
+    off, shape = layout['h_neumf']
+    want_h = 0.5 * np.concatenate([g.h_gmf.cpu().numpy(), v['NeuMF_params/h_mlp']])
+    assert np.array_equal(m.dense[off:off + shape[0]].cpu().numpy(), want_h.astype(np.float32))
+    off, shape = layout['W_1']
+    assert np.array_equal(m.dense[off:off + shape[0] * shape[1]].cpu().numpy().reshape(shape), v['NeuMF_params/W_1'])
+    assert np.isfinite(m.train_model())

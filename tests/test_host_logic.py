@@ -45,3 +45,17 @@ def test_initializers_and_config_parsing():
     assert float(t.abs().max()) <= 1.0
     assert get_initializer('nope', 0.1) is None
     assert re_index(['b', 'a']) == {'b': 0, 'a': 1}
+
+
+def test_checkpoint_helpers_round_trip(tmp_path):
+    import time
+    import torch
+    from cleverrec_b200.utils.tools import latest_checkpoint, load_checkpoint, save_checkpoint
+    assert latest_checkpoint(str(tmp_path / "missing")) is None and latest_checkpoint(None) is None
+    a = save_checkpoint(str(tmp_path / "GMF"), "GMF", {"GMF_params/P": torch.arange(6.0).reshape(2, 3), "GMF_params/h_gmf": np.ones(3)})
+    time.sleep(0.02)
+    b = save_checkpoint(str(tmp_path / "GMF"), "GMF", {"GMF_params/P": torch.zeros(2, 3)}, step=7)
+    assert latest_checkpoint(str(tmp_path / "GMF")) == b and a != b
+    v = load_checkpoint(a)
+    assert set(v) == {"GMF_params/P", "GMF_params/h_gmf"} and v["GMF_params/P"].dtype == np.float32
+    assert v["GMF_params/P"].tolist() == [[0.0, 1.0, 2.0], [3.0, 4.0, 5.0]]
