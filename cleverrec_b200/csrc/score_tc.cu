@@ -505,17 +505,61 @@ __global__ void __launch_bounds__(256) rescore_kernel(RescoreArgs a) {
         const float* p = a.P + (int64_t)a.users[g] * a.dim;
         float theta = -INFINITY;
         int total = 0;
+        // error bound of one approximate score for this user (same expression as the certificate below)
+        float eps;
+        {
+            const float qmax = __uint_as_float(a.maxbits[0]);
+            if (KIND == CRB_SCORE_SQDIST) { const float s_ = a.pnorm[g] + qmax; eps = a.cbound * s_ * s_; }
+            else { eps = a.cbound * a.pnorm[g] * qmax; if (KIND == CRB_SCORE_DOT_BIAS) eps += a.cbound * __uint_as_float(a.maxbits[1]); }
+        }
+        // Pre-filter on the APPROXIMATE scores: with T <= the K-th best approximate score of the user's candidates, a candidate
+        // whose approximate score is below T - 2 eps has at least K candidates canonically above it (|approx - canonical| <= eps
+        // for both), so it cannot be in the top K and needs no fp32 dot product.  T is found by bisection on the order-preserving
+        // score bits (count >= K keeps T a lower bound; stop once the count is within [K, 2K]).  This does not touch theta.
+        uint32_t lo_b = 0xFFFFFFFFu, hi_b = 0u;
+        for (int sp = 0; sp < a.n_splits; ++sp) {
+            const int64_t slot = (int64_t)sp * a.n_users_pad + g;
+            const int n = a.cand_cnt[slot];
+            const unsigned long long* list = a.cand + slot * TC_C;
+            for (int k = lane; k < n; k += 32) {
+                const uint32_t o = ord_bits((uint32_t)(list[k] >> 32));
+                lo_b = min(lo_b, o); hi_b = max(hi_b, o);
+            }
+            total += n;
+        }
+        lo_b = __reduce_min_sync(0xffffffffu, lo_b);
+        hi_b = __reduce_max_sync(0xffffffffu, hi_b);
+        uint32_t T_b = lo_b;   // count(o >= lo_b) = total: a valid (if useless) lower bound when total >= K
+        if (total > 2 * a.K) {
+            uint32_t lo = lo_b, hi = hi_b;   // invariant: count(o >= lo) >= K
+            for (int it = 0; it < 32 && lo < hi; ++it) {
+                const uint32_t mid = lo + ((hi - lo + 1) >> 1);
+                int c = 0;
+                for (int sp = 0; sp < a.n_splits; ++sp) {
+                    const int64_t slot = (int64_t)sp * a.n_users_pad + g;
+                    const int n = a.cand_cnt[slot];
+                    const unsigned long long* list = a.cand + slot * TC_C;
+                    for (int k = lane; k < n; k += 32) c += ord_bits((uint32_t)(list[k] >> 32)) >= mid;
+                }
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (c >= a.K) { lo = mid; if (c <= 2 * a.K) break; } else hi = mid - 1;
+            }
+            T_b = lo;
+        }
+        const float T_f = __uint_as_float((T_b & 0x80000000u) ? (T_b & 0x7fffffffu) : ~T_b);
+        const float cutoff = (total > 2 * a.K) ? T_f - 2.f * eps : -INFINITY;
         for (int sp = 0; sp < a.n_splits; ++sp) {
             const int64_t slot = (int64_t)sp * a.n_users_pad + g;
             const int n = a.cand_cnt[slot];
             theta = fmaxf(theta, a.cand_thr[slot]);
             unsigned long long* list = a.cand + slot * TC_C;
-            for (int k = lane; k < n; k += 32) {  // canonical score, entry rewritten as a ranking key
-                const uint32_t item = (uint32_t)list[k];
+            for (int k = lane; k < n; k += 32) {  // canonical score, entry rewritten as a ranking key (0 = filtered out)
+                const unsigned long long e = list[k];
+                const uint32_t item = (uint32_t)e;
+                if (__uint_as_float((uint32_t)(e >> 32)) < cutoff) { list[k] = 0ULL; continue; }
                 const float sc = canonical_score<KIND>(p, a.Q + (int64_t)item * a.dim, a.hvec, (int32_t)item, a.dim);
                 list[k] = rank_key(sc, item, ASC);
             }
-            total += n;
         }
         __syncwarp();
         if (lane == 0) atomicMax(a.counters + 1, (unsigned int)total);
