@@ -76,7 +76,7 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------------------------- synthetic data (device)
-def build_history_device(torch, dev, users, items, mean_hist, seed, user_lo=0, user_hi=None):
+def build_history_device(torch, dev, users, items, mean_hist, seed, user_lo=0, user_hi=None, zipf=False):
     """Per-user sorted unique histories for users [user_lo, user_hi) drawn on the device, chunk by chunk.
     Returns (pos_user int32 [global ids], pos_item int32, rowptr int64 over ALL `users` rows)."""
     user_hi = users if user_hi is None else user_hi
@@ -89,7 +89,10 @@ def build_history_device(torch, dev, users, items, mean_hist, seed, user_lo=0, u
         lens = torch.clamp((torch.rand(b - a, device=dev, generator=g) * 2 * (mean_hist - 1)).long() + 1, max=items // 2)
         tot = int(lens.sum().item())
         uid = torch.repeat_interleave(torch.arange(a, b, device=dev, dtype=torch.int64), lens)
-        it = torch.randint(0, items, (tot,), device=dev, generator=g, dtype=torch.int64)
+        if zipf:   # Zipf(1.0) item popularity (SURVEY 8d 'hub contention' variant): rank = floor(I^U), item 0 is the hub
+            it = torch.clamp(torch.exp(torch.rand(tot, device=dev, generator=g, dtype=torch.float64) * math.log(items)).long() - 1, 0, items - 1)
+        else:
+            it = torch.randint(0, items, (tot,), device=dev, generator=g, dtype=torch.int64)
         key = torch.unique(uid * items + it)  # sorted, duplicates dropped
         del uid, it
         ku = torch.div(key, items, rounding_mode="floor")
@@ -185,7 +188,7 @@ def run_ours(args, w):
     # row-sharded (owner = item % N) and read / updated over NVLink peer memory (cleverrec_b200/dist.py) ----
     u_lo, u_hi = (users * rank) // world, (users * (rank + 1)) // world
     t_setup = time.time()
-    pu, pi, rowptr = build_history_device(torch, dev, u_hi - u_lo, items, w["mean_hist"], seed=1234 + rank)
+    pu, pi, rowptr = build_history_device(torch, dev, u_hi - u_lo, items, w["mean_hist"], seed=1234 + rank, zipf=args.item_popularity == "zipf")
     eng.set_history_arrays(u_hi - u_lo, items, pu, pi, rowptr, pi)
     n_pos = int(pu.numel())
     g = torch.Generator(device=dev).manual_seed(rank)
@@ -352,7 +355,7 @@ def run_ours(args, w):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": args.workload, "users": users, "items": items, "dim": dim, "interactions_per_gpu": n_pos, "batch_per_gpu": B,
-                           "neg_ratio": R, "optimizer": opt_kind, "adam_mode": adam_mode if opt_kind == "Adam" else None, "reg": reg,
+                           "neg_ratio": R, "item_popularity": args.item_popularity, "optimizer": opt_kind, "adam_mode": adam_mode if opt_kind == "Adam" else None, "reg": reg,
                            "l2_policy": "inputs larger than L2 (tables %.1f GB vs 126 MB L2)" % ((users + items) * dim * 4 / 1e9),
                            "parallelism": ("single GPU" if world == 1 else "%d ranks: users partitioned, item table row-sharded (item %% N), rows and gradients "
                                            "over NVLink peer memory, NCCL only as the step barrier" % world), "inbox_overflow": overflow,
@@ -376,6 +379,8 @@ def main():
     ap.add_argument("--eval-users", dest="eval_users", type=int, default=262144)
     ap.add_argument("--eval-exact", dest="eval_exact", action="store_true")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--item-popularity", dest="item_popularity", default="uniform", choices=["uniform", "zipf"],
+                    help="popularity of the positives' items in the synthetic history (zipf = Zipf(1.0): hub rows repeat ~10^4 times per batch)")
     ap.add_argument("--sharded", action="store_true", help="use the multi-GPU code path even at N=1 (experiments)")
     ap.add_argument("--users", type=int, default=0, help="override the workload's user count (experiments)")
     ap.add_argument("--items", type=int, default=0)

@@ -411,21 +411,42 @@ __global__ void __launch_bounds__(256, 3) bpr_step_kernel(BprArgs a) {
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     double loss_acc = 0.0;
-    for (int64_t base = warp * GPW; base < a.batch; base += n_warps * GPW) {
+    // Software pipeline over the index side: the triplet's ids are fetched two iterations ahead and its multiplicity words / `last`
+    // steps one iteration ahead, so that when an iteration starts everything that decides WHICH rows and slots to load is already
+    // in registers and the weights and optimizer slots go out in one round trip (instead of ids -> meta -> slots, three dependent
+    // round trips: the SGD / Adagrad variants were latency bound on that chain).  Out-of-range iterations clamp (loads only).
+    // The Adam variants sit at the 85-register limit of three CTAs per SM and are bandwidth bound already: there the extra live
+    // registers spill and the pipeline costs 20 % (measured), so they keep the plain order.
+    constexpr bool PIPE = !OptTraits<OPT>::has_s2;
+    const int64_t stride = n_warps * GPW;
+    const int64_t base0 = warp * GPW;
+    auto clampt = [&](int64_t b_) { const int64_t t_ = b_ + sub; return t_ < a.batch ? t_ : a.batch - 1; };
+    int32_t nu = 0, ni = 0, nj = 0, fu = 0, fi = 0, fj = 0;
+    unsigned long long nmu = 0, nmi = 0, nmj = 0;
+    int32_t nlu = 0, nli = 0, nlj = 0;
+    if (PIPE) {
+        { const int64_t t0 = clampt(base0); nu = a.u[t0]; ni = a.i[t0]; nj = a.j[t0]; }
+        { const int64_t t1 = clampt(base0 + stride); fu = a.u[t1]; fi = a.i[t1]; fj = a.j[t1]; }
+        nmu = a.metaU[nu]; nmi = a.metaI[ni]; nmj = a.metaI[nj];
+    }
+    for (int64_t base = base0; base < a.batch; base += stride) {
         const int64_t t = base + sub;
         const bool active = t < a.batch;
-        const int64_t tt = active ? t : a.batch - 1;
-        const int32_t u = a.u[tt], i = a.i[tt], j = a.j[tt];
-        const unsigned long long mu = a.metaU[u], mi = a.metaI[i], mj = a.metaI[j];
+        if (!PIPE) {
+            const int64_t tt = clampt(base);
+            nu = a.u[tt]; ni = a.i[tt]; nj = a.j[tt];
+            nmu = a.metaU[nu]; nmi = a.metaI[ni]; nmj = a.metaI[nj];
+            if (OptTraits<OPT>::replay) { nlu = a.P.last[nu]; nli = a.Q.last[ni]; nlj = a.Q.last[nj]; }
+        }
+        const int32_t u = nu, i = ni, j = nj;
+        const unsigned long long mu = nmu, mi = nmi, mj = nmj;
         RowRegs<LANES, VPL> ru, ri, rj;
+        ru.last = nlu; ri.last = nli; rj.last = nlj;
         row_load_w<LANES, VPL>(ru, a.P, u, a.dim, gl);
         row_load_w<LANES, VPL>(ri, a.Q, i, a.dim, gl);
         row_load_w<LANES, VPL>(rj, a.Q, j, a.dim, gl);
         // optimizer slots are needed here only for rows this group will update in place, or -- CRB_ADAM_TF1 -- rows with
         // missed decay steps, because the forward must see the replayed (dense-equivalent) value.
-        ru.last = OptTraits<OPT>::replay ? a.P.last[u] : 0;
-        ri.last = OptTraits<OPT>::replay ? a.Q.last[i] : 0;
-        rj.last = OptTraits<OPT>::replay ? a.Q.last[j] : 0;
         const bool su = (uint32_t)mu == 1u || replay_pending<OPT>(ru.last, a.opt);
         const bool si = (uint32_t)mi == 1u || replay_pending<OPT>(ri.last, a.opt);
         const bool sj = (uint32_t)mj == 1u || replay_pending<OPT>(rj.last, a.opt);
@@ -433,6 +454,13 @@ __global__ void __launch_bounds__(256, 3) bpr_step_kernel(BprArgs a) {
             if (su) row_load_state<LANES, VPL, OPT>(ru, a.P, u, a.dim, gl);
             if (si) row_load_state<LANES, VPL, OPT>(ri, a.Q, i, a.dim, gl);
             if (sj) row_load_state<LANES, VPL, OPT>(rj, a.Q, j, a.dim, gl);
+        }
+        // rotate the index pipeline: next iteration's multiplicity words / last steps, and the ids after that
+        if (PIPE) {
+            nu = fu; ni = fi; nj = fj;
+            nmu = a.metaU[nu]; nmi = a.metaI[ni]; nmj = a.metaI[nj];
+            const int64_t t2 = clampt(base + 2 * stride);
+            fu = a.u[t2]; fi = a.i[t2]; fj = a.j[t2];
         }
         if (replay_pending<OPT>(ru.last, a.opt)) row_replay<LANES, VPL, OPT>(ru, a.opt, a.opt.step);
         if (replay_pending<OPT>(ri.last, a.opt)) row_replay<LANES, VPL, OPT>(ri, a.opt, a.opt.step);
