@@ -24,7 +24,7 @@ EXPORTS = [
     "crb_train_step_neumf", "crb_score_pairs_neumf", "crb_mask_seen",
     "crb_sample_nais", "crb_train_step_nais", "crb_train_epoch_nais", "crb_score_nais",
     "crb_shard_step_compute", "crb_shard_step_prepare", "crb_shard_apply_inbox", "crb_shard_inbox_overflow", "crb_malloc", "crb_free", "crb_ipc_export",
-    "crb_ipc_open", "crb_ipc_close", "crb_build_history", "crb_np_seed", "crb_np_set_state", "crb_np_get_state", "crb_sample_epoch_numpy",
+    "crb_ipc_open", "crb_ipc_close", "crb_build_history", "crb_set_item_lists", "crb_train_step_transcf", "crb_transcf_neighbourhood", "crb_score_pairs_transcf", "crb_np_seed", "crb_np_set_state", "crb_np_get_state", "crb_sample_epoch_numpy",
 ]
 
 
@@ -106,6 +106,10 @@ def load():
     lib.crb_score_nais.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, i32, vp, i32, f32, vp, vp]
     S = C.POINTER(CrbShard)
     lib.crb_shard_step_compute.argtypes = [vp, T, S, O, vp, vp, vp, u64, u32, i64, i32, i64, f32, vp, vp]
+    lib.crb_set_item_lists.argtypes = [vp, vp, vp, vp]
+    lib.crb_train_step_transcf.argtypes = [vp, T, T, vp, vp, O, vp, vp, vp, i64, f32, f32, f32, vp, vp]
+    lib.crb_transcf_neighbourhood.argtypes = [vp, i32, vp, i32, vp, i64, vp, vp]
+    lib.crb_score_pairs_transcf.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, i64, vp, vp]
     lib.crb_shard_step_prepare.argtypes = [vp, T, u64, u32, i64, i32, i64, i64, vp]
     lib.crb_shard_apply_inbox.argtypes = [vp, S, O, vp]
     lib.crb_shard_inbox_overflow.argtypes = [vp, S, C.POINTER(i32), vp]

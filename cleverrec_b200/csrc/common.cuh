@@ -68,6 +68,9 @@ struct crb_handle {
     const int32_t* seen_cols;
     const int64_t* list_start;  // per-user offset / length of the interaction list inside pos_item (FISM / NAIS)
     const int32_t* list_len;
+    const int64_t* ilist_start; // item-side lists (TransCF's iu_sp_mat, utils/tools.py:100-113): users of each item inside ipos_user
+    const int32_t* ilist_len;
+    const int32_t* ipos_user;
     double* dense_loss;         // [4 * loss_blocks] per-block partials of the dense loss terms
     // per-row batch multiplicity words: low 32 bits = count, high 32 bits = slot base
     unsigned long long* meta[2];

@@ -584,6 +584,276 @@ extern "C" int crb_clip_rows(crb_handle* h, const float* src, float* dst, int64_
     return CRB_OK;
 }
 
+int crb_dense_table_apply(crb_handle* h, const crb_table* T, float* grad, int opt_kind, const OptDev& od, float l2, double* loss_part,
+                          int* grid_out, cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------------ TransCF
+// model/ranking/TransCF.py:38-71.  alpha_u = mean of Q over the user's training items (ui_sp_mat, utils/tools.py:100-113: values
+// 1/len(items), duplicates counted), beta_i = mean of P over the item's users (iu_sp_mat: values 1/iu_nums[i]);
+//   e_i = p_u + alpha_u * beta_i - q_i,  d_ui = |e_i|^2  (same for j);  loss = sum max(d_ui - d_uj + margin, 0)   (tools.py:73)
+//        + reg1 * (|p_u - alpha_u|^2 + |q_i - beta_i|^2) + reg2 * (d_ui + margin - d_uj)^2                            (:65-71)
+// The reference recomputes both SpMMs over ALL interactions every step; only the rows the batch touches are needed, so here a lane
+// group builds alpha_u, beta_i, beta_j for its triplet from the two CSR-style lists and scatters the neighbourhood gradients back
+// through them.  The table gradients are dense in TF (they flow through the SpMMs), hence the dense optimizer apply.
+struct TcfArgs {
+    const float* P;
+    const float* Q;
+    float* gP;
+    float* gQ;
+    const int32_t* u;
+    const int32_t* i;
+    const int32_t* j;
+    const int64_t* ul_start;   // user -> items list inside upos
+    const int32_t* ul_len;
+    const int32_t* upos;
+    const int64_t* il_start;   // item -> users list inside ipos
+    const int32_t* il_len;
+    const int32_t* ipos;
+    int64_t batch;
+    int dim;
+    float margin, reg1, reg2;
+    double* loss_part;
+};
+
+// mean of `table` rows members[0..n) in list order: acc = fma(x, 1/n, acc)  (the canonical order; restated in the tests' oracle)
+template <int LANES, int VPL>
+__device__ __forceinline__ void seg_mean(float4* s, const float* __restrict__ table, const int32_t* __restrict__ members, int n, int dim, int gl) {
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) s[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n <= 0) return;
+    const float inv = 1.f / (float)n;
+    for (int k = 0; k < n; ++k) {
+        const int64_t row = members[k];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const int c = (gl + LANES * v) * 4;
+            if (c < dim) {
+                const float4 x = ld4(table + row * dim + c);
+                s[v].x = fmaf(x.x, inv, s[v].x); s[v].y = fmaf(x.y, inv, s[v].y); s[v].z = fmaf(x.z, inv, s[v].z); s[v].w = fmaf(x.w, inv, s[v].w);
+            }
+        }
+    }
+}
+
+template <int LANES, int VPL>
+__device__ __forceinline__ void seg_scatter(float* __restrict__ grad, const int32_t* __restrict__ members, int n, const float4* g, int dim, int gl) {
+    if (n <= 0) return;
+    const float inv = 1.f / (float)n;
+    for (int k = 0; k < n; ++k) {
+        const int64_t row = members[k];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const int c = (gl + LANES * v) * 4;
+            if (c < dim) atomic_add4(grad + row * dim + c, make_float4(g[v].x * inv, g[v].y * inv, g[v].z * inv, g[v].w * inv));
+        }
+    }
+}
+
+__device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 f4_sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_scale(float4 a, float k) { return make_float4(a.x * k, a.y * k, a.z * k, a.w * k); }
+
+template <int LANES, int VPL>
+__global__ void __launch_bounds__(256) transcf_step_kernel(TcfArgs a) {
+    constexpr int GPW = 32 / LANES;
+    const int lane = threadIdx.x & 31, gl = lane % LANES, sub = lane / LANES;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double loss = 0.0;
+    for (int64_t base = warp * GPW; base < a.batch; base += n_warps * GPW) {
+        const int64_t t = base + sub;
+        const bool active = t < a.batch;
+        const int64_t tt = active ? t : a.batch - 1;
+        const int32_t u = a.u[tt], it = a.i[tt], jt = a.j[tt];
+        const int32_t* u_items = a.upos + a.ul_start[u];
+        const int32_t* i_users = a.ipos + a.il_start[it];
+        const int32_t* j_users = a.ipos + a.il_start[jt];
+        const int nu = a.ul_len[u], ni = a.il_len[it], nj = a.il_len[jt];
+        float4 al[VPL], bi[VPL], bj[VPL], p[VPL], qi[VPL], qj[VPL], ei[VPL], ej[VPL];
+        seg_mean<LANES, VPL>(al, a.Q, u_items, nu, a.dim, gl);
+        seg_mean<LANES, VPL>(bi, a.P, i_users, ni, a.dim, gl);
+        seg_mean<LANES, VPL>(bj, a.P, j_users, nj, a.dim, gl);
+        float dui = 0.f, duj = 0.f, rn = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const int c = (gl + LANES * v) * 4;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            p[v] = c < a.dim ? ld4(a.P + (int64_t)u * a.dim + c) : z;
+            qi[v] = c < a.dim ? ld4(a.Q + (int64_t)it * a.dim + c) : z;
+            qj[v] = c < a.dim ? ld4(a.Q + (int64_t)jt * a.dim + c) : z;
+            ei[v] = f4_sub(f4_add(p[v], f4_mul(al[v], bi[v])), qi[v]);
+            ej[v] = f4_sub(f4_add(p[v], f4_mul(al[v], bj[v])), qj[v]);
+            dui += dot4(ei[v], ei[v]);
+            duj += dot4(ej[v], ej[v]);
+            const float4 pa = f4_sub(p[v], al[v]), qb = f4_sub(qi[v], bi[v]);
+            rn += dot4(pa, pa) + dot4(qb, qb);
+        }
+        dui = group_sum<LANES>(dui);
+        duj = group_sum<LANES>(duj);
+        rn = group_sum<LANES>(rn);
+        const float x = dui - duj + a.margin;   // hinge argument and the residual of the distance regulariser
+        const float cgrad = (x > 0.f ? 1.f : 0.f) + 2.f * a.reg2 * x;   // dL/dd_ui = -dL/dd_uj
+        if (active) {
+            if (gl == 0) loss += (double)fmaxf(x, 0.f) + (double)a.reg1 * (double)rn + (double)a.reg2 * (double)x * (double)x;
+            float4 g_al[VPL], g_bi[VPL], g_bj[VPL];
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int c = (gl + LANES * v) * 4;
+                if (c >= a.dim) continue;
+                const float4 ci = f4_scale(ei[v], 2.f * cgrad), cj = f4_scale(ej[v], 2.f * cgrad);   // c * d d_ui/d e_i, c * d d_uj/d e_j
+                const float4 pa = f4_scale(f4_sub(p[v], al[v]), 2.f * a.reg1), qb = f4_scale(f4_sub(qi[v], bi[v]), 2.f * a.reg1);
+                atomic_add4(a.gP + (int64_t)u * a.dim + c, f4_add(f4_sub(ci, cj), pa));
+                atomic_add4(a.gQ + (int64_t)it * a.dim + c, f4_sub(qb, ci));
+                atomic_add4(a.gQ + (int64_t)jt * a.dim + c, cj);
+                g_al[v] = f4_sub(f4_sub(f4_mul(ci, bi[v]), f4_mul(cj, bj[v])), pa);
+                g_bi[v] = f4_sub(f4_mul(ci, al[v]), qb);
+                g_bj[v] = f4_scale(f4_mul(cj, al[v]), -1.f);
+            }
+            seg_scatter<LANES, VPL>(a.gQ, u_items, nu, g_al, a.dim, gl);
+            seg_scatter<LANES, VPL>(a.gP, i_users, ni, g_bi, a.dim, gl);
+            seg_scatter<LANES, VPL>(a.gP, j_users, nj, g_bj, a.dim, gl);
+        }
+    }
+    block_sum_to(loss, a.loss_part);
+}
+
+// out[r] = mean of `table` over the members of row rows[r] (or row r when rows == NULL): alpha for users, beta for items (evaluation)
+template <int LANES, int VPL>
+__global__ void __launch_bounds__(256) seg_mean_rows_kernel(const float* table, int dim, const int32_t* rows, int64_t n, const int64_t* start,
+                                                            const int32_t* len, const int32_t* members, float* out) {
+    constexpr int GPW = 32 / LANES;
+    const int lane = threadIdx.x & 31, gl = lane % LANES, sub = lane / LANES;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = warp * GPW; base < n; base += n_warps * GPW) {
+        const int64_t r = base + sub;
+        if (r >= n) continue;
+        const int64_t row = rows ? rows[r] : r;
+        float4 s[VPL];
+        seg_mean<LANES, VPL>(s, table, members + start[row], len[row], dim, gl);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const int c = (gl + LANES * v) * 4;
+            if (c < dim) st4(out + r * dim + c, s[v]);
+        }
+    }
+}
+
+// TransCF._predict (TransCF.py:79-85): dist(u, i) = sum_k (p_uk + A_uk * B_ik - q_ik)^2 as ONE sequential fp32 chain over k
+// (e = fma(A, B, p) - q; acc = fma(e, e, acc)); A = alpha of all users, B = beta of all items (seg_mean_rows_kernel).
+__global__ void __launch_bounds__(256) transcf_pairs_kernel(const float* __restrict__ P, const float* __restrict__ Q, const float* __restrict__ A,
+                                                            const float* __restrict__ B, int dim, const int32_t* __restrict__ u,
+                                                            const int32_t* __restrict__ it, int64_t n, float* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const float* p = P + (int64_t)u[k] * dim;
+        const float* al = A + (int64_t)u[k] * dim;
+        const float* q = Q + (int64_t)it[k] * dim;
+        const float* be = B + (int64_t)it[k] * dim;
+        float acc = 0.f;
+        for (int c = 0; c < dim; ++c) {
+            const float e = __fsub_rn(fmaf(al[c], be[c], p[c]), q[c]);
+            acc = fmaf(e, e, acc);
+        }
+        out[k] = acc;
+    }
+}
+
+template <int LANES, int VPL>
+static int launch_tcf_t(crb_handle* h, const TcfArgs& a, int grid, cudaStream_t s) {
+    transcf_step_kernel<LANES, VPL><<<grid, 256, 0, s>>>(a);
+    return CRB_OK;
+}
+template <int LANES, int VPL>
+static int launch_segmean_t(crb_handle* h, const float* table, int dim, const int32_t* rows, int64_t n, const int64_t* start, const int32_t* len,
+                            const int32_t* members, float* out, int grid, cudaStream_t s) {
+    seg_mean_rows_kernel<LANES, VPL><<<grid, 256, 0, s>>>(table, dim, rows, n, start, len, members, out);
+    return CRB_OK;
+}
+
+extern "C" int crb_set_item_lists(crb_handle* h, const int64_t* item_start, const int32_t* item_len, const int32_t* item_users) {
+    CRB_CHECK_ARG(h, "null handle");
+    CRB_CHECK_ARG(crb_is_device_ptr(item_start) && crb_is_device_ptr(item_len) && crb_is_device_ptr(item_users), "item lists must be device pointers");
+    h->ilist_start = item_start;
+    h->ilist_len = item_len;
+    h->ipos_user = item_users;
+    return CRB_OK;
+}
+
+extern "C" int crb_train_step_transcf(crb_handle* h, const crb_table* P, const crb_table* Q, float* gradP, float* gradQ, const crb_opt* opt,
+                                      const int32_t* u, const int32_t* i, const int32_t* j, int64_t batch, float margin, float reg1, float reg2,
+                                      double* loss_out, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    CRB_CHECK_ARG(h && u && i && j, "null argument");
+    CRB_CHECK_ARG(batch > 0, "batch");
+    if (!h->list_start || !h->pos_item || !h->ilist_start) {
+        crb_set_error("crb_train_step_transcf before crb_set_history / crb_set_history_lists / crb_set_item_lists");
+        return CRB_ERR_STATE;
+    }
+    OptDev od;
+    int opt_kind = 0;
+    int rc = crb_opt_to_dev(h, opt, &od, &opt_kind, s);
+    if (rc) return rc;
+    if ((rc = check_dense_table(P, gradP, opt_kind, "P"))) return rc;
+    if ((rc = check_dense_table(Q, gradQ, opt_kind, "Q"))) return rc;
+    CRB_CHECK_ARG(P->dim == Q->dim, "P.dim != Q.dim");
+    CRB_CUDA(cudaSetDevice(h->device));
+    const int dim = P->dim;
+    if ((rc = crb_ws_reserve(h, batch, dim, 4, s))) return rc;
+    const int32_t *du, *di, *dj;
+    if ((rc = stage_dev_i32(h, u, batch, h->idx[0], &du, s))) return rc;
+    if ((rc = stage_dev_i32(h, i, batch, h->idx[1], &di, s))) return rc;
+    if ((rc = stage_dev_i32(h, j, batch, h->idx[2], &dj, s))) return rc;
+    const int grid = dgrid(h, batch, 256 / 32);
+    TcfArgs a = {P->w, Q->w, gradP, gradQ, du, di, dj, h->list_start, h->list_len, h->pos_item, h->ilist_start, h->ilist_len, h->ipos_user,
+                 batch, dim, margin, reg1, reg2, h->block_loss};
+    if ((rc = crb_prof_begin(h, s))) return rc;
+    CRB_DIM_DISPATCH(dim, launch_tcf_t, h, a, grid, s);
+    if ((rc = crb_prof_end(h, s))) return rc;
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    double* dp = h->dense_loss;
+    int gp = 0, gq = 0;
+    if ((rc = crb_dense_table_apply(h, P, gradP, opt_kind, od, 0.f, dp, &gp, s))) return rc;
+    if ((rc = crb_dense_table_apply(h, Q, gradQ, opt_kind, od, 0.f, dp + gp, &gq, s))) return rc;
+    double* ld = (loss_out && crb_is_device_ptr(loss_out)) ? loss_out : h->loss_dev;
+    sum_parts_kernel<<<1, 32, 0, s>>>(h->block_loss, grid, dp, gp + gq, nullptr, 0, ld);
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    return finish_loss_host(h, loss_out, s);
+}
+
+// which = 0: alpha of `rows` users (mean of Q over their items);  which = 1: beta of `rows` items (mean of P over their users)
+extern "C" int crb_transcf_neighbourhood(crb_handle* h, int32_t which, const float* table, int32_t dim, const int32_t* rows, int64_t n, float* out,
+                                         void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    CRB_CHECK_ARG(h && table && out && (which == 0 || which == 1), "bad argument");
+    CRB_CHECK_ARG(dim % 4 == 0 && dim <= 512, "dim % 4 == 0, dim <= 512");
+    CRB_CHECK_ARG((!rows || crb_is_device_ptr(rows)) && crb_is_device_ptr(out), "rows/out must be device pointers");
+    if (which == 0 && (!h->list_start || !h->pos_item)) { crb_set_error("crb_transcf_neighbourhood before crb_set_history_lists"); return CRB_ERR_STATE; }
+    if (which == 1 && !h->ilist_start) { crb_set_error("crb_transcf_neighbourhood before crb_set_item_lists"); return CRB_ERR_STATE; }
+    if (n == 0) return CRB_OK;
+    const int64_t* st = which == 0 ? h->list_start : h->ilist_start;
+    const int32_t* ln = which == 0 ? h->list_len : h->ilist_len;
+    const int32_t* mem = which == 0 ? h->pos_item : h->ipos_user;
+    CRB_DIM_DISPATCH(dim, launch_segmean_t, h, table, dim, rows, n, st, ln, mem, out, dgrid(h, n, 8), s);
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}
+
+extern "C" int crb_score_pairs_transcf(crb_handle* h, const float* P, const float* Q, const float* A, const float* B, int32_t dim, const int32_t* u,
+                                       const int32_t* i, int64_t n, float* scores, void* stream) {
+    CRB_CHECK_ARG(h && P && Q && A && B && u && i && scores, "null argument");
+    CRB_CHECK_ARG(crb_is_device_ptr(u) && crb_is_device_ptr(i) && crb_is_device_ptr(scores), "u/i/scores must be device pointers");
+    if (n == 0) return CRB_OK;
+    transcf_pairs_kernel<<<dgrid(h, n, 256), 256, 0, (cudaStream_t)stream>>>(P, Q, A, B, dim, u, i, n, scores);
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}
+
 // shared with train_neumf.cu / train_nais.cu: TF dense optimizer apply of one table from its dense gradient buffer
 int crb_dense_table_apply(crb_handle* h, const crb_table* T, float* grad, int opt_kind, const OptDev& od, float l2, double* loss_part,
                           int* grid_out, cudaStream_t s) {

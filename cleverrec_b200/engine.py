@@ -281,6 +281,51 @@ class Engine(object):
                                            int(conf_batch_size), ptr(host) if loss_out is None else ptr(loss_out), self.stream))
         return float(host[0]) if loss_out is None else None
 
+    # ------------------------------------------------------------------ TransCF
+    def set_item_lists(self):
+        """Item-side lists of TransCF's iu_sp_mat (utils/tools.py:100-113) from the current history: the users of every item,
+        duplicates kept -- crb_build_history on the swapped columns."""
+        pu, pi = self._hist[0], self._hist[1]
+        n, dev = int(pu.numel()), self.device
+        members = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        grouped_item = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        rp, sc = torch.empty(self.n_items + 1, dtype=torch.int64, device=dev), torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        start, ln = torch.empty(self.n_items + 1, dtype=torch.int64, device=dev), torch.empty(self.n_items, dtype=torch.int32, device=dev)
+        n_seen = C.c_int64(0)
+        # rows in the order utils/tools.py:103-109 appends them: users in dict order, items in list order = pos_user / pos_item order
+        check(self.lib.crb_build_history(self.h, ptr(pi), ptr(pu), n, self.n_items, self.n_users, ptr(grouped_item), ptr(members), ptr(rp), ptr(sc),
+                                         C.byref(n_seen), ptr(start), ptr(ln), self.stream))
+        self._item_lists = (start, ln, members)
+        check(self.lib.crb_set_item_lists(self.h, ptr(start), ptr(ln), ptr(members)))
+        return self._item_lists
+
+    def train_step_transcf(self, P, Q, opt, u, i, j, margin, reg1, reg2, loss_out=None):
+        """One `sess.run([train, loss], {u_idx, i_idx, j_idx})` of TransCF (TransCF.py:38-71)."""
+        u, i, j = (self._feed_i32(x) for x in (u, i, j))
+        for T_ in (P, Q):
+            if getattr(T_, "grad", None) is None:
+                T_.grad = torch.zeros_like(T_.w)
+        opt.t += 1
+        co = opt.c(opt.t)
+        host = np.zeros(1, dtype=np.float64) if loss_out is None else None
+        check(self.lib.crb_train_step_transcf(self.h, C.byref(P.c), C.byref(Q.c), ptr(P.grad), ptr(Q.grad), C.byref(co), ptr(u), ptr(i), ptr(j),
+                                              len(u), float(margin), float(reg1), float(reg2), ptr(host) if loss_out is None else ptr(loss_out),
+                                              self.stream))
+        return float(host[0]) if loss_out is None else None
+
+    def transcf_neighbourhood(self, which, table, n_rows):
+        """which = 0: alpha of all users (table = Q); which = 1: beta of all items (table = P)."""
+        out = torch.empty((n_rows, table.shape[1]), dtype=torch.float32, device=self.device)
+        check(self.lib.crb_transcf_neighbourhood(self.h, which, ptr(table), table.shape[1], None, n_rows, ptr(out), self.stream))
+        return out
+
+    def score_pairs_transcf(self, P, Q, A, B, u, i):
+        u = torch.as_tensor(np.asarray(u), dtype=torch.int32).to(self.device) if not isinstance(u, torch.Tensor) else u.to(torch.int32).contiguous()
+        i = torch.as_tensor(np.asarray(i), dtype=torch.int32).to(self.device) if not isinstance(i, torch.Tensor) else i.to(torch.int32).contiguous()
+        out = torch.empty(u.numel(), dtype=torch.float32, device=self.device)
+        check(self.lib.crb_score_pairs_transcf(self.h, ptr(P), ptr(Q), ptr(A), ptr(B), P.shape[1], ptr(u), ptr(i), u.numel(), ptr(out), self.stream))
+        return out
+
     def fism_user_vectors(self, P, users, nbr, alpha):
         users = torch.as_tensor(np.asarray(users), dtype=torch.int32).to(self.device) if not isinstance(users, torch.Tensor) else users.to(torch.int32)
         nbr = torch.as_tensor(np.asarray(nbr), dtype=torch.int32).to(self.device) if not isinstance(nbr, torch.Tensor) else nbr.to(torch.int32)

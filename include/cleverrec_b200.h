@@ -186,6 +186,23 @@ int crb_train_step_cml(crb_handle* h, const crb_table* P, const crb_table* Q, fl
                        const int32_t* u, const int32_t* i, const int32_t* neg, int64_t batch, int32_t neg_ratio,
                        float margin, float reg, int64_t item_nums, double* loss_out, void* stream);
 
+/* TransCF (model/ranking/TransCF.py:38-85).  crb_set_item_lists: the item-side lists of iu_sp_mat (utils/tools.py:100-113): for
+ * every item the users that interacted with it (duplicates kept), item_users grouped by item, item_start [I+1] / item_len [I] --
+ * crb_build_history on the swapped columns produces exactly these.  DEVICE arrays, borrowed.
+ * crb_train_step_transcf: sess.run([train, loss], {u_idx, i_idx, j_idx}) (TransCF.py:38-62 + :65-71); gradP / gradQ zeroed
+ * device buffers of the tables' shape (the gradients are dense in the reference: they flow through the two SpMMs).
+ * crb_transcf_neighbourhood: which = 0 -> alpha rows (mean of `table` = Q over each user's items) for `rows` users (NULL = 0..n-1),
+ * which = 1 -> beta rows (mean of `table` = P over each item's users).  crb_score_pairs_transcf: TransCF._predict's ui_dist for
+ * flattened (u, i) pairs given A = alpha of all users [U, dim] and B = beta of all items [I, dim]. */
+int crb_set_item_lists(crb_handle* h, const int64_t* item_start, const int32_t* item_len, const int32_t* item_users);
+int crb_train_step_transcf(crb_handle* h, const crb_table* P, const crb_table* Q, float* gradP, float* gradQ, const crb_opt* opt,
+                           const int32_t* u, const int32_t* i, const int32_t* j, int64_t batch, float margin, float reg1, float reg2,
+                           double* loss_out, void* stream);
+int crb_transcf_neighbourhood(crb_handle* h, int32_t which, const float* table, int32_t dim, const int32_t* rows, int64_t n, float* out,
+                              void* stream);
+int crb_score_pairs_transcf(crb_handle* h, const float* P, const float* Q, const float* A, const float* B, int32_t dim, const int32_t* u,
+                            const int32_t* i, int64_t n, float* scores, void* stream);
+
 /* Per-user interaction lists inside pos_item (the `items` lists of data.ui_train, order and duplicates kept): what
  * get_ui_sp_mat (utils/tools.py:90-97) encodes.  DEVICE arrays [n_users], borrowed.  Call after crb_set_history. */
 int crb_set_history_lists(crb_handle* h, const int64_t* list_start, const int32_t* list_len);

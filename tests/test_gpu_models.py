@@ -23,6 +23,8 @@ CONFS = {
               'init_method': 'xavier_uniform '},
     'CML': {'embed_size': '32', 'margin': '1.0', 'reg': '10.0', 'cml_like': 'True', 'is_pairwise': 'False', 'loss_func': 'hinge', 'init_method': 'xavier ',
             'neg_ratio': '10', 'lr': '0.003'},
+    'TransCF': {'embed_size': '32', 'margin': '0.5', 'reg1': '0.1', 'reg2': '0.01', 'cml_like': 'True', 'is_pairwise': 'True', 'loss_func': 'hinge',
+                'lr': '0.003'},
     'FISM': {'embed_size': '32', 'alpha': '0.4', 'reg': '1e-3', 'reg_bias': '1e-3', 'fism_like': 'True', 'is_pairwise': 'True', 'loss_func': 'bpr',
              'init_method': 'xavier_uniform'},
     'NAIS_single': {'embed_size': '32', 'atten_size': '16', 'atten_type': "'prod'", 'beta': '0.5', 'reg': '1e-3', 'lr': '0.01', 'optimizer': 'Adagrad',
@@ -63,7 +65,7 @@ def test_train_and_loo_eval(name):
     # (the synthetic interactions carry no signal; ranking quality is asserted on the real ml-100k split in test_gpu_driver.py)
 
 
-@pytest.mark.parametrize("name", ["BPR", "GMF", "CML", "FISM", "NeuMF", "NAIS_single"])
+@pytest.mark.parametrize("name", ["BPR", "GMF", "CML", "FISM", "NeuMF", "NAIS_single", "TransCF"])
 def test_train_and_rs_eval(name):
     data = _data('rs', 0)
     m = _model(name, data, **{'data.split_way': 'rs', 'test.neg_samples': 0})
