@@ -707,7 +707,11 @@ int crb_score_topk_tc(crb_handle* h, int32_t kind, const float* P, const float* 
         ta.n_users = nu; ta.n_users_pad = nu_pad; ta.n_items = n_items; ta.n_tiles = n_tiles; ta.n_splits = n_splits;
         ta.tiles_per_split = tiles_per_split; ta.kb = kb; ta.stages = stages; ta.users = users + u0;
         ta.hist_users = hist_users ? hist_users + u0 : nullptr; ta.seen_rowptr = h->seen_rowptr; ta.seen_cols = h->seen_cols;
+#ifdef TC_DEBUG_SWITCHES
         ta.debug = getenv("CRB_TC_DEBUG") ? atoi(getenv("CRB_TC_DEBUG")) : 0;
+#else
+        ta.debug = 0;
+#endif
         ta.cand = (unsigned long long*)(ws + o_cand); ta.cand_cnt = (int32_t*)(ws + o_cnt); ta.cand_thr = (float*)(ws + o_thr);
         const int64_t n_work = (nu_pad / TC_BM) * n_splits;
         const int grid = (int)(n_work < h->sm_count ? n_work : h->sm_count);

@@ -25,7 +25,7 @@ struct NeumfShape {
 };
 
 static int make_shape(int E, int L0, int n_layers, NeumfShape* s) {
-    if (n_layers < 1 || n_layers > NM_MAX_LAYERS || L0 < 2 || (L0 % (1 << n_layers)) != 0 || L0 > 512 || E < 1 || E > 256) return -1;
+    if (n_layers < 1 || n_layers > NM_MAX_LAYERS || L0 < 2 || (L0 % (1 << n_layers)) != 0 || L0 > 512 || E < 0 || E > 256) return -1;   // E == 0: the MLP model (MLP.py), no GMF branch
     s->E = E; s->L0 = L0; s->n_layers = n_layers;
     int off = 0, soff = 0, n = L0, aoff = 0;
     s->act_off[0] = 0; aoff = L0;
@@ -295,12 +295,15 @@ extern "C" int crb_train_step_neumf(crb_handle* h, const crb_table* Pg, const cr
                                     int32_t n_layers, const crb_opt* opt, int32_t loss_kind, const int32_t* u, const int32_t* i,
                                     const float* y, int64_t batch, float reg1, float reg2, double* loss_out, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    CRB_CHECK_ARG(h && Pg && Qg && Pm && Qm && gPg && gQg && gPm && gQm && dense && u && i && y, "null argument");
+    CRB_CHECK_ARG(h && Pm && Qm && gPm && gQm && dense && u && i && y, "null argument");
+    const bool gmf = Pg != nullptr;   // Pg == Qg == NULL: model/ranking/MLP.py (the tower alone, logit = h_mlp . tower)
+    CRB_CHECK_ARG(gmf ? (Qg && gPg && gQg) : (!Qg && !gPg && !gQg), "the GMF branch tables must be all given or all NULL");
     CRB_CHECK_ARG(batch > 0, "batch");
     CRB_CHECK_ARG(loss_kind == CRB_LOSS_CROSS_ENTROPY || loss_kind == CRB_LOSS_SQUARE, "pointwise loss must be cross_entropy or square");
-    CRB_CHECK_ARG(Pg->dim == Qg->dim && Pm->dim == Qm->dim, "table dims");
+    CRB_CHECK_ARG((!gmf || Pg->dim == Qg->dim) && Pm->dim == Qm->dim, "table dims");
     NeumfArgs a;
-    if (make_shape(Pg->dim, 2 * Pm->dim, n_layers, &a.sh)) { crb_set_error("unsupported NeuMF shape (E=%d, L0=%d, layers=%d)", Pg->dim, 2 * Pm->dim, n_layers); return CRB_ERR_ARG; }
+    const int E_gmf = gmf ? Pg->dim : 0;
+    if (make_shape(E_gmf, 2 * Pm->dim, n_layers, &a.sh)) { crb_set_error("unsupported NeuMF shape (E=%d, L0=%d, layers=%d)", E_gmf, 2 * Pm->dim, n_layers); return CRB_ERR_ARG; }
     OptDev od;
     int opt_kind = 0;
     int rc = crb_opt_to_dev(h, opt, &od, &opt_kind, s);
@@ -327,7 +330,7 @@ extern "C" int crb_train_step_neumf(crb_handle* h, const crb_table* Pg, const cr
     if (!crb_is_device_ptr(u)) { CRB_CUDA(cudaMemcpyAsync(h->idx[0], u, 4 * batch, cudaMemcpyHostToDevice, s)); du = h->idx[0]; }
     if (!crb_is_device_ptr(i)) { CRB_CUDA(cudaMemcpyAsync(h->idx[1], i, 4 * batch, cudaMemcpyHostToDevice, s)); di = h->idx[1]; }
     if (!crb_is_device_ptr(y)) { CRB_CUDA(cudaMemcpyAsync(h->yv, y, 4 * batch, cudaMemcpyHostToDevice, s)); dy = h->yv; }
-    a.Pg = Pg->w; a.Qg = Qg->w; a.Pm = Pm->w; a.Qm = Qm->w;
+    a.Pg = gmf ? Pg->w : nullptr; a.Qg = gmf ? Qg->w : nullptr; a.Pm = Pm->w; a.Qm = Qm->w;
     a.gPg = gPg; a.gQg = gQg; a.gPm = gPm; a.gQm = gQm;
     a.dense = dense; a.dense_part = h->dense_grad; a.u = du; a.i = di; a.y = dy; a.batch = batch; a.loss_kind = loss_kind;
     a.reg1 = reg1; a.reg2 = reg2; a.loss_part = h->block_loss;
@@ -346,7 +349,7 @@ extern "C" int crb_train_step_neumf(crb_handle* h, const crb_table* Pg, const cr
     double* dp = h->dense_loss;
     const crb_table* tabs[4] = {Pg, Qg, Pm, Qm};
     float* grads[4] = {gPg, gQg, gPm, gQm};
-    for (int k = 0; k < 4; ++k) {
+    for (int k = gmf ? 0 : 2; k < 4; ++k) {
         if ((rc = crb_dense_table_apply(h, tabs[k], grads[k], dk, od, 0.f, dp, &g1, s))) return rc;
     }
     dense_vector_apply_kernel<<<(a.sh.n_dense + 255) / 256, 256, 0, s>>>(dense, dense_s1, dense_s2, h->dense_grad, grid, a.sh.n_dense, dk, od);
@@ -366,7 +369,8 @@ extern "C" int crb_score_pairs_neumf(crb_handle* h, const float* Pg, const float
                                      int32_t E, int32_t Em, int32_t n_layers, const int32_t* u, const int32_t* i, int64_t n, float* scores,
                                      void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    CRB_CHECK_ARG(h && Pg && Qg && Pm && Qm && dense && u && i && scores, "null argument");
+    CRB_CHECK_ARG(h && Pm && Qm && dense && u && i && scores, "null argument");
+    CRB_CHECK_ARG(E == 0 ? (!Pg && !Qg) : (Pg && Qg), "GMF branch tables: both given (E > 0) or both NULL (E == 0, the MLP model)");
     CRB_CHECK_ARG(crb_is_device_ptr(u) && crb_is_device_ptr(i) && crb_is_device_ptr(scores), "u/i/scores must be device pointers");
     NeumfScoreArgs a;
     if (make_shape(E, 2 * Em, n_layers, &a.sh) || 2 * Em > 256) { crb_set_error("unsupported NeuMF shape"); return CRB_ERR_ARG; }

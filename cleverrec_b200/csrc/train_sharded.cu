@@ -41,7 +41,7 @@ struct ShardStepArgs {
     float* dup_grad;
     uint32_t* dup_t;
     double* block_loss;
-    int debug;   // experiments only (CRB_SH_DEBUG): 1 = no gradient sends, 2 = item rows read from the local shard, 3 = both
+    int debug;   // experiments only (-DSH_DEBUG_SWITCHES + CRB_SH_DEBUG): 1 = no gradient sends, 2 = item rows read from the local shard, 3 = both
 };
 
 #define SH_CHUNK 32u   // inbox slots a warp reserves per system-scope atomic (unused ones stay holes: row = -1)
@@ -84,9 +84,15 @@ __global__ void __launch_bounds__(256, 3) shard_step_kernel(ShardStepArgs a) {
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int G = a.sh.n_ranks;
+#ifdef SH_DEBUG_SWITCHES
     const int RG = (a.debug & 2) ? 1 : G;              // debug: every read goes to the local shard
     const int RO = (a.debug & 2) ? a.sh.rank : 0;
 #define SH_Q(item) a.sh.q[(a.debug & 2) ? RO : (item) % RG]
+#define SH_SEND (!(a.debug & 1))
+#else
+#define SH_Q(item) a.sh.q[(item) % G]
+#define SH_SEND true
+#endif
     __shared__ unsigned int s_resv[8][2][CRB_MAX_RANKS];   // per warp: next slot / slots left of the current reservation per owner
     if (lane < CRB_MAX_RANKS) { s_resv[threadIdx.x >> 5][0][lane] = 0u; s_resv[threadIdx.x >> 5][1][lane] = 0u; }
     __syncwarp();
@@ -160,7 +166,7 @@ __global__ void __launch_bounds__(256, 3) shard_step_kernel(ShardStepArgs a) {
             emit_row<LANES, VPL, OPT>(ru, gu, a.P, a.metaU, u, mu, a.rk_u[t], (uint32_t)t, 0u, a.dim, gl, a.opt, a.dup_grad, a.dup_t);
         // ordering key of the occurrence: unique and identical from run to run -> deterministic duplicate sums at the owner
         const uint32_t kbase = ((uint32_t)a.sh.rank * (uint32_t)a.batch + (uint32_t)tt) << 1;
-        if (!(a.debug & 1)) {
+        if (SH_SEND) {
             send_item_grad<LANES, VPL>(a.sh, s_base, s_left, oi, li, kbase, gi, a.dim, gl, sub, active);
             send_item_grad<LANES, VPL>(a.sh, s_base, s_left, oj, lj, kbase | 1u, gj, a.dim, gl, sub, active);
         }
@@ -333,7 +339,11 @@ extern "C" int crb_shard_step_compute(crb_handle* h, const crb_table* P, const c
     }
     a.P = crb_to_dev(P); a.metaU = h->meta[0]; a.u = du; a.i = di; a.j = dj; a.rk_u = h->rank[0];
     a.batch = batch; a.dim = P->dim; a.reg = reg; a.opt = od; a.dup_grad = h->dup_grad; a.dup_t = h->dup_t; a.block_loss = h->block_loss;
+#ifdef SH_DEBUG_SWITCHES
     a.debug = getenv("CRB_SH_DEBUG") ? atoi(getenv("CRB_SH_DEBUG")) : 0;
+#else
+    a.debug = 0;
+#endif
     if ((rc = crb_prof_begin(h, s))) return rc;
     if ((rc = CRB_DIM_DISPATCH(a.dim, launch_shard_t, h, a, opt_kind, s))) return rc;
     if ((rc = crb_prof_end(h, s))) return rc;

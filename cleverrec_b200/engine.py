@@ -343,13 +343,14 @@ class Engine(object):
         u, i = self._feed_i32(u), self._feed_i32(i)
         if not isinstance(y, torch.Tensor):
             y = np.ascontiguousarray(np.asarray(y), dtype=np.float32)
-        for T_ in tabs:
-            if getattr(T_, "grad", None) is None:
+        for T_ in tabs:   # tabs[0] = tabs[1] = None: the MLP model (no GMF branch)
+            if T_ is not None and getattr(T_, "grad", None) is None:
                 T_.grad = torch.zeros_like(T_.w)
         opt.t += 1
         co = opt.c(opt.t)
         host = np.zeros(1, dtype=np.float64) if loss_out is None else None
-        check(self.lib.crb_train_step_neumf(self.h, *(C.byref(T_.c) for T_ in tabs), *(ptr(T_.grad) for T_ in tabs), ptr(dense), ptr(dense_s1),
+        check(self.lib.crb_train_step_neumf(self.h, *(C.byref(T_.c) if T_ is not None else None for T_ in tabs),
+                                            *(ptr(T_.grad) if T_ is not None else None for T_ in tabs), ptr(dense), ptr(dense_s1),
                                             ptr(dense_s2), n_layers, C.byref(co), loss_kind, ptr(u), ptr(i), ptr(y), len(u), float(reg1),
                                             float(reg2), ptr(host) if loss_out is None else ptr(loss_out), self.stream))
         return float(host[0]) if loss_out is None else None
@@ -358,8 +359,9 @@ class Engine(object):
         u = torch.as_tensor(np.asarray(u), dtype=torch.int32).to(self.device) if not isinstance(u, torch.Tensor) else u.to(torch.int32).contiguous()
         i = torch.as_tensor(np.asarray(i), dtype=torch.int32).to(self.device) if not isinstance(i, torch.Tensor) else i.to(torch.int32).contiguous()
         out = torch.empty(u.numel(), dtype=torch.float32, device=self.device)
-        check(self.lib.crb_score_pairs_neumf(self.h, ptr(tabs[0].w), ptr(tabs[1].w), ptr(tabs[2].w), ptr(tabs[3].w), ptr(dense), tabs[0].dim,
-                                             tabs[2].dim, n_layers, ptr(u), ptr(i), u.numel(), ptr(out), self.stream))
+        gmf = tabs[0] is not None
+        check(self.lib.crb_score_pairs_neumf(self.h, ptr(tabs[0].w) if gmf else None, ptr(tabs[1].w) if gmf else None, ptr(tabs[2].w), ptr(tabs[3].w),
+                                             ptr(dense), tabs[0].dim if gmf else 0, tabs[2].dim, n_layers, ptr(u), ptr(i), u.numel(), ptr(out), self.stream))
         return out
 
     def mask_seen(self, scores, users, value=float("-inf")):

@@ -226,7 +226,8 @@ int crb_clip_rows(crb_handle* h, const float* src, float* dst, int64_t rows, int
 /* sess.run([train, loss], {u_idx, i_idx, y}) for model/ranking/NeuMF.py:58-95.  Tables: GMF pair [.,E], MLP pair [.,L0/2].
  * `dense` packs the dense variables in this order: for k in layers: W_k [layers[k], layers[k]/2] row-major, b_k; then
  * h_neumf [E + layers[-1]/2]  (layers[k+1] == layers[k]/2, n_layers <= 4, L0 <= 512).  g* are zeroed dense gradient
- * buffers of the tables (left zeroed); dense_s1/s2 the optimizer slots of `dense`. */
+ * buffers of the tables (left zeroed); dense_s1/s2 the optimizer slots of `dense`.  * Pg == Qg == gPg == gQg == NULL selects model/ranking/MLP.py:44-70: the tower alone (logit = h_mlp . tower, h_neumf then holds
+ * h_mlp only; reg1 unused, reg2 = MLP.py's reg). */
 int crb_train_step_neumf(crb_handle* h, const crb_table* Pg, const crb_table* Qg, const crb_table* Pm, const crb_table* Qm,
                          float* gPg, float* gQg, float* gPm, float* gQm, float* dense, float* dense_s1, float* dense_s2,
                          int32_t n_layers, const crb_opt* opt, int32_t loss_kind, const int32_t* u, const int32_t* i,

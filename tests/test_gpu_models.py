@@ -21,6 +21,7 @@ CONFS = {
     'GMF': {'embed_size': '32', 'reg_gmf': '1e-2', 'is_pairwise': 'False', 'loss_func': 'cross_entropy', 'init_method': 'xavier_uniform'},
     'NeuMF': {'embed_size': '16', 'layers': '[64,32,16]', 'reg_gmf': '1e-2', 'reg_mlp': '1e-3', 'is_pairwise': 'False', 'loss_func': 'cross_entropy',
               'init_method': 'xavier_uniform '},
+    'MLP': {'layers': '[64,32,16]', 'reg_mlp': '1e-2', 'is_pairwise': 'False', 'loss_func': 'cross_entropy', 'init_method': 'xavier_uniform'},
     'CML': {'embed_size': '32', 'margin': '1.0', 'reg': '10.0', 'cml_like': 'True', 'is_pairwise': 'False', 'loss_func': 'hinge', 'init_method': 'xavier ',
             'neg_ratio': '10', 'lr': '0.003'},
     'TransCF': {'embed_size': '32', 'margin': '0.5', 'reg1': '0.1', 'reg2': '0.01', 'cml_like': 'True', 'is_pairwise': 'True', 'loss_func': 'hinge',
@@ -65,7 +66,7 @@ def test_train_and_loo_eval(name):
     # (the synthetic interactions carry no signal; ranking quality is asserted on the real ml-100k split in test_gpu_driver.py)
 
 
-@pytest.mark.parametrize("name", ["BPR", "GMF", "CML", "FISM", "NeuMF", "NAIS_single", "TransCF"])
+@pytest.mark.parametrize("name", ["BPR", "GMF", "CML", "FISM", "NeuMF", "MLP", "NAIS_single", "TransCF"])
 def test_train_and_rs_eval(name):
     data = _data('rs', 0)
     m = _model(name, data, **{'data.split_way': 'rs', 'test.neg_samples': 0})
@@ -207,3 +208,23 @@ def test_neumf_starts_from_gmf_and_mlp_checkpoints(tmp_path):
     off, shape = layout['W_1']
     assert np.array_equal(m.dense[off:off + shape[0] * shape[1]].cpu().numpy().reshape(shape), v['NeuMF_params/W_1'])
     assert np.isfinite(m.train_model())
+
+
+def test_neumf_pretraining_chain_gmf_plus_mlp(tmp_path):
+    """The NCF recipe the reference's confs describe (conf/NeuMF.properties gmf_pretrain / mlp_pretrain): train GMF and MLP, save,
+    start NeuMF from both.  NeuMF's first logits are then 0.5 * (GMF logit + MLP logit) (NeuMF.py:56)."""
+    import torch
+    data = _data('loo', 49)
+    g = _model('GMF', data, saved_dir=str(tmp_path), embed_size=16)
+    m = _model('MLP', data, saved_dir=str(tmp_path))
+    for _ in range(2):
+        g.train_model(); m.train_model()
+    g.save_model(); m.save_model()
+    n = _model('NeuMF', data, gmf_pretrain=str(tmp_path / 'GMF'), mlp_pretrain=str(tmp_path / 'MLP'))
+    u = torch.arange(0, 50, dtype=torch.int32, device='cuda')
+    i = torch.arange(100, 150, dtype=torch.int32, device='cuda')
+    lg = g.engine.score_pairs(1, g.P.w, g.Q.w, u, i, hvec=g.h_gmf)
+    lm = m.engine.score_pairs_neumf(m.tabs, m.dense, len(m.layers), u, i)
+    ln = n.engine.score_pairs_neumf(n.tabs, n.dense, len(n.layers), u, i)
+    assert torch.allclose(ln, 0.5 * (lg + lm), rtol=1e-5, atol=1e-6)
+    assert np.isfinite(n.train_model())

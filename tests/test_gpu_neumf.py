@@ -67,3 +67,41 @@ def test_neumf_steps(eng, kind, layers, E):
     cur.update({k: v for k, v in ref.items() if k not in cur})
     lg, _ = T.neumf_logits({k: v.double() for k, v in cur.items()}, torch.tensor(u), torch.tensor(i), len(layers))
     np.testing.assert_allclose(sc, lg.numpy(), rtol=2e-4, atol=2e-5)
+
+
+def test_mlp_model_step_matches_restated_tower(eng):
+    """model/ranking/MLP.py (the tower alone, E = 0 in the fused kernels) against the restated NeuMF graph with the GMF branch
+    removed: same loss and same tables after 3 steps."""
+    import torch
+    from oracle import tf1_restatement as T
+    from cleverrec_b200.engine import Optimizer, Table
+    U, I, Em, layers = 30, 50, 8, 2
+    g = torch.Generator().manual_seed(4)
+    p = {"P": torch.randn(U, Em, generator=g) * 0.3, "Q": torch.randn(I, Em, generator=g) * 0.3,
+         "W_0": torch.randn(16, 8, generator=g) * 0.3, "b_0": torch.randn(8, generator=g) * 0.1,
+         "W_1": torch.randn(8, 4, generator=g) * 0.3, "b_1": torch.randn(4, generator=g) * 0.1, "h_mlp": torch.randn(4, generator=g) * 0.3}
+
+    def mlp_loss(q, b, hp):   # MLP.py:44-70
+        x = torch.cat([q["P"][b["u"]], q["Q"][b["i"]]], 1)
+        y_ = T.mlp_tower(x, q, 2)
+        logits = y_ @ q["h_mlp"]
+        return T.get_loss("cross_entropy", b["y"], logits=logits) + hp["reg"] * (T.l2_loss(q["P"][b["u"]]) + T.l2_loss(q["Q"][b["i"]]))
+    for kind in ("SGD", "Adagrad"):
+        ref = {k: v.clone() for k, v in p.items()}
+        ropt = T.TF1Optimizer(kind, 0.05)
+        P, Q = Table(p["P"].clone().cuda(), kind, "lazy"), Table(p["Q"].clone().cuda(), kind, "lazy")
+        dense = torch.cat([p["W_0"].reshape(-1), p["b_0"], p["W_1"].reshape(-1), p["b_1"], p["h_mlp"]]).cuda()
+        s1 = torch.full_like(dense, 0.1) if kind == "Adagrad" else None
+        opt = Optimizer(kind, 0.05)
+        rs = np.random.RandomState(0)
+        for step in range(3):
+            u, i = rs.randint(0, U, 64), rs.randint(0, I, 64)
+            y = (rs.rand(64) < 0.3).astype(np.float32)
+            got = eng.train_step_neumf([None, None, P, Q], dense, s1, None, layers, opt, u, i, y, 0.0, 0.01, 1)
+            b = {"u": torch.tensor(u.astype(np.int64)), "i": torch.tensor(i.astype(np.int64)), "y": torch.tensor(y)}
+            want = T.train_step(mlp_loss, ref, b, {"reg": 0.01}, ropt)
+            assert abs(got - want) <= 1e-5 * abs(want)
+        np.testing.assert_allclose(P.w.cpu().numpy(), ref["P"].numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(Q.w.cpu().numpy(), ref["Q"].numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(dense[:128].cpu().numpy().reshape(16, 8), ref["W_0"].numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(dense[-4:].cpu().numpy(), ref["h_mlp"].numpy(), rtol=1e-5, atol=1e-6)
