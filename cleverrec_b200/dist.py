@@ -154,15 +154,20 @@ class ShardedBPR(object):
         self.barrier()
         return float(host[0]) if loss_out is None else None
 
-    def run_steps(self, n_steps, reg, neg_ratio, seed, epoch, first, batch=None, loss_out=None):
+    def run_steps(self, n_steps, reg, neg_ratio, seed, epoch, first=0, batch=None, loss_out=None, bounds=None):
         """n synchronous steps over consecutive batches of this rank's epoch, sampled on the device.  Step k+1's index work
         (sampler, user-row counting and slot assignment) is prepared on the engine's auxiliary stream while step k's barriers and
-        inbox phase run (crb_shard_step_prepare).  loss_out: device float64 [n_steps] or None."""
+        inbox phase run (crb_shard_step_prepare).  loss_out: device float64 [n_steps] or None.  bounds: optional n_steps+1 row
+        offsets (step k covers rows [bounds[k], bounds[k+1]) of this rank's epoch) instead of a fixed batch."""
         eng, lib = self.engine, self.engine.lib
         batch = self.batch if batch is None else batch
+        if bounds is None:
+            bounds = [first + k * batch for k in range(n_steps + 1)]
+        assert len(bounds) == n_steps + 1 and all(b > a for a, b in zip(bounds[:-1], bounds[1:])), "every step needs at least one row"
 
         def prepare(k):
-            check(lib.crb_shard_step_prepare(eng.h, C.byref(self.P.c), seed, epoch, first + k * batch, neg_ratio, batch, self.inbox_cap, eng.stream))
+            check(lib.crb_shard_step_prepare(eng.h, C.byref(self.P.c), seed, epoch, bounds[k], neg_ratio, bounds[k + 1] - bounds[k], self.inbox_cap,
+                                             eng.stream))
         prepare(0)
         host = np.zeros(1, dtype=np.float64)
         for k in range(n_steps):
@@ -170,7 +175,7 @@ class ShardedBPR(object):
             co = self.opt.c(self.opt.t)
             lo = ptr(host) if loss_out is None else ptr(loss_out[k:k + 1])
             check(lib.crb_shard_step_compute(eng.h, C.byref(self.P.c), C.byref(self.shard), C.byref(co), None, None, None, seed, epoch,
-                                             first + k * batch, neg_ratio, batch, float(reg), lo, eng.stream))
+                                             bounds[k], neg_ratio, bounds[k + 1] - bounds[k], float(reg), lo, eng.stream))
             if k + 1 < n_steps:
                 prepare(k + 1)
             self.barrier()
@@ -188,6 +193,18 @@ class ShardedBPR(object):
         if self.opt.kind == "Adam" and self.opt.adam_mode == "tf1" and self.opt.t > 0:
             co = self.opt.c(self.opt.t)
             check(self.engine.lib.crb_adam_flush(self.engine.h, C.byref(self.shard.q[self.rank]), C.byref(co), self.engine.stream))
+
+    def gather_P(self):
+        """All user rows on every rank, in global user order (checkpoints / tests)."""
+        self.flush()
+        parts = [torch.zeros(user_range(self.n_users, r, self.world)[1] - user_range(self.n_users, r, self.world)[0], self.dim,
+                             device=self.engine.device) for r in range(self.world)]
+        for r in range(self.world):
+            if r == self.rank:
+                parts[r].copy_(self.P.w)
+            if self.world > 1:
+                dist.broadcast(parts[r], src=r, group=self.group)
+        return torch.cat(parts)
 
     def gather_Q(self):
         """Full item table on every rank (tests / evaluation set-up)."""

@@ -25,13 +25,22 @@ class RankingRecommender(Recommender):
         self.test_users = list(data.ui_test.keys())
         self.test_batches = math.ceil(len(self.test_users) / self.batch_size_t)
         self.epoch = 0            # epochs sampled so far (the sampler's `epoch` counter)
+        if self.world > 1 and not self.supports_sharding:
+            raise NotImplementedError('%s under WORLD_SIZE=%d: the multi-GPU path (users partitioned, item table row-sharded over '
+                                      'NVLink peer memory) is implemented for BPR' % (self.model, self.world))
+        self._install_history()
+        self._test_cache = None
+
+    supports_sharding = False
+
+    def _install_history(self):
+        data = self.data
         if getattr(data, 'train_rows', None) is not None:
             # the packaged RankingPreprocess also keeps the training split as two int32 columns in the dict's enumeration
             # order: the device history is built from them natively (csrc/history.cu) instead of walking the dict of lists
             self.engine.build_history(data.train_rows[0], data.train_rows[1], self._history_rows(), data.item_nums)
         else:
             self.engine.set_history(data.ui_train, self._history_rows(), data.item_nums)
-        self._test_cache = None
 
     def _history_rows(self):
         return self.data.user_nums

@@ -43,11 +43,18 @@ class Recommender(object):
         self.T = int(c['test.interval'])  # Test every T epoches
         self.topk = list(map(int, c['topk'][1:-1].split(',')))
         self.model_params = 'lr=%s, loss_func=%s' % (self.lr, c['loss_func'])
+        # one process per GPU (torchrun): rank / world from torch.distributed when it is initialised, else from the launcher's env
+        import os
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        else:
+            self.rank, self.world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
         # device handle
         if isinstance(self.sess, Engine):
             self.engine = self.sess
         else:
-            self.engine = Engine(int(c.get('engine.device', 0)))
+            self.engine = Engine(int(c.get('engine.device', os.environ.get('LOCAL_RANK', '0') if self.world > 1 else 0)))
 
     def build_model(self):
         raise NotImplementedError
