@@ -227,6 +227,15 @@ __global__ void __launch_bounds__(256) dense_vector_apply_kernel(float* w, float
     }
 }
 
+// shared with train_lrml.cu
+int crb_dense_vector_apply(crb_handle* h, float* w, float* s1, float* s2, const float* parts, int n_parts, int n, int opt_kind, const OptDev& od,
+                           cudaStream_t s) {
+    dense_vector_apply_kernel<<<(n + 255) / 256, 256, 0, s>>>(w, s1, s2, parts, n_parts, n, opt_kind, od);
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ scoring
 // canonical NeuMF logit of (user, item) pairs: per layer acc = b[o]; acc = fma(x[k], W[k][o], acc) for k ascending; ReLU;
 // logit = fma chain over the GMF products (rounded first) then over the tower output.  One thread per pair.

@@ -364,6 +364,28 @@ class Engine(object):
                                              ptr(dense), tabs[0].dim if gmf else 0, tabs[2].dim, n_layers, ptr(u), ptr(i), u.numel(), ptr(out), self.stream))
         return out
 
+    def train_step_lrml(self, P, Q, dense, dense_s1, dense_s2, mem_size, opt, u, i, j, margin, reg, loss_out=None):
+        """One `sess.run([train, loss], {u_idx, i_idx, j_idx})` of LRML (LRML.py:53-64).  dense = K [d, mem] then M [mem, d]."""
+        u, i, j = (self._feed_i32(x) for x in (u, i, j))
+        for T_ in (P, Q):
+            if getattr(T_, "grad", None) is None:
+                T_.grad = torch.zeros_like(T_.w)
+        opt.t += 1
+        co = opt.c(opt.t)
+        host = np.zeros(1, dtype=np.float64) if loss_out is None else None
+        check(self.lib.crb_train_step_lrml(self.h, C.byref(P.c), C.byref(Q.c), ptr(P.grad), ptr(Q.grad), ptr(dense), ptr(dense_s1), ptr(dense_s2),
+                                           int(mem_size), C.byref(co), ptr(u), ptr(i), ptr(j), len(u), float(margin), float(reg),
+                                           ptr(host) if loss_out is None else ptr(loss_out), self.stream))
+        return float(host[0]) if loss_out is None else None
+
+    def score_pairs_lrml(self, P, Q, dense, mem_size, u, i):
+        u = torch.as_tensor(np.asarray(u), dtype=torch.int32).to(self.device) if not isinstance(u, torch.Tensor) else u.to(torch.int32).contiguous()
+        i = torch.as_tensor(np.asarray(i), dtype=torch.int32).to(self.device) if not isinstance(i, torch.Tensor) else i.to(torch.int32).contiguous()
+        out = torch.empty(u.numel(), dtype=torch.float32, device=self.device)
+        check(self.lib.crb_score_pairs_lrml(self.h, ptr(P), ptr(Q), ptr(dense), P.shape[1], int(mem_size), ptr(u), ptr(i), u.numel(), ptr(out),
+                                            self.stream))
+        return out
+
     def mask_seen(self, scores, users, value=float("-inf")):
         users = users.to(torch.int32).contiguous()
         check(self.lib.crb_mask_seen(self.h, ptr(scores), ptr(users), scores.shape[0], scores.shape[1], float(value), self.stream))

@@ -50,11 +50,13 @@ class Recommender(object):
             self.rank, self.world = dist.get_rank(), dist.get_world_size()
         else:
             self.rank, self.world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+        if c.get('dist.mode', 'auto') == 'replica':   # an independent single-GPU model inside a multi-process job (main_tuning)
+            self.rank, self.world = 0, 1
         # device handle
         if isinstance(self.sess, Engine):
             self.engine = self.sess
         else:
-            self.engine = Engine(int(c.get('engine.device', os.environ.get('LOCAL_RANK', '0') if self.world > 1 else 0)))
+            self.engine = Engine(int(c.get('engine.device', os.environ.get('LOCAL_RANK', '0') if int(os.environ.get('WORLD_SIZE', '1')) > 1 else 0)))
 
     def build_model(self):
         raise NotImplementedError

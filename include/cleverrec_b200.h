@@ -238,6 +238,18 @@ int crb_score_pairs_neumf(crb_handle* h, const float* Pg, const float* Qg, const
                           int32_t E, int32_t Em, int32_t n_layers, const int32_t* u, const int32_t* i, int64_t n,
                           float* scores, void* stream);
 
+/* LRML (model/ranking/LRML.py:42-78).  crb_train_step_lrml: sess.run([train, loss], {u_idx, i_idx, j_idx}) -- the LRAM memory
+ * module (x = p*q, softmax(x K) M, :42-51), translated distances (:59-60), hinge + reg * l2 of the three gathered rows (:62-63).
+ * `dense` packs K [embed_size, mem_size] row-major then M [mem_size, embed_size] row-major; dense_s1 / dense_s2 its optimizer
+ * slots; gradP / gradQ zeroed dense gradient buffers of the tables (left zeroed).  embed_size % 4 == 0, <= 256; mem_size <= 128.
+ * crb_score_pairs_lrml: LRML._predict's ui_dist (:73 for fed pairs; :75-76 is the same distance for every (user, item) pair) on
+ * flattened pairs, same forward arithmetic as the training step.  DEVICE buffers. */
+int crb_train_step_lrml(crb_handle* h, const crb_table* P, const crb_table* Q, float* gradP, float* gradQ, float* dense,
+                        float* dense_s1, float* dense_s2, int32_t mem_size, const crb_opt* opt, const int32_t* u, const int32_t* i,
+                        const int32_t* j, int64_t batch, float margin, float reg, double* loss_out, void* stream);
+int crb_score_pairs_lrml(crb_handle* h, const float* P, const float* Q, const float* dense, int32_t dim, int32_t mem_size,
+                         const int32_t* u, const int32_t* i, int64_t n, float* scores, void* stream);
+
 /* RankingRecommender.py:235-240 as a mask: scores[k, item] = value for every item users[k] has seen.  DEVICE buffers. */
 int crb_mask_seen(crb_handle* h, float* scores, const int32_t* users, int64_t n_users, int64_t n_items, float value, void* stream);
 

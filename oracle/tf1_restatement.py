@@ -18,6 +18,8 @@ Forward graphs (each returns the scalar loss exactly as `self.loss`):
   fism_loss    <- model/ranking/FISM.py:40-63 + utils/tools.py:90-97
   nais_loss    <- model/ranking/NAIS_single.py:59-90
   transcf_loss <- model/ranking/TransCF.py:38-71 + utils/tools.py:100-113
+  lrml_loss    <- model/ranking/LRML.py:42-64
+  sbpr_loss    <- model/ranking/SBPR.py:38-57
 Losses        <- utils/tools.py:66-76
 Optimizers    <- utils/tools.py:79-87 with TF-1 defaults
 """
@@ -175,6 +177,34 @@ def transcf_loss(p, b, hp, ui_coo, iu_coo):
     reg_nbr = ((ue - un) ** 2).sum() + ((ie - inb) ** 2).sum()
     reg_dist = ((d_ui + hp["margin"] - d_uj) ** 2).sum()
     return loss + hp["reg1"] * reg_nbr + hp["reg2"] * reg_dist
+
+
+def lrml_dist(p, ue, ie):
+    """LRML.py:42-51 (_lram, training branch) + :59: relation vector from the memory module, translated squared distance."""
+    joint = ue * ie
+    att = torch.softmax(joint @ p["K"], dim=1)
+    r = att @ p["M"]
+    return ((ue + r - ie) ** 2).sum(1)
+
+
+def lrml_loss(p, b, hp):
+    ue, ie, je = p["P"][b["u"]], p["Q"][b["i"]], p["Q"][b["j"]]
+    d_ui, d_uj = lrml_dist(p, ue, ie), lrml_dist(p, ue, je)
+    return get_loss("hinge", d_ui - d_uj, margin=hp["margin"]) + hp["reg"] * (l2_loss(ue) + l2_loss(ie) + l2_loss(je))
+
+
+def sbpr_loss(p, b, hp):
+    """SBPR.py:38-57: u prefers its own item i over a friend's item k (scaled by 1/suk) and k over an unobserved j; the bias
+    vector has item_nums + 1 entries (:36)."""
+    ue = p["P"][b["u"]]
+    def side(idx):
+        e, bias = p["Q"][idx], p["bias"][idx]
+        return e, bias, (ue * e).sum(1) + bias
+    ie, ib, ui = side(b["i"])
+    ke, kb, uk = side(b["k"])
+    je, jb, uj = side(b["j"])
+    return get_loss("bpr", (ui - uk) / b["suk"]) + get_loss("bpr", uk - uj) + hp["reg"] * (
+        l2_loss(ue) + l2_loss(ie) + l2_loss(ke) + l2_loss(je) + l2_loss(ib) + l2_loss(kb) + l2_loss(jb))
 
 
 # ----------------------------------------------------------------------------- scores (pre_scores)

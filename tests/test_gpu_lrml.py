@@ -1,0 +1,126 @@
+"""-m gpu: LRML (csrc/train_lrml.cu; model/ranking/LRML.py:42-78) against the torch restatement of the TF graph
+(oracle/tf1_restatement.py::lrml_loss) under the three TF-1 optimizers, and the pair scorer against the restated distance."""
+import logging
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import synthetic_data
+from oracle import ref_host as H
+from oracle import tf1_restatement as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from cleverrec_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _close(got, want, rtol, atol, name):
+    bad = ~np.isclose(got, want, rtol=rtol, atol=atol)
+    assert bad.sum() <= max(1, 3e-3 * bad.size), (name, int(bad.sum()), float(np.abs(got - want).max()))
+
+
+@pytest.mark.parametrize("kind", ["SGD", "Adagrad", "Adam"])
+@pytest.mark.parametrize("d,mem", [(128, 50), (32, 7), (64, 64)])
+def test_lrml_steps(eng, kind, d, mem):
+    from cleverrec_b200.engine import Optimizer, Table
+    U, I = 40, 60
+    g = torch.Generator().manual_seed(d + mem)
+    ref = {"P": torch.randn(U, d, generator=g) * 0.3, "Q": torch.randn(I, d, generator=g) * 0.3,
+           "K": torch.randn(d, mem, generator=g) * 0.5, "M": torch.randn(mem, d, generator=g) * 0.3}
+    lr = 0.02 if kind != "Adam" else 0.005
+    opt, ropt = Optimizer(kind, lr, adam_mode="lazy"), T.TF1Optimizer(kind, lr, adam_mode="tf1")
+    P, Q = Table(ref["P"].clone().cuda(), kind, "lazy"), Table(ref["Q"].clone().cuda(), kind, "lazy")
+    dense = torch.cat([ref["K"].reshape(-1), ref["M"].reshape(-1)]).cuda()
+    s1 = torch.full_like(dense, 0.1) if kind == "Adagrad" else (torch.zeros_like(dense) if kind == "Adam" else None)
+    s2 = torch.zeros_like(dense) if kind == "Adam" else None
+    hp = {"reg": 1e-2, "margin": 0.2}
+    rs = np.random.RandomState(1)
+    for B in (128, 1, 77):
+        u, i, j = rs.randint(0, U, B), rs.randint(0, I, B), rs.randint(0, I, B)
+        got = eng.train_step_lrml(P, Q, dense, s1, s2, mem, opt, u, i, j, hp["margin"], hp["reg"])
+        b = {"u": torch.tensor(u), "i": torch.tensor(i), "j": torch.tensor(j)}
+        want = T.train_step(T.lrml_loss, ref, b, hp, ropt, sparse_index={"P": ["u"], "Q": ["i", "j"]})
+        assert abs(got - want) <= 5e-5 * abs(want), (got, want)
+    rtol, atol = (3e-4, 3e-5) if kind == "Adam" else (3e-5, 2e-6)
+    _close(P.w.cpu().numpy(), ref["P"].numpy(), rtol, atol, "P")
+    _close(Q.w.cpu().numpy(), ref["Q"].numpy(), rtol, atol, "Q")
+    _close(dense.cpu().numpy(), torch.cat([ref["K"].reshape(-1), ref["M"].reshape(-1)]).numpy(), rtol, atol, "K|M")
+    assert float(P.grad.abs().max()) == 0.0 and float(Q.grad.abs().max()) == 0.0   # gradient buffers are left zeroed
+    # scoring: the distance of LRML._predict against the fp64 restatement on the current tables
+    u, i = rs.randint(0, U, 500), rs.randint(0, I, 500)
+    sc = eng.score_pairs_lrml(P.w, Q.w, dense, mem, u, i).cpu().numpy()
+    cur = {"K": dense[:d * mem].reshape(d, mem).cpu().double(), "M": dense[d * mem:].reshape(mem, d).cpu().double()}
+    want = T.lrml_dist(cur, P.w.cpu().double()[u], Q.w.cpu().double()[i]).numpy()
+    np.testing.assert_allclose(sc, want, rtol=2e-4, atol=2e-5)
+
+
+def test_lrml_inactive_hinge_only_regularises(eng):
+    """With a very negative margin no hinge is active: the loss is the L2 term alone and K / M do not move (SGD)."""
+    from cleverrec_b200.engine import Optimizer, Table
+    d, mem, U, I = 16, 5, 10, 12
+    g = torch.Generator().manual_seed(0)
+    P0, Q0 = torch.randn(U, d, generator=g) * 0.1, torch.randn(I, d, generator=g) * 0.1
+    P, Q = Table(P0.clone().cuda(), "SGD"), Table(Q0.clone().cuda(), "SGD")
+    dense0 = torch.randn(2 * d * mem, generator=g)
+    dense = dense0.clone().cuda()
+    u, i, j = np.array([0, 1, 1]), np.array([2, 3, 4]), np.array([5, 6, 2])
+    loss = eng.train_step_lrml(P, Q, dense, None, None, mem, Optimizer("SGD", 0.1), u, i, j, -1e6, 0.5)
+    want = 0.5 * 0.5 * float((P0[u] ** 2).sum() + (Q0[i] ** 2).sum() + (Q0[j] ** 2).sum())
+    assert abs(loss - want) <= 1e-6 * want
+    assert torch.equal(dense.cpu(), dense0)
+    # row 1 of P occurs twice: gradient 2 * reg * p  ->  p * (1 - lr * 2 * reg)
+    np.testing.assert_allclose(P.w.cpu().numpy()[1], (P0[1] * (1 - 0.1 * 2 * 0.5)).numpy(), rtol=1e-6)
+
+
+def test_lrml_shape_limits(eng):
+    from cleverrec_b200._lib import CrbError
+    from cleverrec_b200.engine import Optimizer, Table
+    P, Q = Table(torch.zeros(4, 512).cuda(), "SGD"), Table(torch.zeros(4, 512).cuda(), "SGD")
+    dense = torch.zeros(2 * 512 * 8).cuda()
+    with pytest.raises(CrbError):
+        eng.train_step_lrml(P, Q, dense, None, None, 8, Optimizer("SGD", 0.1), [0], [1], [2], 0.2, 0.0)
+
+
+def test_lrml_model_eval_matches_reference_loops():
+    """LRML behind the reference's interface: test_model_loo / test_model_rs equal the reference's evaluation loops
+    (restated in oracle/ref_host.py, bit-equal to the genuine ones) fed with the device's own distances."""
+    import importlib
+    cfg = {'model_type': 'ranking', 'saved_dir': './saved_model', 'data.split_way': 'loo', 'test.neg_samples': '49', 'test.batch_size': '64',
+           'test.interval': '1', 'topk': '[5,10]', 'epoches': '2', 'batch_size': '512', 'lr': '0.003', 'neg_ratio': '2', 'optimizer': 'Adam',
+           'init_method': 'normal', 'stddev': '0.05', 'seed': '3', 'recommender': 'LRML', 'embed_size': '32', 'mem_size': '10',
+           'margin': '0.2', 'reg': '0.001', 'cml_like': 'True', 'is_pairwise': 'True', 'loss_func': 'hinge'}
+    data = synthetic_data(120, 300, 12, seed=11, test_per_user=1)
+    rs = np.random.RandomState(0)
+    for u in data.ui_test:
+        cand = np.setdiff1d(np.arange(data.item_nums), data.ui_train[u])
+        data.ui_test[u] = rs.choice(cand, 49, replace=False).tolist() + data.ui_test[u]
+    cls = getattr(importlib.import_module('cleverrec_b200.model.ranking.LRML'), 'LRML')
+    m = cls(None, data, cfg, logging.getLogger('test'))
+    m.build_model()
+    losses = [m.train_model() for _ in range(5)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    HR, MRR, NDCG = m.test_model_loo()
+    scores = {u: m._dist(np.full(len(data.ui_test[u]), u), np.asarray(data.ui_test[u])).cpu().numpy() for u in m.test_users}
+    oHR, oMRR, oNDCG = H.eval_loo(m.test_users, data.ui_test, scores, 49, m.topk, cml_like=True)
+    for k in range(len(m.topk)):
+        assert HR[k] == oHR[k] and MRR[k] == oMRR[k] and NDCG[k] == oNDCG[k]
+    # full ranking
+    data2 = synthetic_data(120, 300, 12, seed=11, test_per_user=2)
+    cfg2 = dict(cfg, **{'data.split_way': 'rs', 'test.neg_samples': '0'})
+    m2 = cls(None, data2, cfg2, logging.getLogger('test'))
+    m2.build_model()
+    m2.train_model()
+    HR, MRR, NDCG = m2.test_model_rs()
+    I = data2.item_nums
+    users = np.asarray(m2.test_users)
+    sc = m2._dist(np.repeat(users, I), np.tile(np.arange(I), len(users))).cpu().numpy().reshape(len(users), I)
+    oHR, oMRR, oNDCG = H.eval_rs(m2.test_users, data2.ui_train, data2.ui_test, sc, m2.topk, cml_like=True)
+    for k in range(len(m2.topk)):
+        assert HR[k] == oHR[k] and NDCG[k] == oNDCG[k]

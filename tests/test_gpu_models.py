@@ -26,6 +26,8 @@ CONFS = {
             'neg_ratio': '10', 'lr': '0.003'},
     'TransCF': {'embed_size': '32', 'margin': '0.5', 'reg1': '0.1', 'reg2': '0.01', 'cml_like': 'True', 'is_pairwise': 'True', 'loss_func': 'hinge',
                 'lr': '0.003'},
+    'LRML': {'embed_size': '32', 'mem_size': '10', 'margin': '0.2', 'reg': '0.001', 'cml_like': 'True', 'is_pairwise': 'True', 'loss_func': 'hinge',
+             'lr': '0.003'},
     'FISM': {'embed_size': '32', 'alpha': '0.4', 'reg': '1e-3', 'reg_bias': '1e-3', 'fism_like': 'True', 'is_pairwise': 'True', 'loss_func': 'bpr',
              'init_method': 'xavier_uniform'},
     'NAIS_single': {'embed_size': '32', 'atten_size': '16', 'atten_type': "'prod'", 'beta': '0.5', 'reg': '1e-3', 'lr': '0.01', 'optimizer': 'Adagrad',
@@ -66,7 +68,7 @@ def test_train_and_loo_eval(name):
     # (the synthetic interactions carry no signal; ranking quality is asserted on the real ml-100k split in test_gpu_driver.py)
 
 
-@pytest.mark.parametrize("name", ["BPR", "GMF", "CML", "FISM", "NeuMF", "MLP", "NAIS_single", "TransCF"])
+@pytest.mark.parametrize("name", ["BPR", "GMF", "CML", "FISM", "NeuMF", "MLP", "NAIS_single", "TransCF", "LRML"])
 def test_train_and_rs_eval(name):
     data = _data('rs', 0)
     m = _model(name, data, **{'data.split_way': 'rs', 'test.neg_samples': 0})

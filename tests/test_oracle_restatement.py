@@ -78,6 +78,21 @@ def test_cml_fism_nais_transcf_neumf_gradients():
     _fd_check(T.neumf_loss, pm, bm, {"reg1": 1e-2, "reg2": 1e-3, "n_layers": 2, "loss_func": "cross_entropy"})
 
 
+def test_lrml_sbpr_gradients():
+    p = _tables(6, 12, 8, 5)
+    g = torch.Generator().manual_seed(6)
+    p["K"], p["M"] = torch.randn(8, 5, generator=g, dtype=torch.float64), torch.randn(5, 8, generator=g, dtype=torch.float64) * 0.5
+    b = {"u": torch.tensor([0, 2, 2, 5]), "i": torch.tensor([1, 3, 3, 7]), "j": torch.tensor([4, 3, 0, 11])}
+    _fd_check(T.lrml_loss, p, b, {"reg": 1e-3, "margin": 0.2})
+    # a margin large enough that every hinge is active, and zero: both branches of the hinge
+    _fd_check(T.lrml_loss, p, b, {"reg": 1e-3, "margin": 50.0})
+    ps = _tables(6, 12, 8, 7)
+    ps["bias"] = torch.randn(13, generator=g, dtype=torch.float64) * 0.1
+    bs = {"u": torch.tensor([0, 2, 2, 5]), "i": torch.tensor([1, 3, 3, 7]), "k": torch.tensor([2, 5, 6, 7]), "j": torch.tensor([4, 9, 0, 11]),
+          "suk": torch.tensor([1., 2., 3., 1.], dtype=torch.float64)}
+    _fd_check(T.sbpr_loss, ps, bs, {"reg": 0.05})
+
+
 def test_tf1_optimizer_hand_examples():
     # one variable, two rows, row 0 touched with g = 2, row 1 never touched
     def run(kind, mode="tf1", steps=2):
