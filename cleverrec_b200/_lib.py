@@ -25,7 +25,7 @@ EXPORTS = [
     "crb_sample_nais", "crb_train_step_nais", "crb_train_epoch_nais", "crb_score_nais",
     "crb_shard_step_compute", "crb_shard_step_prepare", "crb_shard_apply_inbox", "crb_shard_inbox_overflow", "crb_malloc", "crb_free", "crb_ipc_export",
     "crb_ipc_open", "crb_ipc_close", "crb_build_history", "crb_set_item_lists", "crb_train_step_transcf", "crb_transcf_neighbourhood", "crb_score_pairs_transcf", "crb_np_seed", "crb_np_set_state", "crb_np_get_state", "crb_sample_epoch_numpy",
-    "crb_train_step_lrml", "crb_score_pairs_lrml",
+    "crb_train_step_lrml", "crb_score_pairs_lrml", "crb_set_social", "crb_sample_sbpr", "crb_train_step_sbpr",
 ]
 
 
@@ -102,6 +102,9 @@ def load():
     lib.crb_score_pairs_neumf.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, i64, vp, vp]
     lib.crb_train_step_lrml.argtypes = [vp, T, T, vp, vp, vp, vp, vp, i32, O, vp, vp, vp, i64, f32, f32, vp, vp]
     lib.crb_score_pairs_lrml.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, i64, vp, vp]
+    lib.crb_set_social.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp]
+    lib.crb_sample_sbpr.argtypes = [vp, u64, u32, i64, i64, i32, vp, vp, vp, vp, vp, vp]
+    lib.crb_train_step_sbpr.argtypes = [vp, T, T, T, vp, vp, vp, O, vp, vp, vp, vp, vp, i64, f32, vp, vp]
     lib.crb_mask_seen.argtypes = [vp, vp, vp, i64, i64, f32, vp]
     lib.crb_sample_nais.argtypes = [vp, u64, u32, i64, i32, i32, vp, vp, vp]
     lib.crb_train_step_nais.argtypes = [vp, T, T, T, vp, vp, vp, vp, vp, vp, i32, O, vp, i32, vp, vp, i32, f32, f32, vp, vp]

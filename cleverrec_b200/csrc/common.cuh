@@ -72,6 +72,17 @@ struct crb_handle {
     const int32_t* ilist_len;
     const int32_t* ipos_user;
     double* dense_loss;         // [4 * loss_blocks] per-block partials of the dense loss terms
+    // social structures of SBPR (crb_set_social; borrowed device pointers): the positives of users that have a non-empty SPu in
+    // the sampler's enumeration order, every user's SPu list with the social coefficient of each entry, and the sorted-unique
+    // union of the user's own and social items (the rejection set of utils/sampler.py:118-120)
+    int64_t sp_n_pos;
+    const int32_t* sp_pos_user;
+    const int32_t* sp_pos_item;
+    const int64_t* spu_start;
+    const int32_t* spu_items;
+    const float* spu_suk;
+    const int64_t* excl_rowptr;
+    const int32_t* excl_cols;
     // per-row batch multiplicity words: low 32 bits = count, high 32 bits = slot base
     unsigned long long* meta[2];
     int64_t meta_rows[2];

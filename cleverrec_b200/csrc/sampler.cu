@@ -285,6 +285,7 @@ extern "C" int64_t crb_epoch_rows(crb_handle* h, int32_t neg_ratio, int32_t samp
     if (!h) return -1;
     if (sampler_kind == 0) return h->n_pos * neg_ratio;
     if (sampler_kind == 1) return h->n_pos * (neg_ratio + 1);
+    if (sampler_kind == 3) return h->sp_n_pos * neg_ratio;   // SBPR: positives of users with a non-empty SPu only
     return h->n_pos;
 }
 
@@ -307,5 +308,98 @@ extern "C" int crb_sample_nais(crb_handle* h, uint64_t seed, uint32_t epoch, int
     cudaStream_t s = (cudaStream_t)stream;
     int rc = crb_launch_sample_nais(h, seed, epoch, pos_first, n_pos_user, neg_ratio, targets, y, s);
     if (rc) return rc;
+    return sampler_epilogue(h, s);
+}
+
+// ------------------------------------------------------------------------------------------------ SBPR (utils/sampler.py:102-141)
+// Per positive (u, i) of a user with a non-empty SPu, neg_ratio rows: a social item k uniform over SPu[u] and a negative j uniform
+// over the items that are neither u's nor in SPu[u]; rows are independent (no distinctness inside a group, :113-121), s_uk = number
+// of u's friends that consumed k (:124-131, precomputed per SPu entry).  Spec shared with oracle/philox.py::sample_sbpr: row r of
+// the epoch (before the shuffle) draws from the Philox blocks with counter (r_lo, r_hi, 0x80000000 | blk, epoch); words in order;
+// the first word w with (w & mask(len(SPu[u]) - 1)) < len(SPu[u]) picks k, every later word is a negative candidate under
+// np.random.randint's masked rejection and the membership test.
+struct SbprSamplerArgs {
+    SamplerArgs base;       // keys / bits / n_rows / group / item mask; pos_* and seen_* replaced by the social structures
+    const int64_t* spu_start;
+    const int32_t* spu_items;
+    const float* spu_suk;
+};
+
+__global__ void __launch_bounds__(256) sample_sbpr_kernel(SbprSamplerArgs A, int64_t first, int64_t count, int32_t* __restrict__ ou,
+                                                          int32_t* __restrict__ oi, int32_t* __restrict__ ok_, int32_t* __restrict__ oj,
+                                                          float* __restrict__ osuk, crb_step_ctr* ctr) {
+    const SamplerArgs& a = A.base;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
+        const uint64_t s = feistel_perm((uint64_t)(first + t), a);
+        const uint64_t p = s / a.group;
+        const int32_t u = a.pos_user[p];
+        const int64_t sp0 = A.spu_start[u];
+        const uint32_t n_sp = (uint32_t)(A.spu_start[u + 1] - sp0);
+        uint32_t sm = n_sp - 1;
+        sm |= sm >> 1; sm |= sm >> 2; sm |= sm >> 4; sm |= sm >> 8; sm |= sm >> 16;
+        const int64_t lo = a.seen_rowptr[u], hi = a.seen_rowptr[u + 1];
+        int64_t pick = -1;
+        int32_t neg = -1;
+        for (uint32_t blk = 0; blk < CRB_SAMPLER_MAX_BLOCKS && neg < 0; ++blk) {
+            uint32_t w[4];
+            philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), 0x80000000u | blk, a.epoch, a.k0, a.k1, w);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (neg >= 0) continue;
+                if (pick < 0) {
+                    const uint32_t c = w[q] & sm;
+                    if (c < n_sp) pick = c;
+                    continue;
+                }
+                const int32_t v = (int32_t)(w[q] & a.item_mask);
+                if (v >= a.n_items) continue;
+                if (history_contains(a.seen_cols, lo, hi, v)) continue;
+                neg = v;
+            }
+        }
+        const bool ok = neg >= 0;
+        ou[t] = u; oi[t] = a.pos_item[p];
+        ok_[t] = ok ? A.spu_items[sp0 + pick] : 0;
+        oj[t] = ok ? neg : 0;
+        if (osuk) osuk[t] = ok ? A.spu_suk[sp0 + pick] : 1.f;
+        if (!ok) atomicAdd(&ctr->sampler_err, 1u);
+    }
+}
+
+extern "C" int crb_set_social(crb_handle* h, int64_t n_sp_pos, const int32_t* sp_pos_user, const int32_t* sp_pos_item, const int64_t* spu_start,
+                              const int32_t* spu_items, const float* spu_suk, const int64_t* excl_rowptr, const int32_t* excl_cols) {
+    CRB_CHECK_ARG(h, "null handle");
+    if (!h->pos_user) { crb_set_error("crb_set_social before crb_set_history"); return CRB_ERR_STATE; }
+    CRB_CHECK_ARG(n_sp_pos >= 0 && spu_start && excl_rowptr, "null argument");
+    CRB_CHECK_ARG(n_sp_pos == 0 || (sp_pos_user && sp_pos_item && spu_items && spu_suk && excl_cols), "null argument");
+    h->sp_n_pos = n_sp_pos; h->sp_pos_user = sp_pos_user; h->sp_pos_item = sp_pos_item; h->spu_start = spu_start; h->spu_items = spu_items;
+    h->spu_suk = spu_suk; h->excl_rowptr = excl_rowptr; h->excl_cols = excl_cols;
+    return CRB_OK;
+}
+
+extern "C" int crb_sample_sbpr(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t first, int64_t count, int32_t neg_ratio, int32_t* u,
+                               int32_t* i, int32_t* k, int32_t* j, float* suk, void* stream) {
+    CRB_CHECK_ARG(h, "null handle");
+    if (!h->spu_start) { crb_set_error("crb_sample_sbpr before crb_set_social"); return CRB_ERR_STATE; }
+    if (count == 0) return CRB_OK;
+    int rc = check_outputs_device(u, i, k);
+    if (rc) return rc;
+    if ((rc = check_outputs_device(j, j, suk ? (const void*)suk : (const void*)j))) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    SbprSamplerArgs A;
+    if ((rc = make_args(h, seed, epoch, neg_ratio, 0, &A.base))) return rc;
+    // the epoch runs over the social positives only, rejection is against own + social items
+    A.base.n_rows = (uint64_t)h->sp_n_pos * A.base.group;
+    uint32_t bits = 2;
+    while (((uint64_t)1 << bits) < A.base.n_rows) bits += 2;
+    A.base.half_bits = bits / 2;
+    A.base.half_mask = (uint32_t)(((uint64_t)1 << A.base.half_bits) - 1);
+    A.base.pos_user = h->sp_pos_user; A.base.pos_item = h->sp_pos_item; A.base.seen_rowptr = h->excl_rowptr; A.base.seen_cols = h->excl_cols;
+    A.spu_start = h->spu_start; A.spu_items = h->spu_items; A.spu_suk = h->spu_suk;
+    CRB_CHECK_ARG(first >= 0 && count >= 0 && (uint64_t)(first + count) <= A.base.n_rows, "rows outside the epoch");
+    sample_sbpr_kernel<<<sampler_grid(h, count), 256, 0, s>>>(A, first, count, u, i, k, j, suk, h->ctr);
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
     return sampler_epilogue(h, s);
 }

@@ -870,3 +870,135 @@ int crb_dense_table_apply(crb_handle* h, const crb_table* T, float* grad, int op
     CRB_CUDA(cudaGetLastError());
     return CRB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ SBPR
+// model/ranking/SBPR.py:38-57.  x_ui = p.q_i + b_i, x_uk (a friend's item), x_uj (unobserved);
+//   loss = sum softplus(-(x_ui - x_uk) / s_uk) + softplus(-(x_uk - x_uj))                                  (:54, utils/tools.py:71)
+//        + reg * (l2(p) + l2(q_i) + l2(q_k) + l2(q_j) + l2(b_i) + l2(b_k) + l2(b_j))                       (:55-56)
+// All four gathers are IndexedSlices in TF; the tables take the dense apply (zero gradient on untouched rows: exactly
+// tf.train.AdamOptimizer's sparse apply, a no-op for SGD / Adagrad), the gradients are accumulated in the dense buffers.
+struct SbprArgs {
+    const float* P;
+    const float* Q;
+    const float* b;
+    float* gP;
+    float* gQ;
+    float* gb;
+    const int32_t* u;
+    const int32_t* i;
+    const int32_t* k;
+    const int32_t* j;
+    const float* suk;
+    int64_t batch;
+    int dim;
+    float reg;
+    double* loss_part;
+};
+
+template <int LANES, int VPL>
+__global__ void __launch_bounds__(256) sbpr_step_kernel(SbprArgs a) {
+    constexpr int GPW = 32 / LANES;
+    const int lane = threadIdx.x & 31, gl = lane % LANES, sub = lane / LANES;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double loss = 0.0;
+    for (int64_t base = warp * GPW; base < a.batch; base += n_warps * GPW) {
+        const int64_t t = base + sub;
+        const bool active = t < a.batch;
+        const int64_t tt = active ? t : a.batch - 1;
+        const int64_t u = a.u[tt], it = a.i[tt], kt = a.k[tt], jt = a.j[tt];
+        const float inv_s = __fdividef(1.f, a.suk[tt]);
+        float4 p[VPL], qi[VPL], qk[VPL], qj[VPL];
+        float xi = 0.f, xk = 0.f, xj = 0.f, sq = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const int c = (gl + LANES * v) * 4;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            p[v] = c < a.dim ? ld4(a.P + u * a.dim + c) : z;
+            qi[v] = c < a.dim ? ld4(a.Q + it * a.dim + c) : z;
+            qk[v] = c < a.dim ? ld4(a.Q + kt * a.dim + c) : z;
+            qj[v] = c < a.dim ? ld4(a.Q + jt * a.dim + c) : z;
+            xi += dot4(p[v], qi[v]); xk += dot4(p[v], qk[v]); xj += dot4(p[v], qj[v]);
+            sq += dot4(p[v], p[v]) + dot4(qi[v], qi[v]) + dot4(qk[v], qk[v]) + dot4(qj[v], qj[v]);
+        }
+        const float bi = a.b[it], bk = a.b[kt], bj = a.b[jt];
+        xi = group_sum<LANES>(xi) + bi;
+        xk = group_sum<LANES>(xk) + bk;
+        xj = group_sum<LANES>(xj) + bj;
+        sq = group_sum<LANES>(sq) + bi * bi + bk * bk + bj * bj;
+        const float x1 = (xi - xk) * inv_s, x2 = xk - xj;
+        const float g1 = -sigmoid_f(-x1) * inv_s, g2 = -sigmoid_f(-x2);   // dL/dx_ui = g1, dL/dx_uk = g2 - g1, dL/dx_uj = -g2
+        const float gk = g2 - g1;
+        if (active) {
+            if (gl == 0) {
+                loss += (double)(softplus_neg(x1) + softplus_neg(x2) + a.reg * 0.5f * sq);
+                atomicAdd(a.gb + it, fmaf(a.reg, bi, g1));
+                atomicAdd(a.gb + kt, fmaf(a.reg, bk, gk));
+                atomicAdd(a.gb + jt, fmaf(a.reg, bj, -g2));
+            }
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int c = (gl + LANES * v) * 4;
+                if (c >= a.dim) continue;
+                const float4 P_ = p[v], I_ = qi[v], K_ = qk[v], J_ = qj[v];
+                atomic_add4(a.gP + u * a.dim + c, make_float4(fmaf(a.reg, P_.x, g1 * I_.x + gk * K_.x - g2 * J_.x), fmaf(a.reg, P_.y, g1 * I_.y + gk * K_.y - g2 * J_.y),
+                                                               fmaf(a.reg, P_.z, g1 * I_.z + gk * K_.z - g2 * J_.z), fmaf(a.reg, P_.w, g1 * I_.w + gk * K_.w - g2 * J_.w)));
+                atomic_add4(a.gQ + it * a.dim + c, make_float4(fmaf(a.reg, I_.x, g1 * P_.x), fmaf(a.reg, I_.y, g1 * P_.y), fmaf(a.reg, I_.z, g1 * P_.z), fmaf(a.reg, I_.w, g1 * P_.w)));
+                atomic_add4(a.gQ + kt * a.dim + c, make_float4(fmaf(a.reg, K_.x, gk * P_.x), fmaf(a.reg, K_.y, gk * P_.y), fmaf(a.reg, K_.z, gk * P_.z), fmaf(a.reg, K_.w, gk * P_.w)));
+                atomic_add4(a.gQ + jt * a.dim + c, make_float4(fmaf(a.reg, J_.x, -g2 * P_.x), fmaf(a.reg, J_.y, -g2 * P_.y), fmaf(a.reg, J_.z, -g2 * P_.z), fmaf(a.reg, J_.w, -g2 * P_.w)));
+            }
+        }
+    }
+    block_sum_to(loss, a.loss_part);
+}
+
+template <int LANES, int VPL>
+static int launch_sbpr_t(crb_handle* h, const SbprArgs& a, int grid, cudaStream_t s) {
+    sbpr_step_kernel<LANES, VPL><<<grid, 256, 0, s>>>(a);
+    h->launches++;
+    return CRB_OK;
+}
+
+extern "C" int crb_train_step_sbpr(crb_handle* h, const crb_table* P, const crb_table* Q, const crb_table* B, float* gradP, float* gradQ, float* gradB,
+                                   const crb_opt* opt, const int32_t* u, const int32_t* i, const int32_t* k, const int32_t* j, const float* suk,
+                                   int64_t batch, float reg, double* loss_out, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    CRB_CHECK_ARG(h && u && i && k && j && suk, "null argument");
+    CRB_CHECK_ARG(batch > 0, "batch");
+    OptDev od;
+    int opt_kind = 0;
+    int rc = crb_opt_to_dev(h, opt, &od, &opt_kind, s);
+    if (rc) return rc;
+    if ((rc = check_dense_table(P, gradP, opt_kind, "P"))) return rc;
+    if ((rc = check_dense_table(Q, gradQ, opt_kind, "Q"))) return rc;
+    CRB_CHECK_ARG(B && B->w && B->dim == 1 && gradB && B->rows % 4 == 0, "bias table must have dim 1 and a length padded to a multiple of 4");
+    CRB_CHECK_ARG(P->dim == Q->dim, "P.dim != Q.dim");
+    CRB_CUDA(cudaSetDevice(h->device));
+    const int dim = P->dim;
+    if ((rc = crb_ws_reserve(h, batch, dim, 4, s))) return rc;
+    const int32_t *du, *di, *dk, *dj;
+    if ((rc = stage_dev_i32(h, u, batch, h->idx[0], &du, s))) return rc;
+    if ((rc = stage_dev_i32(h, i, batch, h->idx[1], &di, s))) return rc;
+    if ((rc = stage_dev_i32(h, k, batch, h->idx[2], &dk, s))) return rc;
+    if ((rc = stage_dev_i32(h, j, batch, h->idx[3], &dj, s))) return rc;
+    const float* ds = suk;
+    if (!crb_is_device_ptr(suk)) { CRB_CUDA(cudaMemcpyAsync(h->yv, suk, sizeof(float) * batch, cudaMemcpyHostToDevice, s)); ds = h->yv; }
+    const int grid = dgrid(h, batch, 256 / 32);
+    SbprArgs a = {P->w, Q->w, B->w, gradP, gradQ, gradB, du, di, dk, dj, ds, batch, dim, reg, h->block_loss};
+    if ((rc = crb_prof_begin(h, s))) return rc;
+    CRB_DIM_DISPATCH(dim, launch_sbpr_t, h, a, grid, s);
+    if ((rc = crb_prof_end(h, s))) return rc;
+    double* dp = h->dense_loss;
+    const int dk_ = dense_opt_kind(opt_kind);
+    int g1 = 0;
+    if ((rc = crb_dense_table_apply(h, P, gradP, dk_, od, 0.f, dp, &g1, s))) return rc;
+    if ((rc = crb_dense_table_apply(h, Q, gradQ, dk_, od, 0.f, dp, &g1, s))) return rc;
+    crb_table B4 = *B;      // the bias vector as a [n/4, 4] table
+    B4.rows = B->rows / 4; B4.dim = 4;
+    if ((rc = crb_dense_table_apply(h, &B4, gradB, dk_, od, 0.f, dp, &g1, s))) return rc;
+    h->step_grid = grid;
+    double* ld = (loss_out && crb_is_device_ptr(loss_out)) ? loss_out : h->loss_dev;
+    if ((rc = crb_launch_loss_final(h, ld, s))) return rc;
+    CRB_CUDA(cudaGetLastError());
+    return finish_loss_host(h, loss_out, s);
+}

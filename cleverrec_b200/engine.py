@@ -147,7 +147,7 @@ class Engine(object):
         check(self.lib.crb_set_history_lists(self.h, ptr(self._lists[0]), ptr(self._lists[1])))
 
     def epoch_rows(self, neg_ratio, kind="pairwise"):
-        return int(self.lib.crb_epoch_rows(self.h, neg_ratio, {"pairwise": 0, "pointwise": 1, "cml": 2}[kind]))
+        return int(self.lib.crb_epoch_rows(self.h, neg_ratio, {"pairwise": 0, "pointwise": 1, "cml": 2, "sbpr": 3}[kind]))
 
     # ------------------------------------------------------------------ sampler
     def sample_pairwise(self, seed, epoch, first, count, neg_ratio, with_nbr=False):
@@ -279,6 +279,39 @@ class Engine(object):
         check(self.lib.crb_train_step_fism(self.h, C.byref(P.c), C.byref(Q.c), C.byref(B.c), ptr(P.grad), ptr(Q.grad), ptr(B.grad), C.byref(co),
                                            ptr(u), ptr(i), ptr(j), ptr(nbr), len(u), float(alpha), float(reg), float(reg_bias),
                                            int(conf_batch_size), ptr(host) if loss_out is None else ptr(loss_out), self.stream))
+        return float(host[0]) if loss_out is None else None
+
+    # ------------------------------------------------------------------ SBPR
+    def set_social(self, ui_train, user_friends, SPu, n_users):
+        """Device form of what ranking_sampler_sbpr (utils/sampler.py:102-141) walks: see crb_set_social in the header."""
+        arrs = social_arrays(ui_train, user_friends, SPu, n_users)
+        dts = (torch.int32, torch.int32, torch.int64, torch.int32, torch.float32, torch.int64, torch.int32)
+        self._social = tuple(torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(self.device) for a, dt in zip(arrs, dts))
+        t = self._social
+        check(self.lib.crb_set_social(self.h, int(t[0].numel()), ptr(t[0]), ptr(t[1]), ptr(t[2]), ptr(t[3]), ptr(t[4]), ptr(t[5]), ptr(t[6])))
+
+    def sample_sbpr(self, seed, epoch, first, count, neg_ratio, is_suk=True):
+        u, i, k, j = (torch.empty(count, dtype=torch.int32, device=self.device) for _ in range(4))
+        suk = torch.empty(count, dtype=torch.float32, device=self.device) if is_suk else None
+        check(self.lib.crb_sample_sbpr(self.h, seed, epoch, first, count, neg_ratio, ptr(u), ptr(i), ptr(k), ptr(j), ptr(suk), self.stream))
+        return (u, i, k, j, suk) if is_suk else (u, i, k, j)
+
+    def train_step_sbpr(self, P, Q, B, opt, u, i, k, j, suk, reg, loss_out=None):
+        """One `sess.run([train, loss], {u_idx, i_idx, i_s_idx, i_neg_idx, suk})` of SBPR (SBPR.py:51-57)."""
+        u, i, k, j = (self._feed_i32(x) for x in (u, i, k, j))
+        if not isinstance(suk, torch.Tensor):
+            suk = np.ascontiguousarray(np.asarray(suk), dtype=np.float32)
+        elif suk.dtype != torch.float32:
+            suk = suk.to(torch.float32)
+        for T_ in (P, Q, B):
+            if getattr(T_, "grad", None) is None:
+                T_.grad = torch.zeros_like(T_.w)
+        opt.t += 1
+        co = opt.c(opt.t)
+        host = np.zeros(1, dtype=np.float64) if loss_out is None else None
+        check(self.lib.crb_train_step_sbpr(self.h, C.byref(P.c), C.byref(Q.c), C.byref(B.c), ptr(P.grad), ptr(Q.grad), ptr(B.grad), C.byref(co),
+                                           ptr(u), ptr(i), ptr(k), ptr(j), ptr(suk), len(u), float(reg),
+                                           ptr(host) if loss_out is None else ptr(loss_out), self.stream))
         return float(host[0]) if loss_out is None else None
 
     # ------------------------------------------------------------------ TransCF
@@ -503,3 +536,40 @@ def history_from_dict(ui_train, n_users):
     seen_rowptr = np.zeros(n_users + 1, dtype=np.int64)
     np.cumsum(np.bincount(su, minlength=n_users), out=seen_rowptr[1:])
     return pos_user, pos_item, seen_rowptr, sc
+
+
+def social_arrays(ui_train, user_friends, SPu, n_users):
+    """-> (sp_pos_user, sp_pos_item, spu_start, spu_items, spu_suk, excl_rowptr, excl_cols): the flat form of the loops of
+    ranking_sampler_sbpr (utils/sampler.py:105-131).  suk of an SPu entry counts u's friends -- as often as they are listed --
+    that have a training list containing the item (:126-130)."""
+    pos_u, pos_i = [], []
+    spu_start = np.zeros(n_users + 1, dtype=np.int64)
+    excl_len = np.zeros(n_users + 1, dtype=np.int64)
+    sp_items, sp_suk, excl = [], [], []
+    lens = np.zeros(n_users, dtype=np.int64)
+    per_user = {}
+    for u, items in ui_train.items():
+        if u not in SPu:
+            continue
+        pos_u.extend([u] * len(items))
+        pos_i.extend(items)
+        spu = np.asarray(SPu[u], dtype=np.int64)
+        counts = {}
+        for friend in user_friends[u]:
+            if friend not in ui_train:
+                continue
+            for it in set(ui_train[friend]):
+                counts[it] = counts.get(it, 0) + 1
+        per_user[u] = (spu, np.asarray([counts.get(int(it), 0) for it in spu], dtype=np.float32),
+                       np.union1d(np.asarray(items, dtype=np.int64), spu))
+        lens[u] = spu.shape[0]
+    for u in range(n_users):
+        if u in per_user:
+            spu, suk, ex = per_user[u]
+            sp_items.append(spu); sp_suk.append(suk); excl.append(ex)
+            excl_len[u + 1] = ex.shape[0]
+    np.cumsum(lens, out=spu_start[1:])
+    excl_rowptr = np.cumsum(excl_len)
+    cat = lambda parts, dt: np.concatenate(parts).astype(dt) if parts else np.zeros(0, dtype=dt)
+    return (np.asarray(pos_u, dtype=np.int32), np.asarray(pos_i, dtype=np.int32), spu_start, cat(sp_items, np.int32), cat(sp_suk, np.float32),
+            excl_rowptr.astype(np.int64), cat(excl, np.int32))

@@ -12,7 +12,8 @@ vectorised.
 Additions for the B200 path: `train_rows = (users int32[n], items int32[n])`, the training split as two columns in the
 order the dict enumerates it, so that a model can hand them to `Engine.build_history` (csrc/history.cu) instead of walking
 the dict; `lazy_dicts=True` skips building `ui_train` as a dict of Python lists when only the columns are needed.
-Social files (`social_file`, RankingPreprocess.py:49-66) belong to the out-of-scope social models and are not read."""
+`social_file` (RankingPreprocess.py:49-58) gives `user_friends: dict[int -> list[int]]` for SBPR; the SAMN padding (:60-67) belongs to
+an out-of-scope model and is not applied."""
 import os
 
 import numpy as np
@@ -45,8 +46,17 @@ class RankingPreprocess(object):
         # New ids follow the iteration order of a Python set of the raw ids (utils/tools.py:9-15 re_index over a set)
         user_ids, item_ids = set(ratings['u_id'].unique()), set(ratings['i_id'].unique())
         self.user_nums, self.item_nums = len(user_ids), len(item_ids)
-        ratings['u_id'] = self._renumber(ratings['u_id'].to_numpy(), user_ids)
+        raw_users = ratings['u_id'].to_numpy()
+        ratings['u_id'] = self._renumber(raw_users, user_ids)
         ratings['i_id'] = self._renumber(ratings['i_id'].to_numpy(), item_ids)
+        if 'social_file' in c:   # RankingPreprocess.py:49-58: trust pairs among the kept users, re-indexed, grouped by the trustor
+            trusts = pd.read_csv(os.path.join(self.file_path, c['social_file']), sep=c['data.sep'], header=0, names=['u_id', 'v_id'], usecols=[0, 1])
+            tu, tv = trusts['u_id'].to_numpy(), trusts['v_id'].to_numpy()
+            known = np.fromiter(user_ids, dtype=raw_users.dtype, count=len(user_ids))
+            keep = np.isin(tu, known) & np.isin(tv, known)
+            tu, tv = self._renumber(tu[keep].astype(raw_users.dtype), user_ids), self._renumber(tv[keep].astype(raw_users.dtype), user_ids)
+            order = np.argsort(tu, kind='stable')        # groupby('u_id').v_id.apply(list): ascending trustor, file order inside
+            self.user_friends = _to_dict(tu[order], tv[order])
         return ratings, set(ratings['i_id'].unique())
 
     @staticmethod

@@ -136,3 +136,22 @@ def load_checkpoint(path):
     import numpy as np
     with np.load(path) as z:
         return {k.replace('__', '/'): z[k] for k in z.files}
+
+
+# Get SPu for SBPR (reference utils/tools.py:115-127): the items u's friends consumed and u did not, as a list per user.
+def get_SPu(data):
+    """The list order is the iteration order of the Python set the reference builds, and the sampler indexes the list by position
+    (utils/sampler.py:114-115), so the same sequence of set operations is performed here: per friend, union then difference."""
+    SPu = {}
+    friends_of = data.user_friends
+    for u in data.ui_train:
+        if u not in friends_of:
+            continue
+        own = set(data.ui_train[u])
+        social = set()
+        for friend in friends_of[u]:
+            if friend in data.ui_train:
+                social = social.union(set(data.ui_train[friend])).difference(own)
+        if social:
+            SPu[u] = list(social)
+    return SPu

@@ -155,7 +155,7 @@ int crb_sample_epoch_numpy(crb_handle* h, int32_t kind, int32_t neg_ratio, int32
                            void* stream);
 
 /* number of rows in one epoch of each sampler (utils/sampler.py:65 `train_nums`) */
-int64_t crb_epoch_rows(crb_handle* h, int32_t neg_ratio, int32_t sampler_kind /*0 pairwise,1 pointwise,2 cml*/);
+int64_t crb_epoch_rows(crb_handle* h, int32_t neg_ratio, int32_t sampler_kind /*0 pairwise,1 pointwise,2 cml,3 sbpr*/);
 
 /* sess.run([self.train, self.loss], {u_idx, i_idx, j_idx})  for model/ranking/BPR.py:31-44.
  * loss_out (double*, DEVICE or HOST) receives this step's summed loss (`loss_val`). */
@@ -237,6 +237,25 @@ int crb_train_step_neumf(crb_handle* h, const crb_table* Pg, const crb_table* Qg
 int crb_score_pairs_neumf(crb_handle* h, const float* Pg, const float* Qg, const float* Pm, const float* Qm, const float* dense,
                           int32_t E, int32_t Em, int32_t n_layers, const int32_t* u, const int32_t* i, int64_t n,
                           float* scores, void* stream);
+
+/* SBPR (model/ranking/SBPR.py:38-66; sampler utils/sampler.py:102-141; SPu utils/tools.py:115-127).
+ * crb_set_social installs what get_SPu and the sampler's inner loops derive from data.user_friends, as DEVICE arrays (borrowed):
+ *   sp_pos_user / sp_pos_item [n_sp_pos]  the positives of the users that have a non-empty SPu, in the sampler's enumeration order
+ *                                         (utils/sampler.py:105-110: dict order, users without SPu skipped)
+ *   spu_start [U+1], spu_items [n_spu]    SPu[u] as a list (the order `s = randint(len(spu)); SPu[u][s]` indexes, :114-115)
+ *   spu_suk [n_spu]                       the social coefficient of each entry: how many of u's friends consumed it (:124-131)
+ *   excl_rowptr [U+1], excl_cols          sorted unique union of u's own and social items: the rejection set of :118-120
+ * crb_sample_sbpr: rows [first, first+count) of the shuffled epoch -> (u, i, i_s, i_neg, suk) DEVICE outputs (suk may be NULL:
+ * is_suk=False).  crb_train_step_sbpr: sess.run([train, loss], {u_idx, i_idx, i_s_idx, i_neg_idx, suk}) (RankingRecommender.py:103-117);
+ * B is the bias vector [item_nums + 1] as a crb_table with dim = 1, rows padded to a multiple of 4; gradP / gradQ / gradB zeroed
+ * dense gradient buffers (left zeroed); feeds HOST or DEVICE. */
+int crb_set_social(crb_handle* h, int64_t n_sp_pos, const int32_t* sp_pos_user, const int32_t* sp_pos_item, const int64_t* spu_start,
+                   const int32_t* spu_items, const float* spu_suk, const int64_t* excl_rowptr, const int32_t* excl_cols);
+int crb_sample_sbpr(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t first, int64_t count, int32_t neg_ratio, int32_t* u,
+                    int32_t* i, int32_t* k, int32_t* j, float* suk, void* stream);
+int crb_train_step_sbpr(crb_handle* h, const crb_table* P, const crb_table* Q, const crb_table* B, float* gradP, float* gradQ, float* gradB,
+                        const crb_opt* opt, const int32_t* u, const int32_t* i, const int32_t* k, const int32_t* j, const float* suk,
+                        int64_t batch, float reg, double* loss_out, void* stream);
 
 /* LRML (model/ranking/LRML.py:42-78).  crb_train_step_lrml: sess.run([train, loss], {u_idx, i_idx, j_idx}) -- the LRAM memory
  * module (x = p*q, softmax(x K) M, :42-51), translated distances (:59-60), hinge + reg * l2 of the three gathered rows (:62-63).

@@ -96,6 +96,25 @@ def main():
     rs_out = np.asarray([[HR[k], MRR[k], NDCG[k]] for k in range(len(drv.topk))], dtype=np.float64)
     np.savez_compressed(os.path.join(OUT, "eval_loops.npz"), loo=loo, rs=rs_out, topk=np.asarray(drv.topk),
                         batch_size_t=drv.batch_size_t)
+    # F: SBPR on Ciao (the dataset with a trust file): the genuine preprocessing with social_file, get_SPu and ranking_sampler_sbpr
+    # on the first 150 training users (dict order; friends outside the slice are skipped by the reference's own membership tests)
+    cfg_sb = R.default_configs(recommender="SBPR", **{"data.dataset": "Ciao", "data.file_name": "ratings.csv", "data.sep": ",", "data.format": "UI",
+                                                       "data.split_way": "rs", "test.neg_samples": 0})
+    np.random.seed(5)
+    d_sb = R.preprocess(cfg_sb)
+    sub_users = list(d_sb.ui_train.keys())[:150]
+    sub = R.Data(d_sb.user_nums, d_sb.item_nums, {u: d_sb.ui_train[u] for u in sub_users}, {})
+    sub.user_friends = {u: d_sb.user_friends[u] for u in sub_users if u in d_sb.user_friends}
+    SPu = ref.get_SPu(sub)
+    np.random.seed(3)
+    sb = ref.ranking_sampler_sbpr(sub, SPu, 2, 4096)
+    np.savez_compressed(os.path.join(OUT, "sbpr_ciao.npz"), user_nums=sub.user_nums, item_nums=sub.item_nums,
+                        n_friend_users=len(d_sb.user_friends), n_friend_pairs=sum(len(v) for v in d_sb.user_friends.values()),
+                        **{"train_" + k: v for k, v in zip(("keys", "lens", "items"), flat(sub.ui_train))},
+                        **{"friends_" + k: v for k, v in zip(("keys", "lens", "items"), flat(sub.user_friends))},
+                        **{"spu_" + k: v for k, v in zip(("keys", "lens", "items"), flat(SPu))},
+                        sb_batches=sb[0], sb_u=sb[1].astype(np.int32), sb_i=sb[2].astype(np.int32), sb_k=sb[3].astype(np.int32),
+                        sb_j=sb[4].astype(np.int32), sb_suk=sb[5].astype(np.int32))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

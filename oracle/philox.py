@@ -205,3 +205,56 @@ def build_history(ui_train, user_nums):
             seen_rowptr[u + 1] = seen_rowptr[u]
     seen_cols = np.concatenate(cols).astype(np.int32) if cols else np.zeros(0, np.int32)
     return (np.asarray(pos_user, dtype=np.int32), np.asarray(pos_item, dtype=np.int32), seen_rowptr, seen_cols)
+
+
+def social_history(ui_train, user_friends, SPu, user_nums):
+    """What the SBPR sampler walks (utils/sampler.py:105-131), flattened: positives of the users that have an SPu (dict order),
+    per-user SPu lists with the social coefficient of every entry, and the sorted own + social item sets."""
+    pos_user, pos_item = [], []
+    spu, suk, excl = {}, {}, {}
+    for u, items in ui_train.items():
+        if u not in SPu:
+            continue
+        pos_user.extend([u] * len(items))
+        pos_item.extend(items)
+        spu[u] = list(SPu[u])
+        suk[u] = [sum(1 for f in user_friends[u] if f in ui_train and k in ui_train[f]) for k in SPu[u]]   # :126-130
+        excl[u] = sorted(set(items) | set(SPu[u]))
+    return (np.asarray(pos_user, dtype=np.int32), np.asarray(pos_item, dtype=np.int32), spu, suk, excl)
+
+
+def sample_sbpr(seed, epoch, first, count, neg_ratio, item_nums, social):
+    """Rows at epoch positions [first, first+count) -> (u, i, k, j, suk).  Twin of crb_sample_sbpr: source row s = pi(position)
+    draws from Philox blocks with counter (s_lo, s_hi, 0x80000000 | blk, epoch); the first word w with
+    (w & mask(len(SPu[u]) - 1)) < len(SPu[u]) picks the social item, each later word is a negative candidate (masked rejection,
+    then membership in own + social items).  Rows are independent: no distinctness inside a positive's group."""
+    pos_user, pos_item, spu, suk, excl = social
+    N = pos_user.shape[0] * neg_ratio
+    keys = perm_keys(seed, epoch)
+    src = feistel_perm(np.arange(first, first + count, dtype=np.uint64), N, keys)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    imask = item_mask(item_nums)
+    out = np.zeros((5, count), dtype=np.int64)
+    for t, s in enumerate(src.tolist()):
+        p = s // neg_ratio
+        u = int(pos_user[p])
+        n_sp = len(spu[u])
+        smask = item_mask(n_sp)
+        ex = set(excl[u])
+        pick, neg, blk = -1, -1, 0
+        while neg < 0 and blk < MAX_BLOCKS:
+            words = philox4x32_10(s & 0xFFFFFFFF, s >> 32, 0x80000000 | blk, epoch, k0, k1)
+            for w in words:
+                w = int(w)
+                if neg >= 0:
+                    break
+                if pick < 0:
+                    if (w & smask) < n_sp:
+                        pick = w & smask
+                    continue
+                v = w & imask
+                if v < item_nums and v not in ex:
+                    neg = v
+            blk += 1
+        out[:, t] = (u, pos_item[p], spu[u][pick], neg, suk[u][pick])
+    return tuple(out[r].astype(np.int32) for r in range(4)) + (out[4].astype(np.float32),)

@@ -9,6 +9,8 @@ build container and against the committed fixtures in ``tests/golden/`` everywhe
   pairwise_ranking_sampler   <- utils/sampler.py:46-74
   pointwise_ranking_sampler  <- utils/sampler.py:10-43
   ranking_sampler_cml        <- utils/sampler.py:77-99
+  ranking_sampler_sbpr       <- utils/sampler.py:102-141
+  get_SPu                    <- utils/tools.py:115-127
   nais_user_batches          <- model/RankingRecommender.py:64-87 (sampling part)
   cal_ranking_metrics        <- utils/metrics.py:9-19
   eval_loo / eval_rs         <- model/RankingRecommender.py:250-299 / 198-247 (everything after sess.run)
@@ -81,6 +83,54 @@ def ranking_sampler_cml(data, neg_ratio, batch_size):
     train_batches = math.ceil(n / batch_size)
     s_idx = np.random.permutation(n)
     return train_batches, np.array(u_f)[s_idx], np.array(i_f)[s_idx], np.array(negs)[s_idx]
+
+
+def get_SPu(data):
+    # utils/tools.py:115-127: items of u's friends that u has not consumed; list(set) order is what the sampler indexes
+    SPu = {}
+    for u in data.ui_train:
+        acc = set()
+        if u in data.user_friends:
+            for friend in data.user_friends[u]:
+                if friend not in data.ui_train:
+                    continue
+                acc = acc.union(set(data.ui_train[friend])).difference(set(data.ui_train[u]))
+            if acc:
+                SPu[u] = list(acc)
+    return SPu
+
+
+def ranking_sampler_sbpr(data, SPu, neg_ratio, batch_size, is_suk=True):
+    u_f, i_f, k_f, j_f, suk_f = [], [], [], [], []
+    for u, items in data.ui_train.items():
+        if u not in SPu:
+            continue
+        tru, spu = set(items), set(SPu[u])
+        for i in items:
+            for _ in range(neg_ratio):
+                u_f.append(u)
+                i_f.append(i)
+                s = np.random.randint(len(spu))
+                k_f.append(SPu[u][s])
+                neg = np.random.randint(data.item_nums)
+                while neg in tru or neg in spu:
+                    neg = np.random.randint(data.item_nums)
+                j_f.append(neg)
+                if is_suk:
+                    suk = 0
+                    for friend in data.user_friends[u]:
+                        if friend not in data.ui_train:
+                            continue
+                        if SPu[u][s] in data.ui_train[friend]:
+                            suk += 1
+                    suk_f.append(suk)
+    n = len(u_f)
+    train_batches = math.ceil(n / batch_size)
+    s_idx = np.random.permutation(n)
+    out = (train_batches, np.array(u_f)[s_idx], np.array(i_f)[s_idx], np.array(k_f)[s_idx], np.array(j_f)[s_idx])
+    if is_suk:
+        out = out + (np.array(suk_f)[s_idx],)
+    return out
 
 
 def nais_user_batches(data, neg_ratio):

@@ -8,6 +8,7 @@ is committed as a fixture under ``tests/golden/`` by ``oracle/make_golden.py``.
 
 What is exposed (all unmodified reference code):
   * utils/sampler.py:10-99   pointwise_ranking_sampler / pairwise_ranking_sampler / ranking_sampler_cml
+  * utils/sampler.py:102-141 ranking_sampler_sbpr;  utils/tools.py:115-127 get_SPu
   * utils/metrics.py:9-19    cal_ranking_metrics
   * model/RankingPreprocess.py:13-134  RankingPreprocess
   * model/RankingRecommender.py:33-100,198-348  train/test loops, driven by a FakeSession
@@ -69,6 +70,8 @@ def load():
         pairwise_ranking_sampler=sampler.pairwise_ranking_sampler,
         pointwise_ranking_sampler=sampler.pointwise_ranking_sampler,
         ranking_sampler_cml=sampler.ranking_sampler_cml,
+        ranking_sampler_sbpr=sampler.ranking_sampler_sbpr,
+        get_SPu=tools.get_SPu,
         cal_ranking_metrics=metrics.cal_ranking_metrics,
         cal_rmse_mae=metrics.cal_rmse_mae,
         re_index=tools.re_index,
