@@ -151,6 +151,44 @@ __device__ __forceinline__ void sum_slots(float4* acc, const float* __restrict__
                                           const uint32_t* __restrict__ dup_src, uint32_t lo, uint32_t hi, bool ordered, int dim, int gl) {
 #pragma unroll
     for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t n = hi - lo;
+    // Two to four occurrences (all but ~1e-3 of the duplicated rows of a uniform batch): every slot is requested at once, so the
+    // row costs one memory round trip instead of one per occurrence; the adds then run in ascending key order from registers
+    // (for two occurrences the order is immaterial: (0 + a) + b == (0 + b) + a bit for bit).
+    if (ordered && n >= 2u && n <= 4u && VPL <= 2) {
+        float4 G[4][VPL];
+        uint32_t key[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const bool on = (uint32_t)q < n;
+            const uint32_t sq = lo + (on ? q : 0);
+            key[q] = on ? (n > 2u ? dup_t[sq] : (uint32_t)q) : 0xFFFFFFFFu;
+            const int64_t src = dup_src ? dup_src[sq] : sq;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int c = (gl + LANES * v) * 4;
+                G[q][v] = (on && c < dim) ? ld4(dup_grad + src * dim + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        // rank of each slot among the keys (keys are unique; absent slots carry the maximum and sort last)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if ((uint32_t)k >= n) break;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int rk = 0;
+#pragma unroll
+                for (int o = 0; o < 4; ++o) rk += (key[o] < key[q]) ? 1 : 0;
+                if (rk == k && (uint32_t)q < n) {
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        acc[v].x += G[q][v].x; acc[v].y += G[q][v].y; acc[v].z += G[q][v].z; acc[v].w += G[q][v].w;
+                    }
+                }
+            }
+        }
+        return;
+    }
     if (ordered) {
         int64_t prev = -1;
         for (uint32_t k = lo; k < hi; ++k) {
