@@ -156,6 +156,7 @@ extern "C" int crb_destroy(crb_handle* h) {
     cudaFree(h->dense_loss);
     cudaFree(h->np_state); cudaFree(h->np_raw); cudaFree(h->np_scratch); cudaFree(h->np_sort_tmp); cudaFree(h->np_result);
     cudaFree(h->dense_grad);
+    cudaFree(h->bloom);
     cudaFree(h->eval_ws);
     if (h->prof_ev) { for (int k = 0; k < 2 * CRB_PROF_CAP; ++k) cudaEventDestroy(h->prof_ev[k]); free(h->prof_ev); }
     free(h);
@@ -164,6 +165,62 @@ extern "C" int crb_destroy(crb_handle* h) {
 
 extern "C" int64_t crb_launch_count(crb_handle* h) { return h ? h->launches : -1; }
 
+// ---------------------------------------------------------------------------------------------- seen-item Bloom filters
+__global__ void __launch_bounds__(256) bloom_build_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ cols, int64_t n_users,
+                                                          uint32_t* bloom, int shift) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t u = warp; u < n_users; u += n_warps) {
+        const int64_t lo = rowptr[u], hi = rowptr[u + 1];
+        uint32_t* mine = bloom + (u << shift);
+        for (int64_t p = lo + lane; p < hi; p += 32) {
+            const uint32_t bit = crb_bloom_bit((uint32_t)cols[p], shift);
+            atomicOr(mine + (bit >> 5), 1u << (bit & 31));
+        }
+    }
+}
+
+// (Re)builds the per-user Bloom filters for the history just installed.  ~8 bits per seen entry on average, 32..2048 bits per user;
+// skipped (bloom = NULL, exact search only) when it would not fit in a quarter of the free device memory or CRB_NO_BLOOM is set.
+int crb_bloom_build(crb_handle* h, cudaStream_t s) {
+    CRB_CUDA(cudaSetDevice(h->device));
+    int64_t n_seen = 0;
+    CRB_CUDA(cudaMemcpyAsync(&n_seen, h->seen_rowptr + h->n_users, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CRB_CUDA(cudaStreamSynchronize(s));
+    const bool off = getenv("CRB_NO_BLOOM") != nullptr || n_seen <= 0 || !h->seen_cols;
+    int shift = 0;
+    if (!off) {
+        const double bits = 8.0 * (double)n_seen / (double)h->n_users;
+        while (shift < 6 && (double)(32u << shift) < bits) ++shift;
+        size_t free_b = 0, total_b = 0;
+        CRB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        while (shift > 0 && (size_t)(h->n_users << shift) * 4 > free_b / 4) --shift;
+        if ((size_t)(h->n_users << shift) * 4 > free_b / 4) shift = -1;
+    }
+    if (off || shift < 0) {
+        if (h->bloom) { CRB_CUDA(cudaStreamSynchronize(s)); cudaFree(h->bloom); }
+        h->bloom = nullptr; h->bloom_words = 0; h->bloom_shift = 0;
+        return CRB_OK;
+    }
+    const int64_t words = h->n_users << shift;
+    if (words > h->bloom_words) {
+        CRB_CUDA(cudaStreamSynchronize(s));
+        cudaFree(h->bloom);
+        h->bloom = nullptr; h->bloom_words = 0;
+        CRB_CUDA(cudaMalloc(&h->bloom, sizeof(uint32_t) * words));
+        h->bloom_words = words;
+    }
+    h->bloom_shift = shift;
+    CRB_CUDA(cudaMemsetAsync(h->bloom, 0, sizeof(uint32_t) * words, s));
+    int64_t grid = (h->n_users + 7) / 8;
+    if (grid > (int64_t)h->sm_count * 32) grid = (int64_t)h->sm_count * 32;
+    bloom_build_kernel<<<(int)grid, 256, 0, s>>>(h->seen_rowptr, h->seen_cols, h->n_users, h->bloom, shift);
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}
+
 extern "C" int crb_set_history(crb_handle* h, int64_t n_users, int64_t n_items, int64_t n_pos, const int32_t* pos_user,
                                const int32_t* pos_item, const int64_t* seen_rowptr, const int32_t* seen_cols, void* stream) {
     CRB_CHECK_ARG(h, "null handle");
@@ -171,7 +228,6 @@ extern "C" int crb_set_history(crb_handle* h, int64_t n_users, int64_t n_items, 
     CRB_CHECK_ARG(n_users < 0x7fffffffLL && n_items < 0x7fffffffLL, "row ids are int32");
     CRB_CHECK_ARG(crb_is_device_ptr(seen_rowptr), "seen_rowptr must be a device pointer");
     CRB_CHECK_ARG(n_pos == 0 || (crb_is_device_ptr(pos_user) && crb_is_device_ptr(pos_item)), "pos_user/pos_item must be device pointers");
-    (void)stream;
     h->n_users = n_users;
     h->n_items = n_items;
     h->n_pos = n_pos;
@@ -181,7 +237,7 @@ extern "C" int crb_set_history(crb_handle* h, int64_t n_users, int64_t n_items, 
     h->seen_cols = seen_cols;
     h->list_start = nullptr;
     h->list_len = nullptr;
-    return CRB_OK;
+    return crb_bloom_build(h, (cudaStream_t)stream);
 }
 
 int crb_meta_reserve(crb_handle* h, int which, int64_t rows, cudaStream_t s) {

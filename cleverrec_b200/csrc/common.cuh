@@ -66,6 +66,12 @@ struct crb_handle {
     const int32_t* pos_item;
     const int64_t* seen_rowptr;
     const int32_t* seen_cols;
+    // Per-user Bloom filter over the seen items (library-owned, built by crb_set_history): 2^bloom_shift words per user, one hash.
+    // A clear bit proves "not in the history" with ONE 32-byte probe whose address needs only (u, item) -- the sampler's rejection
+    // test (utils/sampler.py:58-59) falls back to the exact binary search over seen_cols only on a set bit (~9 % at 8 bits/entry).
+    uint32_t* bloom;
+    int bloom_shift;
+    int64_t bloom_words;        // allocated words
     const int64_t* list_start;  // per-user offset / length of the interaction list inside pos_item (FISM / NAIS)
     const int32_t* list_len;
     const int64_t* ilist_start; // item-side lists (TransCF's iu_sp_mat, utils/tools.py:100-113): users of each item inside ipos_user
@@ -212,7 +218,11 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// bit of `item` inside a user's Bloom filter of 32 << shift bits (one multiplicative hash, top bits)
+__host__ __device__ __forceinline__ uint32_t crb_bloom_bit(uint32_t item, int shift) { return (item * 0x9E3779B1u) >> (27 - shift); }
+
 // internal entry points shared between translation units
+int crb_bloom_build(crb_handle* h, cudaStream_t s);
 int crb_ws_reserve(crb_handle* h, int64_t batch, int32_t dim, int64_t steps, cudaStream_t s);
 int crb_meta_reserve(crb_handle* h, int which, int64_t rows, cudaStream_t s);
 int crb_eval_ws_reserve(crb_handle* h, int64_t bytes);

@@ -21,6 +21,8 @@ struct SamplerArgs {
     const int32_t* pos_item;
     const int64_t* seen_rowptr;
     const int32_t* seen_cols;
+    const uint32_t* bloom;  // per-user seen-item Bloom filters (NULL: exact search only)
+    int bloom_shift;
 };
 
 __device__ __forceinline__ uint32_t mix32(uint32_t x, uint32_t k) {
@@ -59,17 +61,37 @@ __device__ __forceinline__ bool history_contains(const int32_t* __restrict__ col
 }
 
 // Accepts negatives of positive p until `need` are found; acc[] receives them in order.  false on attempt overflow.
+// The four candidates of a Philox block are tested against the user's Bloom filter with four independent probes issued together
+// (one round trip); only a set bit (or no filter) costs the dependent binary search over the sorted history.  The accept / reject
+// decisions, hence the output, are those of the exact test alone.
 __device__ __forceinline__ bool draw_negatives(uint64_t p, int32_t u, uint32_t need, int32_t* acc, const SamplerArgs& a) {
-    const int64_t lo = a.seen_rowptr[u], hi = a.seen_rowptr[u + 1];
+    const uint32_t* bl = a.bloom ? a.bloom + ((int64_t)u << a.bloom_shift) : nullptr;
+    int64_t lo = 0, hi = -1;     // the history bounds are fetched only if a candidate needs the exact test
+    if (!bl) { lo = a.seen_rowptr[u]; hi = a.seen_rowptr[u + 1]; }
     uint32_t got = 0;
     for (uint32_t blk = 0; blk < CRB_SAMPLER_MAX_BLOCKS; ++blk) {
-        uint32_t w[4];
+        uint32_t w[4], bw[4];
         philox4x32_10((uint32_t)p, (uint32_t)(p >> 32), blk, a.epoch, a.k0, a.k1, w);
+        // probe for as many candidates as are still needed plus one spare (a random 32-byte sector each)
+        const uint32_t probes = need - got + 1u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t v = w[q] & a.item_mask;
+            const uint32_t bit = crb_bloom_bit(v, a.bloom_shift);
+            bw[q] = (bl && (uint32_t)q < probes && (int32_t)v < a.n_items) ? (__ldg(bl + (bit >> 5)) >> (bit & 31)) & 1u : 2u;
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             int32_t v = (int32_t)(w[q] & a.item_mask);
             if (v >= a.n_items) continue;
-            if (history_contains(a.seen_cols, lo, hi, v)) continue;
+            if (bl && bw[q] == 2u) {   // not probed yet
+                const uint32_t bit = crb_bloom_bit((uint32_t)v, a.bloom_shift);
+                bw[q] = (__ldg(bl + (bit >> 5)) >> (bit & 31)) & 1u;
+            }
+            if (bw[q]) {
+                if (hi < 0) { lo = a.seen_rowptr[u]; hi = a.seen_rowptr[u + 1]; }
+                if (history_contains(a.seen_cols, lo, hi, v)) continue;
+            }
             bool dup = false;
             for (uint32_t s = 0; s < got; ++s) dup |= (acc[s] == v);
             if (dup) continue;
@@ -180,6 +202,8 @@ static int make_args(crb_handle* h, uint64_t seed, uint32_t epoch, int32_t neg_r
     a->pos_item = h->pos_item;
     a->seen_rowptr = h->seen_rowptr;
     a->seen_cols = h->seen_cols;
+    a->bloom = h->bloom;
+    a->bloom_shift = h->bloom_shift;
     return CRB_OK;
 }
 
@@ -396,6 +420,7 @@ extern "C" int crb_sample_sbpr(crb_handle* h, uint64_t seed, uint32_t epoch, int
     A.base.half_bits = bits / 2;
     A.base.half_mask = (uint32_t)(((uint64_t)1 << A.base.half_bits) - 1);
     A.base.pos_user = h->sp_pos_user; A.base.pos_item = h->sp_pos_item; A.base.seen_rowptr = h->excl_rowptr; A.base.seen_cols = h->excl_cols;
+    A.base.bloom = nullptr; A.base.bloom_shift = 0;   // the filter covers the history, not the own + social exclusion sets
     A.spu_start = h->spu_start; A.spu_items = h->spu_items; A.spu_suk = h->spu_suk;
     CRB_CHECK_ARG(first >= 0 && count >= 0 && (uint64_t)(first + count) <= A.base.n_rows, "rows outside the epoch");
     sample_sbpr_kernel<<<sampler_grid(h, count), 256, 0, s>>>(A, first, count, u, i, k, j, suk, h->ctr);
