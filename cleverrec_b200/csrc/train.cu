@@ -468,8 +468,16 @@ struct BprArgs {
     double* block_loss;
 };
 
+// CTAs per SM: the Adam variants need ~80 registers (3 CTAs).  SGD moves 3x fewer bytes per triplet and is bound by the bytes in
+// flight: it fits 64 registers without spilling and takes a fourth resident CTA (K3 1.03 -> 0.76 ms).  Adagrad spills at 64 registers
+// and gets slower (1.23 -> 1.32 ms), so it stays at three.
+#ifndef CRB_SGD_CTAS
+#define CRB_SGD_CTAS 4
+#endif
+template <int OPT> struct BprOcc { static constexpr int ctas = OPT == OPT_SGD ? CRB_SGD_CTAS : 3; };
+
 template <int LANES, int VPL, int OPT>
-__global__ void __launch_bounds__(256, 3) bpr_step_kernel(BprArgs a) {
+__global__ void __launch_bounds__(256, BprOcc<OPT>::ctas) bpr_step_kernel(BprArgs a) {
     constexpr int GPW = 32 / LANES;
     const int lane = threadIdx.x & 31;
     const int gl = lane % LANES;
