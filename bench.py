@@ -269,6 +269,22 @@ def run_ours(args, w):
         e2e_step(feeds[k])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    e2e_sync = world * B * n_e2e / e2e_s   # one blocking call per step: feed in, loss out, host waits (the reference's sess.run)
+    e2e_path = "crb_train_step_bpr per step (host int32 feeds, host loss, blocking)"
+    if sharded is None:
+        # the reference's epoch loop (RankingRecommender.py:39-46) as ONE call over the caller-sampled epoch arrays: every step still
+        # copies its own 12*B bytes of feed from pinned host memory and returns its own loss to pinned host memory, but step k+1's
+        # feed is staged on the copy stream while step k computes
+        eu, ei, ej = (torch.cat([f[c] for f in feeds[:n_e2e]]).pin_memory() for c in range(3))
+        host_losses = torch.zeros(n_e2e, dtype=torch.float64).pin_memory()
+        eng.train_epoch_bpr_feeds(P, Q, opt, feeds[n_e2e][0], feeds[n_e2e][1], feeds[n_e2e][2], B, reg, host_losses[:1])  # warm
+        barrier()
+        t0 = time.perf_counter()
+        eng.train_epoch_bpr_feeds(P, Q, opt, eu, ei, ej, B, reg, host_losses)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        assert bool(torch.isfinite(host_losses).all()) and float(host_losses.min()) > 0
+        e2e_path = "crb_train_epoch_bpr_feeds: the reference's epoch loop over host feed arrays, per-step H2D feed + per-step D2H loss, feeds staged one step ahead"
     if world > 1:
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -360,7 +376,8 @@ def run_ours(args, w):
                            "parallelism": ("single GPU" if world == 1 else "%d ranks: users partitioned, item table row-sharded (item %% N), rows and gradients "
                                            "over NVLink peer memory, NCCL only as the step barrier" % world), "inbox_overflow": overflow,
                            "setup_s": round(t_setup, 1)},
-                "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 8, "steps": n_e2e},
+                "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 8, "steps": n_e2e, "path": e2e_path,
+                        "blocking_per_step_value": e2e_sync},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "eval": ev, "final_loss": loss_last}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -791,6 +791,73 @@ extern "C" int crb_train_epoch_bpr(crb_handle* h, const crb_table* P, const crb_
     return CRB_OK;
 }
 
+// RankingRecommender.train_model's loop (:39-46) over an epoch the CALLER sampled (the reference's own sampler output, host arrays):
+//   for id in range(train_batches): sess.run([train, loss], {u_idx: u[id*B:(id+1)*B], ...})
+// as one call.  Step k+1's feed is copied host -> device and counted / assigned on the auxiliary stream into the alternate copy of the
+// step state while step k computes (the copy engine runs beside the SMs, so the 12*B bytes of a feed cost no step time); every step's
+// loss goes back to the host with its own asynchronous copy when loss_out is page-locked memory (one copy at the end otherwise).
+extern "C" int crb_train_epoch_bpr_feeds(crb_handle* h, const crb_table* P, const crb_table* Q, const crb_opt* opt, const int32_t* u,
+                                         const int32_t* i, const int32_t* j, int64_t n_rows, int64_t batch, float reg, double* loss_out,
+                                         void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    OptDev od;
+    int opt_kind = 0;
+    CRB_CHECK_ARG(u && i && j && n_rows >= 1, "null / empty feed");
+    int rc = bpr_common_checks(h, P, Q, opt, &od, &opt_kind, batch, (n_rows + batch - 1) / batch, s);
+    if (rc) return rc;
+    const int64_t n_steps = (n_rows + batch - 1) / batch;
+    const bool dev_feed = crb_is_device_ptr(u);
+    CRB_CHECK_ARG(dev_feed == crb_is_device_ptr(i) && dev_feed == crb_is_device_ptr(j), "u / i / j must all be host or all be device arrays");
+    const bool host_loss = !(loss_out && crb_is_device_ptr(loss_out));
+    bool pinned_loss = false;
+    if (loss_out && host_loss) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, loss_out) == cudaSuccess) pinned_loss = at.type == cudaMemoryTypeHost; else cudaGetLastError();
+    }
+    crb_opt step_opt = *opt;
+    const bool overlap = n_steps > 1;
+    struct Restore { crb_handle* h; ~Restore() { if (h->alt_active) crb_alt_swap(h); } } restore{h};
+    cudaStream_t ps = s;
+    if (overlap) {
+        if ((rc = crb_alt_reserve(h, s))) return rc;
+        ps = h->aux_stream;
+        CRB_CUDA(cudaEventRecord(h->ev_entry, s));
+        CRB_CUDA(cudaStreamWaitEvent(ps, h->ev_entry, 0));
+    }
+    for (int64_t k = 0; k < n_steps; ++k) {
+        const int64_t lo = k * batch;
+        const int64_t b = (n_rows - lo) < batch ? (n_rows - lo) : batch;
+        const int set = (int)(k & 1);
+        if (overlap && h->alt_active != set) crb_alt_swap(h);
+        step_opt.step = opt->step + k;
+        if ((rc = crb_opt_to_dev(h, &step_opt, &od, &opt_kind, s))) return rc;
+        if (overlap && k >= 2) CRB_CUDA(cudaStreamWaitEvent(ps, h->ev_done[set], 0));
+        if ((rc = crb_zero_step_counters(h, ps))) return rc;
+        const int32_t *du = u + lo, *di = i + lo, *dj = j + lo;
+        if (!dev_feed) {
+            CRB_CUDA(cudaMemcpyAsync(h->idx[0], u + lo, sizeof(int32_t) * b, cudaMemcpyHostToDevice, ps));
+            CRB_CUDA(cudaMemcpyAsync(h->idx[1], i + lo, sizeof(int32_t) * b, cudaMemcpyHostToDevice, ps));
+            CRB_CUDA(cudaMemcpyAsync(h->idx[2], j + lo, sizeof(int32_t) * b, cudaMemcpyHostToDevice, ps));
+            du = h->idx[0]; di = h->idx[1]; dj = h->idx[2];
+        }
+        if ((rc = bpr_step_prepare(h, du, di, dj, b, false, ps))) return rc;
+        if (overlap) {
+            CRB_CUDA(cudaEventRecord(h->ev_prep[set], ps));
+            CRB_CUDA(cudaStreamWaitEvent(s, h->ev_prep[set], 0));
+        }
+        double* ld = host_loss ? h->loss_dev + k : loss_out + k;
+        if ((rc = bpr_step_compute(h, P, Q, od, opt_kind, du, di, dj, b, reg, ld, s))) return rc;
+        if (pinned_loss) CRB_CUDA(cudaMemcpyAsync(loss_out + k, ld, sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (overlap) CRB_CUDA(cudaEventRecord(h->ev_done[set], s));
+    }
+    if (overlap && h->alt_active) crb_alt_swap(h);
+    if (loss_out && host_loss) {
+        if (pinned_loss) CRB_CUDA(cudaStreamSynchronize(s));
+        else if ((rc = finish_loss(h, loss_out, n_steps, s))) return rc;
+    }
+    return CRB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ Adam flush
 template <int OPT>
 __global__ void __launch_bounds__(256) adam_flush_kernel(TableDev T, int64_t rows, int dim, OptDev o) {

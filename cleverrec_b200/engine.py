@@ -236,6 +236,22 @@ class Engine(object):
                                            neg_ratio, float(reg), ptr(loss_out), self.stream))
         opt.t += n_steps
 
+    def train_epoch_bpr_feeds(self, P, Q, opt, u, i, j, batch, reg, loss_out):
+        """RankingRecommender.train_model's loop (:39-46) over caller-sampled epoch arrays u / i / j (host NumPy / pinned torch CPU
+        tensors, or device tensors): ceil(len(u) / batch) steps, feeds staged one step ahead.  loss_out: double [n_steps], device
+        tensor (no sync) or host (NumPy / pinned tensor; the call returns when the last loss has landed)."""
+        def feed(x):
+            if isinstance(x, torch.Tensor):
+                return x if x.dtype == torch.int32 and x.is_contiguous() else x.to(torch.int32).contiguous()
+            return np.ascontiguousarray(np.asarray(x), dtype=np.int32)
+        u, i, j = feed(u), feed(i), feed(j)
+        n = len(u)
+        n_steps = -(-n // batch)
+        co = opt.c(opt.t + 1)
+        check(self.lib.crb_train_epoch_bpr_feeds(self.h, C.byref(P.c), C.byref(Q.c), C.byref(co), ptr(u), ptr(i), ptr(j), n, batch, float(reg),
+                                                 ptr(loss_out), self.stream))
+        opt.t += n_steps
+
     def train_step_pointwise(self, kind, P, Q, opt, u, i, y, reg, loss_kind, hvec=None, h_s1=None, h_s2=None, loss_out=None):
         """One `sess.run([train, loss], {u_idx, i_idx, y})` of MF (kind SCORE_DOT) / GMF (kind SCORE_GMF, hvec = h_gmf and
         its optimizer slots, device tensors).  Host or device feeds; returns the loss when loss_out is None."""

@@ -170,6 +170,15 @@ int crb_train_epoch_bpr(crb_handle* h, const crb_table* P, const crb_table* Q, c
                         uint64_t seed, uint32_t epoch, int64_t first, int64_t batch, int64_t n_steps,
                         int32_t neg_ratio, float reg, double* loss_out, void* stream);
 
+/* The same loop over an epoch the CALLER sampled -- the reference's own `train_ = pairwise_ranking_sampler(...)` arrays, HOST (or
+ * DEVICE) int32 [n_rows]: step k trains on rows [k*batch, min((k+1)*batch, n_rows)), exactly the slices of RankingRecommender.py:40-42.
+ * Feeds are staged one step ahead on the library's copy stream, so the host -> device copies overlap the previous step's kernels.
+ * loss_out: DEVICE or HOST double [ceil(n_rows / batch)]; page-locked host memory receives each step's loss with its own asynchronous
+ * copy.  The call returns after the last loss has landed when loss_out is on the host.  opt->step is the index of the first step. */
+int crb_train_epoch_bpr_feeds(crb_handle* h, const crb_table* P, const crb_table* Q, const crb_opt* opt,
+                              const int32_t* u, const int32_t* i, const int32_t* j, int64_t n_rows, int64_t batch,
+                              float reg, double* loss_out, void* stream);
+
 /* sess.run([train, loss], {u_idx, i_idx, y}) for the pointwise dot-product family:
  *   kind CRB_SCORE_DOT : MF   (BPR.py:39 dot + get_loss('square'|'cross_entropy'))
  *   kind CRB_SCORE_GMF : GMF  (GMF.py:37-49), h/h_s1/h_s2 = the dense variable h_gmf and its slots */

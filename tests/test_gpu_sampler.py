@@ -76,3 +76,29 @@ def test_catalogue_exhausted_is_an_error(eng):
     with pytest.raises(CrbError) as e:
         eng.sample_pairwise(0, 0, 0, 11, 1)
     assert e.value.code == -4
+
+
+@pytest.mark.parametrize("shape", [(60, 40, 18, 3), (200, 3000, 2, 2), (50, 20000, 600, 4)])
+def test_bloom_filter_never_changes_the_output(eng, shape, monkeypatch):
+    """The per-user seen-item Bloom filters (csrc/api.cu::crb_bloom_build) only short-cut the rejection test of
+    utils/sampler.py:58-59: with the filters disabled (CRB_NO_BLOOM, read when the history is installed) the sampler takes the exact
+    binary search for every candidate and must return the same triplets -- including saturated filters (histories much longer than
+    the 2048-bit cap) and nearly empty ones (32 bits per user)."""
+    U, I, L, R = shape
+    d = synthetic_data(U, I, L, seed=U + 1)
+    pu, pi, rp, sc = X.build_history(d.ui_train, d.user_nums)
+    n = pu.shape[0] * R
+    outs = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("CRB_NO_BLOOM", "1")
+        else:
+            monkeypatch.delenv("CRB_NO_BLOOM", raising=False)
+        eng.set_history(d.ui_train, d.user_nums, d.item_nums)
+        outs.append([t.cpu().numpy() for t in eng.sample_pairwise(0xABCDEF, 2, 0, n, R)])
+        outs[-1] += [t.cpu().numpy() for t in eng.sample_cml(5, 1, 0, pu.shape[0], R)]
+    monkeypatch.delenv("CRB_NO_BLOOM", raising=False)
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    ru, ri, rj, _ = X.sample_pairwise(0xABCDEF, 2, 0, n, R, d.item_nums, pu, pi, rp, sc)
+    assert np.array_equal(outs[0][2], rj) and np.array_equal(outs[0][0], ru)

@@ -156,3 +156,37 @@ def test_argument_errors(eng):
     assert e.value.code == -1
     with pytest.raises(ValueError):
         Optimizer("RMSProp", 0.1)
+
+
+@pytest.mark.parametrize("kind", ["SGD", "Adam"])
+def test_epoch_over_host_feeds_equals_step_by_step(kind):
+    """crb_train_epoch_bpr_feeds (the reference's epoch loop, RankingRecommender.py:39-46, over caller-sampled host arrays with the
+    feeds staged one step ahead) == one blocking crb_train_step_bpr per slice: same losses, same tables, bit for bit; ragged tail;
+    pinned / pageable / device feeds and loss buffers."""
+    import torch
+    from cleverrec_b200.engine import Engine, Optimizer, Table
+    eng = Engine(0)
+    U, I, d, B = 300, 500, 64, 1000
+    g = torch.Generator().manual_seed(2)
+    P0, Q0 = torch.randn(U, d, generator=g) * 0.1, torch.randn(I, d, generator=g) * 0.1
+    rs = np.random.RandomState(4)
+    n = 4 * B + 137
+    u, i, j = rs.randint(0, U, n).astype(np.int32), rs.randint(0, I, n).astype(np.int32), rs.randint(0, I, n).astype(np.int32)
+    Pa, Qa, oa = Table(P0.clone().cuda(), kind), Table(Q0.clone().cuda(), kind), Optimizer(kind, 0.01)
+    want = [eng.train_step_bpr(Pa, Qa, oa, u[k:k + B], i[k:k + B], j[k:k + B], 0.01) for k in range(0, n, B)]
+    eng.adam_flush(Pa, oa); eng.adam_flush(Qa, oa)
+    for mode in ("pageable", "pinned", "device"):
+        Pb, Qb, ob = Table(P0.clone().cuda(), kind), Table(Q0.clone().cuda(), kind), Optimizer(kind, 0.01)
+        if mode == "pageable":
+            feeds, losses = (u, i, j), np.zeros(5)
+        elif mode == "pinned":
+            feeds, losses = tuple(torch.from_numpy(x).pin_memory() for x in (u, i, j)), torch.zeros(5, dtype=torch.float64).pin_memory()
+        else:
+            feeds, losses = tuple(torch.from_numpy(x).cuda() for x in (u, i, j)), torch.zeros(5, dtype=torch.float64, device="cuda")
+        eng.train_epoch_bpr_feeds(Pb, Qb, ob, feeds[0], feeds[1], feeds[2], B, 0.01, losses)
+        got = losses.tolist() if mode == "pageable" else losses.cpu().tolist()
+        assert got == want, mode
+        assert ob.t == oa.t == 5
+        eng.adam_flush(Pb, ob); eng.adam_flush(Qb, ob)
+        assert torch.equal(Pb.w, Pa.w) and torch.equal(Qb.w, Qa.w), mode
+    eng.close()
