@@ -269,7 +269,13 @@ def run_ours(args, w):
         e2e_step(feeds[k])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    e2e_sync = world * B * n_e2e / e2e_s   # one blocking call per step: feed in, loss out, host waits (the reference's sess.run)
+    def max_over_ranks(sec):
+        if world > 1:
+            t = torch.tensor([sec], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return sec
+    e2e_sync = world * B * n_e2e / max_over_ranks(e2e_s)   # one blocking call per step: feed in, loss out, host waits (the reference's sess.run)
     e2e_path = "crb_train_step_bpr per step (host int32 feeds, host loss, blocking)"
     if sharded is None:
         # the reference's epoch loop (RankingRecommender.py:39-46) as ONE call over the caller-sampled epoch arrays: every step still
@@ -285,11 +291,19 @@ def run_ours(args, w):
         e2e_s = time.perf_counter() - t0
         assert bool(torch.isfinite(host_losses).all()) and float(host_losses.min()) > 0
         e2e_path = "crb_train_epoch_bpr_feeds: the reference's epoch loop over host feed arrays, per-step H2D feed + per-step D2H loss, feeds staged one step ahead"
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * B * n_e2e / e2e_s
+    if sharded is not None:
+        # the same epoch loop on the multi-GPU path: every rank's feeds are staged one step ahead (crb_shard_step_prepare with feeds),
+        # every step's loss goes to pinned host memory with its own copy
+        host_losses = torch.zeros(n_e2e, dtype=torch.float64).pin_memory()
+        sharded.run_steps(1, reg, neg_ratio=R, seed=0, epoch=0, feeds=[feeds[n_e2e]], host_losses=host_losses[:1])  # warm
+        barrier()
+        t0 = time.perf_counter()
+        sharded.run_steps(n_e2e, reg, neg_ratio=R, seed=0, epoch=0, feeds=feeds[:n_e2e], host_losses=host_losses)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        assert bool(torch.isfinite(host_losses).all()) and float(host_losses.min()) > 0
+        e2e_path = "ShardedBPR.run_steps(feeds=...): the epoch loop over host feed arrays, per-step H2D feed + per-step D2H loss, feeds staged one step ahead"
+    e2e_value = world * B * n_e2e / max_over_ranks(e2e_s)
     overflow = sharded.inbox_overflowed() if sharded is not None else False
 
     # ---- roofline of the dominant kernel (K3 fused step) ----

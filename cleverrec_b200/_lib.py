@@ -117,7 +117,7 @@ def load():
     lib.crb_train_step_transcf.argtypes = [vp, T, T, vp, vp, O, vp, vp, vp, i64, f32, f32, f32, vp, vp]
     lib.crb_transcf_neighbourhood.argtypes = [vp, i32, vp, i32, vp, i64, vp, vp]
     lib.crb_score_pairs_transcf.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, i64, vp, vp]
-    lib.crb_shard_step_prepare.argtypes = [vp, T, u64, u32, i64, i32, i64, i64, vp]
+    lib.crb_shard_step_prepare.argtypes = [vp, T, u64, u32, i64, i32, i64, i64, vp, vp, vp, vp]
     lib.crb_shard_apply_inbox.argtypes = [vp, S, O, vp]
     lib.crb_shard_inbox_overflow.argtypes = [vp, S, C.POINTER(i32), vp]
     lib.crb_malloc.argtypes = [vp, i64, C.POINTER(vp)]

@@ -265,8 +265,12 @@ static void fill_dup(crb_handle* h, DupArgs* d, const TableDev& t0, const TableD
 // previous step, so that it overlaps that step's barriers and inbox phase (none of it touches the tables).  The next
 // crb_shard_step_compute with u == NULL and the same (seed, epoch, first, neg_ratio, batch) consumes it.  reserve_rows >= batch
 // sizes the workspace once for both phases (pass the inbox capacity) so that no later call reallocates it under the prepared step.
+// With feed_u / feed_i / feed_j (HOST or DEVICE int32 [batch]: the caller's own triplets, local user rows and global item ids) the
+// step is staged from them instead of being sampled -- the host -> device copies then run on the copy stream beside the previous
+// step's kernels; (seed, epoch, first, neg_ratio, batch) only serve as the ticket the consuming crb_shard_step_compute presents.
 extern "C" int crb_shard_step_prepare(crb_handle* h, const crb_table* P, uint64_t seed, uint32_t epoch, int64_t first, int32_t neg_ratio,
-                                      int64_t batch, int64_t reserve_rows, void* stream) {
+                                      int64_t batch, int64_t reserve_rows, const int32_t* feed_u, const int32_t* feed_i,
+                                      const int32_t* feed_j, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     CRB_CHECK_ARG(h && P, "null argument");
     CRB_CHECK_ARG(batch > 0, "batch");
@@ -282,7 +286,12 @@ extern "C" int crb_shard_step_prepare(crb_handle* h, const crb_table* P, uint64_
     crb_alt_swap(h);
     struct Restore { crb_handle* h; ~Restore() { if (h->alt_active) crb_alt_swap(h); } } restore{h};
     if ((rc = crb_zero_step_counters(h, ps))) return rc;
-    if ((rc = crb_launch_sample_pairwise(h, seed, epoch, first, batch, neg_ratio, h->idx[0], h->idx[1], h->idx[2], nullptr, false, ps))) return rc;
+    if (feed_u) {
+        CRB_CHECK_ARG(feed_i && feed_j, "null index feed");
+        const int32_t* src[3] = {feed_u, feed_i, feed_j};
+        for (int q = 0; q < 3; ++q)
+            CRB_CUDA(cudaMemcpyAsync(h->idx[q], src[q], sizeof(int32_t) * batch, crb_is_device_ptr(src[q]) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ps));
+    } else if ((rc = crb_launch_sample_pairwise(h, seed, epoch, first, batch, neg_ratio, h->idx[0], h->idx[1], h->idx[2], nullptr, false, ps))) return rc;
     const int32_t* idx[3] = {h->idx[0], nullptr, nullptr};
     const int role_table[3] = {0, 0, 0};
     if ((rc = crb_count_rows(h, batch, 1, idx, role_table, ps))) return rc;

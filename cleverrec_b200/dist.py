@@ -154,20 +154,34 @@ class ShardedBPR(object):
         self.barrier()
         return float(host[0]) if loss_out is None else None
 
-    def run_steps(self, n_steps, reg, neg_ratio, seed, epoch, first=0, batch=None, loss_out=None, bounds=None):
+    def run_steps(self, n_steps, reg, neg_ratio, seed, epoch, first=0, batch=None, loss_out=None, bounds=None, feeds=None, host_losses=None):
         """n synchronous steps over consecutive batches of this rank's epoch, sampled on the device.  Step k+1's index work
         (sampler, user-row counting and slot assignment) is prepared on the engine's auxiliary stream while step k's barriers and
         inbox phase run (crb_shard_step_prepare).  loss_out: device float64 [n_steps] or None.  bounds: optional n_steps+1 row
-        offsets (step k covers rows [bounds[k], bounds[k+1]) of this rank's epoch) instead of a fixed batch."""
+        offsets (step k covers rows [bounds[k], bounds[k+1]) of this rank's epoch) instead of a fixed batch.
+        feeds: optional list of n_steps (u_local, i_global, j_global) int32 arrays (host -- ideally pinned -- or device): the caller's
+        own triplets are staged one step ahead instead of being sampled (the reference's epoch loop over its sampler's output).
+        host_losses: optional pinned float64 CPU tensor [n_steps]: every step's loss is copied to it asynchronously as the step ends."""
         eng, lib = self.engine, self.engine.lib
         batch = self.batch if batch is None else batch
         if bounds is None:
             bounds = [first + k * batch for k in range(n_steps + 1)]
         assert len(bounds) == n_steps + 1 and all(b > a for a, b in zip(bounds[:-1], bounds[1:])), "every step needs at least one row"
 
+        if feeds is not None:
+            feeds = [tuple(eng._feed_i32(x) for x in f) for f in feeds]
+            assert len(feeds) == n_steps
+            bounds = [0]
+            for f in feeds:
+                bounds.append(bounds[-1] + len(f[0]))
+            neg_ratio = neg_ratio or 1
+        if host_losses is not None and loss_out is None:
+            loss_out = torch.zeros(n_steps, dtype=torch.float64, device=eng.device)
+
         def prepare(k):
+            f = feeds[k] if feeds is not None else (None, None, None)
             check(lib.crb_shard_step_prepare(eng.h, C.byref(self.P.c), seed, epoch, bounds[k], neg_ratio, bounds[k + 1] - bounds[k], self.inbox_cap,
-                                             eng.stream))
+                                             ptr(f[0]), ptr(f[1]), ptr(f[2]), eng.stream))
         prepare(0)
         host = np.zeros(1, dtype=np.float64)
         for k in range(n_steps):
@@ -176,6 +190,8 @@ class ShardedBPR(object):
             lo = ptr(host) if loss_out is None else ptr(loss_out[k:k + 1])
             check(lib.crb_shard_step_compute(eng.h, C.byref(self.P.c), C.byref(self.shard), C.byref(co), None, None, None, seed, epoch,
                                              bounds[k], neg_ratio, bounds[k + 1] - bounds[k], float(reg), lo, eng.stream))
+            if host_losses is not None:
+                host_losses[k:k + 1].copy_(loss_out[k:k + 1], non_blocking=True)
             if k + 1 < n_steps:
                 prepare(k + 1)
             self.barrier()

@@ -318,9 +318,13 @@ int crb_shard_step_compute(crb_handle* h, const crb_table* P, const crb_shard* s
 /* Optional phase 0 of the NEXT step: sample rows [first, first+batch) and count / assign the user rows on the handle's auxiliary
  * stream, so that this index-only work (utils/sampler.py:46-74 + the feed slicing of RankingRecommender.py:38-46) overlaps the
  * current step's barriers and inbox phase.  Consumed by the next crb_shard_step_compute with u == NULL and the same
- * (seed, epoch, first, neg_ratio, batch).  reserve_rows >= batch sizes the workspace once for both phases (the inbox capacity). */
+ * (seed, epoch, first, neg_ratio, batch).  reserve_rows >= batch sizes the workspace once for both phases (the inbox capacity).
+ * feed_u / feed_i / feed_j (HOST or DEVICE int32 [batch], or all NULL): stage the caller's own triplets (the reference's sampler
+ * output sliced as RankingRecommender.py:40-42; local user rows, global item ids) instead of sampling -- the copies then overlap
+ * the current step; the five scalars only serve as the ticket the consuming crb_shard_step_compute presents. */
 int crb_shard_step_prepare(crb_handle* h, const crb_table* P, uint64_t seed, uint32_t epoch, int64_t first, int32_t neg_ratio,
-                           int64_t batch, int64_t reserve_rows, void* stream);
+                           int64_t batch, int64_t reserve_rows, const int32_t* feed_u, const int32_t* feed_i, const int32_t* feed_j,
+                           void* stream);
 /* phase 2: de-duplicate this rank's inbox, one optimizer apply per unique item row with the gradient summed over all ranks. */
 int crb_shard_apply_inbox(crb_handle* h, const crb_shard* shard, const crb_opt* opt, void* stream);
 int crb_shard_inbox_overflow(crb_handle* h, const crb_shard* shard, int32_t* overflowed, void* stream);

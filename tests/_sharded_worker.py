@@ -28,6 +28,7 @@ def main():
         if rank == 0:
             ref = (Table(P0.clone().cuda(), kind, mode), Table(Q0.clone().cuda(), kind, mode), Optimizer(kind, m.opt.lr, adam_mode=mode))
         rs = np.random.RandomState(5)
+        my_feeds, my_losses = [], []
         for step in range(4):
             feeds = []
             for r in range(world):  # every rank draws all feeds so rank 0 can build the union batch
@@ -36,6 +37,7 @@ def main():
                 feeds.append((rs.randint(l, h_, n), rs.randint(0, I, n), rs.randint(0, I, n)))
             u, i, j = feeds[rank]
             loss = m.step(0.01, feed=(u - lo, i, j))
+            my_feeds.append((u - lo, i, j)); my_losses.append(loss)
             t = torch.tensor([loss], device="cuda", dtype=torch.float64)
             dist.all_reduce(t)
             if rank == 0:
@@ -60,6 +62,18 @@ def main():
                 if bad.float().mean() > 1e-3:
                     print("TABLE MISMATCH", kind, mode, name, int(bad.sum()), float((got - want).abs().max()))
                     ok = False
+        # the same feeds through run_steps(feeds=...) -- staged one step ahead on the copy stream, losses to pinned host memory --
+        # must give this rank's step-by-step losses and tables bit for bit
+        m2 = ShardedBPR(eng, U, I, d, kind, 0.05 if kind != "Adam" else 0.01, mode, B, init_P=P0[lo:hi], init_Q=Q0)
+        hl = torch.zeros(4, dtype=torch.float64).pin_memory()
+        pinned = [tuple(torch.from_numpy(np.ascontiguousarray(x, dtype=np.int32)).pin_memory() for x in f) for f in my_feeds]
+        m2.run_steps(4, 0.01, neg_ratio=1, seed=0, epoch=0, feeds=pinned, host_losses=hl)
+        torch.cuda.synchronize()
+        m2.flush()
+        if hl.tolist() != my_losses or not torch.equal(m2.P.w, m.P.w) or not torch.equal(m2.q["w"].tensor, m.q["w"].tensor):
+            print("FEED PIPELINE MISMATCH", kind, mode, hl.tolist(), my_losses)
+            ok = False
+        m2.close()
         m.close()
     # ---- evaluation across the item shards: per-shard exact top-K merged at the owner == single-GPU top-K on the gathered tables
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
