@@ -316,9 +316,10 @@ def run_ours(args, w):
                 "algorithmic_bytes_per_launch": per_triplet * B, "kernel_ms": k3_avg_ms, "kernel_share_of_step": k3_avg_ms / ms_step,
                 "step_frac": per_triplet * B / (ms_step / 1000.0) / 1e9 / hbm}
     if world > 1 and k3_n:
-        # per triplet two item rows are fetched and two gradients returned, (N-1)/N of them over NVLink: 8*d bytes per
+        # per triplet two item rows are fetched and two gradients returned, (N-1)/N of them over NVLink.  Every GPU's
+        # ingress carries the rows it fetches plus the gradients its peers send it (and its egress the mirror image): 16*d bytes per
         # direction per triplet.  Peak: NVLink 5, 900 GB/s per direction per GPU (raw link rate; not measured on this pool).
-        nv_bytes = 8 * dim * B * (world - 1) / world
+        nv_bytes = 16 * dim * B * (world - 1) / world
         nv_rate = nv_bytes / (k3_avg_ms / 1000.0) / 1e9
         roofline["nvlink"] = {"bytes_per_direction_per_launch": nv_bytes, "achieved": nv_rate, "peak": 900.0, "unit": "GB/s per direction per GPU",
                               "frac": nv_rate / 900.0, "note": "the multi-GPU step kernel is bound by NVLink, not by HBM: read `frac` above as HBM headroom"}
