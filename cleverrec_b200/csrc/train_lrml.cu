@@ -28,8 +28,8 @@ static int lrml_shape(int d, int mem, LrmlShape* s) {
     s->d = d; s->mem = mem;
     s->ks = mem | 1; s->ms = d | 1;
     s->n_dense = 2 * d * mem;
-    // p, q_i, q_j, e_i, e_j, tmp  [d] each;  a_i, a_j, tmp [mem] each
-    s->per_warp = 6 * d + 3 * mem;
+    // p, q_i, q_j, e_i, e_j  [d] each;  a_i, a_j, tmp [mem] each
+    s->per_warp = 5 * d + 3 * mem;
     return 0;
 }
 
@@ -153,8 +153,7 @@ __global__ void __launch_bounds__(LR_WARPS * 32) lrml_step_kernel(LrmlArgs A) {
     float* vqj = vqi + S.d;
     float* ei = vqj + S.d;
     float* ej = ei + S.d;
-    float* td = ej + S.d;        // unused d-vector kept for alignment of the mem vectors
-    float* ai = td + S.d;
+    float* ai = ej + S.d;
     float* aj = ai + S.mem;
     float* tm = aj + S.mem;
     for (int t = threadIdx.x; t < S.d * S.mem; t += blockDim.x) {
