@@ -74,7 +74,10 @@ def main():
     import importlib
     log = logging.getLogger('bench_models')
     out, cache = [], {}
+    only = set(sys.argv[1:])
     for name, shape, conf in MODELS:
+        if only and name not in only:
+            continue
         key = (shape['users'], name == 'SBPR')
         if key not in cache:
             cache[key] = make_data(shape, 1, friends=name == 'SBPR')
@@ -109,6 +112,8 @@ def main():
     # the reference's CPU path for the headline model at this shape: Python sampler + restated TF-1 step, bounded sample
     from oracle import ref_host as H
     from oracle import tf1_restatement as T
+    if (ML1M['users'], False) not in cache:
+        cache[(ML1M['users'], False)] = make_data(ML1M, 1)
     data = cache[(ML1M['users'], False)]
     sub = Data(data.user_nums, data.item_nums, {u: data.ui_train[u] for u in list(data.ui_train)[:400]}, {})
     np.random.seed(0)
