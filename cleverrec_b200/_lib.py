@@ -25,7 +25,7 @@ EXPORTS = [
     "crb_sample_nais", "crb_train_step_nais", "crb_train_epoch_nais", "crb_score_nais",
     "crb_shard_step_compute", "crb_shard_step_prepare", "crb_shard_apply_inbox", "crb_shard_inbox_overflow", "crb_malloc", "crb_free", "crb_ipc_export",
     "crb_ipc_open", "crb_ipc_close", "crb_build_history", "crb_set_item_lists", "crb_train_step_transcf", "crb_transcf_neighbourhood", "crb_score_pairs_transcf", "crb_np_seed", "crb_np_set_state", "crb_np_get_state", "crb_sample_epoch_numpy",
-    "crb_train_step_lrml", "crb_score_pairs_lrml", "crb_set_social", "crb_sample_sbpr", "crb_train_step_sbpr", "crb_train_epoch_bpr_feeds",
+    "crb_train_step_lrml", "crb_score_pairs_lrml", "crb_set_social", "crb_sample_sbpr", "crb_train_step_sbpr", "crb_train_epoch_bpr_feeds", "crb_train_epoch_pointwise",
 ]
 
 
@@ -84,6 +84,8 @@ def load():
     lib.crb_train_epoch_bpr_feeds.argtypes = [vp, C.POINTER(CrbTable), C.POINTER(CrbTable), C.POINTER(CrbOpt), vp, vp, vp, i64, i64, f32, vp, vp]
     lib.crb_train_step_pointwise.argtypes = [vp, i32, C.POINTER(CrbTable), C.POINTER(CrbTable), vp, vp, vp, C.POINTER(CrbOpt), i32,
                                              vp, vp, vp, i64, f32, vp, vp]
+    lib.crb_train_epoch_pointwise.argtypes = [vp, i32, C.POINTER(CrbTable), C.POINTER(CrbTable), vp, vp, vp, C.POINTER(CrbOpt), i32, u64, u32, i64, i64, i64,
+                                              i32, f32, vp, vp]
     lib.crb_adam_flush.argtypes = [vp, C.POINTER(CrbTable), C.POINTER(CrbOpt), vp]
     lib.crb_score_pairs.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, i64, vp, vp]
     lib.crb_topk_segments.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]

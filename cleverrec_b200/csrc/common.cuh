@@ -229,5 +229,7 @@ int crb_eval_ws_reserve(crb_handle* h, int64_t bytes);
 int crb_alt_reserve(crb_handle* h, cudaStream_t s);   // allocate / resize the alternate step state to match the primary
 void crb_alt_swap(crb_handle* h);
 int crb_lrt_prepare(crb_handle* h, const crb_opt* opt, cudaStream_t s);
+int crb_launch_sample_pointwise(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t first, int64_t count, int32_t neg_ratio, int32_t* u,
+                                int32_t* i, float* y, bool count_rows, cudaStream_t s);
 int crb_launch_sample_pairwise(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t first, int64_t count, int32_t neg_ratio,
                                int32_t* u, int32_t* i, int32_t* j, int32_t* nbr, bool count_rows, cudaStream_t s);

@@ -267,6 +267,25 @@ extern "C" int crb_sample_pairwise(crb_handle* h, uint64_t seed, uint32_t epoch,
     return sampler_epilogue(h, s);
 }
 
+// pointwise rows [first, first+count) into (u, i, y); count_rows also bumps the per-row multiplicities (K1 of a fused epoch loop)
+int crb_launch_sample_pointwise(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t first, int64_t count, int32_t neg_ratio, int32_t* u,
+                                int32_t* i, float* y, bool count_rows, cudaStream_t s) {
+    SamplerArgs a;
+    int rc = make_args(h, seed, epoch, neg_ratio, 1, &a);
+    if (rc) return rc;
+    CRB_CHECK_ARG(first >= 0 && count >= 0 && (uint64_t)(first + count) <= a.n_rows, "rows outside the epoch");
+    if (count == 0) return CRB_OK;
+    if (count_rows)
+        sample_kernel<1, true><<<sampler_grid(h, count), 256, 0, s>>>(a, first, count, u, i, nullptr, y, nullptr, h->meta[0], h->meta[1], h->rank[0],
+                                                                      h->rank[1], nullptr, h->ctr);
+    else
+        sample_kernel<1, false><<<sampler_grid(h, count), 256, 0, s>>>(a, first, count, u, i, nullptr, y, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                                       nullptr, h->ctr);
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}
+
 extern "C" int crb_sample_pointwise(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t first, int64_t count,
                                     int32_t neg_ratio, int32_t* u, int32_t* i, float* y, int32_t* nbr, void* stream) {
     CRB_CHECK_ARG(h, "null handle");

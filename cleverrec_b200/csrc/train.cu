@@ -1067,22 +1067,16 @@ static int launch_pw_t(crb_handle* h, const PwArgs& a, int opt_kind, bool gmf, c
     return CRB_OK;
 }
 
-extern "C" int crb_train_step_pointwise(crb_handle* h, int32_t kind, const crb_table* P, const crb_table* Q, float* hvec, float* h_s1,
-                                        float* h_s2, const crb_opt* opt, int32_t loss_kind, const int32_t* u, const int32_t* i,
-                                        const float* y, int64_t batch, float reg, double* loss_out, void* stream) {
-    cudaStream_t s = (cudaStream_t)stream;
-    OptDev od;
-    int opt_kind = 0;
-    int rc = bpr_common_checks(h, P, Q, opt, &od, &opt_kind, batch, 1, s);
+static int pointwise_checks(crb_handle* h, int32_t kind, const crb_table* P, const crb_table* Q, float* hvec, float* h_s1, float* h_s2,
+                            const crb_opt* opt, int32_t loss_kind, int64_t batch, int64_t steps, OptDev* od, int* opt_kind, cudaStream_t s) {
+    int rc = bpr_common_checks(h, P, Q, opt, od, opt_kind, batch, steps, s);
     if (rc) return rc;
-    CRB_CHECK_ARG(u && i && y, "null feed");
     CRB_CHECK_ARG(kind == CRB_SCORE_DOT || kind == CRB_SCORE_GMF, "kind must be CRB_SCORE_DOT (MF) or CRB_SCORE_GMF");
     CRB_CHECK_ARG(loss_kind == CRB_LOSS_CROSS_ENTROPY || loss_kind == CRB_LOSS_SQUARE, "pointwise loss must be cross_entropy or square");
-    const bool gmf = kind == CRB_SCORE_GMF;
-    if (gmf) {
+    if (kind == CRB_SCORE_GMF) {
         CRB_CHECK_ARG(hvec && crb_is_device_ptr(hvec), "GMF needs the device vector h");
-        CRB_CHECK_ARG(opt_kind == OPT_SGD || h_s1, "h optimizer slot s1 is NULL");
-        CRB_CHECK_ARG((opt_kind != OPT_ADAM_LAZY && opt_kind != OPT_ADAM_TF1) || h_s2, "h optimizer slot s2 is NULL");
+        CRB_CHECK_ARG(*opt_kind == OPT_SGD || h_s1, "h optimizer slot s1 is NULL");
+        CRB_CHECK_ARG((*opt_kind != OPT_ADAM_LAZY && *opt_kind != OPT_ADAM_TF1) || h_s2, "h optimizer slot s2 is NULL");
         const int64_t need = (int64_t)h->loss_blocks * P->dim;
         if (need > h->cap_dense) {
             CRB_CUDA(cudaStreamSynchronize(s));
@@ -1092,18 +1086,17 @@ extern "C" int crb_train_step_pointwise(crb_handle* h, int32_t kind, const crb_t
             h->cap_dense = need;
         }
     }
-    const int32_t *du, *di;
-    if ((rc = stage_i32(h, u, 0, batch, &du, s))) return rc;
-    if ((rc = stage_i32(h, i, 1, batch, &di, s))) return rc;
-    const float* dy = y;
-    if (!crb_is_device_ptr(y)) {
-        CRB_CUDA(cudaMemcpyAsync(h->yv, y, sizeof(float) * batch, cudaMemcpyHostToDevice, s));
-        dy = h->yv;
-    }
-    if ((rc = crb_zero_step_counters(h, s))) return rc;
+    return CRB_OK;
+}
+
+// K2 .. K5 of one pointwise step; `counted`: the sampler already bumped the multiplicities (K1)
+static int pointwise_step_device(crb_handle* h, bool gmf, const crb_table* P, const crb_table* Q, float* hvec, float* h_s1, float* h_s2,
+                                 const OptDev& od, int opt_kind, int32_t loss_kind, const int32_t* du, const int32_t* di, const float* dy,
+                                 int64_t batch, float reg, bool counted, double* loss_dev, cudaStream_t s) {
+    int rc;
     const int32_t* idx[3] = {du, di, nullptr};
     const int role_table[3] = {0, 1, 0};
-    if ((rc = crb_count_rows(h, batch, 2, idx, role_table, s))) return rc;
+    if (!counted && (rc = crb_count_rows(h, batch, 2, idx, role_table, s))) return rc;
     if ((rc = crb_launch_assign(h, batch, 2, idx, role_table, s))) return rc;
     PwArgs a;
     a.P = crb_to_dev(P); a.Q = crb_to_dev(Q);
@@ -1129,7 +1122,72 @@ extern "C" int crb_train_step_pointwise(crb_handle* h, int32_t kind, const crb_t
         h->launches++;
         CRB_CUDA(cudaGetLastError());
     }
+    return crb_launch_loss_final(h, loss_dev, s);
+}
+
+extern "C" int crb_train_step_pointwise(crb_handle* h, int32_t kind, const crb_table* P, const crb_table* Q, float* hvec, float* h_s1,
+                                        float* h_s2, const crb_opt* opt, int32_t loss_kind, const int32_t* u, const int32_t* i,
+                                        const float* y, int64_t batch, float reg, double* loss_out, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    OptDev od;
+    int opt_kind = 0;
+    int rc = pointwise_checks(h, kind, P, Q, hvec, h_s1, h_s2, opt, loss_kind, batch, 1, &od, &opt_kind, s);
+    if (rc) return rc;
+    CRB_CHECK_ARG(u && i && y, "null feed");
+    const int32_t *du, *di;
+    if ((rc = stage_i32(h, u, 0, batch, &du, s))) return rc;
+    if ((rc = stage_i32(h, i, 1, batch, &di, s))) return rc;
+    const float* dy = y;
+    if (!crb_is_device_ptr(y)) {
+        CRB_CUDA(cudaMemcpyAsync(h->yv, y, sizeof(float) * batch, cudaMemcpyHostToDevice, s));
+        dy = h->yv;
+    }
+    if ((rc = crb_zero_step_counters(h, s))) return rc;
     double* ld = (loss_out && crb_is_device_ptr(loss_out)) ? loss_out : h->loss_dev;
-    if ((rc = crb_launch_loss_final(h, ld, s))) return rc;
+    if ((rc = pointwise_step_device(h, kind == CRB_SCORE_GMF, P, Q, hvec, h_s1, h_s2, od, opt_kind, loss_kind, du, di, dy, batch, reg, false, ld, s)))
+        return rc;
     return finish_loss(h, loss_out, 1, s);
+}
+
+// RankingRecommender.train_model's pointwise loop (:48-60) with the sampler fused in: n_steps iterations in one call, step k trains on
+// epoch rows [first + k*batch, min(first + (k+1)*batch, epoch_rows)) of pointwise_ranking_sampler's epoch (utils/sampler.py:10-43).
+// One stream, no host round trips: at the batch sizes the reference ships (6144) a step is a handful of microsecond kernels and the
+// per-call host cost of stepping from Python was twice the device time.
+extern "C" int crb_train_epoch_pointwise(crb_handle* h, int32_t kind, const crb_table* P, const crb_table* Q, float* hvec, float* h_s1,
+                                         float* h_s2, const crb_opt* opt, int32_t loss_kind, uint64_t seed, uint32_t epoch, int64_t first,
+                                         int64_t batch, int64_t n_steps, int32_t neg_ratio, float reg, double* loss_out, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    OptDev od;
+    int opt_kind = 0;
+    CRB_CHECK_ARG(n_steps >= 1, "n_steps");
+    int rc = pointwise_checks(h, kind, P, Q, hvec, h_s1, h_s2, opt, loss_kind, batch, n_steps, &od, &opt_kind, s);
+    if (rc) return rc;
+    const int64_t rows = crb_epoch_rows(h, neg_ratio, 1);
+    CRB_CHECK_ARG(first >= 0 && first < rows, "first row outside the epoch");
+    const bool host_loss = !(loss_out && crb_is_device_ptr(loss_out));
+    crb_opt step_opt = *opt;
+    for (int64_t k = 0; k < n_steps; ++k) {
+        const int64_t lo = first + k * batch;
+        if (lo >= rows) { crb_set_error("step %lld starts past the end of the epoch", (long long)k); return CRB_ERR_ARG; }
+        const int64_t b = (rows - lo) < batch ? (rows - lo) : batch;
+        step_opt.step = opt->step + k;
+        if ((rc = crb_opt_to_dev(h, &step_opt, &od, &opt_kind, s))) return rc;
+        if ((rc = crb_zero_step_counters(h, s))) return rc;
+        if ((rc = crb_launch_sample_pointwise(h, seed, epoch, lo, b, neg_ratio, h->idx[0], h->idx[1], h->yv, true, s))) return rc;
+        double* ld = host_loss ? h->loss_dev + k : loss_out + k;
+        if ((rc = pointwise_step_device(h, kind == CRB_SCORE_GMF, P, Q, hvec, h_s1, h_s2, od, opt_kind, loss_kind, h->idx[0], h->idx[1], h->yv, b, reg,
+                                        true, ld, s)))
+            return rc;
+    }
+    if (loss_out && host_loss) {
+        if ((rc = finish_loss(h, loss_out, n_steps, s))) return rc;
+        unsigned int err = 0;
+        CRB_CUDA(cudaMemcpy(&err, &h->ctr->sampler_err, sizeof(err), cudaMemcpyDeviceToHost));
+        if (err) {
+            CRB_CUDA(cudaMemset(&h->ctr->sampler_err, 0, sizeof(err)));
+            crb_set_error("sampler: %u rows found no admissible negative", err);
+            return CRB_ERR_SAMPLER;
+        }
+    }
+    return CRB_OK;
 }

@@ -252,6 +252,14 @@ class Engine(object):
                                                  ptr(loss_out), self.stream))
         opt.t += n_steps
 
+    def train_epoch_pointwise(self, kind, P, Q, opt, seed, epoch, first, batch, n_steps, neg_ratio, reg, loss_kind, hvec=None, h_s1=None,
+                              h_s2=None, loss_out=None):
+        """n_steps fused sample+train steps of MF / GMF; loss_out: double tensor [n_steps] on the device (no sync) or NumPy (sync)."""
+        co = opt.c(opt.t + 1)
+        check(self.lib.crb_train_epoch_pointwise(self.h, kind, C.byref(P.c), C.byref(Q.c), ptr(hvec), ptr(h_s1), ptr(h_s2), C.byref(co), loss_kind,
+                                                 seed, epoch, first, batch, n_steps, neg_ratio, float(reg), ptr(loss_out), self.stream))
+        opt.t += n_steps
+
     def train_step_pointwise(self, kind, P, Q, opt, u, i, y, reg, loss_kind, hvec=None, h_s1=None, h_s2=None, loss_out=None):
         """One `sess.run([train, loss], {u_idx, i_idx, y})` of MF (kind SCORE_DOT) / GMF (kind SCORE_GMF, hvec = h_gmf and
         its optimizer slots, device tensors).  Host or device feeds; returns the loss when loss_out is None."""

@@ -53,11 +53,9 @@ class GMF(_rr.RankingRecommender):
                                                 _LOSS[self.loss_func], self.h_gmf, self.h_s1, self.h_s2, loss_out=loss_out)
 
     def _train_epoch_pointwise(self, epoch, n_rows, n_batches, losses):
-        for k in range(n_batches):
-            lo = k * self.batch_size
-            cnt = min(self.batch_size, n_rows - lo)
-            u, i, y = self.engine.sample_pointwise(self.seed, epoch, lo, cnt, self.neg_ratio)
-            self.train_step(u, i, y, loss_out=losses[k:k + 1])
+        # the whole loop of RankingRecommender.py:48-60 in one call (sampler fused in, no host round trip per batch)
+        self.engine.train_epoch_pointwise(self.score_kind, self.P, self.Q, self.optimizer, self.seed, epoch, 0, self.batch_size, n_batches,
+                                          self.neg_ratio, self.reg, _LOSS[self.loss_func], self.h_gmf, self.h_s1, self.h_s2, loss_out=losses)
 
     def _before_eval(self):
         self.engine.adam_flush(self.P, self.optimizer)

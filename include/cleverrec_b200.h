@@ -187,6 +187,13 @@ int crb_train_step_pointwise(crb_handle* h, int32_t kind, const crb_table* P, co
                              const int32_t* u, const int32_t* i, const float* y, int64_t batch,
                              float reg, double* loss_out, void* stream);
 
+/* RankingRecommender.train_model's pointwise loop (:48-60) with the sampler fused in, `n_steps` iterations per call: step k trains on
+ * rows [first + k*batch, min(first + (k+1)*batch, epoch_rows)) of pointwise_ranking_sampler's epoch (utils/sampler.py:10-43).
+ * loss_out[k] (DEVICE or HOST double [n_steps]); opt->step is the index of the first step. */
+int crb_train_epoch_pointwise(crb_handle* h, int32_t kind, const crb_table* P, const crb_table* Q, float* hvec, float* h_s1,
+                              float* h_s2, const crb_opt* opt, int32_t loss_kind, uint64_t seed, uint32_t epoch, int64_t first,
+                              int64_t batch, int64_t n_steps, int32_t neg_ratio, float reg, double* loss_out, void* stream);
+
 /* sess.run([train, loss], {u_idx, i_idx, neg_items}) for model/ranking/CML.py:39-70 (train_model_cml,
  * RankingRecommender.py:90-100).  The covariance regulariser makes both table gradients dense in the reference, so TF
  * applies the DENSE optimizer form to every row: gradP/gradQ are caller-owned zeroed [rows, dim] device buffers (left zeroed).
