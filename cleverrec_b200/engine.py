@@ -485,11 +485,13 @@ class Engine(object):
         check(self.lib.crb_sample_nais(self.h, seed, epoch, pos_first, n_pos_user, neg_ratio, ptr(tg), ptr(y), self.stream))
         return tg, y
 
-    def score_nais(self, P, Q, bias, dense, atten_size, hist, targets, beta):
+    def score_nais(self, P, Q, bias, dense, atten_size, hist, targets, beta, out=None):
+        """out: optional contiguous float32 device tensor [len(targets)] to write into (e.g. a slice of a larger buffer)."""
         dev = self.device
         hist = torch.as_tensor(np.asarray(hist), dtype=torch.int32).to(dev) if not isinstance(hist, torch.Tensor) else hist.to(torch.int32)
         targets = torch.as_tensor(np.asarray(targets), dtype=torch.int32).to(dev) if not isinstance(targets, torch.Tensor) else targets.to(torch.int32)
-        out = torch.empty(targets.numel(), dtype=torch.float32, device=dev)
+        if out is None:
+            out = torch.empty(targets.numel(), dtype=torch.float32, device=dev)
         check(self.lib.crb_score_nais(self.h, ptr(P), ptr(Q), ptr(bias), ptr(dense), P.shape[1], atten_size, ptr(hist), hist.numel(), ptr(targets),
                                       targets.numel(), float(beta), ptr(out), self.stream))
         return out

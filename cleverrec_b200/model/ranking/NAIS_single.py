@@ -92,11 +92,34 @@ class NAIS_single(_rr.RankingRecommender):
         hist = self.data.ui_train[u] if u in self.data.ui_train else [self.data.item_nums]
         return self.engine.score_nais(self.P.w, self.Q.w, self.bias, self.dense, self.atten_size, hist, targets, self.beta).cpu().numpy()
 
+    def _device_history(self, u):
+        """The user's interaction list as a view of the engine's device copy of data.ui_train (no host -> device copy per user)."""
+        k = self._train_pos.get(u)
+        if k is None:
+            return self._no_history
+        a = int(self._list_start[k])
+        return self.engine._hist[1][a:a + int(self._list_len[k])]
+
+    def _eval_setup(self):
+        if getattr(self, '_train_pos', None) is None:
+            self._train_pos = {u: k for k, u in enumerate(self._train_users)}
+            self._no_history = torch.tensor([self.data.item_nums], dtype=torch.int32, device=self.engine.device)
+        return self.bias   # one contiguous copy of the (padded) bias vector per evaluation
+
     def test_model_loo_nais(self):  # RankingRecommender.py:330-348
+        """One scoring call per user like the reference's one sess.run per user, but every call reads the history and the candidates
+        from device memory and writes into one score buffer; the host sees the scores once, then ranks per user as the reference does."""
         HR, MRR, NDCG = defaultdict(list), defaultdict(list), defaultdict(list)
-        for u in self.test_users:
-            i_idx = self.data.ui_test[u]
-            pre_scores = self._scores(u, i_idx)
+        bias = self._eval_setup()
+        offsets, u_dev, i_dev, i_host = self._loo_feed()
+        scores_dev = torch.empty(int(offsets[-1]), dtype=torch.float32, device=self.engine.device)
+        for k, u in enumerate(self.test_users):
+            a, b = int(offsets[k]), int(offsets[k + 1])
+            self.engine.score_nais(self.P.w, self.Q.w, bias, self.dense, self.atten_size, self._device_history(u), i_dev[a:b], self.beta,
+                                   out=scores_dev[a:b])
+        scores = scores_dev.cpu().numpy()
+        for k, u in enumerate(self.test_users):
+            pre_scores = scores[offsets[k]:offsets[k + 1]]
             args_u = np.argsort(-pre_scores, kind='stable')[:self.topk[-1]]
             real_items = self.data.ui_test[u][self.neg_samples:]
             for kid in range(len(self.topk)):
@@ -106,20 +129,27 @@ class NAIS_single(_rr.RankingRecommender):
         return HR, MRR, NDCG
 
     def test_model_rs_nais(self):  # RankingRecommender.py:301-328
+        """All-item scores per user (id = item_nums, which the reference scores and then drops, is not scored), seen items masked,
+        first topk[-1] by (score descending, id ascending) -- np.argsort(-scores, kind='stable') followed by the reference's skip loop --
+        taken on the device for a block of users at a time."""
+        from ...utils.metrics import batch_ranking_metrics
         HR, MRR, NDCG = defaultdict(list), defaultdict(list), defaultdict(list)
-        all_items = torch.arange(self.data.item_nums, dtype=torch.int32, device=self.engine.device)
-        for u in self.test_users:
-            seen_items = set(self.data.ui_train[u]) if u in self.data.ui_train else set()
-            pre_scores = self._scores(u, all_items)  # the reference scores id=item_nums too and drops it
-            args_u = np.argsort(-pre_scores, kind='stable')
-            topk_items = np.zeros(self.topk[-1])
-            count, j = 0, 0
-            while count < self.topk[-1]:
-                if args_u[j] not in seen_items:
-                    topk_items[count] = args_u[j]
-                    count += 1
-                j += 1
+        bias = self._eval_setup()
+        K, I, dev = self.topk[-1], self.data.item_nums, self.engine.device
+        all_items = torch.arange(I, dtype=torch.int32, device=dev)
+        block = max(1, min(self.batch_size_t, (1 << 26) // max(1, I)))
+        for a in range(0, len(self.test_users), block):
+            cur = self.test_users[a:a + block]
+            scores = torch.empty((len(cur), I), dtype=torch.float32, device=dev)
+            for k, u in enumerate(cur):
+                self.engine.score_nais(self.P.w, self.Q.w, bias, self.dense, self.atten_size, self._device_history(u), all_items, self.beta,
+                                       out=scores[k])
+            users = torch.as_tensor(np.asarray(cur), dtype=torch.int32, device=dev)
+            scores = self.engine.mask_seen(scores, users)
+            seg = torch.arange(len(cur) + 1, dtype=torch.int64, device=dev) * I
+            topk_items = self.engine.topk_segments(scores.reshape(-1), seg, K).cpu().numpy()
+            real_lists = [self.data.ui_test[u] for u in cur]
             for kid in range(len(self.topk)):
-                hr_u, mrr_u, ndcg_u = cal_ranking_metrics(self.data.ui_test[u], topk_items[:self.topk[kid]], self.topk[kid])
-                HR[kid].append(hr_u); MRR[kid].append(mrr_u); NDCG[kid].append(ndcg_u)
+                hr, mrr, ndcg = batch_ranking_metrics(real_lists, topk_items, self.topk[kid])
+                HR[kid].extend(hr.tolist()); MRR[kid].extend(mrr.tolist()); NDCG[kid].extend(ndcg.tolist())
         return HR, MRR, NDCG

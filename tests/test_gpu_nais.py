@@ -74,3 +74,40 @@ def test_nais_sampler_matches_twin(eng):
         assert np.array_equal(tg.cpu().numpy(), want)
         assert np.array_equal(y.cpu().numpy(), np.tile(np.asarray([1.0] + [0.0] * R, dtype=np.float32), n))
         first += n
+
+
+def test_nais_model_evaluation_equals_the_reference_loops():
+    """test_model_loo_nais / test_model_rs_nais (scores written into one device buffer from device-resident histories and candidates,
+    ranking on the host / device) against the reference's loops (RankingRecommender.py:301-348, restated in oracle/ref_host.py) fed
+    with per-user scores obtained the plain way (host lists in, host scores out)."""
+    import logging
+    from conftest import synthetic_data
+    from oracle import ref_host as H
+    from cleverrec_b200.model.ranking.NAIS_single import NAIS_single
+    cfg = {'model_type': 'ranking', 'saved_dir': './saved_model', 'data.split_way': 'loo', 'test.neg_samples': '49', 'test.batch_size': '64',
+           'test.interval': '1', 'topk': '[5,10]', 'epoches': '1', 'batch_size': '512', 'lr': '0.01', 'neg_ratio': '2', 'optimizer': 'Adagrad',
+           'init_method': 'xavier_uniform', 'stddev': '0.05', 'seed': '3', 'recommender': 'NAIS_single', 'embed_size': '32', 'atten_size': '16',
+           'atten_type': "'prod'", 'beta': '0.5', 'reg': '1e-3', 'nais_like': 'True', 'is_pairwise': 'False', 'loss_func': 'cross_entropy'}
+    data = synthetic_data(120, 300, 12, seed=11, test_per_user=1)
+    rs = np.random.RandomState(0)
+    for u in data.ui_test:
+        cand = np.setdiff1d(np.arange(data.item_nums), data.ui_train[u])
+        data.ui_test[u] = rs.choice(cand, 49, replace=False).tolist() + data.ui_test[u]
+    data.ui_test[7] = rs.choice(300, 49, replace=False).tolist() + [5]        # a test user without training history (u % 11 == 7)
+    m = NAIS_single(None, data, cfg, logging.getLogger('test'))
+    m.build_model()
+    m.train_model()
+    HR, MRR, NDCG = m.test_model_loo()
+    scores = {u: m._scores(u, data.ui_test[u]) for u in m.test_users}
+    oHR, oMRR, oNDCG = H.eval_loo(m.test_users, data.ui_test, scores, 49, m.topk)
+    for k in range(len(m.topk)):
+        assert HR[k] == oHR[k] and MRR[k] == oMRR[k] and NDCG[k] == oNDCG[k]
+    data2 = synthetic_data(120, 300, 12, seed=11, test_per_user=2)
+    m2 = NAIS_single(None, data2, dict(cfg, **{'data.split_way': 'rs', 'test.neg_samples': '0'}), logging.getLogger('test'))
+    m2.build_model()
+    m2.train_model()
+    HR, MRR, NDCG = m2.test_model_rs()
+    rows = np.stack([m2._scores(u, np.arange(data2.item_nums)) for u in m2.test_users])
+    oHR, oMRR, oNDCG = H.eval_rs(m2.test_users, data2.ui_train, data2.ui_test, rows, m2.topk)
+    for k in range(len(m2.topk)):
+        assert HR[k] == oHR[k] and NDCG[k] == oNDCG[k]
