@@ -360,6 +360,37 @@ def run_ours(args, w):
         except Exception as e:  # reported, never hidden
             ev = {"error": str(e)}
 
+    # ---- secondary metric: sampled-candidate evaluation (test_model_loo with 1000 negatives, SURVEY 8(d) "Eval loo") ----
+    ev_loo = None
+    if args.eval_users > 0 and sharded is None and ev is not None and "error" not in ev:
+        try:
+            n_loo, n_cand = min(65536, args.eval_users, u_hi - u_lo), 1001
+            g2 = torch.Generator(device=dev).manual_seed(99)
+            lu = torch.arange(n_loo, device=dev, dtype=torch.int32).repeat_interleave(n_cand)
+            li = torch.randint(0, items, (n_loo * n_cand,), device=dev, generator=g2, dtype=torch.int32)
+            seg = torch.arange(n_loo + 1, device=dev, dtype=torch.int64) * n_cand
+            out = torch.empty(n_loo * n_cand, dtype=torch.float32, device=dev)
+
+            def loo_once():
+                eng.score_pairs(0, P.w, Q.w, lu, li, out=out)          # pre_scores of every (user, candidate) pair
+                return eng.topk_segments(out, seg, 20)                  # np.argsort(-scores_u)[:20] per user
+            loo_once()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            loo_once()
+            e1.record()
+            barrier()
+            lms = e0.elapsed_time(e1)
+            lbytes = float(n_loo) * n_cand * 4 * dim                    # (1 + neg_samples) * 4 * d bytes per user: the gathered item rows
+            ev_loo = {"metric": "loo_1000neg_top20_eval_users_per_sec", "value": n_loo / (lms / 1000.0), "unit": "users/s", "users": n_loo,
+                      "candidates_per_user": n_cand, "ms": lms,
+                      "roofline": {"bound": "hbm", "achieved": lbytes / (lms / 1000.0) / 1e9, "peak": hbm, "unit": "GB/s",
+                                   "frac": lbytes / (lms / 1000.0) / 1e9 / hbm, "algorithmic_bytes": lbytes}}
+            del lu, li, out
+        except Exception as e:
+            ev_loo = {"error": str(e)}
+
     if args.eval_users > 0 and sharded is not None:
         from cleverrec_b200.dist import ShardedEval
         try:
@@ -404,7 +435,7 @@ def run_ours(args, w):
                            "setup_s": round(t_setup, 1)},
                 "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 8, "steps": n_e2e, "path": e2e_path,
                         "blocking_per_step_value": e2e_sync},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "eval": ev, "final_loss": loss_last}
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "eval": ev, "eval_loo": ev_loo, "final_loss": loss_last}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

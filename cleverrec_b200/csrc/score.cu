@@ -4,6 +4,9 @@
 //   score_pairs_kernel      sess.run(pre_scores, {u_idx, i_idx})        test_model_loo :257-278
 //   topk_segments_kernel    np.argsort(-scores_u)[:K] per user           test_model_loo :281-288
 //   fullrank_exact_kernel   matmul + argsort + seen filter + first K     test_model_rs  :203-240
+#include <cuda_pipeline.h>
+#include <stdlib.h>
+
 #include "score_common.cuh"
 
 template <int KIND>
@@ -15,6 +18,88 @@ __global__ void __launch_bounds__(256) score_pairs_kernel(const float* __restric
         const int32_t item = it[k];
         out[k] = canonical_score<KIND>(P + (int64_t)u[k] * dim, Q + (int64_t)item * dim, hvec, item, dim);
     }
+}
+
+// The same scores for large calls (test_model_loo over every test user: (1 + neg_samples) pairs per user).  A thread still owns one pair
+// and runs the canonical sequential fma chain -- that is what makes the result bit-identical to score_pairs_kernel and to the oracle --
+// but the rows are no longer read by the thread that consumes them (32 scattered 16-byte reads per warp instruction, the chain stalling
+// on each): a warp stages a 64-column chunk of its 32 item rows (and of the user row, once if the warp's pairs share the user) in
+// shared memory with coalesced 128-byte reads, all issued before the first use, then every thread walks its own row out of shared
+// memory (row stride 65: conflict free).  Bound: HBM, (1 + neg_samples) * 4 * d bytes per user.
+#define SP_CH 64
+#define SP_WARPS 4
+// rows `row` (one per lane) of `table`, columns [kc, kc+len): row r lands at dst[r * (SP_CH + 1) ...]; lane l copies columns l and l + 32
+// of every row (128-byte coalesced) with cp.async (LDGSTS): global -> shared without passing through registers, so all 64 copies of
+// the chunk are in flight at once (written as register loads + stores, ptxas re-schedules them to ~6 in flight to save registers)
+__device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ table, int32_t row, int dim, int kc, int len, int lane) {
+    const bool in0 = lane < len, in1 = lane + 32 < len;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        const float* src = table + (int64_t)__shfl_sync(0xffffffffu, row, r) * dim + kc;
+        if (in0) __pipeline_memcpy_async(dst + r * (SP_CH + 1) + lane, src + lane, 4);
+        if (in1) __pipeline_memcpy_async(dst + r * (SP_CH + 1) + lane + 32, src + lane + 32, 4);
+    }
+    __pipeline_commit();
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(SP_WARPS * 32) score_pairs_tiled_kernel(const float* __restrict__ P, const float* __restrict__ Q,
+                                                                          const float* __restrict__ hvec, int dim, const int32_t* __restrict__ u,
+                                                                          const int32_t* __restrict__ it, int64_t n, float* __restrict__ out) {
+    extern __shared__ float sp_sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* sQ = sp_sm + warp * (2 * 32 * (SP_CH + 1));
+    float* sP = sQ + 32 * (SP_CH + 1);
+    const int64_t n_batches = (n + 31) / 32;
+    const int64_t gw = (int64_t)blockIdx.x * SP_WARPS + warp, nw = (int64_t)gridDim.x * SP_WARPS;
+    for (int64_t b = gw; b < n_batches; b += nw) {
+        const int64_t k = b * 32 + lane;
+        const bool valid = k < n;
+        const int64_t kk = valid ? k : n - 1;
+        const int32_t item = it[kk], usr = u[kk];
+        const int32_t usr0 = __shfl_sync(0xffffffffu, usr, 0);
+        const bool uniform = __all_sync(0xffffffffu, usr == usr0);
+        float acc = 0.f;
+        for (int kc = 0; kc < dim; kc += SP_CH) {
+            const int len = dim - kc < SP_CH ? dim - kc : SP_CH;
+            stage_rows(sQ, Q, item, dim, kc, len, lane);
+            if (uniform) {
+                for (int c = lane; c < len; c += 32) sP[c] = P[(int64_t)usr0 * dim + kc + c];
+            } else {
+                stage_rows(sP, P, usr, dim, kc, len, lane);
+            }
+            __pipeline_wait_prior(0);
+            __syncwarp();
+            const float* q = sQ + lane * (SP_CH + 1);
+            const float* p = uniform ? sP : sP + lane * (SP_CH + 1);
+            for (int c = 0; c < len; ++c) {
+                const float a = p[c], bq = q[c];
+                if (KIND == CRB_SCORE_DOT || KIND == CRB_SCORE_DOT_BIAS) acc = fmaf(a, bq, acc);
+                else if (KIND == CRB_SCORE_GMF) acc = fmaf(__fmul_rn(a, bq), __ldg(hvec + kc + c), acc);
+                else { const float dd = __fsub_rn(a, bq); acc = fmaf(dd, dd, acc); }
+            }
+            __syncwarp();
+        }
+        if (KIND == CRB_SCORE_DOT_BIAS) acc = __fadd_rn(acc, hvec[item]);
+        if (valid) out[k] = acc;
+    }
+}
+
+template <int KIND>
+static int launch_score_pairs(crb_handle* h, const float* P, const float* Q, const float* hvec, int dim, const int32_t* u, const int32_t* it,
+                              int64_t n, float* out, cudaStream_t s) {
+    if (n >= 8192 && !getenv("CRB_SCORE_PAIRS_SIMPLE")) {
+        const size_t smem = sizeof(float) * SP_WARPS * 2 * 32 * (SP_CH + 1);
+        CRB_CUDA(cudaFuncSetAttribute(score_pairs_tiled_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int64_t grid = (n + 32 * SP_WARPS - 1) / (32 * SP_WARPS);
+        if (grid > (int64_t)h->sm_count * 3) grid = (int64_t)h->sm_count * 3;
+        score_pairs_tiled_kernel<KIND><<<(int)grid, SP_WARPS * 32, smem, s>>>(P, Q, hvec, dim, u, it, n, out);
+    } else {
+        int64_t grid = (n + 255) / 256;
+        if (grid > (int64_t)h->sm_count * 8) grid = (int64_t)h->sm_count * 8;
+        score_pairs_kernel<KIND><<<(int)(grid < 1 ? 1 : grid), 256, 0, s>>>(P, Q, hvec, dim, u, it, n, out);
+    }
+    return CRB_OK;
 }
 
 // One warp per user segment: K rounds of arg-best over the remaining candidates.
@@ -204,14 +289,14 @@ extern "C" int crb_score_pairs(crb_handle* h, int32_t kind, const float* P, cons
     if ((rc = stage_in(st, u, n, &du))) return rc;
     if ((rc = stage_in(st, i, n, &di))) return rc;
     if ((rc = stage_out(st, scores, n, &ds))) return rc;
-    const int grid = grid_for(h, n, 256);
     switch (kind) {
-        case CRB_SCORE_DOT: score_pairs_kernel<CRB_SCORE_DOT><<<grid, 256, 0, s>>>(P, Q, hvec, dim, du, di, n, ds); break;
-        case CRB_SCORE_GMF: score_pairs_kernel<CRB_SCORE_GMF><<<grid, 256, 0, s>>>(P, Q, hvec, dim, du, di, n, ds); break;
-        case CRB_SCORE_SQDIST: score_pairs_kernel<CRB_SCORE_SQDIST><<<grid, 256, 0, s>>>(P, Q, hvec, dim, du, di, n, ds); break;
-        case CRB_SCORE_DOT_BIAS: score_pairs_kernel<CRB_SCORE_DOT_BIAS><<<grid, 256, 0, s>>>(P, Q, hvec, dim, du, di, n, ds); break;
+        case CRB_SCORE_DOT: rc = launch_score_pairs<CRB_SCORE_DOT>(h, P, Q, hvec, dim, du, di, n, ds, s); break;
+        case CRB_SCORE_GMF: rc = launch_score_pairs<CRB_SCORE_GMF>(h, P, Q, hvec, dim, du, di, n, ds, s); break;
+        case CRB_SCORE_SQDIST: rc = launch_score_pairs<CRB_SCORE_SQDIST>(h, P, Q, hvec, dim, du, di, n, ds, s); break;
+        case CRB_SCORE_DOT_BIAS: rc = launch_score_pairs<CRB_SCORE_DOT_BIAS>(h, P, Q, hvec, dim, du, di, n, ds, s); break;
         default: crb_set_error("unknown score kind %d", kind); return CRB_ERR_ARG;
     }
+    if (rc) return rc;
     h->launches++;
     CRB_CUDA(cudaGetLastError());
     bool sync = false;

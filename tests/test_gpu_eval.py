@@ -97,3 +97,23 @@ def test_fullrank_exact_few_users_chunked_catalogue(eng, kind):
     got_i, got_s = eng.score_topk(kind, torch.tensor(P).cuda(), torch.tensor(Q).cuda(), users, 50, exact=True, return_scores=True)
     assert np.array_equal(got_i, want_i)
     assert np.array_equal(got_s.view(np.uint32), want_s.view(np.uint32))
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+@pytest.mark.parametrize("d", [7, 64, 100, 128, 200])
+def test_score_pairs_large_calls_bit_exact(eng, kind, d):
+    """Calls of >= 8192 pairs take score_pairs_tiled_kernel (rows staged in shared memory by coalesced reads; each thread still runs the
+    canonical sequential chain): bit-identical to the C oracle for user-uniform warps (test_model_loo's layout: all candidates of a user
+    are contiguous), mixed warps, a ragged tail and dimensions that are not multiples of the 64-column chunk."""
+    rs = np.random.RandomState(d * 7 + kind)
+    U, I = 300, 500
+    P, Q = rs.randn(U, d).astype(np.float32), rs.randn(I, d).astype(np.float32)
+    hvec = rs.randn(d if kind == 1 else I).astype(np.float32) if kind in (1, 3) else None
+    u = np.concatenate([np.repeat(rs.randint(0, U, 150), 101), rs.randint(0, U, 5003)])      # loo layout, then fully mixed users
+    i = rs.randint(0, I, u.shape[0])
+    assert u.shape[0] >= 8192 and u.shape[0] % 32 != 0
+    want = O.score_pairs(kind, P, Q, u, i, hvec)
+    hd = torch.tensor(hvec).cuda() if hvec is not None else None
+    got = eng.score_pairs(kind, torch.tensor(P).cuda(), torch.tensor(Q).cuda(), torch.tensor(u, dtype=torch.int32).cuda(),
+                          torch.tensor(i, dtype=torch.int32).cuda(), hvec=hd)
+    assert np.array_equal(got.cpu().numpy().view(np.uint32), want.view(np.uint32))
