@@ -92,3 +92,70 @@ def test_main_module_as_a_script(tmp_path):
     assert r.returncode == 0, r.stdout[-3000:]
     assert "Current model: BPR" in r.stdout and " epoch 3" in r.stdout and "best_epoch:" in r.stdout
     assert os.path.exists(tmp_path / "logs" / "BPR.log")
+
+
+SBPR_CONF = """[parameters]
+social_file=trusts.csv
+epoches=3
+batch_size=6144
+embed_size=64
+reg=0.05
+lr=0.01
+neg_ratio=4
+optimizer=Adam
+is_pairwise=True
+loss_func=bpr
+init_method=normal 
+stddev=0.01
+"""
+TUNING_CONF = """[parameters]
+epoches=2
+batch_size=6144
+embed_size=[16,32]
+reg=[0.01,0.1]
+neg_ratio=[4]
+lr=0.01
+optimizer=Adam
+is_pairwise=True
+loss_func=bpr
+init_method=normal
+stddev=0.01
+tuning.workers=2
+"""
+
+
+def test_sbpr_through_the_entry_point_with_a_trust_file(tmp_path):
+    """recommender=SBPR with conf/SBPR.properties in the reference's format (social_file=trusts.csv): the packaged RankingPreprocess
+    reads the trust pairs (RankingPreprocess.py:49-58), SBPR builds SPu and trains on the social sampler, run_model logs as usual."""
+    write_tree(tmp_path, "loo", 99)
+    (tmp_path / "conf" / "SBPR.properties").write_text(SBPR_CONF)
+    (tmp_path / "CleverRec.properties").write_text((DEFAULTS % {"split": "loo", "neg": 99}).replace("recommender=BPR", "recommender=SBPR"))
+    rs = np.random.RandomState(3)
+    rows = ["trustor,trustee"]
+    for u in range(400):   # friends mostly from the user's own preference cluster, plus ids that never rated (dropped by the filter)
+        for v in np.unique(np.r_[rs.randint(0, 50, 4) * 8 + (u % 8), rs.randint(0, 400, 1)]):
+            if v != u:
+                rows.append("%d,%d" % (1000 + u, 1000 + v))
+        rows.append("%d,%d" % (1000 + u, 99999))
+    (tmp_path / "dataset" / "toy" / "trusts.csv").write_text("\n".join(rows) + "\n")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-m", "cleverrec_b200.main", "."], cwd=str(tmp_path), env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "Current model: SBPR" in r.stdout and " epoch 3" in r.stdout and "best_epoch:" in r.stdout
+    import re
+    hr = [float(x) for x in re.findall(r"\(k=10\) HR=([0-9.]+)", r.stdout)]
+    assert hr and max(hr) > 0.15, r.stdout[-1500:]      # chance is 0.10 with 99 negatives
+
+
+def test_main_tuning_as_a_script(tmp_path):
+    """python -m cleverrec_b200.main_tuning: the reference's grid (main_tuning.py:38-45) over bracketed lists in the model's conf,
+    two combinations at a time on the GPU; one run_model log per combination and the summary lines."""
+    write_tree(tmp_path, "loo", 99)
+    (tmp_path / "conf" / "BPR.properties").write_text(TUNING_CONF)
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-m", "cleverrec_b200.main_tuning", "."], cwd=str(tmp_path), env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert r.stdout.count("best_epoch:") == 4 and r.stdout.count("[tuning ") == 4
+    assert "best by NDCG@topk[0]:" in r.stdout and "'embed_size': 32" in r.stdout
