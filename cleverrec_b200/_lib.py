@@ -110,9 +110,9 @@ def load():
     lib.crb_train_step_sbpr.argtypes = [vp, T, T, T, vp, vp, vp, O, vp, vp, vp, vp, vp, i64, f32, vp, vp]
     lib.crb_mask_seen.argtypes = [vp, vp, vp, i64, i64, f32, vp]
     lib.crb_sample_nais.argtypes = [vp, u64, u32, i64, i32, i32, vp, vp, vp]
-    lib.crb_train_step_nais.argtypes = [vp, T, T, T, vp, vp, vp, vp, vp, vp, i32, O, vp, i32, vp, vp, i32, f32, f32, vp, vp]
-    lib.crb_train_epoch_nais.argtypes = [vp, T, T, T, vp, vp, vp, vp, vp, vp, i32, O, u64, u32, vp, vp, i64, i32, f32, f32, vp, vp]
-    lib.crb_score_nais.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, i32, vp, i32, f32, vp, vp]
+    lib.crb_train_step_nais.argtypes = [vp, T, T, T, vp, vp, vp, vp, vp, vp, i32, i32, O, vp, i32, vp, vp, i32, f32, f32, vp, vp]
+    lib.crb_train_epoch_nais.argtypes = [vp, T, T, T, vp, vp, vp, vp, vp, vp, i32, i32, O, u64, u32, vp, vp, i64, i32, f32, f32, vp, vp]
+    lib.crb_score_nais.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, i32, vp, i32, f32, vp, vp]
     S = C.POINTER(CrbShard)
     lib.crb_shard_step_compute.argtypes = [vp, T, S, O, vp, vp, vp, u64, u32, i64, i32, i64, f32, vp, vp]
     lib.crb_set_item_lists.argtypes = [vp, vp, vp, vp]

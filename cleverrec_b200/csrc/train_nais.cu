@@ -1,6 +1,7 @@
 // NAIS_single (reference: model/ranking/NAIS_single.py:59-97, train_model_nais RankingRecommender.py:64-87): one optimizer
-// step per user.  History H (n items, list order), targets T (m = n*(1+neg_ratio)), product attention:
-//   a_tk = h . relu(W^T (q_t * p_k) + b);  e = exp(a);  w_tk = e_tk / (sum_k e_tk)^beta;  s_t = sum_k w_tk p_k;
+// step per user.  History H (n items, list order), targets T (m = n*(1+neg_ratio)), attention over j_tk = q_t * p_k (atten_type
+// 'prod', W [d, A]) or j_tk = [p_k ; q_t] (atten_type 'concat', W [2d, A]; NAIS_single.py:67-71):
+//   a_tk = h . relu(W^T j_tk + b);  e = exp(a);  w_tk = e_tk / (sum_k e_tk)^beta;  s_t = sum_k w_tk p_k;
 //   x_t = s_t . q_t + bias_t;  loss = sum CE(x, y) + reg * (l2(s) + l2(q_T) + l2(bias_T))          (NAIS_single.py:66-90)
 // Three kernels per step (+ dense applies):
 //   nais_attn_kernel<false>   a_tk for every (target, history) pair, one warp per pair, W in shared memory
@@ -24,6 +25,7 @@ struct NaisArgs {
     const int32_t* tgt;    // [m]
     const float* y;        // [m]
     int n, m, d, A;
+    int concat;            // 1: j_tk = [p_k ; q_t], W has 2d rows
     float beta, reg;
     float* abuf;           // [m, n]  a_tk, then d(loss)/da_tk
     float* wbuf;           // [m, n]  d(loss)/dw_tk scratch
@@ -41,20 +43,21 @@ template <bool BWD>
 __global__ void __launch_bounds__(NA_WARPS * 32) nais_attn_kernel(NaisArgs a) {
     extern __shared__ float sm[];
     const int d = a.d, A = a.A, AP = A + 1;
+    const int JD = a.concat ? 2 * d : d;          // rows of W = length of the joint vector
     float* sW = sm;
-    float* sb = sW + d * AP;
+    float* sb = sW + JD * AP;
     float* sh = sb + A;
     float* gW = sh + A;
-    float* gb = gW + (BWD ? d * AP : 0);
+    float* gb = gW + (BWD ? JD * AP : 0);
     float* gh = gb + (BWD ? A : 0);
     float* wbase = gh + (BWD ? A : 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* jbuf = wbase + warp * (d + 32);
-    float* dzbuf = jbuf + d;
-    for (int k = threadIdx.x; k < d * A; k += blockDim.x) sW[(k / A) * AP + (k % A)] = a.dense[k];
-    for (int k = threadIdx.x; k < A; k += blockDim.x) { sb[k] = a.dense[d * A + k]; sh[k] = a.dense[d * A + A + k]; }
+    float* jbuf = wbase + warp * (JD + 32);
+    float* dzbuf = jbuf + JD;
+    for (int k = threadIdx.x; k < JD * A; k += blockDim.x) sW[(k / A) * AP + (k % A)] = a.dense[k];
+    for (int k = threadIdx.x; k < A; k += blockDim.x) { sb[k] = a.dense[JD * A + k]; sh[k] = a.dense[JD * A + A + k]; }
     if (BWD)
-        for (int k = threadIdx.x; k < d * AP + 2 * A; k += blockDim.x) gW[k] = 0.f;
+        for (int k = threadIdx.x; k < JD * AP + 2 * A; k += blockDim.x) gW[k] = 0.f;
     __syncthreads();
     const int64_t pairs = (int64_t)a.m * a.n;
     for (int64_t idx = (int64_t)blockIdx.x * NA_WARPS + warp; idx < pairs; idx += (int64_t)gridDim.x * NA_WARPS) {
@@ -67,14 +70,15 @@ __global__ void __launch_bounds__(NA_WARPS * 32) nais_attn_kernel(NaisArgs a) {
             if (c < d) {
                 qv[v] = a.Q[qrow * d + c];
                 pv[v] = a.P[prow * d + c];
-                jbuf[c] = qv[v] * pv[v];          // einsum('ac,bc->abc', q, p)
+                if (a.concat) { jbuf[c] = pv[v]; jbuf[d + c] = qv[v]; }   // concat([tile(p), tile(q)], 2)   (:68-69)
+                else jbuf[c] = qv[v] * pv[v];                             // einsum('ac,bc->abc', q, p)      (:71)
             }
         }
         __syncwarp();
         float pre = 0.f, z = 0.f;
         if (lane < A) {
             pre = sb[lane];
-            for (int c = 0; c < d; ++c) pre = fmaf(jbuf[c], sW[c * AP + lane], pre);
+            for (int c = 0; c < JD; ++c) pre = fmaf(jbuf[c], sW[c * AP + lane], pre);
             z = fmaxf(pre, 0.f);
         }
         if (!BWD) {
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(NA_WARPS * 32) nais_attn_kernel(NaisArgs a) {
                 atomicAdd(gh + lane, da * z);
                 atomicAdd(gb + lane, dz);
                 if (dz != 0.f)
-                    for (int c = 0; c < d; ++c) atomicAdd(gW + c * AP + lane, jbuf[c] * dz);
+                    for (int c = 0; c < JD; ++c) atomicAdd(gW + c * AP + lane, jbuf[c] * dz);
             }
             dzbuf[lane] = dz;
             __syncwarp();
@@ -98,8 +102,15 @@ __global__ void __launch_bounds__(NA_WARPS * 32) nais_attn_kernel(NaisArgs a) {
                 if (c < d) {
                     float dj = 0.f;
                     for (int q = 0; q < A; ++q) dj = fmaf(sW[c * AP + q], dzbuf[q], dj);
-                    atomicAdd(a.gQ + qrow * d + c, dj * pv[v]);
-                    atomicAdd(a.gP + prow * d + c, dj * qv[v]);
+                    if (a.concat) {   // the joint vector holds p and q themselves: d/dp = dj[c], d/dq = dj[d + c]
+                        float dq = 0.f;
+                        for (int q = 0; q < A; ++q) dq = fmaf(sW[(d + c) * AP + q], dzbuf[q], dq);
+                        atomicAdd(a.gP + prow * d + c, dj);
+                        atomicAdd(a.gQ + qrow * d + c, dq);
+                    } else {
+                        atomicAdd(a.gQ + qrow * d + c, dj * pv[v]);
+                        atomicAdd(a.gP + prow * d + c, dj * qv[v]);
+                    }
                 }
             }
         }
@@ -107,9 +118,9 @@ __global__ void __launch_bounds__(NA_WARPS * 32) nais_attn_kernel(NaisArgs a) {
     }
     if (BWD) {
         __syncthreads();
-        float* part = a.dense_part + (int64_t)blockIdx.x * (d * A + 2 * A);
-        for (int k = threadIdx.x; k < d * A; k += blockDim.x) part[k] = gW[(k / A) * AP + (k % A)];
-        for (int k = threadIdx.x; k < A; k += blockDim.x) { part[d * A + k] = gb[k]; part[d * A + A + k] = gh[k]; }
+        float* part = a.dense_part + (int64_t)blockIdx.x * (JD * A + 2 * A);
+        for (int k = threadIdx.x; k < JD * A; k += blockDim.x) part[k] = gW[(k / A) * AP + (k % A)];
+        for (int k = threadIdx.x; k < A; k += blockDim.x) { part[JD * A + k] = gb[k]; part[JD * A + A + k] = gh[k]; }
     }
 }
 
@@ -224,18 +235,19 @@ int crb_dense_table_apply(crb_handle* h, const crb_table* T, float* grad, int op
 int crb_opt_to_dev(crb_handle* h, const crb_opt* opt, OptDev* out, int* opt_kind, cudaStream_t s);
 
 static int nais_prepare(crb_handle* h, NaisArgs& a, const float* P, const float* Q, const float* bias, const float* dense, int32_t d, int32_t A,
-                        const int32_t* hist, int32_t n, const int32_t* tgt, int32_t m, float beta, int64_t* buf_floats, cudaStream_t s) {
+                        int32_t concat, const int32_t* hist, int32_t n, const int32_t* tgt, int32_t m, float beta, int64_t* buf_floats, cudaStream_t s) {
     CRB_CHECK_ARG(d >= 1 && d <= 512 && A >= 1 && A <= 32, "NAIS needs embed_size <= 512 and atten_size <= 32");
     CRB_CHECK_ARG(n >= 1 && m >= 1, "empty history / target list");
     CRB_CHECK_ARG(crb_is_device_ptr(hist) && crb_is_device_ptr(tgt), "hist/targets must be device pointers");
-    a.P = P; a.Q = Q; a.bias = bias; a.dense = dense; a.hist = hist; a.tgt = tgt; a.n = n; a.m = m; a.d = d; a.A = A; a.beta = beta;
+    a.P = P; a.Q = Q; a.bias = bias; a.dense = dense; a.hist = hist; a.tgt = tgt; a.n = n; a.m = m; a.d = d; a.A = A; a.concat = concat ? 1 : 0; a.beta = beta;
     *buf_floats = 2 * (int64_t)m * n;
     (void)h; (void)s;
     return CRB_OK;
 }
 
-static size_t nais_smem(int d, int A, bool bwd) {
-    return sizeof(float) * ((size_t)(bwd ? 2 : 1) * (d * (A + 1) + 2 * A) + (size_t)NA_WARPS * (d + 32));
+static size_t nais_smem(int d, int A, bool bwd, int concat) {
+    const int JD = concat ? 2 * d : d;
+    return sizeof(float) * ((size_t)(bwd ? 2 : 1) * (JD * (A + 1) + 2 * A) + (size_t)NA_WARPS * (JD + 32));
 }
 
 static int nais_ws(crb_handle* h, int64_t floats, cudaStream_t s) {
@@ -243,9 +255,9 @@ static int nais_ws(crb_handle* h, int64_t floats, cudaStream_t s) {
 }
 
 extern "C" int crb_train_step_nais(crb_handle* h, const crb_table* P, const crb_table* Q, const crb_table* B, float* gradP, float* gradQ,
-                                   float* gradB, float* dense, float* dense_s1, float* dense_s2, int32_t atten_size, const crb_opt* opt,
-                                   const int32_t* hist, int32_t n_hist, const int32_t* targets, const float* y, int32_t n_targets,
-                                   float beta, float reg, double* loss_out, void* stream) {
+                                   float* gradB, float* dense, float* dense_s1, float* dense_s2, int32_t atten_size, int32_t atten_concat,
+                                   const crb_opt* opt, const int32_t* hist, int32_t n_hist, const int32_t* targets, const float* y,
+                                   int32_t n_targets, float beta, float reg, double* loss_out, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     CRB_CHECK_ARG(h && P && Q && B && gradP && gradQ && gradB && dense && hist && targets && y, "null argument");
     CRB_CHECK_ARG(crb_is_device_ptr(y), "y must be a device pointer");
@@ -260,8 +272,8 @@ extern "C" int crb_train_step_nais(crb_handle* h, const crb_table* P, const crb_
     CRB_CUDA(cudaSetDevice(h->device));
     NaisArgs a;
     int64_t bufs = 0;
-    if ((rc = nais_prepare(h, a, P->w, Q->w, B->w, dense, P->dim, atten_size, hist, n_hist, targets, n_targets, beta, &bufs, s))) return rc;
-    const int n_dense = P->dim * atten_size + 2 * atten_size;
+    if ((rc = nais_prepare(h, a, P->w, Q->w, B->w, dense, P->dim, atten_size, atten_concat, hist, n_hist, targets, n_targets, beta, &bufs, s))) return rc;
+    const int n_dense = (atten_concat ? 2 : 1) * P->dim * atten_size + 2 * atten_size;
     const int64_t pairs = (int64_t)n_targets * n_hist;
     int grid_p = (int)((pairs + NA_WARPS - 1) / NA_WARPS);
     if (grid_p > h->sm_count * 2) grid_p = h->sm_count * 2;
@@ -272,7 +284,7 @@ extern "C" int crb_train_step_nais(crb_handle* h, const crb_table* P, const crb_
     a.wbuf = a.abuf + pairs;
     a.dense_part = a.wbuf + pairs;
     a.gP = gradP; a.gQ = gradQ; a.gbias = gradB; a.y = y; a.reg = reg; a.scores = nullptr; a.loss_part = h->block_loss;
-    const size_t sm_f = nais_smem(P->dim, atten_size, false), sm_b = nais_smem(P->dim, atten_size, true);
+    const size_t sm_f = nais_smem(P->dim, atten_size, false, atten_concat), sm_b = nais_smem(P->dim, atten_size, true, atten_concat);
     if (sm_b > 200 * 1024) { crb_set_error("NAIS attention too large for shared memory"); return CRB_ERR_UNSUPPORTED; }
     CRB_CUDA(cudaFuncSetAttribute(nais_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f));
     CRB_CUDA(cudaFuncSetAttribute(nais_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_b));
@@ -304,7 +316,7 @@ extern "C" int crb_train_step_nais(crb_handle* h, const crb_table* P, const crb_
 }
 
 extern "C" int crb_score_nais(crb_handle* h, const float* P, const float* Q, const float* bias, const float* dense, int32_t dim,
-                              int32_t atten_size, const int32_t* hist, int32_t n_hist, const int32_t* targets, int32_t n_targets, float beta,
+                              int32_t atten_size, int32_t atten_concat, const int32_t* hist, int32_t n_hist, const int32_t* targets, int32_t n_targets, float beta,
                               float* scores, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     CRB_CHECK_ARG(h && P && Q && bias && dense && hist && targets && scores, "null argument");
@@ -312,7 +324,7 @@ extern "C" int crb_score_nais(crb_handle* h, const float* P, const float* Q, con
     CRB_CUDA(cudaSetDevice(h->device));
     NaisArgs a;
     int64_t bufs = 0;
-    int rc = nais_prepare(h, a, P, Q, bias, dense, dim, atten_size, hist, n_hist, targets, n_targets, beta, &bufs, s);
+    int rc = nais_prepare(h, a, P, Q, bias, dense, dim, atten_size, atten_concat, hist, n_hist, targets, n_targets, beta, &bufs, s);
     if (rc) return rc;
     const int64_t pairs = (int64_t)n_targets * n_hist;
     if ((rc = nais_ws(h, pairs, s))) return rc;
@@ -322,7 +334,8 @@ extern "C" int crb_score_nais(crb_handle* h, const float* P, const float* Q, con
     if (grid_p > (int64_t)h->sm_count * 4) grid_p = (int64_t)h->sm_count * 4;
     int grid_t = (n_targets + NA_WARPS - 1) / NA_WARPS;
     if (grid_t > h->sm_count * 4) grid_t = h->sm_count * 4;
-    const size_t sm_f = nais_smem(dim, atten_size, false);
+    const size_t sm_f = nais_smem(dim, atten_size, false, atten_concat);
+    if (sm_f > 200 * 1024) { crb_set_error("NAIS attention too large for shared memory"); return CRB_ERR_UNSUPPORTED; }
     CRB_CUDA(cudaFuncSetAttribute(nais_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f));
     nais_attn_kernel<false><<<(int)grid_p, NA_WARPS * 32, sm_f, s>>>(a);
     nais_target_kernel<false><<<grid_t, NA_WARPS * 32, 0, s>>>(a);
@@ -337,8 +350,8 @@ int crb_launch_sample_nais(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t
 // train_model_nais for `n_users` users in one call: user k has its interaction list at pos_item[list_start[k] .. +list_len[k]) (HOST
 // arrays, in the order the reference iterates data.ui_train); one sampler launch + one optimizer step per user; loss_out[k].
 extern "C" int crb_train_epoch_nais(crb_handle* h, const crb_table* P, const crb_table* Q, const crb_table* B, float* gradP, float* gradQ,
-                                    float* gradB, float* dense, float* dense_s1, float* dense_s2, int32_t atten_size, const crb_opt* opt,
-                                    uint64_t seed, uint32_t epoch, const int64_t* list_start, const int32_t* list_len, int64_t n_users,
+                                    float* gradB, float* dense, float* dense_s1, float* dense_s2, int32_t atten_size, int32_t atten_concat,
+                                    const crb_opt* opt, uint64_t seed, uint32_t epoch, const int64_t* list_start, const int32_t* list_len, int64_t n_users,
                                     int32_t neg_ratio, float beta, float reg, double* loss_out, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     CRB_CHECK_ARG(h && list_start && list_len && loss_out, "null argument");
@@ -357,7 +370,8 @@ extern "C" int crb_train_epoch_nais(crb_handle* h, const crb_table* P, const crb
         const int32_t m = n * (neg_ratio + 1);
         if ((rc = crb_launch_sample_nais(h, seed, epoch, list_start[k], n, neg_ratio, h->idx[0], h->yv, s))) return rc;
         step_opt.step = opt->step + k;
-        rc = crb_train_step_nais(h, P, Q, B, gradP, gradQ, gradB, dense, dense_s1, dense_s2, atten_size, &step_opt, h->pos_item + list_start[k], n,
+        rc = crb_train_step_nais(h, P, Q, B, gradP, gradQ, gradB, dense, dense_s1, dense_s2, atten_size, atten_concat, &step_opt,
+                                 h->pos_item + list_start[k], n,
                                  h->idx[0], h->yv, m, beta, reg, loss_out + k, stream);
         if (rc) return rc;
     }

@@ -453,8 +453,9 @@ class Engine(object):
             if getattr(T_, "grad", None) is None:
                 T_.grad = torch.zeros_like(T_.w)
 
-    def train_step_nais(self, P, Q, B, dense, dense_s1, dense_s2, atten_size, opt, hist, targets, y, beta, reg, loss_out=None):
-        """One `sess.run([train, loss], {u_idx: history, i_idx: targets, y})` of NAIS_single (one user)."""
+    def train_step_nais(self, P, Q, B, dense, dense_s1, dense_s2, atten_size, opt, hist, targets, y, beta, reg, loss_out=None, concat=False):
+        """One `sess.run([train, loss], {u_idx: history, i_idx: targets, y})` of NAIS_single (one user).  concat: atten_type 'concat'
+        (W has 2*dim rows) instead of 'prod'."""
         dev = self.device
         hist = torch.as_tensor(np.asarray(hist), dtype=torch.int32).to(dev) if not isinstance(hist, torch.Tensor) else hist.to(torch.int32)
         targets = torch.as_tensor(np.asarray(targets), dtype=torch.int32).to(dev) if not isinstance(targets, torch.Tensor) else targets.to(torch.int32)
@@ -464,18 +465,19 @@ class Engine(object):
         co = opt.c(opt.t)
         lo = torch.zeros(1, dtype=torch.float64, device=dev) if loss_out is None else loss_out
         check(self.lib.crb_train_step_nais(self.h, C.byref(P.c), C.byref(Q.c), C.byref(B.c), ptr(P.grad), ptr(Q.grad), ptr(B.grad), ptr(dense),
-                                           ptr(dense_s1), ptr(dense_s2), atten_size, C.byref(co), ptr(hist), hist.numel(), ptr(targets), ptr(y),
-                                           targets.numel(), float(beta), float(reg), ptr(lo), self.stream))
+                                           ptr(dense_s1), ptr(dense_s2), atten_size, 1 if concat else 0, C.byref(co), ptr(hist), hist.numel(), ptr(targets),
+                                           ptr(y), targets.numel(), float(beta), float(reg), ptr(lo), self.stream))
         return float(lo.item()) if loss_out is None else None
 
-    def train_epoch_nais(self, P, Q, B, dense, dense_s1, dense_s2, atten_size, opt, seed, epoch, list_start, list_len, neg_ratio, beta, reg, losses):
+    def train_epoch_nais(self, P, Q, B, dense, dense_s1, dense_s2, atten_size, opt, seed, epoch, list_start, list_len, neg_ratio, beta, reg, losses,
+                         concat=False):
         self._ensure_grads((P, Q, B))
         list_start = np.ascontiguousarray(list_start, dtype=np.int64)
         list_len = np.ascontiguousarray(list_len, dtype=np.int32)
         co = opt.c(opt.t + 1)
         check(self.lib.crb_train_epoch_nais(self.h, C.byref(P.c), C.byref(Q.c), C.byref(B.c), ptr(P.grad), ptr(Q.grad), ptr(B.grad), ptr(dense),
-                                            ptr(dense_s1), ptr(dense_s2), atten_size, C.byref(co), seed, epoch, ptr(list_start), ptr(list_len),
-                                            len(list_len), neg_ratio, float(beta), float(reg), ptr(losses), self.stream))
+                                            ptr(dense_s1), ptr(dense_s2), atten_size, 1 if concat else 0, C.byref(co), seed, epoch, ptr(list_start),
+                                            ptr(list_len), len(list_len), neg_ratio, float(beta), float(reg), ptr(losses), self.stream))
         opt.t += len(list_len)
 
     def sample_nais(self, seed, epoch, pos_first, n_pos_user, neg_ratio):
@@ -485,15 +487,15 @@ class Engine(object):
         check(self.lib.crb_sample_nais(self.h, seed, epoch, pos_first, n_pos_user, neg_ratio, ptr(tg), ptr(y), self.stream))
         return tg, y
 
-    def score_nais(self, P, Q, bias, dense, atten_size, hist, targets, beta, out=None):
+    def score_nais(self, P, Q, bias, dense, atten_size, hist, targets, beta, out=None, concat=False):
         """out: optional contiguous float32 device tensor [len(targets)] to write into (e.g. a slice of a larger buffer)."""
         dev = self.device
         hist = torch.as_tensor(np.asarray(hist), dtype=torch.int32).to(dev) if not isinstance(hist, torch.Tensor) else hist.to(torch.int32)
         targets = torch.as_tensor(np.asarray(targets), dtype=torch.int32).to(dev) if not isinstance(targets, torch.Tensor) else targets.to(torch.int32)
         if out is None:
             out = torch.empty(targets.numel(), dtype=torch.float32, device=dev)
-        check(self.lib.crb_score_nais(self.h, ptr(P), ptr(Q), ptr(bias), ptr(dense), P.shape[1], atten_size, ptr(hist), hist.numel(), ptr(targets),
-                                      targets.numel(), float(beta), ptr(out), self.stream))
+        check(self.lib.crb_score_nais(self.h, ptr(P), ptr(Q), ptr(bias), ptr(dense), P.shape[1], atten_size, 1 if concat else 0, ptr(hist), hist.numel(),
+                                      ptr(targets), targets.numel(), float(beta), ptr(out), self.stream))
         return out
 
     def adam_flush(self, table, opt):

@@ -15,9 +15,9 @@ class NAIS_single(_rr.RankingRecommender):
         super(NAIS_single, self).__init__(sess, data, configs, logger)
         self.embed_size, self.atten_size, self.reg = int(configs['embed_size']), int(configs['atten_size']), float(configs['reg'])
         self.beta = float(configs['beta'])  # The smoothing coefficient of Softmax
-        self.atten_type = configs['atten_type']
-        if self.atten_type == 'concat':
-            raise NotImplementedError("atten_type=concat is not built; the shipped conf (atten_type='prod', quoted) takes the product branch")
+        self.atten_type = configs['atten_type']  # concat/prod -- compared with == 'concat' as in NAIS_single.py:52,67: the shipped conf's
+        # quoted value atten_type='prod' (and anything else) takes the product branch
+        self.concat = self.atten_type == 'concat'
         logger.info(' model_params: embed_size=%d, atten_size=%d, atten_type=%s, reg=%s, beta=%s' % (self.embed_size, self.atten_size,
                     self.atten_type, self.reg, self.beta) + ', ' + self.model_params)
         # Specify training and testing model (NAIS_single.py:20-21)
@@ -42,7 +42,7 @@ class NAIS_single(_rr.RankingRecommender):
         b = get('bias', lambda: unif(n))
         self.B = Table(torch.cat([b, torch.zeros((-n) % 4)]).reshape(-1, 1).to(dev).contiguous(), kind, 'lazy')
         self.n_bias = n
-        W = get('W', lambda: self.initializer([self.embed_size, self.atten_size]))
+        W = get('W', lambda: self.initializer([(2 if self.concat else 1) * self.embed_size, self.atten_size]))   # NAIS_single.py:52-55
         self.dense = torch.cat([W.reshape(-1), get('b', lambda: unif(self.atten_size)), get('h', lambda: unif(self.atten_size))]).to(dev)
         self.dense_s1 = torch.full_like(self.dense, 0.1) if kind == 'Adagrad' else (torch.zeros_like(self.dense) if kind == 'Adam' else None)
         self.dense_s2 = torch.zeros_like(self.dense) if kind == 'Adam' else None
@@ -67,7 +67,7 @@ class NAIS_single(_rr.RankingRecommender):
         return out
 
     def _variables(self):   # NAIS_single.py:99-106
-        d, a = self.embed_size, self.atten_size
+        d, a = (2 if self.concat else 1) * self.embed_size, self.atten_size
         return {'NAIS_paras/P': self.P.w, 'NAIS_params/Q': self.Q.w, 'NAIS_params/bias': self.bias, 'NAIS_params/W': self.dense[:d * a].reshape(d, a),
                 'NAIS_params/b': self.dense[d * a:d * a + a], 'NAIS_params/h': self.dense[d * a + a:d * a + 2 * a]}
 
@@ -78,19 +78,19 @@ class NAIS_single(_rr.RankingRecommender):
     def train_step(self, u_idx, i_idx, y, loss_out=None):
         """sess.run([train, loss], {u_idx: history, u_nbrs_num, i_idx, i_nums, y})  (NAIS_single.py:82-90)."""
         return self.engine.train_step_nais(self.P, self.Q, self.B, self.dense, self.dense_s1, self.dense_s2, self.atten_size, self.optimizer,
-                                           u_idx, i_idx, y, self.beta, self.reg, loss_out=loss_out)
+                                           u_idx, i_idx, y, self.beta, self.reg, loss_out=loss_out, concat=self.concat)
 
     # Form mini-batch by user (RankingRecommender.py:64-87): one optimizer step per user, in data.ui_train order
     def train_model_nais(self):
         losses = torch.zeros(len(self._train_users), dtype=torch.float64, device=self.engine.device)
         self.engine.train_epoch_nais(self.P, self.Q, self.B, self.dense, self.dense_s1, self.dense_s2, self.atten_size, self.optimizer, self.seed,
-                                     self.epoch, self._list_start, self._list_len, self.neg_ratio, self.beta, self.reg, losses)
+                                     self.epoch, self._list_start, self._list_len, self.neg_ratio, self.beta, self.reg, losses, concat=self.concat)
         self.epoch += 1
         return float(losses.sum().item()) / len(self._train_users)
 
     def _scores(self, u, targets):
         hist = self.data.ui_train[u] if u in self.data.ui_train else [self.data.item_nums]
-        return self.engine.score_nais(self.P.w, self.Q.w, self.bias, self.dense, self.atten_size, hist, targets, self.beta).cpu().numpy()
+        return self.engine.score_nais(self.P.w, self.Q.w, self.bias, self.dense, self.atten_size, hist, targets, self.beta, concat=self.concat).cpu().numpy()
 
     def _device_history(self, u):
         """The user's interaction list as a view of the engine's device copy of data.ui_train (no host -> device copy per user)."""
@@ -116,7 +116,7 @@ class NAIS_single(_rr.RankingRecommender):
         for k, u in enumerate(self.test_users):
             a, b = int(offsets[k]), int(offsets[k + 1])
             self.engine.score_nais(self.P.w, self.Q.w, bias, self.dense, self.atten_size, self._device_history(u), i_dev[a:b], self.beta,
-                                   out=scores_dev[a:b])
+                                   out=scores_dev[a:b], concat=self.concat)
         scores = scores_dev.cpu().numpy()
         for k, u in enumerate(self.test_users):
             pre_scores = scores[offsets[k]:offsets[k + 1]]
@@ -143,7 +143,7 @@ class NAIS_single(_rr.RankingRecommender):
             scores = torch.empty((len(cur), I), dtype=torch.float32, device=dev)
             for k, u in enumerate(cur):
                 self.engine.score_nais(self.P.w, self.Q.w, bias, self.dense, self.atten_size, self._device_history(u), all_items, self.beta,
-                                       out=scores[k])
+                                       out=scores[k], concat=self.concat)
             users = torch.as_tensor(np.asarray(cur), dtype=torch.int32, device=dev)
             scores = self.engine.mask_seen(scores, users)
             seg = torch.arange(len(cur) + 1, dtype=torch.int64, device=dev) * I

@@ -293,26 +293,27 @@ int crb_mask_seen(crb_handle* h, float* scores, const int32_t* users, int64_t n_
 int crb_sample_nais(crb_handle* h, uint64_t seed, uint32_t epoch, int64_t pos_first, int32_t n_pos_user, int32_t neg_ratio,
                     int32_t* targets, float* y, void* stream);
 
-/* sess.run([train, loss], {u_idx: history, i_idx: targets, y}) for model/ranking/NAIS_single.py:59-90 (product attention;
- * one step per user).  P, Q [(I+1), dim]; B the item bias as a dim-1 table padded to a multiple of 4 rows; `dense` packs
- * W [dim, atten_size] row-major, b [atten_size], h [atten_size].  hist / targets / y are DEVICE arrays. */
+/* sess.run([train, loss], {u_idx: history, i_idx: targets, y}) for model/ranking/NAIS_single.py:59-90 (one step per user).
+ * atten_concat = 0: atten_type 'prod', joint = q * p, W [dim, atten_size]; 1: atten_type 'concat', joint = [p ; q],
+ * W [2*dim, atten_size] (NAIS_single.py:52-55, 67-71).  P, Q [(I+1), dim]; B the item bias as a dim-1 table padded to a multiple of
+ * 4 rows; `dense` packs W row-major, b [atten_size], h [atten_size].  hist / targets / y are DEVICE arrays. */
 int crb_train_step_nais(crb_handle* h, const crb_table* P, const crb_table* Q, const crb_table* B, float* gradP, float* gradQ,
-                        float* gradB, float* dense, float* dense_s1, float* dense_s2, int32_t atten_size, const crb_opt* opt,
-                        const int32_t* hist, int32_t n_hist, const int32_t* targets, const float* y, int32_t n_targets,
-                        float beta, float reg, double* loss_out, void* stream);
+                        float* gradB, float* dense, float* dense_s1, float* dense_s2, int32_t atten_size, int32_t atten_concat,
+                        const crb_opt* opt, const int32_t* hist, int32_t n_hist, const int32_t* targets, const float* y,
+                        int32_t n_targets, float beta, float reg, double* loss_out, void* stream);
 
 /* train_model_nais (RankingRecommender.py:64-87) for n_users users in one call: sampler + one step per user.
  * list_start / list_len: HOST arrays (offset and length of each user's interaction list inside pos_item, in the order the
  * reference iterates data.ui_train); loss_out: DEVICE double [n_users]; opt->step = index of the first step. */
 int crb_train_epoch_nais(crb_handle* h, const crb_table* P, const crb_table* Q, const crb_table* B, float* gradP, float* gradQ,
-                         float* gradB, float* dense, float* dense_s1, float* dense_s2, int32_t atten_size, const crb_opt* opt,
-                         uint64_t seed, uint32_t epoch, const int64_t* list_start, const int32_t* list_len, int64_t n_users,
+                         float* gradB, float* dense, float* dense_s1, float* dense_s2, int32_t atten_size, int32_t atten_concat,
+                         const crb_opt* opt, uint64_t seed, uint32_t epoch, const int64_t* list_start, const int32_t* list_len, int64_t n_users,
                          int32_t neg_ratio, float beta, float reg, double* loss_out, void* stream);
 
 /* NAIS_single._predict (NAIS_single.py:92-97) for one user: scores[t] = s_t . q_t + bias_t over `targets`.  DEVICE buffers. */
 int crb_score_nais(crb_handle* h, const float* P, const float* Q, const float* bias, const float* dense, int32_t dim,
-                   int32_t atten_size, const int32_t* hist, int32_t n_hist, const int32_t* targets, int32_t n_targets,
-                   float beta, float* scores, void* stream);
+                   int32_t atten_size, int32_t atten_concat, const int32_t* hist, int32_t n_hist, const int32_t* targets,
+                   int32_t n_targets, float beta, float* scores, void* stream);
 
 /* Multi-GPU BPR step, phase 1 (every rank, same step index): sess.run([train, loss]) on this rank's slice of the union batch.
  * P: this rank's user rows; u = local user rows, i/j = GLOBAL item ids (DEVICE or HOST), or u == NULL to sample rows

@@ -19,14 +19,17 @@ def eng():
 
 
 @pytest.mark.parametrize("kind", ["SGD", "Adagrad", "Adam"])
-@pytest.mark.parametrize("d,A", [(32, 16), (128, 32)])
-def test_nais_user_steps(eng, kind, d, A):
+@pytest.mark.parametrize("d,A,atten", [(32, 16, "prod"), (128, 32, "prod"), (32, 16, "concat"), (128, 32, "concat")])
+def test_nais_user_steps(eng, kind, d, A, atten):
+    """Both attention types of NAIS_single.py:66-71: 'prod' (joint = q * p, W [d, A]) and 'concat' (joint = [p ; q], W [2d, A])."""
     from cleverrec_b200.engine import Optimizer, Table
     I = 60
     n = I + 1
+    concat = atten == "concat"
+    jd = 2 * d if concat else d
     g = torch.Generator().manual_seed(d)
     rnd = lambda *s: torch.randn(*s, generator=g) * 0.2
-    ref = {"P": rnd(n, d), "Q": rnd(n, d), "bias": rnd(n) * 0.5, "W": rnd(d, A), "b_att": rnd(A) * 0.5, "h": rnd(A)}
+    ref = {"P": rnd(n, d), "Q": rnd(n, d), "bias": rnd(n) * 0.5, "W": rnd(jd, A), "b_att": rnd(A) * 0.5, "h": rnd(A)}
     lr = 0.02 if kind != "Adam" else 0.005
     opt, ropt = Optimizer(kind, lr, adam_mode="lazy"), T.TF1Optimizer(kind, lr, adam_mode="tf1")
     P, Q = Table(ref["P"].clone().cuda(), kind, "lazy"), Table(ref["Q"].clone().cuda(), kind, "lazy")
@@ -35,25 +38,25 @@ def test_nais_user_steps(eng, kind, d, A):
     s1 = torch.full_like(dense, 0.1) if kind == "Adagrad" else (torch.zeros_like(dense) if kind == "Adam" else None)
     s2 = torch.zeros_like(dense) if kind == "Adam" else None
     rs = np.random.RandomState(A)
-    hp = {"reg": 1e-3, "beta": 0.5}
+    hp = {"reg": 1e-3, "beta": 0.5, "atten_type": atten}
     for n_hist in (5, 1, 40):
         hist = rs.choice(I, n_hist, replace=False)
         tg = rs.randint(0, I, n_hist * 3)
         y = (rs.rand(n_hist * 3) < 0.3).astype(np.float32)
-        got = eng.train_step_nais(P, Q, B, dense, s1, s2, A, opt, hist, tg, y, 0.5, 1e-3)
+        got = eng.train_step_nais(P, Q, B, dense, s1, s2, A, opt, hist, tg, y, 0.5, 1e-3, concat=concat)
         b = {"hist": torch.tensor(hist), "i": torch.tensor(tg), "y": torch.tensor(y)}
         want = T.train_step(T.nais_loss, ref, b, hp, ropt, sparse_index={"P": ["hist"], "Q": ["i"], "bias": ["i"]})
         assert abs(got - want) <= 5e-5 * abs(want), (got, want)
     rtol, atol = (3e-4, 3e-5) if kind == "Adam" else (3e-5, 2e-6)
-    cur = {"P": P.w.cpu().numpy(), "Q": Q.w.cpu().numpy(), "bias": B.w.cpu().numpy().reshape(-1)[:n], "W": dense[:d * A].cpu().numpy().reshape(d, A),
-           "b_att": dense[d * A:d * A + A].cpu().numpy(), "h": dense[d * A + A:].cpu().numpy()}
+    cur = {"P": P.w.cpu().numpy(), "Q": Q.w.cpu().numpy(), "bias": B.w.cpu().numpy().reshape(-1)[:n], "W": dense[:jd * A].cpu().numpy().reshape(jd, A),
+           "b_att": dense[jd * A:jd * A + A].cpu().numpy(), "h": dense[jd * A + A:].cpu().numpy()}
     for name, got in cur.items():
         want = ref[name].numpy()
         bad = ~np.isclose(got, want, rtol=rtol, atol=atol)
         assert bad.sum() <= max(1, 3e-3 * bad.size), (name, int(bad.sum()), float(np.abs(got - want).max()))
     # scoring (NAIS_single.py:92-97)
     hist, tg = rs.choice(I, 12, replace=False), np.arange(I)
-    sc = eng.score_nais(P.w, Q.w, B.w.reshape(-1)[:n].contiguous(), dense, A, hist, tg, 0.5).cpu().numpy()
+    sc = eng.score_nais(P.w, Q.w, B.w.reshape(-1)[:n].contiguous(), dense, A, hist, tg, 0.5, concat=concat).cpu().numpy()
     p64 = {k: torch.tensor(v).double() for k, v in cur.items()}
     q = p64["Q"][torch.tensor(tg)]
     s = T.nais_user_embed(p64, torch.tensor(hist), q, hp)
@@ -94,6 +97,11 @@ def test_nais_model_evaluation_equals_the_reference_loops():
         cand = np.setdiff1d(np.arange(data.item_nums), data.ui_train[u])
         data.ui_test[u] = rs.choice(cand, 49, replace=False).tolist() + data.ui_test[u]
     data.ui_test[7] = rs.choice(300, 49, replace=False).tolist() + [5]        # a test user without training history (u % 11 == 7)
+    mc = NAIS_single(None, data, dict(cfg, atten_type='concat'), logging.getLogger('test'))     # the other attention type, end to end
+    mc.build_model()
+    assert mc.dense.numel() == 2 * 32 * 16 + 2 * 16 and mc._variables()['NAIS_params/W'].shape == (64, 16)
+    lc = [mc.train_model() for _ in range(3)]
+    assert np.all(np.isfinite(lc)) and lc[-1] < lc[0] and len(mc.test_model_loo()[0][0]) == len(mc.test_users)
     m = NAIS_single(None, data, cfg, logging.getLogger('test'))
     m.build_model()
     m.train_model()
