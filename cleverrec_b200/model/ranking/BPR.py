@@ -20,6 +20,9 @@ class BPR(_rr.RankingRecommender):
         super(BPR, self).__init__(sess, data, configs, logger)
         self.embed_size, self.reg = int(configs['embed_size']), float(configs['reg'])
         logger.info(' model_params: embed_size=%d, reg=%s' % (self.embed_size, self.reg) + ', ' + self.model_params)
+        if self.loss_func != 'bpr' or self.is_pairwise != 'True':
+            # BPR.py:42 calls get_loss(self.loss_func, ui - uj) without margin / logits: only 'bpr' builds in the reference
+            raise ValueError("BPR is defined with is_pairwise=True, loss_func=bpr (conf/BPR.properties), got %r / %r" % (self.is_pairwise, self.loss_func))
 
     # ------------------------------------------------------------------------------------------ multi-GPU plumbing
     @property

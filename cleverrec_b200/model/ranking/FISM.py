@@ -19,6 +19,8 @@ class FISM(_rr.RankingRecommender):
             # FISM.py:61 uses an undefined `y` and the pointwise sampler feeds mismatched lengths
             raise NotImplementedError('FISM pointwise is broken in the reference; use the shipped pairwise configuration')
         logger.info(' model_params: embed_size=%d, alpha=%s, reg=%s, reg_bias=%s' % (self.embed_size, self.alpha, self.reg, self.reg_bias) + ', ' + self.model_params)
+        if self.loss_func != 'bpr':
+            raise ValueError('FISM (pairwise) is defined with loss_func=bpr (conf/FISM.properties), got %r' % self.loss_func)
 
     def _create_params(self, init=None):
         """FISM.py:32-38: P, Q [(I+1), d] and b ~ U(-0.1, 0.1) [(I+1)] (padded to a multiple of 4 for the dense apply)."""

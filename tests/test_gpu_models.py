@@ -230,3 +230,11 @@ def test_neumf_pretraining_chain_gmf_plus_mlp(tmp_path):
     ln = n.engine.score_pairs_neumf(n.tabs, n.dense, len(n.layers), u, i)
     assert torch.allclose(ln, 0.5 * (lg + lm), rtol=1e-5, atol=1e-6)
     assert np.isfinite(n.train_model())
+
+
+@pytest.mark.parametrize("name", ["BPR", "FISM"])
+def test_losses_the_reference_graph_cannot_build_are_rejected(name):
+    """BPR.py:42 / FISM.py:59 call get_loss(loss_func, ui - uj) with neither margin nor logits: only 'bpr' builds in the reference, and
+    the mirror classes say so at construction instead of silently training another loss."""
+    with pytest.raises(ValueError):
+        _model(name, _data('loo', 49), loss_func='hinge')

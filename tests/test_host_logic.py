@@ -59,3 +59,4 @@ def test_checkpoint_helpers_round_trip(tmp_path):
     v = load_checkpoint(a)
     assert set(v) == {"GMF_params/P", "GMF_params/h_gmf"} and v["GMF_params/P"].dtype == np.float32
     assert v["GMF_params/P"].tolist() == [[0.0, 1.0, 2.0], [3.0, 4.0, 5.0]]
+
