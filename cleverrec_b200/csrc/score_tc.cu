@@ -13,6 +13,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 #include <cuda_bf16.h>
+#include <cuda_pipeline.h>
 
 #include "score_common.cuh"
 
@@ -495,10 +496,14 @@ struct RescoreArgs {
     unsigned int* counters;  // [0] uncertified users, [1] max candidates
 };
 
+#define RS_CH 64   // columns of the item rows staged per round (shared memory: 8 warps x (32 rows x 65 + 64) floats)
 template <int KIND>
 __global__ void __launch_bounds__(256) rescore_kernel(RescoreArgs a) {
     constexpr int ASC = KIND == CRB_SCORE_SQDIST ? 1 : 0;
+    extern __shared__ float rs_sm[];
     const int lane = threadIdx.x & 31;
+    float* sQ = rs_sm + (threadIdx.x >> 5) * (32 * (RS_CH + 1) + RS_CH);
+    float* sP = sQ + 32 * (RS_CH + 1);
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t g = warp; g < a.n_users; g += n_warps) {
@@ -553,12 +558,46 @@ __global__ void __launch_bounds__(256) rescore_kernel(RescoreArgs a) {
             const int n = a.cand_cnt[slot];
             theta = fmaxf(theta, a.cand_thr[slot]);
             unsigned long long* list = a.cand + slot * TC_C;
-            for (int k = lane; k < n; k += 32) {  // canonical score, entry rewritten as a ranking key (0 = filtered out)
-                const unsigned long long e = list[k];
+            // canonical score of every surviving candidate, entry rewritten as a ranking key (0 = filtered out).  A lane owns a candidate
+            // and runs the canonical sequential chain (the scores are those of canonical_score, bit for bit), but the item rows are staged
+            // in shared memory by cp.async, 64 columns of up to 32 rows at a time, instead of being read 16 bytes at a time by the lane
+            // that consumes them (same scheme as score_pairs_tiled_kernel).
+            for (int k0 = 0; k0 < n; k0 += 32) {
+                const int k = k0 + lane;
+                const unsigned long long e = k < n ? list[k] : 0ULL;
                 const uint32_t item = (uint32_t)e;
-                if (__uint_as_float((uint32_t)(e >> 32)) < cutoff) { list[k] = 0ULL; continue; }
-                const float sc = canonical_score<KIND>(p, a.Q + (int64_t)item * a.dim, a.hvec, (int32_t)item, a.dim);
-                list[k] = rank_key(sc, item, ASC);
+                const bool live = k < n && !(__uint_as_float((uint32_t)(e >> 32)) < cutoff);
+                if (k < n && !live) list[k] = 0ULL;
+                const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+                if (!live_mask) continue;
+                float acc = 0.f;
+                for (int kc = 0; kc < a.dim; kc += RS_CH) {
+                    const int len = a.dim - kc < RS_CH ? a.dim - kc : RS_CH;
+                    const bool in0 = lane < len, in1 = lane + 32 < len;
+                    for (unsigned m = live_mask; m; m &= m - 1) {
+                        const int r = __ffs(m) - 1;
+                        const float* src = a.Q + (int64_t)__shfl_sync(0xffffffffu, item, r) * a.dim + kc;
+                        if (in0) __pipeline_memcpy_async(sQ + r * (RS_CH + 1) + lane, src + lane, 4);
+                        if (in1) __pipeline_memcpy_async(sQ + r * (RS_CH + 1) + lane + 32, src + lane + 32, 4);
+                    }
+                    __pipeline_commit();
+                    if (in0) sP[lane] = p[kc + lane];
+                    if (in1) sP[lane + 32] = p[kc + lane + 32];
+                    __pipeline_wait_prior(0);
+                    __syncwarp();
+                    if (live) {
+                        const float* q = sQ + lane * (RS_CH + 1);
+                        for (int c = 0; c < len; ++c) {
+                            const float pa = sP[c], qb = q[c];
+                            if (KIND == CRB_SCORE_DOT || KIND == CRB_SCORE_DOT_BIAS) acc = fmaf(pa, qb, acc);
+                            else if (KIND == CRB_SCORE_GMF) acc = fmaf(__fmul_rn(pa, qb), __ldg(a.hvec + kc + c), acc);
+                            else { const float dd = __fsub_rn(pa, qb); acc = fmaf(dd, dd, acc); }
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (KIND == CRB_SCORE_DOT_BIAS) acc = __fadd_rn(acc, live ? a.hvec[item] : 0.f);
+                if (live) list[k] = rank_key(acc, item, ASC);
             }
         }
         __syncwarp();
@@ -725,11 +764,14 @@ int crb_score_topk_tc(crb_handle* h, int32_t kind, const float* P, const float* 
         ra.out_items = topk_items + u0 * K; ra.out_scores = topk_scores ? topk_scores + u0 * K : nullptr;
         ra.todo = (int32_t*)(ws + o_todo); ra.counters = misc + 2;
         const int rgrid = (int)((nu + 7) / 8 < (int64_t)h->sm_count * 8 ? (nu + 7) / 8 : (int64_t)h->sm_count * 8);
+        const size_t rsm = sizeof(float) * 8 * (32 * (RS_CH + 1) + RS_CH);
+#define CRB_RESCORE(KK) CRB_CUDA(cudaFuncSetAttribute(rescore_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm)); \
+                        rescore_kernel<KK><<<rgrid, 256, rsm, s>>>(ra);
         switch (kind) {
-            case CRB_SCORE_DOT: rescore_kernel<CRB_SCORE_DOT><<<rgrid, 256, 0, s>>>(ra); break;
-            case CRB_SCORE_GMF: rescore_kernel<CRB_SCORE_GMF><<<rgrid, 256, 0, s>>>(ra); break;
-            case CRB_SCORE_SQDIST: rescore_kernel<CRB_SCORE_SQDIST><<<rgrid, 256, 0, s>>>(ra); break;
-            case CRB_SCORE_DOT_BIAS: rescore_kernel<CRB_SCORE_DOT_BIAS><<<rgrid, 256, 0, s>>>(ra); break;
+            case CRB_SCORE_DOT: { CRB_RESCORE(CRB_SCORE_DOT) } break;
+            case CRB_SCORE_GMF: { CRB_RESCORE(CRB_SCORE_GMF) } break;
+            case CRB_SCORE_SQDIST: { CRB_RESCORE(CRB_SCORE_SQDIST) } break;
+            case CRB_SCORE_DOT_BIAS: { CRB_RESCORE(CRB_SCORE_DOT_BIAS) } break;
             default: crb_set_error("unknown score kind %d", kind); return CRB_ERR_ARG;
         }
         h->launches += 3;
