@@ -1,7 +1,7 @@
 """Epoch and evaluation times of every model class behind the reference's interface, at the shapes of BASELINE.json configs[0..3]
 (synthetic data of those shapes: the datasets themselves are not redistributable / not all in the reference mount), with the
-reference's CPU path beside it: the reference-algorithm Python sampler (oracle/ref_host.py, bit-equal to the genuine one) + the
-restated TF-1 graph step in torch-CPU fp32 (oracle/tf1_restatement.py), timed on a bounded sample of steps.
+reference's CPU path beside it (bench.py's cpu_baseline leg: reference-algorithm Python sampler + restated TF-1 step in torch-CPU
+fp32, a bounded sample of steps).
     python scripts/bench_models.py > profiles/r01_models.json          (GPU box; ~1-2 minutes)
 Not a bench.py line: bench.py measures the headline metric; this is the measurement of the rows widened into."""
 import json
@@ -109,31 +109,15 @@ def main():
         out.append(rec)
         sys.stderr.write("%-12s epoch %.3f s (%.3e rows/s, %d steps)  loo eval %.3f s\n" % (name, epoch_s, rec["rows_per_s"], rec["steps_per_epoch"], eval_s))
         m.engine.close()
-    # the reference's CPU path for the headline model at this shape: Python sampler + restated TF-1 step, bounded sample
-    from oracle import ref_host as H
-    from oracle import tf1_restatement as T
-    if (ML1M['users'], False) not in cache:
-        cache[(ML1M['users'], False)] = make_data(ML1M, 1)
-    data = cache[(ML1M['users'], False)]
-    sub = Data(data.user_nums, data.item_nums, {u: data.ui_train[u] for u in list(data.ui_train)[:400]}, {})
-    np.random.seed(0)
-    t0 = time.perf_counter()
-    tr = H.pairwise_ranking_sampler(sub, 4, 6144)
-    samp_s = time.perf_counter() - t0
-    g = torch.Generator().manual_seed(0)
-    ref = {"P": torch.randn(data.user_nums, 64, generator=g) * 0.01, "Q": torch.randn(data.item_nums, 64, generator=g) * 0.01}
-    ropt = T.TF1Optimizer("Adam", 1e-3)
-    torch.set_num_threads(os.cpu_count() or 1)
-    n_steps = min(8, tr[0])
-    t0 = time.perf_counter()
-    for k in range(n_steps):
-        sl = slice(k * 6144, (k + 1) * 6144)
-        b = {"u": torch.tensor(tr[1][sl]), "i": torch.tensor(tr[2][sl]), "j": torch.tensor(tr[3][sl])}
-        T.train_step(T.bpr_loss, ref, b, {"reg": 0.01}, ropt, sparse_index={"P": ["u"], "Q": ["i", "j"]})
-    step_s = (time.perf_counter() - t0) / n_steps
-    n_rows = len(tr[1])
-    cpu = {"what": "reference CPU path restated, BPR at the ml-1m shape: Python sampler over 400 users + dense-moment TF-1 Adam step (torch-CPU fp32)",
-           "cores": os.cpu_count(), "sampler_rows_per_s": n_rows / samp_s, "step_s": step_s, "rows_per_s": 1.0 / (samp_s / n_rows + step_s / 6144)}
+    # the reference's CPU path for the headline model at this shape: bench.py's cpu_baseline leg (the one place outside tests/ that
+    # may execute oracle/) -- reference-algorithm Python sampler + restated TF-1 BPR/Adam step, one 6144-row batch per step
+    from bench import cpu_reference_steps
+    threads = os.cpu_count() or 1
+    times, done, n_users = cpu_reference_steps(dict(users=ML1M['users'], items=ML1M['items'], dim=64, mean_hist=ML1M['mean'], batch=6144, neg_ratio=4),
+                                               6, 6144, threads)
+    sec = sum(times[1:]) / len(times[1:])
+    cpu = {"what": "reference CPU path restated (bench.py cpu_reference_steps), BPR at the ml-1m shape: Python sampler + row-sparse TF-1 Adam step "
+                   "(torch-CPU fp32) per 6144-row batch", "cores": threads, "rows_per_step": done, "step_s": sec, "rows_per_s": done / sec}
     print(json.dumps({"models": out, "cpu_reference_bpr_ml1m": cpu}, indent=1))
 
 
