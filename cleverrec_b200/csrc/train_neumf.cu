@@ -510,6 +510,63 @@ __global__ void __launch_bounds__(128) neumf_score_kernel(NeumfScoreArgs a) {
     }
 }
 
+// The same canonical logit, one WARP per pair: lane o owns output o of a layer and runs its sequential k-chain out of shared memory
+// (weights padded like the training kernel's), so every layer output -- and the final chain over the GMF products and the tower output,
+// run by lane 0 alone in the same order -- is bit-identical to neumf_score_kernel.  No per-thread arrays in local memory: ~100x the
+// pair rate of the thread-per-pair version, which is kept for validation (CRB_NEUMF_SCORE_SIMPLE).
+__global__ void __launch_bounds__(NM_WARPS * 32) neumf_score_warp_kernel(NeumfScoreArgs a) {
+    extern __shared__ float sm[];
+    const NeumfShape& S = a.sh;
+    const int n_small = S.n_dense - S.h_off;
+    int n_bias = 0;
+    for (int l = 0; l < S.n_layers; ++l) n_bias += S.n_out[l];
+    float* sW = sm;
+    float* sB = sW + S.n_smem_w;
+    float* sH = sB + n_bias;
+    float* warp_base = sH + n_small;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* act = warp_base + warp * (S.act_total + S.E);
+    float* eg = act + S.act_total;   // rounded GMF products p * q
+    int boff = 0;
+    for (int l = 0; l < S.n_layers; ++l) {
+        const int ni = S.n_in[l], no = S.n_out[l];
+        for (int k = threadIdx.x; k < ni * no; k += blockDim.x) sW[S.sw_off[l] + (k / no) * (no + 1) + (k % no)] = a.dense[S.w_off[l] + k];
+        for (int k = threadIdx.x; k < no; k += blockDim.x) sB[boff + k] = a.dense[S.b_off[l] + k];
+        boff += no;
+    }
+    for (int k = threadIdx.x; k < n_small; k += blockDim.x) sH[k] = a.dense[S.h_off + k];
+    __syncthreads();
+    const int Em = S.L0 / 2;
+    for (int64_t t = (int64_t)blockIdx.x * NM_WARPS + warp; t < a.n; t += (int64_t)gridDim.x * NM_WARPS) {
+        const int64_t u = a.u[t], it = a.i[t];
+        for (int k = lane; k < S.E; k += 32) eg[k] = __fmul_rn(a.Pg[u * S.E + k], a.Qg[it * S.E + k]);
+        for (int k = lane; k < S.L0; k += 32) act[k] = k < Em ? a.Pm[u * Em + k] : a.Qm[it * Em + (k - Em)];
+        __syncwarp();
+        int bo = 0;
+        for (int l = 0; l < S.n_layers; ++l) {
+            const int ni = S.n_in[l], no = S.n_out[l];
+            const float* x = act + S.act_off[l];
+            const float* W = sW + S.sw_off[l];
+            for (int o = lane; o < no; o += 32) {
+                float acc = sB[bo + o];
+                for (int k = 0; k < ni; ++k) acc = fmaf(x[k], W[k * (no + 1) + o], acc);
+                act[S.act_off[l + 1] + o] = fmaxf(acc, 0.f);
+            }
+            bo += no;
+            __syncwarp();
+        }
+        if (lane == 0) {
+            const int nl = S.n_out[S.n_layers - 1];
+            const float* alast = act + S.act_off[S.n_layers];
+            float acc = 0.f;
+            for (int k = 0; k < S.E; ++k) acc = fmaf(eg[k], sH[k], acc);
+            for (int k = 0; k < nl; ++k) acc = fmaf(alast[k], sH[S.E + k], acc);
+            a.out[t] = acc;
+        }
+        __syncwarp();
+    }
+}
+
 // scores[k, item] = value for every item the k-th user has seen (RankingRecommender.py:235-240 skip rule as a mask)
 __global__ void __launch_bounds__(256) mask_seen_kernel(float* scores, const int32_t* users, int64_t n_users, int64_t n_items,
                                                        const int64_t* seen_rowptr, const int32_t* seen_cols, float value) {
@@ -623,11 +680,21 @@ extern "C" int crb_score_pairs_neumf(crb_handle* h, const float* Pg, const float
     if (make_shape(E, 2 * Em, n_layers, &a.sh) || 2 * Em > 256) { crb_set_error("unsupported NeuMF shape"); return CRB_ERR_ARG; }
     if (n == 0) return CRB_OK;
     a.Pg = Pg; a.Qg = Qg; a.Pm = Pm; a.Qm = Qm; a.dense = dense; a.u = u; a.i = i; a.n = n; a.out = scores;
-    const size_t smem = sizeof(float) * a.sh.n_dense;
-    CRB_CUDA(cudaFuncSetAttribute(neumf_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t grid = (n + 127) / 128;
-    if (grid > (int64_t)h->sm_count * 8) grid = (int64_t)h->sm_count * 8;
-    neumf_score_kernel<<<(int)grid, 128, smem, s>>>(a);
+    int n_bias = 0;
+    for (int l = 0; l < a.sh.n_layers; ++l) n_bias += a.sh.n_out[l];
+    const size_t smem_w = sizeof(float) * ((size_t)a.sh.n_smem_w + n_bias + (a.sh.n_dense - a.sh.h_off) + (size_t)NM_WARPS * (a.sh.act_total + a.sh.E));
+    if (smem_w <= 200 * 1024 && !getenv("CRB_NEUMF_SCORE_SIMPLE")) {
+        CRB_CUDA(cudaFuncSetAttribute(neumf_score_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+        int64_t grid = (n + NM_WARPS - 1) / NM_WARPS;
+        if (grid > (int64_t)h->sm_count * 2) grid = (int64_t)h->sm_count * 2;
+        neumf_score_warp_kernel<<<(int)grid, NM_WARPS * 32, smem_w, s>>>(a);
+    } else {
+        const size_t smem = sizeof(float) * a.sh.n_dense;
+        CRB_CUDA(cudaFuncSetAttribute(neumf_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int64_t grid = (n + 127) / 128;
+        if (grid > (int64_t)h->sm_count * 8) grid = (int64_t)h->sm_count * 8;
+        neumf_score_kernel<<<(int)grid, 128, smem, s>>>(a);
+    }
     h->launches++;
     CRB_CUDA(cudaGetLastError());
     return CRB_OK;

@@ -105,3 +105,28 @@ def test_mlp_model_step_matches_restated_tower(eng):
         np.testing.assert_allclose(Q.w.cpu().numpy(), ref["Q"].numpy(), rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(dense[:128].cpu().numpy().reshape(16, 8), ref["W_0"].numpy(), rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(dense[-4:].cpu().numpy(), ref["h_mlp"].numpy(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("layers,E", [([128, 64, 32], 32), ([16, 8], 8), ([64, 32, 16], 0)])
+def test_neumf_warp_scorer_is_bit_identical_to_the_thread_scorer(eng, layers, E, monkeypatch):
+    """neumf_score_warp_kernel (one warp per pair, layer outputs by lanes) and neumf_score_kernel (one thread per pair) run the same
+    sequential chains: identical bits, including the MLP model (E = 0)."""
+    from cleverrec_b200.engine import Table
+    U, I = 70, 90
+    g = torch.Generator().manual_seed(E + len(layers))
+    rnd = lambda *s: torch.randn(*s, generator=g) * 0.3
+    Em = layers[0] // 2
+    tabs = [Table(rnd(U, E).cuda(), "SGD") if E else None, Table(rnd(I, E).cuda(), "SGD") if E else None, Table(rnd(U, Em).cuda(), "SGD"),
+            Table(rnd(I, Em).cuda(), "SGD")]
+    parts = []
+    for n in layers:
+        parts += [rnd(n, n // 2).reshape(-1), rnd(n // 2)]
+    parts.append(rnd(E + layers[-1] // 2))
+    dense = torch.cat(parts).cuda()
+    rs = np.random.RandomState(0)
+    u, i = rs.randint(0, U, 4001), rs.randint(0, I, 4001)
+    monkeypatch.delenv("CRB_NEUMF_SCORE_SIMPLE", raising=False)
+    fast = eng.score_pairs_neumf(tabs, dense, len(layers), u, i).cpu().numpy()
+    monkeypatch.setenv("CRB_NEUMF_SCORE_SIMPLE", "1")
+    slow = eng.score_pairs_neumf(tabs, dense, len(layers), u, i).cpu().numpy()
+    assert np.array_equal(fast.view(np.uint32), slow.view(np.uint32))
