@@ -80,11 +80,11 @@ struct DenseApplyArgs {
     float loss_cov;    // loss += loss_cov * (S_r^2 - sum_c xc^2)                (CML: reg / n)
 };
 
-// one warp per row (dim <= 512: up to 4 float4 per lane)
-__global__ void __launch_bounds__(256) dense_table_apply_kernel(DenseApplyArgs a) {
+// one warp per row (dim <= 512: up to 4 float4 per lane); `block` / `n_blocks`: this CTA's position among the CTAs working on the table
+__device__ __forceinline__ void dense_table_apply_rows(const DenseApplyArgs& a, int block, int n_blocks, double* loss_slot) {
     const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t warp = ((int64_t)block * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)n_blocks * blockDim.x) >> 5;
     double loss = 0.0;
     const float msum = a.cov != 0.f ? *a.mean_sum : 0.f;
     for (int64_t r = warp; r < a.T.rows; r += n_warps) {
@@ -142,7 +142,34 @@ __global__ void __launch_bounds__(256) dense_table_apply_kernel(DenseApplyArgs a
             st4(a.T.grad + off, make_float4(0.f, 0.f, 0.f, 0.f));
         }
     }
-    block_sum_to(loss, a.loss_part);
+    // block-level sum of the per-thread loss into *loss_slot
+    __shared__ double sm_l[8];
+    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    if ((threadIdx.x & 31) == 0) sm_l[threadIdx.x >> 5] = loss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += sm_l[k];
+        *loss_slot = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) dense_table_apply_kernel(DenseApplyArgs a) {
+    dense_table_apply_rows(a, blockIdx.x, gridDim.x, a.loss_part + blockIdx.x);
+}
+
+// Up to four tables in ONE launch (NeuMF's four embedding tables, NAIS / SBPR's P, Q and bias, LRML's P and Q): at the batch sizes
+// the reference ships these steps are a chain of microsecond kernels, so every launch removed is a few per cent of the step.  CTAs
+// [first[t], first[t+1]) work on table t.
+struct DenseApplyMulti {
+    DenseApplyArgs t[4];
+    int first[5];
+};
+__global__ void __launch_bounds__(256) dense_tables_apply_kernel(DenseApplyMulti m) {
+    int t = 0;
+#pragma unroll
+    for (int q = 1; q < 4; ++q) t += ((int)blockIdx.x >= m.first[q]) ? 1 : 0;
+    dense_table_apply_rows(m.t[t], blockIdx.x - m.first[t], m.first[t + 1] - m.first[t], m.t[t].loss_part + blockIdx.x);
 }
 
 __device__ __forceinline__ void atomic_add4(float* p, float4 v) {
@@ -586,6 +613,7 @@ extern "C" int crb_clip_rows(crb_handle* h, const float* src, float* dst, int64_
 
 int crb_dense_table_apply(crb_handle* h, const crb_table* T, float* grad, int opt_kind, const OptDev& od, float l2, double* loss_part,
                           int* grid_out, cudaStream_t s);
+int crb_dense_tables_apply(crb_handle* h, int n, const crb_table* const* tables, float* const* grads, int opt_kind, const OptDev& od, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------ TransCF
 // model/ranking/TransCF.py:38-71.  alpha_u = mean of Q over the user's training items (ui_sp_mat, utils/tools.py:100-113: values
@@ -871,6 +899,33 @@ int crb_dense_table_apply(crb_handle* h, const crb_table* T, float* grad, int op
     return CRB_OK;
 }
 
+// several plain (no L2 / covariance term) dense applies in one launch; tables[k] == NULL entries are skipped
+int crb_dense_tables_apply(crb_handle* h, int n, const crb_table* const* tables, float* const* grads, int opt_kind, const OptDev& od, cudaStream_t s) {
+    DenseApplyMulti m;
+    int used = 0, blocks = 0;
+    for (int k = 0; k < n; ++k) {
+        if (!tables[k]) continue;
+        if (used == 4) { crb_set_error("crb_dense_tables_apply: at most four tables"); return CRB_ERR_ARG; }
+        int rc = check_dense_table(tables[k], grads[k], opt_kind, "dense table");
+        if (rc) return rc;
+        DenseApplyArgs& da = m.t[used];
+        da.dim = tables[k]->dim; da.opt_kind = dense_opt_kind(opt_kind); da.opt = od; da.cov = 0.f; da.mean = nullptr; da.mean_sum = nullptr;
+        da.loss_cov = 0.f; da.l2 = 0.f; da.loss_l2 = 0.f;
+        da.T = {tables[k]->w, tables[k]->s1, tables[k]->s2, grads[k], tables[k]->rows}; da.loss_part = h->dense_loss;
+        m.first[used] = blocks;
+        blocks += dgrid(h, tables[k]->rows, 8);
+        ++used;
+    }
+    if (!used) return CRB_OK;
+    for (int k = used; k <= 4; ++k) m.first[k] = blocks;
+    for (int k = used; k < 4; ++k) m.t[k] = m.t[used - 1];
+    if (blocks > 4 * h->loss_blocks) { crb_set_error("crb_dense_tables_apply: grid too large"); return CRB_ERR_ARG; }
+    dense_tables_apply_kernel<<<blocks, 256, 0, s>>>(m);
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ SBPR
 // model/ranking/SBPR.py:38-57.  x_ui = p.q_i + b_i, x_uk (a friend's item), x_uj (unobserved);
 //   loss = sum softplus(-(x_ui - x_uk) / s_uk) + softplus(-(x_uk - x_uj))                                  (:54, utils/tools.py:71)
@@ -990,12 +1045,12 @@ extern "C" int crb_train_step_sbpr(crb_handle* h, const crb_table* P, const crb_
     if ((rc = crb_prof_end(h, s))) return rc;
     double* dp = h->dense_loss;
     const int dk_ = dense_opt_kind(opt_kind);
-    int g1 = 0;
-    if ((rc = crb_dense_table_apply(h, P, gradP, dk_, od, 0.f, dp, &g1, s))) return rc;
-    if ((rc = crb_dense_table_apply(h, Q, gradQ, dk_, od, 0.f, dp, &g1, s))) return rc;
     crb_table B4 = *B;      // the bias vector as a [n/4, 4] table
     B4.rows = B->rows / 4; B4.dim = 4;
-    if ((rc = crb_dense_table_apply(h, &B4, gradB, dk_, od, 0.f, dp, &g1, s))) return rc;
+    const crb_table* tabs3[3] = {P, Q, &B4};
+    float* grads3[3] = {gradP, gradQ, gradB};
+    (void)dp;
+    if ((rc = crb_dense_tables_apply(h, 3, tabs3, grads3, dk_, od, s))) return rc;
     h->step_grid = grid;
     double* ld = (loss_out && crb_is_device_ptr(loss_out)) ? loss_out : h->loss_dev;
     if ((rc = crb_launch_loss_final(h, ld, s))) return rc;

@@ -253,8 +253,7 @@ __global__ void __launch_bounds__(LR_WARPS * 32) lrml_score_kernel(LrmlScoreArgs
 // dense_vector_apply_kernel / crb_dense_table_apply live in train_neumf.cu / train_dense.cu
 int crb_dense_vector_apply(crb_handle* h, float* w, float* s1, float* s2, const float* parts, int n_parts, int n, int opt_kind, const OptDev& od,
                            cudaStream_t s);
-int crb_dense_table_apply(crb_handle* h, const crb_table* T, float* grad, int opt_kind, const OptDev& od, float l2, double* loss_part,
-                          int* grid_out, cudaStream_t s);
+int crb_dense_tables_apply(crb_handle* h, int n, const crb_table* const* tables, float* const* grads, int opt_kind, const OptDev& od, cudaStream_t s);
 
 extern "C" int crb_train_step_lrml(crb_handle* h, const crb_table* P, const crb_table* Q, float* gradP, float* gradQ, float* dense,
                                    float* dense_s1, float* dense_s2, int32_t mem_size, const crb_opt* opt, const int32_t* u, const int32_t* i,
@@ -301,9 +300,9 @@ extern "C" int crb_train_step_lrml(crb_handle* h, const crb_table* P, const crb_
     lrml_step_kernel<<<grid, LR_WARPS * 32, smem, s>>>(a);
     if ((rc = crb_prof_end(h, s))) return rc;
     h->launches++;
-    int g1 = 0;
-    if ((rc = crb_dense_table_apply(h, P, gradP, dk, od, 0.f, h->dense_loss, &g1, s))) return rc;
-    if ((rc = crb_dense_table_apply(h, Q, gradQ, dk, od, 0.f, h->dense_loss, &g1, s))) return rc;
+    const crb_table* tabs2[2] = {P, Q};
+    float* grads2[2] = {gradP, gradQ};
+    if ((rc = crb_dense_tables_apply(h, 2, tabs2, grads2, dk, od, s))) return rc;
     if ((rc = crb_dense_vector_apply(h, dense, dense_s1, dense_s2, h->dense_grad, grid, a.sh.n_dense, dk, od, s))) return rc;
     h->step_grid = grid;
     double* ld = (loss_out && crb_is_device_ptr(loss_out)) ? loss_out : h->loss_dev;

@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(256) nais_dense_apply_kernel(float* w, float* 
 
 int crb_dense_table_apply(crb_handle* h, const crb_table* T, float* grad, int opt_kind, const OptDev& od, float l2, double* loss_part,
                           int* grid_out, cudaStream_t s);
+int crb_dense_tables_apply(crb_handle* h, int n, const crb_table* const* tables, float* const* grads, int opt_kind, const OptDev& od, cudaStream_t s);
 int crb_opt_to_dev(crb_handle* h, const crb_opt* opt, OptDev* out, int* opt_kind, cudaStream_t s);
 
 static int nais_prepare(crb_handle* h, NaisArgs& a, const float* P, const float* Q, const float* bias, const float* dense, int32_t d, int32_t A,
@@ -296,11 +297,11 @@ extern "C" int crb_train_step_nais(crb_handle* h, const crb_table* P, const crb_
     h->launches += 3;
     CRB_CUDA(cudaGetLastError());
     // sparse TF applies on P, Q, bias == dense applies with zero gradient on untouched rows (see train_neumf.cu)
-    if ((rc = crb_dense_table_apply(h, P, gradP, dk, od, 0.f, h->dense_loss, nullptr, s))) return rc;
-    if ((rc = crb_dense_table_apply(h, Q, gradQ, dk, od, 0.f, h->dense_loss, nullptr, s))) return rc;
     crb_table Bt = *B;
     Bt.rows = B->rows / 4; Bt.dim = 4;
-    if ((rc = crb_dense_table_apply(h, &Bt, gradB, dk, od, 0.f, h->dense_loss, nullptr, s))) return rc;
+    const crb_table* tabs3[3] = {P, Q, &Bt};
+    float* grads3[3] = {gradP, gradQ, gradB};
+    if ((rc = crb_dense_tables_apply(h, 3, tabs3, grads3, dk, od, s))) return rc;
     nais_dense_apply_kernel<<<(n_dense + 255) / 256, 256, 0, s>>>(dense, dense_s1, dense_s2, a.dense_part, grid_p, n_dense, dk, od);
     h->launches++;
     h->step_grid = grid_t;

@@ -584,6 +584,7 @@ __global__ void __launch_bounds__(256) mask_seen_kernel(float* scores, const int
 
 // ------------------------------------------------------------------------------------------------ host side
 struct DenseApplyArgsFwd;  // dense table apply lives in train_dense.cu
+int crb_dense_tables_apply(crb_handle* h, int n, const crb_table* const* tables, float* const* grads, int opt_kind, const OptDev& od, cudaStream_t s);
 int crb_dense_table_apply(crb_handle* h, const crb_table* T, float* grad, int opt_kind, const OptDev& od, float l2, double* loss_part,
                           int* grid_out, cudaStream_t s);
 
@@ -649,13 +650,9 @@ extern "C" int crb_train_step_neumf(crb_handle* h, const crb_table* Pg, const cr
     if ((rc = crb_prof_end(h, s))) return rc;
     // embedding tables: dense apply (zero gradient on untouched rows == TF's sparse apply for SGD/Adagrad, and exactly
     // tf.train.AdamOptimizer's dense-in-the-moments sparse apply for Adam)
-    int g1 = 0;
-    double* dp = h->dense_loss;
-    const crb_table* tabs[4] = {Pg, Qg, Pm, Qm};
+    const crb_table* tabs[4] = {Pg, Qg, Pm, Qm};      // NULL entries (the MLP model has no GMF branch) are skipped
     float* grads[4] = {gPg, gQg, gPm, gQm};
-    for (int k = gmf ? 0 : 2; k < 4; ++k) {
-        if ((rc = crb_dense_table_apply(h, tabs[k], grads[k], dk, od, 0.f, dp, &g1, s))) return rc;
-    }
+    if ((rc = crb_dense_tables_apply(h, 4, tabs, grads, dk, od, s))) return rc;
     dense_vector_apply_kernel<<<(a.sh.n_dense + 255) / 256, 256, 0, s>>>(dense, dense_s1, dense_s2, h->dense_grad, grid, a.sh.n_dense, dk, od);
     h->step_grid = grid;
     h->launches += 2;
