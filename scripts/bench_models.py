@@ -4,6 +4,7 @@ reference's CPU path beside it (bench.py's cpu_baseline leg: reference-algorithm
 fp32, a bounded sample of steps).
     python scripts/bench_models.py > profiles/r01_models.json          (GPU box; ~1-2 minutes)
 Not a bench.py line: bench.py measures the headline metric; this is the measurement of the rows widened into."""
+import gc
 import json
 import logging
 import math
@@ -92,12 +93,14 @@ def main():
         setup = time.perf_counter() - t0
         m.train_model()                                   # warm epoch (allocations, first-launch costs)
         torch.cuda.synchronize()
+        gc.collect()                                      # keep a generation-2 collection of earlier models' objects out of the timed regions
         t0 = time.perf_counter()
         loss = m.train_model()
         torch.cuda.synchronize()
         epoch_s = time.perf_counter() - t0
         m.test_model_loo()
         torch.cuda.synchronize()
+        gc.collect()
         t0 = time.perf_counter()
         HR, MRR, NDCG = m.test_model_loo()
         torch.cuda.synchronize()
