@@ -5,7 +5,6 @@ are local); the item table Q is row-sharded by `item % world` and every rank map
 CUDA IPC.  torch.distributed (NCCL) is used for exactly two things: exchanging the 64-byte IPC handles once, and the per-step
 barrier (a one-element all-reduce enqueued on the compute stream).  There is no data-path collective."""
 import ctypes as C
-import math
 
 import numpy as np
 import torch

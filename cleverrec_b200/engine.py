@@ -2,7 +2,6 @@
 one call into libcleverrec_b200.so.  This is the replacement for the reference's `tf.Session` (main.py:39-45):
 the mirror classes under cleverrec_b200/model call it where the reference calls `self.sess.run`."""
 import ctypes as C
-import math
 
 import numpy as np
 import torch

@@ -1,6 +1,5 @@
 # coding: utf-8
 " FISM: Factorized Item Similarity Model (2013) -- mirror of the reference model/ranking/FISM.py (pairwise branch). "
-import math
 
 import numpy as np
 import torch
