@@ -180,3 +180,31 @@ def test_fullrank_top20_tensor_core_equals_exact_and_torch(world):
     assert (top.values[:, -1] - sc[:64, -1].double()).abs().max().item() <= 1e-5
     same = (torch.sort(top.indices, dim=1).values == srt[:64]).float().mean().item()
     assert same >= 0.99                                                 # the tf32/fp32 matmul of torch may swap near-ties at rank 20
+
+
+def test_sampled_candidate_scores_at_full_size(world, monkeypatch):
+    """test_model_loo's scoring at the full table sizes: the tiled pair scorer (rows staged by cp.async) returns the bits of the
+    thread-per-pair scorer, both are the fp32 dot products of the pairs (fp64 torch on the same rows), and the per-user top-20 of
+    crb_topk_segments is torch.topk's on the same scores."""
+    from cleverrec_b200 import _lib
+    eng, dev, keys, pu, pi, rowptr = world
+    g = torch.Generator(device=dev).manual_seed(9)
+    P = torch.randn(USERS, DIM, device=dev, generator=g) * 0.1
+    Q = torch.randn(ITEMS, DIM, device=dev, generator=g) * 0.1
+    n_users, n_cand = 20000, 101
+    u = torch.randint(0, USERS, (n_users,), device=dev, generator=g, dtype=torch.int32).repeat_interleave(n_cand)
+    i = torch.randint(0, ITEMS, (n_users * n_cand,), device=dev, generator=g, dtype=torch.int32)
+    monkeypatch.delenv("CRB_SCORE_PAIRS_SIMPLE", raising=False)
+    tiled = eng.score_pairs(_lib.SCORE_DOT, P, Q, u, i)
+    monkeypatch.setenv("CRB_SCORE_PAIRS_SIMPLE", "1")
+    simple = eng.score_pairs(_lib.SCORE_DOT, P, Q, u, i)
+    monkeypatch.delenv("CRB_SCORE_PAIRS_SIMPLE", raising=False)
+    assert torch.equal(tiled.view(torch.int32), simple.view(torch.int32))
+    ref = (P[u.long()].double() * Q[i.long()].double()).sum(1)
+    assert (tiled.double() - ref).abs().max().item() <= 2e-6
+    seg = torch.arange(n_users + 1, device=dev, dtype=torch.int64) * n_cand
+    top = eng.topk_segments(tiled, seg, 20).long()
+    want = torch.topk(tiled.reshape(n_users, n_cand), 20, dim=1)
+    got_scores = torch.gather(tiled.reshape(n_users, n_cand), 1, top)
+    assert torch.equal(got_scores, want.values)                          # same score sequence; ids may differ only inside exact ties
+    assert bool(((got_scores[:, :-1] > got_scores[:, 1:]) | (top[:, :-1] < top[:, 1:])).all())   # ties: ascending position
