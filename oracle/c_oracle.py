@@ -48,3 +48,17 @@ def fullrank_topk(kind, P, Q, users, seen_rowptr, seen_cols, K, hvec=None, hist_
     lib().oracle_fullrank_topk(C.c_int(kind), _p(P), _p(Q), _p(hvec), C.c_int64(n_items), C.c_int(P.shape[1]), _p(users), _p(hist_users),
                                C.c_int64(users.shape[0]), _p(seen_rowptr), _p(seen_cols), C.c_int(K), _p(items), _p(scores))
     return items, scores
+
+
+def score_pairs_neumf(Pg, Qg, Pm, Qm, dense, n_layers, u, i):
+    """Canonical NeuMF (Pg / Qg given) or MLP (Pg = Qg = None) logit of flattened pairs; `dense` = packed W_l, b_l, h."""
+    Pm, Qm = np.ascontiguousarray(Pm, np.float32), np.ascontiguousarray(Qm, np.float32)
+    E = 0 if Pg is None else Pg.shape[1]
+    if E:
+        Pg, Qg = np.ascontiguousarray(Pg, np.float32), np.ascontiguousarray(Qg, np.float32)
+    dense = np.ascontiguousarray(dense, np.float32)
+    u, i = np.ascontiguousarray(u, np.int32), np.ascontiguousarray(i, np.int32)
+    out = np.empty(u.shape[0], np.float32)
+    lib().oracle_score_pairs_neumf(_p(Pg) if E else None, _p(Qg) if E else None, _p(Pm), _p(Qm), _p(dense), C.c_int(E), C.c_int(Pm.shape[1]),
+                                   C.c_int(n_layers), _p(u), _p(i), C.c_int64(u.shape[0]), _p(out))
+    return out

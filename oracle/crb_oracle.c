@@ -8,6 +8,7 @@
  *   oracle_score_pairs    <- each model's `_predict` on flattened pairs: BPR.py:49, GMF.py:43 (the logit),
  *                            CML.py:82, FISM.py:53; fed as in model/RankingRecommender.py:257-278
  *   oracle_topk_segments  <- np.argsort(-pre_scores_u)[:topk[-1]]            RankingRecommender.py:281-288
+ *   oracle_score_pairs_neumf <- NeuMF._get_logits (NeuMF.py:63-85; MLP.py:44-53 when E = 0) on flattened pairs, the logit
  *   oracle_fullrank_topk  <- matmul + np.argsort + skip ui_train[u] + first K RankingRecommender.py:203-240
  * Tie rule: score descending (ascending for distance models), index ascending; np.argsort's
  * default introsort gives the same order whenever scores are distinct.
@@ -100,4 +101,42 @@ void oracle_fullrank_topk(int kind, const float* P, const float* Q, const float*
         }
     }
     free(c);
+}
+
+/* NeuMF / MLP logit of flattened pairs in the canonical order of csrc/train_neumf.cu: per layer acc = b[o], then
+ * acc = fma(x[k], W[k][o], acc) for k ascending, ReLU; logit = one chain over the rounded GMF products p*q times h[0..E), then
+ * over the tower output times h[E..).  `dense` packs W_l [n_in, n_in/2] row-major, b_l per layer, then h.  E = 0: the MLP model. */
+void oracle_score_pairs_neumf(const float* Pg, const float* Qg, const float* Pm, const float* Qm, const float* dense, int E, int Em,
+                              int n_layers, const int32_t* u, const int32_t* it, int64_t n, float* out) {
+    const int L0 = 2 * Em;
+    float* x = (float*)malloc(sizeof(float) * (size_t)L0);
+    float* z = (float*)malloc(sizeof(float) * (size_t)L0);
+    for (int64_t t = 0; t < n; ++t) {
+        const int64_t uu = u[t], ii = it[t];
+        for (int k = 0; k < L0; ++k) x[k] = k < Em ? Pm[uu * Em + k] : Qm[ii * Em + (k - Em)];
+        int off = 0, ni = L0;
+        for (int l = 0; l < n_layers; ++l) {
+            const int no = ni / 2;
+            const float* W = dense + off;
+            const float* b = W + (size_t)ni * no;
+            for (int o = 0; o < no; ++o) {
+                float acc = b[o];
+                for (int k = 0; k < ni; ++k) acc = fmaf(x[k], W[(size_t)k * no + o], acc);
+                z[o] = acc > 0.f ? acc : 0.f;
+            }
+            memcpy(x, z, sizeof(float) * (size_t)no);
+            off += ni * no + no;
+            ni = no;
+        }
+        const float* h = dense + off;
+        float acc = 0.f;
+        for (int k = 0; k < E; ++k) {
+            volatile float pq = Pg[uu * E + k] * Qg[ii * E + k];
+            acc = fmaf(pq, h[k], acc);
+        }
+        for (int k = 0; k < ni; ++k) acc = fmaf(x[k], h[E + k], acc);
+        out[t] = acc;
+    }
+    free(x);
+    free(z);
 }

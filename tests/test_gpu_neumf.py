@@ -130,3 +130,8 @@ def test_neumf_warp_scorer_is_bit_identical_to_the_thread_scorer(eng, layers, E,
     monkeypatch.setenv("CRB_NEUMF_SCORE_SIMPLE", "1")
     slow = eng.score_pairs_neumf(tabs, dense, len(layers), u, i).cpu().numpy()
     assert np.array_equal(fast.view(np.uint32), slow.view(np.uint32))
+    # ... and both are the C oracle's canonical logit, bit for bit (oracle/crb_oracle.c::oracle_score_pairs_neumf)
+    from oracle import c_oracle as O
+    want = O.score_pairs_neumf(tabs[0].w.cpu().numpy() if E else None, tabs[1].w.cpu().numpy() if E else None, tabs[2].w.cpu().numpy(),
+                               tabs[3].w.cpu().numpy(), dense.cpu().numpy(), len(layers), u, i)
+    assert np.array_equal(fast.view(np.uint32), want.view(np.uint32))

@@ -117,3 +117,22 @@ def test_tf1_optimizer_hand_examples():
         before = float(var["w"][1])
         opt.step(var, {"w": torch.tensor([[2.0], [0.0]])}, {"w": torch.tensor([0])})
         assert (float(var["w"][1]) != before) == moves
+
+
+def test_c_oracle_neumf_logit_is_the_restated_graph():
+    """oracle/crb_oracle.c::oracle_score_pairs_neumf (the canonical fp32 order the GPU scorers are pinned to bit for bit) against the
+    restated TF graph (oracle/tf1_restatement.py::neumf_logits, NeuMF.py:63-85) in fp64: NeuMF and the MLP model (E = 0)."""
+    from oracle import c_oracle as O
+    rs = np.random.RandomState(2)
+    U, I, E, layers = 9, 11, 8, [32, 16, 8]
+    Em = layers[0] // 2
+    p = {"P_gmf": rs.randn(U, E), "Q_gmf": rs.randn(I, E), "P_mlp": rs.randn(U, Em), "Q_mlp": rs.randn(I, Em)}
+    for k, n in enumerate(layers):
+        p["W_%d" % k], p["b_%d" % k] = rs.randn(n, n // 2) * 0.3, rs.randn(n // 2) * 0.3
+    p["h_neumf"] = rs.randn(E + layers[-1] // 2)
+    p = {k: v.astype(np.float32) for k, v in p.items()}
+    u, i = rs.randint(0, U, 50), rs.randint(0, I, 50)
+    dense = np.concatenate([np.concatenate([p["W_%d" % k].ravel(), p["b_%d" % k]]) for k in range(len(layers))] + [p["h_neumf"]])
+    got = O.score_pairs_neumf(p["P_gmf"], p["Q_gmf"], p["P_mlp"], p["Q_mlp"], dense, len(layers), u, i)
+    want, _ = T.neumf_logits({k: torch.tensor(v).double() for k, v in p.items()}, torch.tensor(u), torch.tensor(i), len(layers))
+    np.testing.assert_allclose(got, want.numpy(), rtol=2e-5, atol=2e-5)
