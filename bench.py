@@ -215,11 +215,13 @@ def run_ours(args, w):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_steps(first_step, n, losses):
+    phase_ms = {} if args.phases else None
+
+    def run_steps(first_step, n, losses, phases=None):
         if sharded is None:
             eng.train_epoch_bpr(P, Q, opt, 7, 0, first_step * B, B, n, R, reg, losses)
         else:
-            sharded.run_steps(n, reg, neg_ratio=R, seed=7, epoch=0, first=first_step * B, batch=B, loss_out=losses)
+            sharded.run_steps(n, reg, neg_ratio=R, seed=7, epoch=0, first=first_step * B, batch=B, loss_out=losses, phase_ms=phases)
 
     # ---- device-resident run: value ----
     losses = torch.zeros(steps_total, dtype=torch.float64, device=dev)
@@ -232,7 +234,7 @@ def run_ours(args, w):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    run_steps(args.warmup, args.steps, losses[args.warmup:])
+    run_steps(args.warmup, args.steps, losses[args.warmup:], phase_ms)
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -304,7 +306,8 @@ def run_ours(args, w):
         assert bool(torch.isfinite(host_losses).all()) and float(host_losses.min()) > 0
         e2e_path = "ShardedBPR.run_steps(feeds=...): the epoch loop over host feed arrays, per-step H2D feed + per-step D2H loss, feeds staged one step ahead"
     e2e_value = world * B * n_e2e / max_over_ranks(e2e_s)
-    overflow = sharded.inbox_overflowed() if sharded is not None else False
+    if sharded is not None:
+        sharded.check()   # raises if a cross-rank barrier timed out or the sampler gave up on a row
 
     # ---- roofline of the dominant kernel (K3 fused step) ----
     hbm, tf, which = peaks()
@@ -315,6 +318,8 @@ def run_ours(args, w):
                 "frac": (achieved / hbm) if achieved else None, "traffic": None, "peak_source": which,
                 "algorithmic_bytes_per_launch": per_triplet * B, "kernel_ms": k3_avg_ms, "kernel_share_of_step": k3_avg_ms / ms_step,
                 "step_frac": per_triplet * B / (ms_step / 1000.0) / 1e9 / hbm}
+    if phase_ms:
+        roofline["phase_ms_per_step"] = {k: v / phase_ms["steps"] for k, v in phase_ms.items() if k != "steps"}
     if world > 1 and k3_n:
         # per triplet two item rows are fetched and two gradients returned, (N-1)/N of them over NVLink.  Every GPU's
         # ingress carries the rows it fetches plus the gradients its peers send it (and its egress the mirror image): 16*d bytes per
@@ -431,7 +436,7 @@ def run_ours(args, w):
                            "neg_ratio": R, "item_popularity": args.item_popularity, "optimizer": opt_kind, "adam_mode": adam_mode if opt_kind == "Adam" else None, "reg": reg,
                            "l2_policy": "inputs larger than L2 (tables %.1f GB vs 126 MB L2)" % ((users + items) * dim * 4 / 1e9),
                            "parallelism": ("single GPU" if world == 1 else "%d ranks: users partitioned, item table row-sharded (item %% N), rows and gradients "
-                                           "over NVLink peer memory, NCCL only as the step barrier" % world), "inbox_overflow": overflow,
+                                           "over NVLink peer memory (per-rank de-duplicated), flag barriers in peer memory, no data-path collective" % world),
                            "setup_s": round(t_setup, 1)},
                 "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 8, "steps": n_e2e, "path": e2e_path,
                         "blocking_per_step_value": e2e_sync},
@@ -456,6 +461,7 @@ def main():
     ap.add_argument("--item-popularity", dest="item_popularity", default="uniform", choices=["uniform", "zipf"],
                     help="popularity of the positives' items in the synthetic history (zipf = Zipf(1.0): hub rows repeat ~10^4 times per batch)")
     ap.add_argument("--sharded", action="store_true", help="use the multi-GPU code path even at N=1 (experiments)")
+    ap.add_argument("--phases", action="store_true", help="multi-GPU path: split every step into compute / barrier / apply with CUDA events (rank 0)")
     ap.add_argument("--users", type=int, default=0, help="override the workload's user count (experiments)")
     ap.add_argument("--items", type=int, default=0)
     ap.add_argument("--batch", type=int, default=0)

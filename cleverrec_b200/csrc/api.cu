@@ -56,7 +56,7 @@ extern "C" int crb_create(int device, crb_handle** out) {
 void crb_alt_swap(crb_handle* h) {
 #define CRB_SWAP(a, b) do { auto t__ = (a); (a) = (b); (b) = t__; } while (0)
     for (int k = 0; k < 3; ++k) { CRB_SWAP(h->idx[k], h->alt.idx[k]); CRB_SWAP(h->rank[k], h->alt.rank[k]); }
-    for (int k = 0; k < 2; ++k) { CRB_SWAP(h->meta[k], h->alt.meta[k]); CRB_SWAP(h->meta_rows[k], h->alt.meta_rows[k]); }
+    for (int k = 0; k < 2; ++k) { CRB_SWAP(h->meta[k], h->alt.meta[k]); CRB_SWAP(h->meta_rows[k], h->alt.meta_rows[k]); CRB_SWAP(h->sb[k], h->alt.sb[k]); }
     CRB_SWAP(h->ctr, h->alt.ctr);
     CRB_SWAP(h->dup_rows, h->alt.dup_rows);
     CRB_SWAP(h->work, h->alt.work);
@@ -67,6 +67,7 @@ void crb_alt_swap(crb_handle* h) {
 
 static void free_alt_ws(crb_handle* h) {
     for (int k = 0; k < 3; ++k) { cudaFree(h->alt.idx[k]); h->alt.idx[k] = nullptr; cudaFree(h->alt.rank[k]); h->alt.rank[k] = nullptr; }
+    for (int k = 0; k < 2; ++k) { cudaFree(h->alt.sb[k]); h->alt.sb[k] = nullptr; }
     cudaFree(h->alt.dup_rows); h->alt.dup_rows = nullptr;
     cudaFree(h->alt.work); h->alt.work = nullptr;
     cudaFree(h->alt.multi); h->alt.multi = nullptr;
@@ -94,6 +95,7 @@ int crb_alt_reserve(crb_handle* h, cudaStream_t s) {
             CRB_CUDA(cudaMalloc(&h->alt.idx[k], sizeof(int32_t) * nb));
             CRB_CUDA(cudaMalloc(&h->alt.rank[k], sizeof(uint32_t) * nb));
         }
+        for (int k = 0; k < 2; ++k) CRB_CUDA(cudaMalloc(&h->alt.sb[k], sizeof(int32_t) * nb));
         CRB_CUDA(cudaMalloc(&h->alt.dup_rows, sizeof(crb_dup_row) * (occ / 2 + 1)));
         CRB_CUDA(cudaMalloc(&h->alt.work, sizeof(crb_work) * (occ / 2 + occ / CRB_DUP_CHUNK + 2)));
         CRB_CUDA(cudaMalloc(&h->alt.multi, sizeof(unsigned int) * (occ / CRB_DUP_CHUNK + 2)));
@@ -123,6 +125,8 @@ static void free_ws(crb_handle* h) {
     cudaFree(h->dup_src); h->dup_src = nullptr;
     for (int k = 0; k < 4; ++k) { cudaFree(h->idx[k]); h->idx[k] = nullptr; }
     for (int k = 0; k < 3; ++k) { cudaFree(h->rank[k]); h->rank[k] = nullptr; }
+    for (int k = 0; k < 2; ++k) { cudaFree(h->sb[k]); h->sb[k] = nullptr; }
+    cudaFree(h->stage); h->stage = nullptr; h->stage_rows = 0; h->stage_dim = 0;
     cudaFree(h->yv); h->yv = nullptr;
     cudaFree(h->dup_grad); h->dup_grad = nullptr;
     cudaFree(h->dup_t); h->dup_t = nullptr;
@@ -269,6 +273,7 @@ int crb_ws_reserve(crb_handle* h, int64_t batch, int32_t dim, int64_t steps, cud
     const int64_t occ = 3 * nb;
     for (int k = 0; k < 4; ++k) CRB_CUDA(cudaMalloc(&h->idx[k], sizeof(int32_t) * nb));
     for (int k = 0; k < 3; ++k) CRB_CUDA(cudaMalloc(&h->rank[k], sizeof(uint32_t) * nb));
+    for (int k = 0; k < 2; ++k) CRB_CUDA(cudaMalloc(&h->sb[k], sizeof(int32_t) * nb));
     CRB_CUDA(cudaMalloc(&h->yv, sizeof(float) * nb));
     CRB_CUDA(cudaMalloc(&h->dup_grad, sizeof(float) * occ * nd));
     CRB_CUDA(cudaMalloc(&h->dup_t, sizeof(uint32_t) * occ));

@@ -98,6 +98,10 @@ struct crb_handle {
     int32_t* idx[4];       // sampled u, i, j, nbr (or staged host feeds)
     float* yv;             // sampled / staged labels
     uint32_t* rank[3];     // occurrence rank of u, i, j inside their row
+    int32_t* sb[2];        // multi-GPU step: per triplet, first gradient slot of the i / j item row if it repeats in the batch, else -1
+    float* stage;          // multi-GPU step: [stage_rows, stage_dim] local copies of repeated item rows (row = first gradient slot)
+    int64_t stage_rows;
+    int32_t stage_dim;
     float* dup_grad;       // [3*cap_batch, dim] gradient slots of duplicate occurrences
     uint32_t* dup_t;       // [3*cap_batch] triplet index of each slot (deterministic order)
     uint32_t* dup_src;     // [3*cap_batch] source row of each slot when gradients are summed in place (DupArgs::dup_src)
@@ -137,6 +141,7 @@ struct crb_handle {
     struct {
         int32_t* idx[3];
         uint32_t* rank[3];
+        int32_t* sb[2];
         unsigned long long* meta[2];
         int64_t meta_rows[2];
         crb_step_ctr* ctr;

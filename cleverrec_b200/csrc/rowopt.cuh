@@ -194,6 +194,32 @@ __device__ __forceinline__ void block_loss_store(double v, double* block_loss) {
     }
 }
 
+// Multi-GPU step (train_sharded.cu): where the gradient of an ITEM row goes.  The item table is row-sharded (owner = item % n_ranks,
+// local row = item / n_ranks); every owner holds a DIRECT-MAPPED inbox with one gradient slot per (source rank, local row):
+// grad[owner] is [n_ranks][rows_cap][dim], stamp[owner] is [n_ranks][rows_cap] and holds the step whose gradient the slot carries.
+// A source rank therefore sends at most ONE gradient per item row and step (duplicates are summed locally first), needs no slot
+// reservation, and the inbox can neither overflow nor has to be cleared.  All pointers are valid on THIS device (CUDA IPC).
+struct ShardSend {
+    int n_ranks, rank;
+    int64_t rows_cap;
+    uint32_t stamp;                        // = opt.step of the current step (>= 1; slots are created zeroed)
+    float* grad[CRB_MAX_RANKS];
+    uint32_t* stamps[CRB_MAX_RANKS];
+};
+
+template <int LANES, int VPL>
+__device__ __forceinline__ void shard_send(const ShardSend& sh, int32_t item, const float4* g, int dim, int gl) {
+    const int owner = item % sh.n_ranks;
+    const int64_t e = (int64_t)sh.rank * sh.rows_cap + item / sh.n_ranks;
+    float* dst = sh.grad[owner] + e * dim;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        const int c = (gl + LANES * v) * 4;
+        if (c < dim) st4(dst + c, g[v]);
+    }
+    if (gl == 0) sh.stamps[owner][e] = sh.stamp;
+}
+
 // Arguments of the duplicate-row kernels (shared by all row-sparse steps)
 struct DupArgs {
     TableDev tab[2];
@@ -211,6 +237,7 @@ struct DupArgs {
     // gradients that already sit in a buffer are summed from where they are instead of being copied into slots first.
     const uint32_t* dup_src = nullptr;
     const float* src_grad = nullptr;
+    ShardSend send;   // SHARD kernels only: rows of table 1 are GLOBAL item ids whose summed gradient is sent to the owner
 };
 
 int crb_launch_dup_pipeline(crb_handle* h, const DupArgs& a, int opt_kind, cudaStream_t s);

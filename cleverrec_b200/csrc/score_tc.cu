@@ -677,12 +677,13 @@ static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 int crb_score_topk_tc(crb_handle* h, int32_t kind, const float* P, const float* Q, const float* hvec, int64_t n_items, int32_t dim,
                       const int32_t* users, const int32_t* hist_users, int64_t n_users, int32_t K, int32_t* topk_items,
                       float* topk_scores, cudaStream_t s) {
-    CRB_CHECK_ARG(K >= 1 && K <= 32, "tensor-core path supports K <= 32");
+    CRB_CHECK_ARG(K >= 1, "K");
     const bool aug = kind == CRB_SCORE_SQDIST || kind == CRB_SCORE_DOT_BIAS;
     const int d_pad = (int)round_up(dim + (aug ? 2 : 0), 64);
     const int kb = d_pad / 64;
-    if (kb > TC_MAX_KB) {
-        // operand tile would not fit in shared memory: this size runs on the exact kernel (documented in DESIGN.md)
+    if (kb > TC_MAX_KB || K > 32) {
+        // operand tile would not fit in shared memory, or K is beyond the candidate lists' certificate (the reference's argsort takes
+        // any K, e.g. topk=[10,20,50]): this call runs on the exact kernel, K <= 256 (documented in DESIGN.md)
         h->topk_stats[0] = 0; h->topk_stats[1] = n_users; h->topk_stats[2] = 0;
         return crb_launch_fullrank_exact(h, kind, P, Q, hvec, n_items, dim, users, hist_users, nullptr, n_users, K, topk_items, topk_scores, s);
     }

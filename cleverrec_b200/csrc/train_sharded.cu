@@ -1,39 +1,47 @@
 // Multi-GPU BPR step over NVLink peer memory.  One process per GPU.  Users (rows of P, their histories, their
 // sampling) are partitioned across ranks; the item table Q is row-sharded (owner = item % G, local row = item / G) and every
-// rank maps every shard through CUDA IPC, so no NCCL all-to-all, no id de-duplication and no host synchronisation is needed:
+// rank maps every shard and every inbox through CUDA IPC, so there is no NCCL all-to-all and no host synchronisation.
 //
-//   phase 1  shard_step_kernel   each rank, for its own B triplets: gathers p_u locally and q_i, q_j STRAIGHT FROM THE OWNER'S HBM
-//                                (peer loads over NVLink), forward/backward, applies the user row locally (same multiplicity
-//                                machinery as the single-GPU step) and writes the two item gradients into the OWNER's inbox:
-//                                one system-scope atomic claims a slot, then 128-bit peer stores.
-//   -- cross-rank barrier (a one-element NCCL all-reduce enqueued on the same stream by the caller) --
-//   phase 2  inbox_apply_kernel  each owner de-duplicates its inbox (count -> assign), applies rows that arrived once in place and
-//                                reduces the others through the duplicate-slot pipeline: one optimizer apply per unique row with
-//                                the gradient summed over ALL ranks -- the semantics of one TF step on the union batch.
-//   -- barrier --
+// What crosses the wire is de-duplicated PER RANK first: an item row that a rank's batch draws more than once is fetched from its
+// owner once and its gradients are summed locally before one peer store (2^21 item draws over 2M items: 62 % distinct rows).
+//
+//   phase 0  (auxiliary stream, overlaps the previous step's phase 2)  sample, count every user / item row's occurrences,
+//            give repeated rows gradient slots (K1 / K2 of the single-GPU step) and resolve each triplet's item sources
+//   phase 1a item_fetch_kernel   every REPEATED item row: one peer load from the owner into a local staging row
+//   phase 1b shard_step_kernel   per triplet: p_u locally, q_i / q_j from the staging buffer (repeated rows) or STRAIGHT FROM THE
+//                                OWNER'S HBM (rows that occur once: peer loads requested two iterations ahead), forward/backward,
+//                                the user row applied locally (multiplicity machinery of the single-GPU step), the gradient of a
+//                                once-occurring item row stored straight into the owner's DIRECT-MAPPED inbox
+//                                (slot = (source rank, local row): no reservation, no atomics), a repeated row's into a local slot
+//   phase 1c dup_reduce_kernel<SHARD>  user rows: summed and applied as on one GPU; item rows: summed in triplet order and SENT once
+//   -- crb_shard_barrier (flag barrier in peer memory, on the stream) --
+//   phase 2  inbox_apply_kernel  one pass over the owner's rows: the <= G gradients that arrived for a row are summed in source-rank
+//                                order and applied once -- the semantics of one TF step on the union batch; CRB_ADAM_TF1 rows that
+//                                received nothing take their decay-only step (remote readers never need a row's `last`)
+//   -- crb_shard_barrier --
 #include <cstddef>
 #include <stdlib.h>
 
-#include "rowopt.cuh"
+#include "dup.cuh"
 
 struct ShardDev {
     int n_ranks, rank;
-    int64_t inbox_cap;
     TableDev q[CRB_MAX_RANKS];
-    float* inbox_grad[CRB_MAX_RANKS];
-    int32_t* inbox_row[CRB_MAX_RANKS];
-    uint32_t* inbox_key[CRB_MAX_RANKS];
-    unsigned int* inbox_cnt[CRB_MAX_RANKS];   // [0] entries, [1] overflow flag
+    ShardSend send;
 };
 
 struct ShardStepArgs {
     TableDev P;
     unsigned long long* metaU;
+    unsigned long long* metaI;   // indexed by GLOBAL item id: this rank's multiplicities
     ShardDev sh;
     const int32_t* u;   // local user rows
     const int32_t* i;   // GLOBAL item ids
     const int32_t* j;
-    const uint32_t* rk_u;
+    const int32_t* sbi; // per triplet: first gradient slot (= staging row) of item i / j when the row repeats in this rank's batch, else -1
+    const int32_t* sbj;
+    const uint32_t* rk[3];
+    const float* stage;
     int64_t batch;
     int dim;
     float reg;
@@ -44,36 +52,57 @@ struct ShardStepArgs {
     int debug;   // experiments only (-DSH_DEBUG_SWITCHES + CRB_SH_DEBUG): 1 = no gradient sends, 2 = item rows read from the local shard, 3 = both
 };
 
-#define SH_CHUNK 32u   // inbox slots a warp reserves per system-scope atomic (unused ones stay holes: row = -1)
+// ------------------------------------------------------------------------------------------------ phase 0: item sources
+__global__ void __launch_bounds__(256) shard_resolve_kernel(const unsigned long long* __restrict__ metaI, const int32_t* __restrict__ i,
+                                                            const int32_t* __restrict__ j, int64_t batch, int32_t* __restrict__ sbi,
+                                                            int32_t* __restrict__ sbj) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < batch; t += stride) {
+        const unsigned long long mi = metaI[i[t]], mj = metaI[j[t]];
+        sbi[t] = (uint32_t)mi > 1u ? (int32_t)(mi >> 32) : -1;
+        sbj[t] = (uint32_t)mj > 1u ? (int32_t)(mj >> 32) : -1;
+    }
+}
 
-// Takes one slot of the owner's inbox for every active group of the warp and stores the gradient there.  Slots are handed out
-// from per-warp reservations of SH_CHUNK (one system-scope atomic on the owner's counter per 32 gradients instead of one per
-// gradient: the single hot counter was the bottleneck of the first version).
+// ------------------------------------------------------------------------------------------------ phase 1a: fetch repeated rows
+// One lane group per duplicate-row descriptor; item rows (table 1) are copied from the owner's shard to stage[base].  The loop is
+// two deep: the next descriptor's row is requested before the current one is stored.
 template <int LANES, int VPL>
-__device__ __forceinline__ void send_item_grad(const ShardDev& sh, unsigned int* s_base, unsigned int* s_left, int owner, int32_t local_row,
-                                               uint32_t key, const float4* g, int dim, int gl, int sub, bool active) {
-    constexpr int GPW = 32 / LANES;
-    unsigned int slot = 0xFFFFFFFFu;
+__global__ void __launch_bounds__(256) item_fetch_kernel(ShardDev sh, const crb_dup_row* __restrict__ dup_rows, const crb_step_ctr* ctr,
+                                                         float* __restrict__ stage, int dim) {
+    const int gl = threadIdx.x % LANES;
+    const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / LANES;
+    const int64_t n = ctr->dup_rows;
+    const int G = sh.n_ranks;
+    for (int64_t k = group; k < n; k += n_groups) {
+        const crb_dup_row d = dup_rows[k];
+        if (d.table != 1) continue;
+        const float* src = sh.q[d.row % G].w + (int64_t)(d.row / G) * dim;
+        float* dst = stage + (int64_t)d.base * dim;
+        float4 r[VPL];
 #pragma unroll
-    for (int q = 0; q < GPW; ++q) {
-        if (sub == q && gl == 0 && active) {
-            if (s_left[owner] == 0u) { s_base[owner] = atomicAdd_system(sh.inbox_cnt[owner], SH_CHUNK); s_left[owner] = SH_CHUNK; }
-            slot = s_base[owner]++;
-            s_left[owner]--;
+        for (int v = 0; v < VPL; ++v) {
+            const int c = (gl + LANES * v) * 4;
+            if (c < dim) r[v] = ld4(src + c);
         }
-        __syncwarp();
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const int c = (gl + LANES * v) * 4;
+            if (c < dim) st4(dst + c, r[v]);
+        }
     }
-    slot = __shfl_sync(0xffffffffu, slot, sub * LANES);
-    if (!active) return;
-    if ((int64_t)slot >= sh.inbox_cap) {
-        if (gl == 0) atomicExch_system(sh.inbox_cnt[owner] + 1, 1u);   // overflow: reported by crb_shard_inbox_overflow
-        return;
-    }
-    if (gl == 0) { sh.inbox_key[owner][slot] = key; sh.inbox_row[owner][slot] = local_row; }
+}
+
+// ------------------------------------------------------------------------------------------------ phase 1b: the fused step
+template <int LANES, int VPL>
+__device__ __forceinline__ void item_row_load(RowRegs<LANES, VPL>& r, const ShardStepArgs& a, int32_t item, int32_t sb, int dim, int gl) {
+    const int G = a.sh.n_ranks;
+    const float* src = sb >= 0 ? a.stage + (int64_t)sb * dim : a.sh.q[item % G].w + (int64_t)(item / G) * dim;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         const int c = (gl + LANES * v) * 4;
-        if (c < dim) st4(sh.inbox_grad[owner] + (int64_t)slot * dim + c, g[v]);
+        r.w[v] = c < dim ? ld4(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
@@ -83,60 +112,48 @@ __global__ void __launch_bounds__(256, 3) shard_step_kernel(ShardStepArgs a) {
     const int lane = threadIdx.x & 31, gl = lane % LANES, sub = lane / LANES;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int G = a.sh.n_ranks;
-#ifdef SH_DEBUG_SWITCHES
-    const int RG = (a.debug & 2) ? 1 : G;              // debug: every read goes to the local shard
-    const int RO = (a.debug & 2) ? a.sh.rank : 0;
-#define SH_Q(item) a.sh.q[(a.debug & 2) ? RO : (item) % RG]
-#define SH_SEND (!(a.debug & 1))
-#else
-#define SH_Q(item) a.sh.q[(item) % G]
-#define SH_SEND true
-#endif
-    __shared__ unsigned int s_resv[8][2][CRB_MAX_RANKS];   // per warp: next slot / slots left of the current reservation per owner
-    if (lane < CRB_MAX_RANKS) { s_resv[threadIdx.x >> 5][0][lane] = 0u; s_resv[threadIdx.x >> 5][1][lane] = 0u; }
-    __syncwarp();
-    unsigned int* s_base = s_resv[threadIdx.x >> 5][0];
-    unsigned int* s_left = s_resv[threadIdx.x >> 5][1];
     double loss_acc = 0.0;
-    // Software pipeline.  Item rows mostly live on other GPUs (2-3 us away over NVLink), so they are requested TWO iterations ahead;
-    // the local user row one iteration ahead; indices three iterations ahead.  Out-of-range iterations clamp to the last triplet
-    // (loads only).
+    // Software pipeline.  Once-occurring item rows live on other GPUs (2-3 us away over NVLink), so item rows are requested TWO
+    // iterations ahead; the local user row one iteration ahead; indices and item sources three iterations ahead.  Out-of-range
+    // iterations clamp to the last triplet (loads only).
     const int64_t stride = n_warps * GPW;
     const int64_t base0 = warp * GPW;
     auto clampt = [&](int64_t b) { const int64_t t_ = b + sub; return t_ < a.batch ? t_ : a.batch - 1; };
-    int32_t u1, i1, j1;          // indices of iteration n+1 (its item rows are in flight, its user row is about to be)
-    int32_t u2, i2, j2;          // indices of iteration n+2
-    int32_t nu, ni, nj;          // indices of the current iteration
-    { const int64_t t0 = clampt(base0); nu = a.u[t0]; ni = a.i[t0]; nj = a.j[t0]; }
-    { const int64_t t1 = clampt(base0 + stride); u1 = a.u[t1]; i1 = a.i[t1]; j1 = a.j[t1]; }
-    { const int64_t t2 = clampt(base0 + 2 * stride); u2 = a.u[t2]; i2 = a.i[t2]; j2 = a.j[t2]; }
+    int32_t u1, i1, j1;                  // indices of iteration n+1 (its item rows are in flight, its user row is about to be)
+    int32_t u2, i2, j2, si2, sj2;        // indices and item sources of iteration n+2
+    int32_t nu, ni, nj;                  // indices of the current iteration
     RowRegs<LANES, VPL> nru, nri, nrj, fri, frj;
-    row_load_w<LANES, VPL>(nri, SH_Q(ni), ni / G, a.dim, gl);
-    row_load_w<LANES, VPL>(nrj, SH_Q(nj), nj / G, a.dim, gl);
-    row_load_w<LANES, VPL>(fri, SH_Q(i1), i1 / G, a.dim, gl);
-    row_load_w<LANES, VPL>(frj, SH_Q(j1), j1 / G, a.dim, gl);
-    row_load_w<LANES, VPL>(nru, a.P, nu, a.dim, gl);
+    {
+        const int64_t t0 = clampt(base0), t1 = clampt(base0 + stride), t2 = clampt(base0 + 2 * stride);
+        nu = a.u[t0]; ni = a.i[t0]; nj = a.j[t0];
+        u1 = a.u[t1]; i1 = a.i[t1]; j1 = a.j[t1];
+        u2 = a.u[t2]; i2 = a.i[t2]; j2 = a.j[t2]; si2 = a.sbi[t2]; sj2 = a.sbj[t2];
+        item_row_load<LANES, VPL>(nri, a, ni, a.sbi[t0], a.dim, gl);
+        item_row_load<LANES, VPL>(nrj, a, nj, a.sbj[t0], a.dim, gl);
+        item_row_load<LANES, VPL>(fri, a, i1, a.sbi[t1], a.dim, gl);
+        item_row_load<LANES, VPL>(frj, a, j1, a.sbj[t1], a.dim, gl);
+        row_load_w<LANES, VPL>(nru, a.P, nu, a.dim, gl);
+    }
     for (int64_t base = base0; base < a.batch; base += stride) {
         const int64_t t = base + sub;
         const bool active = t < a.batch;
         const int64_t tt = active ? t : a.batch - 1;
         const int32_t u = nu, i = ni, j = nj;
         RowRegs<LANES, VPL> ru = nru, ri = nri, rj = nrj;
-        // rotate the pipeline: iteration n+1's item rows were requested last time; request n+2's (peer loads when the owner is
-        // another rank) and n+1's user row
+        // this triplet's own slots (re-read: cheaper than carrying them through the pipeline registers)
+        const int32_t sbi = a.sbi[tt], sbj = a.sbj[tt];
+        const uint32_t rki = a.rk[1][tt], rkj = a.rk[2][tt];
+        // rotate the pipeline: iteration n+1's item rows were requested last time; request n+2's and n+1's user row
         nu = u1; ni = i1; nj = j1;
         nri = fri; nrj = frj;
         row_load_w<LANES, VPL>(nru, a.P, nu, a.dim, gl);
-        row_load_w<LANES, VPL>(fri, SH_Q(i2), i2 / G, a.dim, gl);
-        row_load_w<LANES, VPL>(frj, SH_Q(j2), j2 / G, a.dim, gl);
+        item_row_load<LANES, VPL>(fri, a, i2, si2, a.dim, gl);
+        item_row_load<LANES, VPL>(frj, a, j2, sj2, a.dim, gl);
         u1 = u2; i1 = i2; j1 = j2;
-        { const int64_t t3 = clampt(base + 3 * stride); u2 = a.u[t3]; i2 = a.i[t3]; j2 = a.j[t3]; }
-        const int oi = i % G, oj = j % G;
-        const int32_t li = i / G, lj = j / G;
+        { const int64_t t3 = clampt(base + 3 * stride); u2 = a.u[t3]; i2 = a.i[t3]; j2 = a.j[t3]; si2 = a.sbi[t3]; sj2 = a.sbj[t3]; }
         const unsigned long long mu = a.metaU[u];
-        // item rows are always current at a step boundary (the owner decays its whole shard in phase 2), so only the local user
-        // row can have missed steps to replay
+        // item rows are always current at a step boundary (the owner brings its whole shard to the step in phase 2), so only the
+        // local user row can have missed steps to replay
         ru.last = OptTraits<OPT>::replay ? a.P.last[u] : 0;
         const bool su = (uint32_t)mu == 1u || replay_pending<OPT>(ru.last, a.opt);
         if (OptTraits<OPT>::has_s1 && su) row_load_state<LANES, VPL, OPT>(ru, a.P, u, a.dim, gl);
@@ -162,58 +179,162 @@ __global__ void __launch_bounds__(256, 3) shard_step_kernel(ShardStepArgs a) {
             gi[v] = make_float4(fmaf(g, p.x, a.reg * qi.x), fmaf(g, p.y, a.reg * qi.y), fmaf(g, p.z, a.reg * qi.z), fmaf(g, p.w, a.reg * qi.w));
             gj[v] = make_float4(fmaf(-g, p.x, a.reg * qj.x), fmaf(-g, p.y, a.reg * qj.y), fmaf(-g, p.z, a.reg * qj.z), fmaf(-g, p.w, a.reg * qj.w));
         }
-        if (active)
-            emit_row<LANES, VPL, OPT>(ru, gu, a.P, a.metaU, u, mu, a.rk_u[t], (uint32_t)t, 0u, a.dim, gl, a.opt, a.dup_grad, a.dup_t);
-        // ordering key of the occurrence: unique and identical from run to run -> deterministic duplicate sums at the owner
-        const uint32_t kbase = ((uint32_t)a.sh.rank * (uint32_t)a.batch + (uint32_t)tt) << 1;
-        if (SH_SEND) {
-            send_item_grad<LANES, VPL>(a.sh, s_base, s_left, oi, li, kbase, gi, a.dim, gl, sub, active);
-            send_item_grad<LANES, VPL>(a.sh, s_base, s_left, oj, lj, kbase | 1u, gj, a.dim, gl, sub, active);
+        if (!active) continue;
+        emit_row<LANES, VPL, OPT>(ru, gu, a.P, a.metaU, u, mu, a.rk[0][t], (uint32_t)t, 0u, a.dim, gl, a.opt, a.dup_grad, a.dup_t);
+        // item gradients: a once-occurring row goes straight into its owner's inbox; a repeated row's into its local slot (the slot
+        // key orders the local sum by triplet: identical from run to run)
+#pragma unroll
+        for (int role = 1; role <= 2; ++role) {
+            const int32_t item = role == 1 ? i : j, sb = role == 1 ? sbi : sbj;
+            const float4* gv = role == 1 ? gi : gj;
+            if (sb < 0) {
+#ifdef SH_DEBUG_SWITCHES
+                if (a.debug & 1) continue;
+#endif
+                shard_send<LANES, VPL>(a.sh.send, item, gv, a.dim, gl);
+                if (gl == 0) a.metaI[item] = 0ULL;
+            } else {
+                const uint32_t slot = (uint32_t)sb + (role == 1 ? rki : rkj);
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    const int c = (gl + LANES * v) * 4;
+                    if (c < a.dim) st4(a.dup_grad + (int64_t)slot * a.dim + c, gv[v]);
+                }
+                if (gl == 0) a.dup_t[slot] = ((uint32_t)t << 2) | (uint32_t)role;
+            }
         }
     }
-    __threadfence_system();   // peer stores visible before the kernel retires (the barrier that follows orders them across ranks)
     block_loss_store(loss_acc, a.block_loss);
 }
 
-struct InboxArgs {
-    unsigned long long* meta;
-    const int32_t* row;
-    const uint32_t* key;
-    const unsigned int* cnt;
-    const uint32_t* rk;
-    int64_t cap;
-    uint32_t* dup_src;
-    uint32_t* dup_t;
+// ------------------------------------------------------------------------------------------------ phase 2: the owner's pass
+struct InboxApplyArgs {
+    TableDev Q;           // this rank's shard
+    int64_t rows;         // its rows
+    int64_t rows_cap;
+    int n_ranks;
+    int dim;
+    uint32_t stamp;
+    const float* grad;    // [n_ranks][rows_cap][dim]
+    const uint32_t* stamps;
+    OptDev opt;
 };
 
-// Phase 2 never copies a gradient: every row that received at least one gradient owns a slot range (assign_kernel with
-// alloc_rank 0), this kernel -- one thread per inbox entry -- only records WHERE the row's gradients are (slot -> inbox entry, plus
-// the ordering key), and dup_reduce_kernel sums them straight out of the inbox (DupArgs::dup_src) in key order and applies the
-// optimizer once per row.  A gradient that crossed NVLink is read from HBM exactly once.
-__global__ void __launch_bounds__(256) inbox_index_kernel(InboxArgs a) {
-    int64_t n = *a.cnt;
-    if (n > a.cap) n = a.cap;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
-        const int32_t row = a.row[e];
-        if (row < 0) continue;   // hole of a partly used reservation
-        const uint32_t slot = (uint32_t)(a.meta[row] >> 32) + a.rk[e];
-        a.dup_src[slot] = (uint32_t)e;
-        a.dup_t[slot] = a.key[e];
+template <int LANES, int VPL, int OPT>
+__global__ void __launch_bounds__(256) inbox_apply_kernel(InboxApplyArgs a) {
+    const int lane = threadIdx.x & 31, gl = lane % LANES;
+    const uint32_t gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << (lane - gl));
+    const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / LANES;
+    // whole warps leave together (a row index is per lane group; the shuffles below are group-wide)
+    for (int64_t row = group; row < a.rows; row += n_groups) {
+        // lane s of the group looks at source rank s (LANES >= 8 >= n_ranks)
+        const bool mine = gl < a.n_ranks && a.stamps[(int64_t)gl * a.rows_cap + row] == a.stamp;
+        uint32_t present = __ballot_sync(gmask, mine);
+        present = LANES == 32 ? present : (present >> (lane - gl)) & ((1u << LANES) - 1u);
+        RowRegs<LANES, VPL> r;
+        r.last = OptTraits<OPT>::replay ? a.Q.last[row] : 0;
+        if (present == 0u) {
+            // nothing arrived: CRB_ADAM_TF1 rows decay (tf.train.AdamOptimizer moves every row every step); others are untouched
+            if (OptTraits<OPT>::replay && r.last != 0 && r.last < a.opt.step) {
+                row_load_w<LANES, VPL>(r, a.Q, row, a.dim, gl);
+                row_load_state<LANES, VPL, OPT>(r, a.Q, row, a.dim, gl);
+                row_replay<LANES, VPL, OPT>(r, a.opt, a.opt.step + 1);
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    const int c = (gl + LANES * v) * 4;
+                    if (c >= a.dim) continue;
+                    st4(a.Q.w + row * a.dim + c, r.w[v]);
+                    st4(a.Q.s1 + row * a.dim + c, r.s1[v]);
+                    st4(a.Q.s2 + row * a.dim + c, r.s2[v]);
+                }
+                if (gl == 0) a.Q.last[row] = a.opt.step;
+            }
+            continue;
+        }
+        row_load_w<LANES, VPL>(r, a.Q, row, a.dim, gl);
+        row_load_state<LANES, VPL, OPT>(r, a.Q, row, a.dim, gl);
+        // all arrived gradients are requested together (one round trip), then added in source-rank order
+        float4 acc[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        constexpr int SB = VPL == 1 ? 8 : 4;
+        for (int s0 = 0; s0 < a.n_ranks; s0 += SB) {
+            float4 g[SB][VPL];
+#pragma unroll
+            for (int q = 0; q < SB; ++q) {
+                const bool on = s0 + q < a.n_ranks && ((present >> (s0 + q)) & 1u);
+                const float* src = a.grad + ((int64_t)(s0 + q) * a.rows_cap + row) * a.dim;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    const int c = (gl + LANES * v) * 4;
+                    g[q][v] = (on && c < a.dim) ? ld4(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < SB; ++q) {
+                if (!(s0 + q < a.n_ranks && ((present >> (s0 + q)) & 1u))) continue;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) { acc[v].x += g[q][v].x; acc[v].y += g[q][v].y; acc[v].z += g[q][v].z; acc[v].w += g[q][v].w; }
+            }
+        }
+        row_replay<LANES, VPL, OPT>(r, a.opt, a.opt.step);
+        row_apply_store<LANES, VPL, OPT>(r, acc, a.Q, row, a.dim, gl, a.opt);
     }
 }
 
-static int shard_to_dev(const crb_shard* sh, ShardDev* d) {
+// ------------------------------------------------------------------------------------------------ flag barrier in peer memory
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+struct BarrierArgs {
+    int n_ranks, rank;
+    uint32_t* flags[CRB_MAX_RANKS];
+    uint32_t ticket;
+    unsigned long long timeout_ns;
+};
+
+__global__ void shard_barrier_kernel(BarrierArgs a) {
+    const int r = threadIdx.x;
+    if (r >= a.n_ranks) return;
+    // everything this stream did before the barrier (peer stores included) is complete: the kernel boundary orders it; the fence
+    // makes it visible system-wide before the flag that announces it
+    __threadfence_system();
+    volatile uint32_t* theirs = a.flags[r] + a.rank;
+    *theirs = a.ticket;
+    __threadfence_system();
+    volatile uint32_t* mine = a.flags[a.rank] + r;
+    const unsigned long long t0 = global_ns();
+    while ((int32_t)(*mine - a.ticket) < 0) {
+        if (global_ns() - t0 > a.timeout_ns) { a.flags[a.rank][CRB_SHARD_ERR] = 1u; break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static int shard_to_dev(const crb_shard* sh, ShardDev* d, uint32_t stamp) {
     CRB_CHECK_ARG(sh && sh->n_ranks >= 1 && sh->n_ranks <= CRB_MAX_RANKS && sh->rank >= 0 && sh->rank < sh->n_ranks, "shard descriptor");
-    CRB_CHECK_ARG(sh->inbox_cap > 0, "inbox capacity");
-    d->n_ranks = sh->n_ranks; d->rank = sh->rank; d->inbox_cap = sh->inbox_cap;
+    CRB_CHECK_ARG(sh->rows_cap > 0, "shard descriptor: rows_cap");
+    d->n_ranks = sh->n_ranks; d->rank = sh->rank;
+    d->send.n_ranks = sh->n_ranks; d->send.rank = sh->rank; d->send.rows_cap = sh->rows_cap; d->send.stamp = stamp;
+    for (int r = 0; r < CRB_MAX_RANKS; ++r) { d->send.grad[r] = nullptr; d->send.stamps[r] = nullptr; d->q[r] = TableDev{nullptr, nullptr, nullptr, nullptr}; }
     for (int r = 0; r < sh->n_ranks; ++r) {
-        CRB_CHECK_ARG(sh->q[r].w && sh->inbox_grad[r] && sh->inbox_row[r] && sh->inbox_key[r] && sh->inbox_cnt[r], "shard descriptor: null peer pointer");
+        CRB_CHECK_ARG(sh->q[r].w && sh->inbox_grad[r] && sh->inbox_stamp[r] && sh->flags[r], "shard descriptor: null peer pointer");
+        CRB_CHECK_ARG(sh->q[r].rows <= sh->rows_cap, "shard descriptor: rows_cap smaller than a shard");
         d->q[r] = crb_to_dev(&sh->q[r]);
-        d->inbox_grad[r] = sh->inbox_grad[r]; d->inbox_row[r] = sh->inbox_row[r]; d->inbox_key[r] = sh->inbox_key[r];
-        d->inbox_cnt[r] = sh->inbox_cnt[r];
+        d->send.grad[r] = sh->inbox_grad[r]; d->send.stamps[r] = sh->inbox_stamp[r];
     }
     return CRB_OK;
+}
+
+static int64_t shard_items(const crb_shard* sh) {
+    int64_t n = 0;
+    for (int r = 0; r < sh->n_ranks; ++r) n += sh->q[r].rows;
+    return n;
 }
 
 template <typename K>
@@ -231,6 +352,12 @@ static int one_wave(crb_handle* h, K kernel, int64_t groups, int gpb) {
 template <int LANES, int VPL>
 static int launch_shard_t(crb_handle* h, const ShardStepArgs& a, int opt_kind, cudaStream_t s) {
     const int gpb = 256 / LANES;
+    int rc;
+    // phase 1a: repeated item rows -> staging buffer (grid: every SM full, the loop covers the descriptor list)
+    item_fetch_kernel<LANES, VPL><<<h->sm_count * 8, 256, 0, s>>>(a.sh, h->dup_rows, h->ctr, h->stage, a.dim);
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    if ((rc = crb_prof_begin(h, s))) return rc;
 #define CRB_SH_CASE(O)                                                                          \
     case O: {                                                                                   \
         const int grid = one_wave(h, shard_step_kernel<LANES, VPL, O>, a.batch, gpb);           \
@@ -240,6 +367,40 @@ static int launch_shard_t(crb_handle* h, const ShardStepArgs& a, int opt_kind, c
     }
     switch (opt_kind) { CRB_SH_CASE(OPT_SGD) CRB_SH_CASE(OPT_ADAGRAD) CRB_SH_CASE(OPT_ADAM_LAZY) CRB_SH_CASE(OPT_ADAM_TF1) }
 #undef CRB_SH_CASE
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    if ((rc = crb_prof_end(h, s))) return rc;
+    // phase 1c: duplicate rows -- users applied locally, items summed and sent
+    DupArgs d;
+    d.tab[0] = a.P; d.tab[1] = a.P;   // table 1 rows never reach an apply in SHARD kernels
+    d.meta[0] = a.metaU; d.meta[1] = a.metaI;
+    d.dim = a.dim; d.opt = a.opt;
+    d.dup_rows = h->dup_rows; d.work = h->work; d.multi = h->multi;
+    d.dup_grad = h->dup_grad; d.dup_t = h->dup_t; d.partial = h->partial; d.ctr = h->ctr;
+    d.send = a.sh.send;
+    const int grid = h->sm_count * 4;
+#define CRB_SHDUP_CASE(O)                                                        \
+    case O:                                                                      \
+        dup_reduce_kernel<LANES, VPL, O, true><<<grid, 256, 0, s>>>(d);          \
+        dup_final_kernel<LANES, VPL, O, true><<<h->sm_count, 256, 0, s>>>(d);    \
+        break;
+    switch (opt_kind) { CRB_SHDUP_CASE(OPT_SGD) CRB_SHDUP_CASE(OPT_ADAGRAD) CRB_SHDUP_CASE(OPT_ADAM_LAZY) CRB_SHDUP_CASE(OPT_ADAM_TF1) }
+#undef CRB_SHDUP_CASE
+    h->launches += 2;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}
+
+template <int LANES, int VPL>
+static int launch_inbox_t(crb_handle* h, const InboxApplyArgs& a, int opt_kind, cudaStream_t s) {
+    const int gpb = 256 / LANES;
+    int64_t grid = (a.rows + gpb - 1) / gpb;
+    const int64_t cap = (int64_t)h->sm_count * 32;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+#define CRB_IN_CASE(O) case O: inbox_apply_kernel<LANES, VPL, O><<<(int)grid, 256, 0, s>>>(a); break;
+    switch (opt_kind) { CRB_IN_CASE(OPT_SGD) CRB_IN_CASE(OPT_ADAGRAD) CRB_IN_CASE(OPT_ADAM_LAZY) CRB_IN_CASE(OPT_ADAM_TF1) }
+#undef CRB_IN_CASE
     h->launches++;
     CRB_CUDA(cudaGetLastError());
     return CRB_OK;
@@ -252,33 +413,45 @@ static int launch_shard_t(crb_handle* h, const ShardStepArgs& a, int opt_kind, c
      : (dim) <= 256 ? FN<32, 2>(__VA_ARGS__)                             \
                     : FN<32, 4>(__VA_ARGS__))
 
-static void fill_dup(crb_handle* h, DupArgs* d, const TableDev& t0, const TableDev& t1, int dim, const OptDev& od) {
-    d->tab[0] = t0; d->tab[1] = t1;
-    d->meta[0] = h->meta[0]; d->meta[1] = h->meta[1];
-    d->dim = dim; d->opt = od;
-    d->dup_rows = h->dup_rows; d->work = h->work; d->multi = h->multi;
-    d->dup_grad = h->dup_grad; d->dup_t = h->dup_t; d->partial = h->partial; d->ctr = h->ctr;
+static int stage_reserve(crb_handle* h, int32_t dim, cudaStream_t s) {
+    const int64_t rows = 3 * h->cap_batch;
+    if (h->stage && h->stage_rows >= rows && h->stage_dim >= dim) return CRB_OK;
+    CRB_CUDA(cudaStreamSynchronize(s));
+    cudaFree(h->stage);
+    h->stage = nullptr; h->stage_rows = 0; h->stage_dim = 0;
+    CRB_CUDA(cudaMalloc(&h->stage, sizeof(float) * (size_t)rows * dim));
+    h->stage_rows = rows; h->stage_dim = dim;
+    return CRB_OK;
 }
 
-// Optional phase 0: sample rows [first, first+batch) of this rank's epoch and count / assign the user rows NOW, on the handle's
-// auxiliary stream, into the alternate copy of the step state -- typically called right after crb_shard_step_compute of the
-// previous step, so that it overlaps that step's barriers and inbox phase (none of it touches the tables).  The next
-// crb_shard_step_compute with u == NULL and the same (seed, epoch, first, neg_ratio, batch) consumes it.  reserve_rows >= batch
-// sizes the workspace once for both phases (pass the inbox capacity) so that no later call reallocates it under the prepared step.
-// With feed_u / feed_i / feed_j (HOST or DEVICE int32 [batch]: the caller's own triplets, local user rows and global item ids) the
-// step is staged from them instead of being sampled -- the host -> device copies then run on the copy stream beside the previous
-// step's kernels; (seed, epoch, first, neg_ratio, batch) only serve as the ticket the consuming crb_shard_step_compute presents.
+// everything of a step that depends only on its indices: occurrence counts (unless the sampler counted), slot assignment, item sources
+static int shard_index_work(crb_handle* h, const int32_t* u, const int32_t* i, const int32_t* j, int64_t batch, bool counted, cudaStream_t s) {
+    const int32_t* idx[3] = {u, i, j};
+    const int role_table[3] = {0, 1, 1};
+    int rc;
+    if (!counted && (rc = crb_count_rows(h, batch, 3, idx, role_table, s))) return rc;
+    if ((rc = crb_launch_assign(h, batch, 3, idx, role_table, s))) return rc;
+    int64_t blocks = (batch + 255) / 256;
+    const int64_t capb = (int64_t)h->sm_count * 16;
+    shard_resolve_kernel<<<(int)(blocks < capb ? blocks : capb), 256, 0, s>>>(h->meta[1], i, j, batch, h->sb[0], h->sb[1]);
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}
+
 extern "C" int crb_shard_step_prepare(crb_handle* h, const crb_table* P, uint64_t seed, uint32_t epoch, int64_t first, int32_t neg_ratio,
-                                      int64_t batch, int64_t reserve_rows, const int32_t* feed_u, const int32_t* feed_i,
+                                      int64_t batch, int64_t n_items, const int32_t* feed_u, const int32_t* feed_i,
                                       const int32_t* feed_j, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     CRB_CHECK_ARG(h && P, "null argument");
-    CRB_CHECK_ARG(batch > 0, "batch");
+    CRB_CHECK_ARG(batch > 0 && batch < 0x20000000LL && n_items > 0, "batch / n_items");
     CRB_CUDA(cudaSetDevice(h->device));
     int rc;
-    if ((rc = crb_ws_reserve(h, reserve_rows > batch ? reserve_rows : batch, P->dim, 4, s))) return rc;
+    if ((rc = crb_ws_reserve(h, batch, P->dim, 4, s))) return rc;
     if ((rc = crb_meta_reserve(h, 0, P->rows, s))) return rc;
+    if ((rc = crb_meta_reserve(h, 1, n_items, s))) return rc;
     if ((rc = crb_alt_reserve(h, s))) return rc;
+    if ((rc = stage_reserve(h, P->dim, s))) return rc;
     cudaStream_t ps = h->aux_stream;
     // the alternate copy is free once the last compute that used it has finished; a freshly zeroed meta needs the caller's stream
     CRB_CUDA(cudaEventRecord(h->ev_entry, s));
@@ -286,16 +459,17 @@ extern "C" int crb_shard_step_prepare(crb_handle* h, const crb_table* P, uint64_
     crb_alt_swap(h);
     struct Restore { crb_handle* h; ~Restore() { if (h->alt_active) crb_alt_swap(h); } } restore{h};
     if ((rc = crb_zero_step_counters(h, ps))) return rc;
+    bool counted = false;
     if (feed_u) {
         CRB_CHECK_ARG(feed_i && feed_j, "null index feed");
         const int32_t* src[3] = {feed_u, feed_i, feed_j};
         for (int q = 0; q < 3; ++q)
             CRB_CUDA(cudaMemcpyAsync(h->idx[q], src[q], sizeof(int32_t) * batch, crb_is_device_ptr(src[q]) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ps));
-    } else if ((rc = crb_launch_sample_pairwise(h, seed, epoch, first, batch, neg_ratio, h->idx[0], h->idx[1], h->idx[2], nullptr, false, ps))) return rc;
-    const int32_t* idx[3] = {h->idx[0], nullptr, nullptr};
-    const int role_table[3] = {0, 0, 0};
-    if ((rc = crb_count_rows(h, batch, 1, idx, role_table, ps))) return rc;
-    if ((rc = crb_launch_assign(h, batch, 1, idx, role_table, ps))) return rc;
+    } else {
+        if ((rc = crb_launch_sample_pairwise(h, seed, epoch, first, batch, neg_ratio, h->idx[0], h->idx[1], h->idx[2], nullptr, true, ps))) return rc;
+        counted = true;
+    }
+    if ((rc = shard_index_work(h, h->idx[0], h->idx[1], h->idx[2], batch, counted, ps))) return rc;
     CRB_CUDA(cudaEventRecord(h->ev_prep[1], ps));
     h->prep_valid = 1; h->prep_seed = seed; h->prep_epoch = epoch; h->prep_first = first; h->prep_batch = batch; h->prep_neg_ratio = neg_ratio;
     return CRB_OK;
@@ -308,57 +482,55 @@ extern "C" int crb_shard_step_compute(crb_handle* h, const crb_table* P, const c
                                       int64_t batch, float reg, double* loss_out, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     CRB_CHECK_ARG(h && P && shard, "null argument");
-    CRB_CHECK_ARG(batch > 0 && (int64_t)shard->n_ranks * batch < 0x20000000LL, "batch");
+    CRB_CHECK_ARG(batch > 0 && batch < 0x20000000LL, "batch");
     OptDev od;
     int opt_kind = 0;
     int rc = crb_opt_to_dev(h, opt, &od, &opt_kind, s);
     if (rc) return rc;
     if ((rc = crb_table_check(P, opt_kind, "P"))) return rc;
     ShardStepArgs a;
-    if ((rc = shard_to_dev(shard, &a.sh))) return rc;
+    if ((rc = shard_to_dev(shard, &a.sh, (uint32_t)od.step))) return rc;
     CRB_CHECK_ARG(shard->q[shard->rank].dim == P->dim, "P.dim != Q.dim");
+    const int64_t n_items = shard_items(shard);
     CRB_CUDA(cudaSetDevice(h->device));
     if ((rc = crb_ws_reserve(h, batch, P->dim, 4, s))) return rc;
     if ((rc = crb_meta_reserve(h, 0, P->rows, s))) return rc;
+    if ((rc = crb_meta_reserve(h, 1, n_items, s))) return rc;
+    if ((rc = stage_reserve(h, P->dim, s))) return rc;
     const bool prepared = !u && h->prep_valid && h->prep_seed == seed && h->prep_epoch == epoch && h->prep_first == first &&
                           h->prep_batch == batch && h->prep_neg_ratio == neg_ratio;
     struct Restore { crb_handle* h; ~Restore() { if (h->alt_active) crb_alt_swap(h); } } restore{h};
     if (prepared) {
         h->prep_valid = 0;
         CRB_CUDA(cudaStreamWaitEvent(s, h->ev_prep[1], 0));
-        crb_alt_swap(h);   // K3 / K4 / K5 below read the prepared copy
+        crb_alt_swap(h);   // the kernels below read the prepared copy
     } else if ((rc = crb_zero_step_counters(h, s))) return rc;
     const int32_t *du = u, *di = i, *dj = j;
     if (prepared) {
         du = h->idx[0]; di = h->idx[1]; dj = h->idx[2];
-    } else if (!u) {
-        if ((rc = crb_launch_sample_pairwise(h, seed, epoch, first, batch, neg_ratio, h->idx[0], h->idx[1], h->idx[2], nullptr, false, s))) return rc;
-        du = h->idx[0]; di = h->idx[1]; dj = h->idx[2];
     } else {
-        CRB_CHECK_ARG(i && j, "null index feed");
-        if (!crb_is_device_ptr(u)) { CRB_CUDA(cudaMemcpyAsync(h->idx[0], u, 4 * batch, cudaMemcpyHostToDevice, s)); du = h->idx[0]; }
-        if (!crb_is_device_ptr(i)) { CRB_CUDA(cudaMemcpyAsync(h->idx[1], i, 4 * batch, cudaMemcpyHostToDevice, s)); di = h->idx[1]; }
-        if (!crb_is_device_ptr(j)) { CRB_CUDA(cudaMemcpyAsync(h->idx[2], j, 4 * batch, cudaMemcpyHostToDevice, s)); dj = h->idx[2]; }
+        bool counted = false;
+        if (!u) {
+            if ((rc = crb_launch_sample_pairwise(h, seed, epoch, first, batch, neg_ratio, h->idx[0], h->idx[1], h->idx[2], nullptr, true, s))) return rc;
+            du = h->idx[0]; di = h->idx[1]; dj = h->idx[2];
+            counted = true;
+        } else {
+            CRB_CHECK_ARG(i && j, "null index feed");
+            if (!crb_is_device_ptr(u)) { CRB_CUDA(cudaMemcpyAsync(h->idx[0], u, 4 * batch, cudaMemcpyHostToDevice, s)); du = h->idx[0]; }
+            if (!crb_is_device_ptr(i)) { CRB_CUDA(cudaMemcpyAsync(h->idx[1], i, 4 * batch, cudaMemcpyHostToDevice, s)); di = h->idx[1]; }
+            if (!crb_is_device_ptr(j)) { CRB_CUDA(cudaMemcpyAsync(h->idx[2], j, 4 * batch, cudaMemcpyHostToDevice, s)); dj = h->idx[2]; }
+        }
+        if ((rc = shard_index_work(h, du, di, dj, batch, counted, s))) return rc;
     }
-    const int32_t* idx[3] = {du, nullptr, nullptr};
-    const int role_table[3] = {0, 0, 0};
-    if (!prepared) {
-        if ((rc = crb_count_rows(h, batch, 1, idx, role_table, s))) return rc;
-        if ((rc = crb_launch_assign(h, batch, 1, idx, role_table, s))) return rc;
-    }
-    a.P = crb_to_dev(P); a.metaU = h->meta[0]; a.u = du; a.i = di; a.j = dj; a.rk_u = h->rank[0];
+    a.P = crb_to_dev(P); a.metaU = h->meta[0]; a.metaI = h->meta[1]; a.u = du; a.i = di; a.j = dj; a.sbi = h->sb[0]; a.sbj = h->sb[1];
+    a.rk[0] = h->rank[0]; a.rk[1] = h->rank[1]; a.rk[2] = h->rank[2]; a.stage = h->stage;
     a.batch = batch; a.dim = P->dim; a.reg = reg; a.opt = od; a.dup_grad = h->dup_grad; a.dup_t = h->dup_t; a.block_loss = h->block_loss;
 #ifdef SH_DEBUG_SWITCHES
     a.debug = getenv("CRB_SH_DEBUG") ? atoi(getenv("CRB_SH_DEBUG")) : 0;
 #else
     a.debug = 0;
 #endif
-    if ((rc = crb_prof_begin(h, s))) return rc;
     if ((rc = CRB_DIM_DISPATCH(a.dim, launch_shard_t, h, a, opt_kind, s))) return rc;
-    if ((rc = crb_prof_end(h, s))) return rc;
-    DupArgs d;
-    fill_dup(h, &d, a.P, a.P, a.dim, od);
-    if ((rc = crb_launch_dup_pipeline(h, d, opt_kind, s))) return rc;
     double* ld = (loss_out && crb_is_device_ptr(loss_out)) ? loss_out : h->loss_dev;
     if ((rc = crb_launch_loss_final(h, ld, s))) return rc;
     if (loss_out && !crb_is_device_ptr(loss_out)) {
@@ -368,7 +540,7 @@ extern "C" int crb_shard_step_compute(crb_handle* h, const crb_table* P, const c
     return CRB_OK;
 }
 
-// phase 2 (after the cross-rank barrier): reduce + apply this rank's inbox, then empty it.
+// phase 2 (after the cross-rank barrier): sum + apply what arrived for each of this rank's rows.
 extern "C" int crb_shard_apply_inbox(crb_handle* h, const crb_shard* shard, const crb_opt* opt, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     CRB_CHECK_ARG(h && shard, "null argument");
@@ -377,48 +549,68 @@ extern "C" int crb_shard_apply_inbox(crb_handle* h, const crb_shard* shard, cons
     int rc = crb_opt_to_dev(h, opt, &od, &opt_kind, s);
     if (rc) return rc;
     ShardDev sd;
-    if ((rc = shard_to_dev(shard, &sd))) return rc;
+    if ((rc = shard_to_dev(shard, &sd, (uint32_t)od.step))) return rc;
     const crb_table* Q = &shard->q[shard->rank];
     if ((rc = crb_table_check(Q, opt_kind, "Q shard"))) return rc;
     CRB_CUDA(cudaSetDevice(h->device));
-    const int64_t cap = shard->inbox_cap;
-    if ((rc = crb_ws_reserve(h, cap, Q->dim, 4, s))) return rc;
-    if ((rc = crb_meta_reserve(h, 1, Q->rows, s))) return rc;
-    if ((rc = crb_zero_step_counters(h, s))) return rc;
-    const int r = shard->rank;
-    const int32_t* idx[3] = {sd.inbox_row[r], nullptr, nullptr};
-    const int role_table[3] = {1, 0, 0};
-    if ((rc = crb_count_rows(h, cap, 1, idx, role_table, s, sd.inbox_cnt[r]))) return rc;
-    if ((rc = crb_launch_assign(h, cap, 1, idx, role_table, s, sd.inbox_cnt[r], /*every_row=*/true))) return rc;
-    InboxArgs a;
-    a.meta = h->meta[1]; a.row = sd.inbox_row[r]; a.key = sd.inbox_key[r]; a.cnt = sd.inbox_cnt[r];
-    a.rk = h->rank[0]; a.cap = cap; a.dup_src = h->dup_src; a.dup_t = h->dup_t;
-    {
-        int64_t blocks = (cap + 255) / 256, capb = (int64_t)h->sm_count * 16;
-        inbox_index_kernel<<<(int)(blocks < capb ? blocks : capb), 256, 0, s>>>(a);
-        h->launches++;
-        CRB_CUDA(cudaGetLastError());
-    }
-    DupArgs d;
-    fill_dup(h, &d, sd.q[r], sd.q[r], Q->dim, od);
-    d.dup_src = h->dup_src;
-    d.src_grad = sd.inbox_grad[r];
-    if ((rc = crb_launch_dup_pipeline(h, d, opt_kind, s))) return rc;
-    // CRB_ADAM_TF1: bring every row of the shard to this step (rows not touched now take their decay-only step), so that the next
-    // step's readers -- local or over NVLink -- never need a row's `last` (a dependent 4-byte peer load cost 2.3 ms per step)
-    if ((rc = crb_adam_flush(h, Q, opt, stream))) return rc;
-    // overflow flag is sticky until read by crb_shard_inbox_overflow; the entry counter is reset for the next step
-    CRB_CUDA(cudaMemsetAsync(sd.inbox_cnt[r], 0, sizeof(unsigned int), s));
-    CRB_CUDA(cudaMemsetAsync(sd.inbox_row[r], 0xFF, sizeof(int32_t) * (size_t)cap, s));   // every slot is a hole until written
+    InboxApplyArgs a;
+    a.Q = sd.q[shard->rank]; a.rows = Q->rows; a.rows_cap = shard->rows_cap; a.n_ranks = shard->n_ranks; a.dim = Q->dim;
+    a.stamp = (uint32_t)od.step; a.grad = shard->inbox_grad[shard->rank]; a.stamps = shard->inbox_stamp[shard->rank]; a.opt = od;
+    return CRB_DIM_DISPATCH(a.dim, launch_inbox_t, h, a, opt_kind, s);
+}
+
+extern "C" int crb_shard_barrier(crb_handle* h, const crb_shard* shard, uint32_t ticket, int32_t timeout_ms, void* stream) {
+    CRB_CHECK_ARG(h && shard && ticket >= 1, "null argument / ticket");
+    CRB_CHECK_ARG(shard->n_ranks >= 1 && shard->n_ranks <= CRB_MAX_RANKS, "shard descriptor");
+    BarrierArgs a;
+    a.n_ranks = shard->n_ranks; a.rank = shard->rank; a.ticket = ticket;
+    a.timeout_ns = (unsigned long long)(timeout_ms > 0 ? timeout_ms : 10000) * 1000000ULL;
+    for (int r = 0; r < CRB_MAX_RANKS; ++r) a.flags[r] = r < shard->n_ranks ? shard->flags[r] : nullptr;
+    for (int r = 0; r < shard->n_ranks; ++r) CRB_CHECK_ARG(a.flags[r], "shard descriptor: null flag pointer");
+    CRB_CUDA(cudaSetDevice(h->device));
+    shard_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
     return CRB_OK;
 }
 
-extern "C" int crb_shard_inbox_overflow(crb_handle* h, const crb_shard* shard, int32_t* overflowed, void* stream) {
-    CRB_CHECK_ARG(h && shard && overflowed, "null argument");
+extern "C" int crb_sampler_errors(crb_handle* h, uint32_t* n_rows, void* stream) {
+    CRB_CHECK_ARG(h && n_rows, "null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    CRB_CUDA(cudaSetDevice(h->device));
+    if (h->aux_stream) CRB_CUDA(cudaStreamSynchronize(h->aux_stream));
+    CRB_CUDA(cudaStreamSynchronize(s));
+    unsigned int err[2] = {0, 0};
+    const bool alt_active = h->alt_active;
+    crb_step_ctr* c0 = alt_active ? h->alt.ctr : h->ctr;
+    crb_step_ctr* c1 = alt_active ? h->ctr : h->alt.ctr;
+    CRB_CUDA(cudaMemcpy(&err[0], &c0->sampler_err, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    if (c1) CRB_CUDA(cudaMemcpy(&err[1], &c1->sampler_err, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    if (err[0]) CRB_CUDA(cudaMemset(&c0->sampler_err, 0, sizeof(unsigned int)));
+    if (err[1]) CRB_CUDA(cudaMemset(&c1->sampler_err, 0, sizeof(unsigned int)));
+    *n_rows = err[0] + err[1];
+    return CRB_OK;
+}
+
+extern "C" int crb_shard_check(crb_handle* h, const crb_shard* shard, void* stream) {
+    CRB_CHECK_ARG(h && shard, "null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    uint32_t serr = 0;
+    int rc = crb_sampler_errors(h, &serr, stream);
+    if (rc) return rc;
     unsigned int v = 0;
-    CRB_CUDA(cudaMemcpyAsync(&v, shard->inbox_cnt[shard->rank] + 1, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    CRB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-    *overflowed = (int32_t)v;
+    uint32_t* word = shard->flags[shard->rank] + CRB_SHARD_ERR;
+    CRB_CUDA(cudaMemcpyAsync(&v, word, sizeof(v), cudaMemcpyDeviceToHost, s));
+    CRB_CUDA(cudaStreamSynchronize(s));
+    if (v) {
+        CRB_CUDA(cudaMemsetAsync(word, 0, sizeof(v), s));
+        crb_set_error("multi-GPU step: a cross-rank barrier timed out (a peer rank failed or fell behind)");
+        return CRB_ERR_STATE;
+    }
+    if (serr) {
+        crb_set_error("sampler: %u rows found no admissible negative", serr);
+        return CRB_ERR_SAMPLER;
+    }
     return CRB_OK;
 }
 

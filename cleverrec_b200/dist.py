@@ -1,9 +1,12 @@
 """Multi-GPU (one process per GPU, one box) BPR training over NVLink peer memory -- the host side of csrc/train_sharded.cu.
 
 Partitioning: users are split into contiguous ranges, one per rank (rows of P, their histories and their sampling
-are local); the item table Q is row-sharded by `item % world` and every rank maps every shard and every gradient inbox through
-CUDA IPC.  torch.distributed (NCCL) is used for exactly two things: exchanging the 64-byte IPC handles once, and the per-step
-barrier (a one-element all-reduce enqueued on the compute stream).  There is no data-path collective."""
+are local); the item table Q is row-sharded by `item % world` and every rank maps every shard, every gradient inbox and every
+barrier flag array through CUDA IPC.  torch.distributed is used for exactly one thing on the data path: exchanging the 64-byte
+IPC handles once.  The per-step barriers are flag barriers in peer memory (crb_shard_barrier, on the compute stream, no host
+synchronisation); there is no data-path collective.  `barrier="host"` (stream synchronise + a torch.distributed barrier) serves
+process groups whose ranks share ONE device (the 1-GPU parity tests: gloo control plane, CUDA IPC between two processes on the
+same GPU -- a spinning flag barrier would only burn the other process's time slice there)."""
 import ctypes as C
 
 import numpy as np
@@ -59,23 +62,64 @@ class _DeviceBuffer(object):
         return bytes(buf.raw)
 
 
+def _is_gloo(group):
+    return dist.get_backend(group) == "gloo"
+
+
+def broadcast_dev(t, src, group=None):
+    """dist.broadcast of a CUDA tensor that also works on a gloo group (staged through the host)."""
+    if _is_gloo(group):
+        c = t.cpu()
+        dist.broadcast(c, src=src, group=group)
+        t.copy_(c)
+    else:
+        dist.broadcast(t, src=src, group=group)
+
+
+def all_reduce_dev(t, op=None, group=None):
+    op = dist.ReduceOp.SUM if op is None else op
+    if _is_gloo(group):
+        c = t.cpu()
+        dist.all_reduce(c, op=op, group=group)
+        t.copy_(c)
+    else:
+        dist.all_reduce(t, op=op, group=group)
+
+
+def gather_dev(t, dst, group=None):
+    """dist.gather of equally shaped CUDA tensors -> list at `dst` (None elsewhere); host-staged on a gloo group."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if _is_gloo(group):
+        c = t.cpu()
+        parts = [torch.empty_like(c) for _ in range(world)] if rank == dst else None
+        dist.gather(c, parts, dst=dst, group=group)
+        return [p.to(t.device) for p in parts] if rank == dst else None
+    parts = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+    dist.gather(t, parts, dst=dst, group=group)
+    return parts
+
+
 class ShardedBPR(object):
     """BPR (model/ranking/BPR.py:31-44) with P partitioned by user and Q row-sharded over the ranks of one box."""
 
-    def __init__(self, engine, n_users, n_items, dim, optimizer, lr, adam_mode, batch, init_P=None, init_Q=None, seed=0, group=None):
+    def __init__(self, engine, n_users, n_items, dim, optimizer, lr, adam_mode, batch, init_P=None, init_Q=None, seed=0, group=None,
+                 barrier=None, barrier_timeout_ms=20000):
         self.engine, self.group = engine, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         assert self.world <= _lib.MAX_RANKS
         self.n_users, self.n_items, self.dim, self.batch = n_users, n_items, dim, batch
         self.u_lo, self.u_hi = user_range(n_users, self.rank, self.world)
         self.opt = Optimizer(optimizer, lr, adam_mode=adam_mode)
+        self.barrier_mode = barrier or ("host" if _is_gloo(group) else "flag")
+        assert self.barrier_mode in ("flag", "host")
+        self.barrier_timeout_ms, self._ticket = int(barrier_timeout_ms), 0
         dev = engine.device
         g = torch.Generator(device=dev).manual_seed(seed)
         # user rows: ordinary torch memory
         if init_P is None:
             init_P = torch.randn(self.u_hi - self.u_lo, dim, device=dev, generator=g) * 0.01
         self.P = Table(torch.as_tensor(init_P, dtype=torch.float32).to(dev).contiguous(), optimizer, adam_mode)
-        # item shard + inbox: IPC-exportable memory
+        # item shard + inbox + flags: IPC-exportable memory
         rows = shard_rows(n_items, self.rank, self.world)
         self.q_rows = rows
         kinds = ["w"] + (["s1"] if optimizer != "SGD" else []) + (["s2"] if optimizer == "Adam" else [])
@@ -89,15 +133,15 @@ class ShardedBPR(object):
             self.q["w"].tensor.copy_(torch.as_tensor(init_Q, dtype=torch.float32)[self.rank::self.world].to(dev))
         if optimizer == "Adagrad":
             self.q["s1"].tensor.fill_(0.1)
-        # every rank may receive up to 2 * batch * world gradients per step (2 per triplet); hubs make the split uneven
-        self.inbox_cap = int(2 * batch * min(self.world, 2)) + 32 * 4096 * self.world  # + slack for partly used reservations
-        self.inbox = {"grad": _DeviceBuffer(engine, (self.inbox_cap, dim), torch.float32), "row": _DeviceBuffer(engine, (self.inbox_cap,), torch.int32),
-                      "key": _DeviceBuffer(engine, (self.inbox_cap,), torch.int32), "cnt": _DeviceBuffer(engine, (4,), torch.int32)}
-        self.inbox["row"].tensor.fill_(-1)   # every slot is a hole until a gradient is written into it
+        # direct-mapped inbox: one gradient slot per (source rank, local row) -- a source sums its own duplicates before it sends,
+        # so the inbox cannot overflow whatever the skew; world * rows_cap * dim floats = the size of the whole item table
+        self.rows_cap = shard_rows(n_items, 0, self.world)
+        self.inbox = {"grad": _DeviceBuffer(engine, (self.world * self.rows_cap, dim), torch.float32),
+                      "stamp": _DeviceBuffer(engine, (self.world * self.rows_cap,), torch.int32),
+                      "flags": _DeviceBuffer(engine, (_lib.SHARD_FLAGS,), torch.int32)}
         self._map_peers()
-        self._flag = torch.zeros(1, device=dev)
         torch.cuda.synchronize()
-        self.barrier()
+        dist.barrier(group=self.group)
 
     def _map_peers(self):
         mine = {"rows": self.q_rows}
@@ -107,7 +151,7 @@ class ShardedBPR(object):
         dist.all_gather_object(everyone, mine, group=self.group)
         self._opened = []
         sh = CrbShard()
-        sh.n_ranks, sh.rank, sh.inbox_cap = self.world, self.rank, self.inbox_cap
+        sh.n_ranks, sh.rank, sh.rows_cap = self.world, self.rank, self.rows_cap
 
         def open_(handle):
             p = C.c_void_p()
@@ -122,14 +166,19 @@ class ShardedBPR(object):
                     return None
                 return store[kind].ptr if local else open_(info[("q_" if store is self.q else "in_") + kind])
             sh.q[r] = CrbTable(pointer("w", self.q), pointer("s1", self.q), pointer("s2", self.q), pointer("last", self.q), info["rows"], self.dim, 0)
-            sh.inbox_grad[r], sh.inbox_row[r] = pointer("grad", self.inbox), pointer("row", self.inbox)
-            sh.inbox_key[r], sh.inbox_cnt[r] = pointer("key", self.inbox), pointer("cnt", self.inbox)
+            sh.inbox_grad[r], sh.inbox_stamp[r], sh.flags[r] = pointer("grad", self.inbox), pointer("stamp", self.inbox), pointer("flags", self.inbox)
         self.shard = sh
 
     def barrier(self):
-        """Cross-rank barrier ordered with the compute stream (no host synchronisation)."""
-        if self.world > 1:
-            dist.all_reduce(self._flag, group=self.group)
+        """Cross-rank barrier ordered with the compute stream."""
+        if self.world == 1:
+            return
+        if self.barrier_mode == "host":
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            return
+        self._ticket += 1
+        check(self.engine.lib.crb_shard_barrier(self.engine.h, C.byref(self.shard), self._ticket, self.barrier_timeout_ms, self.engine.stream))
 
     def set_history(self, ui_train_local, n_users_local):
         """ui_train_local: this rank's users keyed by LOCAL row (see shard_history), item ids global."""
@@ -153,14 +202,17 @@ class ShardedBPR(object):
         self.barrier()
         return float(host[0]) if loss_out is None else None
 
-    def run_steps(self, n_steps, reg, neg_ratio, seed, epoch, first=0, batch=None, loss_out=None, bounds=None, feeds=None, host_losses=None):
+    def run_steps(self, n_steps, reg, neg_ratio, seed, epoch, first=0, batch=None, loss_out=None, bounds=None, feeds=None, host_losses=None,
+                  phase_ms=None):
         """n synchronous steps over consecutive batches of this rank's epoch, sampled on the device.  Step k+1's index work
         (sampler, user-row counting and slot assignment) is prepared on the engine's auxiliary stream while step k's barriers and
         inbox phase run (crb_shard_step_prepare).  loss_out: device float64 [n_steps] or None.  bounds: optional n_steps+1 row
         offsets (step k covers rows [bounds[k], bounds[k+1]) of this rank's epoch) instead of a fixed batch.
         feeds: optional list of n_steps (u_local, i_global, j_global) int32 arrays (host -- ideally pinned -- or device): the caller's
         own triplets are staged one step ahead instead of being sampled (the reference's epoch loop over its sampler's output).
-        host_losses: optional pinned float64 CPU tensor [n_steps]: every step's loss is copied to it asynchronously as the step ends."""
+        host_losses: optional pinned float64 CPU tensor [n_steps]: every step's loss is copied to it asynchronously as the step ends.
+        phase_ms: optional dict; CUDA events on the compute stream then split every step into compute (fetch + fused step + duplicate
+        reduce / send + loss) / barrier1 / apply (the owner's inbox pass) / barrier2 and the totals are added to it (profiling)."""
         eng, lib = self.engine, self.engine.lib
         batch = self.batch if batch is None else batch
         if bounds is None:
@@ -179,28 +231,48 @@ class ShardedBPR(object):
 
         def prepare(k):
             f = feeds[k] if feeds is not None else (None, None, None)
-            check(lib.crb_shard_step_prepare(eng.h, C.byref(self.P.c), seed, epoch, bounds[k], neg_ratio, bounds[k + 1] - bounds[k], self.inbox_cap,
+            check(lib.crb_shard_step_prepare(eng.h, C.byref(self.P.c), seed, epoch, bounds[k], neg_ratio, bounds[k + 1] - bounds[k], self.n_items,
                                              ptr(f[0]), ptr(f[1]), ptr(f[2]), eng.stream))
         prepare(0)
         host = np.zeros(1, dtype=np.float64)
+        marks = [] if phase_ms is not None else None
+
+        def mark():
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append(e)
         for k in range(n_steps):
             self.opt.t += 1
             co = self.opt.c(self.opt.t)
             lo = ptr(host) if loss_out is None else ptr(loss_out[k:k + 1])
+            mark()
             check(lib.crb_shard_step_compute(eng.h, C.byref(self.P.c), C.byref(self.shard), C.byref(co), None, None, None, seed, epoch,
                                              bounds[k], neg_ratio, bounds[k + 1] - bounds[k], float(reg), lo, eng.stream))
             if host_losses is not None:
                 host_losses[k:k + 1].copy_(loss_out[k:k + 1], non_blocking=True)
             if k + 1 < n_steps:
                 prepare(k + 1)
+            mark()
             self.barrier()
+            mark()
             check(lib.crb_shard_apply_inbox(eng.h, C.byref(self.shard), C.byref(co), eng.stream))
+            mark()
             self.barrier()
+        if marks is not None:
+            mark()
+            torch.cuda.synchronize()
+            names = ("compute", "barrier1", "apply", "barrier2")
+            for k in range(n_steps):
+                for q, name in enumerate(names):
+                    a, b = marks[4 * k + q], marks[4 * k + q + 1]
+                    phase_ms[name] = phase_ms.get(name, 0.0) + a.elapsed_time(b)
+            phase_ms["steps"] = phase_ms.get("steps", 0) + n_steps
 
-    def inbox_overflowed(self):
-        v = C.c_int32()
-        check(self.engine.lib.crb_shard_inbox_overflow(self.engine.h, C.byref(self.shard), C.byref(v), self.engine.stream))
-        return bool(v.value)
+    def check(self):
+        """Synchronises and raises CrbError if a cross-rank barrier timed out or the sampler gave up on a row since the last check
+        (call once per epoch: the step calls themselves never synchronise)."""
+        check(self.engine.lib.crb_shard_check(self.engine.h, C.byref(self.shard), self.engine.stream))
 
     def flush(self):
         """Bring CRB_ADAM_TF1 tables up to date before reading them."""
@@ -218,7 +290,7 @@ class ShardedBPR(object):
             if r == self.rank:
                 parts[r].copy_(self.P.w)
             if self.world > 1:
-                dist.broadcast(parts[r], src=r, group=self.group)
+                broadcast_dev(parts[r], r, self.group)
         return torch.cat(parts)
 
     def gather_Q(self):
@@ -226,7 +298,10 @@ class ShardedBPR(object):
         self.flush()
         parts = [torch.zeros(shard_rows(self.n_items, r, self.world), self.dim, device=self.engine.device) for r in range(self.world)]
         if self.world > 1:
-            dist.all_gather(parts, self.q["w"].tensor.contiguous(), group=self.group) if len({p.shape for p in parts}) == 1 else self._gather_ragged(parts)
+            if len({p.shape for p in parts}) == 1 and not _is_gloo(self.group):
+                dist.all_gather(parts, self.q["w"].tensor.contiguous(), group=self.group)
+            else:
+                self._gather_ragged(parts)
         else:
             parts[0] = self.q["w"].tensor
         full = torch.zeros(self.n_items, self.dim, device=self.engine.device)
@@ -238,12 +313,11 @@ class ShardedBPR(object):
         for r in range(self.world):
             if r == self.rank:
                 parts[r].copy_(self.q["w"].tensor)
-            dist.broadcast(parts[r], src=r, group=self.group)
+            broadcast_dev(parts[r], r, self.group)
 
     def close(self):
         torch.cuda.synchronize()
-        self.barrier()
-        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
         for p in self._opened:
             self.engine.lib.crb_ipc_close(self.engine.h, p)
         for b in list(self.q.values()) + list(self.inbox.values()):
@@ -256,6 +330,9 @@ def transpose_history(seen_rowptr, seen_cols, u_lo, n_users_total, world, rank, 
     """Each rank holds the histories of ITS users (global item ids).  Evaluation needs the opposite cut: for ALL users, the seen
     items that live on THIS rank's item shard (owner = item % world), as local rows.  One all-to-all of (user, local row) pairs at
     set-up; works on CPU tensors with gloo (tests) and CUDA tensors with NCCL.  -> (rowptr int64 [n_users_total+1], cols int32)."""
+    out_dev = seen_cols.device
+    if world > 1 and seen_cols.is_cuda and _is_gloo(group):   # ranks sharing one device (tests): the exchange runs on host copies
+        seen_rowptr, seen_cols = seen_rowptr.cpu(), seen_cols.cpu()
     dev = seen_cols.device
     counts = (seen_rowptr[1:] - seen_rowptr[:-1])
     users = torch.repeat_interleave(torch.arange(counts.numel(), device=dev, dtype=torch.int64) + u_lo, counts)
@@ -282,7 +359,7 @@ def transpose_history(seen_rowptr, seen_cols, u_lo, n_users_total, world, rank, 
     ku = torch.div(key, stride, rounding_mode="floor")
     rowptr = torch.zeros(n_users_total + 1, dtype=torch.int64, device=dev)
     torch.cumsum(torch.bincount(ku, minlength=n_users_total), 0, out=rowptr[1:])
-    return rowptr, (key - ku * stride).to(torch.int32)
+    return rowptr.to(out_dev), (key - ku * stride).to(torch.int32).to(out_dev)
 
 
 def merge_topk(ids_per_rank, scores_per_rank, K, ascending=False):
@@ -352,16 +429,13 @@ class ShardedEval(object):
                 b = min(hi, a + batch_users)
                 rows = m.P.w[a - lo:b - lo].contiguous() if owner == self.rank else torch.empty(b - a, m.dim, device=dev)
                 if self.world > 1:
-                    dist.broadcast(rows, src=owner, group=m.group)
+                    broadcast_dev(rows, owner, m.group)
                 local_u = torch.arange(b - a, dtype=torch.int32, device=dev)
                 hist_u = torch.arange(a, b, dtype=torch.int32, device=dev)
                 ids, sc = self.eng.score_topk(self.kind, rows, Qw, local_u, K, hist_users=hist_u, exact=exact, n_items=m.q_rows, return_scores=True)
                 gids = torch.where(ids >= 0, ids * self.world + self.rank, ids)   # local row -> global item id
                 if self.world > 1:
-                    all_ids = [torch.empty_like(gids) for _ in range(self.world)] if owner == self.rank else None
-                    all_sc = [torch.empty_like(sc) for _ in range(self.world)] if owner == self.rank else None
-                    dist.gather(gids, all_ids, dst=owner, group=m.group)
-                    dist.gather(sc, all_sc, dst=owner, group=m.group)
+                    all_ids, all_sc = gather_dev(gids, owner, m.group), gather_dev(sc, owner, m.group)
                 else:
                     all_ids, all_sc = [gids], [sc]
                 if owner == self.rank:

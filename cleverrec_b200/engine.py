@@ -497,6 +497,13 @@ class Engine(object):
                                       ptr(targets), targets.numel(), float(beta), ptr(out), self.stream))
         return out
 
+    def sampler_errors(self):
+        """Rows for which the device sampler ran out of attempts since the last call (synchronises; clears the counter).  The
+        reference loops forever in that case (utils/sampler.py:58-61); here it is an error the epoch loop raises."""
+        n = C.c_uint32()
+        check(self.lib.crb_sampler_errors(self.h, C.byref(n), self.stream))
+        return int(n.value)
+
     def adam_flush(self, table, opt):
         if opt.kind == "Adam" and opt.adam_mode == "tf1" and opt.t > 0:
             co = opt.c(opt.t)

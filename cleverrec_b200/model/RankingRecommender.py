@@ -96,6 +96,10 @@ class RankingRecommender(Recommender):
             self._train_epoch_pointwise(self.epoch, n_rows, n_batches, losses)
         self.epoch += 1
         total_loss = float(losses.sum().item())  # one device->host read per epoch
+        bad = self.engine.sampler_errors()       # the stream is already drained by the read above
+        if bad:
+            raise RuntimeError('sampler: %d rows found no admissible negative (a user has fewer than neg_ratio unseen items; '
+                               'the reference would loop forever, utils/sampler.py:58-61)' % bad)
         return total_loss / n_batches
 
     # ---- Leave-One-Out / Random split with 1000 negative items ---------------------------------------------

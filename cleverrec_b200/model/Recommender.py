@@ -56,7 +56,11 @@ class Recommender(object):
         if isinstance(self.sess, Engine):
             self.engine = self.sess
         else:
-            self.engine = Engine(int(c.get('engine.device', os.environ.get('LOCAL_RANK', '0') if int(os.environ.get('WORLD_SIZE', '1')) > 1 else 0)))
+            # CRB_SHARED_DEVICE=1: every rank of the job uses device 0 (CUDA IPC between processes on ONE GPU, gloo control plane):
+            # the multi-GPU code path on a single-GPU box (parity tests)
+            shared = os.environ.get('CRB_SHARED_DEVICE', '0') == '1'
+            local = os.environ.get('LOCAL_RANK', '0') if int(os.environ.get('WORLD_SIZE', '1')) > 1 and not shared else 0
+            self.engine = Engine(int(c.get('engine.device', local)))
 
     def build_model(self):
         raise NotImplementedError

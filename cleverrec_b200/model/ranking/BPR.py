@@ -37,7 +37,10 @@ class BPR(_rr.RankingRecommender):
         from ...dist import shard_history, user_range
         if not dist.is_initialized():
             os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-            dist.init_process_group('nccl', device_id=self.engine.device)
+            if os.environ.get('CRB_SHARED_DEVICE', '0') == '1':
+                dist.init_process_group('gloo')     # ranks share one GPU: NCCL refuses that, the data path (CUDA IPC) does not care
+            else:
+                dist.init_process_group('nccl', device_id=self.engine.device)
         self.u_lo, self.u_hi = user_range(self.data.user_nums, self.rank, self.world)
         mine, n_local = shard_history(self.data.ui_train, self.data.user_nums, self.rank, self.world)
         self.engine.set_history(mine, n_local, self.data.item_nums)   # local user rows, global item ids
@@ -50,7 +53,7 @@ class BPR(_rr.RankingRecommender):
             full[name] = torch.as_tensor(np.asarray(init[name]), dtype=torch.float32) if init and name in init else self.initializer(shapes[name])
         per_rank = -(-self.batch_size // self.world)
         self._shm = ShardedBPR(self.engine, self.data.user_nums, self.data.item_nums, self.embed_size, self.optimizer.kind, self.optimizer.lr,
-                               self.optimizer.adam_mode, 2 * per_rank, init_P=full['P'][self.u_lo:self.u_hi], init_Q=full['Q'])
+                               self.optimizer.adam_mode, per_rank, init_P=full['P'][self.u_lo:self.u_hi], init_Q=full['Q'])
         self.optimizer = self._shm.opt
         self.P = self._shm.P          # this rank's user rows
         self.tables = {'P': self.P}
@@ -63,16 +66,19 @@ class BPR(_rr.RankingRecommender):
         import torch.distributed as dist
         if self.sampler_mode == 'numpy_stream':
             raise NotImplementedError("sampler=numpy_stream reproduces ONE process's np.random stream; it is single-GPU only")
+        from ...dist import all_reduce_dev
         rows = self.engine.epoch_rows(self.neg_ratio, 'pairwise')
-        t = torch.tensor([rows], dtype=torch.int64, device=self.engine.device)
-        dist.all_reduce(t)
-        n_steps = math.ceil(int(t.item()) / self.batch_size)       # the global epoch in global batches (RankingRecommender.py:38-39)
-        if rows < n_steps:
-            raise ValueError('rank %d holds %d training rows for %d steps: too little data for %d ranks' % (self.rank, rows, n_steps, self.world))
+        every = [None] * self.world
+        dist.all_gather_object(every, int(rows))
+        total, fewest = sum(every), min(every)
+        n_steps = math.ceil(total / self.batch_size)                # the global epoch in global batches (RankingRecommender.py:38-39)
+        if fewest < n_steps:                                         # decided from gathered values: every rank raises, none hangs
+            raise ValueError('a rank holds %d training rows for %d steps: too little data for %d ranks' % (fewest, n_steps, self.world))
         bounds = [rows * k // n_steps for k in range(n_steps + 1)]   # this rank's share of every union batch
         losses = torch.zeros(n_steps, dtype=torch.float64, device=self.engine.device)
         self._shm.run_steps(n_steps, self.reg, self.neg_ratio, self.seed, self.epoch, bounds=bounds, loss_out=losses)
-        dist.all_reduce(losses)                                      # the step's loss is the sum over the union batch
+        self._shm.check()                                            # barrier time-outs / sampler give-ups surface here, once per epoch
+        all_reduce_dev(losses)                                       # the step's loss is the sum over the union batch
         self.epoch += 1
         self._Qfull = None
         return float(losses.sum().item()) / n_steps

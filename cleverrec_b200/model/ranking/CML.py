@@ -46,6 +46,21 @@ class CML(_rr.RankingRecommender):
 
     # For CML (RankingRecommender.py:90-100)
     def train_model_cml(self):
+        if self.sampler_mode == 'numpy_stream':
+            # the epoch ranking_sampler_cml (utils/sampler.py:77-99) returns under NumPy's CURRENT global stream, bit for bit
+            import numpy as np_
+            eng = self.engine
+            eng.np_set_state()
+            u, i, neg = eng.sample_epoch_numpy('cml', self.neg_ratio)
+            np_.random.set_state(eng.np_get_state())
+            n_rows = u.numel()
+            n_batches = math.ceil(n_rows / self.batch_size)
+            losses = torch.zeros(n_batches, dtype=torch.float64, device=eng.device)
+            for k in range(n_batches):
+                sl = slice(k * self.batch_size, min((k + 1) * self.batch_size, n_rows))
+                self.train_step(u[sl], i[sl], neg[sl], loss_out=losses[k:k + 1])
+            self.epoch += 1
+            return float(losses.sum().item()) / n_batches
         n_rows = self.engine.epoch_rows(self.neg_ratio, 'cml')
         n_batches = math.ceil(n_rows / self.batch_size)
         losses = torch.zeros(n_batches, dtype=torch.float64, device=self.engine.device)

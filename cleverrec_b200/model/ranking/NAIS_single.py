@@ -82,6 +82,9 @@ class NAIS_single(_rr.RankingRecommender):
 
     # Form mini-batch by user (RankingRecommender.py:64-87): one optimizer step per user, in data.ui_train order
     def train_model_nais(self):
+        if self.sampler_mode == 'numpy_stream':
+            raise NotImplementedError("sampler=numpy_stream is not wired into NAIS_single's fused per-user epoch (crb_train_epoch_nais draws "
+                                      "its negatives from the Philox sampler); use sampler=philox")
         losses = torch.zeros(len(self._train_users), dtype=torch.float64, device=self.engine.device)
         self.engine.train_epoch_nais(self.P, self.Q, self.B, self.dense, self.dense_s1, self.dense_s2, self.atten_size, self.optimizer, self.seed,
                                      self.epoch, self._list_start, self._list_len, self.neg_ratio, self.beta, self.reg, losses, concat=self.concat)

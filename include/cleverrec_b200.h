@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CRB_ABI_VERSION 1
+#define CRB_ABI_VERSION 2
 
 typedef enum {
     CRB_OK = 0,
@@ -75,19 +75,25 @@ typedef struct {
 } crb_opt;
 
 /* Multi-GPU (one process per GPU, one box): the item table is row-sharded, owner = item % n_ranks, local row = item / n_ranks.
- * Every rank maps every shard and every inbox into its own address space (crb_malloc + crb_ipc_export / crb_ipc_open), so
- * q[r] / inbox_*[r] are pointers valid ON THIS DEVICE to rank r's memory (NVLink peer access); index `rank` is local memory.
- * An inbox holds item gradients sent by all ranks during one step: grad [inbox_cap, dim], row/key [inbox_cap], cnt [2]. */
+ * Every rank maps every shard, every inbox and every flag array into its own address space (crb_malloc + crb_ipc_export /
+ * crb_ipc_open), so q[r] / inbox_*[r] / flags[r] are pointers valid ON THIS DEVICE to rank r's memory (NVLink peer access);
+ * index `rank` is local memory.  An inbox is DIRECT-MAPPED: one gradient slot per (source rank, local row) --
+ * inbox_grad[r] is float [n_ranks][rows_cap][dim], inbox_stamp[r] is uint32 [n_ranks][rows_cap] (the step whose gradient the slot
+ * holds; created zeroed).  A source sums its own duplicates before sending, so a slot is written at most once per step: the inbox
+ * cannot overflow and is never cleared.  rows_cap >= q[r].rows for every r.  flags[r] is uint32 [CRB_SHARD_FLAGS]: words
+ * [0, n_ranks) are the arrival flags of crb_shard_barrier (word s = last barrier ticket rank s announced to rank r), word
+ * CRB_SHARD_ERR is a sticky error word (a barrier that timed out). */
 #define CRB_MAX_RANKS 8
+#define CRB_SHARD_FLAGS 16
+#define CRB_SHARD_ERR 8
 typedef struct {
     int32_t n_ranks;
     int32_t rank;
-    int64_t inbox_cap;
+    int64_t rows_cap;
     crb_table q[CRB_MAX_RANKS];
     float* inbox_grad[CRB_MAX_RANKS];
-    int32_t* inbox_row[CRB_MAX_RANKS];
-    uint32_t* inbox_key[CRB_MAX_RANKS];
-    uint32_t* inbox_cnt[CRB_MAX_RANKS];
+    uint32_t* inbox_stamp[CRB_MAX_RANKS];
+    uint32_t* flags[CRB_MAX_RANKS];
 } crb_shard;
 
 /* utils/tools.py:66-76 (get_loss) */
@@ -315,27 +321,44 @@ int crb_score_nais(crb_handle* h, const float* P, const float* Q, const float* b
                    int32_t atten_size, int32_t atten_concat, const int32_t* hist, int32_t n_hist, const int32_t* targets,
                    int32_t n_targets, float beta, float* scores, void* stream);
 
-/* Multi-GPU BPR step, phase 1 (every rank, same step index): sess.run([train, loss]) on this rank's slice of the union batch.
+/* Multi-GPU BPR step, phase 1 (every rank, same step index): sess.run([train, loss]) on this rank's slice of the union batch
+ * (model/ranking/BPR.py:31-44; the slicing of RankingRecommender.py:38-46).
  * P: this rank's user rows; u = local user rows, i/j = GLOBAL item ids (DEVICE or HOST), or u == NULL to sample rows
- * [first, first+batch) of this rank's epoch (crb_set_history holds the rank's own users, item ids global).  Item rows are read
- * from their owners over peer memory; item gradients are written into the owners' inboxes.  The caller then runs a cross-rank
- * barrier on the same stream, crb_shard_apply_inbox, and a second barrier. */
+ * [first, first+batch) of this rank's epoch (crb_set_history holds the rank's own users, item ids global).
+ * Kernels: item rows that occur more than once in this rank's batch are fetched from their owners ONCE into a local staging
+ * buffer (item_fetch_kernel); the fused step (shard_step_kernel) reads the remaining item rows straight from the owner's HBM over
+ * NVLink, applies user rows locally and sends the gradient of a once-occurring item row straight into its owner's direct-mapped
+ * inbox; gradients of repeated item rows are summed locally in triplet order and sent once (dup_reduce_kernel<SHARD>).  The caller
+ * then runs crb_shard_barrier, crb_shard_apply_inbox and a second crb_shard_barrier on the same stream. */
 int crb_shard_step_compute(crb_handle* h, const crb_table* P, const crb_shard* shard, const crb_opt* opt, const int32_t* u,
                            const int32_t* i, const int32_t* j, uint64_t seed, uint32_t epoch, int64_t first, int32_t neg_ratio,
                            int64_t batch, float reg, double* loss_out, void* stream);
-/* Optional phase 0 of the NEXT step: sample rows [first, first+batch) and count / assign the user rows on the handle's auxiliary
- * stream, so that this index-only work (utils/sampler.py:46-74 + the feed slicing of RankingRecommender.py:38-46) overlaps the
- * current step's barriers and inbox phase.  Consumed by the next crb_shard_step_compute with u == NULL and the same
- * (seed, epoch, first, neg_ratio, batch).  reserve_rows >= batch sizes the workspace once for both phases (the inbox capacity).
- * feed_u / feed_i / feed_j (HOST or DEVICE int32 [batch], or all NULL): stage the caller's own triplets (the reference's sampler
- * output sliced as RankingRecommender.py:40-42; local user rows, global item ids) instead of sampling -- the copies then overlap
- * the current step; the five scalars only serve as the ticket the consuming crb_shard_step_compute presents. */
+/* Optional phase 0 of the NEXT step on the handle's auxiliary stream: sample rows [first, first+batch), count the occurrences of
+ * every user and item row, give repeated rows their gradient slots and resolve every triplet's item sources -- the index-only work
+ * (utils/sampler.py:46-74 + the feed slicing of RankingRecommender.py:38-46) then overlaps the current step's barriers and
+ * inbox phase.  Consumed by the next crb_shard_step_compute with u == NULL and the same (seed, epoch, first, neg_ratio, batch).
+ * n_items: rows of the GLOBAL item table.  feed_u / feed_i / feed_j (HOST or DEVICE int32 [batch], or all NULL): stage the caller's
+ * own triplets (the reference's sampler output sliced as RankingRecommender.py:40-42; local user rows, global item ids) instead
+ * of sampling -- the copies then overlap the current step; the five scalars only serve as the ticket the consuming
+ * crb_shard_step_compute presents. */
 int crb_shard_step_prepare(crb_handle* h, const crb_table* P, uint64_t seed, uint32_t epoch, int64_t first, int32_t neg_ratio,
-                           int64_t batch, int64_t reserve_rows, const int32_t* feed_u, const int32_t* feed_i, const int32_t* feed_j,
+                           int64_t batch, int64_t n_items, const int32_t* feed_u, const int32_t* feed_i, const int32_t* feed_j,
                            void* stream);
-/* phase 2: de-duplicate this rank's inbox, one optimizer apply per unique item row with the gradient summed over all ranks. */
+/* phase 2 (after the barrier): one pass over this rank's item rows -- the gradients that arrived for a row are summed in source-rank
+ * order and applied once (TF's de-duplicated sparse apply on the union batch); with CRB_ADAM_TF1 a row that received nothing
+ * takes its decay-only step, so remote readers always find current weights. */
 int crb_shard_apply_inbox(crb_handle* h, const crb_shard* shard, const crb_opt* opt, void* stream);
-int crb_shard_inbox_overflow(crb_handle* h, const crb_shard* shard, int32_t* overflowed, void* stream);
+/* Cross-rank barrier ON THE STREAM, no host synchronisation and no collective library: a one-block kernel stores `ticket` into
+ * word `rank` of every peer's flag array (system-scope release) and spins until every word of its own array has reached `ticket`.
+ * Every rank must call it with the same strictly increasing tickets (>= 1).  A wait longer than timeout_ms sets the sticky error
+ * word instead of hanging; crb_shard_check reports it. */
+int crb_shard_barrier(crb_handle* h, const crb_shard* shard, uint32_t ticket, int32_t timeout_ms, void* stream);
+/* Synchronises the stream and returns CRB_ERR_STATE if a barrier timed out or the sampler found no admissible negative for some
+ * row since the last check (both sticky until read here). */
+int crb_shard_check(crb_handle* h, const crb_shard* shard, void* stream);
+/* Sampler attempt overflows (utils/sampler.py:58-61 has no such bound; ours is CRB_SAMPLER_MAX_BLOCKS Philox blocks per row)
+ * since the last call; synchronises the stream and clears the counter. */
+int crb_sampler_errors(crb_handle* h, uint32_t* n_rows, void* stream);
 
 /* Peer-memory plumbing: cudaMalloc'd (zeroed) buffers that can be exported to the other ranks of the box through CUDA IPC. */
 int crb_malloc(crb_handle* h, int64_t bytes, void** out);

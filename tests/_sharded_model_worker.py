@@ -23,6 +23,8 @@ CFG = {'recommender': 'BPR', 'model_type': 'ranking', 'saved_dir': './saved_mode
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    if os.environ.get("CRB_SHARED_DEVICE", "0") == "1":   # both processes on device 0 (gloo control plane, CUDA IPC data path)
+        local = 0
     torch.cuda.set_device(local)
     from cleverrec_b200.model.ranking.BPR import BPR
     ok = True
@@ -60,7 +62,8 @@ def main():
                 print("QUALITY", np.mean(HR[0])); ok = False
         m._shm.close()
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    from cleverrec_b200.dist import all_reduce_dev
+    all_reduce_dev(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("SHARDED_MODEL_OK" if flag.item() == 1.0 else "SHARDED_MODEL_FAIL")
     dist.destroy_process_group()

@@ -1,5 +1,7 @@
-"""Worker for tests/test_gpu2_sharded.py (launched with torch.distributed.run, one process per GPU): ShardedBPR over NVLink
-peer memory must reproduce the single-GPU step on the union batch."""
+"""Worker for tests/test_gpu2_sharded.py and tests/test_gpu_sharded_one_device.py (launched with torch.distributed.run): ShardedBPR
+over peer memory must reproduce the single-GPU step on the union batch.  One process per GPU over NCCL, or -- CRB_SHARED_DEVICE=1 --
+every process on device 0 with a gloo control plane: CUDA IPC works between processes on one GPU, so the same kernels
+(item_fetch / shard_step / dup_reduce<SHARD> / inbox_apply) run with real cross-process peer pointers on a single-GPU box."""
 import os
 import sys
 
@@ -8,14 +10,20 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from cleverrec_b200.dist import ShardedBPR, user_range  # noqa: E402
+from cleverrec_b200.dist import ShardedBPR, all_reduce_dev, broadcast_dev, user_range  # noqa: E402
 from cleverrec_b200.engine import Engine, Optimizer, Table  # noqa: E402
 
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    shared = os.environ.get("CRB_SHARED_DEVICE", "0") == "1"
+    if shared:
+        local = 0
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if shared:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = Engine(local)
     U, I, d, B = 64, 101, 64, 256
     g = torch.Generator().manual_seed(0)
@@ -39,21 +47,21 @@ def main():
             loss = m.step(0.01, feed=(u - lo, i, j))
             my_feeds.append((u - lo, i, j)); my_losses.append(loss)
             t = torch.tensor([loss], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t)
+            all_reduce_dev(t)
             if rank == 0:
                 uu, ii, jj = (np.concatenate([f[k] for f in feeds]) for k in range(3))
                 want = eng.train_step_bpr(ref[0], ref[1], ref[2], uu, ii, jj, 0.01)
                 if abs(float(t.item()) - want) > 1e-5 * abs(want):
                     print("LOSS MISMATCH", kind, mode, step, float(t.item()), want)
                     ok = False
-        assert not m.inbox_overflowed()
+        m.check()
         m.flush()
         Qfull = m.gather_Q()
         Pparts = [torch.zeros(user_range(U, r, world)[1] - user_range(U, r, world)[0], d, device="cuda") for r in range(world)]
         for r in range(world):
             if r == rank:
                 Pparts[r].copy_(m.P.w)
-            dist.broadcast(Pparts[r], src=r)
+            broadcast_dev(Pparts[r], r)
         if rank == 0:
             eng.adam_flush(ref[0], ref[2]); eng.adam_flush(ref[1], ref[2])
             rtol, atol = (1e-4, 1e-5) if kind == "Adam" else (1e-5, 2e-7)
@@ -96,7 +104,7 @@ def main():
         for r in range(world):
             if r == rank:
                 Pparts[r].copy_(m.P.w)
-            dist.broadcast(Pparts[r], src=r)
+            broadcast_dev(Pparts[r], r)
         ref_eng = Engine(local)
         ref_eng.set_history(data.ui_train, U, I)
         want = ref_eng.score_topk(0, torch.cat(Pparts), Qfull, torch.arange(lo, hi, dtype=torch.int32, device="cuda"), 10, exact=True)
@@ -125,7 +133,7 @@ def main():
             ok = False
     # device-sampled path runs and stays finite
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    all_reduce_dev(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("SHARDED_OK" if flag.item() == 1.0 else "SHARDED_FAIL")
     dist.destroy_process_group()

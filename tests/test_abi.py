@@ -29,7 +29,7 @@ def test_header_symbols_are_exported(lib):
 
 def test_abi_version_and_struct_layout(lib):
     from cleverrec_b200 import _lib
-    assert lib.crb_abi_version() == 1
+    assert lib.crb_abi_version() == 2
     assert C.sizeof(_lib.CrbTable) == 48 and C.sizeof(_lib.CrbOpt) == 48
 
 
