@@ -239,6 +239,7 @@ def run_ours(args, w):
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     k3_ms, k3_n = eng.profile_read()
+    other_kernels = {name: eng.profile_read(tag) for tag, name in ((1, "item_fetch_kernel"), (2, "dup_reduce+dup_final"), (3, "inbox_apply_kernel"))}
     eng.profile(False)
     launches = eng.launches - l0
     clk = clocks.summary()
@@ -318,6 +319,7 @@ def run_ours(args, w):
                 "frac": (achieved / hbm) if achieved else None, "traffic": None, "peak_source": which,
                 "algorithmic_bytes_per_launch": per_triplet * B, "kernel_ms": k3_avg_ms, "kernel_share_of_step": k3_avg_ms / ms_step,
                 "step_frac": per_triplet * B / (ms_step / 1000.0) / 1e9 / hbm}
+    roofline["other_kernels_ms"] = {k: v[0] / v[1] for k, v in other_kernels.items() if v[1]}
     if phase_ms:
         roofline["phase_ms_per_step"] = {k: v / phase_ms["steps"] for k, v in phase_ms.items() if k != "steps"}
     if world > 1 and k3_n:

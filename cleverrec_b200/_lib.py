@@ -18,8 +18,8 @@ SCORE_DOT, SCORE_GMF, SCORE_SQDIST, SCORE_DOT_BIAS = 0, 1, 2, 3
 EXPORTS = [
     "crb_abi_version", "crb_last_error", "crb_create", "crb_destroy", "crb_set_history", "crb_sample_pairwise",
     "crb_sample_pointwise", "crb_sample_cml", "crb_epoch_rows", "crb_train_step_bpr", "crb_train_epoch_bpr",
-    "crb_train_step_pointwise", "crb_adam_flush", "crb_score_pairs", "crb_topk_segments", "crb_score_topk",
-    "crb_score_topk_stats", "crb_launch_count", "crb_profile_enable", "crb_profile_read",
+    "crb_train_step_pointwise", "crb_adam_flush", "crb_score_pairs", "crb_score_pairs_topk", "crb_topk_segments", "crb_score_topk",
+    "crb_score_topk_stats", "crb_eval_cache_invalidate", "crb_launch_count", "crb_profile_enable", "crb_profile_read", "crb_profile_read_tag",
     "crb_train_step_cml", "crb_set_history_lists", "crb_train_step_fism", "crb_fism_user_vectors", "crb_clip_rows",
     "crb_train_step_neumf", "crb_score_pairs_neumf", "crb_mask_seen",
     "crb_sample_nais", "crb_train_step_nais", "crb_train_epoch_nais", "crb_score_nais",
@@ -89,12 +89,15 @@ def load():
     lib.crb_adam_flush.argtypes = [vp, C.POINTER(CrbTable), C.POINTER(CrbOpt), vp]
     lib.crb_score_pairs.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, i64, vp, vp]
     lib.crb_topk_segments.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
+    lib.crb_score_pairs_topk.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, i64, i32, i32, vp, vp]
     lib.crb_score_topk.argtypes = [vp, i32, vp, vp, vp, i64, i32, vp, vp, i64, i32, i32, vp, vp, vp]
     lib.crb_score_topk_stats.argtypes = [vp, C.POINTER(C.c_int64 * 4)]
+    lib.crb_eval_cache_invalidate.argtypes = [vp]
     lib.crb_launch_count.argtypes = [vp]
     lib.crb_launch_count.restype = i64
     lib.crb_profile_enable.argtypes = [vp, i32]
     lib.crb_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.crb_profile_read_tag.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     T, O = C.POINTER(CrbTable), C.POINTER(CrbOpt)
     lib.crb_train_step_cml.argtypes = [vp, T, T, vp, vp, O, vp, vp, vp, i64, i32, f32, f32, i64, vp, vp]
     lib.crb_set_history_lists.argtypes = [vp, vp, vp]

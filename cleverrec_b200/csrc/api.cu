@@ -162,7 +162,8 @@ extern "C" int crb_destroy(crb_handle* h) {
     cudaFree(h->dense_grad);
     cudaFree(h->bloom);
     cudaFree(h->eval_ws);
-    if (h->prof_ev) { for (int k = 0; k < 2 * CRB_PROF_CAP; ++k) cudaEventDestroy(h->prof_ev[k]); free(h->prof_ev); }
+    for (int t = 0; t < CRB_PROF_TAGS; ++t)
+        if (h->prof_ev[t]) { for (int k = 0; k < 2 * CRB_PROF_CAP; ++k) cudaEventDestroy(h->prof_ev[t][k]); free(h->prof_ev[t]); }
     free(h);
     return CRB_OK;
 }
@@ -288,8 +289,15 @@ int crb_ws_reserve(crb_handle* h, int64_t batch, int32_t dim, int64_t steps, cud
     return CRB_OK;
 }
 
+extern "C" int crb_eval_cache_invalidate(crb_handle* h) {
+    CRB_CHECK_ARG(h, "null handle");
+    h->evq_valid = 0;
+    return CRB_OK;
+}
+
 int crb_eval_ws_reserve(crb_handle* h, int64_t bytes) {
     if (bytes <= h->eval_ws_bytes) return CRB_OK;
+    h->evq_valid = 0;
     CRB_CUDA(cudaDeviceSynchronize());
     cudaFree(h->eval_ws);
     h->eval_ws = nullptr;
@@ -318,50 +326,56 @@ int crb_lrt_prepare(crb_handle* h, const crb_opt* opt, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------ profiling hook
-static int prof_drain(crb_handle* h) {
-    for (int k = 0; k < h->prof_n; ++k) {
+static int prof_drain(crb_handle* h, int tag) {
+    for (int k = 0; k < h->prof_n[tag]; ++k) {
         float ms = 0.f;
-        CRB_CUDA(cudaEventSynchronize(h->prof_ev[2 * k + 1]));
-        CRB_CUDA(cudaEventElapsedTime(&ms, h->prof_ev[2 * k], h->prof_ev[2 * k + 1]));
-        h->prof_ms += (double)ms;
-        h->prof_launches++;
+        CRB_CUDA(cudaEventSynchronize(h->prof_ev[tag][2 * k + 1]));
+        CRB_CUDA(cudaEventElapsedTime(&ms, h->prof_ev[tag][2 * k], h->prof_ev[tag][2 * k + 1]));
+        h->prof_ms[tag] += (double)ms;
+        h->prof_launches[tag]++;
     }
-    h->prof_n = 0;
+    h->prof_n[tag] = 0;
     return CRB_OK;
 }
 
-int crb_prof_begin(crb_handle* h, cudaStream_t s) {
+int crb_prof_begin(crb_handle* h, cudaStream_t s, int tag) {
     if (!h->prof_on) return CRB_OK;
-    if (h->prof_n == CRB_PROF_CAP) { int rc = prof_drain(h); if (rc) return rc; }
-    CRB_CUDA(cudaEventRecord(h->prof_ev[2 * h->prof_n], s));
+    if (h->prof_n[tag] == CRB_PROF_CAP) { int rc = prof_drain(h, tag); if (rc) return rc; }
+    CRB_CUDA(cudaEventRecord(h->prof_ev[tag][2 * h->prof_n[tag]], s));
     return CRB_OK;
 }
 
-int crb_prof_end(crb_handle* h, cudaStream_t s) {
+int crb_prof_end(crb_handle* h, cudaStream_t s, int tag) {
     if (!h->prof_on) return CRB_OK;
-    CRB_CUDA(cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], s));
-    h->prof_n++;
+    CRB_CUDA(cudaEventRecord(h->prof_ev[tag][2 * h->prof_n[tag] + 1], s));
+    h->prof_n[tag]++;
     return CRB_OK;
 }
 
 extern "C" int crb_profile_enable(crb_handle* h, int32_t on) {
     CRB_CHECK_ARG(h, "null handle");
-    if (on && !h->prof_ev) {
-        h->prof_ev = (cudaEvent_t*)calloc(2 * CRB_PROF_CAP, sizeof(cudaEvent_t));
-        for (int k = 0; k < 2 * CRB_PROF_CAP; ++k) CRB_CUDA(cudaEventCreate(&h->prof_ev[k]));
+    if (on && !h->prof_ev[0]) {
+        for (int t = 0; t < CRB_PROF_TAGS; ++t) {
+            h->prof_ev[t] = (cudaEvent_t*)calloc(2 * CRB_PROF_CAP, sizeof(cudaEvent_t));
+            for (int k = 0; k < 2 * CRB_PROF_CAP; ++k) CRB_CUDA(cudaEventCreate(&h->prof_ev[t][k]));
+        }
     }
-    if (!on && h->prof_on) { int rc = prof_drain(h); if (rc) return rc; }
+    if (!on && h->prof_on)
+        for (int t = 0; t < CRB_PROF_TAGS; ++t) { int rc = prof_drain(h, t); if (rc) return rc; }
     h->prof_on = on ? 1 : 0;
     return CRB_OK;
 }
 
-extern "C" int crb_profile_read(crb_handle* h, double* step_kernel_ms, int64_t* n_launches) {
-    CRB_CHECK_ARG(h && step_kernel_ms && n_launches, "null argument");
-    int rc = prof_drain(h);
-    if (rc) return rc;
-    *step_kernel_ms = h->prof_ms;
-    *n_launches = h->prof_launches;
-    h->prof_ms = 0.0;
-    h->prof_launches = 0;
+extern "C" int crb_profile_read_tag(crb_handle* h, int32_t tag, double* ms, int64_t* n_launches) {
+    CRB_CHECK_ARG(h && ms && n_launches && tag >= 0 && tag < CRB_PROF_TAGS, "bad argument");
+    if (h->prof_ev[0]) { int rc = prof_drain(h, tag); if (rc) return rc; }
+    *ms = h->prof_ms[tag];
+    *n_launches = h->prof_launches[tag];
+    h->prof_ms[tag] = 0.0;
+    h->prof_launches[tag] = 0;
     return CRB_OK;
+}
+
+extern "C" int crb_profile_read(crb_handle* h, double* step_kernel_ms, int64_t* n_launches) {
+    return crb_profile_read_tag(h, 0, step_kernel_ms, n_launches);
 }

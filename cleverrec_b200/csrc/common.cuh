@@ -10,6 +10,8 @@
 #define CRB_SAMPLER_MAX_BLOCKS 4096u  // attempt guard (oracle/philox.py MAX_BLOCKS)
 #define CRB_LRT_TABLE 65536           // Adam lr_t table length; beyond it lr_t == lr in fp32
 #define CRB_DUP_CHUNK 256             // slots per work item of the duplicate-row reduction
+#define CRB_PROF_CAP 1024
+#define CRB_PROF_TAGS 4               // profiling hook: 0 fused step kernel, 1 staged fetch, 2 duplicate reduce / send, 3 owner's inbox pass
 
 void crb_set_error(const char* fmt, ...);
 
@@ -124,6 +126,13 @@ struct crb_handle {
     void* eval_ws;
     int64_t eval_ws_bytes;
     int64_t topk_stats[4];
+    // bf16 copy of the item table kept in the evaluation workspace between crb_score_topk calls (score_tc.cu): valid for exactly
+    // these arguments until a library call writes a table (crb_opt_to_dev clears it) or reuses the workspace
+    int evq_valid;
+    const void* evq_q;
+    const void* evq_hvec;
+    int64_t evq_items;
+    int32_t evq_dim, evq_kind;
     int64_t launches;
     // numpy_stream sampler mode (sampler_np.cu)
     void* np_state;        // device RandomState (624 words + pos)
@@ -161,14 +170,13 @@ struct crb_handle {
     cudaEvent_t ev_entry, ev_prep[2], ev_done[2];
     // profiling hook
     int prof_on;
-    int prof_n;          // event pairs recorded since last read
-    cudaEvent_t* prof_ev; // 2 * CRB_PROF_CAP events
-    double prof_ms;
-    int64_t prof_launches;
+    int prof_n[CRB_PROF_TAGS];          // event pairs recorded since last read, per tag (0 = the fused step kernel)
+    cudaEvent_t* prof_ev[CRB_PROF_TAGS]; // 2 * CRB_PROF_CAP events each
+    double prof_ms[CRB_PROF_TAGS];
+    int64_t prof_launches[CRB_PROF_TAGS];
 };
-#define CRB_PROF_CAP 1024
-int crb_prof_begin(crb_handle* h, cudaStream_t s);
-int crb_prof_end(crb_handle* h, cudaStream_t s);
+int crb_prof_begin(crb_handle* h, cudaStream_t s, int tag = 0);
+int crb_prof_end(crb_handle* h, cudaStream_t s, int tag = 0);
 
 static inline bool crb_is_device_ptr(const void* p) {
     if (!p) return false;

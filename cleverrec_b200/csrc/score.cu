@@ -283,6 +283,7 @@ extern "C" int crb_score_pairs(crb_handle* h, int32_t kind, const float* P, cons
     CRB_CUDA(cudaSetDevice(h->device));
     int rc = crb_eval_ws_reserve(h, 12 * n + 4096);
     if (rc) return rc;
+    h->evq_valid = 0;   // the staging area below overlays the cached bf16 item table
     Stage st = {h, s, (char*)h->eval_ws, 0, h->eval_ws_bytes};
     const int32_t *du, *di;
     float* ds;
@@ -322,6 +323,7 @@ extern "C" int crb_topk_segments(crb_handle* h, const float* scores, const int64
     }
     int rc = crb_eval_ws_reserve(h, 4 * total + 8 * (n_users + 1) + 4 * n_users * K + 4096);
     if (rc) return rc;
+    h->evq_valid = 0;
     Stage st = {h, s, (char*)h->eval_ws, 0, h->eval_ws_bytes};
     const float* dsc;
     const int64_t* doff;

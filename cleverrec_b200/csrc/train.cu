@@ -210,6 +210,7 @@ __device__ __forceinline__ void block_loss_store_(double v, double* block_loss) 
 // ------------------------------------------------------------------------------------------------ optimizer plumbing
 int crb_opt_to_dev(crb_handle* h, const crb_opt* opt, OptDev* o, int* opt_kind, cudaStream_t s) {
     CRB_CHECK_ARG(opt, "opt is null");
+    h->evq_valid = 0;   // every entry point that writes a table comes through here: the cached bf16 item table is stale from now on
     CRB_CHECK_ARG(opt->step >= 1 && opt->step < 0x7fffffffLL, "opt.step must be >= 1");
     o->lr = (float)opt->lr;
     o->b1 = (float)opt->beta1;
@@ -465,8 +466,10 @@ static int bpr_step_compute(crb_handle* h, const crb_table* P, const crb_table* 
     d.dim = a.dim; d.opt = od;
     d.dup_rows = h->dup_rows; d.work = h->work; d.multi = h->multi;
     d.dup_grad = h->dup_grad; d.dup_t = h->dup_t; d.partial = h->partial; d.ctr = h->ctr;
+    if ((rc = crb_prof_begin(h, s, 2))) return rc;
     rc = crb_launch_dup_pipeline(h, d, opt_kind, s);
     if (rc) return rc;
+    if ((rc = crb_prof_end(h, s, 2))) return rc;
     return crb_launch_loss_final(h, loss_dev, s);
 }
 

@@ -252,6 +252,7 @@ static size_t nais_smem(int d, int A, bool bwd, int concat) {
 }
 
 static int nais_ws(crb_handle* h, int64_t floats, cudaStream_t s) {
+    h->evq_valid = 0;
     return crb_eval_ws_reserve(h, floats * 4 + 1024) ? CRB_ERR_CUDA : CRB_OK;
 }
 

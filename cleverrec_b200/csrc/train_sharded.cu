@@ -354,9 +354,11 @@ static int launch_shard_t(crb_handle* h, const ShardStepArgs& a, int opt_kind, c
     const int gpb = 256 / LANES;
     int rc;
     // phase 1a: repeated item rows -> staging buffer (grid: every SM full, the loop covers the descriptor list)
+    if ((rc = crb_prof_begin(h, s, 1))) return rc;
     item_fetch_kernel<LANES, VPL><<<h->sm_count * 8, 256, 0, s>>>(a.sh, h->dup_rows, h->ctr, h->stage, a.dim);
     h->launches++;
     CRB_CUDA(cudaGetLastError());
+    if ((rc = crb_prof_end(h, s, 1))) return rc;
     if ((rc = crb_prof_begin(h, s))) return rc;
 #define CRB_SH_CASE(O)                                                                          \
     case O: {                                                                                   \
@@ -379,6 +381,7 @@ static int launch_shard_t(crb_handle* h, const ShardStepArgs& a, int opt_kind, c
     d.dup_grad = h->dup_grad; d.dup_t = h->dup_t; d.partial = h->partial; d.ctr = h->ctr;
     d.send = a.sh.send;
     const int grid = h->sm_count * 4;
+    if ((rc = crb_prof_begin(h, s, 2))) return rc;
 #define CRB_SHDUP_CASE(O)                                                        \
     case O:                                                                      \
         dup_reduce_kernel<LANES, VPL, O, true><<<grid, 256, 0, s>>>(d);          \
@@ -388,7 +391,7 @@ static int launch_shard_t(crb_handle* h, const ShardStepArgs& a, int opt_kind, c
 #undef CRB_SHDUP_CASE
     h->launches += 2;
     CRB_CUDA(cudaGetLastError());
-    return CRB_OK;
+    return crb_prof_end(h, s, 2);
 }
 
 template <int LANES, int VPL>
@@ -398,12 +401,14 @@ static int launch_inbox_t(crb_handle* h, const InboxApplyArgs& a, int opt_kind, 
     const int64_t cap = (int64_t)h->sm_count * 32;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
+    int rc;
+    if ((rc = crb_prof_begin(h, s, 3))) return rc;
 #define CRB_IN_CASE(O) case O: inbox_apply_kernel<LANES, VPL, O><<<(int)grid, 256, 0, s>>>(a); break;
     switch (opt_kind) { CRB_IN_CASE(OPT_SGD) CRB_IN_CASE(OPT_ADAGRAD) CRB_IN_CASE(OPT_ADAM_LAZY) CRB_IN_CASE(OPT_ADAM_TF1) }
 #undef CRB_IN_CASE
     h->launches++;
     CRB_CUDA(cudaGetLastError());
-    return CRB_OK;
+    return crb_prof_end(h, s, 3);
 }
 
 #define CRB_DIM_DISPATCH(dim, FN, ...)                                   \

@@ -87,10 +87,11 @@ class Engine(object):
     def profile(self, on):
         check(self.lib.crb_profile_enable(self.h, 1 if on else 0))
 
-    def profile_read(self):
-        """-> (milliseconds spent in the fused step kernel, launches) since the last read"""
+    def profile_read(self, tag=0):
+        """-> (milliseconds spent in the bracketed kernel, launches) since the last read.  tag 0 = the fused step kernel,
+        1 = staged fetch (multi-GPU), 2 = duplicate reduce / send, 3 = the owner's inbox pass (multi-GPU)."""
         ms, n = C.c_double(), C.c_int64()
-        check(self.lib.crb_profile_read(self.h, C.byref(ms), C.byref(n)))
+        check(self.lib.crb_profile_read_tag(self.h, tag, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
     # ------------------------------------------------------------------ history
@@ -534,6 +535,32 @@ class Engine(object):
         check(self.lib.crb_topk_segments(self.h, ptr(scores), ptr(offsets), n_users, K, 1 if ascending else 0, ptr(out), self.stream))
         return out
 
+    def score_pairs_topk(self, kind, P, Q, seg_users, items, offsets, K, hvec=None, ascending=False):
+        """test_model_loo's predict + argsort in one kernel: for segment k (user row seg_users[k], candidates
+        items[offsets[k]:offsets[k+1]]) the K best positions inside the segment, -1 padded.  Host feeds -> NumPy, device -> tensor.
+        Shapes the fused kernel does not take (K > 32, dim % 4 != 0) run crb_score_pairs + crb_topk_segments: same results."""
+        n_users = len(offsets) - 1
+        host = not isinstance(items, torch.Tensor)
+        if K > 32 or P.shape[1] % 4 != 0 or P.shape[1] > 512:
+            lens = np.diff(np.asarray(offsets.cpu() if isinstance(offsets, torch.Tensor) else offsets, dtype=np.int64))
+            if host:
+                u = np.repeat(np.asarray(seg_users, dtype=np.int32), lens)
+            else:
+                u = torch.repeat_interleave(torch.as_tensor(seg_users, dtype=torch.int32, device=self.device), torch.from_numpy(lens).to(self.device))
+            return self.topk_segments(self.score_pairs(kind, P, Q, u, items, hvec=hvec), offsets, K, ascending=ascending)
+        if host:
+            seg_users, items = np.ascontiguousarray(seg_users, dtype=np.int32), np.ascontiguousarray(items, dtype=np.int32)
+            offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+            out = np.empty((n_users, K), dtype=np.int32)
+        else:
+            seg_users = torch.as_tensor(seg_users, dtype=torch.int32, device=self.device).contiguous()
+            items = items.to(torch.int32).contiguous()
+            offsets = torch.as_tensor(offsets, dtype=torch.int64, device=self.device).contiguous()
+            out = torch.empty((n_users, K), dtype=torch.int32, device=self.device)
+        check(self.lib.crb_score_pairs_topk(self.h, kind, ptr(P), ptr(Q), ptr(hvec), P.shape[1], ptr(seg_users), ptr(items), ptr(offsets), n_users, K,
+                                            1 if ascending else 0, ptr(out), self.stream))
+        return out
+
     def score_topk(self, kind, P, Q, users, K, hvec=None, hist_users=None, exact=False, n_items=None, return_scores=False):
         """Best K unseen item ids of each user (test_model_rs).  users host -> NumPy out; device -> tensors."""
         users = self._feed_i32(users)
@@ -551,6 +578,11 @@ class Engine(object):
         check(self.lib.crb_score_topk(self.h, kind, ptr(P), ptr(Q), ptr(hvec), n_items, P.shape[1], ptr(users), ptr(hist_users), n, K,
                                       1 if exact else 0, ptr(items), ptr(scores), self.stream))
         return (items, scores) if return_scores else items
+
+    def invalidate_eval_cache(self):
+        """score_topk keeps the bf16 copy of the item table between calls; library calls that write tables drop it themselves.
+        Call this after writing Q / hvec with torch (e.g. restoring a checkpoint into the same buffer)."""
+        check(self.lib.crb_eval_cache_invalidate(self.h))
 
     def score_topk_stats(self):
         st = (C.c_int64 * 4)()

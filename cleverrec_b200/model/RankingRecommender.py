@@ -120,34 +120,43 @@ class RankingRecommender(Recommender):
         """user-side row of each flattened pair (FISM-like models override: rows of the precomputed user matrix)."""
         return u_idx
 
-    def test_model_loo(self):
-        HR, MRR, NDCG = defaultdict(list), defaultdict(list), defaultdict(list)  # evaluation metrics
-        self._before_eval()
-        offsets, u_dev, i_dev, i_host = self._loo_feed()
-        kind, P, Q, hvec = self._score_spec()
-        K = self.topk[-1]
-        for t_id in range(self.test_batches):
-            a, b = t_id * self.batch_size_t, min((t_id + 1) * self.batch_size_t, len(self.test_users))
-            lo, hi = int(offsets[a]), int(offsets[b])
-            # Predict: pre_scores = sess.run(self.pre_scores, {u_idx, i_idx})
-            scores = self.engine.score_pairs(kind, P, Q, self._pair_users(u_dev[lo:hi]), i_dev[lo:hi], hvec=hvec)
-            # Evaluate: args_u = np.argsort(-pre_scores_u)[:topk[-1]]  (ascending for cml_like)
-            seg = torch.from_numpy(offsets[a:b + 1] - lo).to(self.engine.device)
-            args = self.engine.topk_segments(scores, seg, K, ascending=self.cml_like).cpu().numpy()
-            real_lists, rec = [], np.full((b - a, K), -1, dtype=np.int64)
-            for k in range(b - a):
-                u = self.test_users[a + k]
+    def _loo_lists(self):
+        """Per test user: the real items (ui_test[u][neg_samples:], RankingRecommender.py:283-285), built once."""
+        if getattr(self, '_real_cache', None) is None or self._real_cache[0] is not self.test_users:
+            real_lists = []
+            for u in self.test_users:
                 real_items = self.data.ui_test[u][self.neg_samples:]
                 if not isinstance(real_items, list):  # loo
                     real_items = [real_items]
                 real_lists.append(real_items)
-                valid = args[k] >= 0
-                rec[k, valid] = i_host[offsets[a + k] + args[k][valid]]  # np.take(ui_test[u], args_u)
-            for kid in range(len(self.topk)):
-                hr, mrr, ndcg = batch_ranking_metrics(real_lists, rec, self.topk[kid])
-                HR[kid].extend(hr.tolist())
-                MRR[kid].extend(mrr.tolist())
-                NDCG[kid].extend(ndcg.tolist())
+            dev = self.engine.device
+            self._real_cache = (self.test_users, real_lists, torch.as_tensor(np.asarray(self.test_users, dtype=np.int32), device=dev))
+        return self._real_cache[1], self._real_cache[2]
+
+    def test_model_loo(self):
+        """The reference walks the test users in batches of test.batch_size (one sess.run + a Python loop per batch, :255-298); every
+        user's result is independent of the batching, so here ALL test users go through one fused score + top-K call
+        (crb_score_pairs_topk) and one vectorised metric pass; the returned lists are in self.test_users order as in the reference."""
+        HR, MRR, NDCG = defaultdict(list), defaultdict(list), defaultdict(list)  # evaluation metrics
+        self._before_eval()
+        offsets, u_dev, i_dev, i_host = self._loo_feed()
+        real_lists, users_dev = self._loo_lists()
+        kind, P, Q, hvec = self._score_spec()
+        K = self.topk[-1]
+        n = len(self.test_users)
+        if n == 0:
+            return HR, MRR, NDCG
+        # Predict + evaluate: args_u = np.argsort(-pre_scores_u)[:topk[-1]]  (ascending for cml_like)
+        args = self.engine.score_pairs_topk(kind, P, Q, self._pair_users(users_dev), i_dev, offsets, K, hvec=hvec, ascending=self.cml_like)
+        args = args.cpu().numpy().astype(np.int64)
+        valid = args >= 0
+        idx = np.minimum(offsets[:-1, None] + np.where(valid, args, 0), max(int(offsets[-1]) - 1, 0))
+        rec = np.where(valid, i_host[idx] if i_host.shape[0] else -1, -1)   # np.take(ui_test[u], args_u)
+        for kid in range(len(self.topk)):
+            hr, mrr, ndcg = batch_ranking_metrics(real_lists, rec, self.topk[kid])
+            HR[kid].extend(hr.tolist())
+            MRR[kid].extend(mrr.tolist())
+            NDCG[kid].extend(ndcg.tolist())
         return HR, MRR, NDCG
 
     # ---- Random split with all ------------------------------------------------------------------------------
@@ -156,22 +165,24 @@ class RankingRecommender(Recommender):
         return np.asarray(cur_users, dtype=np.int32), None
 
     def test_model_rs(self):
+        """One fused call for ALL test users (the reference's per-batch loop :201-246 gives each user the same result whatever
+        test.batch_size is): the item table is converted for the tensor cores once per evaluation instead of once per batch."""
         HR, MRR, NDCG = defaultdict(list), defaultdict(list), defaultdict(list)  # evaluation metrics
         self._before_eval()
         kind, P, Q, hvec = self._score_spec()
         K = self.topk[-1]
-        for t_id in range(self.test_batches):
-            cur_users = self.test_users[t_id * self.batch_size_t:(t_id + 1) * self.batch_size_t]
-            rows, hist = self._fullrank_users(cur_users)
-            # pre_scores = sess.run(...); argsort; skip ui_train[u]; first topk[-1]  -> one fused call
-            topk_items = self.engine.score_topk(kind, P, Q, rows, K, hvec=hvec, hist_users=hist, exact=self.score_exact,
-                                                n_items=self.data.item_nums)
-            real_lists = [self.data.ui_test[u] for u in cur_users]
-            for kid in range(len(self.topk)):
-                hr, mrr, ndcg = batch_ranking_metrics(real_lists, topk_items, self.topk[kid])
-                HR[kid].extend(hr.tolist())
-                MRR[kid].extend(mrr.tolist())
-                NDCG[kid].extend(ndcg.tolist())
+        if not self.test_users:
+            return HR, MRR, NDCG
+        rows, hist = self._fullrank_users(self.test_users)
+        # pre_scores = sess.run(...); argsort; skip ui_train[u]; first topk[-1]  -> one fused call
+        topk_items = self.engine.score_topk(kind, P, Q, rows, K, hvec=hvec, hist_users=hist, exact=self.score_exact,
+                                            n_items=self.data.item_nums)
+        real_lists = [self.data.ui_test[u] for u in self.test_users]
+        for kid in range(len(self.topk)):
+            hr, mrr, ndcg = batch_ranking_metrics(real_lists, topk_items, self.topk[kid])
+            HR[kid].extend(hr.tolist())
+            MRR[kid].extend(mrr.tolist())
+            NDCG[kid].extend(ndcg.tolist())
         return HR, MRR, NDCG
 
     @timer('run_model')

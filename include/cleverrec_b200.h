@@ -376,6 +376,15 @@ int crb_adam_flush(crb_handle* h, const crb_table* T, const crb_opt* opt, void* 
 int crb_score_pairs(crb_handle* h, int32_t kind, const float* P, const float* Q, const float* hvec, int32_t dim,
                     const int32_t* u, const int32_t* i, int64_t n, float* scores, void* stream);
 
+/* test_model_loo's scoring AND ranking in one kernel (model/RankingRecommender.py:257-288): for user segment k -- the pairs
+ * (seg_user[k], items[offsets[k] .. offsets[k+1])) -- the K best positions inside the segment, np.argsort(-scores_u)[:K] under the
+ * documented tie rule (ascending != 0: distance models), -1 padded.  A warp owns a user and keeps the running top-K in registers;
+ * scores are the canonical chain of crb_score_pairs bit for bit but never reach HBM.  Buffers DEVICE or HOST.  Needs K <= 32,
+ * dim % 4 == 0, dim <= 512 (else CRB_ERR_UNSUPPORTED: use crb_score_pairs + crb_topk_segments). */
+int crb_score_pairs_topk(crb_handle* h, int32_t kind, const float* P, const float* Q, const float* hvec, int32_t dim,
+                         const int32_t* seg_user, const int32_t* items, const int64_t* offsets, int64_t n_users, int32_t K,
+                         int32_t ascending, int32_t* topk_pos, void* stream);
+
 /* Lines :281-288 of test_model_loo for a ragged batch: user k owns scores[offsets[k]..offsets[k+1]); writes the
  * positions of its best K candidates (score descending -- ascending when `ascending` --, ties by position
  * ascending; -1 padded) to topk_pos[k*K..].  DEVICE or HOST buffers. */
@@ -395,6 +404,10 @@ int crb_score_topk(crb_handle* h, int32_t kind, const float* P, const float* Q, 
 /* statistics of the last crb_score_topk(exact=0) call: [0] users certified by the tensor-core pass,
  * [1] users re-run exactly, [2] candidate slots used (max over users). */
 int crb_score_topk_stats(crb_handle* h, int64_t stats[4]);
+/* crb_score_topk keeps the tensor-core path's bf16 copy of the item table between calls with the same (Q, hvec, n_items, dim,
+ * kind); every library call that writes a table drops it.  A caller that writes Q / hvec ITSELF between two crb_score_topk calls
+ * (e.g. restores a checkpoint into the same buffer) must call this. */
+int crb_eval_cache_invalidate(crb_handle* h);
 
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 int64_t crb_launch_count(crb_handle* h);
@@ -404,6 +417,9 @@ int64_t crb_launch_count(crb_handle* h);
  * kernel milliseconds and the number of launches since the last read, and resets the accumulators. */
 int crb_profile_enable(crb_handle* h, int32_t on);
 int crb_profile_read(crb_handle* h, double* step_kernel_ms, int64_t* n_launches);
+/* The same for the other bracketed kernels of a step: tag 0 = fused step kernel, 1 = item_fetch_kernel (multi-GPU),
+ * 2 = duplicate reduce / send pipeline, 3 = inbox_apply_kernel (multi-GPU). */
+int crb_profile_read_tag(crb_handle* h, int32_t tag, double* ms, int64_t* n_launches);
 
 #ifdef __cplusplus
 }

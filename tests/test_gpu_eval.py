@@ -117,3 +117,77 @@ def test_score_pairs_large_calls_bit_exact(eng, kind, d):
     got = eng.score_pairs(kind, torch.tensor(P).cuda(), torch.tensor(Q).cuda(), torch.tensor(u, dtype=torch.int32).cuda(),
                           torch.tensor(i, dtype=torch.int32).cuda(), hvec=hd)
     assert np.array_equal(got.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+@pytest.mark.parametrize("d", [8, 64, 100, 128, 256])
+def test_score_pairs_topk_fused_bit_exact(eng, kind, d):
+    """loo_topk_kernel (test_model_loo's predict + argsort fused; scores never reach HBM) == oracle scores + oracle top-K per segment:
+    positions bit-exact, ragged / empty / shorter-than-K segments, exact score ties (duplicate candidates), K in {1, 20, 32}."""
+    rs = np.random.RandomState(100 * kind + d)
+    U, I = 40, 300
+    P, Q = rs.randn(U, d).astype(np.float32), rs.randn(I, d).astype(np.float32)
+    hvec = rs.randn(d if kind == 1 else I).astype(np.float32) if kind in (1, 3) else None
+    lens = np.array([1001, 0, 1, 19, 20, 21, 33, 64, 100, 333, 7, 32], dtype=np.int64)
+    offsets = np.concatenate([[0], np.cumsum(lens)])
+    seg_users = rs.randint(0, U, lens.shape[0]).astype(np.int32)
+    items = rs.randint(0, I, offsets[-1]).astype(np.int32)        # 1001 draws over 300 items: many exact ties inside a segment
+    u_flat = np.repeat(seg_users, lens)
+    scores = O.score_pairs(kind, P, Q, u_flat, items, hvec)
+    Pd, Qd = torch.tensor(P).cuda(), torch.tensor(Q).cuda()
+    hd = torch.tensor(hvec).cuda() if hvec is not None else None
+    for K in (1, 20, 32):
+        for asc in (False, True):
+            want = O.topk_segments(scores, offsets, K, asc)
+            got_host = eng.score_pairs_topk(kind, Pd, Qd, seg_users, items, offsets, K, hvec=hd, ascending=asc)
+            got_dev = eng.score_pairs_topk(kind, Pd, Qd, torch.tensor(seg_users).cuda(), torch.tensor(items).cuda(), torch.tensor(offsets).cuda(), K,
+                                           hvec=hd, ascending=asc)
+            assert np.array_equal(got_host, want), (K, asc)
+            assert np.array_equal(got_dev.cpu().numpy(), want), (K, asc)
+    want = O.topk_segments(scores, offsets, 50, False)            # K > 32: the two-kernel route behind the same call
+    assert np.array_equal(eng.score_pairs_topk(kind, Pd, Qd, seg_users, items, offsets, 50, hvec=hd), want)
+
+
+def test_fullrank_item_table_cache_tracks_writes(eng):
+    """The tensor-core path keeps its bf16 copy of Q between calls (the reference's test.batch_size loop ranks users in many small
+    calls): a second call with the same table skips the conversion, a training step through the library drops the copy, a torch
+    write needs invalidate_eval_cache().  Every result equals the oracle on the CURRENT table."""
+    from cleverrec_b200.engine import Optimizer, Table
+    d = synthetic_data(120, 2500, 40, seed=21)
+    pu, pi, rp, sc = X.build_history(d.ui_train, d.user_nums)
+    eng.set_history(d.ui_train, d.user_nums, d.item_nums)
+    rs = np.random.RandomState(3)
+    dim = 64
+    P = Table(torch.tensor((rs.randn(d.user_nums, dim) * 0.1).astype(np.float32)).cuda(), "SGD")
+    Q = Table(torch.tensor((rs.randn(d.item_nums, dim) * 0.1).astype(np.float32)).cuda(), "SGD")
+    users = np.arange(d.user_nums, dtype=np.int32)
+
+    def check_now():
+        want, _ = O.fullrank_topk(0, P.w.cpu().numpy(), Q.w.cpu().numpy(), users, rp, sc, 20)
+        l0 = eng.launches
+        got = eng.score_topk(0, P.w, Q.w, users, 20)
+        assert np.array_equal(got, want)
+        return eng.launches - l0
+    first = check_now()
+    assert check_now() == first - 1                       # prep_kernel<Q> skipped
+    opt = Optimizer("SGD", 0.5)
+    u, i, j = rs.randint(0, d.user_nums, 4096), rs.randint(0, d.item_nums, 4096), rs.randint(0, d.item_nums, 4096)
+    eng.train_step_bpr(P, Q, opt, u, i, j, 0.01)
+    assert check_now() == first                           # the step dropped the cached copy
+    Q.w.mul_(-1.0)
+    eng.invalidate_eval_cache()
+    assert check_now() == first
+
+
+def test_fullrank_topk_beyond_32(eng):
+    """topk=[10,20,50] with data.split_way=rs: K > 32 is beyond the tensor-core path's candidate lists and runs the exact kernel behind
+    the same call (the reference's argsort takes any K)."""
+    d = synthetic_data(60, 900, 30, seed=33)
+    pu, pi, rp, sc = X.build_history(d.ui_train, d.user_nums)
+    eng.set_history(d.ui_train, d.user_nums, d.item_nums)
+    rs = np.random.RandomState(5)
+    P, Q = (rs.randn(d.user_nums, 32) * 0.1).astype(np.float32), (rs.randn(d.item_nums, 32) * 0.1).astype(np.float32)
+    users = np.arange(d.user_nums, dtype=np.int32)
+    want, _ = O.fullrank_topk(0, P, Q, users, rp, sc, 50)
+    got = eng.score_topk(0, torch.tensor(P).cuda(), torch.tensor(Q).cuda(), users, 50, exact=False)
+    assert np.array_equal(got, want)
