@@ -110,7 +110,10 @@ def build_history_device(torch, dev, users, items, mean_hist, seed, user_lo=0, u
 # --------------------------------------------------------------------------------------------- reference arm (CPU)
 def cpu_reference_steps(w, n_steps, batch, threads, seed=0):
     """The reference's CPU path restated (oracle/): Python-loop sampler with np.random (utils/sampler.py:46-74) +
-    one TF-1 graph step per batch in torch-CPU fp32 (BPR.py:31-44, Adam).  Returns seconds per step list."""
+    one TF-1 graph step per batch in torch-CPU fp32 (BPR.py:31-44, Adam).  Same configuration as the GPU arm: full-size tables
+    (users x d and items x d, when host memory allows) and the GPU arm's batch; the bounded part is the epoch -- the sampler walks
+    only as many users (random rows of the user table) as fill ONE batch per step, not all of them.
+    Returns (seconds per step list, triplets per step, users sampled per step, user-table rows)."""
     import torch
     from oracle import ref_host as H
     from oracle import tf1_restatement as T
@@ -118,21 +121,32 @@ def cpu_reference_steps(w, n_steps, batch, threads, seed=0):
     rs = np.random.RandomState(seed)
     np.random.seed(seed)
     items, dim, R = w["items"], w["dim"], w["neg_ratio"]
-    n_users = max(8, int(math.ceil(batch / (R * w["mean_hist"]))))  # users whose full epoch is about one batch
-    ui_train = {}
-    for u in range(n_users):
-        n = int(min(items // 2, 1 + rs.randint(0, 2 * (w["mean_hist"] - 1) + 1)))
-        ui_train[u] = np.unique(rs.randint(0, items, n)).tolist()
+    n_sample = max(8, int(math.ceil(1.08 * batch / (R * w["mean_hist"]))))  # users whose full epoch is about one batch
+    table_rows = w["users"]
+    try:
+        import psutil
+        need = 3.2 * 4.0 * dim * (w["users"] + items)     # tables + Adam m, v (+ slack)
+        if psutil.virtual_memory().available < need:
+            table_rows = n_sample
+    except Exception:
+        table_rows = n_sample
+    n_sample = min(n_sample, table_rows)
 
     class D(object):
         pass
     data = D()
-    data.ui_train, data.item_nums, data.user_nums = ui_train, items, n_users
-    g = torch.Generator().manual_seed(seed)
-    params = {"P": torch.randn(n_users, dim, generator=g) * 0.01, "Q": torch.randn(items, dim, generator=g) * 0.01}
+    data.item_nums, data.user_nums = items, table_rows
+    params = {"P": torch.empty(table_rows, dim).normal_(0, 0.01, generator=torch.Generator().manual_seed(seed)),
+              "Q": torch.empty(items, dim).normal_(0, 0.01, generator=torch.Generator().manual_seed(seed + 1))}
     opt = T.TF1Optimizer("Adam", 1e-3, adam_mode="lazy")  # row-sparse apply: generous to the CPU baseline
     times, done = [], 0
     for _ in range(n_steps):
+        rows = np.sort(rs.choice(table_rows, n_sample, replace=False)) if table_rows > n_sample else np.arange(n_sample)
+        ui_train = {}
+        for u in rows.tolist():   # synthetic histories of the workload's law (not timed: the reference gets them from its preprocessing)
+            n = int(min(items // 2, 1 + rs.randint(0, 2 * (w["mean_hist"] - 1) + 1)))
+            ui_train[u] = np.unique(rs.randint(0, items, n)).tolist()
+        data.ui_train = ui_train
         t0 = time.perf_counter()
         out = H.pairwise_ranking_sampler(data, R, batch)
         n = min(batch, out[1].shape[0])
@@ -140,7 +154,13 @@ def cpu_reference_steps(w, n_steps, batch, threads, seed=0):
         T.bpr_step_rowsparse(params, b, 0.01, opt)
         times.append(time.perf_counter() - t0)
         done = n
-    return times, done, n_users
+    return times, done, n_sample, table_rows
+
+
+def cpu_sample_text(done, n_sample, table_rows, w):
+    return ("%d triplets/step: reference-algorithm Python sampler (np.random, utils/sampler.py:46-74) over %d users per step (random rows of a "
+            "%d-row user table) + restated TF-1 BPR/Adam step in torch-CPU fp32 (row-sparse apply), %d-item x d=%d item table"
+            % (done, n_sample, table_rows, w["items"], w["dim"]))
 
 
 def run_reference(args, w):
@@ -148,17 +168,17 @@ def run_reference(args, w):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    batch = min(w["batch"], 1 << 17)  # bounded sample per step (sampler is ~2e5 triplets/s/core in pure Python)
-    times, done, n_users = cpu_reference_steps(w, args.warmup + args.steps, batch, threads)
+    batch = args.ref_batch or w["batch"]   # the GPU arm's per-GPU batch (2^20 at s_large: ~6 s per step on the host cores)
+    times, done, n_sample, table_rows = cpu_reference_steps(w, args.warmup + args.steps, batch, threads)
     t = times[args.warmup:]
     ms = 1000.0 * sum(t) / len(t)
     value = done / (ms / 1000.0)
-    sample = ("%d triplets/step: reference-algorithm Python sampler (np.random, utils/sampler.py:46-74) over %d synthetic users + "
-              "restated TF-1 BPR/Adam step in torch-CPU fp32 (row-sparse apply), %d-item x d=%d table" % (done, n_users, w["items"], w["dim"]))
+    sample = cpu_sample_text(done, n_sample, table_rows, w)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "users": w["users"], "items": w["items"], "dim": w["dim"], "batch_per_step": done,
-                       "neg_ratio": w["neg_ratio"], "optimizer": "Adam"},
+            "config": {"workload": args.workload, "users": w["users"], "items": w["items"], "dim": w["dim"], "batch_per_gpu": done,
+                       "neg_ratio": w["neg_ratio"], "item_popularity": "uniform", "optimizer": "Adam", "reg": 0.01,
+                       "user_table_rows_on_host": table_rows, "sampler_in_timed_region": True},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -307,6 +327,26 @@ def run_ours(args, w):
         assert bool(torch.isfinite(host_losses).all()) and float(host_losses.min()) > 0
         e2e_path = "ShardedBPR.run_steps(feeds=...): the epoch loop over host feed arrays, per-step H2D feed + per-step D2H loss, feeds staged one step ahead"
     e2e_value = world * B * n_e2e / max_over_ranks(e2e_s)
+    # the same loop with the SAMPLER inside the timed region (what the reference arm times): triplets drawn on the device from the
+    # resident history (no host input exists for such a step), every step's loss returned to the host
+    n_ws = args.steps
+    first_ws = 0 if (steps_total + 2 * n_ws) * B > rows else steps_total * B
+    if sharded is None:
+        hl = np.zeros(n_ws, dtype=np.float64)
+        eng.train_epoch_bpr(P, Q, opt, 9, 1, first_ws, B, 1, R, reg, hl[:1])   # warm
+        barrier()
+        t0 = time.perf_counter()
+        eng.train_epoch_bpr(P, Q, opt, 9, 1, first_ws, B, n_ws, R, reg, hl)     # returns when the losses are on the host
+        ws_s = time.perf_counter() - t0
+    else:
+        hl = torch.zeros(n_ws, dtype=torch.float64).pin_memory()
+        sharded.run_steps(1, reg, neg_ratio=R, seed=9, epoch=1, first=first_ws, batch=B, host_losses=hl[:1])   # warm
+        barrier()
+        t0 = time.perf_counter()
+        sharded.run_steps(n_ws, reg, neg_ratio=R, seed=9, epoch=1, first=first_ws, batch=B, host_losses=hl)
+        torch.cuda.synchronize()
+        ws_s = time.perf_counter() - t0
+    e2e_with_sampling = world * B * n_ws / max_over_ranks(ws_s)
     if sharded is not None:
         sharded.check()   # raises if a cross-rank barrier timed out or the sampler gave up on a row
 
@@ -367,20 +407,37 @@ def run_ours(args, w):
         except Exception as e:  # reported, never hidden
             ev = {"error": str(e)}
 
+    # ---- the whole user table through one call (north_star: "full-rank top-20 evaluation of 10M users x 2M items in seconds") ----
+    if args.eval_full and sharded is None and ev is not None and "error" not in ev:
+        try:
+            allu = torch.arange(u_lo, u_hi, device=dev, dtype=torch.int32)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            full_ids = eng.score_topk(0, P.w, Q.w, allu, 20, exact=args.eval_exact)
+            e1.record()
+            barrier()
+            fms = e0.elapsed_time(e1)
+            ev["full_sweep"] = {"users": int(allu.numel()), "items": items, "seconds": fms / 1000.0, "users_per_sec": allu.numel() / (fms / 1000.0),
+                                "frac_of_tensor_peak": 2.0 * allu.numel() * items * dim / (fms / 1000.0) / 1e12 / tf,
+                                "stats": eng.score_topk_stats(), "measured": True}
+            del full_ids, allu
+        except Exception as e:
+            ev["full_sweep"] = {"error": str(e)}
+
     # ---- secondary metric: sampled-candidate evaluation (test_model_loo with 1000 negatives, SURVEY 8(d) "Eval loo") ----
     ev_loo = None
     if args.eval_users > 0 and sharded is None and ev is not None and "error" not in ev:
         try:
             n_loo, n_cand = min(65536, args.eval_users, u_hi - u_lo), 1001
             g2 = torch.Generator(device=dev).manual_seed(99)
-            lu = torch.arange(n_loo, device=dev, dtype=torch.int32).repeat_interleave(n_cand)
+            lu = torch.arange(n_loo, device=dev, dtype=torch.int32)
             li = torch.randint(0, items, (n_loo * n_cand,), device=dev, generator=g2, dtype=torch.int32)
             seg = torch.arange(n_loo + 1, device=dev, dtype=torch.int64) * n_cand
-            out = torch.empty(n_loo * n_cand, dtype=torch.float32, device=dev)
 
             def loo_once():
-                eng.score_pairs(0, P.w, Q.w, lu, li, out=out)          # pre_scores of every (user, candidate) pair
-                return eng.topk_segments(out, seg, 20)                  # np.argsort(-scores_u)[:20] per user
+                # pre_scores of every (user, candidate) pair + np.argsort(-scores_u)[:20] per user, one kernel (crb_score_pairs_topk)
+                return eng.score_pairs_topk(0, P.w, Q.w, lu, li, seg, 20)
             loo_once()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
@@ -394,7 +451,8 @@ def run_ours(args, w):
                       "candidates_per_user": n_cand, "ms": lms,
                       "roofline": {"bound": "hbm", "achieved": lbytes / (lms / 1000.0) / 1e9, "peak": hbm, "unit": "GB/s",
                                    "frac": lbytes / (lms / 1000.0) / 1e9 / hbm, "algorithmic_bytes": lbytes}}
-            del lu, li, out
+            ev_loo["path"] = "loo_topk_kernel: scores and top-20 in one kernel, the score vector never reaches HBM"
+            del lu, li
         except Exception as e:
             ev_loo = {"error": str(e)}
 
@@ -415,21 +473,36 @@ def run_ours(args, w):
             ems = float(t.item())
             flops = 2.0 * world * n_eval * items * dim
             ev = {"metric": "fullrank_top20_eval_users_per_sec", "value": world * n_eval / (ems / 1000.0), "unit": "users/s", "users": world * n_eval,
-                  "items": items, "ms": ems, "path": "item shards all-gathered over NVLink once, then every rank ranks its own users: bf16 tcgen05 + certified fp32 rescoring",
+                  "users_per_gpu": n_eval, "items": items, "ms": ems,
+                  "path": "item shards all-gathered over NVLink once, then every rank ranks its own users: bf16 tcgen05 + certified fp32 rescoring",
                   "roofline": {"bound": "tensor", "achieved": flops / (ems / 1000.0) / 1e12 / world, "peak": tf, "unit": "TFLOP/s per GPU",
                                "frac": flops / (ems / 1000.0) / 1e12 / world / tf}}
+            if args.eval_full:
+                # every user of the job: each rank ranks ALL its own users in one call (the all-gather of the item shards is inside)
+                n_all = u_hi - u_lo
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()
+                e0.record()
+                sev.topk(20, batch_users=n_all)
+                e1.record()
+                barrier()
+                t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                fms = float(t.item())
+                ev["full_sweep"] = {"users": users, "items": items, "seconds": fms / 1000.0, "users_per_sec": users / (fms / 1000.0),
+                                    "frac_of_tensor_peak": 2.0 * users * items * dim / (fms / 1000.0) / 1e12 / tf / world, "measured": True}
         except Exception as e:
             ev = {"error": str(e)}
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        times, done, n_users = cpu_reference_steps(w, 3, min(B, 1 << 17), threads)
+        times, done, n_sample, table_rows = cpu_reference_steps(w, 3, args.ref_batch or B, threads)
         sec = sum(times[1:]) / len(times[1:])
-        cpu = {"value": done / sec, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d triplets/step x 2 timed steps: reference-algorithm Python sampler (utils/sampler.py:46-74) + restated TF-1 BPR/Adam "
-                         "step (torch-CPU fp32, row-sparse apply), %d users, %d items, d=%d" % (done, n_users, items, dim)}
+        cpu = {"value": done / sec, "unit": UNIT, "cores": threads, "kind": "port", "sample": "2 timed steps (1 warm-up) of " + cpu_sample_text(done, n_sample, table_rows, w)}
+    if world > 1:
+        dist.barrier()   # the other ranks wait for rank 0's host baseline before the process group goes away
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -441,7 +514,9 @@ def run_ours(args, w):
                                            "over NVLink peer memory (per-rank de-duplicated), flag barriers in peer memory, no data-path collective" % world),
                            "setup_s": round(t_setup, 1)},
                 "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 8, "steps": n_e2e, "path": e2e_path,
-                        "blocking_per_step_value": e2e_sync},
+                        "blocking_per_step_value": e2e_sync,
+                        "with_device_sampling": {"value": e2e_with_sampling, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
+                                                 "note": "sampler inside the timed region like the reference arm: triplets drawn on the device, per-step loss to the host"}},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "eval": ev, "eval_loo": ev_loo, "final_loss": loss_last}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -459,7 +534,9 @@ def main():
     ap.add_argument("--adam-mode", dest="adam_mode", default="tf1", choices=["tf1", "lazy"])
     ap.add_argument("--eval-users", dest="eval_users", type=int, default=262144)
     ap.add_argument("--eval-exact", dest="eval_exact", action="store_true")
+    ap.add_argument("--no-eval-full", dest="eval_full", action="store_false", help="skip the sweep over ALL users (about 5 s at 10M users on one GPU)")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--ref-batch", dest="ref_batch", type=int, default=0, help="triplets per step of the CPU baseline / reference arm (default: the GPU arm's batch)")
     ap.add_argument("--item-popularity", dest="item_popularity", default="uniform", choices=["uniform", "zipf"],
                     help="popularity of the positives' items in the synthetic history (zipf = Zipf(1.0): hub rows repeat ~10^4 times per batch)")
     ap.add_argument("--sharded", action="store_true", help="use the multi-GPU code path even at N=1 (experiments)")
