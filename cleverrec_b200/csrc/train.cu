@@ -258,22 +258,7 @@ TableDev crb_to_dev(const crb_table* T) {
 }
 
 // ------------------------------------------------------------------------------------------------ K3: BPR
-struct BprArgs {
-    TableDev P, Q;
-    unsigned long long* metaU;
-    unsigned long long* metaI;
-    const int32_t* u;
-    const int32_t* i;
-    const int32_t* j;
-    const uint32_t* rk[3];
-    int64_t batch;
-    int dim;
-    float reg;
-    OptDev opt;
-    float* dup_grad;
-    uint32_t* dup_t;
-    double* block_loss;
-};
+#include "bpr_args.cuh"
 
 // CTAs per SM: the Adam variants need ~80 registers (3 CTAs).  SGD moves 3x fewer bytes per triplet and is bound by the bytes in
 // flight: it fits 64 registers without spilling and takes a fourth resident CTA (K3 1.03 -> 0.76 ms).  Adagrad spills at 64 registers
@@ -457,7 +442,7 @@ static int bpr_step_compute(crb_handle* h, const crb_table* P, const crb_table* 
     a.batch = batch; a.dim = P->dim; a.reg = reg; a.opt = od;
     a.dup_grad = h->dup_grad; a.dup_t = h->dup_t; a.block_loss = h->block_loss;
     if ((rc = crb_prof_begin(h, s))) return rc;
-    rc = CRB_DIM_DISPATCH(a.dim, launch_bpr_t, h, a, opt_kind, s);
+    rc = crb_bpr_ring_enabled(a.dim) ? crb_launch_bpr_ring(h, a, opt_kind, s) : CRB_DIM_DISPATCH(a.dim, launch_bpr_t, h, a, opt_kind, s);
     if (rc) return rc;
     if ((rc = crb_prof_end(h, s))) return rc;
     DupArgs d;

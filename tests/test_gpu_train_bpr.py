@@ -190,3 +190,41 @@ def test_epoch_over_host_feeds_equals_step_by_step(kind):
         eng.adam_flush(Pb, ob); eng.adam_flush(Qb, ob)
         assert torch.equal(Pb.w, Pa.w) and torch.equal(Qb.w, Qa.w), mode
     eng.close()
+
+
+@pytest.mark.parametrize("kind,mode", OPTS)
+@pytest.mark.parametrize("d", [32, 64, 100, 128, 256, 512])
+def test_ring_kernel_is_bit_identical_to_register_kernel(eng, kind, mode, d, monkeypatch):
+    """bpr_ring_kernel (row gathers as cp.async.bulk copies into a shared-memory ring, mbarrier hand-off, CRB_BPR_RING=1) runs the
+    same device functions on the same values as bpr_step_kernel: tables bit-identical after several device-sampled steps with
+    duplicated rows, hub rows, ragged last batch and (Adam tf1) rows that skip steps and are replayed."""
+    from cleverrec_b200.engine import Optimizer, Table
+    U, I, B, R = 700, 1500, 1000, 3     # row multiplicities stay <= 32: summation order (and so every bit) is defined
+    data = synthetic_data(U, I, 14, seed=d)
+    eng.set_history(data.ui_train, U, I)
+    n_rows = eng.epoch_rows(R)
+    n_steps = min(5, -(-n_rows // B))
+    g = torch.Generator().manual_seed(d)
+    P0, Q0 = torch.randn(U, d, generator=g) * 0.1, torch.randn(I, d, generator=g) * 0.1
+    out = []
+    for ring in ("0", "1"):
+        monkeypatch.setenv("CRB_BPR_RING", ring)
+        P, Q = Table(P0.clone().cuda(), kind, mode), Table(Q0.clone().cuda(), kind, mode)
+        opt = Optimizer(kind, 0.05 if kind != "Adam" else 0.01, adam_mode=mode)
+        losses = torch.zeros(n_steps, dtype=torch.float64, device="cuda")
+        eng.train_epoch_bpr(P, Q, opt, 3, 0, n_rows - n_steps * B if n_rows % B == 0 else n_rows - (n_steps - 1) * B - n_rows % B, B, n_steps, R, 0.01, losses)
+        # a host-fed step with a 30-fold row and a 7-row step
+        rs = np.random.RandomState(1)
+        u, i, j = rs.randint(0, U, 777), rs.randint(0, I, 777), rs.randint(0, I, 777)
+        i[:750:25] = 5
+        assert np.bincount(np.concatenate([i, j])).max() <= 32 and np.bincount(u).max() <= 32
+        l1 = eng.train_step_bpr(P, Q, opt, u, i, j, 0.01)
+        l2 = eng.train_step_bpr(P, Q, opt, u[:7], i[:7], j[:7], 0.01)
+        eng.adam_flush(P, opt); eng.adam_flush(Q, opt)
+        torch.cuda.synchronize()
+        out.append((losses.cpu().numpy(), l1, l2, P.w.clone(), Q.w.clone(), None if P.s1 is None else P.s1.clone(), None if Q.s1 is None else Q.s1.clone()))
+    a, b = out
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-12)
+    assert abs(a[1] - b[1]) <= 1e-12 * abs(a[1]) and abs(a[2] - b[2]) <= 1e-12 * abs(a[2])
+    for k in (3, 4, 5, 6):
+        assert (a[k] is None and b[k] is None) or torch.equal(a[k], b[k]), k
