@@ -75,6 +75,27 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def nvlink_counters(index):
+    """Sum of the per-link NVLink data counters of one GPU (`nvidia-smi nvlink -gt d`), bytes: (tx, rx) or None.  Read before and
+    after the timed steps at N > 1: measured wire payload per step, next to the formula."""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+                             timeout=10).stdout
+        tx = rx = 0
+        seen = False
+        for line in out.splitlines():
+            if "Data Tx:" in line or "Data Rx:" in line:
+                val = int(line.split(":")[-1].strip().split()[0]) * 1024
+                seen = True
+                if "Tx" in line:
+                    tx += val
+                else:
+                    rx += val
+        return (tx, rx) if seen else None
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------------------- synthetic data (device)
 def build_history_device(torch, dev, users, items, mean_hist, seed, user_lo=0, user_hi=None, zipf=False):
     """Per-user sorted unique histories for users [user_lo, user_hi) drawn on the device, chunk by chunk.
@@ -253,10 +274,12 @@ def run_ours(args, w):
     l0 = eng.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    nv0 = nvlink_counters(local) if world > 1 and rank == 0 else None
     ev0.record()
     run_steps(args.warmup, args.steps, losses[args.warmup:], phase_ms)
     ev1.record()
     barrier()
+    nv1 = nvlink_counters(local) if world > 1 and rank == 0 else None
     ms_total = ev0.elapsed_time(ev1)
     k3_ms, k3_n = eng.profile_read()
     other_kernels = {name: eng.profile_read(tag) for tag, name in ((1, "item_fetch_kernel"), (2, "dup_reduce+dup_final"), (3, "inbox_apply_kernel"))}
@@ -367,9 +390,15 @@ def run_ours(args, w):
         # ingress carries the rows it fetches plus the gradients its peers send it (and its egress the mirror image): 16*d bytes per
         # direction per triplet.  Peak: NVLink 5, 900 GB/s per direction per GPU (raw link rate; not measured on this pool).
         nv_bytes = 16 * dim * B * (world - 1) / world
-        nv_rate = nv_bytes / (k3_avg_ms / 1000.0) / 1e9
-        roofline["nvlink"] = {"bytes_per_direction_per_launch": nv_bytes, "achieved": nv_rate, "peak": 900.0, "unit": "GB/s per direction per GPU",
-                              "frac": nv_rate / 900.0, "note": "the multi-GPU step kernel is bound by NVLink, not by HBM: read `frac` above as HBM headroom"}
+        roofline["nvlink"] = {"undeduplicated_bytes_per_direction_per_step": nv_bytes, "peak": 770.0, "unit": "GB/s per direction per GPU",
+                              "peak_source": "measured peer copy on this pool (B200_PROFILING.md); 900 nominal",
+                              "note": "16*d*B*(N-1)/N is what the step would move without the per-rank de-duplication (round 1); the measured "
+                                      "counters below are what it does move"}
+        if nv0 and nv1:
+            tx, rx = (nv1[0] - nv0[0]) / args.steps, (nv1[1] - nv0[1]) / args.steps
+            roofline["nvlink"].update({"measured_tx_bytes_per_step": tx, "measured_rx_bytes_per_step": rx,
+                                       "measured_rate_over_step": max(tx, rx) / (ms_step / 1000.0) / 1e9,
+                                       "counter": "nvidia-smi nvlink -gt d on rank 0's GPU, read around the timed steps (includes the sampler's and barriers' few bytes)"})
         roofline["traffic"] = None
     traffic_file = os.path.join(ROOT, "profiles", "r01_bpr_step_traffic.json")
     if os.path.exists(traffic_file):
