@@ -48,6 +48,8 @@ extern "C" int crb_create(int device, crb_handle** out) {
     CRB_CUDA(cudaMemset(h->block_loss, 0, sizeof(double) * h->loss_blocks));
     CRB_CUDA(cudaMalloc(&h->lrt, sizeof(float) * CRB_LRT_TABLE));
     CRB_CUDA(cudaMalloc(&h->dense_loss, sizeof(double) * 4 * h->loss_blocks));
+    CRB_CUDA(cudaMalloc(&h->dyn_dev, sizeof(uint32_t) * 8));
+    CRB_CUDA(cudaMemset(h->dyn_dev, 0, sizeof(uint32_t) * 8));
     h->lrt_lr = -1.0;
     *out = h;
     return CRB_OK;
@@ -118,6 +120,7 @@ int crb_alt_reserve(crb_handle* h, cudaStream_t s) {
 }
 
 static void free_ws(crb_handle* h) {
+    h->ws_generation++;
     if (h->aux_stream) cudaStreamSynchronize(h->aux_stream);
     if (h->alt_active) crb_alt_swap(h);
     free_alt_ws(h);
@@ -153,6 +156,8 @@ extern "C" int crb_destroy(crb_handle* h) {
         cudaEventDestroy(h->ev_entry);
         for (int k = 0; k < 2; ++k) { cudaEventDestroy(h->ev_prep[k]); cudaEventDestroy(h->ev_done[k]); }
     }
+    if (h->epoch_graph) cudaGraphExecDestroy((cudaGraphExec_t)h->epoch_graph);
+    cudaFree(h->dyn_dev);
     cudaFree(h->ctr);
     cudaFree(h->block_loss);
     cudaFree(h->loss_dev);
@@ -249,6 +254,7 @@ int crb_meta_reserve(crb_handle* h, int which, int64_t rows, cudaStream_t s) {
     if (h->alt_active) crb_alt_swap(h);
     if (h->meta_rows[which] >= rows) return CRB_OK;
     CRB_CUDA(cudaStreamSynchronize(s));
+    h->ws_generation++;
     cudaFree(h->meta[which]);
     h->meta[which] = nullptr;
     h->meta_rows[which] = 0;
@@ -261,6 +267,7 @@ int crb_meta_reserve(crb_handle* h, int which, int64_t rows, cudaStream_t s) {
 int crb_ws_reserve(crb_handle* h, int64_t batch, int32_t dim, int64_t steps, cudaStream_t s) {
     if (steps > h->cap_steps) {
         CRB_CUDA(cudaStreamSynchronize(s));
+        h->ws_generation++;
         cudaFree(h->loss_dev);
         h->loss_dev = nullptr;
         CRB_CUDA(cudaMalloc(&h->loss_dev, sizeof(double) * steps));

@@ -38,8 +38,8 @@ struct crb_step_ctr {
     unsigned int dup_rows;    // number of duplicate rows
     unsigned int work_items;  // chunk work items of the duplicate reduction
     unsigned int multi_rows;  // duplicate rows with more than one chunk
-    unsigned int sampler_err; // a positive ran out of attempts
     unsigned int partial_slots; // partial-sum rows handed to multi-chunk duplicate rows
+    unsigned int sampler_err; // a positive ran out of attempts (sticky: everything BEFORE this word is zeroed between steps)
     unsigned int pad[2];
 };
 
@@ -160,6 +160,15 @@ struct crb_handle {
         int64_t cap_batch;
     } alt;
     int alt_active;          // 1 while the handle's fields hold the alternate copy
+    // Whole-epoch CUDA graph of crb_train_epoch_bpr for launch-bound shapes (train.cu): the epoch's kernels are captured once with
+    // everything that changes from epoch to epoch (the sampler's permutation keys and epoch word, the optimizer's step base) read
+    // from `dyn_dev` on the device, and replayed with one launch per epoch.
+    uint32_t* dyn_dev;       // [8]: keys[6], epoch, step_base
+    int dyn_mode;            // 1 while capturing: kernels get the dyn pointers
+    void* epoch_graph;       // cudaGraphExec_t
+    unsigned char epoch_graph_key[256];
+    int epoch_graph_key_len;
+    int64_t ws_generation;   // bumped whenever a workspace pointer baked into the graph may have changed
     // a sharded step prepared ahead of time in the alternate copy (crb_shard_step_prepare)
     int prep_valid;
     uint64_t prep_seed;

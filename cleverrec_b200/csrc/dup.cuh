@@ -140,6 +140,7 @@ __device__ __forceinline__ void dup_apply(const DupArgs& a, const crb_dup_row& d
 // and row are in flight, so a group's critical path per item is one memory round trip instead of four.
 template <int LANES, int VPL, int OPT, bool SHARD = false>
 __global__ void __launch_bounds__(256) dup_reduce_kernel(DupArgs a) {
+    opt_resolve(a.opt);
     const int gl = threadIdx.x % LANES;
     const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
     const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / LANES;
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(256) dup_reduce_kernel(DupArgs a) {
 
 template <int LANES, int VPL, int OPT, bool SHARD = false>
 __global__ void __launch_bounds__(256) dup_final_kernel(DupArgs a) {
+    opt_resolve(a.opt);
     const int gl = threadIdx.x % LANES;
     const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
     const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / LANES;

@@ -27,6 +27,7 @@ struct OptDev {
     float omb1, omb2;  // 1 - b1, 1 - b2 in fp32
     int32_t step;  // 1-based index of this step
     const float* lrt;  // lr_t table for replay (CRB_ADAM_TF1)
+    const uint32_t* step_base;  // NULL, or (epoch graph, train.cu) a device word added to `step` when the kernel starts
 };
 
 enum { OPT_SGD = 0, OPT_ADAGRAD = 1, OPT_ADAM_LAZY = 2, OPT_ADAM_TF1 = 3 };
@@ -38,6 +39,15 @@ template <int OPT> struct OptTraits {
 };
 
 __device__ __forceinline__ float lrt_at(const OptDev& o, int s) { return s < CRB_LRT_TABLE ? o.lrt[s] : o.lr; }
+
+// Kernels replayed from a captured graph carry a RELATIVE step; the absolute one (and Adam's lr_t, the same table entry the host
+// would have passed) is resolved when the kernel starts.  A no-op for ordinary launches.
+__device__ __forceinline__ void opt_resolve(OptDev& o) {
+    if (o.step_base) {
+        o.step += (int32_t)*o.step_base;
+        o.lr_t = lrt_at(o, o.step);
+    }
+}
 
 // Optimizer arithmetic.  Multiplies/adds are plain IEEE ops without contraction (the op-by-op sequence of TF's kernels);
 // the square root and the division use the SFU approximations (sqrt.approx / rcp.approx, <= 2 ulp), which keeps the step

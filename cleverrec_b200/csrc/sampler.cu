@@ -23,6 +23,7 @@ struct SamplerArgs {
     const int32_t* seen_cols;
     const uint32_t* bloom;  // per-user seen-item Bloom filters (NULL: exact search only)
     int bloom_shift;
+    const uint32_t* dyn;    // NULL, or (epoch graph) device words that replace keys[0..5] and epoch when the kernel starts
 };
 
 __device__ __forceinline__ uint32_t mix32(uint32_t x, uint32_t k) {
@@ -114,6 +115,11 @@ __global__ void __launch_bounds__(256) sample_kernel(SamplerArgs a, int64_t firs
                                                      unsigned long long* metaI, uint32_t* __restrict__ rk0,
                                                      uint32_t* __restrict__ rk1, uint32_t* __restrict__ rk2,
                                                      crb_step_ctr* ctr) {
+    if (a.dyn) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) a.keys[q] = a.dyn[q];
+        a.epoch = a.dyn[6];
+    }
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
         const uint64_t s = feistel_perm((uint64_t)(first + t), a);
@@ -170,7 +176,9 @@ __global__ void __launch_bounds__(128) sample_nais_kernel(SamplerArgs a, int64_t
     if (!ok) atomicAdd(&ctr->sampler_err, 1u);
 }
 
-static void host_perm_keys(uint64_t seed, uint32_t epoch, uint32_t keys[6]) {
+void crb_sampler_perm_keys(uint64_t seed, uint32_t epoch, uint32_t keys[6]);
+static void host_perm_keys(uint64_t seed, uint32_t epoch, uint32_t keys[6]) { crb_sampler_perm_keys(seed, epoch, keys); }
+void crb_sampler_perm_keys(uint64_t seed, uint32_t epoch, uint32_t keys[6]) {
     uint32_t a[4], b[4];
     philox4x32_10(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, epoch, (uint32_t)seed, (uint32_t)(seed >> 32), a);
     philox4x32_10(0xFFFFFFFFu, 0xFFFFFFFFu, 1u, epoch, (uint32_t)seed, (uint32_t)(seed >> 32), b);
@@ -204,6 +212,7 @@ static int make_args(crb_handle* h, uint64_t seed, uint32_t epoch, int32_t neg_r
     a->seen_cols = h->seen_cols;
     a->bloom = h->bloom;
     a->bloom_shift = h->bloom_shift;
+    a->dyn = h->dyn_mode ? h->dyn_dev : nullptr;
     return CRB_OK;
 }
 

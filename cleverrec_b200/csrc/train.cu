@@ -221,6 +221,7 @@ int crb_opt_to_dev(crb_handle* h, const crb_opt* opt, OptDev* o, int* opt_kind, 
     o->step = (int32_t)opt->step;
     o->lr_t = 0.f;
     o->lrt = h->lrt;
+    o->step_base = nullptr;
     switch (opt->kind) {
         case CRB_OPT_SGD: *opt_kind = OPT_SGD; break;
         case CRB_OPT_ADAGRAD: *opt_kind = OPT_ADAGRAD; break;
@@ -270,6 +271,7 @@ template <int OPT> struct BprOcc { static constexpr int ctas = OPT == OPT_SGD ? 
 
 template <int LANES, int VPL, int OPT>
 __global__ void __launch_bounds__(256, BprOcc<OPT>::ctas) bpr_step_kernel(BprArgs a) {
+    opt_resolve(a.opt);
     constexpr int GPW = 32 / LANES;
     const int lane = threadIdx.x & 31;
     const int gl = lane % LANES;
@@ -475,7 +477,6 @@ __global__ void merge_sampler_err_kernel(crb_step_ctr* into, crb_step_ctr* from)
 int crb_zero_step_counters(crb_handle* h, cudaStream_t s) {
     // everything except sampler_err (sticky until reported)
     CRB_CUDA(cudaMemsetAsync(h->ctr, 0, offsetof(crb_step_ctr, sampler_err), s));
-    CRB_CUDA(cudaMemsetAsync(&h->ctr->partial_slots, 0, sizeof(unsigned int), s));
     return CRB_OK;
 }
 
@@ -514,6 +515,110 @@ extern "C" int crb_train_step_bpr(crb_handle* h, const crb_table* P, const crb_t
     return finish_loss(h, loss_out, 1, s);
 }
 
+// ------------------------------------------------------------------------------------------------ whole-epoch graph
+// At the shapes the reference ships (ml-1m: 6144-row batches, tables of a few MB) a step is a handful of microsecond kernels and
+// the epoch costs launch count x launch latency: 649 steps x 8 launches from the host.  For such shapes the single-stream epoch loop
+// is captured ONCE into a CUDA graph and replayed with one launch per epoch.  What changes from epoch to epoch -- the sampler's
+// permutation keys and epoch word, the optimizer's absolute step -- is read by the kernels from handle->dyn_dev (SamplerArgs::dyn,
+// OptDev::step_base), which is rewritten before every replay; everything else (row offsets of the steps, batch sizes, loss slots,
+// workspace pointers) is identical every epoch and baked into the nodes.  Same kernels, same order, same arguments: the tables are
+// bit-identical to the step-by-step path (tests/test_gpu_train_bpr.py::test_epoch_graph_is_bit_identical).
+void crb_sampler_perm_keys(uint64_t seed, uint32_t epoch, uint32_t keys[6]);
+
+struct EpochGraphKey {
+    crb_table P, Q;
+    crb_opt opt;            // step zeroed
+    uint64_t seed;
+    int64_t first, batch, n_steps, rows, ws_generation, n_pos;
+    int32_t neg_ratio;
+    float reg;
+    const void *pos_user, *seen_rowptr, *bloom, *stream;
+};
+static_assert(sizeof(EpochGraphKey) <= 256, "epoch graph key");
+
+// MEASURED (B200, ml-1m shape: 649 steps of 6144 rows, d=64, Adam): graph replay 24.4 ms per epoch, ordinary launch loop 24.3 ms.
+// The epoch is NOT bound by host launches: a step is six kernels whose cost is their chains of dependent L2 / DRAM round trips
+// (sampler 19 us, assign 10, step 8, duplicate reduce up to 40 under ncu), and the ordinary path already overlaps step k+1's
+// index kernels with step k's compute on a second stream, which the single-stream graph gives up.  So the graph is opt-in
+// (CRB_EPOCH_GRAPH=1), kept because it is bit-identical and removes the host from the loop (one launch per epoch).
+static bool epoch_graph_eligible(crb_handle* h, int64_t batch, int64_t n_steps) {
+    const char* e = getenv("CRB_EPOCH_GRAPH");
+    if (h->prof_on || !e || atoi(e) != 1) return false;
+    return n_steps >= 8 && batch <= 32768;
+}
+
+// the epoch loop on ONE stream (no second copy of the step state); relative optimizer steps + device-side resolution when dyn != 0
+static int bpr_epoch_single_stream(crb_handle* h, const crb_table* P, const crb_table* Q, const crb_opt* opt, uint64_t seed, uint32_t epoch,
+                                   int64_t first, int64_t batch, int64_t n_steps, int64_t rows, int32_t neg_ratio, float reg, bool dyn,
+                                   double* loss_dev, cudaStream_t s) {
+    crb_opt step_opt = *opt;
+    OptDev od;
+    int opt_kind = 0, rc;
+    for (int64_t k = 0; k < n_steps; ++k) {
+        const int64_t lo = first + k * batch;
+        if (lo >= rows) { crb_set_error("step %lld starts past the end of the epoch", (long long)k); return CRB_ERR_ARG; }
+        const int64_t b = (rows - lo) < batch ? (rows - lo) : batch;
+        step_opt.step = dyn ? k + 1 : opt->step + k;
+        if ((rc = crb_opt_to_dev(h, &step_opt, &od, &opt_kind, s))) return rc;
+        if (dyn) { od.step_base = h->dyn_dev + 7; od.lr_t = 0.f; }
+        if ((rc = crb_zero_step_counters(h, s))) return rc;
+        if ((rc = crb_launch_sample_pairwise(h, seed, epoch, lo, b, neg_ratio, h->idx[0], h->idx[1], h->idx[2], nullptr, true, s))) return rc;
+        if ((rc = bpr_step_prepare(h, h->idx[0], h->idx[1], h->idx[2], b, true, s))) return rc;
+        if ((rc = bpr_step_compute(h, P, Q, od, opt_kind, h->idx[0], h->idx[1], h->idx[2], b, reg, loss_dev + k, s))) return rc;
+    }
+    return CRB_OK;
+}
+
+// returns CRB_OK with *done = true when the epoch ran from the graph; *done = false means "use the ordinary path"
+static int bpr_epoch_graph(crb_handle* h, const crb_table* P, const crb_table* Q, const crb_opt* opt, uint64_t seed, uint32_t epoch,
+                           int64_t first, int64_t batch, int64_t n_steps, int64_t rows, int32_t neg_ratio, float reg, cudaStream_t s, bool* done) {
+    *done = false;
+    EpochGraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.P = *P; key.Q = *Q; key.opt = *opt; key.opt.step = 0;
+    key.seed = seed; key.first = first; key.batch = batch; key.n_steps = n_steps; key.rows = rows; key.ws_generation = h->ws_generation;
+    key.n_pos = h->n_pos; key.neg_ratio = neg_ratio; key.reg = reg;
+    key.pos_user = h->pos_user; key.seen_rowptr = h->seen_rowptr; key.bloom = h->bloom; key.stream = (const void*)s;
+    const bool hit = h->epoch_graph && h->epoch_graph_key_len == (int)sizeof(key) && memcmp(h->epoch_graph_key, &key, sizeof(key)) == 0;
+    if (!hit) {
+        if (h->epoch_graph) { cudaGraphExecDestroy((cudaGraphExec_t)h->epoch_graph); h->epoch_graph = nullptr; }
+        // everything that may allocate or synchronise happens before the capture (lr_t table, workspaces: done by the caller's checks)
+        OptDev od;
+        int opt_kind = 0;
+        int rc = crb_opt_to_dev(h, opt, &od, &opt_kind, s);
+        if (rc) return rc;
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return CRB_OK; }
+        h->dyn_mode = 1;
+        const int64_t launches_before = h->launches;
+        rc = bpr_epoch_single_stream(h, P, Q, opt, seed, epoch, first, batch, n_steps, rows, neg_ratio, reg, true, h->loss_dev, s);
+        h->dyn_mode = 0;
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        h->launches = launches_before;
+        if (rc || ce != cudaSuccess || !graph) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            return rc;   // an argument error is an error; a capture failure falls back to the ordinary path
+        }
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess || !exec) { cudaGetLastError(); return CRB_OK; }
+        h->epoch_graph = exec;
+        memcpy(h->epoch_graph_key, &key, sizeof(key));
+        h->epoch_graph_key_len = (int)sizeof(key);
+    }
+    uint32_t dyn[8];
+    crb_sampler_perm_keys(seed, epoch, dyn);
+    dyn[6] = epoch;
+    dyn[7] = (uint32_t)(opt->step - 1);
+    CRB_CUDA(cudaMemcpyAsync(h->dyn_dev, dyn, sizeof(dyn), cudaMemcpyHostToDevice, s));   // pageable source: staged before the call returns
+    CRB_CUDA(cudaGraphLaunch((cudaGraphExec_t)h->epoch_graph, s));
+    h->launches += n_steps * 6;   // K1, K2, K3, K4 (two kernels), K5 per step
+    *done = true;
+    return CRB_OK;
+}
+
 extern "C" int crb_train_epoch_bpr(crb_handle* h, const crb_table* P, const crb_table* Q, const crb_opt* opt, uint64_t seed,
                                    uint32_t epoch, int64_t first, int64_t batch, int64_t n_steps, int32_t neg_ratio, float reg,
                                    double* loss_out, void* stream) {
@@ -526,6 +631,25 @@ extern "C" int crb_train_epoch_bpr(crb_handle* h, const crb_table* P, const crb_
     const int64_t rows = crb_epoch_rows(h, neg_ratio, 0);
     CRB_CHECK_ARG(first >= 0 && first < rows, "first row outside the epoch");
     const bool host_loss = !(loss_out && crb_is_device_ptr(loss_out));
+    if (epoch_graph_eligible(h, batch, n_steps) && !crb_bpr_ring_enabled(P->dim)) {
+        if (h->alt_active) crb_alt_swap(h);
+        bool done = false;
+        if ((rc = bpr_epoch_graph(h, P, Q, opt, seed, epoch, first, batch, n_steps, rows, neg_ratio, reg, s, &done))) return rc;
+        if (done) {
+            if (loss_out && !host_loss) CRB_CUDA(cudaMemcpyAsync(loss_out, h->loss_dev, sizeof(double) * n_steps, cudaMemcpyDeviceToDevice, s));
+            if (loss_out && host_loss) {
+                if ((rc = finish_loss(h, loss_out, n_steps, s))) return rc;
+                unsigned int err = 0;
+                CRB_CUDA(cudaMemcpy(&err, &h->ctr->sampler_err, sizeof(err), cudaMemcpyDeviceToHost));
+                if (err) {
+                    CRB_CUDA(cudaMemset(&h->ctr->sampler_err, 0, sizeof(err)));
+                    crb_set_error("sampler: %u rows found no admissible negative", err);
+                    return CRB_ERR_SAMPLER;
+                }
+            }
+            return CRB_OK;
+        }
+    }
     crb_opt step_opt = *opt;
     // Two copies of the sampling / assignment state: step k's K1 (sampler + row counts) and K2 (slot assignment) run on the
     // auxiliary stream into copy k & 1 while step k-1's K3/K4 (the HBM-bound part) run on the caller's stream from the other

@@ -228,3 +228,40 @@ def test_ring_kernel_is_bit_identical_to_register_kernel(eng, kind, mode, d, mon
     assert abs(a[1] - b[1]) <= 1e-12 * abs(a[1]) and abs(a[2] - b[2]) <= 1e-12 * abs(a[2])
     for k in (3, 4, 5, 6):
         assert (a[k] is None and b[k] is None) or torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("kind,mode", OPTS)
+def test_epoch_graph_is_bit_identical(eng, kind, mode, monkeypatch):
+    """CRB_EPOCH_GRAPH=1 replays a captured whole-epoch CUDA graph (one launch per epoch; sampler keys / epoch word / optimizer step
+    read from device memory).  Three epochs through the graph == the same epochs step by step (the default): losses and
+    tables bit for bit, including the epoch-dependent sampling and Adam's step-dependent lr_t and replay."""
+    from cleverrec_b200.engine import Optimizer, Table
+    U, I, d, B, R = 400, 900, 64, 512, 2
+    data = synthetic_data(U, I, 12, seed=7)
+    eng.set_history(data.ui_train, U, I)
+    n_rows = eng.epoch_rows(R)
+    n_steps = -(-n_rows // B)
+    assert n_steps >= 8
+    g = torch.Generator().manual_seed(2)
+    P0, Q0 = torch.randn(U, d, generator=g) * 0.1, torch.randn(I, d, generator=g) * 0.1
+    out = []
+    for no_graph in (False, True):
+        if no_graph:
+            monkeypatch.delenv("CRB_EPOCH_GRAPH", raising=False)
+        else:
+            monkeypatch.setenv("CRB_EPOCH_GRAPH", "1")
+        P, Q = Table(P0.clone().cuda(), kind, mode), Table(Q0.clone().cuda(), kind, mode)
+        opt = Optimizer(kind, 0.05 if kind != "Adam" else 0.01, adam_mode=mode)
+        all_losses = []
+        l0 = eng.launches
+        for epoch in range(3):
+            losses = torch.zeros(n_steps, dtype=torch.float64, device="cuda")
+            eng.train_epoch_bpr(P, Q, opt, 5, epoch, 0, B, n_steps, R, 0.01, losses)
+            all_losses.append(losses.cpu().numpy())
+        assert eng.launches - l0 == 3 * n_steps * 6   # the same six kernels per step either way
+        eng.adam_flush(P, opt); eng.adam_flush(Q, opt)
+        torch.cuda.synchronize()
+        out.append((np.concatenate(all_losses), P.w.clone(), Q.w.clone()))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
+    assert out[0][0][-1] < out[0][0][0]
