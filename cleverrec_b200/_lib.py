@@ -24,7 +24,7 @@ EXPORTS = [
     "crb_train_step_neumf", "crb_score_pairs_neumf", "crb_mask_seen",
     "crb_sample_nais", "crb_train_step_nais", "crb_train_epoch_nais", "crb_score_nais",
     "crb_shard_step_compute", "crb_shard_step_prepare", "crb_shard_apply_inbox", "crb_shard_barrier", "crb_shard_check", "crb_sampler_errors", "crb_malloc", "crb_free", "crb_ipc_export",
-    "crb_ipc_open", "crb_ipc_close", "crb_build_history", "crb_set_item_lists", "crb_train_step_transcf", "crb_transcf_neighbourhood", "crb_score_pairs_transcf", "crb_np_seed", "crb_np_set_state", "crb_np_get_state", "crb_sample_epoch_numpy",
+    "crb_ipc_open", "crb_ipc_close", "crb_build_history", "crb_prep_filter_reindex", "crb_prep_split_loo", "crb_prep_eval_negatives", "crb_set_item_lists", "crb_train_step_transcf", "crb_transcf_neighbourhood", "crb_score_pairs_transcf", "crb_np_seed", "crb_np_set_state", "crb_np_get_state", "crb_sample_epoch_numpy",
     "crb_train_step_lrml", "crb_score_pairs_lrml", "crb_set_social", "crb_sample_sbpr", "crb_train_step_sbpr", "crb_train_epoch_bpr_feeds", "crb_train_epoch_pointwise",
 ]
 
@@ -73,6 +73,9 @@ def load():
     lib.crb_destroy.argtypes = [vp]
     lib.crb_set_history.argtypes = [vp, i64, i64, i64, vp, vp, vp, vp, vp]
     lib.crb_build_history.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, C.POINTER(i64), vp, vp, vp]
+    lib.crb_prep_filter_reindex.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp, vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), vp, vp, vp]
+    lib.crb_prep_split_loo.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp]
+    lib.crb_prep_eval_negatives.argtypes = [vp, u64, vp, i64, i32, vp, vp]
     lib.crb_sample_pairwise.argtypes = [vp, u64, u32, i64, i64, i32, vp, vp, vp, vp, vp]
     lib.crb_sample_pointwise.argtypes = [vp, u64, u32, i64, i64, i32, vp, vp, vp, vp, vp]
     lib.crb_sample_cml.argtypes = [vp, u64, u32, i64, i64, i32, vp, vp, vp, vp]

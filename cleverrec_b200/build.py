@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcleverrec_b200.so")
-SOURCES = ["api.cu", "sampler.cu", "train.cu", "train_ring.cu", "score.cu", "score_loo.cu", "score_topk.cu", "score_tc.cu", "train_dense.cu", "train_neumf.cu", "train_lrml.cu", "train_nais.cu", "train_sharded.cu", "sampler_np.cu", "history.cu"]
+SOURCES = ["api.cu", "sampler.cu", "train.cu", "train_ring.cu", "score.cu", "score_loo.cu", "score_topk.cu", "score_tc.cu", "train_dense.cu", "train_neumf.cu", "train_lrml.cu", "train_nais.cu", "train_sharded.cu", "sampler_np.cu", "history.cu", "preprocess.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -134,6 +134,47 @@ class Engine(object):
         check(self.lib.crb_set_history_lists(self.h, ptr(start), ptr(ln)))
         return self._hist
 
+    # ------------------------------------------------------------------ preprocessing on the device (csrc/preprocess.cu)
+    def prep_filter_reindex(self, raw_u, raw_i, user_min=0, item_min=0):
+        """RankingPreprocess._filter_users / _filter_items / re_index on two id columns (any integer dtype, host or device).
+        -> dict(u, i: int32 new ids of the kept rows in file order; row: their original row numbers; user_ids / item_ids: raw id of
+        each new id; n_users, n_items)."""
+        dev = self.device
+        def col(a):
+            if not isinstance(a, torch.Tensor):
+                a = torch.from_numpy(np.array(a, dtype=np.int64))   # a copy: pandas hands out read-only views
+            return a.to(device=dev, dtype=torch.int64).contiguous()
+        ru, ri = col(raw_u), col(raw_i)
+        n = int(ru.numel())
+        u, i = torch.empty(max(n, 1), dtype=torch.int32, device=dev), torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        row, uid, iid = (torch.empty(max(n, 1), dtype=torch.int64, device=dev) for _ in range(3))
+        nk, nu, ni = C.c_int64(), C.c_int64(), C.c_int64()
+        check(self.lib.crb_prep_filter_reindex(self.h, ptr(ru), ptr(ri), n, int(user_min), int(item_min), ptr(u), ptr(i), ptr(row), C.byref(nk),
+                                               C.byref(nu), C.byref(ni), ptr(uid), ptr(iid), self.stream))
+        k = int(nk.value)
+        return {"u": u[:k], "i": i[:k], "row": row[:k], "user_ids": uid[:int(nu.value)], "item_ids": iid[:int(ni.value)],
+                "n_users": int(nu.value), "n_items": int(ni.value)}
+
+    def prep_split_loo(self, u, n_users, time=None):
+        """The leave-one-out split: -> (perm int64 [n], is_test bool [n]) in the reference's enumeration order (ascending user,
+        then time / file order); is_test marks a user's last row when the user has more than 3 rows."""
+        dev = self.device
+        u = torch.as_tensor(u).to(device=dev, dtype=torch.int32).contiguous()
+        t = None if time is None else torch.as_tensor(time).to(device=dev, dtype=torch.int64).contiguous()
+        n = int(u.numel())
+        perm = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        flag = torch.zeros(max(n, 1), dtype=torch.uint8, device=dev)
+        check(self.lib.crb_prep_split_loo(self.h, ptr(u), ptr(t), n, int(n_users), ptr(perm), ptr(flag), self.stream))
+        return perm[:n], flag[:n].bool()
+
+    def prep_eval_negatives(self, seed, test_users, neg_samples):
+        """neg_samples distinct items outside each test user's training items (the installed history): int32 [n_test, neg_samples]."""
+        dev = self.device
+        tu = torch.as_tensor(test_users).to(device=dev, dtype=torch.int32).contiguous()
+        out = torch.empty((int(tu.numel()), int(neg_samples)), dtype=torch.int32, device=dev)
+        check(self.lib.crb_prep_eval_negatives(self.h, int(seed), ptr(tu), int(tu.numel()), int(neg_samples), ptr(out), self.stream))
+        return out
+
     def set_history(self, ui_train, n_users, n_items):
         self.set_history_arrays(n_users, n_items, *history_from_dict(ui_train, n_users))
         # per-user interaction lists (order and duplicates kept) inside pos_item: FISM / NAIS need them

@@ -22,7 +22,8 @@ def run(configs, data, logger):
     if importlib.util.find_spec(module) is None:
         raise Exception('Module %s not found.' % module)
     myclass = getattr(importlib.import_module(module), configs['recommender'])
-    model = myclass(None, data, configs, logger)  # `sess` slot unused: the engine replaces tf.Session
+    # the `sess` slot carries the engine when the data object already owns one (data.preprocess=device), else None
+    model = myclass(getattr(data, 'engine', None), data, configs, logger)
     return model.run_model()
 
 
@@ -38,6 +39,8 @@ if __name__ == '__main__':
     if configs.get('data.preprocess', 'packaged') == 'reference':
         sys.path.insert(0, root)
         from model.RankingPreprocess import RankingPreprocess
+    elif configs.get('data.preprocess', 'packaged') == 'device':   # filter / re-index / split / evaluation negatives on the GPU
+        from cleverrec_b200.model.RankingPreprocess import DeviceRankingPreprocess as RankingPreprocess
     else:
         from cleverrec_b200.model.RankingPreprocess import RankingPreprocess
     data = RankingPreprocess(configs, logger)

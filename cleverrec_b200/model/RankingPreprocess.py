@@ -154,3 +154,74 @@ class _LazyDict(dict):
     def get(self, k, default=None): return self[k] if k in self._pos else default
     def items(self): return ((k, self[k]) for k in self._pos)
     def values(self): return (self[k] for k in self._pos)
+
+
+class DeviceRankingPreprocess(object):
+    """`data.preprocess=device`: the same constructor and attributes, with filter / re-index / leave-one-out split / evaluation
+    negatives on the device (csrc/preprocess.cu) and the history built natively from the training columns (csrc/history.cu) --
+    no frame-sized Python object is ever built.  The file is still parsed on the host (I/O), then lives as device columns.
+
+    What is the reference's bit for bit: user / item counts, the re-indexing (dense non-negative raw ids: the ascending order a
+    Python set of them iterates in), the leave-one-out split, and -- `data.split_way=rs` -- the random split, whose permutation
+    is drawn by the reference's own call (sklearn `train_test_split` on NumPy's global stream) and only APPLIED on the device.
+    What is not NumPy's stream: the sampled evaluation negatives (`np.random.choice(list(item_set - seen), ...)` permutes the whole
+    unseen catalogue per user, O(users x items)); they are drawn by crb_prep_eval_negatives -- same law, keyed by `seed` -- so
+    HR / NDCG on sampled candidates match the packaged host mode in distribution, not per draw.  `social_file` is not supported here."""
+
+    def __init__(self, configs, logger, engine=None):
+        import torch
+        from ..engine import Engine
+        self.configs, self.logger = configs, logger
+        c = configs
+        if 'social_file' in c:
+            raise NotImplementedError('data.preprocess=device does not load social_file; use the packaged host preprocessing')
+        self.file_path = os.path.join(c['data.root_dir'], c['data.dataset'])
+        self.engine = engine if engine is not None else Engine(int(c.get('engine.device', 0)))
+        eng = self.engine
+        fmt = c['data.format']
+        names = {'UI': ['u_id', 'i_id'], 'UIR': ['u_id', 'i_id', 'rating'], 'UIRT': ['u_id', 'i_id', 'rating', 'time']}[fmt]
+        frame = pd.read_csv(os.path.join(self.file_path, c['data.file_name']), sep=c['data.sep'], header=0, names=names, usecols=list(range(len(names))))
+        res = eng.prep_filter_reindex(frame['u_id'].to_numpy(), frame['i_id'].to_numpy(), int(c['data.user_min']), int(c['data.item_min']))
+        self.user_nums, self.item_nums = res['n_users'], res['n_items']
+        u, i = res['u'], res['i']
+        n = int(u.numel())
+        split_way = c['data.split_way']
+        if split_way == 'loo':
+            time = None
+            if c['data.split_by_time'] == 'True':
+                time = torch.from_numpy(frame['time'].astype(int).to_numpy()).to(eng.device)[res['row']]
+            perm, is_test = eng.prep_split_loo(u, self.user_nums, time)
+            tr, te = perm[~is_test], perm[is_test]
+        else:
+            from sklearn.model_selection import train_test_split
+            r1, r2, r3 = tuple(map(float, c['data.split_ratio'][1:-1].split(',')))
+            if c['data.split_by_time'] == 'True':   # the reference sorts the frame by (user, time) before it permutes the rows
+                time = torch.from_numpy(frame['time'].astype(int).to_numpy()).to(eng.device)[res['row']]
+                perm, _ = eng.prep_split_loo(u, self.user_nums, time)
+                u, i = u[perm].contiguous(), i[perm].contiguous()
+            rows = np.arange(n)
+            if r2 > 0:
+                tr, rest = train_test_split(rows, test_size=1.0 - r1)
+                _, te = train_test_split(rest, test_size=r3 / (r2 + r3))
+            else:
+                tr, te = train_test_split(rows, test_size=r3)
+            tr, te = torch.from_numpy(tr).to(eng.device), torch.from_numpy(te).to(eng.device)
+        # the native history builder groups the training rows by user (stable): its pos_user / pos_item ARE the dict's enumeration
+        hist = eng.build_history(u[tr], i[tr], self.user_nums, self.item_nums)
+        tu, ti = hist[0].cpu().numpy(), hist[1].cpu().numpy()
+        self.train_rows = (tu, ti)
+        self.ui_train = _LazyDict(tu, ti)
+        # test rows grouped by user, frame order inside (groupby('u_id').i_id.apply(list))
+        t_u, t_i = u[te], i[te]
+        order = torch.sort(t_u.long(), stable=True)[1]
+        t_u, t_i = t_u[order].cpu().numpy(), t_i[order].cpu().numpy()
+        ui_test = _to_dict(t_u, t_i)
+        neg_samples = int(c['test.neg_samples'])
+        if split_way == 'loo' or neg_samples > 0:
+            users = np.fromiter(ui_test.keys(), dtype=np.int32, count=len(ui_test))
+            negs = eng.prep_eval_negatives(int(c.get('seed', 0)), users, neg_samples).cpu().numpy() if neg_samples > 0 else np.zeros((len(users), 0), np.int32)
+            ui_test = {int(k): negs[pos].tolist() + ui_test[int(k)] for pos, k in enumerate(users)}
+        self.ui_test = ui_test
+        ratio = '' if split_way == 'loo' else ('split_ratio=%s, ' % c['data.split_ratio'])
+        logger.info(' Data: dataset=%s, split_way=%s, neg_samples=%d, %suser_nums=%d, item_nums=%d, ratings_num=%d' % (
+            c['data.dataset'], split_way, neg_samples, ratio, self.user_nums, self.item_nums, n))

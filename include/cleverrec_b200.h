@@ -122,6 +122,29 @@ int crb_set_history(crb_handle* h, int64_t n_users, int64_t n_items, int64_t n_p
                     const int32_t* pos_user, const int32_t* pos_item,
                     const int64_t* seen_rowptr, const int32_t* seen_cols, void* stream);
 
+/* Device form of model/RankingPreprocess.py -- the producer of every input of the hot path.  All columns are
+ * DEVICE arrays; every call synchronises the stream (the counts are host values).
+ *
+ * crb_prep_filter_reindex: _filter_users / _filter_items (RankingPreprocess.py:70-90; user_min / item_min <= 0 skip a filter) and
+ *   re_index (:41-47).  raw_u / raw_i [n]: the log's id columns in file order.  Out: out_u / out_i [n_kept] new ids of the kept
+ *   rows (file order), out_row [n_kept] their original row numbers (to gather `time` etc.), user_ids / item_ids [n] (first n_users /
+ *   n_items valid): the raw id behind each new id.  New ids are the ranks of the surviving raw ids in ASCENDING order -- the
+ *   reference's order (iteration of a Python set of the ids) for dense non-negative id spaces. */
+int crb_prep_filter_reindex(crb_handle* h, const int64_t* raw_u, const int64_t* raw_i, int64_t n, int32_t user_min, int32_t item_min,
+                            int32_t* out_u, int32_t* out_i, int64_t* out_row, int64_t* n_kept, int64_t* n_users, int64_t* n_items,
+                            int64_t* user_ids, int64_t* item_ids, void* stream);
+/* The leave-one-out split (RankingPreprocess.py:96-109).  u [n]: user of each row; time [n] or NULL (data.split_by_time).
+ * perm [n]: the rows in the order the reference's frame enumerates them (ascending user, then time, ties and the no-time case in
+ * file order); is_test [n], aligned with perm: 1 for a user's last row when the user has more than 3 rows. */
+int crb_prep_split_loo(crb_handle* h, const int32_t* u, const int64_t* time, int64_t n, int64_t n_users, int64_t* perm,
+                       unsigned char* is_test, void* stream);
+/* Sampled evaluation negatives (RankingPreprocess.py:120-129): for each test user neg_samples (<= 1024) DISTINCT items outside
+ * the user's training items (the installed history), out [n_test, neg_samples].  Same law as np.random.choice(..., replace=False)
+ * over the unseen items; a pure function of (seed, user, history) with an integer-exact CPU twin (oracle/philox.py), not NumPy's
+ * stream (use the packaged host preprocessing for that). */
+int crb_prep_eval_negatives(crb_handle* h, uint64_t seed, const int32_t* test_users, int64_t n_test, int32_t neg_samples,
+                            int32_t* out, void* stream);
+
 /* Native builder of the arrays above from the training split's (user, item) rows -- replaces the dict / list / set forms of
  * model/RankingPreprocess.py:117 (`groupby('u_id').i_id.apply(list).to_dict()`), utils/sampler.py:53 and
  * model/RankingRecommender.py:222-240 (`set(ui_train[u])`), which cannot be materialised at 1e9 interactions.

@@ -258,3 +258,32 @@ def sample_sbpr(seed, epoch, first, count, neg_ratio, item_nums, social):
             blk += 1
         out[:, t] = (u, pos_item[p], spu[u][pick], neg, suk[u][pick])
     return tuple(out[r].astype(np.int32) for r in range(4)) + (out[4].astype(np.float32),)
+
+
+def sample_eval_negatives(seed, test_users, neg_samples, item_nums, seen_rowptr, seen_cols):
+    """Integer-exact twin of crb_prep_eval_negatives (csrc/preprocess.cu): per test user, neg_samples distinct unseen items.
+    Restates the LAW of RankingPreprocess.py:120-129 (np.random.choice(list(item_set - seen), size, replace=False)): uniform without
+    replacement over the unseen items.  Candidates come 32 per round -- lane l takes word l & 3 of Philox block
+    (user, 0xE7A1, round * 8 + l // 4, 0xFFFFFFFD) under key (seed lo, seed hi) -- masked to the next power of two; a candidate is
+    accepted in lane order when it is in range, unseen, not accepted before and the first of its value in the round."""
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    mask = item_mask(item_nums)
+    out = np.full((len(test_users), neg_samples), -1, dtype=np.int32)
+    lanes = np.arange(32)
+    for k, u in enumerate(np.asarray(test_users).tolist()):
+        seen = set(seen_cols[seen_rowptr[u]:seen_rowptr[u + 1]].tolist())
+        got, taken, rnd = 0, set(), 0
+        while got < neg_samples:
+            assert rnd < 65536
+            w = philox4x32_10(u, 0xE7A1, rnd * 8 + lanes // 4, 0xFFFFFFFD, k0, k1)
+            words = np.stack(w, axis=1)[lanes, lanes & 3]
+            in_round = set()
+            for v in (words & np.uint32(mask)).tolist():
+                if v < item_nums and v not in seen and v not in taken and v not in in_round:
+                    in_round.add(v)
+                    if got < neg_samples:
+                        out[k, got] = v
+                        taken.add(v)
+                    got += 1
+            rnd += 1
+    return out
