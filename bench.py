@@ -400,7 +400,7 @@ def run_ours(args, w):
                                        "measured_rate_over_step": max(tx, rx) / (ms_step / 1000.0) / 1e9,
                                        "counter": "nvidia-smi nvlink -gt d on rank 0's GPU, read around the timed steps (includes the sampler's and barriers' few bytes)"})
         roofline["traffic"] = None
-    traffic_file = os.path.join(ROOT, "profiles", "r01_bpr_step_traffic.json")
+    traffic_file = os.path.join(ROOT, "profiles", "r02_bpr_step_traffic.json")   # dram__bytes_read + write of one K3 launch, this round's ncu capture
     if os.path.exists(traffic_file):
         try:
             # the committed capture is of the default configuration's kernel (Adam, tf1 semantics, uniform popularity, default shape)

@@ -402,9 +402,25 @@ static int launch_bpr_t(crb_handle* h, const BprArgs& a, int opt_kind, cudaStrea
     return CRB_OK;
 }
 
+// Host feeds of the reference's batch sizes are range-checked before they are used as table rows (a feed_dict with a bad id makes
+// TF's gather raise; here it would be an out-of-bounds access).  Device-resident feeds and very large host feeds are trusted: they
+// come from the library's own sampler / the caller's pipeline, and a scan of 3 x 2^20 ids would cost a third of the step.
+#define CRB_FEED_CHECK_MAX (1 << 16)
+static int check_feed(const int32_t* src, int64_t n, int64_t rows, const char* name) {
+    if (n > CRB_FEED_CHECK_MAX) return CRB_OK;
+    for (int64_t k = 0; k < n; ++k)
+        if (src[k] < 0 || src[k] >= rows) {
+            crb_set_error("feed %s[%lld] = %d is outside [0, %lld)", name, (long long)k, src[k], (long long)rows);
+            return CRB_ERR_ARG;
+        }
+    return CRB_OK;
+}
+
 // stage a possibly-host int32 feed into the handle workspace; returns the device pointer to use
-static int stage_i32(crb_handle* h, const int32_t* src, int slot, int64_t n, const int32_t** out, cudaStream_t s) {
+static int stage_i32(crb_handle* h, const int32_t* src, int slot, int64_t n, const int32_t** out, cudaStream_t s, int64_t rows = -1,
+                     const char* name = "") {
     if (crb_is_device_ptr(src)) { *out = src; return CRB_OK; }
+    if (rows >= 0) { int rc = check_feed(src, n, rows, name); if (rc) return rc; }
     CRB_CUDA(cudaMemcpyAsync(h->idx[slot], src, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
     *out = h->idx[slot];
     return CRB_OK;
@@ -505,9 +521,9 @@ extern "C" int crb_train_step_bpr(crb_handle* h, const crb_table* P, const crb_t
     if (rc) return rc;
     CRB_CHECK_ARG(u && i && j, "null index feed");
     const int32_t *du, *di, *dj;
-    if ((rc = stage_i32(h, u, 0, batch, &du, s))) return rc;
-    if ((rc = stage_i32(h, i, 1, batch, &di, s))) return rc;
-    if ((rc = stage_i32(h, j, 2, batch, &dj, s))) return rc;
+    if ((rc = stage_i32(h, u, 0, batch, &du, s, P->rows, "u_idx"))) return rc;
+    if ((rc = stage_i32(h, i, 1, batch, &di, s, Q->rows, "i_idx"))) return rc;
+    if ((rc = stage_i32(h, j, 2, batch, &dj, s, Q->rows, "j_idx"))) return rc;
     if ((rc = crb_zero_step_counters(h, s))) return rc;
     double* ld = (loss_out && crb_is_device_ptr(loss_out)) ? loss_out : h->loss_dev;
     rc = bpr_step_device(h, P, Q, od, opt_kind, du, di, dj, batch, reg, false, ld, s);
@@ -1053,8 +1069,8 @@ extern "C" int crb_train_step_pointwise(crb_handle* h, int32_t kind, const crb_t
     if (rc) return rc;
     CRB_CHECK_ARG(u && i && y, "null feed");
     const int32_t *du, *di;
-    if ((rc = stage_i32(h, u, 0, batch, &du, s))) return rc;
-    if ((rc = stage_i32(h, i, 1, batch, &di, s))) return rc;
+    if ((rc = stage_i32(h, u, 0, batch, &du, s, P->rows, "u_idx"))) return rc;
+    if ((rc = stage_i32(h, i, 1, batch, &di, s, Q->rows, "i_idx"))) return rc;
     const float* dy = y;
     if (!crb_is_device_ptr(y)) {
         CRB_CUDA(cudaMemcpyAsync(h->yv, y, sizeof(float) * batch, cudaMemcpyHostToDevice, s));

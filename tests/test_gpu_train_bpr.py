@@ -265,3 +265,52 @@ def test_epoch_graph_is_bit_identical(eng, kind, mode, monkeypatch):
     assert np.array_equal(out[0][0], out[1][0])
     assert torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
     assert out[0][0][-1] < out[0][0][0]
+
+
+def test_bad_feed_id_is_an_error(eng):
+    """A host feed with an id outside the table raises (TF's gather would) instead of reading out of bounds."""
+    from cleverrec_b200._lib import CrbError
+    P, Q, opt, ref, ropt = _make(eng, 50, 60, 32, "SGD", "tf1")
+    u, i, j = np.array([1, 2, 3]), np.array([4, 60, 6]), np.array([7, 8, 9])
+    with pytest.raises(CrbError, match="i_idx"):
+        eng.train_step_bpr(P, Q, opt, u, i, j, 0.01)
+    with pytest.raises(CrbError, match="u_idx"):
+        eng.train_step_bpr(P, Q, opt, np.array([1, -1, 3]), np.array([4, 5, 6]), j, 0.01)
+
+
+@pytest.mark.parametrize("kind,mode", [("SGD", "tf1"), ("Adam", "tf1")])
+def test_determinism_across_runs_and_hub_rows(eng, kind, mode):
+    """Two runs of the same steps: every row with <= 32 occurrences per step is BIT-identical (its duplicate gradients are summed in
+    triplet order); a hub row with hundreds of occurrences is summed in slot order, which follows the arrival order of the counting
+    atomics -- its two results agree to fp32 round-off (documented deviation: DESIGN 4), never more."""
+    from cleverrec_b200.engine import Optimizer, Table
+    U, I, d, B = 3000, 2000, 64, 4096
+    rs = np.random.RandomState(4)
+    feeds = []
+    for step in range(3):
+        u, i, j = rs.randint(0, U, B), rs.randint(0, I, B), rs.randint(0, I, B)
+        i[::7] = 11          # hub item: ~585 occurrences per step (3 chunks of 256 slots)
+        u[::16] = 5          # hub user: 256 occurrences
+        feeds.append((u, i, j))
+    g = torch.Generator().manual_seed(0)
+    P0, Q0 = torch.randn(U, d, generator=g) * 0.1, torch.randn(I, d, generator=g) * 0.1
+    runs = []
+    for rep in range(2):
+        P, Q = Table(P0.clone().cuda(), kind, mode), Table(Q0.clone().cuda(), kind, mode)
+        opt = Optimizer(kind, 0.05 if kind != "Adam" else 0.01, adam_mode=mode)
+        snaps = []
+        for f in feeds:
+            eng.train_step_bpr(P, Q, opt, f[0], f[1], f[2], 0.01)
+            torch.cuda.synchronize()
+            snaps.append((P.w.cpu().numpy().copy(), Q.w.cpu().numpy().copy()))
+        runs.append(snaps)
+    hub_i = np.bincount(np.concatenate([feeds[0][1], feeds[0][2]]), minlength=I) > 32
+    hub_u = np.bincount(feeds[0][0], minlength=U) > 32
+    assert hub_i.sum() == 1 and hub_u.sum() == 1
+    # after ONE step (later steps read the hub rows, so their round-off spreads): everything but the two hub rows is bit-identical
+    assert np.array_equal(runs[0][0][0][~hub_u], runs[1][0][0][~hub_u])
+    assert np.array_equal(runs[0][0][1][~hub_i], runs[1][0][1][~hub_i])
+    tol = 1e-6 if kind == "SGD" else 2e-4   # Adam: one sign-like step of lr where a summed gradient nearly cancels
+    for step in range(3):
+        assert np.abs(runs[0][step][0] - runs[1][step][0]).max() <= tol * (step + 1)
+        assert np.abs(runs[0][step][1] - runs[1][step][1]).max() <= tol * (step + 1)
