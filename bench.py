@@ -273,8 +273,8 @@ def run_ours(args, w):
     eng.profile_read()
     l0 = eng.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nv0 = nvlink_counters(local) if world > 1 and rank == 0 else None   # before the barrier: the other ranks must not wait for it inside the timed region
     barrier()
-    nv0 = nvlink_counters(local) if world > 1 and rank == 0 else None
     ev0.record()
     run_steps(args.warmup, args.steps, losses[args.warmup:], phase_ms)
     ev1.record()
@@ -394,6 +394,21 @@ def run_ours(args, w):
                               "peak_source": "measured peer copy on this pool (B200_PROFILING.md); 900 nominal",
                               "note": "16*d*B*(N-1)/N is what the step would move without the per-rank de-duplication (round 1); the measured "
                                       "counters below are what it does move"}
+        # exact payload of one step, counted from the step's own indices (nvidia-smi's NVLink counters read N/A on this pool and
+        # ncu may not wrap a multi-rank command): every DISTINCT remote item row is fetched once and its summed gradient sent once
+        try:
+            allit = torch.cat([feeds[0][1], feeds[0][2]]).to(dev).long()
+            remote = allit[allit % world != rank]
+            n_remote_rows = int(torch.unique(remote).numel())
+            t = torch.tensor([float(n_remote_rows)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wire = 2.0 * float(t.item()) * dim * 4
+            roofline["nvlink"].update({"counted_bytes_per_direction_per_step": wire, "counted_from": "2 x distinct remote item rows of one step's batch (max over ranks) x d x 4: "
+                                       "ingress = the rows this rank fetches + the gradients its peers send it (the mirror image by symmetry), egress likewise",
+                                       "remote_occurrences": int(remote.numel()), "distinct_remote_rows": n_remote_rows,
+                                       "rate_over_step": wire / (ms_step / 1000.0) / 1e9, "frac_of_peak_over_step": wire / (ms_step / 1000.0) / 1e9 / 770.0})
+        except Exception as e:
+            roofline["nvlink"]["counted_error"] = str(e)
         if nv0 and nv1:
             tx, rx = (nv1[0] - nv0[0]) / args.steps, (nv1[1] - nv0[1]) / args.steps
             roofline["nvlink"].update({"measured_tx_bytes_per_step": tx, "measured_rx_bytes_per_step": rx,

@@ -121,26 +121,28 @@ __device__ __forceinline__ void dup_load(RowRegs<LANES, VPL>& r, const DupArgs& 
 }
 
 template <int LANES, int VPL, int OPT>
-__device__ __forceinline__ void dup_finish(RowRegs<LANES, VPL>& r, const DupArgs& a, const crb_dup_row& d, const float4* acc, int gl) {
+__device__ __forceinline__ void dup_finish(RowRegs<LANES, VPL>& r, const DupArgs& a, const OptDev& o, const crb_dup_row& d, const float4* acc,
+                                           int gl) {
     const TableDev& T = a.tab[d.table];
-    row_replay<LANES, VPL, OPT>(r, a.opt, a.opt.step);
-    row_apply_store<LANES, VPL, OPT>(r, acc, T, d.row, a.dim, gl, a.opt);
+    row_replay<LANES, VPL, OPT>(r, o, o.step);
+    row_apply_store<LANES, VPL, OPT>(r, acc, T, d.row, a.dim, gl, o);
     if (gl == 0) a.meta[d.table][d.row] = 0ULL;
 }
 
 template <int LANES, int VPL, int OPT>
-__device__ __forceinline__ void dup_apply(const DupArgs& a, const crb_dup_row& d, const float4* acc, int gl) {
+__device__ __forceinline__ void dup_apply(const DupArgs& a, const OptDev& o, const crb_dup_row& d, const float4* acc, int gl) {
     RowRegs<LANES, VPL> r;
     dup_load<LANES, VPL, OPT>(r, a, d, gl);
-    dup_finish<LANES, VPL, OPT>(r, a, d, acc, gl);
+    dup_finish<LANES, VPL, OPT>(r, a, o, d, acc, gl);
 }
 
 // One lane group per work item (= one duplicate row, or one 256-slot chunk of a very frequent one).  The loop is software
 // pipelined: the next item's descriptors (work -> dup_rows, two dependent loads) are fetched while the current item's slots
 // and row are in flight, so a group's critical path per item is one memory round trip instead of four.
 template <int LANES, int VPL, int OPT, bool SHARD = false>
-__global__ void __launch_bounds__(256) dup_reduce_kernel(DupArgs a) {
-    opt_resolve(a.opt);
+__global__ void __launch_bounds__(256) dup_reduce_kernel(const DupArgs a) {
+    OptDev o = a.opt;   // a resolved COPY: writing into the parameter struct would move all of it to local memory
+    opt_resolve(o);
     const int gl = threadIdx.x % LANES;
     const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
     const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / LANES;
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(256) dup_reduce_kernel(DupArgs a) {
             shard_send<LANES, VPL>(a.send, d.row, acc, a.dim, gl);
             if (gl == 0) a.meta[1][d.row] = 0ULL;
         } else if (d.nchunk == 1) {
-            dup_finish<LANES, VPL, OPT>(r, a, d, acc, gl);
+            dup_finish<LANES, VPL, OPT>(r, a, o, d, acc, gl);
         } else {
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
@@ -181,8 +183,9 @@ __global__ void __launch_bounds__(256) dup_reduce_kernel(DupArgs a) {
 }
 
 template <int LANES, int VPL, int OPT, bool SHARD = false>
-__global__ void __launch_bounds__(256) dup_final_kernel(DupArgs a) {
-    opt_resolve(a.opt);
+__global__ void __launch_bounds__(256) dup_final_kernel(const DupArgs a) {
+    OptDev o = a.opt;
+    opt_resolve(o);
     const int gl = threadIdx.x % LANES;
     const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
     const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / LANES;
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(256) dup_final_kernel(DupArgs a) {
             shard_send<LANES, VPL>(a.send, d.row, acc, a.dim, gl);
             if (gl == 0) a.meta[1][d.row] = 0ULL;
         } else {
-            dup_apply<LANES, VPL, OPT>(a, d, acc, gl);
+            dup_apply<LANES, VPL, OPT>(a, o, d, acc, gl);
         }
     }
 }

@@ -108,14 +108,14 @@ __device__ __forceinline__ uint32_t bump(unsigned long long* meta, int32_t row) 
 }
 
 // kind 0: pairwise (u,i,j[,nbr]); kind 1: pointwise (u,i,y[,nbr]); kind 2: cml (u,i,neg[R])
-template <int KIND, bool COUNT>
+template <int KIND, bool COUNT, bool DYN = false>
 __global__ void __launch_bounds__(256) sample_kernel(SamplerArgs a, int64_t first, int64_t count, int32_t* __restrict__ ou,
                                                      int32_t* __restrict__ oi, int32_t* __restrict__ oj, float* __restrict__ oy,
                                                      int32_t* __restrict__ onbr, unsigned long long* metaU,
                                                      unsigned long long* metaI, uint32_t* __restrict__ rk0,
                                                      uint32_t* __restrict__ rk1, uint32_t* __restrict__ rk2,
                                                      crb_step_ctr* ctr) {
-    if (a.dyn) {
+    if (DYN) {   // epoch-graph replays only: the keys become registers (16 more than the constant-bank operands of the plain kernel)
 #pragma unroll
         for (int q = 0; q < 6; ++q) a.keys[q] = a.dyn[q];
         a.epoch = a.dyn[6];
@@ -232,7 +232,10 @@ int crb_launch_sample_pairwise(crb_handle* h, uint64_t seed, uint32_t epoch, int
     CRB_CHECK_ARG(first >= 0 && count >= 0 && (uint64_t)(first + count) <= a.n_rows, "rows outside the epoch");
     if (count == 0) return CRB_OK;
     int grid = sampler_grid(h, count);
-    if (count_rows)
+    if (count_rows && h->dyn_mode)
+        sample_kernel<0, true, true><<<grid, 256, 0, s>>>(a, first, count, u, i, j, nullptr, nbr, h->meta[0], h->meta[1], h->rank[0],
+                                                          h->rank[1], h->rank[2], h->ctr);
+    else if (count_rows)
         sample_kernel<0, true><<<grid, 256, 0, s>>>(a, first, count, u, i, j, nullptr, nbr, h->meta[0], h->meta[1], h->rank[0],
                                                     h->rank[1], h->rank[2], h->ctr);
     else

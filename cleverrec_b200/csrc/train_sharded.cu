@@ -134,10 +134,7 @@ __global__ void __launch_bounds__(256, 3) shard_step_kernel(ShardStepArgs a) {
         item_row_load<LANES, VPL>(frj, a, j1, a.sbj[t1], a.dim, gl);
         row_load_w<LANES, VPL>(nru, a.P, nu, a.dim, gl);
     }
-    // the user row's multiplicity word and `last` step decide whether its optimizer slots are loaded: fetched one iteration ahead
-    // too, so that decision is not a dependent round trip inside the iteration (it was the kernel's top stall: 30 % of the samples)
-    unsigned long long nmu = a.metaU[nu];
-    int32_t nlu = OptTraits<OPT>::replay ? a.P.last[nu] : 0;
+
     for (int64_t base = base0; base < a.batch; base += stride) {
         const int64_t t = base + sub;
         const bool active = t < a.batch;
@@ -148,19 +145,19 @@ __global__ void __launch_bounds__(256, 3) shard_step_kernel(ShardStepArgs a) {
         const int32_t sbi = a.sbi[tt], sbj = a.sbj[tt];
         const uint32_t rki = a.rk[1][tt], rkj = a.rk[2][tt];
         // rotate the pipeline: iteration n+1's item rows were requested last time; request n+2's and n+1's user row
-        const unsigned long long mu = nmu;
-        ru.last = nlu;
         nu = u1; ni = i1; nj = j1;
         nri = fri; nrj = frj;
         row_load_w<LANES, VPL>(nru, a.P, nu, a.dim, gl);
-        nmu = a.metaU[nu];
-        nlu = OptTraits<OPT>::replay ? a.P.last[nu] : 0;
         item_row_load<LANES, VPL>(fri, a, i2, si2, a.dim, gl);
         item_row_load<LANES, VPL>(frj, a, j2, sj2, a.dim, gl);
         u1 = u2; i1 = i2; j1 = j2;
         { const int64_t t3 = clampt(base + 3 * stride); u2 = a.u[t3]; i2 = a.i[t3]; j2 = a.j[t3]; si2 = a.sbi[t3]; sj2 = a.sbj[t3]; }
+        // (Fetching this word and `last` one iteration ahead was measured: the three extra live registers spill at the 80-register
+        // budget of three CTAs per SM and the kernel went from 1.35 to 1.59 ms at N=2.)
+        const unsigned long long mu = a.metaU[u];
         // item rows are always current at a step boundary (the owner brings its whole shard to the step in phase 2), so only the
         // local user row can have missed steps to replay
+        ru.last = OptTraits<OPT>::replay ? a.P.last[u] : 0;
         const bool su = (uint32_t)mu == 1u || replay_pending<OPT>(ru.last, a.opt);
         if (OptTraits<OPT>::has_s1 && su) row_load_state<LANES, VPL, OPT>(ru, a.P, u, a.dim, gl);
         if (replay_pending<OPT>(ru.last, a.opt)) row_replay<LANES, VPL, OPT>(ru, a.opt, a.opt.step);
