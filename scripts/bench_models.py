@@ -116,8 +116,8 @@ def main():
     # may execute oracle/) -- reference-algorithm Python sampler + restated TF-1 BPR/Adam step, one 6144-row batch per step
     from bench import cpu_reference_steps
     threads = os.cpu_count() or 1
-    times, done, n_users = cpu_reference_steps(dict(users=ML1M['users'], items=ML1M['items'], dim=64, mean_hist=ML1M['mean'], batch=6144, neg_ratio=4),
-                                               6, 6144, threads)
+    times, done, n_users, _ = cpu_reference_steps(dict(users=ML1M['users'], items=ML1M['items'], dim=64, mean_hist=ML1M['mean'], batch=6144, neg_ratio=4),
+                                                  6, 6144, threads)
     sec = sum(times[1:]) / len(times[1:])
     cpu = {"what": "reference CPU path restated (bench.py cpu_reference_steps), BPR at the ml-1m shape: Python sampler + row-sparse TF-1 Adam step "
                    "(torch-CPU fp32) per 6144-row batch", "cores": threads, "rows_per_step": done, "step_s": sec, "rows_per_s": done / sec}
