@@ -47,8 +47,10 @@ def test_lrml_steps(eng, kind, d, mem):
         got = eng.train_step_lrml(P, Q, dense, s1, s2, mem, opt, u, i, j, hp["margin"], hp["reg"])
         b = {"u": torch.tensor(u), "i": torch.tensor(i), "j": torch.tensor(j)}
         want = T.train_step(T.lrml_loss, ref, b, hp, ropt, sparse_index={"P": ["u"], "Q": ["i", "j"]})
-        assert abs(got - want) <= 5e-5 * abs(want), (got, want)
-    rtol, atol = (3e-4, 3e-5) if kind == "Adam" else (3e-5, 2e-6)
+        assert abs(got - want) <= 1e-4 * abs(want), (got, want)
+    # the dense-apply kernels accumulate table gradients with float atomics: the summation order, hence the last bits, vary from
+    # run to run; the bar is north_star's 1e-4 relative (one run in ~20 exceeded the former 3e-5 on a handful of Adagrad entries)
+    rtol, atol = (3e-4, 3e-5) if kind == "Adam" else (1e-4, 5e-6)
     _close(P.w.cpu().numpy(), ref["P"].numpy(), rtol, atol, "P")
     _close(Q.w.cpu().numpy(), ref["Q"].numpy(), rtol, atol, "Q")
     _close(dense.cpu().numpy(), torch.cat([ref["K"].reshape(-1), ref["M"].reshape(-1)]).numpy(), rtol, atol, "K|M")
