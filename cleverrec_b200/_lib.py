@@ -23,7 +23,7 @@ EXPORTS = [
     "crb_train_step_cml", "crb_set_history_lists", "crb_train_step_fism", "crb_fism_user_vectors", "crb_clip_rows",
     "crb_train_step_neumf", "crb_score_pairs_neumf", "crb_mask_seen",
     "crb_sample_nais", "crb_train_step_nais", "crb_train_epoch_nais", "crb_score_nais",
-    "crb_shard_step_compute", "crb_shard_step_prepare", "crb_shard_apply_inbox", "crb_shard_barrier", "crb_shard_check", "crb_sampler_errors", "crb_malloc", "crb_free", "crb_ipc_export",
+    "crb_shard_step_compute", "crb_shard_step_compute_pointwise", "crb_shard_apply_dense", "crb_shard_step_prepare", "crb_shard_apply_inbox", "crb_shard_barrier", "crb_shard_check", "crb_sampler_errors", "crb_malloc", "crb_free", "crb_ipc_export",
     "crb_ipc_open", "crb_ipc_close", "crb_build_history", "crb_prep_filter_reindex", "crb_prep_split_loo", "crb_prep_eval_negatives", "crb_set_item_lists", "crb_train_step_transcf", "crb_transcf_neighbourhood", "crb_score_pairs_transcf", "crb_np_seed", "crb_np_set_state", "crb_np_get_state", "crb_sample_epoch_numpy",
     "crb_train_step_lrml", "crb_score_pairs_lrml", "crb_set_social", "crb_sample_sbpr", "crb_train_step_sbpr", "crb_train_epoch_bpr_feeds", "crb_train_epoch_pointwise",
 ]
@@ -40,12 +40,13 @@ class CrbOpt(C.Structure):
 
 
 MAX_RANKS = 8
-SHARD_FLAGS, SHARD_ERR = 16, 8
+SHARD_FLAGS, SHARD_ERR, SHARD_DENSE = 16, 8, 512
 
 
 class CrbShard(C.Structure):
     _fields_ = [("n_ranks", C.c_int32), ("rank", C.c_int32), ("rows_cap", C.c_int64), ("q", CrbTable * MAX_RANKS),
-                ("inbox_grad", C.c_void_p * MAX_RANKS), ("inbox_stamp", C.c_void_p * MAX_RANKS), ("flags", C.c_void_p * MAX_RANKS)]
+                ("inbox_grad", C.c_void_p * MAX_RANKS), ("inbox_stamp", C.c_void_p * MAX_RANKS), ("flags", C.c_void_p * MAX_RANKS),
+                ("dense_inbox", C.c_void_p * MAX_RANKS)]
 
 
 class CrbError(RuntimeError):
@@ -127,6 +128,8 @@ def load():
     lib.crb_score_pairs_transcf.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, i64, vp, vp]
     lib.crb_shard_step_prepare.argtypes = [vp, T, u64, u32, i64, i32, i64, i64, vp, vp, vp, vp]
     lib.crb_shard_apply_inbox.argtypes = [vp, S, O, vp]
+    lib.crb_shard_step_compute_pointwise.argtypes = [vp, i32, T, S, vp, O, i32, vp, vp, vp, u64, u32, i64, i32, i64, f32, vp, vp]
+    lib.crb_shard_apply_dense.argtypes = [vp, S, O, vp, vp, vp, i32, vp]
     lib.crb_shard_barrier.argtypes = [vp, S, u32, i32, vp]
     lib.crb_shard_check.argtypes = [vp, S, vp]
     lib.crb_sampler_errors.argtypes = [vp, C.POINTER(u32), vp]

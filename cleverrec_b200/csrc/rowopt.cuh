@@ -260,3 +260,7 @@ int crb_table_check(const crb_table* T, int opt_kind, const char* name);
 int crb_launch_loss_final(crb_handle* h, double* loss_out_dev, cudaStream_t s);
 TableDev crb_to_dev(const crb_table* T);
 int crb_zero_step_counters(crb_handle* h, cudaStream_t s);
+int crb_launch_dense_apply_strided(crb_handle* h, float* w, float* s1, float* s2, const float* parts, int n_parts, int n, int part_stride,
+                                   int opt_kind, const OptDev& od, cudaStream_t s);
+int crb_launch_dense_apply(crb_handle* h, float* w, float* s1, float* s2, const float* parts, int n_parts, int n, int opt_kind, const OptDev& od,
+                           cudaStream_t s);   // TF dense apply of a small dense variable from n_parts partial gradients summed in order

@@ -954,10 +954,11 @@ __global__ void __launch_bounds__(256) pointwise_step_kernel(PwArgs a) {
 // TF dense apply of a small dense variable (ApplyGradientDescent / ApplyAdagrad / ApplyAdam) whose gradient arrives as
 // per-block partials [n_parts, n]; summed in block order (deterministic).
 __global__ void __launch_bounds__(256) dense_apply_kernel(float* w, float* s1, float* s2, const float* parts, int n_parts, int n,
-                                                         int opt_kind, OptDev o) {
+                                                         int opt_kind, OptDev o, int part_stride = 0) {
+    const int64_t ps = part_stride > 0 ? part_stride : n;   // distance between consecutive partial vectors
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         float g = 0.f;
-        for (int p = 0; p < n_parts; ++p) g += parts[(int64_t)p * n + k];
+        for (int p = 0; p < n_parts; ++p) g += parts[(int64_t)p * ps + k];
         float x = w[k];
         if (opt_kind == OPT_SGD) {
             x = __fsub_rn(x, __fmul_rn(o.lr, g));
@@ -974,6 +975,22 @@ __global__ void __launch_bounds__(256) dense_apply_kernel(float* w, float* s1, f
         }
         w[k] = x;
     }
+}
+
+int crb_launch_dense_apply(crb_handle* h, float* w, float* s1, float* s2, const float* parts, int n_parts, int n, int opt_kind, const OptDev& od,
+                           cudaStream_t s) {
+    dense_apply_kernel<<<1, 256, 0, s>>>(w, s1, s2, parts, n_parts, n, opt_kind == OPT_ADAM_TF1 ? OPT_ADAM_LAZY : opt_kind, od);
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}
+
+int crb_launch_dense_apply_strided(crb_handle* h, float* w, float* s1, float* s2, const float* parts, int n_parts, int n, int part_stride,
+                                   int opt_kind, const OptDev& od, cudaStream_t s) {
+    dense_apply_kernel<<<1, 256, 0, s>>>(w, s1, s2, parts, n_parts, n, opt_kind == OPT_ADAM_TF1 ? OPT_ADAM_LAZY : opt_kind, od, part_stride);
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
 }
 
 template <int LANES, int VPL>

@@ -30,6 +30,30 @@ struct ShardDev {
     ShardSend send;
 };
 
+// ------------------------------------------------------------------------------------------------ pointwise family (MF / GMF)
+struct ShardPwArgs {
+    TableDev P;
+    unsigned long long* metaU;
+    unsigned long long* metaI;
+    ShardDev sh;
+    const int32_t* u;   // local user rows
+    const int32_t* i;   // GLOBAL item ids
+    const float* y;
+    const int32_t* sbi;
+    const uint32_t* rk[2];
+    const float* stage;
+    const float* hvec;  // GMF's h (replicated), NULL for MF
+    float* hpart;       // [gridDim.x, dim] per-block partial gradient of h
+    int64_t batch;
+    int dim;
+    int loss_kind;
+    float reg;
+    OptDev opt;
+    float* dup_grad;
+    uint32_t* dup_t;
+    double* block_loss;
+};
+
 struct ShardStepArgs {
     TableDev P;
     unsigned long long* metaU;
@@ -620,6 +644,300 @@ extern "C" int crb_shard_check(crb_handle* h, const crb_shard* shard, void* stre
         return CRB_ERR_SAMPLER;
     }
     return CRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ pointwise step (MF / GMF)
+// sess.run([train, loss], {u_idx, i_idx, y}) on this rank's slice of the union batch (GMF.py:37-49): logit = sum_k p_uk q_ik [h_k];
+// loss = get_loss(loss_func, y, logit) + reg * (l2(p_u) + l2(q_i)).  The item row comes from the staging buffer (repeated in this
+// rank's batch) or straight from its owner; its gradient goes to a local slot or straight into the owner's inbox -- as in
+// shard_step_kernel.  The next iteration's rows are requested before the current one is computed.
+template <int LANES, int VPL, int OPT, bool GMF>
+__global__ void __launch_bounds__(256) shard_pw_step_kernel(ShardPwArgs a) {
+    constexpr int GPW = 32 / LANES;
+    __shared__ float4 s_h[GMF ? 256 * VPL : 1];
+    const int lane = threadIdx.x & 31, gl = lane % LANES, sub = lane / LANES;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int G = a.sh.n_ranks;
+    float4 hreg[VPL], gh[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        const int c = (gl + LANES * v) * 4;
+        hreg[v] = (GMF && c < a.dim) ? ld4(a.hvec + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+        gh[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    double loss_acc = 0.0;
+    const int64_t stride = n_warps * GPW;
+    auto clampt = [&](int64_t b) { const int64_t t_ = b + sub; return t_ < a.batch ? t_ : a.batch - 1; };
+    auto load_item = [&](RowRegs<LANES, VPL>& r, int32_t item, int32_t sb) {
+        const float* src = sb >= 0 ? a.stage + (int64_t)sb * a.dim : a.sh.q[item % G].w + (int64_t)(item / G) * a.dim;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const int c = (gl + LANES * v) * 4;
+            r.w[v] = c < a.dim ? ld4(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    int32_t nu, ni, nsb;
+    RowRegs<LANES, VPL> nru, nri;
+    { const int64_t t0 = clampt(warp * GPW); nu = a.u[t0]; ni = a.i[t0]; nsb = a.sbi[t0]; }
+    row_load_w<LANES, VPL>(nru, a.P, nu, a.dim, gl);
+    load_item(nri, ni, nsb);
+    for (int64_t base = warp * GPW; base < a.batch; base += stride) {
+        const int64_t t = base + sub;
+        const bool active = t < a.batch;
+        const int64_t tt = active ? t : a.batch - 1;
+        const int32_t u = nu, i = ni, sbi = nsb;
+        RowRegs<LANES, VPL> ru = nru, ri = nri;
+        { const int64_t t1 = clampt(base + stride); nu = a.u[t1]; ni = a.i[t1]; nsb = a.sbi[t1]; }
+        row_load_w<LANES, VPL>(nru, a.P, nu, a.dim, gl);
+        load_item(nri, ni, nsb);
+        const float y = a.y[tt];
+        const unsigned long long mu = a.metaU[u];
+        ru.last = OptTraits<OPT>::replay ? a.P.last[u] : 0;
+        const bool su = (uint32_t)mu == 1u || replay_pending<OPT>(ru.last, a.opt);
+        if (OptTraits<OPT>::has_s1 && su) row_load_state<LANES, VPL, OPT>(ru, a.P, u, a.dim, gl);
+        if (replay_pending<OPT>(ru.last, a.opt)) row_replay<LANES, VPL, OPT>(ru, a.opt, a.opt.step);
+        float x = 0.f, sq = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const float4 p = ru.w[v], q = ri.w[v], hh = hreg[v];
+            const float4 pq = make_float4(p.x * q.x, p.y * q.y, p.z * q.z, p.w * q.w);
+            x += GMF ? dot4(pq, hh) : (pq.x + pq.y + pq.z + pq.w);
+            sq += dot4(p, p) + dot4(q, q);
+        }
+        x = group_sum<LANES>(x);
+        sq = group_sum<LANES>(sq);
+        float g, l;
+        if (a.loss_kind == CRB_LOSS_CROSS_ENTROPY) {  // utils/tools.py:68-69
+            l = fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x)));
+            g = sigmoid_f(x) - y;
+        } else {                                       // 'square', utils/tools.py:74-75
+            l = (y - x) * (y - x);
+            g = 2.f * (x - y);
+        }
+        if (active && gl == 0) loss_acc += (double)(l + a.reg * 0.5f * sq);
+        float4 gu[VPL], gi[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const float4 p = ru.w[v], q = ri.w[v], hh = hreg[v];
+            gu[v] = make_float4(fmaf(g, q.x * hh.x, a.reg * p.x), fmaf(g, q.y * hh.y, a.reg * p.y), fmaf(g, q.z * hh.z, a.reg * p.z),
+                                fmaf(g, q.w * hh.w, a.reg * p.w));
+            gi[v] = make_float4(fmaf(g, p.x * hh.x, a.reg * q.x), fmaf(g, p.y * hh.y, a.reg * q.y), fmaf(g, p.z * hh.z, a.reg * q.z),
+                                fmaf(g, p.w * hh.w, a.reg * q.w));
+            if (GMF && active) {
+                gh[v].x = fmaf(g, p.x * q.x, gh[v].x); gh[v].y = fmaf(g, p.y * q.y, gh[v].y);
+                gh[v].z = fmaf(g, p.z * q.z, gh[v].z); gh[v].w = fmaf(g, p.w * q.w, gh[v].w);
+            }
+        }
+        if (active) {
+            emit_row<LANES, VPL, OPT>(ru, gu, a.P, a.metaU, u, mu, a.rk[0][t], (uint32_t)t, 0u, a.dim, gl, a.opt, a.dup_grad, a.dup_t);
+            if (sbi < 0) {
+                shard_send<LANES, VPL>(a.sh.send, i, gi, a.dim, gl);
+                if (gl == 0) a.metaI[i] = 0ULL;
+            } else {
+                const uint32_t slot = (uint32_t)sbi + a.rk[1][t];
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    const int c = (gl + LANES * v) * 4;
+                    if (c < a.dim) st4(a.dup_grad + (int64_t)slot * a.dim + c, gi[v]);
+                }
+                if (gl == 0) a.dup_t[slot] = ((uint32_t)t << 2) | 1u;
+            }
+        }
+    }
+    if (GMF) {
+        // fixed-order block reduction of the h gradient: thread -> smem, then one thread per float4 chunk sums the groups
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) s_h[threadIdx.x * VPL + v] = gh[v];
+        __syncthreads();
+        constexpr int GROUPS = 256 / LANES;
+        for (int c = threadIdx.x; c < LANES * VPL; c += blockDim.x) {
+            const int l = c % LANES, v = c / LANES;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int gI = 0; gI < GROUPS; ++gI) {
+                const float4 t4 = s_h[(gI * LANES + l) * VPL + v];
+                acc.x += t4.x; acc.y += t4.y; acc.z += t4.z; acc.w += t4.w;
+            }
+            const int col = (l + LANES * v) * 4;
+            if (col < a.dim) st4(a.hpart + (int64_t)blockIdx.x * a.dim + col, acc);
+        }
+    }
+    block_loss_store(loss_acc, a.block_loss);
+}
+
+__global__ void __launch_bounds__(256) shard_resolve1_kernel(const unsigned long long* __restrict__ metaI, const int32_t* __restrict__ i, int64_t batch,
+                                                             int32_t* __restrict__ sbi) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < batch; t += stride) {
+        const unsigned long long mi = metaI[i[t]];
+        sbi[t] = (uint32_t)mi > 1u ? (int32_t)(mi >> 32) : -1;
+    }
+}
+
+// this rank's total gradient of the replicated dense variable (block partials summed in block order) -> slot `rank` of EVERY rank's
+// dense inbox
+struct DenseSendArgs {
+    const float* parts;
+    int n_parts, n, n_ranks, rank;
+    float* inbox[CRB_MAX_RANKS];
+};
+__global__ void __launch_bounds__(256) shard_dense_send_kernel(DenseSendArgs a) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < a.n; k += gridDim.x * blockDim.x) {
+        float g = 0.f;
+        for (int p = 0; p < a.n_parts; ++p) g += a.parts[(int64_t)p * a.n + k];
+        for (int r = 0; r < a.n_ranks; ++r) a.inbox[r][a.rank * CRB_SHARD_DENSE + k] = g;
+    }
+}
+
+template <int LANES, int VPL>
+static int launch_shard_pw_t(crb_handle* h, const ShardPwArgs& a, int opt_kind, bool gmf, cudaStream_t s) {
+    const int gpb = 256 / LANES;
+    int rc;
+    if ((rc = crb_prof_begin(h, s, 1))) return rc;
+    item_fetch_kernel<LANES, VPL><<<h->sm_count * 8, 256, 0, s>>>(a.sh, h->dup_rows, h->ctr, h->stage, a.dim);
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    if ((rc = crb_prof_end(h, s, 1))) return rc;
+    if ((rc = crb_prof_begin(h, s))) return rc;
+#define CRB_SHPW_CASE(O)                                                                                  \
+    case O: {                                                                                             \
+        if (gmf) {                                                                                        \
+            const int grid = one_wave(h, shard_pw_step_kernel<LANES, VPL, O, true>, a.batch, gpb);        \
+            h->step_grid = grid;                                                                          \
+            shard_pw_step_kernel<LANES, VPL, O, true><<<grid, 256, 0, s>>>(a);                            \
+        } else {                                                                                          \
+            const int grid = one_wave(h, shard_pw_step_kernel<LANES, VPL, O, false>, a.batch, gpb);       \
+            h->step_grid = grid;                                                                          \
+            shard_pw_step_kernel<LANES, VPL, O, false><<<grid, 256, 0, s>>>(a);                           \
+        }                                                                                                 \
+        break;                                                                                            \
+    }
+    switch (opt_kind) { CRB_SHPW_CASE(OPT_SGD) CRB_SHPW_CASE(OPT_ADAGRAD) CRB_SHPW_CASE(OPT_ADAM_LAZY) CRB_SHPW_CASE(OPT_ADAM_TF1) }
+#undef CRB_SHPW_CASE
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    if ((rc = crb_prof_end(h, s))) return rc;
+    DupArgs d;
+    d.tab[0] = a.P; d.tab[1] = a.P;
+    d.meta[0] = a.metaU; d.meta[1] = a.metaI;
+    d.dim = a.dim; d.opt = a.opt;
+    d.dup_rows = h->dup_rows; d.work = h->work; d.multi = h->multi;
+    d.dup_grad = h->dup_grad; d.dup_t = h->dup_t; d.partial = h->partial; d.ctr = h->ctr;
+    d.send = a.sh.send;
+    const int grid = h->sm_count * 4;
+    if ((rc = crb_prof_begin(h, s, 2))) return rc;
+#define CRB_SHDUP_CASE(O)                                                        \
+    case O:                                                                      \
+        dup_reduce_kernel<LANES, VPL, O, true><<<grid, 256, 0, s>>>(d);          \
+        dup_final_kernel<LANES, VPL, O, true><<<h->sm_count, 256, 0, s>>>(d);    \
+        break;
+    switch (opt_kind) { CRB_SHDUP_CASE(OPT_SGD) CRB_SHDUP_CASE(OPT_ADAGRAD) CRB_SHDUP_CASE(OPT_ADAM_LAZY) CRB_SHDUP_CASE(OPT_ADAM_TF1) }
+#undef CRB_SHDUP_CASE
+    h->launches += 2;
+    CRB_CUDA(cudaGetLastError());
+    return crb_prof_end(h, s, 2);
+}
+
+extern "C" int crb_shard_step_compute_pointwise(crb_handle* h, int32_t kind, const crb_table* P, const crb_shard* shard, const float* hvec,
+                                                const crb_opt* opt, int32_t loss_kind, const int32_t* u, const int32_t* i, const float* y,
+                                                uint64_t seed, uint32_t epoch, int64_t first, int32_t neg_ratio, int64_t batch, float reg,
+                                                double* loss_out, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    CRB_CHECK_ARG(h && P && shard, "null argument");
+    CRB_CHECK_ARG(batch > 0 && batch < 0x20000000LL, "batch");
+    CRB_CHECK_ARG(kind == CRB_SCORE_DOT || kind == CRB_SCORE_GMF, "kind must be CRB_SCORE_DOT (MF) or CRB_SCORE_GMF");
+    CRB_CHECK_ARG(loss_kind == CRB_LOSS_CROSS_ENTROPY || loss_kind == CRB_LOSS_SQUARE, "pointwise loss must be cross_entropy or square");
+    const bool gmf = kind == CRB_SCORE_GMF;
+    CRB_CHECK_ARG(!gmf || (hvec && crb_is_device_ptr(hvec)), "GMF needs the device vector h");
+    OptDev od;
+    int opt_kind = 0;
+    int rc = crb_opt_to_dev(h, opt, &od, &opt_kind, s);
+    if (rc) return rc;
+    if ((rc = crb_table_check(P, opt_kind, "P"))) return rc;
+    ShardPwArgs a;
+    if ((rc = shard_to_dev(shard, &a.sh, (uint32_t)od.step))) return rc;
+    CRB_CHECK_ARG(shard->q[shard->rank].dim == P->dim, "P.dim != Q.dim");
+    CRB_CHECK_ARG(!gmf || P->dim <= CRB_SHARD_DENSE, "GMF: dim exceeds the dense inbox");
+    for (int r = 0; gmf && r < shard->n_ranks; ++r) CRB_CHECK_ARG(shard->dense_inbox[r], "shard descriptor: null dense inbox");
+    const int64_t n_items = shard_items(shard);
+    CRB_CUDA(cudaSetDevice(h->device));
+    if (h->alt_active) crb_alt_swap(h);
+    if ((rc = crb_ws_reserve(h, batch, P->dim, 4, s))) return rc;
+    if ((rc = crb_meta_reserve(h, 0, P->rows, s))) return rc;
+    if ((rc = crb_meta_reserve(h, 1, n_items, s))) return rc;
+    if ((rc = stage_reserve(h, P->dim, s))) return rc;
+    if (gmf) {
+        const int64_t need = (int64_t)h->loss_blocks * P->dim;
+        if (need > h->cap_dense) {
+            CRB_CUDA(cudaStreamSynchronize(s));
+            cudaFree(h->dense_grad);
+            h->dense_grad = nullptr;
+            CRB_CUDA(cudaMalloc(&h->dense_grad, sizeof(float) * need));
+            h->cap_dense = need;
+        }
+    }
+    if ((rc = crb_zero_step_counters(h, s))) return rc;
+    const int32_t *du = u, *di = i;
+    const float* dy = y;
+    bool counted = false;
+    if (!u) {
+        if ((rc = crb_launch_sample_pointwise(h, seed, epoch, first, batch, neg_ratio, h->idx[0], h->idx[1], h->yv, true, s))) return rc;
+        du = h->idx[0]; di = h->idx[1]; dy = h->yv;
+        counted = true;
+    } else {
+        CRB_CHECK_ARG(i && y, "null feed");
+        if (!crb_is_device_ptr(u)) { CRB_CUDA(cudaMemcpyAsync(h->idx[0], u, 4 * batch, cudaMemcpyHostToDevice, s)); du = h->idx[0]; }
+        if (!crb_is_device_ptr(i)) { CRB_CUDA(cudaMemcpyAsync(h->idx[1], i, 4 * batch, cudaMemcpyHostToDevice, s)); di = h->idx[1]; }
+        if (!crb_is_device_ptr(y)) { CRB_CUDA(cudaMemcpyAsync(h->yv, y, 4 * batch, cudaMemcpyHostToDevice, s)); dy = h->yv; }
+    }
+    const int32_t* idx[3] = {du, di, nullptr};
+    const int role_table[3] = {0, 1, 0};
+    if (!counted && (rc = crb_count_rows(h, batch, 2, idx, role_table, s))) return rc;
+    if ((rc = crb_launch_assign(h, batch, 2, idx, role_table, s))) return rc;
+    {
+        int64_t blocks = (batch + 255) / 256;
+        const int64_t capb = (int64_t)h->sm_count * 16;
+        shard_resolve1_kernel<<<(int)(blocks < capb ? blocks : capb), 256, 0, s>>>(h->meta[1], di, batch, h->sb[0]);
+        h->launches++;
+        CRB_CUDA(cudaGetLastError());
+    }
+    a.P = crb_to_dev(P); a.metaU = h->meta[0]; a.metaI = h->meta[1]; a.u = du; a.i = di; a.y = dy; a.sbi = h->sb[0];
+    a.rk[0] = h->rank[0]; a.rk[1] = h->rank[1]; a.stage = h->stage; a.hvec = gmf ? hvec : nullptr; a.hpart = h->dense_grad;
+    a.batch = batch; a.dim = P->dim; a.loss_kind = loss_kind; a.reg = reg; a.opt = od;
+    a.dup_grad = h->dup_grad; a.dup_t = h->dup_t; a.block_loss = h->block_loss;
+    if ((rc = CRB_DIM_DISPATCH(a.dim, launch_shard_pw_t, h, a, opt_kind, gmf, s))) return rc;
+    if (gmf) {
+        DenseSendArgs ds;
+        ds.parts = h->dense_grad; ds.n_parts = h->step_grid; ds.n = P->dim; ds.n_ranks = shard->n_ranks; ds.rank = shard->rank;
+        for (int r = 0; r < CRB_MAX_RANKS; ++r) ds.inbox[r] = r < shard->n_ranks ? shard->dense_inbox[r] : nullptr;
+        shard_dense_send_kernel<<<1, 256, 0, s>>>(ds);
+        h->launches++;
+        CRB_CUDA(cudaGetLastError());
+    }
+    double* ld = (loss_out && crb_is_device_ptr(loss_out)) ? loss_out : h->loss_dev;
+    if ((rc = crb_launch_loss_final(h, ld, s))) return rc;
+    if (loss_out && !crb_is_device_ptr(loss_out)) {
+        CRB_CUDA(cudaMemcpyAsync(loss_out, h->loss_dev, sizeof(double), cudaMemcpyDeviceToHost, s));
+        CRB_CUDA(cudaStreamSynchronize(s));
+    }
+    return CRB_OK;
+}
+
+// after the barrier: h -= dense optimizer step on the gradient summed over the ranks in rank order (identical on every rank)
+extern "C" int crb_shard_apply_dense(crb_handle* h, const crb_shard* shard, const crb_opt* opt, float* hvec, float* h_s1, float* h_s2, int32_t dim,
+                                     void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    CRB_CHECK_ARG(h && shard && hvec && dim > 0 && dim <= CRB_SHARD_DENSE, "bad argument");
+    CRB_CHECK_ARG(shard->dense_inbox[shard->rank], "shard descriptor: null dense inbox");
+    OptDev od;
+    int opt_kind = 0;
+    int rc = crb_opt_to_dev(h, opt, &od, &opt_kind, s);
+    if (rc) return rc;
+    CRB_CHECK_ARG(opt_kind == OPT_SGD || h_s1, "h optimizer slot s1 is NULL");
+    CRB_CHECK_ARG((opt_kind != OPT_ADAM_LAZY && opt_kind != OPT_ADAM_TF1) || h_s2, "h optimizer slot s2 is NULL");
+    CRB_CUDA(cudaSetDevice(h->device));
+    // the n_ranks partial vectors sit CRB_SHARD_DENSE floats apart in this rank's dense inbox
+    return crb_launch_dense_apply_strided(h, hvec, h_s1, h_s2, shard->dense_inbox[shard->rank], shard->n_ranks, dim, CRB_SHARD_DENSE, opt_kind, od, s);
 }
 
 // ------------------------------------------------------------------------------------------------ peer memory plumbing

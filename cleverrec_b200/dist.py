@@ -138,7 +138,8 @@ class ShardedBPR(object):
         self.rows_cap = shard_rows(n_items, 0, self.world)
         self.inbox = {"grad": _DeviceBuffer(engine, (self.world * self.rows_cap, dim), torch.float32),
                       "stamp": _DeviceBuffer(engine, (self.world * self.rows_cap,), torch.int32),
-                      "flags": _DeviceBuffer(engine, (_lib.SHARD_FLAGS,), torch.int32)}
+                      "flags": _DeviceBuffer(engine, (_lib.SHARD_FLAGS,), torch.int32),
+                      "dense": _DeviceBuffer(engine, (self.world * _lib.SHARD_DENSE,), torch.float32)}
         self._map_peers()
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
@@ -167,6 +168,7 @@ class ShardedBPR(object):
                 return store[kind].ptr if local else open_(info[("q_" if store is self.q else "in_") + kind])
             sh.q[r] = CrbTable(pointer("w", self.q), pointer("s1", self.q), pointer("s2", self.q), pointer("last", self.q), info["rows"], self.dim, 0)
             sh.inbox_grad[r], sh.inbox_stamp[r], sh.flags[r] = pointer("grad", self.inbox), pointer("stamp", self.inbox), pointer("flags", self.inbox)
+            sh.dense_inbox[r] = pointer("dense", self.inbox)
         self.shard = sh
 
     def barrier(self):
@@ -323,6 +325,64 @@ class ShardedBPR(object):
         for b in list(self.q.values()) + list(self.inbox.values()):
             b.tensor = None
             self.engine.lib.crb_free(self.engine.h, b.ptr)
+
+
+class ShardedPointwise(ShardedBPR):
+    """MF / GMF (model/ranking/GMF.py:37-49; MF per SURVEY F6) over the same partition: P by user, Q row-sharded, item rows and
+    gradients over peer memory exactly as for BPR.  GMF's h is replicated; its gradient is summed over the ranks through the dense
+    inbox (crb_shard_apply_dense), the same update on every rank."""
+
+    def __init__(self, engine, n_users, n_items, dim, optimizer, lr, adam_mode, batch, kind=_lib.SCORE_DOT, loss_kind=_lib.LOSS_CROSS_ENTROPY,
+                 init_P=None, init_Q=None, init_h=None, seed=0, group=None, barrier=None, barrier_timeout_ms=20000):
+        ShardedBPR.__init__(self, engine, n_users, n_items, dim, optimizer, lr, adam_mode, batch, init_P=init_P, init_Q=init_Q, seed=seed, group=group,
+                            barrier=barrier, barrier_timeout_ms=barrier_timeout_ms)
+        self.kind, self.loss_kind = kind, loss_kind
+        self.h = self.h_s1 = self.h_s2 = None
+        if kind == _lib.SCORE_GMF:
+            dev = engine.device
+            if init_h is None:   # the same vector on every rank
+                init_h = torch.randn(dim, generator=torch.Generator().manual_seed(seed + 977)) * 0.01
+            self.h = torch.as_tensor(init_h, dtype=torch.float32).to(dev).contiguous()
+            if optimizer == "Adagrad":
+                self.h_s1 = torch.full_like(self.h, 0.1)
+            elif optimizer == "Adam":
+                self.h_s1, self.h_s2 = torch.zeros_like(self.h), torch.zeros_like(self.h)
+
+    def _one(self, co, u, i, y, seed, epoch, first, neg_ratio, batch, reg, lo):
+        eng, lib = self.engine, self.engine.lib
+        check(lib.crb_shard_step_compute_pointwise(eng.h, self.kind, C.byref(self.P.c), C.byref(self.shard), ptr(self.h), C.byref(co), self.loss_kind,
+                                                   ptr(u), ptr(i), ptr(y), seed, epoch, first, neg_ratio or 1, batch, float(reg), lo, eng.stream))
+        self.barrier()
+        check(lib.crb_shard_apply_inbox(eng.h, C.byref(self.shard), C.byref(co), eng.stream))
+        if self.h is not None:
+            check(lib.crb_shard_apply_dense(eng.h, C.byref(self.shard), C.byref(co), ptr(self.h), ptr(self.h_s1), ptr(self.h_s2), self.dim, eng.stream))
+        self.barrier()
+
+    def step(self, reg, neg_ratio=None, seed=0, epoch=0, first=0, batch=None, feed=None, loss_out=None):
+        """One synchronous step over the union batch.  feed = (u_local, i_global, y) or None to sample on the device."""
+        eng = self.engine
+        self.opt.t += 1
+        co = self.opt.c(self.opt.t)
+        batch = self.batch if batch is None else batch
+        u = i = y = None
+        if feed is not None:
+            u, i = (eng._feed_i32(x) for x in feed[:2])
+            y = feed[2] if isinstance(feed[2], torch.Tensor) else np.ascontiguousarray(np.asarray(feed[2]), dtype=np.float32)
+            batch = len(u)
+        host = np.zeros(1, dtype=np.float64) if loss_out is None else None
+        self._one(co, u, i, y, seed, epoch, first, neg_ratio, batch, reg, ptr(host) if loss_out is None else ptr(loss_out))
+        return float(host[0]) if loss_out is None else None
+
+    def run_steps(self, n_steps, reg, neg_ratio, seed, epoch, first=0, batch=None, loss_out=None, bounds=None, **_):
+        batch = self.batch if batch is None else batch
+        if bounds is None:
+            bounds = [first + k * batch for k in range(n_steps + 1)]
+        host = np.zeros(1, dtype=np.float64)
+        for k in range(n_steps):
+            self.opt.t += 1
+            co = self.opt.c(self.opt.t)
+            lo = ptr(host) if loss_out is None else ptr(loss_out[k:k + 1])
+            self._one(co, None, None, None, seed, epoch, bounds[k], neg_ratio, bounds[k + 1] - bounds[k], reg, lo)
 
 
 # ---------------------------------------------------------------------------------------------- evaluation across the item shards

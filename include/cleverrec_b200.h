@@ -94,7 +94,9 @@ typedef struct {
     float* inbox_grad[CRB_MAX_RANKS];
     uint32_t* inbox_stamp[CRB_MAX_RANKS];
     uint32_t* flags[CRB_MAX_RANKS];
+    float* dense_inbox[CRB_MAX_RANKS];   /* float [n_ranks][CRB_SHARD_DENSE]: per-source-rank gradient of a replicated dense variable (GMF's h) */
 } crb_shard;
+#define CRB_SHARD_DENSE 512
 
 /* utils/tools.py:66-76 (get_loss) */
 enum { CRB_LOSS_BPR = 0, CRB_LOSS_CROSS_ENTROPY = 1, CRB_LOSS_SQUARE = 2, CRB_LOSS_HINGE = 3 };
@@ -367,6 +369,18 @@ int crb_shard_step_compute(crb_handle* h, const crb_table* P, const crb_shard* s
 int crb_shard_step_prepare(crb_handle* h, const crb_table* P, uint64_t seed, uint32_t epoch, int64_t first, int32_t neg_ratio,
                            int64_t batch, int64_t n_items, const int32_t* feed_u, const int32_t* feed_i, const int32_t* feed_j,
                            void* stream);
+/* The same multi-GPU step for the POINTWISE dot-product family (MF: kind CRB_SCORE_DOT, GMF: CRB_SCORE_GMF; GMF.py:37-49, the loop of
+ * RankingRecommender.py:48-60): u = local user rows, i = GLOBAL item ids, y = labels (DEVICE or HOST), or u == NULL to sample rows
+ * [first, first+batch) of this rank's pointwise epoch.  Item rows and gradients travel exactly as in crb_shard_step_compute.  GMF's
+ * h is REPLICATED: every rank writes the sum of its gradient partials into slot `rank` of every peer's dense_inbox; after the
+ * barrier crb_shard_apply_dense adds the n_ranks vectors in rank order and applies TF's dense optimizer -- the same update on
+ * every rank, so the copies stay bit-identical. */
+int crb_shard_step_compute_pointwise(crb_handle* h, int32_t kind, const crb_table* P, const crb_shard* shard, const float* hvec,
+                                     const crb_opt* opt, int32_t loss_kind, const int32_t* u, const int32_t* i, const float* y,
+                                     uint64_t seed, uint32_t epoch, int64_t first, int32_t neg_ratio, int64_t batch, float reg,
+                                     double* loss_out, void* stream);
+int crb_shard_apply_dense(crb_handle* h, const crb_shard* shard, const crb_opt* opt, float* hvec, float* h_s1, float* h_s2, int32_t dim,
+                          void* stream);
 /* phase 2 (after the barrier): one pass over this rank's item rows -- the gradients that arrived for a row are summed in source-rank
  * order and applied once (TF's de-duplicated sparse apply on the union batch); with CRB_ADAM_TF1 a row that received nothing
  * takes its decay-only step, so remote readers always find current weights. */

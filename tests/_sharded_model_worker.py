@@ -61,6 +61,36 @@ def main():
             if split == "loo" and not np.mean(HR[0]) > 0.3:
                 print("QUALITY", np.mean(HR[0])); ok = False
         m._shm.close()
+    # ---- GMF and MF behind the same interface under WORLD_SIZE > 1 (pointwise epochs over the sharded tables)
+    import importlib
+    for name, extra in (("GMF", {'loss_func': 'cross_entropy', 'init_method': 'xavier_uniform', 'embed_size': '32', 'reg': '0.001'}),
+                        ("MF", {'loss_func': 'cross_entropy', 'embed_size': '32', 'reg': '0.001'})):
+        data = load_split("split_ml100k_loo.npz")
+        cfg = dict(CFG, recommender=name, is_pairwise='False', **extra)
+        cls = getattr(importlib.import_module('cleverrec_b200.model.ranking.' + name), name)
+        m = cls(None, data, cfg, logging.getLogger("w%d" % rank))
+        assert m.sharded
+        m.build_model()
+        l0 = m.train_model()
+        for _ in range(3):
+            l1 = m.train_model()
+        both = [None] * world
+        dist.all_gather_object(both, (l0, l1))
+        if not (np.isfinite(l1) and l1 < l0 and all(b == both[0] for b in both)):
+            print("PW LOSS", name, rank, l0, l1, both); ok = False
+        HR, MRR, NDCG = m.test_model_loo()
+        P, Q = m._shm.gather_P().cpu().numpy(), m._shm.gather_Q().cpu().numpy()
+        hv = m.h_gmf.cpu().numpy() if m.h_gmf is not None else None
+        if rank == 0:
+            kind = 1 if name == "GMF" else 0
+            scores = {u: O.score_pairs(kind, P, Q, np.full(len(data.ui_test[u]), u), np.asarray(data.ui_test[u]), hv) for u in m.test_users}
+            want = H.eval_loo(m.test_users, data.ui_test, scores, 99, m.topk)
+            for k in range(len(m.topk)):
+                if not (HR[k] == want[0][k] and MRR[k] == want[1][k] and NDCG[k] == want[2][k]):
+                    print("PW EVAL MISMATCH", name, k); ok = False
+            if not np.mean(HR[0]) > 0.2:
+                print("PW QUALITY", name, np.mean(HR[0])); ok = False
+        m._shm.close()
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     from cleverrec_b200.dist import all_reduce_dev
     all_reduce_dev(flag, op=dist.ReduceOp.MIN)

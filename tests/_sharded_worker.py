@@ -83,6 +83,66 @@ def main():
             ok = False
         m2.close()
         m.close()
+    # ---- the pointwise family (MF: dot, GMF: dot with the replicated vector h) over the same partition == the single-GPU pointwise
+    # step on the union batch; h stays bit-identical on every rank
+    from cleverrec_b200 import _lib as L
+    from cleverrec_b200.dist import ShardedPointwise
+    h0 = torch.randn(d, generator=g) * 0.3
+    for score_kind, loss_kind in ((L.SCORE_DOT, L.LOSS_SQUARE), (L.SCORE_GMF, L.LOSS_CROSS_ENTROPY)):
+        for kind, mode in (("SGD", "tf1"), ("Adagrad", "tf1"), ("Adam", "tf1")):
+            lo, hi = user_range(U, rank, world)
+            lr = 0.05 if kind != "Adam" else 0.01
+            m = ShardedPointwise(eng, U, I, d, kind, lr, mode, B, kind=score_kind, loss_kind=loss_kind, init_P=P0[lo:hi], init_Q=Q0,
+                                 init_h=h0 if score_kind == L.SCORE_GMF else None)
+            ref = None
+            if rank == 0:
+                ref = (Table(P0.clone().cuda(), kind, mode), Table(Q0.clone().cuda(), kind, mode), Optimizer(kind, lr, adam_mode=mode))
+                rh = h0.clone().cuda() if score_kind == L.SCORE_GMF else None
+                rs1 = (torch.full_like(rh, 0.1) if kind == "Adagrad" else torch.zeros_like(rh)) if rh is not None and kind != "SGD" else None
+                rs2 = torch.zeros_like(rh) if rh is not None and kind == "Adam" else None
+            rs = np.random.RandomState(9)
+            for step in range(4):
+                feeds = []
+                for r in range(world):
+                    l, h_ = user_range(U, r, world)
+                    n = B if step != 2 else 41
+                    feeds.append((rs.randint(l, h_, n), rs.randint(0, I, n), (rs.rand(n) < 0.3).astype(np.float32)))
+                u, i, y = feeds[rank]
+                loss = m.step(0.01, feed=(u - lo, i, y))
+                t = torch.tensor([loss], device="cuda", dtype=torch.float64)
+                all_reduce_dev(t)
+                if rank == 0:
+                    uu, ii, yy = (np.concatenate([f[k] for f in feeds]) for k in range(3))
+                    want = eng.train_step_pointwise(score_kind, ref[0], ref[1], ref[2], uu, ii, yy, 0.01, loss_kind, rh, rs1, rs2)
+                    if abs(float(t.item()) - want) > 1e-5 * abs(want):
+                        print("PW LOSS MISMATCH", score_kind, kind, step, float(t.item()), want)
+                        ok = False
+            m.check()
+            m.flush()
+            Qfull = m.gather_Q()
+            Pfull = m.gather_P()
+            hs = None
+            if score_kind == L.SCORE_GMF:
+                hs = [torch.zeros_like(m.h) for _ in range(world)]
+                for r in range(world):
+                    if r == rank:
+                        hs[r].copy_(m.h)
+                    broadcast_dev(hs[r], r)
+            if rank == 0:
+                eng.adam_flush(ref[0], ref[2]); eng.adam_flush(ref[1], ref[2])
+                rtol, atol = (1e-4, 1e-5) if kind == "Adam" else (1e-5, 2e-7)
+                checks = [("P", Pfull, ref[0].w), ("Q", Qfull, ref[1].w)]
+                if hs is not None:
+                    checks.append(("h", hs[0], rh))
+                    if not all(torch.equal(hs[0], x) for x in hs[1:]):
+                        print("PW h NOT REPLICATED", kind)
+                        ok = False
+                for name, got, want in checks:
+                    bad = ~torch.isclose(got, want, rtol=rtol, atol=atol)
+                    if bad.float().mean() > 1e-3:
+                        print("PW TABLE MISMATCH", score_kind, kind, name, int(bad.sum()), float((got - want).abs().max()))
+                        ok = False
+            m.close()
     # ---- evaluation across the item shards: per-shard exact top-K merged at the owner == single-GPU top-K on the gathered tables
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
     from conftest import synthetic_data
