@@ -247,25 +247,36 @@ struct InboxApplyArgs {
     OptDev opt;
 };
 
-template <int LANES, int VPL, int OPT>
+// GMAX = 2 / 4 / 8 >= n_ranks bounds the gradient registers (GMAX float4 per VPL): with two ranks the kernel keeps 8 of them instead of
+// 32 and a fourth CTA fits on the SM.  The row's weights and optimizer slots are requested TOGETHER with its stamps (every touched row
+// needs them, and so does every CRB_ADAM_TF1 row that has ever been updated), so a row costs two dependent round trips -- stamps +
+// row, then the arrived gradients -- instead of three.
+template <int LANES, int VPL, int OPT, int GMAX>
 __global__ void __launch_bounds__(256) inbox_apply_kernel(InboxApplyArgs a) {
     const int lane = threadIdx.x & 31, gl = lane % LANES;
     const uint32_t gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << (lane - gl));
     const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
     const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / LANES;
-    // whole warps leave together (a row index is per lane group; the shuffles below are group-wide)
+    // whole lane groups leave together (a row index is per lane group; the votes below are group-wide)
     for (int64_t row = group; row < a.rows; row += n_groups) {
         // lane s of the group looks at source rank s (LANES >= 8 >= n_ranks)
-        const bool mine = gl < a.n_ranks && a.stamps[(int64_t)gl * a.rows_cap + row] == a.stamp;
-        uint32_t present = __ballot_sync(gmask, mine);
-        present = LANES == 32 ? present : (present >> (lane - gl)) & ((1u << LANES) - 1u);
+        const uint32_t st = gl < a.n_ranks ? a.stamps[(int64_t)gl * a.rows_cap + row] : 0u;
         RowRegs<LANES, VPL> r;
         r.last = OptTraits<OPT>::replay ? a.Q.last[row] : 0;
+        constexpr bool EARLY = OptTraits<OPT>::replay;   // the other optimizers leave untouched rows alone: no speculative reads for them
+        if (EARLY) {
+            row_load_w<LANES, VPL>(r, a.Q, row, a.dim, gl);
+            row_load_state<LANES, VPL, OPT>(r, a.Q, row, a.dim, gl);
+        }
+        uint32_t present = __ballot_sync(gmask, gl < a.n_ranks && st == a.stamp);
+        present = LANES == 32 ? present : (present >> (lane - gl)) & ((1u << LANES) - 1u);
+        if (!EARLY && present != 0u) {
+            row_load_w<LANES, VPL>(r, a.Q, row, a.dim, gl);
+            row_load_state<LANES, VPL, OPT>(r, a.Q, row, a.dim, gl);
+        }
         if (present == 0u) {
             // nothing arrived: CRB_ADAM_TF1 rows decay (tf.train.AdamOptimizer moves every row every step); others are untouched
             if (OptTraits<OPT>::replay && r.last != 0 && r.last < a.opt.step) {
-                row_load_w<LANES, VPL>(r, a.Q, row, a.dim, gl);
-                row_load_state<LANES, VPL, OPT>(r, a.Q, row, a.dim, gl);
                 row_replay<LANES, VPL, OPT>(r, a.opt, a.opt.step + 1);
 #pragma unroll
                 for (int v = 0; v < VPL; ++v) {
@@ -279,31 +290,26 @@ __global__ void __launch_bounds__(256) inbox_apply_kernel(InboxApplyArgs a) {
             }
             continue;
         }
-        row_load_w<LANES, VPL>(r, a.Q, row, a.dim, gl);
-        row_load_state<LANES, VPL, OPT>(r, a.Q, row, a.dim, gl);
         // all arrived gradients are requested together (one round trip), then added in source-rank order
         float4 acc[VPL];
 #pragma unroll
         for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        constexpr int SB = VPL == 1 ? 8 : 4;
-        for (int s0 = 0; s0 < a.n_ranks; s0 += SB) {
-            float4 g[SB][VPL];
+        float4 g[GMAX][VPL];
 #pragma unroll
-            for (int q = 0; q < SB; ++q) {
-                const bool on = s0 + q < a.n_ranks && ((present >> (s0 + q)) & 1u);
-                const float* src = a.grad + ((int64_t)(s0 + q) * a.rows_cap + row) * a.dim;
+        for (int q = 0; q < GMAX; ++q) {
+            const bool on = (present >> q) & 1u;
+            const float* src = a.grad + ((int64_t)q * a.rows_cap + row) * a.dim;
 #pragma unroll
-                for (int v = 0; v < VPL; ++v) {
-                    const int c = (gl + LANES * v) * 4;
-                    g[q][v] = (on && c < a.dim) ? ld4(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+            for (int v = 0; v < VPL; ++v) {
+                const int c = (gl + LANES * v) * 4;
+                g[q][v] = (on && c < a.dim) ? ld4(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        }
 #pragma unroll
-            for (int q = 0; q < SB; ++q) {
-                if (!(s0 + q < a.n_ranks && ((present >> (s0 + q)) & 1u))) continue;
+        for (int q = 0; q < GMAX; ++q) {
+            if (!((present >> q) & 1u)) continue;
 #pragma unroll
-                for (int v = 0; v < VPL; ++v) { acc[v].x += g[q][v].x; acc[v].y += g[q][v].y; acc[v].z += g[q][v].z; acc[v].w += g[q][v].w; }
-            }
+            for (int v = 0; v < VPL; ++v) { acc[v].x += g[q][v].x; acc[v].y += g[q][v].y; acc[v].z += g[q][v].z; acc[v].w += g[q][v].w; }
         }
         row_replay<LANES, VPL, OPT>(r, a.opt, a.opt.step);
         row_apply_store<LANES, VPL, OPT>(r, acc, a.Q, row, a.dim, gl, a.opt);
@@ -430,7 +436,12 @@ static int launch_inbox_t(crb_handle* h, const InboxApplyArgs& a, int opt_kind, 
     if (grid < 1) grid = 1;
     int rc;
     if ((rc = crb_prof_begin(h, s, 3))) return rc;
-#define CRB_IN_CASE(O) case O: inbox_apply_kernel<LANES, VPL, O><<<(int)grid, 256, 0, s>>>(a); break;
+#define CRB_IN_CASE(O)                                                                               \
+    case O:                                                                                          \
+        if (a.n_ranks <= 2) inbox_apply_kernel<LANES, VPL, O, 2><<<(int)grid, 256, 0, s>>>(a);       \
+        else if (a.n_ranks <= 4) inbox_apply_kernel<LANES, VPL, O, 4><<<(int)grid, 256, 0, s>>>(a);  \
+        else inbox_apply_kernel<LANES, VPL, O, 8><<<(int)grid, 256, 0, s>>>(a);                      \
+        break;
     switch (opt_kind) { CRB_IN_CASE(OPT_SGD) CRB_IN_CASE(OPT_ADAGRAD) CRB_IN_CASE(OPT_ADAM_LAZY) CRB_IN_CASE(OPT_ADAM_TF1) }
 #undef CRB_IN_CASE
     h->launches++;
