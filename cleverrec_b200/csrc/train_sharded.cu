@@ -234,6 +234,188 @@ __global__ void __launch_bounds__(256, 3) shard_step_kernel(ShardStepArgs a) {
     block_loss_store(loss_acc, a.block_loss);
 }
 
+// ------------------------------------------------------------------------------------------------ phase 1b, asynchronous staging
+// The same step with the gathers taken off the registers (dim <= 128).  shard_step_kernel holds every prefetched row in registers
+// (five rows ahead of their use at 80 registers per thread) and still stalls twice per triplet on the user row's multiplicity word
+// and optimizer slots: 3.6 TB/s.  Here every warp owns a private slice of shared memory:
+//   * HEADERS of the next 16 iterations (ids, item sources, the user row's multiplicity / slot base / last step, occurrence ranks),
+//     loaded lane-per-iteration in three spaced phases (ids -> multiplicity words -> shared memory) half a block ahead, so nothing on
+//     the index side is ever waited for;
+//   * three ROW STAGES: the rows of iterations n+1 and n+2 are in flight (16-byte cp.async, global / peer memory -> shared, no
+//     registers) while iteration n computes.  A lane copies exactly the 16-byte chunks it later reads, so the only synchronisation is
+//     its own cp.async.wait_group -- no barrier, no mbarrier, no cross-warp hand-off.
+// Arithmetic, order and device functions are those of shard_step_kernel: bit-identical tables.
+#define SA_NBUF 3
+#define SA_HB 16
+#define SA_NROW 5   // p_u, q_i, q_j, s1_u, s2_u
+struct SaHdr {
+    int32_t u, i, j, sbi, sbj;   // u < 0: no triplet (tail)
+    uint32_t cnt, base;          // the user row's multiplicity word
+    int32_t last;
+    uint32_t rku, rki, rkj, pad;
+};
+static_assert(sizeof(SaHdr) == 48, "header size");
+
+__device__ __forceinline__ void sa_copy16(void* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+template <int LANES, int OPT>
+__global__ void __launch_bounds__(256, 3) shard_step_async_kernel(ShardStepArgs a) {
+    constexpr int GPW = 32 / LANES, VPL = 1;
+    extern __shared__ __align__(16) unsigned char sa_sm[];
+    const int lane = threadIdx.x & 31, gl = lane % LANES, sub = lane / LANES;
+    const uint32_t rb = (uint32_t)a.dim * 4u;
+    const size_t hdr_bytes = 2 * SA_HB * GPW * sizeof(SaHdr);
+    const size_t warp_bytes = hdr_bytes + (size_t)SA_NBUF * GPW * SA_NROW * rb;
+    unsigned char* wbase = sa_sm + (threadIdx.x >> 5) * warp_bytes;
+    SaHdr* hdr = reinterpret_cast<SaHdr*>(wbase);
+    unsigned char* rows = wbase + hdr_bytes;
+    const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_groups = (a.batch + GPW - 1) / GPW;
+    const int64_t n_it = n_groups > gwarp ? (n_groups - gwarp + n_warps - 1) / n_warps : 0;
+    const int G = a.sh.n_ranks;
+    const bool my_chunk = gl * 4 < a.dim;
+    double loss_acc = 0.0;
+
+    // ---- header pipeline: lane l < SA_HB owns iteration (block * SA_HB + l) of the block being loaded
+    int32_t hu[GPW], hi[GPW], hj[GPW], hsi[GPW], hsj[GPW], hl[GPW];
+    uint32_t hru[GPW], hri[GPW], hrj[GPW];
+    unsigned long long hm[GPW];
+    auto phase_ids = [&](int64_t blk) {
+        const int64_t m = blk * SA_HB + lane;
+#pragma unroll
+        for (int k = 0; k < GPW; ++k) {
+            const int64_t t = (gwarp + m * n_warps) * GPW + k;
+            hu[k] = -1;
+            if (lane < SA_HB && m < n_it && t < a.batch) {
+                hu[k] = a.u[t]; hi[k] = a.i[t]; hj[k] = a.j[t]; hsi[k] = a.sbi[t]; hsj[k] = a.sbj[t];
+                hru[k] = a.rk[0][t]; hri[k] = a.rk[1][t]; hrj[k] = a.rk[2][t];
+            }
+        }
+    };
+    auto phase_meta = [&]() {
+#pragma unroll
+        for (int k = 0; k < GPW; ++k) {
+            hm[k] = 0ULL; hl[k] = 0;
+            if (hu[k] >= 0) {
+                hm[k] = a.metaU[hu[k]];
+                hl[k] = OptTraits<OPT>::replay ? a.P.last[hu[k]] : 0;
+            }
+        }
+    };
+    auto phase_store = [&](int64_t blk) {
+        if (lane < SA_HB) {
+#pragma unroll
+            for (int k = 0; k < GPW; ++k) {
+                SaHdr H;
+                H.u = hu[k]; H.i = hi[k]; H.j = hj[k]; H.sbi = hsi[k]; H.sbj = hsj[k];
+                H.cnt = (uint32_t)hm[k]; H.base = (uint32_t)(hm[k] >> 32); H.last = hl[k];
+                H.rku = hru[k]; H.rki = hri[k]; H.rkj = hrj[k]; H.pad = 0u;
+                hdr[((blk & 1) * SA_HB + lane) * GPW + k] = H;
+            }
+        }
+        __syncwarp();
+    };
+    auto header = [&](int64_t m) -> const SaHdr& { return hdr[(((m / SA_HB) & 1) * SA_HB + (m % SA_HB)) * GPW + sub]; };
+    // ---- row stage m: this lane's 16-byte chunk of every row iteration m needs
+    auto issue = [&](int64_t m) {
+        if (m < n_it) {
+            const SaHdr& H = header(m);
+            if (H.u >= 0 && my_chunk) {
+                unsigned char* st = rows + ((size_t)(m % SA_NBUF) * GPW + sub) * SA_NROW * rb + (size_t)gl * 16;
+                const bool su = H.cnt == 1u || replay_pending<OPT>(H.last, a.opt);
+                sa_copy16(st, a.P.w + (int64_t)H.u * a.dim + gl * 4);
+                const float* qi = H.sbi >= 0 ? a.stage + (int64_t)H.sbi * a.dim : a.sh.q[H.i % G].w + (int64_t)(H.i / G) * a.dim;
+                const float* qj = H.sbj >= 0 ? a.stage + (int64_t)H.sbj * a.dim : a.sh.q[H.j % G].w + (int64_t)(H.j / G) * a.dim;
+                sa_copy16(st + rb, qi + gl * 4);
+                sa_copy16(st + 2 * rb, qj + gl * 4);
+                if (OptTraits<OPT>::has_s1 && su) sa_copy16(st + 3 * rb, a.P.s1 + (int64_t)H.u * a.dim + gl * 4);
+                if (OptTraits<OPT>::has_s2 && su) sa_copy16(st + 4 * rb, a.P.s2 + (int64_t)H.u * a.dim + gl * 4);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");   // one group per iteration, empty or not: the wait below counts groups
+    };
+
+    phase_ids(0); phase_meta(); phase_store(0);
+    issue(0);
+    issue(1);
+    for (int64_t it = 0; it < n_it; ++it) {
+        const int ph = (int)(it % SA_HB);
+        const int64_t blk = it / SA_HB;
+        if (ph == 0) phase_ids(blk + 1);
+        else if (ph == 5) phase_meta();
+        else if (ph == 10) phase_store(blk + 1);
+        issue(it + 2);
+        asm volatile("cp.async.wait_group 2;" ::: "memory");   // the copies of iteration `it` (issued two iterations ago) have landed
+        const SaHdr H = header(it);
+        const bool active = H.u >= 0;
+        const int32_t u = active ? H.u : 0, i = H.i, j = H.j;
+        const unsigned long long mu = ((unsigned long long)H.base << 32) | H.cnt;
+        RowRegs<LANES, VPL> ru, ri, rj;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        ru.w[0] = ri.w[0] = rj.w[0] = z4;
+        ru.last = H.last;
+        const bool su = active && (H.cnt == 1u || replay_pending<OPT>(H.last, a.opt));
+        if (active && my_chunk) {
+            const unsigned char* st = rows + ((size_t)(it % SA_NBUF) * GPW + sub) * SA_NROW * rb + (size_t)gl * 16;
+            ru.w[0] = *reinterpret_cast<const float4*>(st);
+            ri.w[0] = *reinterpret_cast<const float4*>(st + rb);
+            rj.w[0] = *reinterpret_cast<const float4*>(st + 2 * rb);
+            if (OptTraits<OPT>::has_s1 && su) ru.s1[0] = *reinterpret_cast<const float4*>(st + 3 * rb);
+            if (OptTraits<OPT>::has_s2 && su) ru.s2[0] = *reinterpret_cast<const float4*>(st + 4 * rb);
+        } else if (su) {   // padding lanes (dim not a multiple of 4 * LANES): see row_load_state
+            const float pad1 = OptTraits<OPT>::has_s2 ? 0.f : 1.f;
+            if (OptTraits<OPT>::has_s1) ru.s1[0] = make_float4(pad1, pad1, pad1, pad1);
+            if (OptTraits<OPT>::has_s2) ru.s2[0] = make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+        if (active && replay_pending<OPT>(ru.last, a.opt)) row_replay<LANES, VPL, OPT>(ru, a.opt, a.opt.step);
+        float x = 0.f, sq = 0.f;
+        {
+            const float4 p = ru.w[0], qi = ri.w[0], qj = rj.w[0];
+            const float4 dq = make_float4(qi.x - qj.x, qi.y - qj.y, qi.z - qj.z, qi.w - qj.w);
+            x += dot4(p, dq);
+            sq += dot4(p, p) + dot4(qi, qi) + dot4(qj, qj);
+        }
+        x = group_sum<LANES>(x);
+        sq = group_sum<LANES>(sq);
+        const float g = -sigmoid_f(-x);
+        if (active && gl == 0) loss_acc += (double)(softplus_neg(x) + a.reg * 0.5f * sq);
+        float4 gu[VPL], gi[VPL], gj[VPL];
+        {
+            const float4 p = ru.w[0], qi = ri.w[0], qj = rj.w[0];
+            gu[0] = make_float4(fmaf(g, qi.x - qj.x, a.reg * p.x), fmaf(g, qi.y - qj.y, a.reg * p.y), fmaf(g, qi.z - qj.z, a.reg * p.z),
+                                fmaf(g, qi.w - qj.w, a.reg * p.w));
+            gi[0] = make_float4(fmaf(g, p.x, a.reg * qi.x), fmaf(g, p.y, a.reg * qi.y), fmaf(g, p.z, a.reg * qi.z), fmaf(g, p.w, a.reg * qi.w));
+            gj[0] = make_float4(fmaf(-g, p.x, a.reg * qj.x), fmaf(-g, p.y, a.reg * qj.y), fmaf(-g, p.z, a.reg * qj.z), fmaf(-g, p.w, a.reg * qj.w));
+        }
+        if (!active) continue;
+        const uint32_t t = (uint32_t)((gwarp + it * n_warps) * GPW + sub);
+        emit_row<LANES, VPL, OPT>(ru, gu, a.P, a.metaU, u, mu, H.rku, t, 0u, a.dim, gl, a.opt, a.dup_grad, a.dup_t);
+#pragma unroll
+        for (int role = 1; role <= 2; ++role) {
+            const int32_t item = role == 1 ? i : j, sb = role == 1 ? H.sbi : H.sbj;
+            const float4* gv = role == 1 ? gi : gj;
+            if (sb < 0) {
+                shard_send<LANES, VPL>(a.sh.send, item, gv, a.dim, gl);
+                if (gl == 0) a.metaI[item] = 0ULL;
+            } else {
+                const uint32_t slot = (uint32_t)sb + (role == 1 ? H.rki : H.rkj);
+                if (my_chunk) st4(a.dup_grad + (int64_t)slot * a.dim + gl * 4, gv[0]);
+                if (gl == 0) a.dup_t[slot] = (t << 2) | (uint32_t)role;
+            }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    block_loss_store(loss_acc, a.block_loss);
+}
+
+static bool shard_async_enabled(int dim) {
+    const char* e = getenv("CRB_SHARD_ASYNC");   // 0 = register-staged shard_step_kernel (A/B), default = asynchronous staging
+    return (!e || atoi(e) != 0) && dim <= 128;
+}
+
 // ------------------------------------------------------------------------------------------------ phase 2: the owner's pass
 struct InboxApplyArgs {
     TableDev Q;           // this rank's shard
@@ -393,12 +575,26 @@ static int launch_shard_t(crb_handle* h, const ShardStepArgs& a, int opt_kind, c
     CRB_CUDA(cudaGetLastError());
     if ((rc = crb_prof_end(h, s, 1))) return rc;
     if ((rc = crb_prof_begin(h, s))) return rc;
-#define CRB_SH_CASE(O)                                                                          \
-    case O: {                                                                                   \
-        const int grid = one_wave(h, shard_step_kernel<LANES, VPL, O>, a.batch, gpb);           \
-        h->step_grid = grid;                                                                    \
-        shard_step_kernel<LANES, VPL, O><<<grid, 256, 0, s>>>(a);                               \
-        break;                                                                                  \
+    const bool use_async = VPL == 1 && shard_async_enabled(a.dim);
+    const size_t sa_smem = 8 * (2 * SA_HB * (32 / LANES) * sizeof(SaHdr) + (size_t)SA_NBUF * (32 / LANES) * SA_NROW * a.dim * 4);
+#define CRB_SH_CASE(O)                                                                                                          \
+    case O: {                                                                                                                   \
+        if (use_async) {                                                                                                        \
+            CRB_CUDA(cudaFuncSetAttribute(shard_step_async_kernel<LANES, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa_smem)); \
+            int occ = 0;                                                                                                        \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, shard_step_async_kernel<LANES, O>, 256, sa_smem) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; } \
+            int64_t grid = (int64_t)h->sm_count * occ;                                                                          \
+            const int64_t need = (a.batch + gpb - 1) / gpb;                                                                     \
+            if (grid > need) grid = need;                                                                                       \
+            if (grid > h->loss_blocks) grid = h->loss_blocks;                                                                   \
+            h->step_grid = (int)grid;                                                                                           \
+            shard_step_async_kernel<LANES, O><<<(int)grid, 256, sa_smem, s>>>(a);                                               \
+        } else {                                                                                                                \
+            const int grid = one_wave(h, shard_step_kernel<LANES, VPL, O>, a.batch, gpb);                                       \
+            h->step_grid = grid;                                                                                                \
+            shard_step_kernel<LANES, VPL, O><<<grid, 256, 0, s>>>(a);                                                           \
+        }                                                                                                                       \
+        break;                                                                                                                  \
     }
     switch (opt_kind) { CRB_SH_CASE(OPT_SGD) CRB_SH_CASE(OPT_ADAGRAD) CRB_SH_CASE(OPT_ADAM_LAZY) CRB_SH_CASE(OPT_ADAM_TF1) }
 #undef CRB_SH_CASE
