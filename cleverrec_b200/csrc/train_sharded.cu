@@ -411,9 +411,15 @@ __global__ void __launch_bounds__(256, 3) shard_step_async_kernel(ShardStepArgs 
     block_loss_store(loss_acc, a.block_loss);
 }
 
-static bool shard_async_enabled(int dim) {
-    const char* e = getenv("CRB_SHARD_ASYNC");   // 0 = register-staged shard_step_kernel (A/B), default = asynchronous staging
-    return (!e || atoi(e) != 0) && dim <= 128;
+// MEASURED (S-large, B = 2^20 per GPU, Adam tf1; whole step, ms): N=2 2.71 async vs 2.79 register-staged; N=4 2.61 vs 2.71; N=8 2.70 vs
+// 2.65 (step kernel 1.31 vs 1.22 ms: with 7/8 of the direct reads remote, two iterations of look-ahead no longer cover the NVLink
+// round trip, and a deeper ring would cost the third CTA per SM).  Hence: asynchronous staging up to four ranks.
+// CRB_SHARD_ASYNC=0 / 1 forces one or the other (A/B).
+static bool shard_async_enabled(int dim, int n_ranks) {
+    if (dim > 128) return false;
+    const char* e = getenv("CRB_SHARD_ASYNC");
+    if (e) return atoi(e) != 0;
+    return n_ranks <= 4;
 }
 
 // ------------------------------------------------------------------------------------------------ phase 2: the owner's pass
@@ -575,7 +581,7 @@ static int launch_shard_t(crb_handle* h, const ShardStepArgs& a, int opt_kind, c
     CRB_CUDA(cudaGetLastError());
     if ((rc = crb_prof_end(h, s, 1))) return rc;
     if ((rc = crb_prof_begin(h, s))) return rc;
-    const bool use_async = VPL == 1 && shard_async_enabled(a.dim);
+    const bool use_async = VPL == 1 && shard_async_enabled(a.dim, a.sh.n_ranks);
     const size_t sa_smem = 8 * (2 * SA_HB * (32 / LANES) * sizeof(SaHdr) + (size_t)SA_NBUF * (32 / LANES) * SA_NROW * a.dim * 4);
 #define CRB_SH_CASE(O)                                                                                                          \
     case O: {                                                                                                                   \
