@@ -24,7 +24,7 @@ EXPORTS = [
     "crb_train_step_neumf", "crb_score_pairs_neumf", "crb_mask_seen",
     "crb_sample_nais", "crb_train_step_nais", "crb_train_epoch_nais", "crb_score_nais",
     "crb_shard_step_compute", "crb_shard_step_compute_pointwise", "crb_shard_apply_dense", "crb_shard_step_prepare", "crb_shard_apply_inbox", "crb_shard_barrier", "crb_shard_check", "crb_sampler_errors", "crb_malloc", "crb_free", "crb_ipc_export",
-    "crb_ipc_open", "crb_ipc_close", "crb_build_history", "crb_prep_filter_reindex", "crb_prep_split_loo", "crb_prep_eval_negatives", "crb_set_item_lists", "crb_train_step_transcf", "crb_transcf_neighbourhood", "crb_score_pairs_transcf", "crb_np_seed", "crb_np_set_state", "crb_np_get_state", "crb_sample_epoch_numpy",
+    "crb_ipc_open", "crb_ipc_close", "crb_build_history", "crb_prep_filter_reindex", "crb_prep_split_loo", "crb_prep_eval_negatives", "crb_set_item_lists", "crb_train_step_transcf", "crb_transcf_neighbourhood", "crb_score_pairs_transcf", "crb_np_seed", "crb_np_set_state", "crb_np_get_state", "crb_sample_epoch_numpy", "crb_sample_epoch_numpy_sbpr",
     "crb_train_step_lrml", "crb_score_pairs_lrml", "crb_set_social", "crb_sample_sbpr", "crb_train_step_sbpr", "crb_train_epoch_bpr_feeds", "crb_train_epoch_pointwise",
 ]
 
@@ -142,6 +142,7 @@ def load():
     lib.crb_np_set_state.argtypes = [vp, vp, i32]
     lib.crb_np_get_state.argtypes = [vp, vp, C.POINTER(i32)]
     lib.crb_sample_epoch_numpy.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+    lib.crb_sample_epoch_numpy_sbpr.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     _lib = lib
     return lib
 

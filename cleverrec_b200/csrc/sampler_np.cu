@@ -481,3 +481,186 @@ extern "C" int crb_sample_epoch_numpy(crb_handle* h, int32_t kind, int32_t neg_r
     CRB_CUDA(cudaGetLastError());
     return CRB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ SBPR (utils/sampler.py:102-141)
+// ranking_sampler_sbpr draws, per (positive, k < neg_ratio) SLOT: s = np.random.randint(len(SPu[u])) -- masked rejection over
+// [0, len), and NO raw value at all when len == 1 (NumPy's legacy randint returns `low` for a one-value range without touching the
+// stream) -- then neg = np.random.randint(item_nums) until neg is outside the user's own and social items (no distinctness between
+// slots); finally one np.random.permutation over all slots.  The accepted draws form one sequence; the q-th of them belongs to the
+// slot found by a binary search over prefix[] (accepted draws before each slot: 2 per slot, 1 where len(SPu) == 1) and is the social
+// draw iff it is the first of a two-draw slot.  The same fixpoint-per-window scheme as np_negatives_kernel then applies.
+struct NpSbprArgs {
+    const uint32_t* raw;
+    int64_t n_raw;
+    const int64_t* prefix;       // [n_slots + 1]
+    int64_t n_slots;
+    int32_t R;
+    const int32_t* sp_pos_user;
+    const int64_t* spu_start;
+    const int64_t* excl_rowptr;
+    const int32_t* excl_cols;
+    int32_t n_items;
+    uint32_t item_mask;
+    int32_t* s_out;              // [n_slots] index into SPu[u] (pre-zeroed: the value of the one-item lists)
+    int32_t* neg_out;            // [n_slots]
+    int64_t* result;             // [0] raws consumed, [1] accepted draws produced
+};
+
+__global__ void __launch_bounds__(256) np_sbpr_count_kernel(const int32_t* __restrict__ sp_pos_user, const int64_t* __restrict__ spu_start, int64_t n_slots,
+                                                            int R, int64_t* __restrict__ cons) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_slots; k += stride) {
+        const int32_t u = sp_pos_user[k / R];
+        cons[k] = (spu_start[u + 1] - spu_start[u]) > 1 ? 2 : 1;
+    }
+}
+
+__global__ void __launch_bounds__(NP_W) np_sbpr_draws_kernel(NpSbprArgs a) {
+    typedef cub::BlockScan<int, NP_W> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    __shared__ int s_changed, s_last;
+    const int t = threadIdx.x;
+    const int64_t total_draws = a.prefix[a.n_slots];
+    int64_t k = 0, q = 0;
+    while (q < total_draws && k < a.n_raw) {
+        const int W = (int)((a.n_raw - k) < NP_W ? (a.n_raw - k) : NP_W);
+        const uint32_t r = t < W ? a.raw[k + t] : 0u;
+        int a_t = t, total = W;
+        bool ok = t < W;
+        int64_t slot = 0;
+        int32_t val = 0;
+        bool social = false;
+        for (int iter = 0; iter < 4 * NP_W; ++iter) {
+            if (t == 0) s_changed = 0;
+            __syncthreads();
+            bool nok = false;
+            const int64_t Q = q + a_t;
+            if (t < W && Q < total_draws) {
+                int64_t lo = 0, hi = a.n_slots;      // last slot with prefix[slot] <= Q
+                while (hi - lo > 1) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (a.prefix[mid] <= Q) lo = mid; else hi = mid;
+                }
+                slot = lo;
+                const int32_t u = a.sp_pos_user[slot / a.R];
+                const int64_t L = a.spu_start[u + 1] - a.spu_start[u];
+                social = L > 1 && Q == a.prefix[slot];
+                if (social) {
+                    const uint32_t m = r & mask_of((uint32_t)(L - 1));
+                    nok = (int64_t)m <= L - 1;
+                    val = (int32_t)m;
+                } else {
+                    const int32_t c = (int32_t)(r & a.item_mask);
+                    nok = c < a.n_items && !np_seen(a.excl_cols, a.excl_rowptr[u], a.excl_rowptr[u + 1], c);
+                    val = c;
+                }
+            }
+            int na, ntotal;
+            Scan(tmp).ExclusiveSum(nok ? 1 : 0, na, ntotal);
+            if (nok != ok || (nok && na != a_t)) s_changed = 1;
+            ok = nok; a_t = na; total = ntotal;
+            __syncthreads();
+            if (!s_changed) break;
+        }
+        if (ok) { if (social) a.s_out[slot] = val; else a.neg_out[slot] = val; }
+        if (t == 0) s_last = -1;
+        __syncthreads();
+        const bool finishing = q + total >= total_draws;
+        if (finishing && ok && q + a_t == total_draws - 1) s_last = t;
+        __syncthreads();
+        if (finishing) { k += s_last + 1; q = total_draws; break; }
+        k += W;
+        q += total;
+    }
+    if (t == 0) { a.result[0] = k; a.result[1] = q; }
+}
+
+__global__ void __launch_bounds__(256) np_layout_sbpr_kernel(const int32_t* perm, int64_t N, int R, const int32_t* sp_pos_user, const int32_t* sp_pos_item,
+                                                             const int64_t* spu_start, const int32_t* spu_items, const float* spu_suk,
+                                                             const int32_t* s_out, const int32_t* neg_out, int32_t* u, int32_t* i, int32_t* k_out,
+                                                             int32_t* j, float* suk) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += stride) {
+        const int64_t slot = perm[k];
+        const int64_t p = slot / R;
+        const int32_t uu = sp_pos_user[p];
+        const int64_t e = spu_start[uu] + s_out[slot];
+        u[k] = uu; i[k] = sp_pos_item[p]; k_out[k] = spu_items[e]; j[k] = neg_out[slot];
+        if (suk) suk[k] = spu_suk[e];
+    }
+}
+
+// One epoch exactly as ranking_sampler_sbpr returns it under the current NumPy stream (crb_np_seed / crb_np_set_state; structures of
+// crb_set_social): u, i, i_s, i_neg int32 [sp_n_pos * neg_ratio], suk float (or NULL for is_suk=False).  DEVICE outputs.
+extern "C" int crb_sample_epoch_numpy_sbpr(crb_handle* h, int32_t neg_ratio, int32_t* u, int32_t* i, int32_t* k_out, int32_t* j, float* suk,
+                                           void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    CRB_CHECK_ARG(h && u && i && k_out && j, "null argument");
+    CRB_CHECK_ARG(neg_ratio >= 1 && neg_ratio <= 64, "neg_ratio must be in [1,64]");
+    CRB_CUDA(cudaSetDevice(h->device));
+    int rc = np_require(h);
+    if (rc) return rc;
+    if (!h->np_seeded) { crb_set_error("numpy stream not seeded (crb_np_seed / crb_np_set_state)"); return CRB_ERR_STATE; }
+    if (!h->sp_pos_user) { crb_set_error("SBPR sampler called before crb_set_social"); return CRB_ERR_STATE; }
+    if (!h->np_result) CRB_CUDA(cudaMalloc(&h->np_result, 2 * sizeof(int64_t)));
+    const int64_t N = h->sp_n_pos * neg_ratio;
+    if (N == 0) return CRB_OK;
+    // scratch: prefix (+1) | s_out | neg_out | perm | jd | keys | keys_sorted
+    auto al = [](int64_t b) { return ((b + 255) / 256) * 256; };
+    const int64_t b_pre = al((N + 1) * 8), b_i32 = al(N * 4), b_keys = al(N * 8);
+    if ((rc = np_scratch(h, 2 * b_pre + 4 * b_i32 + 2 * b_keys + 1024))) return rc;
+    char* base = (char*)h->np_scratch;
+    int64_t* cons = (int64_t*)base;
+    int64_t* prefix = (int64_t*)(base + b_pre);
+    int32_t* s_out = (int32_t*)(base + 2 * b_pre);
+    int32_t* neg_out = (int32_t*)(base + 2 * b_pre + b_i32);
+    int32_t* perm = (int32_t*)(base + 2 * b_pre + 2 * b_i32);
+    uint32_t* jd = (uint32_t*)(base + 2 * b_pre + 3 * b_i32);
+    unsigned long long* keys = (unsigned long long*)(base + 2 * b_pre + 4 * b_i32);
+    unsigned long long* keys_sorted = (unsigned long long*)(base + 2 * b_pre + 4 * b_i32 + b_keys);
+    const int grid = h->sm_count * 8;
+    np_sbpr_count_kernel<<<grid, 256, 0, s>>>(h->sp_pos_user, h->spu_start, N, neg_ratio, cons);
+    CRB_CUDA(cudaMemsetAsync(cons + N, 0, sizeof(int64_t), s));
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cons, prefix, (int)(N + 1), s);
+    if ((int64_t)tmp_bytes > h->np_sort_cap) {
+        CRB_CUDA(cudaStreamSynchronize(s));
+        cudaFree(h->np_sort_tmp);
+        h->np_sort_tmp = nullptr; h->np_sort_cap = 0;
+        CRB_CUDA(cudaMalloc(&h->np_sort_tmp, tmp_bytes));
+        h->np_sort_cap = (int64_t)tmp_bytes;
+    }
+    CRB_CUDA(cub::DeviceScan::ExclusiveSum(h->np_sort_tmp, tmp_bytes, cons, prefix, (int)(N + 1), s));
+    CRB_CUDA(cudaMemsetAsync(s_out, 0, sizeof(int32_t) * N, s));
+    h->launches += 2;
+    uint32_t mask = (uint32_t)(h->n_items - 1);
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    int64_t n_raw = 3 * N + 65536;
+    bool done = false;
+    for (int attempt = 0; attempt < 8 && !done; ++attempt) {
+        uint32_t* raw = nullptr;
+        if ((rc = np_generate(h, n_raw, &raw, s))) return rc;
+        NpSbprArgs a = {raw, n_raw, prefix, N, neg_ratio, h->sp_pos_user, h->spu_start, h->excl_rowptr, h->excl_cols, (int32_t)h->n_items, mask, s_out, neg_out,
+                        h->np_result};
+        np_sbpr_draws_kernel<<<1, NP_W, 0, s>>>(a);
+        h->launches++;
+        CRB_CUDA(cudaGetLastError());
+        int64_t res[2], want = 0;
+        CRB_CUDA(cudaMemcpyAsync(res, h->np_result, sizeof(res), cudaMemcpyDeviceToHost, s));
+        CRB_CUDA(cudaMemcpyAsync(&want, prefix + N, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        CRB_CUDA(cudaStreamSynchronize(s));
+        if (res[1] == want) {
+            if ((rc = np_advance(h, res[0], s))) return rc;
+            done = true;
+        } else {
+            n_raw *= 2;
+        }
+    }
+    if (!done) { crb_set_error("numpy-stream SBPR sampler: rejection rate too high"); return CRB_ERR_SAMPLER; }
+    if ((rc = np_permutation(h, N, perm, jd, keys, keys_sorted, s))) return rc;
+    np_layout_sbpr_kernel<<<grid, 256, 0, s>>>(perm, N, neg_ratio, h->sp_pos_user, h->sp_pos_item, h->spu_start, h->spu_items, h->spu_suk, s_out, neg_out, u, i, k_out,
+                                               j, suk);
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    return CRB_OK;
+}

@@ -361,6 +361,14 @@ class Engine(object):
         check(self.lib.crb_sample_sbpr(self.h, seed, epoch, first, count, neg_ratio, ptr(u), ptr(i), ptr(k), ptr(j), ptr(suk), self.stream))
         return (u, i, k, j, suk) if is_suk else (u, i, k, j)
 
+    def sample_epoch_numpy_sbpr(self, neg_ratio, is_suk=True):
+        """One epoch exactly as ranking_sampler_sbpr returns it under the device copy of NumPy's stream (np_seed / np_set_state)."""
+        n = self.epoch_rows(neg_ratio, "sbpr")
+        u, i, k, j = (torch.empty(n, dtype=torch.int32, device=self.device) for _ in range(4))
+        suk = torch.empty(n, dtype=torch.float32, device=self.device) if is_suk else None
+        check(self.lib.crb_sample_epoch_numpy_sbpr(self.h, neg_ratio, ptr(u), ptr(i), ptr(k), ptr(j), ptr(suk), self.stream))
+        return (u, i, k, j, suk) if is_suk else (u, i, k, j)
+
     def train_step_sbpr(self, P, Q, B, opt, u, i, k, j, suk, reg, loss_out=None):
         """One `sess.run([train, loss], {u_idx, i_idx, i_s_idx, i_neg_idx, suk})` of SBPR (SBPR.py:51-57)."""
         u, i, k, j = (self._feed_i32(x) for x in (u, i, k, j))

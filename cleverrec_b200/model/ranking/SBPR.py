@@ -18,8 +18,6 @@ class SBPR(_rr.RankingRecommender):
         logger.info(' model_params: embed_size=%d, reg=%s' % (self.embed_size, self.reg) + ', ' + self.model_params)
         if self.loss_func != 'bpr':
             raise ValueError('SBPR is defined with loss_func=bpr (conf/SBPR.properties), got %r' % self.loss_func)
-        if self.sampler_mode == 'numpy_stream':
-            raise NotImplementedError('sampler=numpy_stream replays the pairwise / pointwise / CML samplers; SBPR trains with sampler=philox')
         # Get SPu (SBPR.py:16) and hand the sampler's view of the social data to the device
         self.SPu = get_SPu(data)
         if not self.SPu:
@@ -58,6 +56,21 @@ class SBPR(_rr.RankingRecommender):
     # For SBPR (RankingRecommender.py:103-117).  is_suk=False would leave the `suk` placeholder unfed in the reference (the graph
     # always divides by it, SBPR.py:54) and fail; it is kept as "coefficient 1".
     def train_model_sbpr(self, is_suk=True):
+        if self.sampler_mode == 'numpy_stream':
+            # the epoch ranking_sampler_sbpr (utils/sampler.py:102-141) returns under NumPy's CURRENT global stream, bit for bit
+            eng = self.engine
+            eng.np_set_state()
+            feeds = eng.sample_epoch_numpy_sbpr(self.neg_ratio, is_suk=is_suk)
+            np.random.set_state(eng.np_get_state())
+            n_rows = feeds[0].numel()
+            n_batches = math.ceil(n_rows / self.batch_size)
+            losses = torch.zeros(n_batches, dtype=torch.float64, device=eng.device)
+            for b in range(n_batches):
+                sl = slice(b * self.batch_size, min((b + 1) * self.batch_size, n_rows))
+                suk = feeds[4][sl] if is_suk else torch.ones(sl.stop - sl.start, dtype=torch.float32, device=eng.device)
+                self.train_step(feeds[0][sl], feeds[1][sl], feeds[2][sl], feeds[3][sl], suk, loss_out=losses[b:b + 1])
+            self.epoch += 1
+            return float(losses.sum().item()) / n_batches
         n_rows = self.engine.epoch_rows(self.neg_ratio, 'sbpr')
         n_batches = math.ceil(n_rows / self.batch_size)
         losses = torch.zeros(n_batches, dtype=torch.float64, device=self.engine.device)

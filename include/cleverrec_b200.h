@@ -184,6 +184,11 @@ int crb_np_get_state(crb_handle* h, uint32_t* key624, int32_t* pos);
  * DEVICE outputs.  The call synchronises (the number of random values consumed is data dependent). */
 int crb_sample_epoch_numpy(crb_handle* h, int32_t kind, int32_t neg_ratio, int32_t* u, int32_t* i, void* third, int32_t* nbr,
                            void* stream);
+/* The same for ranking_sampler_sbpr (utils/sampler.py:102-141; structures of crb_set_social): the social-item draw
+ * np.random.randint(len(SPu[u])) -- which consumes NO value when the list has one item -- the rejection-sampled negative and the final
+ * permutation, bit for bit.  u, i, i_s, i_neg int32 [sp_n_pos * neg_ratio], suk float or NULL; DEVICE outputs. */
+int crb_sample_epoch_numpy_sbpr(crb_handle* h, int32_t neg_ratio, int32_t* u, int32_t* i, int32_t* i_s, int32_t* i_neg, float* suk,
+                                void* stream);
 
 /* number of rows in one epoch of each sampler (utils/sampler.py:65 `train_nums`) */
 int64_t crb_epoch_rows(crb_handle* h, int32_t neg_ratio, int32_t sampler_kind /*0 pairwise,1 pointwise,2 cml,3 sbpr*/);

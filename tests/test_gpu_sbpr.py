@@ -159,3 +159,37 @@ def test_sbpr_without_social_data_is_an_error():
     d.user_friends = {}
     with pytest.raises(ValueError):
         SBPR(None, d, dict(CFG), logging.getLogger('test'))
+
+
+def test_sbpr_numpy_stream_is_the_reference_sampler_bit_for_bit(eng):
+    """sampler=numpy_stream for SBPR: the device replays np.random's MT19937 stream through ranking_sampler_sbpr's draws (the
+    social-item randint -- which consumes nothing for a one-item list --, the rejection-sampled negative, the final permutation).
+    Golden: the GENUINE reference function on Ciao under np.random.seed(3) (oracle/make_golden.py section F), and the stream
+    position afterwards equals NumPy's own."""
+    d, SPu = _ciao()
+    z = np.load(os.path.join(GOLDEN, "sbpr_ciao.npz"))
+    eng.set_history(d.ui_train, d.user_nums, d.item_nums)
+    eng.set_social(d.ui_train, d.user_friends, SPu, d.user_nums)
+    eng.np_seed(3)
+    u, i, k, j, suk = (t.cpu().numpy() for t in eng.sample_epoch_numpy_sbpr(2))
+    for got, key in ((u, "sb_u"), (i, "sb_i"), (k, "sb_k"), (j, "sb_j"), (suk, "sb_suk")):
+        assert np.array_equal(got.astype(np.int64), z[key].astype(np.int64)), key
+    # the stream left behind is NumPy's after the same calls
+    np.random.seed(3)
+    H.ranking_sampler_sbpr(d, SPu, 2, 4096)
+    want = np.random.get_state()
+    got = eng.np_get_state()
+    assert got[2] == want[2] and np.array_equal(got[1], want[1])
+    # a hand-made case with ONE-item social lists (np.random.randint(1) consumes no random value) next to longer ones
+    d2 = Data(6, 14, {0: [0, 1, 2], 1: [0, 1, 2, 3], 2: [4, 5], 3: [4, 5, 6, 7, 8], 4: [9], 5: [0, 9, 10, 11, 12, 13]}, {})
+    d2.user_friends = {0: [1], 1: [0, 3], 2: [3, 5], 3: [2], 4: [5, 0], 5: [4]}
+    SPu2 = H.get_SPu(d2)
+    assert sorted(len(v) for v in SPu2.values())[0] == 1 and max(len(v) for v in SPu2.values()) > 2
+    eng.set_history(d2.ui_train, d2.user_nums, d2.item_nums)
+    eng.set_social(d2.ui_train, d2.user_friends, SPu2, d2.user_nums)
+    np.random.seed(11)
+    want = H.ranking_sampler_sbpr(d2, SPu2, 3, 512)
+    eng.np_seed(11)
+    got = eng.sample_epoch_numpy_sbpr(3)
+    for g, w in zip(got, want[1:]):
+        assert np.array_equal(g.cpu().numpy().astype(np.int64), np.asarray(w).astype(np.int64))
