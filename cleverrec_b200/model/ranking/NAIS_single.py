@@ -83,8 +83,22 @@ class NAIS_single(_rr.RankingRecommender):
     # Form mini-batch by user (RankingRecommender.py:64-87): one optimizer step per user, in data.ui_train order
     def train_model_nais(self):
         if self.sampler_mode == 'numpy_stream':
-            raise NotImplementedError("sampler=numpy_stream is not wired into NAIS_single's fused per-user epoch (crb_train_epoch_nais draws "
-                                      "its negatives from the Philox sampler); use sampler=philox")
+            # the negatives RankingRecommender.py:73-80 draws under NumPy's CURRENT global stream (per positive: neg_ratio distinct unseen
+            # items, users and items in data.ui_train order, no permutation), bit for bit; then one step per user as in the reference
+            eng, R = self.engine, self.neg_ratio
+            eng.np_set_state()
+            negs = eng.sample_epoch_numpy('negatives', R)                      # [n_pos, R]
+            np.random.set_state(eng.np_get_state())
+            pos_item = eng._hist[1]
+            targets_all = torch.cat([pos_item.reshape(-1, 1), negs], dim=1)    # per positive: the item, then its negatives (:70-80)
+            y_row = torch.zeros(1 + R, dtype=torch.float32, device=eng.device)
+            y_row[0] = 1.0
+            losses = torch.zeros(len(self._train_users), dtype=torch.float64, device=eng.device)
+            for k in range(len(self._train_users)):
+                a, n = int(self._list_start[k]), int(self._list_len[k])
+                self.train_step(pos_item[a:a + n], targets_all[a:a + n].reshape(-1), y_row.repeat(n), loss_out=losses[k:k + 1])
+            self.epoch += 1
+            return float(losses.sum().item()) / len(self._train_users)
         losses = torch.zeros(len(self._train_users), dtype=torch.float64, device=self.engine.device)
         self.engine.train_epoch_nais(self.P, self.Q, self.B, self.dense, self.dense_s1, self.dense_s2, self.atten_size, self.optimizer, self.seed,
                                      self.epoch, self._list_start, self._list_len, self.neg_ratio, self.beta, self.reg, losses, concat=self.concat)

@@ -119,3 +119,50 @@ def test_nais_model_evaluation_equals_the_reference_loops():
     oHR, oMRR, oNDCG = H.eval_rs(m2.test_users, data2.ui_train, data2.ui_test, rows, m2.topk)
     for k in range(len(m2.topk)):
         assert HR[k] == oHR[k] and NDCG[k] == oNDCG[k]
+
+
+def test_nais_numpy_stream_feeds_are_the_reference_loop_bit_for_bit():
+    """sampler=numpy_stream for NAIS_single: the per-user feeds (history, targets = every positive followed by its neg_ratio negatives,
+    labels) equal those the reference's train_model_nais loop (RankingRecommender.py:64-87) builds under the same np.random.seed --
+    re-executed here literally -- and NumPy's global stream ends where the reference leaves it."""
+    import logging
+    from conftest import synthetic_data
+    from cleverrec_b200.model.ranking.NAIS_single import NAIS_single
+    cfg = {'model_type': 'ranking', 'saved_dir': './saved_model', 'data.split_way': 'loo', 'test.neg_samples': '49', 'test.batch_size': '64',
+           'test.interval': '1', 'topk': '[5,10]', 'epoches': '1', 'batch_size': '512', 'lr': '0.01', 'neg_ratio': '3', 'optimizer': 'Adagrad',
+           'init_method': 'xavier_uniform', 'stddev': '0.05', 'seed': '3', 'recommender': 'NAIS_single', 'embed_size': '32', 'atten_size': '16',
+           'atten_type': "'prod'", 'beta': '0.5', 'reg': '1e-3', 'nais_like': 'True', 'is_pairwise': 'False', 'loss_func': 'cross_entropy',
+           'sampler': 'numpy_stream'}
+    data = synthetic_data(40, 90, 8, seed=2)
+    m = NAIS_single(None, data, cfg, logging.getLogger('test'))
+    m.build_model()
+    fed = []
+    real_step = m.train_step
+
+    def spy(u_idx, i_idx, y, loss_out=None):
+        fed.append((u_idx.cpu().numpy().tolist(), i_idx.cpu().numpy().tolist(), y.cpu().numpy().tolist()))
+        return real_step(u_idx, i_idx, y, loss_out=loss_out)
+    m.train_step = spy
+    np.random.seed(21)
+    loss = m.train_model()
+    after = np.random.get_state()
+    assert np.isfinite(loss)
+    # the reference loop, literally
+    np.random.seed(21)
+    want = []
+    for u, items in data.ui_train.items():
+        i_idx, y = [], []
+        seen_items = set(data.ui_train[u])
+        for i in items:
+            i_idx.append(i); y.append(1.0)
+            random_j = set()
+            for s in range(3):
+                j = np.random.randint(data.item_nums)
+                while j in random_j or j in seen_items:
+                    j = np.random.randint(data.item_nums)
+                random_j.add(j)
+                i_idx.append(j); y.append(0.0)
+        want.append((list(items), i_idx, y))
+    assert fed == want
+    ref_state = np.random.get_state()
+    assert after[2] == ref_state[2] and np.array_equal(after[1], ref_state[1])
