@@ -79,3 +79,31 @@ def test_negative_distribution_matches_reference_sampler():
     sigma = np.sqrt((1 / len(unseen)) * (1 - 1 / len(unseen)) / n)
     assert np.abs(pt - 1 / len(unseen)).max() < 5 * sigma
     assert np.abs(pr - 1 / len(unseen)).max() < 5 * sigma
+
+
+def test_eval_negative_twin_draws_distinct_unseen_items_uniformly():
+    """oracle/philox.py::sample_eval_negatives (the twin of crb_prep_eval_negatives) has the law of the reference's
+    np.random.choice(list(item_set - seen), size, replace=False) (RankingPreprocess.py:120-129): distinct, unseen, in range, a pure
+    function of (seed, user, history), and every unseen item equally likely (chi-square over many seeds)."""
+    rs = np.random.RandomState(0)
+    I, U = 61, 5
+    ui = {u: rs.choice(I, size=int(rs.randint(3, 30)), replace=False).tolist() for u in range(U)}
+    _, _, rp, sc = X.build_history(ui, U)
+    users = np.arange(U, dtype=np.int32)
+    a = X.sample_eval_negatives(7, users, 10, I, rp, sc)
+    assert np.array_equal(a, X.sample_eval_negatives(7, users, 10, I, rp, sc))
+    assert not np.array_equal(a, X.sample_eval_negatives(8, users, 10, I, rp, sc))
+    counts = np.zeros((U, I))
+    n_seeds = 400
+    for seed in range(n_seeds):
+        out = X.sample_eval_negatives(seed, users, 10, I, rp, sc)
+        for u in range(U):
+            row = out[u].tolist()
+            assert len(set(row)) == 10 and not set(row) & set(ui[u]) and min(row) >= 0 and max(row) < I
+            counts[u, row] += 1
+    for u in range(U):
+        unseen = np.setdiff1d(np.arange(I), ui[u])
+        expected = n_seeds * 10 / unseen.size
+        chi2 = float(((counts[u, unseen] - expected) ** 2 / expected).sum())
+        assert chi2 < 2.2 * unseen.size, (u, chi2, unseen.size)     # far above the 99.9 % quantile would mean a biased sampler
+        assert counts[u, ui[u]].sum() == 0
