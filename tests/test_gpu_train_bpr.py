@@ -1,5 +1,7 @@
 """-m gpu: the fused BPR step (csrc/train.cu) against the torch restatement of model/ranking/BPR.py:31-44 with
-TF-1 optimizer semantics.  Tolerance: 1e-5 relative (north_star allows 1e-4) on loss and every table entry."""
+TF-1 optimizer semantics.  Tolerance: 2e-5 relative (north_star allows 1e-4) on every table entry, 1e-5 on the loss.  (The device
+result is bit-identical from run to run; the torch-CPU restatement's own fp32 round-off moves with the host's vector width and
+thread count -- scripts/smoke_stress.py measured the worst entry at 0.77 of a 1e-5 tolerance on one box.)"""
 import numpy as np
 import pytest
 import torch
@@ -9,7 +11,7 @@ from oracle import philox as X
 from oracle import tf1_restatement as T
 
 pytestmark = pytest.mark.gpu
-RTOL, ATOL = 1e-5, 2e-7
+RTOL, ATOL = 2e-5, 4e-7
 
 
 @pytest.fixture(scope="module")
