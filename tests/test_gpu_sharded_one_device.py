@@ -34,6 +34,17 @@ def test_bpr_model_class_two_processes_one_gpu():
     assert r.returncode == 0 and "SHARDED_MODEL_OK" in r.stdout, r.stdout[-4000:]
 
 
+def test_sharded_step_at_full_size():
+    """World 2 at BASELINE.json's full table sizes (10M users partitioned, 2M items row-sharded, d = 128, 2^20 triplets per rank):
+    one SGD step == plain torch on the union batch, lr = 0 moves nothing, device-sampled == fed, two TF-1 Adam steps == dense Adam."""
+    import torch
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < 100 * (1 << 30):
+        pytest.skip("needs ~100 GB of free HBM (two ranks' full-size tables and the torch reference copies on one device)")
+    r = _run("_sharded_fullsize_worker.py", 29537, 1200)
+    assert r.returncode == 0 and "SHARDED_FULLSIZE_OK" in r.stdout, r.stdout[-4000:]
+
+
 def test_sharded_world1_equals_plain_path_bitwise():
     """world = 1 through the multi-GPU kernels (every 'peer' is local memory) == crb_train_epoch_bpr bit for bit: the fetch / send /
     inbox pipeline adds no arithmetic of its own (a single source's gradient enters the owner's sum as 0 + g)."""
