@@ -129,6 +129,7 @@ struct crb_handle {
     // bf16 copy of the item table kept in the evaluation workspace between crb_score_topk calls (score_tc.cu): valid for exactly
     // these arguments until a library call writes a table (crb_opt_to_dev clears it) or reuses the workspace
     int evq_valid;
+    int tc_robust;      // score_topk_tc: the last call on this item table re-ran > 1/64 of its users exactly -> widest compaction margin
     const void* evq_q;
     const void* evq_hvec;
     int64_t evq_items;

@@ -19,7 +19,6 @@
 
 #define TC_C 256          // candidate slots per (user, split, column half)
 #define TC_EPL (TC_C / 32) // list entries per lane in a compaction
-#define TC_KEEP 64        // kept by a compaction
 #define TC_BM 256         // users per CTA (2 x UMMA_M=128)
 #define TC_BN 128         // items per tile
 #ifndef TC_CH
@@ -189,6 +188,8 @@ struct TcArgs {
     unsigned long long* cand;   // [n_splits, n_users_pad, TC_C]  (approx score bits << 32 | item)
     int32_t* cand_cnt;          // [n_splits, n_users_pad]
     float* cand_thr;            // [n_splits, n_users_pad]
+    int keep_lo, keep_hi;       // a compaction keeps between keep_lo and keep_hi entries (keep_lo >= K)
+    int trig;                   // a list longer than this is compacted after the tile (keep_hi < trig <= TC_C - 64)
     int debug;                  // experiments only (-DTC_DEBUG_SWITCHES, CRB_TC_DEBUG): 1 = read TMEM but skip the scan, 2 = skip the TMEM read too, 3 = scan only
 };
 
@@ -198,10 +199,13 @@ __device__ __forceinline__ uint32_t ord_bits(uint32_t f) { return (f & 0x8000000
 // certificate as long as every dropped entry has score <= T; the list only needs to shrink enough to make room.  So instead of
 // an exact selection (a 32-step radix descent was the straggler that stalled the 2-deep accumulator pipeline) T is found by
 // bisection on the order-preserving score bits between the list's min and max, stopping as soon as the number of kept entries
-// (score > T) lies in [TC_KEEP_MIN, TC_KEEP]: typically 4-6 warp reductions.  Kept entries are packed to the front.
+// (score > T) lies in [keep_lo, keep_hi]: typically 4-6 warp reductions.  Kept entries are packed to the front.
 // Returns T as a float; *kept receives the new count.
-#define TC_KEEP_MIN 32
-__device__ __forceinline__ float compact_list(unsigned long long* list, int n, int lane, int* kept) {
+// The threshold only moves at a compaction, and until the next one the list takes every score above it: the tighter the kept range
+// and the earlier the next compaction, the fewer scores pass the threshold test at all -- and a chunk in which ANY of a warp's 32
+// users has a passing score leaves the branch-free path for the whole warp.  Measured (4096 users x 2M items, one item split): with
+// keep in [32, 64] and a compaction at 192 entries the candidate path cost 3.8 of 16.2 ms; see score_topk_tc for the choice now.
+__device__ __forceinline__ float compact_list(unsigned long long* list, int n, int lane, int* kept, int keep_lo, int keep_hi) {
     unsigned long long e[TC_EPL];
     uint32_t o[TC_EPL];
     uint32_t lo = 0xFFFFFFFFu, hi = 0u;
@@ -214,7 +218,7 @@ __device__ __forceinline__ float compact_list(unsigned long long* list, int n, i
     }
     lo = __reduce_min_sync(0xffffffffu, lo);
     hi = __reduce_max_sync(0xffffffffu, hi);
-    // invariants: count(o > hi) <= TC_KEEP (0 at the start);  count(o > lo - 1) would be n (too many)
+    // invariants: count(o > hi) <= keep_hi (0 at the start);  count(o > lo - 1) would be n (too many)
     uint32_t T = hi;
     while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
@@ -222,8 +226,8 @@ __device__ __forceinline__ float compact_list(unsigned long long* list, int n, i
 #pragma unroll
         for (int t = 0; t < TC_EPL; ++t) c += (o[t] > mid);
         const int tot = __reduce_add_sync(0xffffffffu, c);
-        if (tot > TC_KEEP) { lo = mid + 1; T = hi; }
-        else { hi = mid; T = mid; if (tot >= TC_KEEP_MIN) break; }
+        if (tot > keep_hi) { lo = mid + 1; T = hi; }
+        else { hi = mid; T = mid; if (tot >= keep_lo) break; }
     }
     __syncwarp();
     int base = 0;
@@ -452,14 +456,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 // Compaction is OFF the accumulator hand-off: the TMEM stage has just been released, so the ~1500 cycles a
                 // compaction takes (list round trip through L2 + bisection) overlap the next tiles' MMAs instead of stalling them.
                 // A list is compacted as soon as the next tile could overflow it (worst case 32 appends per chunk).
-                unsigned need = __ballot_sync(0xffffffffu, cnt > TC_C - 32 * (TC_BN / 32 / TC_CH));
+                unsigned need = __ballot_sync(0xffffffffu, cnt > a.trig);
                 while (need) {
                     const int src = __ffs(need) - 1;
                     need &= need - 1;
                     const int n = __shfl_sync(0xffffffffu, cnt, src);
                     unsigned long long* lst = a.cand + (lslot + (mt * TC_BM + half * 128 + quad * 32 + src)) * TC_C;
                     int kept;
-                    const float thr = compact_list(lst, n, lane, &kept);
+                    const float thr = compact_list(lst, n, lane, &kept, a.keep_lo, a.keep_hi);
                     if (lane == src) { theta = fmaxf(theta, thr); cnt = kept; }
                 }
             }
@@ -494,22 +498,291 @@ struct RescoreArgs {
     float* out_scores;
     int32_t* todo;
     unsigned int* counters;  // [0] uncertified users, [1] max candidates
+    int lists_only;          // 1 = every user on rescore_user_lists (CRB_RESCORE_LISTS=1: A/B and the equality test)
 };
 
-#define RS_CH 64   // columns of the item rows staged per round (shared memory: 8 warps x (32 rows x 65 + 64) floats)
+#define RS_CH 64   // columns of the item rows staged per round (shared memory per warp: 32 rows x 65 + 64 floats + the list counts)
+#define RS_ORD (32 * (RS_CH + 1))   // words of a warp's row staging area; before any row is staged it holds the bisection array
+#define RS_MAXL (64 * TC_CH)        // candidate lists per user (item splits x column halves)
+#define RS_LIVE 8                   // surviving candidates per lane kept in registers (256 per user); a user with more takes the list path
+#define RS_WARP_WORDS (RS_ORD + RS_CH + RS_MAXL)
+
+// Canonical scores of up to 32 candidates of one user (lane = candidate): a lane runs the canonical sequential chain (the scores are those
+// of canonical_score, bit for bit), but the item rows are staged in shared memory by cp.async, 64 columns of up to 32 rows at a time,
+// instead of being read 16 bytes at a time by the lane that consumes them (same scheme as score_pairs_tiled_kernel).
+template <int KIND>
+__device__ __forceinline__ float rescore_group(const RescoreArgs& a, const float* __restrict__ p, uint32_t item, bool live, unsigned live_mask,
+                                               int lane, float* sQ, float* sP) {
+    float acc = 0.f;
+    for (int kc = 0; kc < a.dim; kc += RS_CH) {
+        const int len = a.dim - kc < RS_CH ? a.dim - kc : RS_CH;
+        const bool in0 = lane < len, in1 = lane + 32 < len;
+        for (unsigned m = live_mask; m; m &= m - 1) {
+            const int r = __ffs(m) - 1;
+            const float* src = a.Q + (int64_t)__shfl_sync(0xffffffffu, item, r) * a.dim + kc;
+            if (in0) __pipeline_memcpy_async(sQ + r * (RS_CH + 1) + lane, src + lane, 4);
+            if (in1) __pipeline_memcpy_async(sQ + r * (RS_CH + 1) + lane + 32, src + lane + 32, 4);
+        }
+        __pipeline_commit();
+        if (in0) sP[lane] = p[kc + lane];
+        if (in1) sP[lane + 32] = p[kc + lane + 32];
+        __pipeline_wait_prior(0);
+        __syncwarp();
+        if (live) {
+            const float* q = sQ + lane * (RS_CH + 1);
+            for (int c = 0; c < len; ++c) {
+                const float pa = sP[c], qb = q[c];
+                if (KIND == CRB_SCORE_DOT || KIND == CRB_SCORE_DOT_BIAS) acc = fmaf(pa, qb, acc);
+                else if (KIND == CRB_SCORE_GMF) acc = fmaf(__fmul_rn(pa, qb), __ldg(a.hvec + kc + c), acc);
+                else { const float dd = __fsub_rn(pa, qb); acc = fmaf(dd, dd, acc); }
+            }
+        }
+        __syncwarp();
+    }
+    if (KIND == CRB_SCORE_DOT_BIAS) acc = __fadd_rn(acc, live ? a.hvec[item] : 0.f);
+    return acc;
+}
+
+// One user, working on the candidate lists where they lie in global memory: any number of candidates.  The pre-filter bisection, the
+// re-scoring and the K selection rounds each walk all of the user's lists, so the cost grows with (lists x rounds) dependent L2 round
+// trips: this is the fall-back of rescore_user_fast, which handles every user with <= 256 survivors.
+template <int KIND>
+__device__ __noinline__ void rescore_user_lists(const RescoreArgs& a, int64_t g, int lane, float* sQ, float* sP, float eps, float* theta_out,
+                                                unsigned long long* kth_out, int* total_out) {
+    constexpr int ASC = KIND == CRB_SCORE_SQDIST ? 1 : 0;
+    const float* p = a.P + (int64_t)a.users[g] * a.dim;
+    float theta = -INFINITY;
+    int total = 0;
+    // Pre-filter on the APPROXIMATE scores: with T <= the K-th best approximate score of the user's candidates, a candidate
+    // whose approximate score is below T - 2 eps has at least K candidates canonically above it (|approx - canonical| <= eps
+    // for both), so it cannot be in the top K and needs no fp32 dot product.  T is found by bisection on the order-preserving
+    // score bits (count >= K keeps T a lower bound; stop once the count is within [K, 2K]).  This does not touch theta.
+    uint32_t lo_b = 0xFFFFFFFFu, hi_b = 0u;
+    for (int sp = 0; sp < a.n_splits; ++sp) {
+        const int64_t slot = (int64_t)sp * a.n_users_pad + g;
+        const int n = a.cand_cnt[slot];
+        const unsigned long long* list = a.cand + slot * TC_C;
+        for (int k = lane; k < n; k += 32) {
+            const uint32_t o = ord_bits((uint32_t)(list[k] >> 32));
+            lo_b = min(lo_b, o); hi_b = max(hi_b, o);
+        }
+        total += n;
+    }
+    lo_b = __reduce_min_sync(0xffffffffu, lo_b);
+    hi_b = __reduce_max_sync(0xffffffffu, hi_b);
+    uint32_t T_b = lo_b;   // count(o >= lo_b) = total: a valid (if useless) lower bound when total >= K
+    if (total > 2 * a.K) {
+        uint32_t lo = lo_b, hi = hi_b;   // invariant: count(o >= lo) >= K
+        for (int it = 0; it < 32 && lo < hi; ++it) {
+            const uint32_t mid = lo + ((hi - lo + 1) >> 1);
+            int c = 0;
+            for (int sp = 0; sp < a.n_splits; ++sp) {
+                const int64_t slot = (int64_t)sp * a.n_users_pad + g;
+                const int n = a.cand_cnt[slot];
+                const unsigned long long* list = a.cand + slot * TC_C;
+                for (int k = lane; k < n; k += 32) c += ord_bits((uint32_t)(list[k] >> 32)) >= mid;
+            }
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (c >= a.K) { lo = mid; if (c <= 2 * a.K) break; } else hi = mid - 1;
+        }
+        T_b = lo;
+    }
+    const float T_f = __uint_as_float((T_b & 0x80000000u) ? (T_b & 0x7fffffffu) : ~T_b);
+    const float cutoff = (total > 2 * a.K) ? T_f - 2.f * eps : -INFINITY;
+    for (int sp = 0; sp < a.n_splits; ++sp) {
+        const int64_t slot = (int64_t)sp * a.n_users_pad + g;
+        const int n = a.cand_cnt[slot];
+        theta = fmaxf(theta, a.cand_thr[slot]);
+        unsigned long long* list = a.cand + slot * TC_C;
+        // canonical score of every surviving candidate, entry rewritten as a ranking key (0 = filtered out)
+        for (int k0 = 0; k0 < n; k0 += 32) {
+            const int k = k0 + lane;
+            const unsigned long long e = k < n ? list[k] : 0ULL;
+            const uint32_t item = (uint32_t)e;
+            const bool live = k < n && !(__uint_as_float((uint32_t)(e >> 32)) < cutoff);
+            if (k < n && !live) list[k] = 0ULL;
+            const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+            if (!live_mask) continue;
+            const float acc = rescore_group<KIND>(a, p, item, live, live_mask, lane, sQ, sP);
+            if (live) list[k] = rank_key(acc, item, ASC);
+        }
+    }
+    __syncwarp();
+    // K rounds of arg-best over all splits' lists
+    unsigned long long prev = ~0ULL, kth = 0ULL;
+    for (int r = 0; r < a.K; ++r) {
+        unsigned long long best = 0ULL;
+        for (int sp = 0; sp < a.n_splits; ++sp) {
+            const int64_t slot = (int64_t)sp * a.n_users_pad + g;
+            const int n = a.cand_cnt[slot];
+            const unsigned long long* list = a.cand + slot * TC_C;
+            for (int k = lane; k < n; k += 32) {
+                const unsigned long long key = list[k];
+                if (key < prev && key > best) best = key;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        if (lane == 0) {
+            a.out_items[g * a.K + r] = best ? (int32_t)key_index(best) : -1;
+            if (a.out_scores) a.out_scores[g * a.K + r] = best ? key_score(best, ASC) : 0.f;
+        }
+        if (best) { prev = best; kth = best; } else { kth = 0ULL; prev = 0ULL; }
+    }
+    *theta_out = theta; *kth_out = kth; *total_out = total;
+}
+
+// One user, everything after one pass over the lists in shared memory / registers.  The user's lists are read in batches of 8 loads per
+// lane that do not depend on each other (the flat index runs over (list, position) pairs, whatever the lists' lengths); the bisection of
+// the pre-filter runs on a shared-memory copy of the score bits -- up to RS_ORD / lists entries of every list: a threshold with >= K
+// entries of a SUBSET at or above it has >= K of all entries at or above it, so the filter stays valid when a list is longer --; the
+// survivors (<= 2K + the candidates within 2 eps of the threshold: a few dozen) are compacted, re-scored 32 at a time whatever list they
+// came from, and ranked from registers.  Same survivors' canonical scores and same keys as rescore_user_lists, hence the same top K.
+// Returns false (nothing written) when the user has more than 32 * RS_LIVE survivors.
+template <int KIND>
+__device__ __forceinline__ bool rescore_user_fast(const RescoreArgs& a, int64_t g, int lane, float* sQ, float* sP, int* sCnt, float eps,
+                                                  float* theta_out, unsigned long long* kth_out, int* total_out) {
+    constexpr int ASC = KIND == CRB_SCORE_SQDIST ? 1 : 0;
+    const int L = a.n_splits;
+    uint32_t* sO = reinterpret_cast<uint32_t*>(sQ);
+    int total = 0, maxn = 0;
+    float theta = -INFINITY;
+    for (int l = lane; l < L; l += 32) {
+        const int64_t slot = (int64_t)l * a.n_users_pad + g;
+        const int n = a.cand_cnt[slot];
+        sCnt[l] = n;
+        total += n;
+        maxn = max(maxn, n);
+        theta = fmaxf(theta, a.cand_thr[slot]);
+    }
+    total = __reduce_add_sync(0xffffffffu, total);
+    maxn = __reduce_max_sync(0xffffffffu, maxn);
+    for (int o = 16; o > 0; o >>= 1) theta = fmaxf(theta, __shfl_xor_sync(0xffffffffu, theta, o));
+    __syncwarp();
+    float cutoff = -INFINITY;
+    if (total > 2 * a.K) {
+        const int cpl = min(maxn, RS_ORD / L);   // entries of every list that take part in the bisection
+        const int space = L * cpl;
+        uint32_t lo_b = 0xFFFFFFFFu, hi_b = 0u;
+        int sub = 0;
+        for (int f0 = 0; f0 < space; f0 += 256) {
+            unsigned long long e[8];
+            unsigned okm = 0u;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int f = f0 + q * 32 + lane;
+                const int l = f / cpl, k = f - l * cpl;
+                const bool ok = f < space && k < sCnt[l];
+                e[q] = ok ? a.cand[((int64_t)l * a.n_users_pad + g) * TC_C + k] : 0ULL;
+                okm |= (ok ? 1u : 0u) << q;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int f = f0 + q * 32 + lane;
+                const bool ok = (okm >> q) & 1u;
+                const uint32_t o = ok ? ord_bits((uint32_t)(e[q] >> 32)) : 0u;   // 0 sorts below every score: holes never count
+                if (f < space) sO[f] = o;
+                if (ok) { lo_b = min(lo_b, o); hi_b = max(hi_b, o); ++sub; }
+            }
+        }
+        lo_b = __reduce_min_sync(0xffffffffu, lo_b);
+        hi_b = __reduce_max_sync(0xffffffffu, hi_b);
+        sub = __reduce_add_sync(0xffffffffu, sub);
+        __syncwarp();
+        if (sub >= a.K) {
+            uint32_t T_b = lo_b;   // count(o >= lo_b) = sub >= K
+            if (sub > 2 * a.K) {
+                uint32_t lo = lo_b, hi = hi_b;   // invariant: count(o >= lo) >= K
+                for (int it = 0; it < 32 && lo < hi; ++it) {
+                    const uint32_t mid = lo + ((hi - lo + 1) >> 1);
+                    int c = 0;
+                    for (int f = lane; f < space; f += 32) c += sO[f] >= mid;
+                    c = __reduce_add_sync(0xffffffffu, c);
+                    if (c >= a.K) { lo = mid; if (c <= 2 * a.K) break; } else hi = mid - 1;
+                }
+                T_b = lo;
+            }
+            cutoff = __uint_as_float((T_b & 0x80000000u) ? (T_b & 0x7fffffffu) : ~T_b) - 2.f * eps;
+        }
+        __syncwarp();
+    }
+    // survivors of ALL entries, compacted (the bisection array is dead: its words now hold the survivors' item ids)
+    uint32_t* sC = sO;
+    int live_n = 0;
+    const int space2 = L * maxn;
+    for (int f0 = 0; f0 < space2; f0 += 256) {
+        unsigned long long e[8];
+        unsigned okm = 0u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int f = f0 + q * 32 + lane;
+            const int l = f / maxn, k = f - l * maxn;
+            const bool ok = f < space2 && k < sCnt[l];
+            e[q] = ok ? a.cand[((int64_t)l * a.n_users_pad + g) * TC_C + k] : 0ULL;
+            okm |= (ok ? 1u : 0u) << q;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const bool lv = ((okm >> q) & 1u) && !(__uint_as_float((uint32_t)(e[q] >> 32)) < cutoff);
+            const unsigned m = __ballot_sync(0xffffffffu, lv);
+            const int pos = live_n + __popc(m & ((1u << lane) - 1u));
+            if (lv && pos < 32 * RS_LIVE) sC[pos] = (uint32_t)e[q];
+            live_n += __popc(m);
+        }
+    }
+    __syncwarp();
+    if (live_n > 32 * RS_LIVE) return false;
+    uint32_t item[RS_LIVE];
+    unsigned long long key[RS_LIVE];
+#pragma unroll
+    for (int r = 0; r < RS_LIVE; ++r) {
+        item[r] = r * 32 + lane < live_n ? sC[r * 32 + lane] : 0u;
+        key[r] = 0ULL;
+    }
+    __syncwarp();   // the ids are in registers: the staging area is free for item rows
+    const float* p = a.P + (int64_t)a.users[g] * a.dim;
+#pragma unroll
+    for (int r = 0; r < RS_LIVE; ++r) {
+        if (r * 32 < live_n) {
+            const bool live = r * 32 + lane < live_n;
+            const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+            const float acc = rescore_group<KIND>(a, p, item[r], live, live_mask, lane, sQ, sP);
+            if (live) key[r] = rank_key(acc, item[r], ASC);
+        }
+    }
+    unsigned long long prev = ~0ULL, kth = 0ULL;
+    for (int r = 0; r < a.K; ++r) {
+        unsigned long long best = 0ULL;
+#pragma unroll
+        for (int q = 0; q < RS_LIVE; ++q)
+            if (key[q] < prev && key[q] > best) best = key[q];
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        if (lane == 0) {
+            a.out_items[g * a.K + r] = best ? (int32_t)key_index(best) : -1;
+            if (a.out_scores) a.out_scores[g * a.K + r] = best ? key_score(best, ASC) : 0.f;
+        }
+        if (best) { prev = best; kth = best; } else { kth = 0ULL; prev = 0ULL; }
+    }
+    *theta_out = theta; *kth_out = kth; *total_out = total;
+    return true;
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(256) rescore_kernel(RescoreArgs a) {
     constexpr int ASC = KIND == CRB_SCORE_SQDIST ? 1 : 0;
     extern __shared__ float rs_sm[];
     const int lane = threadIdx.x & 31;
-    float* sQ = rs_sm + (threadIdx.x >> 5) * (32 * (RS_CH + 1) + RS_CH);
-    float* sP = sQ + 32 * (RS_CH + 1);
+    float* sQ = rs_sm + (threadIdx.x >> 5) * RS_WARP_WORDS;
+    float* sP = sQ + RS_ORD;
+    int* sCnt = reinterpret_cast<int*>(sP + RS_CH);
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t g = warp; g < a.n_users; g += n_warps) {
-        const float* p = a.P + (int64_t)a.users[g] * a.dim;
-        float theta = -INFINITY;
-        int total = 0;
         // error bound of one approximate score for this user (same expression as the certificate below)
         float eps;
         {
@@ -517,114 +790,13 @@ __global__ void __launch_bounds__(256) rescore_kernel(RescoreArgs a) {
             if (KIND == CRB_SCORE_SQDIST) { const float s_ = a.pnorm[g] + qmax; eps = a.cbound * s_ * s_; }
             else { eps = a.cbound * a.pnorm[g] * qmax; if (KIND == CRB_SCORE_DOT_BIAS) eps += a.cbound * __uint_as_float(a.maxbits[1]); }
         }
-        // Pre-filter on the APPROXIMATE scores: with T <= the K-th best approximate score of the user's candidates, a candidate
-        // whose approximate score is below T - 2 eps has at least K candidates canonically above it (|approx - canonical| <= eps
-        // for both), so it cannot be in the top K and needs no fp32 dot product.  T is found by bisection on the order-preserving
-        // score bits (count >= K keeps T a lower bound; stop once the count is within [K, 2K]).  This does not touch theta.
-        uint32_t lo_b = 0xFFFFFFFFu, hi_b = 0u;
-        for (int sp = 0; sp < a.n_splits; ++sp) {
-            const int64_t slot = (int64_t)sp * a.n_users_pad + g;
-            const int n = a.cand_cnt[slot];
-            const unsigned long long* list = a.cand + slot * TC_C;
-            for (int k = lane; k < n; k += 32) {
-                const uint32_t o = ord_bits((uint32_t)(list[k] >> 32));
-                lo_b = min(lo_b, o); hi_b = max(hi_b, o);
-            }
-            total += n;
-        }
-        lo_b = __reduce_min_sync(0xffffffffu, lo_b);
-        hi_b = __reduce_max_sync(0xffffffffu, hi_b);
-        uint32_t T_b = lo_b;   // count(o >= lo_b) = total: a valid (if useless) lower bound when total >= K
-        if (total > 2 * a.K) {
-            uint32_t lo = lo_b, hi = hi_b;   // invariant: count(o >= lo) >= K
-            for (int it = 0; it < 32 && lo < hi; ++it) {
-                const uint32_t mid = lo + ((hi - lo + 1) >> 1);
-                int c = 0;
-                for (int sp = 0; sp < a.n_splits; ++sp) {
-                    const int64_t slot = (int64_t)sp * a.n_users_pad + g;
-                    const int n = a.cand_cnt[slot];
-                    const unsigned long long* list = a.cand + slot * TC_C;
-                    for (int k = lane; k < n; k += 32) c += ord_bits((uint32_t)(list[k] >> 32)) >= mid;
-                }
-                c = __reduce_add_sync(0xffffffffu, c);
-                if (c >= a.K) { lo = mid; if (c <= 2 * a.K) break; } else hi = mid - 1;
-            }
-            T_b = lo;
-        }
-        const float T_f = __uint_as_float((T_b & 0x80000000u) ? (T_b & 0x7fffffffu) : ~T_b);
-        const float cutoff = (total > 2 * a.K) ? T_f - 2.f * eps : -INFINITY;
-        for (int sp = 0; sp < a.n_splits; ++sp) {
-            const int64_t slot = (int64_t)sp * a.n_users_pad + g;
-            const int n = a.cand_cnt[slot];
-            theta = fmaxf(theta, a.cand_thr[slot]);
-            unsigned long long* list = a.cand + slot * TC_C;
-            // canonical score of every surviving candidate, entry rewritten as a ranking key (0 = filtered out).  A lane owns a candidate
-            // and runs the canonical sequential chain (the scores are those of canonical_score, bit for bit), but the item rows are staged
-            // in shared memory by cp.async, 64 columns of up to 32 rows at a time, instead of being read 16 bytes at a time by the lane
-            // that consumes them (same scheme as score_pairs_tiled_kernel).
-            for (int k0 = 0; k0 < n; k0 += 32) {
-                const int k = k0 + lane;
-                const unsigned long long e = k < n ? list[k] : 0ULL;
-                const uint32_t item = (uint32_t)e;
-                const bool live = k < n && !(__uint_as_float((uint32_t)(e >> 32)) < cutoff);
-                if (k < n && !live) list[k] = 0ULL;
-                const unsigned live_mask = __ballot_sync(0xffffffffu, live);
-                if (!live_mask) continue;
-                float acc = 0.f;
-                for (int kc = 0; kc < a.dim; kc += RS_CH) {
-                    const int len = a.dim - kc < RS_CH ? a.dim - kc : RS_CH;
-                    const bool in0 = lane < len, in1 = lane + 32 < len;
-                    for (unsigned m = live_mask; m; m &= m - 1) {
-                        const int r = __ffs(m) - 1;
-                        const float* src = a.Q + (int64_t)__shfl_sync(0xffffffffu, item, r) * a.dim + kc;
-                        if (in0) __pipeline_memcpy_async(sQ + r * (RS_CH + 1) + lane, src + lane, 4);
-                        if (in1) __pipeline_memcpy_async(sQ + r * (RS_CH + 1) + lane + 32, src + lane + 32, 4);
-                    }
-                    __pipeline_commit();
-                    if (in0) sP[lane] = p[kc + lane];
-                    if (in1) sP[lane + 32] = p[kc + lane + 32];
-                    __pipeline_wait_prior(0);
-                    __syncwarp();
-                    if (live) {
-                        const float* q = sQ + lane * (RS_CH + 1);
-                        for (int c = 0; c < len; ++c) {
-                            const float pa = sP[c], qb = q[c];
-                            if (KIND == CRB_SCORE_DOT || KIND == CRB_SCORE_DOT_BIAS) acc = fmaf(pa, qb, acc);
-                            else if (KIND == CRB_SCORE_GMF) acc = fmaf(__fmul_rn(pa, qb), __ldg(a.hvec + kc + c), acc);
-                            else { const float dd = __fsub_rn(pa, qb); acc = fmaf(dd, dd, acc); }
-                        }
-                    }
-                    __syncwarp();
-                }
-                if (KIND == CRB_SCORE_DOT_BIAS) acc = __fadd_rn(acc, live ? a.hvec[item] : 0.f);
-                if (live) list[k] = rank_key(acc, item, ASC);
-            }
-        }
-        __syncwarp();
+        float theta;
+        unsigned long long kth;
+        int total;
+        __syncwarp();   // the previous user's shared-memory words are dead
+        if (a.lists_only || !rescore_user_fast<KIND>(a, g, lane, sQ, sP, sCnt, eps, &theta, &kth, &total))
+            rescore_user_lists<KIND>(a, g, lane, sQ, sP, eps, &theta, &kth, &total);
         if (lane == 0) atomicMax(a.counters + 1, (unsigned int)total);
-        // K rounds of arg-best over all splits' lists
-        unsigned long long prev = ~0ULL, kth = 0ULL;
-        for (int r = 0; r < a.K; ++r) {
-            unsigned long long best = 0ULL;
-            for (int sp = 0; sp < a.n_splits; ++sp) {
-                const int64_t slot = (int64_t)sp * a.n_users_pad + g;
-                const int n = a.cand_cnt[slot];
-                const unsigned long long* list = a.cand + slot * TC_C;
-                for (int k = lane; k < n; k += 32) {
-                    const unsigned long long key = list[k];
-                    if (key < prev && key > best) best = key;
-                }
-            }
-            for (int o = 16; o > 0; o >>= 1) {
-                const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-                best = other > best ? other : best;
-            }
-            if (lane == 0) {
-                a.out_items[g * a.K + r] = best ? (int32_t)key_index(best) : -1;
-                if (a.out_scores) a.out_scores[g * a.K + r] = best ? key_score(best, ASC) : 0.f;
-            }
-            if (best) { prev = best; kth = best; } else { kth = 0ULL; prev = 0ULL; }
-        }
         // certificate
         bool ok;
         if (theta == -INFINITY) {
@@ -693,17 +865,24 @@ int crb_score_topk_tc(crb_handle* h, int32_t kind, const float* P, const float* 
     const int64_t pass_users = n_users < (1 << 18) ? n_users : (1 << 18);   // bounds the candidate-list workspace (1 GB)
     const int64_t pass_pad = round_up(pass_users, TC_BM);
     const int64_t m_tiles_max = pass_pad / TC_BM;
-    // Item splits: a work item is (256-user tile, item range); every extra range costs a list start-up (the first ~10^4 items of
-    // a list produce half of its appends) and more candidates to re-score, taken here as 150 tiles' worth.  Pick the split count
+    // Item splits: a work item is (256-user tile, item range); every extra range costs a list start-up (until a list has seen ~5e4
+    // items almost every chunk has a score above the threshold of one of the warp's 32 users and takes the divergent path) and more
+    // candidates to re-score: measured ~0.9 ms per work item at 4096 users x 2M items, i.e. 800 tiles' worth.  Pick the split count
     // that minimises waves x (tiles per range + overhead) on this machine.
     int n_splits = 1;
     {
+        double split_overhead = 800.0;
+        if (const char* e = getenv("CRB_TC_SPLIT_OVERHEAD")) split_overhead = atof(e);
         double best = 0.0;
         for (int n = 1; n <= 64 && n <= n_tiles; ++n) {
             const int64_t waves = (m_tiles_max * n + h->sm_count - 1) / h->sm_count;
-            const double cost = (double)waves * ((double)((n_tiles + n - 1) / n) + 150.0);
+            const double cost = (double)waves * ((double)((n_tiles + n - 1) / n) + split_overhead);
             if (n == 1 || cost < best * 0.97) { if (n == 1 || cost < best) { best = cost; n_splits = n; } }
         }
+    }
+    if (const char* fs = getenv("CRB_TC_SPLITS")) {   // experiments: force the split count
+        const int v = atoi(fs);
+        if (v >= 1 && v <= 64 && v <= n_tiles) n_splits = v;
     }
     const int tiles_per_split = (n_tiles + n_splits - 1) / n_splits;
     n_splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
@@ -735,6 +914,7 @@ int crb_score_topk_tc(crb_handle* h, int32_t kind, const float* P, const float* 
         prep_kernel<false><<<prep_grid, 256, 0, s>>>(pq);
         h->launches++;
         CRB_CUDA(cudaGetLastError());
+        h->tc_robust = 0;
         h->evq_valid = 1; h->evq_q = Q; h->evq_hvec = hvec; h->evq_items = n_items; h->evq_dim = dim; h->evq_kind = kind;
     }
     CRB_CUDA(cudaMemsetAsync(ctrs, 0, n_passes * 8, s));
@@ -749,6 +929,8 @@ int crb_score_topk_tc(crb_handle* h, int32_t kind, const float* P, const float* 
     CRB_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     const float cbound = 1.0f / 128.0f + (float)d_pad * (1.0f / 4194304.0f);
     int64_t certified = 0, rerun = 0, maxcand = 0;
+    const char* lo_env = getenv("CRB_RESCORE_LISTS");
+    const int lists_only = (lo_env && atoi(lo_env)) || n_splits * TC_CH > RS_MAXL;
     int64_t pass = 0;
     for (int64_t u0 = 0; u0 < n_users; u0 += pass_users, ++pass) {
         const int64_t nu = (n_users - u0) < pass_users ? (n_users - u0) : pass_users;
@@ -766,6 +948,25 @@ int crb_score_topk_tc(crb_handle* h, int32_t kind, const float* P, const float* 
 #else
         ta.debug = 0;
 #endif
+        // Compaction policy (see compact_list).  The certificate needs the K-th best canonical score of the merged lists to clear the
+        // largest list threshold by the bf16 error bound, i.e. the thresholds to sit around rank 1.5 K of the user's scores or lower:
+        // a list holds a 1 / n_lists share of those on average, so it keeps that share plus four standard deviations (never less than
+        // 16) -- 31 entries for K = 20 with two lists, 16 from eight lists on -- and is compacted again half a range later.  A failed
+        // certificate costs an exact re-run of the user (~0.25 ms), so the margin errs on the safe side.
+        // The share assumes that a user's best items are spread over the item splits like the items themselves.  On a catalogue whose
+        // ids are sorted by popularity they may all sit in one split: the certificates of many users then fail, results stay exact
+        // (re-runs) but slow, and the handle switches to the margin of two lists -- the column halves interleave inside every tile and
+        // cannot be skewed -- until the item table changes (h->tc_robust).
+        {
+            const double share = 1.5 * K / (double)((h->tc_robust ? 1 : n_splits) * TC_CH);
+            int lo = (int)ceil(share + 4.0 * sqrt(share));
+            ta.keep_lo = lo < 16 ? 16 : lo > 64 ? 64 : lo;
+        }
+        if (const char* e = getenv("CRB_TC_KEEP_LO")) { const int v = atoi(e); if (v >= 8 && v <= 64) ta.keep_lo = v; }
+        ta.keep_hi = 2 * ta.keep_lo;
+        ta.trig = ta.keep_hi + (ta.keep_lo / 2 > 16 ? ta.keep_lo / 2 : 16);
+        if (const char* e = getenv("CRB_TC_TRIG")) { const int v = atoi(e); if (v > ta.keep_hi) ta.trig = v; }
+        if (ta.trig > TC_C - 32 * (TC_BN / 32 / TC_CH)) ta.trig = TC_C - 32 * (TC_BN / 32 / TC_CH);   // the next tile must fit (32 appends per chunk at worst)
         ta.cand = (unsigned long long*)(ws + o_cand); ta.cand_cnt = (int32_t*)(ws + o_cnt); ta.cand_thr = (float*)(ws + o_thr);
         const int64_t n_work = (nu_pad / TC_BM) * n_splits;
         const int grid = (int)(n_work < h->sm_count ? n_work : h->sm_count);
@@ -777,8 +978,9 @@ int crb_score_topk_tc(crb_handle* h, int32_t kind, const float* P, const float* 
         ra.pnorm = (const float*)(ws + o_pn); ra.psq = (const float*)(ws + o_psq); ra.maxbits = misc; ra.cbound = cbound;
         ra.out_items = topk_items + u0 * K; ra.out_scores = topk_scores ? topk_scores + u0 * K : nullptr;
         ra.todo = (int32_t*)(ws + o_todo) + pass * pass_pad; ra.counters = ctrs + 2 * pass;
+        ra.lists_only = lists_only;
         const int rgrid = (int)((nu + 7) / 8 < (int64_t)h->sm_count * 8 ? (nu + 7) / 8 : (int64_t)h->sm_count * 8);
-        const size_t rsm = sizeof(float) * 8 * (32 * (RS_CH + 1) + RS_CH);
+        const size_t rsm = sizeof(float) * 8 * RS_WARP_WORDS;
 #define CRB_RESCORE(KK) CRB_CUDA(cudaFuncSetAttribute(rescore_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm)); \
                         rescore_kernel<KK><<<rgrid, 256, rsm, s>>>(ra);
         switch (kind) {
@@ -816,6 +1018,7 @@ int crb_score_topk_tc(crb_handle* h, int32_t kind, const float* P, const float* 
         if ((int64_t)cnts[2 * pass + 1] > maxcand) maxcand = cnts[2 * pass + 1];
     }
     free(cnts);
+    if (rerun * 64 > n_users) h->tc_robust = 1;
     h->topk_stats[0] = certified; h->topk_stats[1] = rerun; h->topk_stats[2] = maxcand; h->topk_stats[3] = n_splits;
     return CRB_OK;
 }

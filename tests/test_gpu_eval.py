@@ -191,3 +191,71 @@ def test_fullrank_topk_beyond_32(eng):
     want, _ = O.fullrank_topk(0, P, Q, users, rp, sc, 50)
     got = eng.score_topk(0, torch.tensor(P).cuda(), torch.tensor(Q).cuda(), users, 50, exact=False)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+@pytest.mark.parametrize("shape", [(150, 3000, 20), (600, 40000, 32), (40, 700, 5)])
+def test_fullrank_rescore_fast_path_equals_list_path(eng, kind, shape, monkeypatch):
+    """rescore_kernel ranks a user from shared memory / registers (rescore_user_fast: bisection on a SUBSET of the list entries when the
+    lists are long, survivors compacted) or, beyond 256 survivors, list by list in global memory (rescore_user_lists, the only path until
+    round 2): same ids and score bits from both and from the exact CUDA-core kernel, at split counts from a few to ~50 (two lists per split)."""
+    n_users, n_items, K = shape
+    d = synthetic_data(n_users, n_items, 30, seed=kind + 10)
+    eng.set_history(d.ui_train, d.user_nums, d.item_nums)
+    rs = np.random.RandomState(kind + 3)
+    dim = 64
+    P = torch.tensor((rs.randn(d.user_nums, dim) * 0.1).astype(np.float32)).cuda()
+    Q = torch.tensor((rs.randn(d.item_nums, dim) * 0.1).astype(np.float32)).cuda()
+    hvec = torch.tensor((rs.randn(dim if kind == 1 else d.item_nums) * 0.1).astype(np.float32)).cuda() if kind in (1, 3) else None
+    users = np.arange(d.user_nums, dtype=np.int32)
+    monkeypatch.delenv("CRB_RESCORE_LISTS", raising=False)
+    fast_i, fast_s = eng.score_topk(kind, P, Q, users, K, hvec=hvec, return_scores=True)
+    st = eng.score_topk_stats()
+    assert st["certified"] + st["exact_rerun"] == d.user_nums and st["certified"] >= 0.9 * d.user_nums
+    monkeypatch.setenv("CRB_RESCORE_LISTS", "1")
+    list_i, list_s = eng.score_topk(kind, P, Q, users, K, hvec=hvec, return_scores=True)
+    monkeypatch.delenv("CRB_RESCORE_LISTS", raising=False)
+    exact_i, exact_s = eng.score_topk(kind, P, Q, users, K, hvec=hvec, exact=True, return_scores=True)
+    assert np.array_equal(fast_i, list_i) and np.array_equal(fast_s.view(np.uint32), list_s.view(np.uint32))
+    assert np.array_equal(fast_i, exact_i) and np.array_equal(fast_s.view(np.uint32), exact_s.view(np.uint32))
+
+
+def test_fullrank_rescore_many_survivors_take_the_list_path(eng):
+    """Every item row identical: every candidate of a user scores the same, nothing can be filtered, a user has thousands of survivors
+    (> 256 = what rescore_user_fast keeps in registers) and is ranked by rescore_user_lists or the exact re-run: the top K are the K
+    smallest unseen ids (tie rule: ascending index), as from the exact kernel."""
+    d = synthetic_data(64, 5000, 20, seed=4)
+    eng.set_history(d.ui_train, d.user_nums, d.item_nums)
+    rs = np.random.RandomState(0)
+    P = torch.tensor((rs.randn(d.user_nums, 32) * 0.1).astype(np.float32)).cuda()
+    Q = torch.tensor(np.tile((rs.randn(1, 32) * 0.1).astype(np.float32), (d.item_nums, 1))).cuda()
+    users = np.arange(d.user_nums, dtype=np.int32)
+    got = eng.score_topk(0, P, Q, users, 20)
+    want = eng.score_topk(0, P, Q, users, 20, exact=True)
+    assert np.array_equal(got, want)
+    pu, pi, rp, sc = X.build_history(d.ui_train, d.user_nums)
+    for u in (0, 5, 63):
+        seen = set(sc[rp[u]:rp[u + 1]].tolist())
+        assert got[u].tolist() == [i for i in range(d.item_nums) if i not in seen][:20]
+
+
+def test_fullrank_popularity_sorted_catalogue_stays_exact(eng):
+    """Item ids sorted by 'popularity' (the first 1500 rows have 4x the norm, so every user's best items sit in the first item split):
+    the per-list compaction margin assumes an even spread, so certificates may fail -- the results must still be the exact kernel's (failed
+    users are re-run exactly), and a second call on the same table, which runs with the two-list margin if the first one re-ran more than
+    1/64 of its users, returns the same."""
+    d = synthetic_data(600, 40000, 30, seed=21)
+    eng.set_history(d.ui_train, d.user_nums, d.item_nums)
+    rs = np.random.RandomState(21)
+    P = torch.tensor((rs.randn(d.user_nums, 64) * 0.1).astype(np.float32)).cuda()
+    q = (rs.randn(d.item_nums, 64) * 0.1).astype(np.float32)
+    q[:1500] *= 4.0
+    Q = torch.tensor(q).cuda()
+    users = np.arange(d.user_nums, dtype=np.int32)
+    want_i, want_s = eng.score_topk(0, P, Q, users, 20, exact=True, return_scores=True)
+    assert int(want_i.max()) < 1500                                   # the skew is what the test says it is
+    for call in range(2):
+        got_i, got_s = eng.score_topk(0, P, Q, users, 20, return_scores=True)
+        st = eng.score_topk_stats()
+        assert st["certified"] + st["exact_rerun"] == d.user_nums
+        assert np.array_equal(got_i, want_i) and np.array_equal(got_s.view(np.uint32), want_s.view(np.uint32)), call
