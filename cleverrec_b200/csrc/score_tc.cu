@@ -190,6 +190,7 @@ struct TcArgs {
     float* cand_thr;            // [n_splits, n_users_pad]
     int keep_lo, keep_hi;       // a compaction keeps between keep_lo and keep_hi entries (keep_lo >= K)
     int trig;                   // a list longer than this is compacted after the tile (keep_hi < trig <= TC_C - 64)
+    unsigned long long* dbg;    // experiments only (-DTC_DEBUG_SWITCHES, CRB_TC_DEBUG_CYCLES=1): cycle counters, see score_topk_tc
     int debug;                  // experiments only (-DTC_DEBUG_SWITCHES, CRB_TC_DEBUG): 1 = read TMEM but skip the scan, 2 = skip the TMEM read too, 3 = scan only
 };
 
@@ -326,12 +327,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             const int t0 = sp * a.tiles_per_split, t1 = min(a.n_tiles, t0 + a.tiles_per_split);
             mbar_wait(a_full, a_phase);
             a_phase ^= 1;
+#ifdef TC_DEBUG_SWITCHES
+            long long dbg_b = 0, dbg_t = 0, dbg_c = 0; const long long dbg_start = clock64();
+#define DBG_T0 dbg_c = clock64();
+#define DBG_ADD(x) x += clock64() - dbg_c;
+#else
+#define DBG_T0
+#define DBG_ADD(x)
+#endif
             for (int t = t0; t < t1; ++t) {
+                DBG_T0
                 mbar_wait(b_full + stage, phase);          // TMA bytes have landed
+                DBG_ADD(dbg_b)
                 const uint32_t b_lo = b_lo0 + stage * b_stage_step;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
+                    DBG_T0
                     mbar_wait(t_empty + acc * 2 + h, acc_phase ^ 1);   // this half's epilogue warps have drained the stage
+                    DBG_ADD(dbg_t)
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (leader) {
                         const uint32_t d_tmem = tmem_base + acc * 256u + (uint32_t)h * 128u;
@@ -351,6 +364,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             }
             if (leader) umma_commit(a_empty);  // A tile reusable after the last item tile's MMAs
             __syncwarp();
+#ifdef TC_DEBUG_SWITCHES
+            if (a.dbg && lane == 0) { atomicAdd(a.dbg + 0, (unsigned long long)dbg_b); atomicAdd(a.dbg + 1, (unsigned long long)dbg_t); atomicAdd(a.dbg + 5, (unsigned long long)(clock64() - dbg_start)); }
+#endif
         }
     } else if (warp >= 4) {
         // ================= epilogue: 16 warps; a thread owns one TMEM lane (= one user) and one column half of every tile ======
@@ -394,8 +410,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             }
             // first column at which a chunk needs the special path: the next seen item or the end of the catalogue
             int32_t special_at = live ? min(seen_cur, n_items32) : 0x7fffffff;
+#ifdef TC_DEBUG_SWITCHES
+            long long dbg_w = 0, dbg_s = 0, dbg_k = 0, dbg_c = 0, dbg_n = 0;
+#endif
             for (int t = t0; t < t1; ++t) {
+                DBG_T0
                 mbar_wait(t_full + acc * 2 + half, acc_phase);
+                DBG_ADD(dbg_w)
+                DBG_T0
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256u + (uint32_t)half * 128u;
 #pragma unroll 1
@@ -451,12 +473,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
+                DBG_ADD(dbg_s)
                 if (lane == 0) mbar_arrive(t_empty + acc * 2 + half);
                 if (++acc == 2u) { acc = 0; acc_phase ^= 1; }
                 // Compaction is OFF the accumulator hand-off: the TMEM stage has just been released, so the ~1500 cycles a
                 // compaction takes (list round trip through L2 + bisection) overlap the next tiles' MMAs instead of stalling them.
                 // A list is compacted as soon as the next tile could overflow it (worst case 32 appends per chunk).
                 unsigned need = __ballot_sync(0xffffffffu, cnt > a.trig);
+                DBG_T0
+#ifdef TC_DEBUG_SWITCHES
+                dbg_n += __popc(need);
+#endif
                 while (need) {
                     const int src = __ffs(need) - 1;
                     need &= need - 1;
@@ -466,7 +493,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                     const float thr = compact_list(lst, n, lane, &kept, a.keep_lo, a.keep_hi);
                     if (lane == src) { theta = fmaxf(theta, thr); cnt = kept; }
                 }
+                DBG_ADD(dbg_k)
             }
+#ifdef TC_DEBUG_SWITCHES
+            if (a.dbg && lane == 0) { atomicAdd(a.dbg + 2, (unsigned long long)dbg_w); atomicAdd(a.dbg + 3, (unsigned long long)dbg_s); atomicAdd(a.dbg + 4, (unsigned long long)dbg_k); atomicAdd(a.dbg + 6, (unsigned long long)dbg_n); }
+#endif
             a.cand_cnt[lslot + g] = live ? cnt : 0;
             a.cand_thr[lslot + g] = theta;
         }
@@ -945,8 +976,11 @@ int crb_score_topk_tc(crb_handle* h, int32_t kind, const float* P, const float* 
         ta.hist_users = hist_users ? hist_users + u0 : nullptr; ta.seen_rowptr = h->seen_rowptr; ta.seen_cols = h->seen_cols;
 #ifdef TC_DEBUG_SWITCHES
         ta.debug = getenv("CRB_TC_DEBUG") ? atoi(getenv("CRB_TC_DEBUG")) : 0;
+        ta.dbg = nullptr;
+        if (getenv("CRB_TC_DEBUG_CYCLES")) { cudaMalloc(&ta.dbg, 64); cudaMemsetAsync(ta.dbg, 0, 64, s); }
 #else
         ta.debug = 0;
+        ta.dbg = nullptr;
 #endif
         // Compaction policy (see compact_list).  The certificate needs the K-th best canonical score of the merged lists to clear the
         // largest list threshold by the bf16 error bound, i.e. the thresholds to sit around rank 1.5 K of the user's scores or lower:
@@ -972,6 +1006,18 @@ int crb_score_topk_tc(crb_handle* h, int32_t kind, const float* P, const float* 
         const int grid = (int)(n_work < h->sm_count ? n_work : h->sm_count);
         score_tc_kernel<<<grid, TC_THREADS, smem_bytes, s>>>(map_a, map_b, ta);
         CRB_CUDA(cudaGetLastError());
+#ifdef TC_DEBUG_SWITCHES
+        if (ta.dbg) {   // sums over all CTAs (MMA warp: [0] wait for B tiles, [1] wait for a drained accumulator, [5] total) and over all
+                        // epilogue warps ([2] wait for an accumulator, [3] scan + appends, [4] compactions, [6] number of compactions)
+            unsigned long long c[8];
+            cudaStreamSynchronize(s);
+            cudaMemcpy(c, ta.dbg, 64, cudaMemcpyDeviceToHost);
+            cudaFree(ta.dbg);
+            const double ctas = (double)grid, ew = ctas * 8 * TC_CH;
+            fprintf(stderr, "tc cycles per CTA: mma total %.0f  wait B %.0f  wait acc %.0f | per epilogue warp: wait %.0f scan %.0f compact %.0f (n %.1f)\n",
+                    c[5] / ctas, c[0] / ctas, c[1] / ctas, c[2] / ew, c[3] / ew, c[4] / ew, c[6] / ew);
+        }
+#endif
         RescoreArgs ra;
         ra.kind = kind; ra.dim = dim; ra.K = K; ra.n_splits = n_splits * TC_CH; ra.n_users = nu; ra.n_users_pad = nu_pad;
         ra.P = P; ra.Q = Q; ra.hvec = hvec; ra.users = users + u0; ra.cand = ta.cand; ra.cand_cnt = ta.cand_cnt; ra.cand_thr = ta.cand_thr;
