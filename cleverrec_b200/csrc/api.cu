@@ -71,6 +71,7 @@ void crb_alt_swap(crb_handle* h) {
     for (int k = 0; k < 3; ++k) { CRB_SWAP(h->idx[k], h->alt.idx[k]); CRB_SWAP(h->rank[k], h->alt.rank[k]); }
     for (int k = 0; k < 2; ++k) { CRB_SWAP(h->meta[k], h->alt.meta[k]); CRB_SWAP(h->meta_rows[k], h->alt.meta_rows[k]); CRB_SWAP(h->sb[k], h->alt.sb[k]); }
     CRB_SWAP(h->ctr, h->alt.ctr);
+    CRB_SWAP(h->ctr_zeroed, h->alt.ctr_zeroed);
     CRB_SWAP(h->dup_rows, h->alt.dup_rows);
     CRB_SWAP(h->work, h->alt.work);
     CRB_SWAP(h->multi, h->alt.multi);
@@ -188,15 +189,15 @@ extern "C" int64_t crb_launch_count(crb_handle* h) { return h ? h->launches : -1
 
 // ---------------------------------------------------------------------------------------------- seen-item Bloom filters
 __global__ void __launch_bounds__(256) bloom_build_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ cols, int64_t n_users,
-                                                          uint32_t* bloom, int shift) {
+                                                          uint32_t* bloom, int shift, int64_t stride, int exact) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t u = warp; u < n_users; u += n_warps) {
         const int64_t lo = rowptr[u], hi = rowptr[u + 1];
-        uint32_t* mine = bloom + (u << shift);
+        uint32_t* mine = bloom + u * stride;
         for (int64_t p = lo + lane; p < hi; p += 32) {
-            const uint32_t bit = crb_bloom_bit((uint32_t)cols[p], shift);
+            const uint32_t bit = exact ? (uint32_t)cols[p] : crb_bloom_bit((uint32_t)cols[p], shift);
             atomicOr(mine + (bit >> 5), 1u << (bit & 31));
         }
     }
@@ -204,6 +205,10 @@ __global__ void __launch_bounds__(256) bloom_build_kernel(const int64_t* __restr
 
 // (Re)builds the per-user Bloom filters for the history just installed.  ~8 bits per seen entry on average, 32..2048 bits per user;
 // skipped (bloom = NULL, exact search only) when it would not fit in a quarter of the free device memory or CRB_NO_BLOOM is set.
+// Small catalogues (users x items bits <= 64 MB: every dataset the reference ships) get the EXACT bitmap instead (bit = item id): a
+// set bit then rejects the candidate without the dependent binary search over the history, which at ml-1m's density (165 of 3706
+// items seen on average, filters 8-40 % full) one lane of almost every warp had to take -- the sampler was the longest kernel of
+// the step there.  Same accept / reject decisions either way (CRB_NO_EXACT_BITMAP=1 keeps the hashed filter: A/B and the test).
 int crb_bloom_build(crb_handle* h, cudaStream_t s) {
     CRB_CUDA(cudaSetDevice(h->device));
     int64_t n_seen = 0;
@@ -221,10 +226,13 @@ int crb_bloom_build(crb_handle* h, cudaStream_t s) {
     }
     if (off || shift < 0) {
         if (h->bloom) { CRB_CUDA(cudaStreamSynchronize(s)); cudaFree(h->bloom); }
-        h->bloom = nullptr; h->bloom_words = 0; h->bloom_shift = 0;
+        h->bloom = nullptr; h->bloom_words = 0; h->bloom_shift = 0; h->bloom_stride = 0; h->bloom_exact = 0;
         return CRB_OK;
     }
-    const int64_t words = h->n_users << shift;
+    const int64_t exact_stride = (h->n_items + 31) / 32;
+    const bool exact = getenv("CRB_NO_EXACT_BITMAP") == nullptr && h->n_users * exact_stride * 4 <= ((int64_t)64 << 20);
+    const int64_t stride = exact ? exact_stride : ((int64_t)1 << shift);
+    const int64_t words = h->n_users * stride;
     if (words > h->bloom_words) {
         CRB_CUDA(cudaStreamSynchronize(s));
         cudaFree(h->bloom);
@@ -233,10 +241,12 @@ int crb_bloom_build(crb_handle* h, cudaStream_t s) {
         h->bloom_words = words;
     }
     h->bloom_shift = shift;
+    h->bloom_stride = stride;
+    h->bloom_exact = exact ? 1 : 0;
     CRB_CUDA(cudaMemsetAsync(h->bloom, 0, sizeof(uint32_t) * words, s));
     int64_t grid = (h->n_users + 7) / 8;
     if (grid > (int64_t)h->sm_count * 32) grid = (int64_t)h->sm_count * 32;
-    bloom_build_kernel<<<(int)grid, 256, 0, s>>>(h->seen_rowptr, h->seen_cols, h->n_users, h->bloom, shift);
+    bloom_build_kernel<<<(int)grid, 256, 0, s>>>(h->seen_rowptr, h->seen_cols, h->n_users, h->bloom, shift, stride, exact ? 1 : 0);
     h->launches++;
     CRB_CUDA(cudaGetLastError());
     return CRB_OK;

@@ -40,7 +40,8 @@ struct crb_step_ctr {
     unsigned int multi_rows;  // duplicate rows with more than one chunk
     unsigned int partial_slots; // partial-sum rows handed to multi-chunk duplicate rows
     unsigned int sampler_err; // a positive ran out of attempts (sticky: everything BEFORE this word is zeroed between steps)
-    unsigned int pad[2];
+    unsigned int tail_done;   // dup_tail_kernel: blocks that have finished their share (reset by the last one)
+    unsigned int pad[1];
 };
 
 struct crb_dup_row {   // one row that occurs >= 2 times in the batch
@@ -74,6 +75,8 @@ struct crb_handle {
     uint32_t* bloom;
     int bloom_shift;
     int64_t bloom_words;        // allocated words
+    int64_t bloom_stride;       // words per user (1 << bloom_shift, or ceil(n_items / 32) in exact mode)
+    int bloom_exact;            // 1 = small catalogue: the filter is the user's exact seen-item bitmap (bit = item id), no search needed
     const int64_t* list_start;  // per-user offset / length of the interaction list inside pos_item (FISM / NAIS)
     const int32_t* list_len;
     const int64_t* ilist_start; // item-side lists (TransCF's iu_sp_mat, utils/tools.py:100-113): users of each item inside ipos_user
@@ -159,7 +162,9 @@ struct crb_handle {
         crb_work* work;
         unsigned int* multi;
         int64_t cap_batch;
+        int ctr_zeroed;
     } alt;
+    int ctr_zeroed;          // 1 = the step counters of the current copy are known to be zero (the last step on it ended in dup_tail_kernel)
     int alt_active;          // 1 while the handle's fields hold the alternate copy
     // Whole-epoch CUDA graph of crb_train_epoch_bpr for launch-bound shapes (train.cu): the epoch's kernels are captured once with
     // everything that changes from epoch to epoch (the sampler's permutation keys and epoch word, the optimizer's step base) read

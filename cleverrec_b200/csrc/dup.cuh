@@ -139,10 +139,8 @@ __device__ __forceinline__ void dup_apply(const DupArgs& a, const OptDev& o, con
 // One lane group per work item (= one duplicate row, or one 256-slot chunk of a very frequent one).  The loop is software
 // pipelined: the next item's descriptors (work -> dup_rows, two dependent loads) are fetched while the current item's slots
 // and row are in flight, so a group's critical path per item is one memory round trip instead of four.
-template <int LANES, int VPL, int OPT, bool SHARD = false>
-__global__ void __launch_bounds__(256) dup_reduce_kernel(const DupArgs a) {
-    OptDev o = a.opt;   // a resolved COPY: writing into the parameter struct would move all of it to local memory
-    opt_resolve(o);
+template <int LANES, int VPL, int OPT, bool SHARD>
+__device__ __forceinline__ void dup_reduce_body(const DupArgs& a, const OptDev& o) {
     const int gl = threadIdx.x % LANES;
     const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
     const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / LANES;
@@ -183,12 +181,16 @@ __global__ void __launch_bounds__(256) dup_reduce_kernel(const DupArgs a) {
 }
 
 template <int LANES, int VPL, int OPT, bool SHARD = false>
-__global__ void __launch_bounds__(256) dup_final_kernel(const DupArgs a) {
-    OptDev o = a.opt;
+__global__ void __launch_bounds__(256) dup_reduce_kernel(const DupArgs a) {
+    OptDev o = a.opt;   // a resolved COPY: writing into the parameter struct would move all of it to local memory
     opt_resolve(o);
+    dup_reduce_body<LANES, VPL, OPT, SHARD>(a, o);
+}
+
+// multi-chunk rows: lane groups [group, group + n_groups, ...) of the launch (or of ONE block, dup_tail_kernel)
+template <int LANES, int VPL, int OPT, bool SHARD>
+__device__ __forceinline__ void dup_final_body(const DupArgs& a, const OptDev& o, int64_t group, int64_t n_groups) {
     const int gl = threadIdx.x % LANES;
-    const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
-    const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / LANES;
     const uint32_t n_multi = a.ctr->multi_rows;
     for (int64_t k = group; k < n_multi; k += n_groups) {
         const crb_dup_row d = a.dup_rows[a.multi[k]];
@@ -211,5 +213,51 @@ __global__ void __launch_bounds__(256) dup_final_kernel(const DupArgs a) {
         } else {
             dup_apply<LANES, VPL, OPT>(a, o, d, acc, gl);
         }
+    }
+}
+
+template <int LANES, int VPL, int OPT, bool SHARD = false>
+__global__ void __launch_bounds__(256) dup_final_kernel(const DupArgs a) {
+    OptDev o = a.opt;
+    opt_resolve(o);
+    dup_final_body<LANES, VPL, OPT, SHARD>(a, o, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES, (int64_t)gridDim.x * blockDim.x / LANES);
+}
+
+// Small batches (the shapes the reference ships: a step is a handful of microsecond kernels and costs launch count x launch latency):
+// K4 and K5 and the reset of the step counters in ONE launch.  Every block does its share of dup_reduce; the block that finishes last
+// (ticket in crb_step_ctr::tail_done, the threadFenceReduction pattern) then finishes the multi-chunk rows -- there are none unless a
+// row occurs more than CRB_DUP_CHUNK times in the batch --, sums the per-block loss partials in loss_final_kernel's fixed order and
+// zeroes the counters for the step that uses this counter set next.  Same arithmetic per row and the same loss bits as the three
+// separate launches.
+struct DupTail {
+    crb_step_ctr* ctr;
+    const double* block_loss;
+    int n_block_loss;
+    double* loss_out;
+};
+
+template <int LANES, int VPL, int OPT>
+__global__ void __launch_bounds__(256) dup_tail_kernel(const DupArgs a, const DupTail t) {
+    OptDev o = a.opt;
+    opt_resolve(o);
+    dup_reduce_body<LANES, VPL, OPT, false>(a, o);
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&t.ctr->tail_done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    dup_final_body<LANES, VPL, OPT, false>(a, o, threadIdx.x / LANES, blockDim.x / LANES);
+    if (threadIdx.x < 32) {
+        double v = 0.0;
+        for (int k = threadIdx.x; k < t.n_block_loss; k += 32) v += t.block_loss[k];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (threadIdx.x == 0) *t.loss_out = v;
+    }
+    __syncthreads();   // every thread of the block has read ctr->multi_rows
+    if (threadIdx.x == 0) {
+        t.ctr->dup_slots = 0; t.ctr->dup_rows = 0; t.ctr->work_items = 0; t.ctr->multi_rows = 0; t.ctr->partial_slots = 0;
+        t.ctr->tail_done = 0;
     }
 }

@@ -251,6 +251,8 @@ struct DupArgs {
 };
 
 int crb_launch_dup_pipeline(crb_handle* h, const DupArgs& a, int opt_kind, cudaStream_t s);
+bool crb_dup_tail_enabled(int64_t batch);
+int crb_launch_dup_tail(crb_handle* h, const DupArgs& a, int opt_kind, double* loss_out_dev, cudaStream_t s);   // K4 + K5 + counter reset in one launch
 int crb_launch_assign(crb_handle* h, int64_t batch, int n_roles, const int32_t* const* idx, const int* role_table,
                       cudaStream_t s, const unsigned int* n_dev = nullptr, bool every_row = false);
 int crb_count_rows(crb_handle* h, int64_t batch, int n_roles, const int32_t* const* idx, const int* role_table, cudaStream_t s,

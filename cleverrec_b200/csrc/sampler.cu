@@ -23,6 +23,8 @@ struct SamplerArgs {
     const int32_t* seen_cols;
     const uint32_t* bloom;  // per-user seen-item Bloom filters (NULL: exact search only)
     int bloom_shift;
+    int bloom_exact;        // 1: the filter is the exact seen-item bitmap (bit = item id)
+    int64_t bloom_stride;   // words per user
     const uint32_t* dyn;    // NULL, or (epoch graph) device words that replace keys[0..5] and epoch when the kernel starts
 };
 
@@ -66,7 +68,7 @@ __device__ __forceinline__ bool history_contains(const int32_t* __restrict__ col
 // (one round trip); only a set bit (or no filter) costs the dependent binary search over the sorted history.  The accept / reject
 // decisions, hence the output, are those of the exact test alone.
 __device__ __forceinline__ bool draw_negatives(uint64_t p, int32_t u, uint32_t need, int32_t* acc, const SamplerArgs& a) {
-    const uint32_t* bl = a.bloom ? a.bloom + ((int64_t)u << a.bloom_shift) : nullptr;
+    const uint32_t* bl = a.bloom ? a.bloom + (int64_t)u * a.bloom_stride : nullptr;
     int64_t lo = 0, hi = -1;     // the history bounds are fetched only if a candidate needs the exact test
     if (!bl) { lo = a.seen_rowptr[u]; hi = a.seen_rowptr[u + 1]; }
     uint32_t got = 0;
@@ -78,7 +80,7 @@ __device__ __forceinline__ bool draw_negatives(uint64_t p, int32_t u, uint32_t n
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const uint32_t v = w[q] & a.item_mask;
-            const uint32_t bit = crb_bloom_bit(v, a.bloom_shift);
+            const uint32_t bit = a.bloom_exact ? v : crb_bloom_bit(v, a.bloom_shift);
             bw[q] = (bl && (uint32_t)q < probes && (int32_t)v < a.n_items) ? (__ldg(bl + (bit >> 5)) >> (bit & 31)) & 1u : 2u;
         }
 #pragma unroll
@@ -86,10 +88,11 @@ __device__ __forceinline__ bool draw_negatives(uint64_t p, int32_t u, uint32_t n
             int32_t v = (int32_t)(w[q] & a.item_mask);
             if (v >= a.n_items) continue;
             if (bl && bw[q] == 2u) {   // not probed yet
-                const uint32_t bit = crb_bloom_bit((uint32_t)v, a.bloom_shift);
+                const uint32_t bit = a.bloom_exact ? (uint32_t)v : crb_bloom_bit((uint32_t)v, a.bloom_shift);
                 bw[q] = (__ldg(bl + (bit >> 5)) >> (bit & 31)) & 1u;
             }
             if (bw[q]) {
+                if (bl && a.bloom_exact) continue;   // the bitmap is the history
                 if (hi < 0) { lo = a.seen_rowptr[u]; hi = a.seen_rowptr[u + 1]; }
                 if (history_contains(a.seen_cols, lo, hi, v)) continue;
             }
@@ -212,6 +215,8 @@ static int make_args(crb_handle* h, uint64_t seed, uint32_t epoch, int32_t neg_r
     a->seen_cols = h->seen_cols;
     a->bloom = h->bloom;
     a->bloom_shift = h->bloom_shift;
+    a->bloom_exact = h->bloom_exact;
+    a->bloom_stride = h->bloom_stride;
     a->dyn = h->dyn_mode ? h->dyn_dev : nullptr;
     return CRB_OK;
 }
@@ -451,7 +456,7 @@ extern "C" int crb_sample_sbpr(crb_handle* h, uint64_t seed, uint32_t epoch, int
     A.base.half_bits = bits / 2;
     A.base.half_mask = (uint32_t)(((uint64_t)1 << A.base.half_bits) - 1);
     A.base.pos_user = h->sp_pos_user; A.base.pos_item = h->sp_pos_item; A.base.seen_rowptr = h->excl_rowptr; A.base.seen_cols = h->excl_cols;
-    A.base.bloom = nullptr; A.base.bloom_shift = 0;   // the filter covers the history, not the own + social exclusion sets
+    A.base.bloom = nullptr; A.base.bloom_shift = 0; A.base.bloom_exact = 0; A.base.bloom_stride = 0;   // the filter covers the history, not the own + social exclusion sets
     A.spu_start = h->spu_start; A.spu_items = h->spu_items; A.spu_suk = h->spu_suk;
     CRB_CHECK_ARG(first >= 0 && count >= 0 && (uint64_t)(first + count) <= A.base.n_rows, "rows outside the epoch");
     sample_sbpr_kernel<<<sampler_grid(h, count), 256, 0, s>>>(A, first, count, u, i, k, j, suk, h->ctr);

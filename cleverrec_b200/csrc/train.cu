@@ -137,6 +137,7 @@ int crb_launch_assign(crb_handle* h, int64_t batch, int n_roles, const int32_t* 
         a.table[r] = r < n_roles ? role_table[r] : 0;
         a.meta[r] = h->meta[a.table[r]];
     }
+    h->ctr_zeroed = 0;
     assign_kernel<<<flat_grid(h, batch, 256), 256, 0, s>>>(a, batch, h->ctr, h->dup_rows, h->work, h->multi, every_row ? 0u : 1u);
     h->launches++;
     CRB_CUDA(cudaGetLastError());
@@ -175,6 +176,33 @@ static int launch_dup_t(crb_handle* h, const DupArgs& a, int opt_kind, cudaStrea
 
 int crb_launch_dup_pipeline(crb_handle* h, const DupArgs& a, int opt_kind, cudaStream_t s) {
     return CRB_DIM_DISPATCH(a.dim, launch_dup_t, h, a, opt_kind, s);
+}
+
+template <int LANES, int VPL>
+static int launch_dup_tail_t(crb_handle* h, const DupArgs& a, const DupTail& t, int opt_kind, cudaStream_t s) {
+    const int grid = h->sm_count * 4;   // as dup_reduce_kernel: one lane group per duplicate row at the shapes this path serves
+    switch (opt_kind) {
+        case OPT_SGD: dup_tail_kernel<LANES, VPL, OPT_SGD><<<grid, 256, 0, s>>>(a, t); break;
+        case OPT_ADAGRAD: dup_tail_kernel<LANES, VPL, OPT_ADAGRAD><<<grid, 256, 0, s>>>(a, t); break;
+        case OPT_ADAM_LAZY: dup_tail_kernel<LANES, VPL, OPT_ADAM_LAZY><<<grid, 256, 0, s>>>(a, t); break;
+        case OPT_ADAM_TF1: dup_tail_kernel<LANES, VPL, OPT_ADAM_TF1><<<grid, 256, 0, s>>>(a, t); break;
+    }
+    h->launches++;
+    CRB_CUDA(cudaGetLastError());
+    h->ctr_zeroed = 1;
+    return CRB_OK;
+}
+
+// batches up to 2^16 rows (see dup_tail_kernel); CRB_DUP_TAIL=0 keeps the three separate launches (A/B and the bit-identity test)
+bool crb_dup_tail_enabled(int64_t batch) {
+    const char* e = getenv("CRB_DUP_TAIL");   // read per call: the test flips it inside one process
+    return !(e && atoi(e) == 0) && batch <= 65536;
+}
+
+int crb_launch_dup_tail(crb_handle* h, const DupArgs& a, int opt_kind, double* loss_out_dev, cudaStream_t s) {
+    DupTail t;
+    t.ctr = h->ctr; t.block_loss = h->block_loss; t.n_block_loss = h->step_grid; t.loss_out = loss_out_dev;
+    return CRB_DIM_DISPATCH(a.dim, launch_dup_tail_t, h, a, t, opt_kind, s);
 }
 
 // ------------------------------------------------------------------------------------------------ K5
@@ -470,10 +498,11 @@ static int bpr_step_compute(crb_handle* h, const crb_table* P, const crb_table* 
     d.dup_rows = h->dup_rows; d.work = h->work; d.multi = h->multi;
     d.dup_grad = h->dup_grad; d.dup_t = h->dup_t; d.partial = h->partial; d.ctr = h->ctr;
     if ((rc = crb_prof_begin(h, s, 2))) return rc;
-    rc = crb_launch_dup_pipeline(h, d, opt_kind, s);
+    const bool tail = crb_dup_tail_enabled(batch);
+    rc = tail ? crb_launch_dup_tail(h, d, opt_kind, loss_dev, s) : crb_launch_dup_pipeline(h, d, opt_kind, s);
     if (rc) return rc;
     if ((rc = crb_prof_end(h, s, 2))) return rc;
-    return crb_launch_loss_final(h, loss_dev, s);
+    return tail ? CRB_OK : crb_launch_loss_final(h, loss_dev, s);
 }
 
 // the part of one BPR step after the indices are on the device and (optionally) already counted
@@ -491,7 +520,8 @@ __global__ void merge_sampler_err_kernel(crb_step_ctr* into, crb_step_ctr* from)
 }
 
 int crb_zero_step_counters(crb_handle* h, cudaStream_t s) {
-    // everything except sampler_err (sticky until reported)
+    // everything except sampler_err (sticky until reported); nothing to do when the last step on this copy ended in dup_tail_kernel
+    if (h->ctr_zeroed) return CRB_OK;
     CRB_CUDA(cudaMemsetAsync(h->ctr, 0, offsetof(crb_step_ctr, sampler_err), s));
     return CRB_OK;
 }
@@ -1067,13 +1097,14 @@ static int pointwise_step_device(crb_handle* h, bool gmf, const crb_table* P, co
     d.dim = a.dim; d.opt = od;
     d.dup_rows = h->dup_rows; d.work = h->work; d.multi = h->multi;
     d.dup_grad = h->dup_grad; d.dup_t = h->dup_t; d.partial = h->partial; d.ctr = h->ctr;
-    if ((rc = crb_launch_dup_pipeline(h, d, opt_kind, s))) return rc;
+    const bool tail = crb_dup_tail_enabled(batch);
+    if ((rc = tail ? crb_launch_dup_tail(h, d, opt_kind, loss_dev, s) : crb_launch_dup_pipeline(h, d, opt_kind, s))) return rc;
     if (gmf) {
         dense_apply_kernel<<<1, 256, 0, s>>>(hvec, h_s1, h_s2, h->dense_grad, h->step_grid, P->dim, opt_kind == OPT_ADAM_TF1 ? OPT_ADAM_LAZY : opt_kind, od);
         h->launches++;
         CRB_CUDA(cudaGetLastError());
     }
-    return crb_launch_loss_final(h, loss_dev, s);
+    return tail ? CRB_OK : crb_launch_loss_final(h, loss_dev, s);
 }
 
 extern "C" int crb_train_step_pointwise(crb_handle* h, int32_t kind, const crb_table* P, const crb_table* Q, float* hvec, float* h_s1,

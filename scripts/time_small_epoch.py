@@ -17,8 +17,9 @@ eng.set_history(data.ui_train, data.user_nums, data.item_nums)
 d, B, R = 64, 6144, 4
 rows = eng.epoch_rows(R)
 n_steps = -(-rows // B)
-for mode in ("graph", "loop"):
-    os.environ["CRB_EPOCH_GRAPH"] = "1" if mode == "graph" else "0"
+for mode in ("graph", "loop", "loop-separate-tail", "graph-separate-tail"):
+    os.environ["CRB_EPOCH_GRAPH"] = "1" if mode.startswith("graph") else "0"
+    os.environ["CRB_DUP_TAIL"] = "0" if mode.endswith("separate-tail") else "1"
     g = torch.Generator().manual_seed(0)
     P = Table((torch.randn(data.user_nums, d, generator=g) * 0.01).cuda(), "Adam", "tf1")
     Q = Table((torch.randn(data.item_nums, d, generator=g) * 0.01).cuda(), "Adam", "tf1")

@@ -89,16 +89,19 @@ def test_bloom_filter_never_changes_the_output(eng, shape, monkeypatch):
     pu, pi, rp, sc = X.build_history(d.ui_train, d.user_nums)
     n = pu.shape[0] * R
     outs = []
-    for off in (False, True):
-        if off:
-            monkeypatch.setenv("CRB_NO_BLOOM", "1")
-        else:
-            monkeypatch.delenv("CRB_NO_BLOOM", raising=False)
+    # three ways to test a candidate: exact seen-item bitmap (small catalogues, the default here), hashed filter + search, search only
+    for env in ({}, {"CRB_NO_EXACT_BITMAP": "1"}, {"CRB_NO_BLOOM": "1"}):
+        monkeypatch.delenv("CRB_NO_BLOOM", raising=False)
+        monkeypatch.delenv("CRB_NO_EXACT_BITMAP", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
         eng.set_history(d.ui_train, d.user_nums, d.item_nums)
         outs.append([t.cpu().numpy() for t in eng.sample_pairwise(0xABCDEF, 2, 0, n, R)])
         outs[-1] += [t.cpu().numpy() for t in eng.sample_cml(5, 1, 0, pu.shape[0], R)]
     monkeypatch.delenv("CRB_NO_BLOOM", raising=False)
-    for a, b in zip(*outs):
-        assert np.array_equal(a, b)
+    monkeypatch.delenv("CRB_NO_EXACT_BITMAP", raising=False)
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert np.array_equal(a, b)
     ru, ri, rj, _ = X.sample_pairwise(0xABCDEF, 2, 0, n, R, d.item_nums, pu, pi, rp, sc)
     assert np.array_equal(outs[0][2], rj) and np.array_equal(outs[0][0], ru)

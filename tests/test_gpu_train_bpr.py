@@ -260,7 +260,7 @@ def test_epoch_graph_is_bit_identical(eng, kind, mode, monkeypatch):
             losses = torch.zeros(n_steps, dtype=torch.float64, device="cuda")
             eng.train_epoch_bpr(P, Q, opt, 5, epoch, 0, B, n_steps, R, 0.01, losses)
             all_losses.append(losses.cpu().numpy())
-        assert eng.launches - l0 == 3 * n_steps * 6   # the same six kernels per step either way
+        assert eng.launches - l0 == 3 * n_steps * 4   # the same four kernels per step either way (sample, assign, step, dup_tail)
         eng.adam_flush(P, opt); eng.adam_flush(Q, opt)
         torch.cuda.synchronize()
         out.append((np.concatenate(all_losses), P.w.clone(), Q.w.clone()))
@@ -316,3 +316,42 @@ def test_determinism_across_runs_and_hub_rows(eng, kind, mode):
     for step in range(3):
         assert np.abs(runs[0][step][0] - runs[1][step][0]).max() <= tol * (step + 1)
         assert np.abs(runs[0][step][1] - runs[1][step][1]).max() <= tol * (step + 1)
+
+
+@pytest.mark.parametrize("kind,mode", OPTS)
+def test_fused_tail_is_bit_identical_to_separate_launches(eng, kind, mode, monkeypatch):
+    """Batches up to 2^16 rows end a step with ONE launch (dup_tail_kernel: duplicate reduction, the multi-chunk rows and the loss sum by
+    the block that finishes last, counters reset for the next step) instead of dup_reduce + dup_final + loss_final + a memset.
+    CRB_DUP_TAIL=0 keeps the separate launches: losses and tables bit for bit over three epochs; then two steps on a hub row with 700
+    occurrences (three chunks -> the last block's dup_final share; > 32 occurrences are summed in slot order, so 1e-6, not bits)."""
+    from cleverrec_b200.engine import Optimizer, Table
+    U, I, d, B, R = 400, 900, 64, 512, 2
+    data = synthetic_data(U, I, 12, seed=9)
+    eng.set_history(data.ui_train, U, I)
+    n_steps = -(-eng.epoch_rows(R) // B)
+    g = torch.Generator().manual_seed(4)
+    P0, Q0 = torch.randn(U, d, generator=g) * 0.1, torch.randn(I, d, generator=g) * 0.1
+    hub = (np.full(700, 3), np.full(700, 7), np.arange(100, 800))
+    out = []
+    for tail in ("0", "1"):
+        monkeypatch.setenv("CRB_DUP_TAIL", tail)
+        P, Q = Table(P0.clone().cuda(), kind, mode), Table(Q0.clone().cuda(), kind, mode)
+        opt = Optimizer(kind, 0.05 if kind != "Adam" else 0.01, adam_mode=mode)
+        got = []
+        l0 = eng.launches
+        for epoch in range(3):
+            losses = torch.zeros(n_steps, dtype=torch.float64, device="cuda")
+            eng.train_epoch_bpr(P, Q, opt, 5, epoch, 0, B, n_steps, R, 0.01, losses)
+            got.append(losses.cpu().numpy())
+        assert eng.launches - l0 == 3 * n_steps * (4 if tail == "1" else 6)
+        torch.cuda.synchronize()
+        snap = (np.concatenate(got), P.w.clone(), Q.w.clone())
+        hub_losses = [eng.train_step_bpr(P, Q, opt, *hub, reg=0.001) for _ in range(2)]
+        eng.adam_flush(P, opt); eng.adam_flush(Q, opt)
+        torch.cuda.synchronize()
+        out.append(snap + (np.array(hub_losses), P.w.clone(), Q.w.clone()))
+    monkeypatch.delenv("CRB_DUP_TAIL", raising=False)
+    assert np.array_equal(out[0][0], out[1][0])
+    assert torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
+    np.testing.assert_allclose(out[0][3], out[1][3], rtol=1e-5)
+    assert torch.allclose(out[0][4], out[1][4], rtol=1e-5, atol=1e-6) and torch.allclose(out[0][5], out[1][5], rtol=1e-5, atol=1e-6)
