@@ -40,7 +40,9 @@ __global__ void __launch_bounds__(256) assign_kernel(RoleArgs a, int64_t batch, 
     // One occurrence of every duplicated row has rank 1: it allocates the row's slot range, work items and partial rows.
     // (alloc_rank == 0 instead lets the FIRST occurrence allocate, i.e. every row gets a slot range -- the multi-GPU inbox.)
     // The five global counters live in one 32-byte sector, so every atomic on them serialises in one L2 slice: they are
-    // bumped once per BLOCK (warp scan -> scan of the 8 warp totals -> one atomic per counter), not once per row or warp.
+    // bumped once per BLOCK and round (a thread first adds up what its up to three roles need, then warp scan -> scan of the 8 warp
+    // totals -> one atomic per counter), not once per row, warp or role: at the batch sizes the reference ships the kernel is one round
+    // of 24 blocks and its duration is the atomics' round trip -- one now, three when the roles took turns.
     if (a.n_dev && (int64_t)*a.n_dev < batch) batch = (int64_t)*a.n_dev;
     __shared__ uint32_t s_tot[8][5];    // per-warp totals, then per-warp exclusive bases (global)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -48,56 +50,73 @@ __global__ void __launch_bounds__(256) assign_kernel(RoleArgs a, int64_t batch, 
     const int64_t rounds = (batch + stride - 1) / stride;
     for (int64_t it = 0; it < rounds; ++it) {
         const int64_t t = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        bool mine[3];
+        int32_t row[3];
+        uint32_t c[3], nch[3];
+        unsigned int* m[3];
+        bool any = false;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            if (r >= a.n_roles) continue;
-            const bool mine = t < batch && a.rank[r][t] == alloc_rank;
-            if (!__syncthreads_or(mine)) continue;   // block-uniform
-            int32_t row = 0;
-            uint32_t c = 0, nch = 0;
-            unsigned int* m = nullptr;
-            if (mine) {
-                row = a.idx[r][t];
-                m = reinterpret_cast<unsigned int*>(a.meta[r] + row);
-                c = m[0];
-                nch = (c + CRB_DUP_CHUNK - 1) / CRB_DUP_CHUNK;
-            }
-            const uint32_t pch = nch > 1 ? nch : 0u, one = mine ? 1u : 0u, mul = nch > 1 ? 1u : 0u;
-            // inclusive warp scans of (c, 1, nch, pch, mul)
-            uint32_t sc = c, s1 = one, sn = nch, sp = pch, sm = mul;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t tc = __shfl_up_sync(0xffffffffu, sc, o), t1 = __shfl_up_sync(0xffffffffu, s1, o);
-                const uint32_t tn = __shfl_up_sync(0xffffffffu, sn, o), tp = __shfl_up_sync(0xffffffffu, sp, o);
-                const uint32_t tm = __shfl_up_sync(0xffffffffu, sm, o);
-                if (lane >= o) { sc += tc; s1 += t1; sn += tn; sp += tp; sm += tm; }
-            }
-            if (lane == 31) { s_tot[wid][0] = sc; s_tot[wid][1] = s1; s_tot[wid][2] = sn; s_tot[wid][3] = sp; s_tot[wid][4] = sm; }
-            __syncthreads();
-            if (wid == 0 && lane < 5) {
-                // lane q owns counter q: exclusive prefix over the 8 warps, one atomic for the block
-                uint32_t pre[8], tot = 0;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) { pre[w] = tot; tot += s_tot[w][lane]; }
-                unsigned int* cp = lane == 0 ? &ctr->dup_slots : lane == 1 ? &ctr->dup_rows : lane == 2 ? &ctr->work_items
-                                   : lane == 3 ? &ctr->partial_slots : &ctr->multi_rows;
-                const uint32_t gb = tot ? atomicAdd(cp, tot) : 0u;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) s_tot[w][lane] = gb + pre[w];
-            }
-            __syncthreads();
-            const uint32_t bc = s_tot[wid][0], b1 = s_tot[wid][1], bn = s_tot[wid][2], bp = s_tot[wid][3], bm = s_tot[wid][4];
-            if (mine) {
-                const uint32_t base = bc + sc - c, k = b1 + s1 - 1u, wb = bn + sn - nch, pb = bp + sp - pch;
-                m[1] = base;
-                if (nch > 1) multi[bm + sm - 1u] = k;
-                crb_dup_row d;
-                d.row = row; d.table = a.table[r]; d.base = base; d.cnt = c; d.wbase = wb; d.nchunk = nch; d.pbase = pb; d.pad = 0;
-                dup_rows[k] = d;
-                for (uint32_t q = 0; q < nch; ++q) { crb_work w; w.dup = k; w.chunk = q; work[wb + q] = w; }
-            }
-            __syncthreads();   // s_tot is reused by the next role / round
+            mine[r] = r < a.n_roles && t < batch && a.rank[r][t] == alloc_rank;
+            row[r] = 0; c[r] = 0; nch[r] = 0; m[r] = nullptr;
+            any |= mine[r];
         }
+        if (!__syncthreads_or(any)) continue;   // block-uniform
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            if (mine[r]) {
+                row[r] = a.idx[r][t];
+                m[r] = reinterpret_cast<unsigned int*>(a.meta[r] + row[r]);
+                c[r] = m[r][0];
+                nch[r] = (c[r] + CRB_DUP_CHUNK - 1) / CRB_DUP_CHUNK;
+            }
+        }
+        // what this thread needs of each counter (slots, rows, work items, partial rows, multi-chunk rows), all roles together
+        uint32_t tc = 0, t1 = 0, tn = 0, tp = 0, tm = 0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            tc += c[r]; t1 += mine[r] ? 1u : 0u; tn += nch[r]; tp += nch[r] > 1 ? nch[r] : 0u; tm += nch[r] > 1 ? 1u : 0u;
+        }
+        // inclusive warp scans
+        uint32_t sc = tc, s1 = t1, sn = tn, sp = tp, sm = tm;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t uc = __shfl_up_sync(0xffffffffu, sc, o), u1 = __shfl_up_sync(0xffffffffu, s1, o);
+            const uint32_t un = __shfl_up_sync(0xffffffffu, sn, o), up = __shfl_up_sync(0xffffffffu, sp, o);
+            const uint32_t um = __shfl_up_sync(0xffffffffu, sm, o);
+            if (lane >= o) { sc += uc; s1 += u1; sn += un; sp += up; sm += um; }
+        }
+        if (lane == 31) { s_tot[wid][0] = sc; s_tot[wid][1] = s1; s_tot[wid][2] = sn; s_tot[wid][3] = sp; s_tot[wid][4] = sm; }
+        __syncthreads();
+        if (wid == 0 && lane < 5) {
+            // lane q owns counter q: exclusive prefix over the 8 warps, one atomic for the block
+            uint32_t pre[8], tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { pre[w] = tot; tot += s_tot[w][lane]; }
+            unsigned int* cp = lane == 0 ? &ctr->dup_slots : lane == 1 ? &ctr->dup_rows : lane == 2 ? &ctr->work_items
+                               : lane == 3 ? &ctr->partial_slots : &ctr->multi_rows;
+            const uint32_t gb = tot ? atomicAdd(cp, tot) : 0u;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s_tot[w][lane] = gb + pre[w];
+        }
+        __syncthreads();
+        // this thread's first slot / row / work item / partial row / multi-chunk entry; its roles take theirs in role order
+        uint32_t base = s_tot[wid][0] + sc - tc, k = s_tot[wid][1] + s1 - t1, wb = s_tot[wid][2] + sn - tn, pb = s_tot[wid][3] + sp - tp,
+                 mb = s_tot[wid][4] + sm - tm;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            if (mine[r]) {
+                const uint32_t pch = nch[r] > 1 ? nch[r] : 0u;
+                m[r][1] = base;
+                if (nch[r] > 1) multi[mb++] = k;
+                crb_dup_row d;
+                d.row = row[r]; d.table = a.table[r]; d.base = base; d.cnt = c[r]; d.wbase = wb; d.nchunk = nch[r]; d.pbase = pb; d.pad = 0;
+                dup_rows[k] = d;
+                for (uint32_t q = 0; q < nch[r]; ++q) { crb_work w; w.dup = k; w.chunk = q; work[wb + q] = w; }
+                base += c[r]; ++k; wb += nch[r]; pb += pch;
+            }
+        }
+        __syncthreads();   // s_tot is reused by the next round
     }
 }
 
