@@ -240,22 +240,28 @@ template <int LANES, int VPL, int OPT>
 __global__ void __launch_bounds__(256) dup_tail_kernel(const DupArgs a, const DupTail t) {
     OptDev o = a.opt;
     opt_resolve(o);
-    dup_reduce_body<LANES, VPL, OPT, false>(a, o);
-    __shared__ bool s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(&t.ctr->tail_done, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    dup_final_body<LANES, VPL, OPT, false>(a, o, threadIdx.x / LANES, blockDim.x / LANES);
-    if (threadIdx.x < 32) {
+    const uint32_t n_multi = a.ctr->multi_rows;   // final since K2; same sector as work_items, which dup_reduce_body reads next
+    // K5: the per-block loss partials are K3's, so any block may sum them at any time: the last block of the grid does it first (its
+    // lane groups are the ones without a work item when there are fewer duplicate rows than groups), in loss_final_kernel's order
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x < 32) {
         double v = 0.0;
         for (int k = threadIdx.x; k < t.n_block_loss; k += 32) v += t.block_loss[k];
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
         if (threadIdx.x == 0) *t.loss_out = v;
     }
-    __syncthreads();   // every thread of the block has read ctr->multi_rows
+    dup_reduce_body<LANES, VPL, OPT, false>(a, o);
+    __shared__ bool s_last;
+    if (n_multi) __threadfence();   // partial sums of multi-chunk rows must be visible to the block that finishes them
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&t.ctr->tail_done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    if (n_multi) {
+        __threadfence();
+        dup_final_body<LANES, VPL, OPT, false>(a, o, threadIdx.x / LANES, blockDim.x / LANES);
+        __syncthreads();   // every thread of the block has read ctr->multi_rows
+    }
+    // every block read the counters before it took its ticket: they can be zeroed for the step that uses this copy next
     if (threadIdx.x == 0) {
         t.ctr->dup_slots = 0; t.ctr->dup_rows = 0; t.ctr->work_items = 0; t.ctr->multi_rows = 0; t.ctr->partial_slots = 0;
         t.ctr->tail_done = 0;
