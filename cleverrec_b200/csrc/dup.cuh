@@ -139,7 +139,9 @@ __device__ __forceinline__ void dup_apply(const DupArgs& a, const OptDev& o, con
 // One lane group per work item (= one duplicate row, or one 256-slot chunk of a very frequent one).  The loop is software
 // pipelined: the next item's descriptors (work -> dup_rows, two dependent loads) are fetched while the current item's slots
 // and row are in flight, so a group's critical path per item is one memory round trip instead of four.
-template <int LANES, int VPL, int OPT, bool SHARD>
+// PDL: the kernel was launched with programmatic stream serialisation behind the step kernel (dup_tail_kernel): what K2 left (counters,
+// work list, row descriptors) is read at once, `griddepcontrol.wait` comes before the first access to anything the step kernel writes.
+template <int LANES, int VPL, int OPT, bool SHARD, bool PDL = false>
 __device__ __forceinline__ void dup_reduce_body(const DupArgs& a, const OptDev& o) {
     const int gl = threadIdx.x % LANES;
     const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
@@ -149,6 +151,7 @@ __device__ __forceinline__ void dup_reduce_body(const DupArgs& a, const OptDev& 
     if (k >= n_work) return;
     crb_work w = a.work[k];
     crb_dup_row d = a.dup_rows[w.dup];
+    if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
     while (true) {
         const int64_t kn = k + n_groups;
         const bool more = kn < n_work;
@@ -244,12 +247,13 @@ __global__ void __launch_bounds__(256) dup_tail_kernel(const DupArgs a, const Du
     // K5: the per-block loss partials are K3's, so any block may sum them at any time: the last block of the grid does it first (its
     // lane groups are the ones without a work item when there are fewer duplicate rows than groups), in loss_final_kernel's order
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x < 32) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         double v = 0.0;
         for (int k = threadIdx.x; k < t.n_block_loss; k += 32) v += t.block_loss[k];
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
         if (threadIdx.x == 0) *t.loss_out = v;
     }
-    dup_reduce_body<LANES, VPL, OPT, false>(a, o);
+    dup_reduce_body<LANES, VPL, OPT, false, true>(a, o);
     __shared__ bool s_last;
     if (n_multi) __threadfence();   // partial sums of multi-chunk rows must be visible to the block that finishes them
     __syncthreads();
@@ -257,6 +261,7 @@ __global__ void __launch_bounds__(256) dup_tail_kernel(const DupArgs a, const Du
     __syncthreads();
     if (!s_last) return;
     if (n_multi) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");   // threads without a work item have not waited yet
         __threadfence();
         dup_final_body<LANES, VPL, OPT, false>(a, o, threadIdx.x / LANES, blockDim.x / LANES);
         __syncthreads();   // every thread of the block has read ctr->multi_rows

@@ -200,11 +200,20 @@ int crb_launch_dup_pipeline(crb_handle* h, const DupArgs& a, int opt_kind, cudaS
 template <int LANES, int VPL>
 static int launch_dup_tail_t(crb_handle* h, const DupArgs& a, const DupTail& t, int opt_kind, cudaStream_t s) {
     const int grid = h->sm_count * 4;   // as dup_reduce_kernel: one lane group per duplicate row at the shapes this path serves
+    // Programmatic dependent launch behind the step kernel (which signals griddepcontrol.launch_dependents when it starts): the blocks
+    // of this kernel become resident as the step kernel's blocks retire and read the counters / work list / row descriptors -- K2's
+    // output -- while the step kernel's tail is still running; `griddepcontrol.wait` orders everything else.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
     switch (opt_kind) {
-        case OPT_SGD: dup_tail_kernel<LANES, VPL, OPT_SGD><<<grid, 256, 0, s>>>(a, t); break;
-        case OPT_ADAGRAD: dup_tail_kernel<LANES, VPL, OPT_ADAGRAD><<<grid, 256, 0, s>>>(a, t); break;
-        case OPT_ADAM_LAZY: dup_tail_kernel<LANES, VPL, OPT_ADAM_LAZY><<<grid, 256, 0, s>>>(a, t); break;
-        case OPT_ADAM_TF1: dup_tail_kernel<LANES, VPL, OPT_ADAM_TF1><<<grid, 256, 0, s>>>(a, t); break;
+        case OPT_SGD: CRB_CUDA(cudaLaunchKernelEx(&cfg, dup_tail_kernel<LANES, VPL, OPT_SGD>, a, t)); break;
+        case OPT_ADAGRAD: CRB_CUDA(cudaLaunchKernelEx(&cfg, dup_tail_kernel<LANES, VPL, OPT_ADAGRAD>, a, t)); break;
+        case OPT_ADAM_LAZY: CRB_CUDA(cudaLaunchKernelEx(&cfg, dup_tail_kernel<LANES, VPL, OPT_ADAM_LAZY>, a, t)); break;
+        case OPT_ADAM_TF1: CRB_CUDA(cudaLaunchKernelEx(&cfg, dup_tail_kernel<LANES, VPL, OPT_ADAM_TF1>, a, t)); break;
     }
     h->launches++;
     CRB_CUDA(cudaGetLastError());
@@ -318,6 +327,7 @@ template <int OPT> struct BprOcc { static constexpr int ctas = OPT == OPT_SGD ? 
 
 template <int LANES, int VPL, int OPT>
 __global__ void __launch_bounds__(256, BprOcc<OPT>::ctas) bpr_step_kernel(BprArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;");   // dup_tail_kernel (small batches) may start its prologue; no-op otherwise
     opt_resolve(a.opt);
     constexpr int GPW = 32 / LANES;
     const int lane = threadIdx.x & 31;
@@ -908,6 +918,7 @@ struct PwArgs {
 
 template <int LANES, int VPL, int OPT, bool GMF>
 __global__ void __launch_bounds__(256) pointwise_step_kernel(PwArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;");   // see bpr_step_kernel
     constexpr int GPW = 32 / LANES;
     __shared__ float4 s_h[GMF ? 256 * VPL : 1];
     const int lane = threadIdx.x & 31;
