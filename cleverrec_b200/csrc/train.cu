@@ -1012,13 +1012,14 @@ __global__ void __launch_bounds__(256) pointwise_step_kernel(PwArgs a) {
 }
 
 // TF dense apply of a small dense variable (ApplyGradientDescent / ApplyAdagrad / ApplyAdam) whose gradient arrives as
-// per-block partials [n_parts, n]; summed in block order (deterministic).
+// per-block partials [n_parts, n]; summed in a fixed order (block_sum_parts: deterministic).
 __global__ void __launch_bounds__(256) dense_apply_kernel(float* w, float* s1, float* s2, const float* parts, int n_parts, int n,
                                                          int opt_kind, OptDev o, int part_stride = 0) {
     const int64_t ps = part_stride > 0 ? part_stride : n;   // distance between consecutive partial vectors
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        float g = 0.f;
-        for (int p = 0; p < n_parts; ++p) g += parts[(int64_t)p * ps + k];
+    for (int k0 = blockIdx.x * 32; k0 < n; k0 += gridDim.x * 32) {
+        const int k = k0 + (threadIdx.x & 31);
+        const float g = block_sum_parts(parts, n_parts, ps, k, k < n);
+        if (threadIdx.x >= 32 || k >= n) continue;
         float x = w[k];
         if (opt_kind == OPT_SGD) {
             x = __fsub_rn(x, __fmul_rn(o.lr, g));
@@ -1039,7 +1040,7 @@ __global__ void __launch_bounds__(256) dense_apply_kernel(float* w, float* s1, f
 
 int crb_launch_dense_apply(crb_handle* h, float* w, float* s1, float* s2, const float* parts, int n_parts, int n, int opt_kind, const OptDev& od,
                            cudaStream_t s) {
-    dense_apply_kernel<<<1, 256, 0, s>>>(w, s1, s2, parts, n_parts, n, opt_kind == OPT_ADAM_TF1 ? OPT_ADAM_LAZY : opt_kind, od);
+    dense_apply_kernel<<<(n + 31) / 32, 256, 0, s>>>(w, s1, s2, parts, n_parts, n, opt_kind == OPT_ADAM_TF1 ? OPT_ADAM_LAZY : opt_kind, od);
     h->launches++;
     CRB_CUDA(cudaGetLastError());
     return CRB_OK;
@@ -1047,7 +1048,7 @@ int crb_launch_dense_apply(crb_handle* h, float* w, float* s1, float* s2, const 
 
 int crb_launch_dense_apply_strided(crb_handle* h, float* w, float* s1, float* s2, const float* parts, int n_parts, int n, int part_stride,
                                    int opt_kind, const OptDev& od, cudaStream_t s) {
-    dense_apply_kernel<<<1, 256, 0, s>>>(w, s1, s2, parts, n_parts, n, opt_kind == OPT_ADAM_TF1 ? OPT_ADAM_LAZY : opt_kind, od, part_stride);
+    dense_apply_kernel<<<(n + 31) / 32, 256, 0, s>>>(w, s1, s2, parts, n_parts, n, opt_kind == OPT_ADAM_TF1 ? OPT_ADAM_LAZY : opt_kind, od, part_stride);
     h->launches++;
     CRB_CUDA(cudaGetLastError());
     return CRB_OK;
@@ -1130,7 +1131,7 @@ static int pointwise_step_device(crb_handle* h, bool gmf, const crb_table* P, co
     const bool tail = crb_dup_tail_enabled(batch);
     if ((rc = tail ? crb_launch_dup_tail(h, d, opt_kind, loss_dev, s) : crb_launch_dup_pipeline(h, d, opt_kind, s))) return rc;
     if (gmf) {
-        dense_apply_kernel<<<1, 256, 0, s>>>(hvec, h_s1, h_s2, h->dense_grad, h->step_grid, P->dim, opt_kind == OPT_ADAM_TF1 ? OPT_ADAM_LAZY : opt_kind, od);
+        dense_apply_kernel<<<(P->dim + 31) / 32, 256, 0, s>>>(hvec, h_s1, h_s2, h->dense_grad, h->step_grid, P->dim, opt_kind == OPT_ADAM_TF1 ? OPT_ADAM_LAZY : opt_kind, od);
         h->launches++;
         CRB_CUDA(cudaGetLastError());
     }

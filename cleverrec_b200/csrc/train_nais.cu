@@ -211,9 +211,10 @@ __global__ void __launch_bounds__(NA_WARPS * 32) nais_target_kernel(NaisArgs a) 
 
 __global__ void __launch_bounds__(256) nais_dense_apply_kernel(float* w, float* s1, float* s2, const float* parts, int n_parts, int n,
                                                               int opt_kind, OptDev o) {
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        float g = 0.f;
-        for (int p = 0; p < n_parts; ++p) g += parts[(int64_t)p * n + k];
+    for (int k0 = blockIdx.x * 32; k0 < n; k0 += gridDim.x * 32) {
+        const int k = k0 + (threadIdx.x & 31);
+        const float g = block_sum_parts(parts, n_parts, n, k, k < n);
+        if (threadIdx.x >= 32 || k >= n) continue;
         float x = w[k];
         if (opt_kind == OPT_SGD) {
             x -= o.lr * g;
@@ -303,7 +304,7 @@ extern "C" int crb_train_step_nais(crb_handle* h, const crb_table* P, const crb_
     const crb_table* tabs3[3] = {P, Q, &Bt};
     float* grads3[3] = {gradP, gradQ, gradB};
     if ((rc = crb_dense_tables_apply(h, 3, tabs3, grads3, dk, od, s))) return rc;
-    nais_dense_apply_kernel<<<(n_dense + 255) / 256, 256, 0, s>>>(dense, dense_s1, dense_s2, a.dense_part, grid_p, n_dense, dk, od);
+    nais_dense_apply_kernel<<<(n_dense + 31) / 32, 256, 0, s>>>(dense, dense_s1, dense_s2, a.dense_part, grid_p, n_dense, dk, od);
     h->launches++;
     h->step_grid = grid_t;
     double* ld = (loss_out && crb_is_device_ptr(loss_out)) ? loss_out : h->loss_dev;

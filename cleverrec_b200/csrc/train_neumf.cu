@@ -439,9 +439,10 @@ static bool try_launch_neumf_tile(const NeumfArgs& a, int grid, cudaStream_t s, 
 // TF dense apply of a packed dense vector from per-CTA partial gradients (fixed summation order)
 __global__ void __launch_bounds__(256) dense_vector_apply_kernel(float* w, float* s1, float* s2, const float* parts, int n_parts, int n,
                                                                 int opt_kind, OptDev o) {
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        float g = 0.f;
-        for (int p = 0; p < n_parts; ++p) g += parts[(int64_t)p * n + k];
+    for (int k0 = blockIdx.x * 32; k0 < n; k0 += gridDim.x * 32) {
+        const int k = k0 + (threadIdx.x & 31);
+        const float g = block_sum_parts(parts, n_parts, n, k, k < n);
+        if (threadIdx.x >= 32 || k >= n) continue;
         float x = w[k];
         if (opt_kind == OPT_SGD) {
             x -= o.lr * g;
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(256) dense_vector_apply_kernel(float* w, float
 // shared with train_lrml.cu
 int crb_dense_vector_apply(crb_handle* h, float* w, float* s1, float* s2, const float* parts, int n_parts, int n, int opt_kind, const OptDev& od,
                            cudaStream_t s) {
-    dense_vector_apply_kernel<<<(n + 255) / 256, 256, 0, s>>>(w, s1, s2, parts, n_parts, n, opt_kind, od);
+    dense_vector_apply_kernel<<<(n + 31) / 32, 256, 0, s>>>(w, s1, s2, parts, n_parts, n, opt_kind, od);
     h->launches++;
     CRB_CUDA(cudaGetLastError());
     return CRB_OK;
@@ -653,7 +654,7 @@ extern "C" int crb_train_step_neumf(crb_handle* h, const crb_table* Pg, const cr
     const crb_table* tabs[4] = {Pg, Qg, Pm, Qm};      // NULL entries (the MLP model has no GMF branch) are skipped
     float* grads[4] = {gPg, gQg, gPm, gQm};
     if ((rc = crb_dense_tables_apply(h, 4, tabs, grads, dk, od, s))) return rc;
-    dense_vector_apply_kernel<<<(a.sh.n_dense + 255) / 256, 256, 0, s>>>(dense, dense_s1, dense_s2, h->dense_grad, grid, a.sh.n_dense, dk, od);
+    dense_vector_apply_kernel<<<(a.sh.n_dense + 31) / 32, 256, 0, s>>>(dense, dense_s1, dense_s2, h->dense_grad, grid, a.sh.n_dense, dk, od);
     h->step_grid = grid;
     h->launches += 2;
     double* ld = (loss_out && crb_is_device_ptr(loss_out)) ? loss_out : h->loss_dev;
