@@ -94,10 +94,12 @@ def main():
         m.train_model()                                   # warm epoch (allocations, first-launch costs)
         torch.cuda.synchronize()
         gc.collect()                                      # keep a generation-2 collection of earlier models' objects out of the timed regions
+        l0 = m.engine.launches
         t0 = time.perf_counter()
         loss = m.train_model()
         torch.cuda.synchronize()
         epoch_s = time.perf_counter() - t0
+        epoch_launches = m.engine.launches - l0
         m.test_model_loo()
         torch.cuda.synchronize()
         gc.collect()
@@ -109,6 +111,12 @@ def main():
         rec = {"model": name, "shape": shape, "conf": conf, "rows_per_epoch": rows, "steps_per_epoch": (len(data.ui_train) if name == 'NAIS_single' else math.ceil(rows / 6144)),
                "setup_s": setup, "epoch_s": epoch_s, "rows_per_s": rows / epoch_s, "loo_eval_s": eval_s, "loo_eval_users_per_s": len(m.test_users) / eval_s,
                "loss": loss, "hr10": float(np.mean(HR[0]))}
+        # what bounds an epoch at these shapes: the step is a chain of dependent microsecond kernels (the tables are L2-resident), so
+        # the floor of a step is (library kernels per step) x (one dependent launch + one L2 round trip ~ 2.5 us), not bytes / bandwidth
+        steps = rec["steps_per_epoch"]
+        rec["us_per_step"] = 1e6 * epoch_s / steps
+        rec["library_kernels_per_step"] = epoch_launches / steps
+        rec["launch_chain_floor_us_per_step"] = 2.5 * epoch_launches / steps
         out.append(rec)
         sys.stderr.write("%-12s epoch %.3f s (%.3e rows/s, %d steps)  loo eval %.3f s\n" % (name, epoch_s, rec["rows_per_s"], rec["steps_per_epoch"], eval_s))
         m.engine.close()
