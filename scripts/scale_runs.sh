@@ -21,6 +21,9 @@ case "$1" in
     run 8 n8_d64 --steps 20 --warmup 5 --dim 64 --no-cpu-baseline --no-eval-full --phases
     run 8 n8_zipf --steps 20 --warmup 5 --item-popularity zipf --no-cpu-baseline --eval-users 0 --phases
     ;;
+  eight_full)
+    run 8 n8_full --steps 20 --warmup 5
+    ;;
   four)
     run 4 n4 --steps 20 --warmup 5 --no-cpu-baseline --no-eval-full --phases
     ;;
