@@ -1104,12 +1104,12 @@ static int pointwise_checks(crb_handle* h, int32_t kind, const crb_table* P, con
 // K2 .. K5 of one pointwise step; `counted`: the sampler already bumped the multiplicities (K1)
 static int pointwise_step_device(crb_handle* h, bool gmf, const crb_table* P, const crb_table* Q, float* hvec, float* h_s1, float* h_s2,
                                  const OptDev& od, int opt_kind, int32_t loss_kind, const int32_t* du, const int32_t* di, const float* dy,
-                                 int64_t batch, float reg, bool counted, double* loss_dev, cudaStream_t s) {
+                                 int64_t batch, float reg, bool counted, double* loss_dev, cudaStream_t s, bool assigned = false) {
     int rc;
     const int32_t* idx[3] = {du, di, nullptr};
     const int role_table[3] = {0, 1, 0};
     if (!counted && (rc = crb_count_rows(h, batch, 2, idx, role_table, s))) return rc;
-    if ((rc = crb_launch_assign(h, batch, 2, idx, role_table, s))) return rc;
+    if (!assigned && (rc = crb_launch_assign(h, batch, 2, idx, role_table, s))) return rc;
     PwArgs a;
     a.P = crb_to_dev(P); a.Q = crb_to_dev(Q);
     a.metaU = h->meta[0]; a.metaI = h->meta[1];
@@ -1179,18 +1179,49 @@ extern "C" int crb_train_epoch_pointwise(crb_handle* h, int32_t kind, const crb_
     CRB_CHECK_ARG(first >= 0 && first < rows, "first row outside the epoch");
     const bool host_loss = !(loss_out && crb_is_device_ptr(loss_out));
     crb_opt step_opt = *opt;
+    // As in crb_train_epoch_bpr: step k's sampler and slot assignment run on the auxiliary stream into copy k & 1 of the step state
+    // while step k-1's K3 / tail / dense apply run on the caller's stream from the other copy.  The labels travel in the copy's third
+    // index buffer (unused by a two-role step; same size, reinterpreted as float), so they are double-buffered with the indices.
+    const bool overlap = n_steps > 1;
+    struct Restore { crb_handle* h; ~Restore() { if (h->alt_active) crb_alt_swap(h); } } restore{h};
+    cudaStream_t ps = s;
+    if (overlap) {
+        if ((rc = crb_alt_reserve(h, s))) return rc;
+        ps = h->aux_stream;
+        CRB_CUDA(cudaEventRecord(h->ev_entry, s));
+        CRB_CUDA(cudaStreamWaitEvent(ps, h->ev_entry, 0));
+    }
     for (int64_t k = 0; k < n_steps; ++k) {
         const int64_t lo = first + k * batch;
         if (lo >= rows) { crb_set_error("step %lld starts past the end of the epoch", (long long)k); return CRB_ERR_ARG; }
         const int64_t b = (rows - lo) < batch ? (rows - lo) : batch;
+        const int set = (int)(k & 1);
+        if (overlap && h->alt_active != set) crb_alt_swap(h);
         step_opt.step = opt->step + k;
         if ((rc = crb_opt_to_dev(h, &step_opt, &od, &opt_kind, s))) return rc;
-        if ((rc = crb_zero_step_counters(h, s))) return rc;
-        if ((rc = crb_launch_sample_pointwise(h, seed, epoch, lo, b, neg_ratio, h->idx[0], h->idx[1], h->yv, true, s))) return rc;
+        if (overlap && k >= 2) CRB_CUDA(cudaStreamWaitEvent(ps, h->ev_done[set], 0));
+        if ((rc = crb_zero_step_counters(h, ps))) return rc;
+        float* labels = reinterpret_cast<float*>(h->idx[2]);
+        if ((rc = crb_launch_sample_pointwise(h, seed, epoch, lo, b, neg_ratio, h->idx[0], h->idx[1], labels, true, ps))) return rc;
+        {
+            const int32_t* idx[3] = {h->idx[0], h->idx[1], nullptr};
+            const int role_table[3] = {0, 1, 0};
+            if ((rc = crb_launch_assign(h, b, 2, idx, role_table, ps))) return rc;
+        }
+        if (overlap) {
+            CRB_CUDA(cudaEventRecord(h->ev_prep[set], ps));
+            CRB_CUDA(cudaStreamWaitEvent(s, h->ev_prep[set], 0));
+        }
         double* ld = host_loss ? h->loss_dev + k : loss_out + k;
-        if ((rc = pointwise_step_device(h, kind == CRB_SCORE_GMF, P, Q, hvec, h_s1, h_s2, od, opt_kind, loss_kind, h->idx[0], h->idx[1], h->yv, b, reg,
-                                        true, ld, s)))
+        if ((rc = pointwise_step_device(h, kind == CRB_SCORE_GMF, P, Q, hvec, h_s1, h_s2, od, opt_kind, loss_kind, h->idx[0], h->idx[1], labels, b, reg,
+                                        true, ld, s, true)))
             return rc;
+        if (overlap) CRB_CUDA(cudaEventRecord(h->ev_done[set], s));
+    }
+    if (overlap) {   // the sampler's sticky error word lives in the step counters: fold the alternate copy's into the primary's
+        if (h->alt_active) crb_alt_swap(h);
+        merge_sampler_err_kernel<<<1, 1, 0, s>>>(h->ctr, h->alt.ctr);
+        CRB_CUDA(cudaGetLastError());
     }
     if (loss_out && host_loss) {
         if ((rc = finish_loss(h, loss_out, n_steps, s))) return rc;
