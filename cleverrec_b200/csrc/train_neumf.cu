@@ -612,12 +612,20 @@ extern "C" int crb_train_step_neumf(crb_handle* h, const crb_table* Pg, const cr
     CRB_CHECK_ARG(dk != OPT_ADAM_LAZY || dense_s2, "dense slot s2 is NULL");
     CRB_CUDA(cudaSetDevice(h->device));
     if ((rc = crb_ws_reserve(h, batch, 4, 4, s))) return rc;
-    // towers with a tiled instantiation (register-resident weight gradients): one CTA per SM, tiles of NM_WARPS samples
+    // towers with a tiled instantiation (register-resident weight gradients): up to three CTAs per SM, tiles of NM_WARPS samples
     const bool tiled = (a.sh.L0 == 128 || a.sh.L0 == 64 || a.sh.L0 == 32) && a.sh.n_layers >= 2 && a.sh.n_layers <= (a.sh.L0 == 32 ? 3 : 4) &&
                        !getenv("CRB_NEUMF_GENERIC");
     int grid = (int)((batch + 63) / 64);
     if (grid > h->sm_count * 2) grid = h->sm_count * 2;
-    if (tiled) { grid = (int)((batch + NM_WARPS - 1) / NM_WARPS); if (grid > h->sm_count) grid = h->sm_count; }
+    if (tiled) {
+        // CTAs per SM: 79 registers x 256 threads and ~60 KB of shared memory leave room for three, and a CTA is a chain of tiles (8 warps,
+        // one sample each, dependent dot-product chains) that needs company to hide its latencies: 1 -> 3 CTAs per SM took the NeuMF
+        // epoch at the ml-1m shape from 136 to 109 ms (more CTAs = more per-CTA partials for the dense apply, which is why not more)
+        int per_sm = 3;
+        if (const char* e = getenv("CRB_NEUMF_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 4) per_sm = v; }
+        grid = (int)((batch + NM_WARPS - 1) / NM_WARPS);
+        if (grid > h->sm_count * per_sm) grid = h->sm_count * per_sm;
+    }
     if (grid < 1) grid = 1;
     // dense workspace: per-CTA partials
     const int64_t need = (int64_t)grid * a.sh.n_dense;
