@@ -2,6 +2,7 @@
 one call into libcleverrec_b200.so.  This is the replacement for the reference's `tf.Session` (main.py:39-45):
 the mirror classes under cleverrec_b200/model call it where the reference calls `self.sess.run`."""
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
@@ -618,6 +619,7 @@ class Engine(object):
         if hist_users is not None:
             hist_users = self._feed_i32(hist_users)
         n_items = Q.shape[0] if n_items is None else n_items
+        self._eval_cache_guard(Q, hvec)
         if host:
             items = np.empty((n, K), dtype=np.int32)
             scores = np.empty((n, K), dtype=np.float32) if return_scores else None
@@ -627,6 +629,30 @@ class Engine(object):
         check(self.lib.crb_score_topk(self.h, kind, ptr(P), ptr(Q), ptr(hvec), n_items, P.shape[1], ptr(users), ptr(hist_users), n, K,
                                       1 if exact else 0, ptr(items), ptr(scores), self.stream))
         return (items, scores) if return_scores else items
+
+    def _eval_cache_guard(self, Q, hvec):
+        """The library keys its cached bf16 item table by ADDRESS (Q, hvec, sizes, kind) and drops it whenever one of its own calls writes
+        a table.  What it cannot see is torch: an in-place op on Q (or on any view of it) and a table that was freed and whose address the
+        caching allocator handed to the next one.  Both are visible here -- the version counter of the tensor (shared by its views) and
+        the identity of the object that owns the memory -- so the copy is dropped for them too.  Anything unexpected drops it as well:
+        a spurious conversion costs 2 ms at 2M items, a stale one returns another table's ranking."""
+        try:
+            sig = []
+            for t in (Q, hvec):
+                if t is None:
+                    sig.append(None)
+                    continue
+                base = t._base if t._base is not None else t
+                sig.append((weakref.ref(base), base._version))
+            prev = getattr(self, "_evq_sig", None)
+            same = prev is not None and all(
+                (a is None and b is None) or (a is not None and b is not None and a[0]() is b[0]() and a[0]() is not None and a[1] == b[1])
+                for a, b in zip(prev, sig))
+            self._evq_sig = sig
+        except Exception:
+            same, self._evq_sig = False, None
+        if not same:
+            self.invalidate_eval_cache()
 
     def invalidate_eval_cache(self):
         """score_topk keeps the bf16 copy of the item table between calls; library calls that write tables drop it themselves.

@@ -150,8 +150,8 @@ def test_score_pairs_topk_fused_bit_exact(eng, kind, d):
 
 def test_fullrank_item_table_cache_tracks_writes(eng):
     """The tensor-core path keeps its bf16 copy of Q between calls (the reference's test.batch_size loop ranks users in many small
-    calls): a second call with the same table skips the conversion, a training step through the library drops the copy, a torch
-    write needs invalidate_eval_cache().  Every result equals the oracle on the CURRENT table."""
+    calls): a second call with the same table skips the conversion, a training step through the library drops the copy, so does a torch
+    in-place write (the engine watches the tensor's version counter; invalidate_eval_cache() is for writes torch cannot see).  Every result equals the oracle on the CURRENT table."""
     from cleverrec_b200.engine import Optimizer, Table
     d = synthetic_data(120, 2500, 40, seed=21)
     pu, pi, rp, sc = X.build_history(d.ui_train, d.user_nums)
@@ -177,6 +177,9 @@ def test_fullrank_item_table_cache_tracks_writes(eng):
     Q.w.mul_(-1.0)
     eng.invalidate_eval_cache()
     assert check_now() == first
+    Q.w[:100].mul_(0.5)                                   # no explicit call: the engine sees torch's version counter move (views share it)
+    assert check_now() == first
+    assert check_now() == first - 1
 
 
 def test_fullrank_topk_beyond_32(eng):

@@ -60,3 +60,36 @@ def test_checkpoint_helpers_round_trip(tmp_path):
     assert set(v) == {"GMF_params/P", "GMF_params/h_gmf"} and v["GMF_params/P"].dtype == np.float32
     assert v["GMF_params/P"].tolist() == [[0.0, 1.0, 2.0], [3.0, 4.0, 5.0]]
 
+
+
+def test_eval_cache_guard_drops_the_cached_item_table_on_torch_writes_and_reallocation():
+    """Engine.score_topk's guard (no GPU needed: the library call is a stub).  The C side keys its bf16 copy of the item table by
+    address; torch in-place writes (also through views) and a new tensor at a recycled address must drop it, repeated calls must not."""
+    import torch
+    from cleverrec_b200.engine import Engine
+
+    class Lib(object):
+        drops = 0
+
+        def crb_eval_cache_invalidate(self, h):
+            Lib.drops += 1
+            return 0
+    e = Engine.__new__(Engine)
+    e.lib, e.h = Lib(), 1
+    try:
+        Q, hv = torch.zeros(10, 4), torch.zeros(4)
+        steps = [
+            (lambda: (Q, None), 1), (lambda: (Q, None), 1), (lambda: (Q[:5], None), 1),        # first use; same table; a view of it
+            (lambda: (Q.mul_(2), None), 2), (lambda: (Q, None), 2),                          # in-place write
+            (lambda: (Q[:3].add_(1)._base, None), 3),                                        # write through a view
+            (lambda: (Q, hv), 4), (lambda: (Q, hv), 4), (lambda: (Q, hv.add_(1)), 5),        # hvec joins the key
+            (lambda: (torch.zeros(10, 4), hv), 6), (lambda: (torch.zeros(10, 4), hv), 7),    # new tables (possibly at a recycled address)
+        ]
+        for make, want in steps:
+            q, h = make()
+            e._eval_cache_guard(q, h)
+            assert Lib.drops == want
+        e._eval_cache_guard(object(), None)      # not a tensor: dropped, not raised
+        assert Lib.drops == 8
+    finally:
+        e.h = None
