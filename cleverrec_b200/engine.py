@@ -257,7 +257,7 @@ class Engine(object):
     def _feed_i32(x):
         """Feeds may be host (NumPy / list, like a TF feed_dict) or device tensors; the library stages host buffers."""
         if isinstance(x, torch.Tensor):
-            return x if x.dtype == torch.int32 else x.to(torch.int32)
+            return x if x.dtype == torch.int32 and x.is_contiguous() else x.to(torch.int32).contiguous()   # e.g. a column of an [n, 3] tensor
         return np.ascontiguousarray(np.asarray(x), dtype=np.int32)
 
     def train_step_bpr(self, P, Q, opt, u, i, j, reg, loss_out=None):
