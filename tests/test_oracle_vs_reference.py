@@ -96,3 +96,132 @@ def test_packaged_preprocess_equals_the_reference_class_over_its_config_space(ca
             assert list(a.keys()) == list(b.keys())
             for u in b:
                 assert list(a[u]) == list(b[u]), (u, lazy)
+
+
+# ---- the packaged evaluation loops' HOST code against the genuine reference loops, on the same scores -------------------------------
+def _pos_scores(u, n):
+    """Distinct scores for the n candidates of user u, by position (a candidate list may hold the same item twice)."""
+    return np.random.RandomState(1000 + int(u)).permutation(n).astype(np.float32)
+
+
+def _full_scores(u, n_items):
+    return np.random.RandomState(5000 + int(u)).permutation(n_items).astype(np.float32)
+
+
+class _RefSession(object):
+    """What the reference loops call as self.sess.run(self.pre_scores, feed) (RankingRecommender.py:221,278)."""
+
+    def __init__(self, item_nums):
+        self.item_nums = item_nums
+
+    def run(self, fetches, feed):
+        users = list(feed["u_idx"])
+        if "i_idx" not in feed:
+            return np.stack([_full_scores(u, self.item_nums) for u in users])
+        out, k = [], 0
+        while k < len(users):            # a batch's users are distinct: one run of equal ids per user
+            e = k
+            while e < len(users) and users[e] == users[k]:
+                e += 1
+            out.append(_pos_scores(users[k], e - k))
+            k = e
+        return np.concatenate(out)
+
+
+class _StubEngine(object):
+    """Stands where the device library stands in the packaged class: top-K positions / ids from the same scores, ranked with the
+    library's documented order (score, then index ascending).  The scores are distinct, so this is np.argsort's order too."""
+
+    def __init__(self, data):
+        import torch
+        self.torch, self.device, self.data = torch, torch.device("cpu"), data
+
+    def score_pairs_topk(self, kind, P, Q, seg_users, items, offsets, K, hvec=None, ascending=False):
+        n = len(offsets) - 1
+        out = np.full((n, K), -1, dtype=np.int32)
+        for s in range(n):
+            sc = _pos_scores(int(seg_users[s]), int(offsets[s + 1] - offsets[s]))
+            order = np.argsort(sc if ascending else -sc, kind="stable")[:K]
+            out[s, :order.shape[0]] = order
+        return self.torch.from_numpy(out)
+
+    def score_topk(self, kind, P, Q, rows, K, hvec=None, hist_users=None, exact=False, n_items=None, ascending=False):
+        out = np.full((len(rows), K), -1, dtype=np.int32)
+        for r, u in enumerate(np.asarray(rows).tolist()):
+            sc = _full_scores(u, n_items)
+            seen = set(self.data.ui_train.get(u, []))
+            keep = [i for i in np.argsort(sc if ascending else -sc, kind="stable").tolist() if i not in seen][:K]
+            out[r, :len(keep)] = keep
+        return out
+
+
+def _packaged_driver(data, cfg, cml_like):
+    from cleverrec_b200.model.RankingRecommender import RankingRecommender
+
+    class Model(RankingRecommender):
+        def _score_spec(self):
+            return (1 if cml_like else 0), None, None, None
+    m = object.__new__(Model)
+    m.data, m.configs, m.engine = data, cfg, _StubEngine(data)
+    m.neg_samples, m.topk, m.cml_like, m.fism_like = int(cfg["test.neg_samples"]), list(map(int, cfg["topk"][1:-1].split(","))), cml_like, False
+    m.batch_size_t, m.score_exact = int(cfg["test.batch_size"]), False
+    m.test_users = list(data.ui_test.keys())
+    m._test_cache = None
+    return m
+
+
+def _assert_same_metrics(got, want, n_topk):
+    for a, b in zip(got, want):
+        for k in range(n_topk):
+            assert a[k] == b[k]          # lists of Python floats, one per test user, in test_users order: bit-equal
+
+
+@pytest.mark.parametrize("cml_like", [False, True])
+def test_packaged_loo_loop_host_code_equals_the_reference_loop(split_loo, cml_like):
+    cfg = R.default_configs(**{"data.split_way": "loo", "test.neg_samples": 99, "topk": "[5,10,20]", "test.batch_size": 100})
+    if cml_like:
+        cfg["cml_like"] = "True"
+    ref = R.make_driver(cfg, split_loo, _RefSession(split_loo.item_nums))
+    want = ref.test_model_loo()
+    got = _packaged_driver(split_loo, cfg, cml_like).test_model_loo()
+    _assert_same_metrics(got, want, 3)
+    assert len(got[0][0]) == len(split_loo.ui_test) and 0.0 < np.mean(got[0][2]) < 1.0
+
+
+def test_packaged_rs_loop_host_code_equals_the_reference_loop(split_rs):
+    cfg = R.default_configs(**{"data.split_way": "rs", "test.neg_samples": 0, "topk": "[10,20]", "test.batch_size": 128})
+    users = list(split_rs.ui_test.keys())[:150]
+    data = Data(split_rs.user_nums, split_rs.item_nums, split_rs.ui_train, {u: split_rs.ui_test[u] for u in users})
+    ref = R.make_driver(cfg, data, _RefSession(data.item_nums))
+    want = ref.test_model_rs()
+    got = _packaged_driver(data, cfg, False).test_model_rs()
+    _assert_same_metrics(got, want, 2)
+
+
+def test_packaged_loo_loop_with_several_real_items_per_user(tmp_path):
+    """data.split_way=rs with test.neg_samples > 0 goes through test_model_loo with a LIST of real items per user
+    (RankingRecommender.py:283-285, :415) -- on a split produced by the genuine preprocessing."""
+    import logging
+    ref = R.load()
+    d = tmp_path / "toy"
+    d.mkdir()
+    _write_log(str(d / "log.csv"), np.random.RandomState(77), "UI", 80, 400, 900, "dense")
+    cfg = R.default_configs(**{"data.root_dir": str(tmp_path), "data.dataset": "toy", "data.file_name": "log.csv", "data.sep": ",", "data.format": "UI",
+                               "data.user_min": 0, "data.item_min": 0, "data.split_way": "rs", "data.split_by_time": "False",
+                               "data.split_ratio": "[0.6,0.1,0.3]", "test.neg_samples": 30, "topk": "[5,10]", "test.batch_size": 16})
+    np.random.seed(9)
+    data = ref.RankingPreprocess(dict(cfg), logging.getLogger("t"))
+    assert max(len(v) for v in data.ui_test.values()) > 32
+    want = R.make_driver(cfg, data, _RefSession(data.item_nums)).test_model_loo()
+    got = _packaged_driver(data, cfg, False).test_model_loo()
+    _assert_same_metrics(got, want, 2)
+
+
+def test_packaged_loo_loop_with_fewer_candidates_than_k(split_loo):
+    """test.neg_samples + 1 < topk[-1]: the reference ranks the few candidates there are (argsort[:K] is just shorter)."""
+    users = list(split_loo.ui_test.keys())[:200]
+    data = Data(split_loo.user_nums, split_loo.item_nums, split_loo.ui_train, {u: split_loo.ui_test[u][-4:] for u in users})
+    cfg = R.default_configs(**{"data.split_way": "loo", "test.neg_samples": 3, "topk": "[2,5,10]", "test.batch_size": 64})
+    want = R.make_driver(cfg, data, _RefSession(data.item_nums)).test_model_loo()
+    got = _packaged_driver(data, cfg, False).test_model_loo()
+    _assert_same_metrics(got, want, 3)
