@@ -225,3 +225,72 @@ def test_packaged_loo_loop_with_fewer_candidates_than_k(split_loo):
     want = R.make_driver(cfg, data, _RefSession(data.item_nums)).test_model_loo()
     got = _packaged_driver(data, cfg, False).test_model_loo()
     _assert_same_metrics(got, want, 3)
+
+
+# ---- model constructors: the shipped conf/<Model>.properties parsed by the genuine classes and by the packaged ones --------------------
+class _AnyLib(object):
+    """Every C entry point 'succeeds' without doing anything: constructors only install the history (no compute on the CPU)."""
+
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        def f(*a, **k):
+            self.calls.append(name)
+            return 0
+        return f
+
+
+def _stub_engine():
+    import torch
+    from cleverrec_b200.engine import Engine
+
+    class Stub(Engine):
+        stream = None
+
+        def __init__(self):
+            self.device, self.h, self.lib, self._hist = torch.device("cpu"), None, _AnyLib(), None
+    return Stub()
+
+
+_SHARED = ("embed_size", "reg", "reg1", "reg2", "reg_bias", "margin", "alpha", "beta", "atten_size", "atten_type", "mem_size", "neg_ratio",
+           "neg_samples", "topk", "T", "epoches", "batch_size", "batch_size_t", "lr", "is_pairwise", "fism_like", "cml_like", "model",
+           "test_users", "test_batches", "model_params", "loss_func")
+
+
+@pytest.mark.parametrize("name", ["BPR", "MF", "GMF", "MLP", "NeuMF", "CML", "FISM", "NAIS_single", "TransCF", "LRML", "SBPR"])
+def test_model_constructors_read_the_shipped_conf_like_the_reference(split_loo, name):
+    """Every packaged model class is constructed from the reference's OWN CleverRec.properties + conf/<name>.properties (the flat
+    str dict of main.py:18-25); where the genuine class can be constructed too (TensorFlow stubbed: no graph is built in __init__),
+    every hyper-parameter both hold is equal, as is the parameter string run_model logs.  The reference's GMF / MLP / NeuMF cannot be
+    constructed from their shipped conf files (KeyError 'reg' / 'reg1': SURVEY 2.3) and MF has no reference source (F6)."""
+    import importlib
+    import logging
+    import sys
+    from cleverrec_b200.main import load_configs
+    R.load()
+    data = Data(split_loo.user_nums, split_loo.item_nums, split_loo.ui_train, split_loo.ui_test)
+    data.user_friends = {0: [1, 2], 1: [0]}
+    cfg = load_configs(R.REFERENCE_ROOT, {"recommender": name})
+    assert cfg == R.default_configs(recommender=name)
+    eng = _stub_engine()
+    ours = getattr(importlib.import_module("cleverrec_b200.model.ranking." + name), name)(eng, data, dict(cfg), logging.getLogger("t"))
+    assert "crb_set_history" in eng.lib.calls and ours.engine is eng
+    if name == "MF":
+        return
+    sys.path.insert(0, R.REFERENCE_ROOT)
+    try:
+        cls = getattr(importlib.import_module("model.ranking." + name), name)
+    finally:
+        sys.path.remove(R.REFERENCE_ROOT)
+    if name in ("GMF", "MLP", "NeuMF"):
+        with pytest.raises(KeyError):
+            cls(None, data, dict(cfg), logging.getLogger("t"))
+        return
+    theirs = cls(None, data, dict(cfg), logging.getLogger("t"))
+    compared = 0
+    for k in _SHARED:
+        if hasattr(theirs, k) and hasattr(ours, k):
+            assert getattr(ours, k) == getattr(theirs, k), k
+            compared += 1
+    assert compared >= 18
