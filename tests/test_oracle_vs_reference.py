@@ -294,3 +294,73 @@ def test_model_constructors_read_the_shipped_conf_like_the_reference(split_loo, 
             assert getattr(ours, k) == getattr(theirs, k), k
             compared += 1
     assert compared >= 18
+
+
+# ---- run_model: epoch orchestration, test interval, best-by-NDCG@topk[0], log lines -----------------------------------------------------
+class _ListHandler(object):
+    def __init__(self):
+        self.lines = []
+
+    def info(self, msg):
+        self.lines.append(msg)
+
+
+def _scripted(cls_or_obj, losses, metrics):
+    """train_model / test_model_* replaced by scripts, build_model by a no-op: what is left is run_model's own logic."""
+    from collections import defaultdict
+    state = {"epoch": 0, "tests": 0}
+
+    def train_model():
+        state["epoch"] += 1
+        return losses[state["epoch"] - 1]
+
+    def test_model(which):
+        def f():
+            HR, MRR, NDCG = defaultdict(list), defaultdict(list), defaultdict(list)
+            vals = metrics[state["tests"]]
+            state["tests"] += 1
+            for kid, (h, m, n) in enumerate(vals):
+                HR[kid].extend([h, h]); MRR[kid].extend([m, m]); NDCG[kid].extend([n, n])
+            state.setdefault("called", []).append(which)
+            return HR, MRR, NDCG
+        return f
+    cls_or_obj.build_model = lambda: None
+    cls_or_obj.train_model = train_model
+    cls_or_obj.test_model_loo, cls_or_obj.test_model_rs = test_model("loo"), test_model("rs")
+    return state
+
+
+@pytest.mark.parametrize("split_way,neg,interval", [("loo", 99, 1), ("rs", 0, 2), ("rs", 50, 3)])
+def test_run_model_orchestration_and_log_lines_equal_the_reference(split_loo, split_way, neg, interval):
+    from cleverrec_b200.model.RankingRecommender import RankingRecommender as Ours
+    cfg = R.default_configs(**{"data.split_way": split_way, "test.neg_samples": neg, "test.interval": interval, "epoches": 7, "topk": "[10,20]"})
+    losses = [9.5, 7.25, 6.125, 5.0, 4.75, 4.5, 4.25]
+    # NDCG@10 rises, dips, rises again, ties its best (a tie must NOT move best_epoch), then falls
+    ndcg = [0.10, 0.30, 0.20, 0.40, 0.40, 0.35, 0.05]
+    metrics = [((0.5 + n, 0.2 + n, n), (0.6 + n, 0.25 + n, 0.1 + n)) for n in ndcg]
+
+    class Sess(object):
+        class graph(object):
+            @staticmethod
+            def finalize():
+                pass
+
+        def run(self, *a, **k):
+            return None
+    theirs = R.make_driver(cfg, split_loo, Sess())
+    theirs.logger = _ListHandler()
+    st_ref = _scripted(theirs, losses, metrics)
+    theirs.run_model()
+
+    ours = object.__new__(Ours)
+    ours.data, ours.configs, ours.logger = split_loo, cfg, _ListHandler()
+    ours.epoches, ours.T, ours.neg_samples, ours.topk, ours.model = 7, interval, neg, [10, 20], "BPR"
+    st_ours = _scripted(ours, losses, metrics)
+    best_epoch, best = ours.run_model()
+
+    assert st_ours["called"] == st_ref["called"] and len(st_ours["called"]) == 7 // interval
+    assert set(st_ours["called"]) == ({"loo"} if (split_way == "loo" or neg > 0) else {"rs"})
+    assert ours.logger.lines == theirs.logger.lines           # timings are all 00:00:00 on both sides
+    tested = ndcg[:7 // interval]
+    assert best_epoch == interval * (1 + int(np.argmax(tested)))   # the FIRST best
+    assert ("best_epoch: %d" % best_epoch) in ours.logger.lines and set(best) == {0, 1}
