@@ -364,3 +364,25 @@ def test_run_model_orchestration_and_log_lines_equal_the_reference(split_loo, sp
     tested = ndcg[:7 // interval]
     assert best_epoch == interval * (1 + int(np.argmax(tested)))   # the FIRST best
     assert ("best_epoch: %d" % best_epoch) in ours.logger.lines and set(best) == {0, 1}
+
+
+def test_product_metric_functions_equal_the_genuine_ones():
+    """cleverrec_b200.utils.metrics (the functions the packaged classes call) against the genuine utils/metrics.py: single user and
+    the vectorised batch form, real items repeated / absent, recommendation lists shorter than K (-1 padded in the batch form)."""
+    from cleverrec_b200.utils.metrics import batch_ranking_metrics, cal_ranking_metrics, cal_rmse_mae
+    ref = R.load()
+    rs = np.random.RandomState(4)
+    reals, recs, K = [], [], 10
+    for _ in range(400):
+        n_rec = int(rs.choice([K, K, K, 7, 3]))
+        rec = rs.permutation(30)[:n_rec].astype(np.int64)
+        real = rs.randint(0, 30, rs.randint(1, 7)).tolist()           # repeats allowed
+        assert cal_ranking_metrics(real, rec, K) == ref.cal_ranking_metrics(real, rec, K)
+        reals.append(real)
+        recs.append(np.pad(rec, (0, K - n_rec), constant_values=-1))
+    hr, mrr, ndcg = batch_ranking_metrics(reals, np.asarray(recs), K)
+    for k in range(400):
+        want = ref.cal_ranking_metrics(reals[k], recs[k][recs[k] >= 0], K)
+        assert (hr[k], mrr[k], ndcg[k]) == want
+    y, p = rs.rand(50).tolist(), rs.rand(50).tolist()
+    assert cal_rmse_mae(y, p) == ref.cal_rmse_mae(y, p)
