@@ -95,16 +95,19 @@ def ranking_sampler_cml(data, neg_ratio, batch_size):
 
 # For SBPR
 def ranking_sampler_sbpr(data, SPu, neg_ratio, batch_size, is_suk=True):
-    """utils/sampler.py:102-141: (train_batches, u, i, i_s, i_neg[, suk]).  philox mode only (numpy_stream replays the reference's
-    pairwise / pointwise / CML samplers)."""
-    if _state["mode"] == "numpy_stream":
-        raise NotImplementedError("ranking_sampler_sbpr: numpy_stream mode covers the pairwise / pointwise / CML samplers")
+    """utils/sampler.py:102-141: (train_batches, u, i, i_s, i_neg[, suk]).  numpy_stream mode returns the reference's arrays bit for
+    bit under NumPy's current global stream (the path SBPR.train_model_sbpr takes with sampler=numpy_stream)."""
     eng = _engine_for(data)
     if _state.get("social_id") != (id(data), id(SPu)):
         eng.set_social(data.ui_train, data.user_friends, SPu, data.user_nums)
         _state["social_id"] = (id(data), id(SPu))
     n = eng.epoch_rows(neg_ratio, "sbpr")
-    out = eng.sample_sbpr(_state["seed"], _next_epoch(), 0, n, neg_ratio, is_suk=is_suk)
+    if _state["mode"] == "numpy_stream":
+        eng.np_set_state()
+        out = eng.sample_epoch_numpy_sbpr(neg_ratio, is_suk=is_suk)
+        np.random.set_state(eng.np_get_state())
+    else:
+        out = eng.sample_sbpr(_state["seed"], _next_epoch(), 0, n, neg_ratio, is_suk=is_suk)
     res = (math.ceil(n / batch_size),) + tuple(t.cpu().numpy().astype(np.int64) for t in out[:4])
     if is_suk:
         res = res + (out[4].cpu().numpy().astype(np.int64),)
