@@ -129,6 +129,19 @@ def build_history_device(torch, dev, users, items, mean_hist, seed, user_lo=0, u
 
 
 # --------------------------------------------------------------------------------------------- reference arm (CPU)
+def workload_config(args, w, world):
+    """The `config` object of the JSON line: the workload and nothing else, a pure function of the command line and the world size, so
+    that the GPU arm and `--impl reference` print the SAME object for the same launch.  What a run measures about itself (setup time,
+    the exact number of synthetic interactions, what the host could hold) goes into `run_info`."""
+    users, items, dim = w["users"], w["items"], w["dim"]
+    return {"workload": args.workload, "users": users, "items": items, "dim": dim, "mean_history": w["mean_hist"], "batch_per_gpu": w["batch"],
+            "neg_ratio": w["neg_ratio"], "item_popularity": args.item_popularity, "optimizer": args.optimizer,
+            "adam_mode": args.adam_mode if args.optimizer == "Adam" else None, "reg": 0.01,
+            "l2_policy": "inputs larger than L2 (tables %.1f GB vs 126 MB L2)" % ((users + items) * dim * 4 / 1e9),
+            "parallelism": ("single GPU" if world == 1 else "%d ranks: users partitioned, item table row-sharded (item %% N), rows and gradients "
+                            "over NVLink peer memory (per-rank de-duplicated), flag barriers in peer memory, no data-path collective" % world)}
+
+
 def cpu_reference_steps(w, n_steps, batch, threads, seed=0):
     """The reference's CPU path restated (oracle/): Python-loop sampler with np.random (utils/sampler.py:46-74) +
     one TF-1 graph step per batch in torch-CPU fp32 (BPR.py:31-44, Adam).  Same configuration as the GPU arm: full-size tables
@@ -197,9 +210,10 @@ def run_reference(args, w):
     sample = cpu_sample_text(done, n_sample, table_rows, w)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "users": w["users"], "items": w["items"], "dim": w["dim"], "batch_per_gpu": done,
-                       "neg_ratio": w["neg_ratio"], "item_popularity": "uniform", "optimizer": "Adam", "reg": 0.01,
-                       "user_table_rows_on_host": table_rows, "sampler_in_timed_region": True},
+            "config": workload_config(args, w, int(os.environ.get("WORLD_SIZE", "1"))),
+            "run_info": {"triplets_per_step": done, "user_table_rows_on_host": table_rows, "sampler_in_timed_region": True,
+                         "apply": "row-sparse Adam (touched rows only): generous to the CPU, TF-1's dense moment update would touch every row",
+                         "histories": "uniform items (the sampler's cost does not depend on the popularity law)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -570,12 +584,8 @@ def run_ours(args, w):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": args.workload, "users": users, "items": items, "dim": dim, "interactions_per_gpu": n_pos, "batch_per_gpu": B,
-                           "neg_ratio": R, "item_popularity": args.item_popularity, "optimizer": opt_kind, "adam_mode": adam_mode if opt_kind == "Adam" else None, "reg": reg,
-                           "l2_policy": "inputs larger than L2 (tables %.1f GB vs 126 MB L2)" % ((users + items) * dim * 4 / 1e9),
-                           "parallelism": ("single GPU" if world == 1 else "%d ranks: users partitioned, item table row-sharded (item %% N), rows and gradients "
-                                           "over NVLink peer memory (per-rank de-duplicated), flag barriers in peer memory, no data-path collective" % world),
-                           "setup_s": round(t_setup, 1)},
+                "config": workload_config(args, w, world),
+                "run_info": {"interactions_per_gpu": n_pos, "setup_s": round(t_setup, 1)},
                 "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 8, "steps": n_e2e, "path": e2e_path,
                         "blocking_per_step_value": e2e_sync,
                         "with_device_sampling": {"value": e2e_with_sampling, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,

@@ -37,8 +37,17 @@ def test_reference_arm_prints_one_contract_line_under_torchrun():
     assert d["impl"] == "reference" and d["metric"] == "bpr_train_triplets_per_sec" and d["unit"] == "triplets/s"
     assert d["n_gpus"] == 2 and d["steps"] == 2 and d["warmup"] == 3 and d["higher_is_better"] is True
     assert d["scaling"] == "weak" and d["vs_baseline"] is None and d["dtype"] == "f32" and d["data"] == "synthetic"
-    assert d["config"]["workload"] == "ml1m" and d["config"]["sampler_in_timed_region"] is True
-    assert d["value"] > 0 and abs(d["value"] - d["config"]["batch_per_gpu"] / (d["ms_per_step"] / 1000.0)) <= 1e-6 * d["value"]
+    assert d["config"]["workload"] == "ml1m" and d["run_info"]["sampler_in_timed_region"] is True
+    assert d["value"] > 0 and abs(d["value"] - d["run_info"]["triplets_per_step"] / (d["ms_per_step"] / 1000.0)) <= 1e-6 * d["value"]
+    # `config` is the workload and nothing else: the object the GPU arm prints for the same launch (both call workload_config)
+    import argparse
+    sys.path.insert(0, ROOT)
+    import bench
+    args = argparse.Namespace(workload="ml1m", item_popularity="uniform", optimizer="Adam", adam_mode="tf1")
+    assert d["config"] == bench.workload_config(args, bench.WORKLOADS["ml1m"], 2)
+    assert d["config"]["batch_per_gpu"] == 6144 and d["config"]["parallelism"].startswith("2 ranks")
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": workload_config(args, w, ') == 2        # the two arms, no third way to build it
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["unit"] == d["unit"] and "sampler" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
