@@ -77,12 +77,17 @@ class TransCF(_rr.RankingRecommender):
         HR, MRR, NDCG = defaultdict(list), defaultdict(list), defaultdict(list)
         K, I, dev = self.topk[-1], self.data.item_nums, self.engine.device
         A, B = self._neighbourhoods()
+        # TransCF.py:59-62,83-85: _unit_clipping rebinds self.u_embed to clip_by_norm(u_embed, 1.0, axes=1) BEFORE _predict is built,
+        # so the all-item branch scores the *clipped* user row; the neighbourhood means (A, B: from the variables) and Q are not
+        # clipped, and the candidate-pair branch (pre_scores = ui_dist, built before the clipping) is not either.  Same quirk as CML's
+        # full-rank branch; found by running the genuine class on the TF-1 shim (tests/test_reference_graphs.py).
+        P_eval = self.engine.clip_rows(self.P.w)
         items = torch.arange(I, dtype=torch.int32, device=dev)
         bt = max(1, min(self.batch_size_t, (1 << 26) // max(1, I)))
         for a in range(0, len(self.test_users), bt):
             cur = self.test_users[a:a + bt]
             users = torch.as_tensor(np.asarray(cur), dtype=torch.int32, device=dev)
-            scores = self.engine.score_pairs_transcf(self.P.w, self.Q.w, A, B, users.repeat_interleave(I), items.repeat(len(cur)))
+            scores = self.engine.score_pairs_transcf(P_eval, self.Q.w, A, B, users.repeat_interleave(I), items.repeat(len(cur)))
             scores = self.engine.mask_seen(scores.reshape(len(cur), I), users, float('inf'))   # ascending: a seen item is infinitely far
             seg = torch.arange(len(cur) + 1, dtype=torch.int64, device=dev) * I
             topk_items = self.engine.topk_segments(scores.reshape(-1), seg, K, True).cpu().numpy()

@@ -14,6 +14,7 @@ Forward graphs (each returns the scalar loss exactly as `self.loss`):
   mf_loss      <- (no source) BPR's dot product under get_loss('square'|'cross_entropy')
   gmf_loss     <- model/ranking/GMF.py:37-49
   neumf_loss   <- model/ranking/NeuMF.py:58-95 (MLP tower: MLP.py:44-53)
+  mlp_loss     <- model/ranking/MLP.py:44-70
   cml_loss     <- model/ranking/CML.py:39-70
   fism_loss    <- model/ranking/FISM.py:40-63 + utils/tools.py:90-97
   nais_loss    <- model/ranking/NAIS_single.py:59-90
@@ -86,6 +87,13 @@ def neumf_loss(p, b, hp):
     logits, (ug, ig, um, im) = neumf_logits(p, b["u"], b["i"], hp["n_layers"])
     return (get_loss(hp["loss_func"], b["y"], logits=logits) + hp["reg1"] * (l2_loss(ug) + l2_loss(ig))
             + hp["reg2"] * (l2_loss(um) + l2_loss(im)))
+
+
+def mlp_loss(p, b, hp):
+    """MLP.py:44-70: the tower alone -- concat(u, i) -> relu(x W_k + b_k) per layer -> . h_mlp; L2 on the two gathered embeddings."""
+    um, im = p["P"][b["u"]], p["Q"][b["i"]]
+    logits = mlp_tower(torch.cat([um, im], 1), p, hp["n_layers"]) @ p["h_mlp"]
+    return get_loss(hp["loss_func"], b["y"], logits=logits) + hp["reg"] * (l2_loss(um) + l2_loss(im))
 
 
 def cml_parts(p, b, hp):
