@@ -369,3 +369,91 @@ def test_all_item_predict_branch_equals_the_pair_branch(classes, data, name):
         assert not np.allclose(full, pairs)
         return
     np.testing.assert_allclose(full, pairs, rtol=1e-11, atol=1e-13)
+
+
+def _epoch_against(params, loss_fn, hp, opt, batches, sparse_index=None, extra=()):
+    total, n = 0.0, 0
+    for b in batches:
+        total += T.train_step(loss_fn, params, b, hp, opt, sparse_index=sparse_index, extra=extra)
+        n += 1
+    return total, n
+
+
+def test_reference_epoch_loops_of_the_special_models_run_on_the_shim(classes, data):
+    """The other genuine epoch loops -- train_model (pointwise branch, GMF), train_model_cml, train_model_nais, train_model_sbpr
+    (RankingRecommender.py:48-117): genuine sampler code + genuine batch slicing + genuine graph, against the restated samplers
+    (oracle/ref_host.py) feeding the restated graphs under the same NumPy seed."""
+    from oracle import ref_host as H
+    # GMF, pointwise
+    sess, m = _build(classes, "GMF", data, "Adagrad", neg_ratio=2, batch_size=40)
+    p = _params({"P": m.P, "Q": m.Q, "h": m.h_gmf})
+    np.random.seed(8)
+    got = m.train_model()
+    np.random.seed(8)
+    n_b, u, i, y = H.pointwise_ranking_sampler(data, 2, 40)
+    batches = [{"u": _t(u[k * 40:(k + 1) * 40]), "i": _t(i[k * 40:(k + 1) * 40]), "y": torch.tensor(y[k * 40:(k + 1) * 40].astype(np.float64))}
+               for k in range(n_b)]
+    total, n = _epoch_against(p, T.gmf_loss, {"reg": m.reg, "loss_func": "cross_entropy"}, T.TF1Optimizer("Adagrad", 0.05), batches, {"P": ["u"], "Q": ["i"]})
+    assert n == n_b and abs(got - total / n) <= 1e-10 * abs(got)
+    np.testing.assert_allclose(m.h_gmf.numpy(), p["h"].numpy(), rtol=0, atol=1e-10)
+
+    # CML
+    sess, m = _build(classes, "CML", data, "Adam", batch_size=40)
+    p = _params({"P": m.P, "Q": m.Q})
+    np.random.seed(9)
+    got = m.train_model()            # = train_model_cml (CML.py:15)
+    np.random.seed(9)
+    n_b, u, i, neg = H.ranking_sampler_cml(data, m.neg_ratio, 40)
+    batches = [{"u": _t(u[k * 40:(k + 1) * 40]), "i": _t(i[k * 40:(k + 1) * 40]), "neg": _t(neg[k * 40:(k + 1) * 40])} for k in range(n_b)]
+    hp = {"reg": m.reg, "margin": m.margin, "item_nums": I, "neg_ratio": m.neg_ratio}
+    total, n = _epoch_against(p, T.cml_loss, hp, T.TF1Optimizer("Adam", 0.05), batches)
+    assert abs(got - total / n) <= 1e-10 * abs(got)
+    np.testing.assert_allclose(m.Q.numpy(), p["Q"].numpy(), rtol=0, atol=1e-10)
+
+    # NAIS_single: one step per user
+    def patch(mm):
+        mm.loss_func = tf.nn.sigmoid_cross_entropy_with_logits
+    sess, m = _build(classes, "NAIS_single", data, "Adagrad", patch=patch, neg_ratio=2)
+    p = _params({"P": m.P, "Q": m.Q, "bias": m.bias, "W": m.W, "b_att": m.b, "h": m.h})
+    np.random.seed(10)
+    got = m.train_model()            # = train_model_nais
+    np.random.seed(10)
+    batches = [{"hist": _t(hist), "i": _t(tg), "y": torch.tensor(np.asarray(y, dtype=np.float64))} for _, hist, tg, y in H.nais_user_batches(data, 2)]
+    total, n = _epoch_against(p, T.nais_loss, {"reg": m.reg, "beta": m.beta, "atten_type": m.atten_type}, T.TF1Optimizer("Adagrad", 0.05), batches,
+                              {"P": ["hist"], "Q": ["i"], "bias": ["i"]})
+    assert n == len(data.ui_train) and abs(got - total / n) <= 1e-10 * abs(got)
+    np.testing.assert_allclose(m.W.numpy(), p["W"].numpy(), rtol=0, atol=1e-10)
+
+    # SBPR
+    sess, m = _build(classes, "SBPR", data, "SGD", neg_ratio=2, batch_size=40)
+    p = _params({"P": m.P, "Q": m.Q, "bias": m.bias})
+    np.random.seed(12)
+    got = m.train_model()            # = train_model_sbpr
+    np.random.seed(12)
+    n_b, u, i, k_, j, suk = H.ranking_sampler_sbpr(data, H.get_SPu(data), 2, 40)
+    sl = lambda a, q: a[q * 40:(q + 1) * 40]          # noqa: E731
+    batches = [{"u": _t(sl(u, q)), "i": _t(sl(i, q)), "k": _t(sl(k_, q)), "j": _t(sl(j, q)), "suk": torch.tensor(sl(suk, q).astype(np.float64))}
+               for q in range(n_b)]
+    total, n = _epoch_against(p, T.sbpr_loss, {"reg": m.reg}, T.TF1Optimizer("SGD", 0.05), batches,
+                              {"P": ["u"], "Q": ["i", "k", "j"], "bias": ["i", "k", "j"]})
+    assert abs(got - total / n) <= 1e-10 * abs(got)
+    np.testing.assert_allclose(m.bias.numpy(), p["bias"].numpy(), rtol=0, atol=1e-10)
+
+
+def test_reference_fism_epoch_runs_on_the_shim(classes, data):
+    """train_model's pairwise branch with fism_like (RankingRecommender.py:36-46): the sampler's fifth array feeds u_neighbors_num."""
+    from oracle import ref_host as H
+    sess, m = _build(classes, "FISM", data, "Adam", neg_ratio=2, batch_size=40)
+    assert m.fism_like and m.is_pairwise == "True"
+    sp = m.ui_sp_mat
+    p = _params({"P": m.P, "Q": m.Q, "b": m.b})
+    np.random.seed(13)
+    got = m.train_model()
+    np.random.seed(13)
+    n_b, u, i, j, nbr = H.pairwise_ranking_sampler(data, 2, 40, fism_like=True)
+    sl = lambda a, q: _t(a[q * 40:(q + 1) * 40])          # noqa: E731
+    batches = [{"u": sl(u, q), "i": sl(i, q), "j": sl(j, q), "nbr_num": sl(nbr, q)} for q in range(n_b)]
+    hp = {"reg": m.reg, "reg_bias": m.reg_bias, "alpha": m.alpha, "batch_size": m.batch_size, "user_nums": U, "loss_func": "bpr"}
+    total, n = _epoch_against(p, T.fism_loss, hp, T.TF1Optimizer("Adam", 0.05), batches, extra=((sp.rows, sp.cols, sp.values),))
+    assert abs(got - total / n) <= 1e-10 * abs(got)
+    np.testing.assert_allclose(m.P.numpy(), p["P"].numpy(), rtol=0, atol=1e-10)
