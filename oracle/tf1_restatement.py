@@ -1,13 +1,17 @@
 """ORACLE / TEST INFRASTRUCTURE ONLY -- never imported by the product path.
 
 CPU restatement of the TensorFlow-1 graphs the reference builds for the hot path, plus the
-TF-1 optimizer semantics they rely on.  PARITY UNPINNED for the arithmetic itself: the
-arithmetic lives in TensorFlow "1.13+" (README.md:57), an un-vendored dependency that is not
-in /root/reference and cannot be installed here, and the reference has no tests or golden
-values.  What pins this file instead: (i) it is a line-by-line
-transcription of the cited graph-building code into torch-CPU ops with *autograd* providing
-the gradients (an independent derivation from the hand-written CUDA backward), (ii) fp64
-runs of the same code, (iii) finite-difference checks in tests/test_oracle_restatement.py.
+TF-1 optimizer semantics they rely on.  PARITY UNPINNED for TensorFlow's own kernels
+(summation order, fp32 rounding): TensorFlow "1.13+" (README.md:57) is an un-vendored
+dependency that is not in /root/reference and cannot be installed here, and the reference
+has no tests or golden values.  What pins this file: (i) the GENUINE
+reference model classes are executed, unmodified, on a TF-1 API shim (oracle/tf1_shim.py) and
+every function below reproduces their losses, updated variables and pre_scores to 1e-10 in
+fp64 over three optimizer steps, for SGD / Adagrad / Adam, and over whole genuine epoch loops
+(tests/test_reference_graphs.py) -- a mechanical check against the reference's own
+graph-building lines; (ii) gradients come from *autograd* (an independent derivation from the
+hand-written CUDA backward); (iii) fp64 finite-difference checks in
+tests/test_oracle_restatement.py.
 
 Forward graphs (each returns the scalar loss exactly as `self.loss`):
   bpr_loss     <- model/ranking/BPR.py:31-44
