@@ -457,3 +457,35 @@ def test_reference_fism_epoch_runs_on_the_shim(classes, data):
     total, n = _epoch_against(p, T.fism_loss, hp, T.TF1Optimizer("Adam", 0.05), batches, extra=((sp.rows, sp.cols, sp.values),))
     assert abs(got - total / n) <= 1e-10 * abs(got)
     np.testing.assert_allclose(m.P.numpy(), p["P"].numpy(), rtol=0, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_checkpoint_variable_names_are_the_reference_savers(classes, data, name):
+    """The names under which the packaged classes save / restore (`_variables`, one .npz keyed by Saver name) are the keys of the
+    var_list the GENUINE `_save_model` hands to tf.train.Saver (typos such as 'FISM_paras/P' and 'NAIS_paras/P' included, because
+    NAIS restores FISM by that spelling, NAIS_single.py:35-38)."""
+    import os
+    import re
+    from conftest import ROOT
+
+    def patch(m):
+        if name == "NAIS_single":
+            m.loss_func = tf.nn.sigmoid_cross_entropy_with_logits
+        m.saved_model_dir = os.path.join(os.environ.get("TMPDIR", "/tmp"), "crb_refgraph_saver")    # _save_model makes the directory
+    sess, m = _build(classes, name, data, "SGD", patch=patch)
+    if not hasattr(m, "saver"):
+        m._save_model()              # TransCF / LRML: the call is commented out in build_model (TransCF.py:99, LRML.py:92)
+    keys = set(m.saver.var_list.keys())
+    assert len(keys) >= 2
+    src = open(os.path.join(ROOT, "cleverrec_b200", "model", "ranking", name + ".py")).read()
+    if name in ("GMF", "MLP", "NeuMF"):     # built from '<Model>_params/' + the variable's own name
+        prefix = {"GMF": "%s_params/", "MLP": "MLP_params/", "NeuMF": "NeuMF_params/"}[name]
+        assert prefix in src
+        assert {k.split("/")[0] for k in keys} == {name + "_params"}
+        tower = {"W_%d" % k for k in range(len(getattr(m, "layers", [])))} | {"b_%d" % k for k in range(len(getattr(m, "layers", [])))}
+        for k in keys:
+            leaf = k.split("/")[1]
+            assert leaf in tower or re.search(r"['/]%s'" % re.escape(leaf), src) or ("'%s'" % leaf) in src, k
+        return
+    for k in keys:
+        assert ("'%s'" % k) in src, k
