@@ -66,6 +66,8 @@ class NeuMF(_rr.RankingRecommender):
         trained GMF ('GMF_params/{P,Q,h_gmf}'), the MLP branch from a trained MLP ('MLP_params/{P,Q,h_mlp,W_k,b_k}'), and
         h_neumf = 0.5 * concat(h_gmf, h_mlp).  The shipped conf names ./saved_model/{GMF,MLP}, which nothing ever writes in the
         reference (saver.save is commented out) so its restore raises; here missing checkpoints are logged and skipped.
+        (Read literally, NeuMF.py:46-51 then REPLACES that h_neumf by a freshly initialised variable -- the `# NeuMF` line runs after
+        `_load_pretrained_model()`; the NCF initialisation the method spells out is what is implemented here.)
         Explicit `init` entries win."""
         from ...utils.tools import latest_checkpoint, load_checkpoint
         if not ('gmf_pretrain' in self.configs and 'mlp_pretrain' in self.configs):
