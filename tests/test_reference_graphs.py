@@ -489,3 +489,19 @@ def test_checkpoint_variable_names_are_the_reference_savers(classes, data, name)
         return
     for k in keys:
         assert ("'%s'" % k) in src, k
+
+
+@pytest.mark.parametrize("atten", ["prod", "concat"])
+def test_nais_all_item_branch_equals_the_pair_branch(classes, data, atten):
+    """NAIS_single.py:92-97: the random-split branch attends over the user's history once per row of Q (item_nums + 1 rows); it is
+    the candidate branch fed with every item as target, which is how the packaged class scores it (crb_score_nais)."""
+    def patch(m):
+        m.loss_func = tf.nn.sigmoid_cross_entropy_with_logits
+    sess_a, a = _build(classes, "NAIS_single", data, "SGD", patch=patch, atten_type=atten)
+    sess_b, b = _build(classes, "NAIS_single", data, "SGD", patch=patch, atten_type=atten, **{"data.split_way": "rs", "test.neg_samples": 0})
+    hist = np.asarray(data.ui_train[7])
+    tg = np.arange(I + 1)
+    pairs = sess_a.run(a.pre_scores, {a.u_idx: hist, a.u_nbrs_num: len(hist), a.i_idx: tg, a.i_nums: len(tg), a.y: np.zeros(len(tg))})
+    full = sess_b.run(b.pre_scores, {b.u_idx: hist, b.u_nbrs_num: len(hist), b.i_idx: tg[:1], b.i_nums: 1, b.y: np.zeros(1)})
+    assert full.shape == (I + 1,)
+    np.testing.assert_allclose(full, pairs, rtol=1e-11, atol=1e-13)
