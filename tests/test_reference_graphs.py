@@ -325,13 +325,17 @@ def test_a_whole_reference_epoch_runs_on_the_shim(classes, data):
 @pytest.mark.parametrize("name", ["GMF", "MLP", "NeuMF", "CML", "FISM", "TransCF", "LRML", "SBPR"])
 def test_all_item_predict_branch_equals_the_pair_branch(classes, data, name):
     """`_predict` has two branches in every model: candidate pairs (loo / sampled negatives) and all items (random split).  The
-    library serves both with ONE scorer per model, so the reference's two graphs must give the same number for the same (u, i):
+    library serves both with ONE scorer per model, so the reference's two graphs must give the same number for the same (u, i) --
+    except where they verifiably do not, and then the packaged class must follow (CML / TransCF: clipped user row; SBPR: no bias):
     built twice on the shim from the same seed (identical variables), all-item scores [n, I(+1)] against pair scores of every (u, i).
     (Real TF-1 would refuse MLP / NeuMF / LRML's rank-3 x rank-2 tf.matmul in the all-item branch; torch broadcasts it.)"""
     sess_a, a = _build(classes, name, data, "SGD")
     sess_b, b = _build(classes, name, data, "SGD", **{"data.split_way": "rs", "test.neg_samples": 0})
     users = np.asarray([0, 3, 7, 11])
     n_items = I + 1 if name == "FISM" else I
+    if name == "SBPR":      # the bias starts at zero (SBPR.py:36): give it a trained-looking value in both graphs
+        bias = np.random.RandomState(1).randn(I + 1) * 0.3
+        a.bias.assign_value(bias); b.bias.assign_value(bias)
     uu, ii = np.repeat(users, n_items), np.tile(np.arange(n_items), len(users))
     zeros = np.zeros(len(uu))
 
@@ -350,6 +354,12 @@ def test_all_item_predict_branch_equals_the_pair_branch(classes, data, name):
     pairs = sess_a.run(a.pre_scores, feed(a, uu, ii)).reshape(len(users), n_items)
     full = sess_b.run(b.pre_scores, feed(b, users))
     assert full.shape == pairs.shape
+    if name == "SBPR":
+        # SBPR.py:59-63: the candidate branch is p.q + bias, the all-item branch the plain matmul WITHOUT the bias
+        # (the packaged class: SCORE_DOT_BIAS vs SCORE_DOT in SBPR._score_spec)
+        np.testing.assert_allclose(full, pairs - bias[None, :I], rtol=1e-11, atol=1e-13)
+        assert not np.allclose(full, pairs)
+        return
     if name in ("CML", "TransCF"):
         # CML.py:58-61,84 / TransCF.py:59-62,83-85: _unit_clipping rebinds self.u_embed to clip_by_norm(u_embed, 1) before _predict is
         # built, so the all-item branch scores the CLIPPED user row (Q, and TransCF's neighbourhood means, stay unclipped) while the
